@@ -1,0 +1,182 @@
+/** @file gsB200Flatten.h
+
+    Host-side extraction layer of the B200 assembly back-end: flattens the G+Smo
+    objects an assembler holds (gsMultiPatch, gsMultiBasis, gsDofMapper, Dirichlet
+    values, options, source term) into the plain-old-data problem description of the
+    C ABI (include/gsb200.h).  Header-only C++ over gismo + Eigen, as the reference's
+    host side is; it performs no arithmetic of the hot path.
+
+    Reference conventions relied upon (file:line in gismo v24.08.0):
+      - knots with repetitions:      gsKnotVector::data()/size()   gsKnotVector.h:242,285
+      - per-direction component:     gsTensorBSplineBasis::knots(i) gsTensorBSplineBasis.h:192
+      - control points, col-major:   gsGeometry::coefs()            gsGeometry.h:343
+      - NURBS weights / source:      gsRationalBasis::weights()     gsRationalBasis.h:290
+      - global numbering:            gsDofMapper::index(i,k,c)      gsDofMapper.h:325-329
+      - free / eliminated counts:    gsDofMapper::freeSize()/boundarySize()
+      - source-term strings:         gsFunctionExpr::expression(i)  gsFunctionExpr.h:169
+*/
+#pragma once
+
+#include <gismo.h>
+#include <gsb200.h>
+#include <deque>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace gismo
+{
+namespace b200
+{
+
+/// Owns every buffer a gsb200_problem points into.
+struct gsB200Problem
+{
+    gsb200_problem pb;
+    std::vector<gsb200_patch> patches;
+    std::deque<std::vector<double> >  dbl;   // knots, coefs, weights
+    std::deque<std::vector<int32_t> > idx;   // dof maps, program opcodes
+    std::vector<double> fixed;
+    std::vector<gsb200_program> programs;
+
+    gsB200Problem() { std::memset(&pb, 0, sizeof(pb)); pb.abi_version = GSB200_ABI_VERSION; pb.nranks = 1; }
+private:
+    gsB200Problem(const gsB200Problem &);
+    gsB200Problem & operator=(const gsB200Problem &);
+};
+
+namespace internal
+{
+template <short_t d, class T>
+bool flattenTensorBasis(const gsBasis<T> & b, gsb200_basis & out, gsB200Problem & st)
+{
+    const gsTensorBSplineBasis<d,T> * tb = dynamic_cast<const gsTensorBSplineBasis<d,T>*>(&b);
+    if (!tb) return false;
+    out.dim = d;
+    for (short_t i = 0; i != d; ++i)
+    {
+        const gsKnotVector<T> & kv = tb->knots(i);
+        st.dbl.push_back(std::vector<double>(kv.data(), kv.data() + kv.size()));
+        out.degree[i] = kv.degree();
+        out.nknots[i] = static_cast<int32_t>(kv.size());
+        out.knots[i]  = st.dbl.back().data();
+    }
+    return true;
+}
+
+template <class T>
+void flattenBasis(const gsBasis<T> & b, gsb200_basis & out, gsB200Problem & st)
+{
+    std::memset(&out, 0, sizeof(out));
+    if (flattenTensorBasis<2,T>(b, out, st) || flattenTensorBasis<3,T>(b, out, st)) return;
+    GISMO_ERROR("gsB200: only 2D/3D tensor-product B-spline bases are supported by the device path");
+}
+
+/// geometry basis + optional weights (gsTensorBSpline / gsTensorNurbs)
+template <class T>
+void flattenGeometry(const gsGeometry<T> & g, gsb200_patch & out, gsB200Problem & st)
+{
+    const gsBasis<T> & gb = g.basis();
+    out.geo_weights = NULL;
+    if (gb.isRational())
+    {
+        flattenBasis(gb.source(), out.geo, st);
+        const gsMatrix<T> & w = gb.weights();
+        st.dbl.push_back(std::vector<double>(w.data(), w.data() + w.size()));
+        out.geo_weights = st.dbl.back().data();
+    }
+    else
+        flattenBasis(gb, out.geo, st);
+    const gsMatrix<T> & c = g.coefs();
+    GISMO_ENSURE(c.cols() == out.geo.dim, "gsB200: geometry must map R^d -> R^d");
+    st.dbl.push_back(std::vector<double>(c.data(), c.data() + c.size()));
+    out.geo_coefs = st.dbl.back().data();
+}
+} // namespace internal
+
+/// Compile the components of a gsFunctionExpr into device programs.
+template <class T>
+void flattenSource(const gsFunction<T> & f, index_t ncompExpected, gsB200Problem & st)
+{
+    const gsFunctionExpr<T> * fe = dynamic_cast<const gsFunctionExpr<T>*>(&f);
+    GISMO_ENSURE(fe, "gsB200: the source term must be a gsFunctionExpr (or pass samples)");
+    GISMO_ENSURE(fe->targetDim() == ncompExpected, "gsB200: source term has wrong target dimension");
+    st.programs.resize(fe->targetDim());
+    for (short_t c = 0; c != fe->targetDim(); ++c)
+    {
+        std::vector<int32_t> ops(GSB200_PROGRAM_MAX_OPS);
+        std::vector<double>  cst(GSB200_PROGRAM_MAX_OPS);
+        int32_t nops = 0, ncst = 0;
+        if (gsb200_expr_compile(fe->expression(c).c_str(), ops.data(), (int32_t)ops.size(), &nops,
+                                cst.data(), (int32_t)cst.size(), &ncst) != GSB200_OK)
+            GISMO_ERROR("gsB200: cannot compile source term '" << fe->expression(c) << "': " << gsb200_last_error());
+        ops.resize(nops); cst.resize(ncst);
+        st.idx.push_back(ops); st.dbl.push_back(cst);
+        st.programs[c].nops = nops;       st.programs[c].ops = st.idx.back().data();
+        st.programs[c].nconsts = ncst;    st.programs[c].consts = st.dbl.back().data();
+    }
+    st.pb.rhs_kind = GSB200_RHS_PROGRAM;
+    st.pb.rhs_programs = st.programs.data();
+}
+
+/** Flatten a whole (multi-patch) discretisation.
+    \param mp      geometry patches        \param mb   solution bases (one per patch)
+    \param mapper  finalized DOF mapper with \a ncomp components
+    \param fixed   eliminated-DOF values, boundarySize() x nrhs (may be empty = homogeneous) */
+template <class T>
+void flatten(const gsMultiPatch<T> & mp, const gsMultiBasis<T> & mb, const gsDofMapper & mapper,
+             index_t ncomp, const gsMatrix<T> & fixed, const gsOptionList & opt, int form,
+             gsB200Problem & st)
+{
+    GISMO_ENSURE(mp.nPatches() == mb.nBases(), "gsB200: patches/bases mismatch");
+    st.patches.resize(mp.nPatches());
+    for (size_t k = 0; k != mp.nPatches(); ++k)
+    {
+        gsb200_patch & P = st.patches[k];
+        std::memset(&P, 0, sizeof(P));
+        internal::flattenBasis(mb.basis(k), P.space, st);
+        internal::flattenGeometry(mp.patch(k), P, st);
+        GISMO_ENSURE(P.space.dim == P.geo.dim, "gsB200: basis/geometry dimension mismatch");
+        const index_t sz = mb.basis(k).size();
+        std::vector<int32_t> dm(static_cast<size_t>(sz) * ncomp);
+        for (index_t c = 0; c != ncomp; ++c)
+            for (index_t i = 0; i != sz; ++i)
+                dm[static_cast<size_t>(c) * sz + i] = mapper.index(i, k, c);
+        st.idx.push_back(dm);
+        P.dofmap = st.idx.back().data();
+    }
+    gsb200_problem & pb = st.pb;
+    pb.form = form;
+    pb.npatches = static_cast<int32_t>(st.patches.size());
+    pb.patches = st.patches.data();
+    pb.ncomp = ncomp;
+    pb.nfree = mapper.freeSize();
+    pb.nfixed = mapper.boundarySize();
+    pb.nrhs = 1;
+    if (fixed.size() != 0)
+    {
+        GISMO_ENSURE(fixed.rows() == mapper.boundarySize(), "gsB200: fixedDofs has wrong size");
+        st.fixed.assign(fixed.data(), fixed.data() + fixed.size());
+        pb.fixed = st.fixed.data();
+        pb.nrhs = static_cast<int32_t>(fixed.cols());
+    }
+    pb.quA = opt.askReal("quA", 1.0);
+    pb.quB = opt.askInt("quB", 1);
+    GISMO_ENSURE(opt.askInt("quRule", 1) == 1, "gsB200: only Gauss-Legendre quadrature (quRule=1) is supported");
+}
+
+/// Move the device result into a gsSparseMatrix exactly as Eigen stores a compressed matrix
+/// (SparseMatrix.h:150-177,626,649).
+template <class T>
+void fillSparse(gsSparseMatrix<T> & m, index_t n, int64_t nnz, const std::vector<int32_t> & outer,
+                const std::vector<int32_t> & inner, const std::vector<double> & values)
+{
+    m.resize(n, n);
+    m.resizeNonZeros(static_cast<index_t>(nnz));
+    std::copy(outer.begin(), outer.end(), m.outerIndexPtr());
+    std::copy(inner.begin(), inner.end(), m.innerIndexPtr());
+    std::copy(values.begin(), values.end(), m.valuePtr());
+}
+
+} // namespace b200
+} // namespace gismo

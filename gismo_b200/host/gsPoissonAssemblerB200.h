@@ -1,0 +1,167 @@
+/** @file gsPoissonAssemblerB200.h
+
+    Drop-in replacement for gsPoissonAssembler<T> (gsPoissonAssembler.h:35-142) whose
+    assemble() runs on a B200 through the C ABI in include/gsb200.h.  Constructors,
+    refresh(), matrix(), rhs(), system(), numDofs(), fixedDofs(), constructSolution()
+    are inherited unchanged; only the virtual assemble() (gsAssembler.h:415,
+    gsPoissonAssembler.hpp:41-78) is overridden, so callers such as
+    unittests/gsPoissonSolver_test.cpp:109-121 switch by changing the type name.
+
+    Also provided: gsExprAssemblerB200<T>, a sibling of gsExprAssembler<T>
+    (gsExprAssembler.h:29-634) exposing the same set-up surface and named entry points
+    for the two bilinear forms of the BASELINE configs (the reference's
+    assemble(expr...) is a variadic template, not a virtual, so it cannot be overridden).
+
+    No CPU fallback: unsupported options raise GISMO_ERROR, as SURVEY 8(b) requires.
+*/
+#pragma once
+
+#include <gismo.h>
+#include <gsAssembler/gsPoissonAssembler.h>
+#include "gsB200Flatten.h"
+
+namespace gismo
+{
+
+template <class T>
+class gsPoissonAssemblerB200 : public gsPoissonAssembler<T>
+{
+public:
+    typedef gsPoissonAssembler<T> Base;
+
+    gsPoissonAssemblerB200(const gsPoissonPde<T> & pde, const gsMultiBasis<T> & bases)
+    : Base(pde, bases), m_device(0) { }
+
+    gsPoissonAssemblerB200(const gsPoissonPde<T> & pde, const gsMultiBasis<T> & bases,
+                           dirichlet::strategy dirStrategy, iFace::strategy intStrategy = iFace::glue)
+    : Base(pde, bases, dirStrategy, intStrategy), m_device(0) { }
+
+    gsPoissonAssemblerB200(gsMultiPatch<T> const & patches, gsMultiBasis<T> const & basis,
+                           gsBoundaryConditions<T> const & bconditions, const gsFunction<T> & rhs,
+                           dirichlet::strategy dirStrategy = dirichlet::elimination,
+                           iFace::strategy intStrategy = iFace::glue)
+    : Base(patches, basis, bconditions, rhs, dirStrategy, intStrategy), m_device(0) { }
+
+    void setDevice(int device) { m_device = device; }
+
+    /// Main assembly routine: same contract as gsPoissonAssembler<T>::assemble().
+    virtual void assemble()
+    {
+        GISMO_ASSERT(m_system.initialized(),
+                     "Sparse system is not initialized, call initialize() or refresh()");
+        GISMO_ENSURE(m_options.getInt("DirichletStrategy") == dirichlet::elimination,
+                     "gsB200: only DirichletStrategy=elimination (11) is supported");
+        GISMO_ENSURE(m_options.getInt("InterfaceStrategy") == iFace::glue,
+                     "gsB200: only InterfaceStrategy=glue (1) is supported");
+        GISMO_ENSURE(m_pde_ptr->bc().neumannSides().empty(),
+                     "gsB200: Neumann sides are not handled by the device path yet");
+
+        // Dirichlet values stay on the reference's host code: they are inputs.
+        Base::computeDirichletDofs();
+
+        b200::gsB200Problem st;
+        b200::flatten(m_pde_ptr->domain(), m_bases[0], m_system.colMapper(0), 1, m_ddof[0],
+                      m_options, GSB200_FORM_POISSON, st);
+        const gsPoissonPde<T> & ppde = static_cast<const gsPoissonPde<T>&>(*m_pde_ptr);
+        b200::flattenSource(*ppde.rhs(), st.pb.nrhs, st);
+
+        int64_t nnz = 0;
+        if (gsb200_assemble_host(&st.pb, m_device, &nnz, NULL, NULL, NULL, NULL) != GSB200_OK)
+            GISMO_ERROR("gsB200: " << gsb200_last_error());
+        const index_t n = st.pb.nfree;
+        std::vector<int32_t> outer(n + 1), inner(nnz);
+        std::vector<double> values(nnz);
+        m_system.rhs().setZero(n, st.pb.nrhs);
+        if (gsb200_assemble_host(&st.pb, m_device, &nnz, outer.data(), inner.data(), values.data(),
+                                 m_system.rhs().data()) != GSB200_OK)
+            GISMO_ERROR("gsB200: " << gsb200_last_error());
+        b200::fillSparse(m_system.matrix(), n, nnz, outer, inner, values);
+    }
+
+protected:
+    using Base::m_system;
+    using Base::m_options;
+    using Base::m_pde_ptr;
+    using Base::m_bases;
+    using Base::m_ddof;
+    int m_device;
+};
+
+/** Sibling of gsExprAssembler<T> for the forms of the BASELINE configs.  Usage mirrors
+    poisson2_example.cpp:90-149 / linear_elasticity_example.cpp:108-194:
+
+        gsExprAssemblerB200<> A;  A.setIntegrationElements(mb);
+        A.setGeometry(mp);  A.setSpace(mb, dim);  A.setup(bc, dirichlet::l2Projection);
+        A.assemblePoisson(f);            // igrad(u,G)*igrad(u,G).tr()*meas(G) , u*ff*meas(G)
+        A.assembleElasticity(lambda, mu, f);
+        A.matrix(); A.rhs();
+*/
+template <class T>
+class gsExprAssemblerB200
+{
+public:
+    gsExprAssemblerB200() : m_ref(1,1), m_mp(NULL), m_mb(NULL), m_dim(1), m_device(0) { }
+
+    void setOptions(const gsOptionList & o) { m_ref.setOptions(o); }
+    gsOptionList & options() { return m_ref.options(); }
+    void setIntegrationElements(const gsMultiBasis<T> & mb) { m_ref.setIntegrationElements(mb); m_mb = &mb; }
+    void setGeometry(const gsMultiPatch<T> & mp) { m_mp = &mp; }
+    void setDevice(int device) { m_device = device; }
+
+    /// getSpace + space::setup (gsExprAssembler.h:166, gsExpressions.h:1091): the DOF
+    /// mapper and the Dirichlet values are computed by the reference's own host code.
+    void setup(const gsBoundaryConditions<T> & bc, index_t dim = 1,
+               dirichlet::values dirValues = dirichlet::l2Projection)
+    {
+        GISMO_ENSURE(m_mp && m_mb, "gsB200: set geometry and integration elements first");
+        m_dim = dim;
+        m_ref.getMap(*m_mp);
+        typename gsExprAssembler<T>::space u = m_ref.getSpace(*m_mb, dim);
+        u.setup(bc, dirValues, 0);
+        m_ref.initSystem();
+        m_mapper = u.mapper();
+        m_fixed = u.fixedPart();
+    }
+
+    index_t numDofs() const { return m_mapper.freeSize(); }
+    const gsSparseMatrix<T> & matrix() const { return m_matrix; }
+    const gsMatrix<T> & rhs() const { return m_rhs; }
+    const gsDofMapper & mapper() const { return m_mapper; }
+    const gsMatrix<T> & fixedPart() const { return m_fixed; }
+
+    void assemblePoisson(const gsFunction<T> & f) { run(GSB200_FORM_POISSON, 0, 0, f); }
+    void assembleElasticity(T lambda, T mu, const gsFunction<T> & f) { run(GSB200_FORM_ELASTICITY, lambda, mu, f); }
+
+private:
+    void run(int form, T c0, T c1, const gsFunction<T> & f)
+    {
+        b200::gsB200Problem st;
+        b200::flatten(*m_mp, *m_mb, m_mapper, m_dim, m_fixed, m_ref.options(), form, st);
+        st.pb.coef[0] = c0; st.pb.coef[1] = c1;
+        st.pb.nrhs = 1;
+        b200::flattenSource(f, form == GSB200_FORM_ELASTICITY ? m_dim : 1, st);
+        int64_t nnz = 0;
+        if (gsb200_assemble_host(&st.pb, m_device, &nnz, NULL, NULL, NULL, NULL) != GSB200_OK)
+            GISMO_ERROR("gsB200: " << gsb200_last_error());
+        const index_t n = st.pb.nfree;
+        std::vector<int32_t> outer(n + 1), inner(nnz);
+        std::vector<double> values(nnz);
+        m_rhs.setZero(n, 1);
+        if (gsb200_assemble_host(&st.pb, m_device, &nnz, outer.data(), inner.data(), values.data(),
+                                 m_rhs.data()) != GSB200_OK)
+            GISMO_ERROR("gsB200: " << gsb200_last_error());
+        b200::fillSparse(m_matrix, n, nnz, outer, inner, values);
+    }
+
+    gsExprAssembler<T> m_ref;      // used for set-up only (mapper, Dirichlet values)
+    const gsMultiPatch<T> * m_mp;
+    const gsMultiBasis<T> * m_mb;
+    index_t m_dim;
+    int m_device;
+    gsDofMapper m_mapper;
+    gsMatrix<T> m_fixed;
+    gsSparseMatrix<T> m_matrix;
+    gsMatrix<T> m_rhs;
+};
+
+} // namespace gismo

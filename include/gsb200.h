@@ -1,0 +1,211 @@
+/* gsb200.h — C ABI of the B200-native isogeometric system-assembly path.
+ *
+ * This is the drop-in boundary behind G+Smo's assembler interface
+ * (gsPoissonAssembler<T>::assemble()/matrix()/rhs(), gsExprAssembler<T>::assemble(...)).
+ * Everything crossing it is plain-old-data: host pointers, sizes, status codes.
+ * No torch / Eigen / gismo types appear here.  All citations are file:line in the
+ * reference tree (gismo/gismo v24.08.0).
+ *
+ * What the caller flattens (reference object -> POD field):
+ *   gsTensorBSplineBasis<d>::knots(i)  (gsTensorBSplineBasis.h:192,
+ *       gsKnotVector::data()/size()  gsKnotVector.h:285,242)      -> gsb200_basis.knots[i]
+ *   gsGeometry::coefs()      (gsGeometry.h:343, Eigen col-major)  -> gsb200_patch.geo_coefs
+ *   gsRationalBasis weights  (gsRationalBasis.h)                  -> gsb200_patch.geo_weights
+ *   gsDofMapper::asVector(c) (gsDofMapper.cpp:80-87)              -> gsb200_patch.dofmap
+ *   gsDofMapper::freeSize()/boundarySize() (gsDofMapper.h:436-461)-> nfree / nfixed
+ *   gsAssembler::fixedDofs() / m_ddof (gsAssembler.h:276-295)     -> gsb200_problem.fixed
+ *   options quA/quB (gsAssembler.hpp:30-42, gsQuadrature.h:152)   -> quA / quB
+ *   gsFunctionExpr source term (gsFunctionExpr.hpp:513-533)       -> rhs program (gsb200_expr_compile)
+ *
+ * What comes back is exactly Eigen's compressed column-major triple of
+ * gsSparseMatrix<T,0,index_t> (gsSparseMatrix.h:139; SparseMatrix.h:150-172):
+ * outer[cols+1], inner[nnz] ascending per column, values[nnz]; plus the dense
+ * column-major right-hand side (rows x nrhs).
+ *
+ * Error convention: every entry point returns 0 on success and a
+ * negative GSB200_E* code otherwise; gsb200_last_error() gives the message the
+ * C++ shim turns into GISMO_ERROR / std::runtime_error (gsDebug.h:89-132).
+ * There is no CPU fallback: without a usable CUDA device every compute entry
+ * point fails with GSB200_ENODEVICE.
+ */
+#ifndef GSB200_H
+#define GSB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSB200_ABI_VERSION 1
+#define GSB200_MAX_DIM 3
+
+enum {
+    GSB200_OK = 0,
+    GSB200_EINVAL = -1,      /* malformed problem description              */
+    GSB200_EUNSUPPORTED = -2,/* valid for the reference, outside this path */
+    GSB200_ENODEVICE = -3,   /* no CUDA device / driver                    */
+    GSB200_ECUDA = -4,       /* CUDA runtime error (message has details)   */
+    GSB200_ENOMEM = -5,
+    GSB200_ERANGE = -6,      /* nnz does not fit the 32-bit index_t of the reference */
+    GSB200_ESTATE = -7       /* call order violated (e.g. download before assemble)  */
+};
+
+/* Bilinear form selector.  POISSON = gsVisitorPoisson.h:89-106 /
+ * igrad(u,G)*igrad(u,G).tr()*meas(G) (poisson2_example.cpp:145);
+ * ELASTICITY = linear_elasticity_example.cpp:183-190 (lambda, mu in coef[0..1]);
+ * MASS = gsVisitorMass.h (u*u.tr()*meas(G)). */
+enum { GSB200_FORM_POISSON = 0, GSB200_FORM_ELASTICITY = 1, GSB200_FORM_MASS = 2 };
+
+/* Source-term description (gsFunctionExpr replacement). */
+enum { GSB200_RHS_NONE = 0, GSB200_RHS_PROGRAM = 1, GSB200_RHS_SAMPLES = 2 };
+
+/* Opcodes of the reverse-polish source-term program (stack machine over doubles).
+ * GSB200_OP_CONST is followed by one extra word: the index into the literal pool. */
+enum {
+    GSB200_OP_CONST = 0, GSB200_OP_X = 1, GSB200_OP_Y = 2, GSB200_OP_Z = 3,
+    GSB200_OP_ADD = 4, GSB200_OP_SUB = 5, GSB200_OP_MUL = 6, GSB200_OP_DIV = 7,
+    GSB200_OP_POW = 8, GSB200_OP_NEG = 9, GSB200_OP_SIN = 10, GSB200_OP_COS = 11,
+    GSB200_OP_TAN = 12, GSB200_OP_EXP = 13, GSB200_OP_LOG = 14, GSB200_OP_SQRT = 15,
+    GSB200_OP_ABS = 16, GSB200_OP_TANH = 17, GSB200_OP_SINH = 18, GSB200_OP_COSH = 19
+};
+#define GSB200_PROGRAM_MAX_OPS 256
+#define GSB200_PROGRAM_MAX_STACK 32
+
+/* Tensor-product B-spline basis of one patch (gsTensorBSplineBasis<d>). */
+typedef struct gsb200_basis {
+    int32_t dim;                          /* parametric dimension d (2 or 3)           */
+    int32_t degree[GSB200_MAX_DIM];       /* degree per direction                      */
+    int32_t nknots[GSB200_MAX_DIM];       /* knots incl. repetitions per direction     */
+    const double *knots[GSB200_MAX_DIM];  /* non-decreasing, open or not               */
+} gsb200_basis;
+
+/* One patch: discretisation basis + geometry map + local->global DOF map. */
+typedef struct gsb200_patch {
+    gsb200_basis space;        /* solution space basis (always polynomial: gsMultiBasis.hpp:37-41) */
+    gsb200_basis geo;          /* the geometry's own (coarse) basis (gsGeometry.hpp:539-597)       */
+    const double *geo_coefs;   /* N_geo x dim, column-major                                        */
+    const double *geo_weights; /* NULL (B-spline) or N_geo NURBS weights                           */
+    const int32_t *dofmap;     /* ncomp blocks of n_basis global indices: index(i,patch,comp);
+                                  index >= nfree means eliminated, row (index-nfree) of `fixed`    */
+} gsb200_patch;
+
+/* Compiled source term: reverse-polish program over x,y,z (see gsb200_expr_compile). */
+typedef struct gsb200_program {
+    int32_t nops;
+    const int32_t *ops;      /* opcode stream                         */
+    int32_t nconsts;
+    const double *consts;    /* literal pool                          */
+} gsb200_program;
+
+typedef struct gsb200_problem {
+    int32_t abi_version;       /* must be GSB200_ABI_VERSION                                  */
+    int32_t form;              /* GSB200_FORM_*                                               */
+    int32_t npatches;
+    const gsb200_patch *patches;
+    int32_t ncomp;             /* unknown components: 1 (Poisson/mass) or dim (elasticity)    */
+    int32_t nfree;             /* gsDofMapper::freeSize()  = matrix rows = cols               */
+    int32_t nfixed;            /* gsDofMapper::boundarySize()                                 */
+    const double *fixed;       /* nfixed x nrhs column-major eliminated-DOF values, or NULL (=0) */
+    int32_t nrhs;              /* right-hand-side columns (1 for all stock configs)           */
+    double coef[4];            /* form coefficients: elasticity lambda, mu                    */
+    double quA;                /* Gauss points per direction = floor(quA*p + quB + 0.5)       */
+    int32_t quB;
+    int32_t rhs_kind;          /* GSB200_RHS_*                                                */
+    const gsb200_program *rhs_programs; /* nrhs*ncomp... one program per rhs row component:
+                                  Poisson: nrhs programs; elasticity: ncomp programs (nrhs=1) */
+    const double *const *rhs_samples;   /* per patch: values at all quadrature points, tensor
+                                  order (direction 0 fastest), one block per component       */
+    /* Partition of the work over ranks.  Rank r integrates and owns the
+       matrix columns/rows of its share; nranks==1 means everything. */
+    int32_t rank, nranks;
+} gsb200_problem;
+
+typedef struct gsb200_assembler gsb200_assembler; /* opaque device-side state */
+
+/* Device-resident result (64-bit offsets; required beyond int32 nnz). */
+typedef struct gsb200_device_view {
+    int64_t nnz;
+    int32_t ncols;           /* = nfree                                       */
+    int32_t col_begin, col_end; /* columns owned by this rank                 */
+    const int64_t *outer;    /* device, ncols+1                               */
+    const int32_t *inner;    /* device, nnz                                   */
+    const double *values;    /* device, nnz                                   */
+    const double *rhs;       /* device, nfree x nrhs                          */
+} gsb200_device_view;
+
+/* Per-stage device times of the last gsb200_assemble(), CUDA events, milliseconds. */
+typedef struct gsb200_timings {
+    float geometry_ms;       /* K0: map data + coefficient tensor at quadrature points   */
+    float sweep_ms[GSB200_MAX_DIM]; /* K2: one sum-factorisation sweep per direction      */
+    float rhs_ms;            /* K3: load vector + elimination                            */
+    float pattern_ms;        /* K1 (last gsb200_build_pattern)                           */
+    float total_ms;          /* whole gsb200_assemble()                                  */
+    int32_t launches;        /* kernels launched by the last gsb200_assemble()           */
+    int64_t sweep_bytes[GSB200_MAX_DIM]; /* algorithmic bytes read+written per sweep     */
+    int64_t sweep_flops[GSB200_MAX_DIM]; /* FP64 flops executed per sweep                */
+    int32_t nchunks;
+} gsb200_timings;
+
+const char *gsb200_last_error(void);
+int gsb200_abi_version(void);
+/* Number of visible CUDA devices (0 and GSB200_OK when none). */
+int gsb200_device_count(int *count);
+
+/* Upload the problem to `device`, build 1-D basis/quadrature tables there. */
+int gsb200_create(const gsb200_problem *problem, int device, gsb200_assembler **out);
+void gsb200_destroy(gsb200_assembler *a);
+/* Use an existing cudaStream_t (e.g. torch's current stream); NULL = default stream. */
+int gsb200_set_stream(gsb200_assembler *a, void *cuda_stream);
+/* Cap for intermediate sum-factorisation storage in bytes (0 = automatic). */
+int gsb200_set_workspace_limit(gsb200_assembler *a, int64_t bytes);
+
+/* K1: sparsity pattern of the sparse system on the device
+   (replaces gsSparseSystem::reserve + sorted insertion of Eigen coeffRef,
+   gsSparseSystem.h:327-370, SparseMatrix.h:208-225,1366-1396). */
+int gsb200_build_pattern(gsb200_assembler *a);
+/* K0+K2+K3: assemble values and right-hand side on the device, asynchronously on the
+   assembler's stream (replaces gsAssembler::apply<gsVisitorPoisson> + push,
+   gsAssembler.h:668-722, gsVisitorPoisson.h:62-118, gsSparseSystem.h:972-1010, and the
+   gsExprAssembler equivalents gsExprAssembler.h:754-833). */
+int gsb200_assemble(gsb200_assembler *a);
+int gsb200_synchronize(gsb200_assembler *a);
+
+int gsb200_nnz(const gsb200_assembler *a, int64_t *nnz);
+int gsb200_device_view_get(const gsb200_assembler *a, gsb200_device_view *view);
+int gsb200_timings_get(const gsb200_assembler *a, gsb200_timings *t);
+
+/* Copy the result into caller-allocated host buffers laid out like Eigen's compressed
+   SparseMatrix (outer: nfree+1, inner/values: nnz) and gsMatrix rhs (nfree x nrhs). */
+int gsb200_download_csc(gsb200_assembler *a, int32_t *outer, int32_t *inner, double *values);
+int gsb200_download_rhs(gsb200_assembler *a, double *rhs);
+
+/* One call, host buffers in, host buffers out: what gsPoissonAssemblerB200::assemble()
+   does.  Pass outer/inner/values/rhs = NULL first to query *nnz. */
+int gsb200_assemble_host(const gsb200_problem *problem, int device, int64_t *nnz,
+                         int32_t *outer, int32_t *inner, double *values, double *rhs);
+
+/* Consumer: y = A x on the device-resident matrix, and a Jacobi-
+   preconditioned CG mirroring gsSparseSolver<>::CGDiagonal (gsSparseSolver.h:71-72).
+   x/y/b are host pointers of length nfree. */
+int gsb200_spmv_host(gsb200_assembler *a, const double *x, double *y);
+int gsb200_cg_host(gsb200_assembler *a, const double *b, double *x, int max_iter,
+                   double tol, int *iters, double *rel_residual);
+
+/* Compile an exprtk-style source term ("2*pi^2*sin(pi*x)*sin(pi*y)") into a
+   reverse-polish program.  Buffers are caller-allocated; on success *nops/*nconsts
+   hold the used lengths.  Supported: + - * / ^, unary -, parentheses, x y z, pi,
+   numeric literals, sin cos tan exp log sqrt abs tanh sinh cosh. */
+int gsb200_expr_compile(const char *expr, int32_t *ops, int32_t ops_cap, int32_t *nops,
+                        double *consts, int32_t consts_cap, int32_t *nconsts);
+/* Host evaluation of a compiled program (used by tests to pin the device VM). */
+int gsb200_expr_eval_host(const gsb200_program *prog, double x, double y, double z, double *out);
+
+/* Measure the device's FP64 FMA and copy-bandwidth peaks (roofline denominators
+   MEASURED_PEAKS.json does not carry). */
+int gsb200_measure_peaks(int device, double *fp64_tflops, double *dmma_tflops, double *hbm_gbs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSB200_H */
