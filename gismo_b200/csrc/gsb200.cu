@@ -1,0 +1,887 @@
+// gsb200.cu — host orchestration + C ABI (include/gsb200.h) of the B200 assembly path.
+// Compiled by nvcc for sm_100a into gismo_b200/csrc/libgsb200.so.  No torch, no Eigen.
+#include "kernels.cuh"
+#include <algorithm>
+#include <cstdarg>
+#include <string>
+#include <vector>
+#ifndef GSB200_EMULATE
+#include <cub/device/device_scan.cuh>
+#endif
+
+namespace gsb {
+
+static thread_local char g_err[1024] = "";
+static int g_launches = 0;
+void set_error(const char *fmt, ...)
+{
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
+}
+void note_launch() { ++g_launches; }
+
+#define GSB_TRY(expr) do { int rc_ = (expr); if (rc_) return rc_; } while (0)
+
+// Gauss-Legendre rule on [-1,1] (the reference tabulates the same numbers to 30 digits,
+// gsGaussRule.hpp:218-547): Newton on P_n in long double, rounded to double.
+static void gauss_rule(int n, std::vector<double> &x, std::vector<double> &w)
+{
+    x.assign(n, 0.0); w.assign(n, 0.0);
+    const long double pi = 3.14159265358979323846264338327950288L;
+    for (int i = 0; i < (n + 1) / 2; ++i) {
+        long double z = cosl(pi * (i + 0.75L) / (n + 0.5L)), dp = 1;
+        for (int it = 0; it < 100; ++it) {
+            long double p0 = 1, p1 = z;
+            for (int k = 2; k <= n; ++k) { const long double p2 = ((2 * k - 1) * z * p1 - (k - 1) * p0) / k; p0 = p1; p1 = p2; }
+            dp = n * (z * p1 - p0) / (z * z - 1);
+            const long double dz = p1 / dp;
+            z -= dz;
+            if (fabsl(dz) < 1e-19L) break;
+        }
+        long double p0 = 1, p1 = z;
+        for (int k = 2; k <= n; ++k) { const long double p2 = ((2 * k - 1) * z * p1 - (k - 1) * p0) / k; p0 = p1; p1 = p2; }
+        dp = n * (z * p1 - p0) / (z * z - 1);
+        const long double ww = 2 / ((1 - z * z) * dp * dp);
+        x[i] = (double)(-z); x[n - 1 - i] = (double)z;
+        w[i] = w[n - 1 - i] = (double)ww;
+    }
+    if (n % 2) x[n / 2] = 0.0;
+}
+
+template <class T>
+static int upload(T **dptr, const std::vector<T> &h, stream_t s)
+{
+    GSB_TRY(dev_malloc((void **)dptr, h.size() * sizeof(T)));
+    if (!h.empty()) GSB_TRY(dev_h2d(*dptr, h.data(), h.size() * sizeof(T), s));
+    return 0;
+}
+
+// ------------------------------------------------------------------ per-direction tables
+struct Dir1D {
+    int p = 0, q = 0, nfun = 0, nel = 0, Q = 0;
+    std::vector<int> span, first, nexit, plo, phi, ffirst, flast;
+    int *d_first = 0, *d_nexit = 0, *d_plo = 0, *d_phi = 0, *d_ffirst = 0, *d_flast = 0;
+    double2 *d_tab = 0; double *d_upt = 0, *d_hpt = 0, *d_gw = 0;
+    double2 *d_gtab = 0; int *d_gfirst = 0; int pg1 = 0, ngeo = 0;
+    void release() {
+        dev_free(d_first); dev_free(d_nexit); dev_free(d_plo); dev_free(d_phi); dev_free(d_ffirst); dev_free(d_flast);
+        dev_free(d_tab); dev_free(d_upt); dev_free(d_hpt); dev_free(d_gw); dev_free(d_gtab); dev_free(d_gfirst);
+    }
+};
+
+static int build_dir(Dir1D &d, const double *kn, int nk, int p, int q, const double *gkn, int gnk, int gp, stream_t s)
+{
+    d.p = p; d.q = q; d.nfun = nk - p - 1;
+    if (d.nfun < 1) { set_error("knot vector too short"); return GSB200_EINVAL; }
+    for (int i = 1; i < nk; ++i) if (kn[i] < kn[i - 1]) { set_error("knot vector not sorted"); return GSB200_EINVAL; }
+    for (int e = p; e < nk - p - 1; ++e) if (kn[e] < kn[e + 1]) d.span.push_back(e);
+    d.nel = (int)d.span.size();
+    if (!d.nel) { set_error("knot vector has no element"); return GSB200_EINVAL; }
+    d.Q = d.nel * q;
+    const int p1 = p + 1;
+    d.first.resize(d.nel); d.nexit.resize(d.nel);
+    d.ffirst.assign(d.nfun, d.nel); d.flast.assign(d.nfun, -1);
+    for (int e = 0; e < d.nel; ++e) {
+        d.first[e] = d.span[e] - p;
+        for (int a = 0; a < p1; ++a) { const int f = d.first[e] + a; d.ffirst[f] = std::min(d.ffirst[f], e); d.flast[f] = std::max(d.flast[f], e); }
+    }
+    for (int e = 0; e < d.nel; ++e) d.nexit[e] = (e + 1 < d.nel) ? d.first[e + 1] - d.first[e] : p1;
+    d.plo.resize(d.nfun); d.phi.resize(d.nfun);
+    for (int f = 0; f < d.nfun; ++f) {
+        if (d.flast[f] < 0) { set_error("basis function %d has empty support (knot multiplicity > degree+1?)", f); return GSB200_EINVAL; }
+        d.plo[f] = d.first[d.ffirst[f]]; d.phi[f] = d.first[d.flast[f]] + p;
+    }
+    std::vector<double> gx, gw;
+    gauss_rule(q, gx, gw);
+    std::vector<double> knv(kn, kn + nk), gknv(gkn, gkn + gnk);
+    double *d_kn = 0, *d_gkn = 0, *d_gx = 0; int *d_span = 0;
+    GSB_TRY(upload(&d_kn, knv, s)); GSB_TRY(upload(&d_gkn, gknv, s)); GSB_TRY(upload(&d_gx, gx, s));
+    GSB_TRY(upload(&d_span, d.span, s)); GSB_TRY(upload(&d.d_gw, gw, s));
+    GSB_TRY(upload(&d.d_first, d.first, s)); GSB_TRY(upload(&d.d_nexit, d.nexit, s));
+    GSB_TRY(upload(&d.d_plo, d.plo, s)); GSB_TRY(upload(&d.d_phi, d.phi, s));
+    GSB_TRY(upload(&d.d_ffirst, d.ffirst, s)); GSB_TRY(upload(&d.d_flast, d.flast, s));
+    GSB_TRY(dev_malloc((void **)&d.d_tab, sizeof(double2) * (size_t)d.Q * p1));
+    GSB_TRY(dev_malloc((void **)&d.d_upt, sizeof(double) * (size_t)d.Q));
+    GSB_TRY(dev_malloc((void **)&d.d_hpt, sizeof(double) * (size_t)d.Q));
+    BasisTableArgs B; B.knots = d_kn; B.span = d_span; B.gnodes = d_gx; B.p = p; B.nel = d.nel; B.q = q;
+    B.tab = d.d_tab; B.upt = d.d_upt; B.hpt = d.d_hpt;
+    GSB_LAUNCH(k_basis_table, dim3((d.Q + 127) / 128), dim3(128), s, B);
+    d.pg1 = gp + 1; d.ngeo = gnk - gp - 1;
+    GSB_TRY(dev_malloc((void **)&d.d_gtab, sizeof(double2) * (size_t)d.Q * d.pg1));
+    GSB_TRY(dev_malloc((void **)&d.d_gfirst, sizeof(int) * (size_t)d.Q));
+    GeoTableArgs G; G.knots = d_gkn; G.nknots = gnk; G.p = gp; G.npts = d.Q; G.upt = d.d_upt; G.gtab = d.d_gtab; G.gfirst = d.d_gfirst;
+    GSB_LAUNCH(k_geo_table, dim3((d.Q + 127) / 128), dim3(128), s, G);
+    GSB_TRY(dev_last_error("table kernels"));
+    GSB_TRY(dev_sync(s));
+    dev_free(d_kn); dev_free(d_gkn); dev_free(d_gx); dev_free(d_span);
+    return 0;
+}
+
+// segments of a sweep: functions [xa,xb) split into nseg contiguous exit ranges
+static std::vector<int> make_segments(const Dir1D &d, int xa, int xb, int nseg)
+{
+    std::vector<int> s;
+    nseg = std::max(1, std::min(nseg, xb - xa));
+    for (int k = 0; k < nseg; ++k) {
+        const int xs = xa + (int)((i64)(xb - xa) * k / nseg), xe = xa + (int)((i64)(xb - xa) * (k + 1) / nseg);
+        if (xe <= xs) continue;
+        s.push_back(d.ffirst[xs]); s.push_back(d.flast[xe - 1] + 1); s.push_back(xs); s.push_back(xe);
+    }
+    return s;
+}
+
+struct PatchDev {
+    int dim = 0;
+    Dir1D dir[3];
+    i64 nb = 0, ngeo_total = 0;
+    int *d_dofmap = 0; double *d_coefs = 0, *d_weights = 0;
+    unsigned char *d_colflag = 0; unsigned *d_st = 0; int nrun = 1;
+    int own_lo = 0, own_hi = 0;     // owner range along the last direction on this rank
+    void release() { for (int k = 0; k < 3; ++k) dir[k].release(); dev_free(d_dofmap); dev_free(d_coefs); dev_free(d_weights); dev_free(d_colflag); dev_free(d_st); }
+};
+
+} // namespace gsb
+
+using namespace gsb;
+
+struct gsb200_assembler {
+    int device = 0, dim = 0, form = 0, ncomp = 1, nfree = 0, nfixed = 0, nrhs = 1, rhs_kind = 0, rank = 0, nranks = 1;
+    double coef[4] = {0, 0, 0, 0};
+    std::vector<PatchDev> patches;
+    double *d_fixed = 0, *d_rhs = 0, *d_values = 0;
+    i64 *d_colptr = 0; int *d_inner = 0; int *d_npre = 0;
+    i64 nnz = 0;
+    std::vector<DevProgram> progs; std::vector<void *> prog_bufs;
+    stream_t stream = 0;
+    bool pattern_built = false, assembled = false, any_generic = false;
+    i64 ws_limit = 0; void *ws = 0; size_t ws_size = 0;
+    gsb200_timings tm;
+    int *d_seg = 0; size_t seg_cap = 0;
+#ifndef GSB200_EMULATE
+    std::vector<cudaEvent_t> ev; std::vector<int> ev_tag;   // tag: 0 geometry, 1..3 sweeps, 4 rhs, 5 total-begin, 6 total-end
+#endif
+    // CG work vectors
+    double *cg[6] = {0, 0, 0, 0, 0, 0};
+    ~gsb200_assembler() {
+        for (auto &p : patches) p.release();
+        dev_free(d_fixed); dev_free(d_rhs); dev_free(d_values); dev_free(d_colptr); dev_free(d_inner); dev_free(d_npre);
+        for (void *b : prog_bufs) dev_free(b);
+        dev_free(ws); dev_free(d_seg);
+        for (int k = 0; k < 6; ++k) dev_free(cg[k]);
+#ifndef GSB200_EMULATE
+        for (auto e : ev) cudaEventDestroy(e);
+#endif
+    }
+};
+
+namespace gsb {
+
+static int num_nodes(double quA, int quB, int p) { return (int)(quA * p + quB + 0.5); }
+
+static int select_device(int device)
+{
+#ifndef GSB200_EMULATE
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) { set_error("no CUDA device available (%s): the B200 path has no CPU fallback", e == cudaSuccess ? "count = 0" : cudaGetErrorString(e)); return GSB200_ENODEVICE; }
+    if (device < 0 || device >= n) { set_error("device %d out of range (have %d)", device, n); return GSB200_EINVAL; }
+    return dev_check(cudaSetDevice(device), "cudaSetDevice");
+#else
+    (void)device; return 0;
+#endif
+}
+
+static int scan_lengths(gsb200_assembler *a, unsigned long long *d_len, i64 *d_ptr, int n)
+{
+#ifndef GSB200_EMULATE
+    void *tmp = 0; size_t bytes = 0;
+    GSB_TRY(dev_check(cub::DeviceScan::ExclusiveSum(tmp, bytes, d_len, d_ptr, n + 1, a->stream), "cub scan size"));
+    GSB_TRY(dev_malloc(&tmp, bytes));
+    int rc = dev_check(cub::DeviceScan::ExclusiveSum(tmp, bytes, d_len, d_ptr, n + 1, a->stream), "cub scan");
+    if (!rc) rc = dev_sync(a->stream);
+    dev_free(tmp);
+    ++g_launches;
+    return rc;
+#else
+    GSB_LAUNCH(k_scan_serial, dim3(1), dim3(1), a->stream, d_len, d_ptr, n);
+    return 0;
+#endif
+}
+
+static void fill_pat_args(const gsb200_assembler *a, const PatchDev &P, PatArgs &A)
+{
+    A.dim = P.dim; A.ncomp = a->ncomp;
+    for (int k = 0; k < 3; ++k) {
+        A.n[k] = k < P.dim ? P.dir[k].nfun : 1; A.p[k] = k < P.dim ? P.dir[k].p : 0;
+        A.plo[k] = k < P.dim ? P.dir[k].d_plo : 0; A.phi[k] = k < P.dim ? P.dir[k].d_phi : 0;
+    }
+    A.dofmap = P.d_dofmap; A.nb = P.nb; A.nfree = a->nfree; A.own_lo = P.own_lo; A.own_hi = P.own_hi;
+    A.npre = a->d_npre; A.colflag = P.d_colflag; A.st = P.d_st; A.nrun = P.nrun;
+}
+
+static int build_pattern(gsb200_assembler *a)
+{
+    const int N = a->nfree;
+    stream_t s = a->stream;
+#ifndef GSB200_EMULATE
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s);
+#endif
+    unsigned long long *d_len = 0; int *d_cursor = 0; unsigned char *d_gneed = 0;
+    GSB_TRY(dev_malloc((void **)&d_len, sizeof(unsigned long long) * (size_t)(N + 1)));
+    GSB_TRY(dev_memset(d_len, 0, sizeof(unsigned long long) * (size_t)(N + 1), s));
+    GSB_TRY(dev_malloc((void **)&d_cursor, sizeof(int) * (size_t)(N + 1)));
+    GSB_TRY(dev_memset(d_cursor, 0, sizeof(int) * (size_t)(N + 1), s));
+    GSB_TRY(dev_malloc((void **)&d_gneed, (size_t)N + 1));
+    GSB_TRY(dev_memset(d_gneed, 0, (size_t)N + 1, s));
+    dev_free(a->d_colptr); dev_free(a->d_inner); dev_free(a->d_values); a->d_colptr = 0; a->d_inner = 0; a->d_values = 0;
+    GSB_TRY(dev_malloc((void **)&a->d_colptr, sizeof(i64) * (size_t)(N + 1)));
+    for (auto &P : a->patches) {
+        PatArgs A; fill_pat_args(a, P, A); A.len = d_len; A.colptr = 0; A.inner = 0; A.cursor = d_cursor; A.gneed = d_gneed;
+        const i64 nt = P.nb * a->ncomp;
+        GSB_LAUNCH(k_pattern<0>, dim3((unsigned)((nt + 127) / 128)), dim3(128), s, A);
+    }
+    GSB_TRY(scan_lengths(a, d_len, a->d_colptr, N));
+    i64 nnz_ub = 0;
+    GSB_TRY(dev_d2h(&nnz_ub, a->d_colptr + N, sizeof(i64), s));
+    GSB_TRY(dev_malloc((void **)&a->d_inner, sizeof(int) * (size_t)std::max<i64>(nnz_ub, 1)));
+    for (auto &P : a->patches) {
+        PatArgs A; fill_pat_args(a, P, A); A.len = d_len; A.colptr = a->d_colptr; A.inner = a->d_inner; A.cursor = d_cursor; A.gneed = d_gneed;
+        const i64 nt = P.nb * a->ncomp;
+        GSB_LAUNCH(k_pattern<1>, dim3((unsigned)((nt + 127) / 128)), dim3(128), s, A);
+    }
+    GSB_LAUNCH(k_pat_sort, dim3((N + 127) / 128), dim3(128), s, N, d_gneed, a->d_colptr, a->d_inner, d_len);
+    // coupled columns may have shrunk: rescan and compact
+    std::vector<unsigned char> gneed(N + 1);
+    GSB_TRY(dev_d2h(gneed.data(), d_gneed, (size_t)N + 1, s));
+    bool coupled = false; a->any_generic = false;
+    for (int g = 0; g < N; ++g) { if (gneed[g] == 2) coupled = true; }
+    if (coupled) {
+        i64 *d_newptr = 0; int *d_newinner = 0;
+        GSB_TRY(dev_malloc((void **)&d_newptr, sizeof(i64) * (size_t)(N + 1)));
+        GSB_TRY(scan_lengths(a, d_len, d_newptr, N));
+        i64 nnz = 0;
+        GSB_TRY(dev_d2h(&nnz, d_newptr + N, sizeof(i64), s));
+        GSB_TRY(dev_malloc((void **)&d_newinner, sizeof(int) * (size_t)std::max<i64>(nnz, 1)));
+        GSB_LAUNCH(k_pat_compact, dim3((N + 127) / 128), dim3(128), s, N, a->d_colptr, d_newptr, a->d_inner, d_newinner);
+        GSB_TRY(dev_sync(s));
+        dev_free(a->d_colptr); dev_free(a->d_inner);
+        a->d_colptr = d_newptr; a->d_inner = d_newinner; a->nnz = nnz;
+    } else a->nnz = nnz_ub;
+    // any column on the generic (search + atomic) path?  then values must start from zero
+    for (auto &P : a->patches) {
+        std::vector<unsigned char> fl((size_t)P.nb * a->ncomp);
+        GSB_TRY(dev_d2h(fl.data(), P.d_colflag, fl.size(), s));
+        for (unsigned char f : fl) if (f == 2) { a->any_generic = true; break; }
+    }
+    GSB_TRY(dev_malloc((void **)&a->d_values, sizeof(double) * (size_t)std::max<i64>(a->nnz, 1)));
+    GSB_TRY(dev_memset(a->d_values, 0, sizeof(double) * (size_t)std::max<i64>(a->nnz, 1), s));
+    GSB_TRY(dev_last_error("pattern kernels"));
+    GSB_TRY(dev_sync(s));
+    dev_free(d_len); dev_free(d_cursor); dev_free(d_gneed);
+#ifndef GSB200_EMULATE
+    cudaEventRecord(e1, s); cudaEventSynchronize(e1); cudaEventElapsedTime(&a->tm.pattern_ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+#endif
+    a->pattern_built = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------ sweep dispatch
+constexpr int pick_is(int P1, int NOUT)
+{
+    int best = 1;
+    for (int d = 1; d <= P1; ++d) if (P1 % d == 0 && d * P1 * NOUT <= 40) best = d;
+    return best;
+}
+template <class T> constexpr int n_has() { int n = 0; for (int o = 0; o < T::NOUT; ++o) for (int b = 0; b < 2; ++b) if (T::has(o, b)) ++n; return n; }
+template <class T> constexpr int n_first() { int n = 0; for (int k = 0; k < T::NT; ++k) if (T::first(k)) ++n; return n; }
+
+template <int P1, class T, bool FINAL>
+static void launch_sweep_t(const SweepArgs &A, int nseg, stream_t s, i64 *flops_per_point)
+{
+    constexpr int IS = pick_is(P1, T::NOUT);
+    dim3 grid((unsigned)((A.ncol + 127) / 128), P1 / IS, nseg);
+    auto kfn = k_sweep<P1, T, IS, FINAL>;
+    GSB_LAUNCH(kfn, grid, dim3(128), s, A);
+    *flops_per_point = (i64)P1 * (2 * T::NT - n_first<T>() + 2 * P1 * n_has<T>());
+}
+template <class T, bool FINAL>
+static int launch_sweep(int P1, const SweepArgs &A, int nseg, stream_t s, i64 *fpp)
+{
+    switch (P1) {
+    case 2: launch_sweep_t<2, T, FINAL>(A, nseg, s, fpp); break;
+    case 3: launch_sweep_t<3, T, FINAL>(A, nseg, s, fpp); break;
+    case 4: launch_sweep_t<4, T, FINAL>(A, nseg, s, fpp); break;
+    case 5: launch_sweep_t<5, T, FINAL>(A, nseg, s, fpp); break;
+    default: set_error("degree %d not supported by the sweep kernels (1..4)", P1 - 1); return GSB200_EUNSUPPORTED;
+    }
+    return 0;
+}
+
+enum { KIND_SYM = 0, KIND_GEN = 1, KIND_MASS = 2 };
+// stage: 0 = first of 3-D, 1 = middle of 3-D, 2 = last; 3 = first of 2-D
+static int dispatch_sweep(int kind, int stage, int P1, const SweepArgs &A, int nseg, stream_t s, i64 *fpp)
+{
+    if (kind == KIND_MASS) return stage == 2 ? launch_sweep<TMass, true>(P1, A, nseg, s, fpp) : launch_sweep<TMass, false>(P1, A, nseg, s, fpp);
+    if (stage == 2) return launch_sweep<TLast, true>(P1, A, nseg, s, fpp);
+    if (stage == 0) return kind == KIND_SYM ? launch_sweep<T3SymS1, false>(P1, A, nseg, s, fpp) : launch_sweep<T3GenS1, false>(P1, A, nseg, s, fpp);
+    if (stage == 1) return kind == KIND_SYM ? launch_sweep<T3SymS2, false>(P1, A, nseg, s, fpp) : launch_sweep<T3GenS2, false>(P1, A, nseg, s, fpp);
+    return kind == KIND_SYM ? launch_sweep<T2SymS1, false>(P1, A, nseg, s, fpp) : launch_sweep<T2GenS1, false>(P1, A, nseg, s, fpp);
+}
+static void stage_io(int kind, int stage, int *nin, int *nout)
+{
+    if (kind == KIND_MASS) { *nin = 1; *nout = 1; return; }
+    if (stage == 2) { *nin = 4; *nout = 1; return; }
+    if (stage == 0) { *nin = kind == KIND_SYM ? 6 : 9; *nout = kind == KIND_SYM ? 8 : 9; return; }
+    if (stage == 1) { *nin = kind == KIND_SYM ? 8 : 9; *nout = 4; return; }
+    *nin = kind == KIND_SYM ? 3 : 4; *nout = 4;
+}
+
+static int upload_segments(gsb200_assembler *a, const std::vector<int> &seg, size_t *offset_ints)
+{
+    // segments of all sweeps of one chunk live in one small device buffer, appended
+    if ((*offset_ints + seg.size()) > a->seg_cap) { set_error("segment buffer overflow"); return GSB200_EINVAL; }
+    GSB_TRY(dev_h2d(a->d_seg + *offset_ints, seg.data(), seg.size() * sizeof(int), a->stream));
+    *offset_ints += seg.size();
+    return 0;
+}
+
+#ifndef GSB200_EMULATE
+static void mark(gsb200_assembler *a, int tag)
+{
+    cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, a->stream); a->ev.push_back(e); a->ev_tag.push_back(tag);
+}
+#else
+static void mark(gsb200_assembler *, int) {}
+#endif
+
+static int nseg_for(i64 threads_per_seg, int nfun, int p1)
+{
+    // enough segments to put ~300k threads in flight, but keep each segment >= 4 spans long
+    const i64 target = 300000;
+    i64 n = (target + threads_per_seg - 1) / std::max<i64>(threads_per_seg, 1);
+    n = std::min<i64>(n, std::max(1, nfun / (4 * p1)));
+    return (int)std::max<i64>(1, n);
+}
+
+static int assemble(gsb200_assembler *a)
+{
+    stream_t s = a->stream;
+    const int N = a->nfree;
+    g_launches = 0;
+#ifndef GSB200_EMULATE
+    for (auto e : a->ev) cudaEventDestroy(e);
+    a->ev.clear(); a->ev_tag.clear();
+#endif
+    memset(a->tm.sweep_bytes, 0, sizeof a->tm.sweep_bytes); memset(a->tm.sweep_flops, 0, sizeof a->tm.sweep_flops);
+    a->tm.nchunks = 0;
+    mark(a, 5);
+    GSB_TRY(dev_memset(a->d_rhs, 0, sizeof(double) * (size_t)N * a->nrhs, s));
+    if (a->any_generic) GSB_TRY(dev_memset(a->d_values, 0, sizeof(double) * (size_t)std::max<i64>(a->nnz, 1), s));
+
+    const int dim = a->dim, L = dim - 1;
+    const int kind = a->form == GSB200_FORM_MASS ? KIND_MASS : (a->form == GSB200_FORM_POISSON ? KIND_SYM : KIND_GEN);
+    const int nblocks = a->form == GSB200_FORM_ELASTICITY ? a->ncomp * a->ncomp : 1;
+    const int nf = a->rhs_kind == GSB200_RHS_PROGRAM ? (int)a->progs.size() : 0;
+    int ncD, no1, no2 = 0, tmp;
+    if (dim == 3) { stage_io(kind, 0, &ncD, &no1); stage_io(kind, 1, &tmp, &no2); }
+    else stage_io(kind, 3, &ncD, &no1);
+
+    // workspace budget
+    i64 limit = a->ws_limit;
+#ifndef GSB200_EMULATE
+    if (limit <= 0) { size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot); limit = (i64)((fr + a->ws_size) * 0.85); }
+#else
+    if (limit <= 0) limit = (i64)1 << 30;
+#endif
+
+    for (size_t ip = 0; ip < a->patches.size(); ++ip) {
+        PatchDev &P = a->patches[ip];
+        if (P.own_hi <= P.own_lo) continue;
+        const Dir1D &d0 = P.dir[0], &d1 = P.dir[1], &dL = P.dir[L];
+        const i64 Q0 = d0.Q, Q1 = dim == 3 ? d1.Q : 1;
+        const i64 NI0 = (i64)d0.nfun * (2 * d0.p + 1), NI1 = dim == 3 ? (i64)d1.nfun * (2 * d1.p + 1) : 1;
+        const i64 n0 = d0.nfun, n1 = dim == 3 ? d1.nfun : 1;
+        // doubles of workspace per last-direction quadrature point
+        i64 perq = ncD * Q0 * Q1 + no1 * NI0 * Q1 + (dim == 3 ? no2 * NI1 * NI0 : 0) + nf * Q0 * Q1 + n0 * Q1 + (dim == 3 ? n1 * n0 : 0);
+        i64 maxpts = limit / (perq * 8);
+        const i64 minpts = (i64)(dL.p + 1) * dL.q;
+        if (maxpts < minpts) { set_error("workspace limit %lld B too small: one slab of patch %zu needs %lld B", (long long)limit, ip, (long long)(perq * 8 * minpts)); return GSB200_ENOMEM; }
+        int x_lo = P.own_lo;
+        while (x_lo < P.own_hi) {
+            // largest chunk [x_lo,x_hi) whose element footprint fits
+            int x_hi = x_lo + 1;
+            while (x_hi < P.own_hi && (i64)(dL.flast[x_hi] - dL.ffirst[x_lo] + 1) * dL.q <= maxpts) ++x_hi;
+            const int eL0 = dL.ffirst[x_lo], eL1 = dL.flast[x_hi - 1] + 1, ELc = eL1 - eL0;
+            const i64 QLc = (i64)ELc * dL.q;
+            const size_t need = (size_t)(perq * QLc) * 8;
+            if (need > a->ws_size) {
+                dev_free(a->ws); a->ws = 0; a->ws_size = 0;
+                GSB_TRY(dev_malloc(&a->ws, need)); a->ws_size = need;
+            }
+            double *w = (double *)a->ws;
+            double *D = w; w += ncD * Q0 * Q1 * QLc;
+            double *A1 = w; w += no1 * NI0 * Q1 * QLc;
+            double *A2 = w; if (dim == 3) w += no2 * NI1 * NI0 * QLc;
+            double *F = w; w += nf * Q0 * Q1 * QLc;
+            double *V1 = w; w += n0 * Q1 * QLc;
+            double *V2 = w;
+            const i64 npts = Q0 * Q1 * QLc;
+            size_t segoff = 0;
+            ++a->tm.nchunks;
+
+            for (int blk = 0; blk < nblocks; ++blk) {
+                const int brow = nblocks == 1 ? 0 : blk / a->ncomp, bcol = nblocks == 1 ? 0 : blk % a->ncomp;
+                // ---------------- K0
+                GeoArgs G; memset(&G, 0, sizeof G);
+                G.dim = dim;
+                for (int k = 0; k < dim; ++k) {
+                    const Dir1D &d = P.dir[k];
+                    G.qn[k] = (k == L) ? (int)QLc : d.Q; G.qoff[k] = (k == L) ? eL0 * d.q : 0;
+                    G.gtab[k] = d.d_gtab; G.gfirst[k] = d.d_gfirst; G.pg1[k] = d.pg1; G.ngeo[k] = d.ngeo;
+                    G.hpt[k] = d.d_hpt; G.gw[k] = d.d_gw; G.q1d[k] = d.q;
+                }
+                G.coefs = P.d_coefs; G.weights = P.d_weights; G.ngeo_total = P.ngeo_total;
+                G.form = a->form; G.brow = brow; G.bcol = bcol; G.lambda = a->coef[0]; G.mu = a->coef[1];
+                G.symD = kind == KIND_SYM;
+                G.D = D; G.dstride = npts;
+                if (blk == 0 && nf) { G.F = F; G.fstride = npts; G.nf = nf; for (int c = 0; c < nf; ++c) G.prog[c] = a->progs[c]; }
+                mark(a, 0);
+                if (dim == 2) { GSB_LAUNCH(k_geometry<2>, dim3((unsigned)((npts + 127) / 128)), dim3(128), s, G); }
+                else { GSB_LAUNCH(k_geometry<3>, dim3((unsigned)((npts + 127) / 128)), dim3(128), s, G); }
+
+                // ---------------- sweeps
+                FinalArgs Fa; memset(&Fa, 0, sizeof Fa);
+                Fa.dim = dim; Fa.L = L;
+                for (int k = 0; k < 3; ++k) {
+                    Fa.n[k] = k < dim ? P.dir[k].nfun : 1; Fa.p[k] = k < dim ? P.dir[k].p : 0;
+                    Fa.plo[k] = k < dim ? P.dir[k].d_plo : 0; Fa.phi[k] = k < dim ? P.dir[k].d_phi : 0;
+                }
+                Fa.dofmap = P.d_dofmap; Fa.nb = P.nb; Fa.brow = brow; Fa.bcol = bcol;
+                Fa.colflag = P.d_colflag; Fa.st = P.d_st; Fa.nrun = P.nrun;
+                Fa.colptr = a->d_colptr; Fa.inner = a->d_inner; Fa.values = a->d_values;
+                Fa.rhs = a->d_rhs; Fa.fixed = a->d_fixed; Fa.nfree = N; Fa.nfixed = a->nfixed; Fa.nrhs = a->nrhs;
+
+                auto base_args = [&](const Dir1D &d) {
+                    SweepArgs A; memset(&A, 0, sizeof A);
+                    A.first = d.d_first; A.nexit = d.d_nexit; A.tab = d.d_tab; A.q = d.q; A.p = d.p; A.fin = Fa;
+                    A.out_bq = 1; return A;
+                };
+                auto account = [&](int slot, const SweepArgs &A, const std::vector<int> &seg, i64 fpp, int nin, int nout, i64 npairs_out) {
+                    i64 pts = 0;
+                    for (size_t k = 0; k < seg.size(); k += 4) pts += (i64)(seg[k + 1] - seg[k]) * A.q;
+                    a->tm.sweep_flops[slot] += fpp * A.ncol * pts;
+                    a->tm.sweep_bytes[slot] += 8 * ((i64)nin * A.ncol * pts + (i64)nout * npairs_out * A.ncol);
+                };
+                i64 fpp = 0; int nin, nout;
+                if (dim == 3) {
+                    {   // S1: direction 0
+                        SweepArgs A = base_args(d0);
+                        A.in = D; A.in_cs = npts; A.in_es = (i64)d0.q * Q1 * QLc; A.in_ts = Q1 * QLc; A.in_os = 0; A.in_is = 1; A.e_in0 = 0;
+                        A.ncol = Q1 * QLc; A.ninner = A.ncol;
+                        A.out = A1; A.out_cs = NI0 * Q1 * QLc; A.out_ps = Q1 * QLc; A.out_os = 0; A.out_bq = A.ncol + 1; A.out_bs = 0; A.out_is = 1;
+                        const int nseg = nseg_for(A.ncol * (d0.p + 1), d0.nfun, d0.p + 1);
+                        std::vector<int> seg = make_segments(d0, 0, d0.nfun, nseg);
+                        A.seg = a->d_seg + segoff; GSB_TRY(upload_segments(a, seg, &segoff));
+                        mark(a, 1);
+                        GSB_TRY(dispatch_sweep(kind, 0, d0.p + 1, A, (int)seg.size() / 4, s, &fpp));
+                        stage_io(kind, 0, &nin, &nout); account(0, A, seg, fpp, nin, nout, NI0);
+                    }
+                    {   // S2: direction 1
+                        SweepArgs A = base_args(d1);
+                        A.in = A1; A.in_cs = NI0 * Q1 * QLc; A.in_es = (i64)d1.q * QLc; A.in_ts = QLc; A.in_os = Q1 * QLc; A.in_is = 1; A.e_in0 = 0;
+                        A.ncol = NI0 * QLc; A.ninner = QLc;
+                        A.out = A2; A.out_cs = NI1 * ELc * NI0 * dL.q; A.out_ps = (i64)ELc * NI0 * dL.q; A.out_os = dL.q; A.out_bq = dL.q; A.out_bs = NI0 * dL.q; A.out_is = 1;
+                        const int nseg = nseg_for(A.ncol * (d1.p + 1), d1.nfun, d1.p + 1);
+                        std::vector<int> seg = make_segments(d1, 0, d1.nfun, nseg);
+                        A.seg = a->d_seg + segoff; GSB_TRY(upload_segments(a, seg, &segoff));
+                        mark(a, 2);
+                        GSB_TRY(dispatch_sweep(kind, 1, d1.p + 1, A, (int)seg.size() / 4, s, &fpp));
+                        stage_io(kind, 1, &nin, &nout); account(1, A, seg, fpp, nin, nout, NI1);
+                    }
+                    {   // S3: direction 2, scatter into the CSC arrays
+                        SweepArgs A = base_args(dL);
+                        A.in = A2; A.in_cs = NI1 * ELc * NI0 * dL.q; A.in_es = NI0 * dL.q; A.in_ts = 1; A.in_os = (i64)ELc * NI0 * dL.q; A.in_is = dL.q; A.e_in0 = eL0;
+                        A.ncol = NI1 * NI0; A.ninner = NI0;
+                        const int nseg = nseg_for(A.ncol, x_hi - x_lo, dL.p + 1);
+                        std::vector<int> seg = make_segments(dL, x_lo, x_hi, nseg);
+                        A.seg = a->d_seg + segoff; GSB_TRY(upload_segments(a, seg, &segoff));
+                        mark(a, 3);
+                        GSB_TRY(dispatch_sweep(kind, 2, dL.p + 1, A, (int)seg.size() / 4, s, &fpp));
+                        stage_io(kind, 2, &nin, &nout); account(2, A, seg, fpp, nin, nout, (i64)(x_hi - x_lo) * (2 * dL.p + 1));
+                    }
+                } else {
+                    {   // S1: direction 0
+                        SweepArgs A = base_args(d0);
+                        A.in = D; A.in_cs = npts; A.in_es = (i64)d0.q * QLc; A.in_ts = QLc; A.in_os = 0; A.in_is = 1; A.e_in0 = 0;
+                        A.ncol = QLc; A.ninner = QLc;
+                        A.out = A1; A.out_cs = (i64)ELc * NI0 * dL.q; A.out_ps = dL.q; A.out_os = 0; A.out_bq = dL.q; A.out_bs = NI0 * dL.q; A.out_is = 1;
+                        const int nseg = nseg_for(A.ncol * (d0.p + 1), d0.nfun, d0.p + 1);
+                        std::vector<int> seg = make_segments(d0, 0, d0.nfun, nseg);
+                        A.seg = a->d_seg + segoff; GSB_TRY(upload_segments(a, seg, &segoff));
+                        mark(a, 1);
+                        GSB_TRY(dispatch_sweep(kind, 3, d0.p + 1, A, (int)seg.size() / 4, s, &fpp));
+                        stage_io(kind, 3, &nin, &nout); account(0, A, seg, fpp, nin, nout, NI0);
+                    }
+                    {   // S2: direction 1, scatter
+                        SweepArgs A = base_args(dL);
+                        A.in = A1; A.in_cs = (i64)ELc * NI0 * dL.q; A.in_es = NI0 * dL.q; A.in_ts = 1; A.in_os = 0; A.in_is = dL.q; A.e_in0 = eL0;
+                        A.ncol = NI0; A.ninner = NI0;
+                        const int nseg = nseg_for(A.ncol, x_hi - x_lo, dL.p + 1);
+                        std::vector<int> seg = make_segments(dL, x_lo, x_hi, nseg);
+                        A.seg = a->d_seg + segoff; GSB_TRY(upload_segments(a, seg, &segoff));
+                        mark(a, 2);
+                        GSB_TRY(dispatch_sweep(kind, 2, dL.p + 1, A, (int)seg.size() / 4, s, &fpp));
+                        stage_io(kind, 2, &nin, &nout); account(1, A, seg, fpp, nin, nout, (i64)(x_hi - x_lo) * (2 * dL.p + 1));
+                    }
+                }
+                // ---------------- K3: load vector (once per chunk)
+                if (blk == 0 && nf) {
+                    mark(a, 4);
+                    for (int c = 0; c < nf; ++c) {
+                        const int rcol = a->form == GSB200_FORM_ELASTICITY ? 0 : c;   // rhs column
+                        const int comp = a->form == GSB200_FORM_ELASTICITY ? c : 0;   // dof component
+                        VSweepArgs V; memset(&V, 0, sizeof V);
+                        auto vbase = [&](const Dir1D &d) { V.ffirst = d.d_ffirst; V.flast = d.d_flast; V.first = d.d_first; V.tab = d.d_tab; V.q = d.q; V.p1 = d.p + 1; };
+                        if (dim == 3) {
+                            vbase(d0); V.final_ = 0; V.x_lo = 0; V.x_hi = d0.nfun; V.e_in0 = 0;
+                            V.in = F + c * npts; V.in_qs = Q1 * QLc; V.in_os = 0; V.in_is = 1; V.ncol = Q1 * QLc; V.ninner = V.ncol;
+                            V.out = V1; V.out_fs = Q1 * QLc; V.out_os = 0; V.out_is = 1;
+                            GSB_LAUNCH(k_vsweep, dim3((unsigned)((V.ncol + 127) / 128), d0.nfun), dim3(128), s, V);
+                            vbase(d1); V.x_lo = 0; V.x_hi = d1.nfun;
+                            V.in = V1; V.in_qs = QLc; V.in_os = Q1 * QLc; V.in_is = 1; V.ncol = n0 * QLc; V.ninner = QLc;
+                            V.out = V2; V.out_fs = n0 * QLc; V.out_os = QLc; V.out_is = 1;
+                            GSB_LAUNCH(k_vsweep, dim3((unsigned)((V.ncol + 127) / 128), d1.nfun), dim3(128), s, V);
+                            vbase(dL); V.x_lo = x_lo; V.x_hi = x_hi; V.e_in0 = eL0; V.final_ = 1;
+                            V.in = V2; V.in_qs = 1; V.in_os = n0 * QLc; V.in_is = QLc; V.ncol = n1 * n0; V.ninner = n0;
+                            V.n0 = (int)n0; V.n1 = (int)n1; V.dimlow = 2; V.dofmap = P.d_dofmap + (i64)comp * P.nb; V.rhs = a->d_rhs + (i64)rcol * N; V.nfree = N;
+                            GSB_LAUNCH(k_vsweep, dim3((unsigned)((V.ncol + 127) / 128), x_hi - x_lo), dim3(128), s, V);
+                        } else {
+                            vbase(d0); V.final_ = 0; V.x_lo = 0; V.x_hi = d0.nfun; V.e_in0 = 0;
+                            V.in = F + c * npts; V.in_qs = QLc; V.in_os = 0; V.in_is = 1; V.ncol = QLc; V.ninner = QLc;
+                            V.out = V1; V.out_fs = QLc; V.out_os = 0; V.out_is = 1;
+                            GSB_LAUNCH(k_vsweep, dim3((unsigned)((V.ncol + 127) / 128), d0.nfun), dim3(128), s, V);
+                            vbase(dL); V.x_lo = x_lo; V.x_hi = x_hi; V.e_in0 = eL0; V.final_ = 1;
+                            V.in = V1; V.in_qs = 1; V.in_os = 0; V.in_is = QLc; V.ncol = n0; V.ninner = n0;
+                            V.n0 = (int)n0; V.n1 = 1; V.dimlow = 1; V.dofmap = P.d_dofmap + (i64)comp * P.nb; V.rhs = a->d_rhs + (i64)rcol * N; V.nfree = N;
+                            GSB_LAUNCH(k_vsweep, dim3((unsigned)((V.ncol + 127) / 128), x_hi - x_lo), dim3(128), s, V);
+                        }
+                    }
+                }
+            }
+            x_lo = x_hi;
+        }
+    }
+    mark(a, 6);
+    GSB_TRY(dev_last_error("assembly kernels"));
+    a->tm.launches = g_launches;
+    a->assembled = true;
+    return 0;
+}
+
+static void finish_timings(gsb200_assembler *a)
+{
+#ifndef GSB200_EMULATE
+    gsb200_timings &t = a->tm;
+    t.geometry_ms = t.rhs_ms = t.total_ms = 0; for (int k = 0; k < 3; ++k) t.sweep_ms[k] = 0;
+    for (size_t i = 0; i + 1 < a->ev.size(); ++i) {
+        float ms = 0; cudaEventElapsedTime(&ms, a->ev[i], a->ev[i + 1]);
+        const int tag = a->ev_tag[i];
+        if (tag == 0) t.geometry_ms += ms; else if (tag >= 1 && tag <= 3) t.sweep_ms[tag - 1] += ms; else if (tag == 4) t.rhs_ms += ms;
+    }
+    if (a->ev.size() >= 2) cudaEventElapsedTime(&t.total_ms, a->ev.front(), a->ev.back());
+#else
+    (void)a;
+#endif
+}
+
+} // namespace gsb
+
+// ====================================================================== C ABI
+extern "C" {
+
+const char *gsb200_last_error(void) { return g_err; }
+int gsb200_abi_version(void) { return GSB200_ABI_VERSION; }
+
+int gsb200_device_count(int *count)
+{
+    if (!count) return GSB200_EINVAL;
+#ifndef GSB200_EMULATE
+    int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) n = 0; *count = n;
+#else
+    *count = 1;
+#endif
+    return GSB200_OK;
+}
+
+int gsb200_create(const gsb200_problem *pb, int device, gsb200_assembler **out)
+{
+    if (!pb || !out) { set_error("create: null argument"); return GSB200_EINVAL; }
+    *out = 0;
+    if (pb->abi_version != GSB200_ABI_VERSION) { set_error("ABI version mismatch: caller %d, library %d", pb->abi_version, GSB200_ABI_VERSION); return GSB200_EINVAL; }
+    if (pb->npatches < 1 || !pb->patches || pb->nfree < 0 || pb->nfixed < 0 || pb->nrhs < 1) { set_error("create: malformed problem sizes"); return GSB200_EINVAL; }
+    const int dim = pb->patches[0].space.dim;
+    if (dim != 2 && dim != 3) { set_error("parametric dimension %d unsupported (2 or 3)", dim); return GSB200_EUNSUPPORTED; }
+    if (pb->form != GSB200_FORM_POISSON && pb->form != GSB200_FORM_ELASTICITY && pb->form != GSB200_FORM_MASS) { set_error("unknown form %d", pb->form); return GSB200_EUNSUPPORTED; }
+    const int ncomp_expected = pb->form == GSB200_FORM_ELASTICITY ? dim : 1;
+    if (pb->ncomp != ncomp_expected) { set_error("form %d needs ncomp=%d, got %d", pb->form, ncomp_expected, pb->ncomp); return GSB200_EINVAL; }
+    if (pb->form == GSB200_FORM_ELASTICITY && pb->nrhs != 1) { set_error("elasticity supports one right-hand side"); return GSB200_EUNSUPPORTED; }
+    if (pb->rhs_kind == GSB200_RHS_SAMPLES) { set_error("sampled source terms are not implemented yet"); return GSB200_EUNSUPPORTED; }
+    if (pb->nranks < 1 || pb->rank < 0 || pb->rank >= pb->nranks) { set_error("bad rank/nranks"); return GSB200_EINVAL; }
+    GSB_TRY(select_device(device));
+
+    gsb200_assembler *a = new gsb200_assembler();
+    a->device = device; a->dim = dim; a->form = pb->form; a->ncomp = pb->ncomp; a->nfree = pb->nfree; a->nfixed = pb->nfixed;
+    a->nrhs = pb->nrhs; a->rhs_kind = pb->rhs_kind; a->rank = pb->rank; a->nranks = pb->nranks;
+    memcpy(a->coef, pb->coef, sizeof a->coef);
+    memset(&a->tm, 0, sizeof a->tm);
+    int rc = 0;
+    a->patches.resize(pb->npatches);
+    for (int ip = 0; ip < pb->npatches && !rc; ++ip) {
+        const gsb200_patch &S = pb->patches[ip];
+        PatchDev &P = a->patches[ip];
+        if (S.space.dim != dim || S.geo.dim != dim) { set_error("patch %d: mixed dimensions", ip); rc = GSB200_EINVAL; break; }
+        P.dim = dim; P.nb = 1; P.ngeo_total = 1;
+        for (int k = 0; k < dim && !rc; ++k) {
+            const int p = S.space.degree[k], gp = S.geo.degree[k];
+            if (p < 1 || p > 4) { set_error("patch %d: degree %d unsupported (1..4)", ip, p); rc = GSB200_EUNSUPPORTED; break; }
+            if (gp < 1 || gp > GSB_MAXP) { set_error("patch %d: geometry degree %d unsupported", ip, gp); rc = GSB200_EUNSUPPORTED; break; }
+            if (!S.space.knots[k] || !S.geo.knots[k]) { set_error("patch %d: null knots", ip); rc = GSB200_EINVAL; break; }
+            const int q = num_nodes(pb->quA, pb->quB, p);
+            if (q < 1 || q > 16) { set_error("quadrature size %d unsupported", q); rc = GSB200_EUNSUPPORTED; break; }
+            rc = build_dir(P.dir[k], S.space.knots[k], S.space.nknots[k], p, q, S.geo.knots[k], S.geo.nknots[k], gp, a->stream);
+            if (rc) break;
+            P.nb *= P.dir[k].nfun; P.ngeo_total *= P.dir[k].ngeo;
+        }
+        if (rc) break;
+        if (!S.dofmap || !S.geo_coefs) { set_error("patch %d: null dofmap/coefs", ip); rc = GSB200_EINVAL; break; }
+        std::vector<int> dm(S.dofmap, S.dofmap + P.nb * pb->ncomp);
+        for (int g : dm) if (g < 0 || g >= pb->nfree + pb->nfixed) { set_error("patch %d: dof index %d out of range", ip, g); rc = GSB200_EINVAL; break; }
+        if (rc) break;
+        std::vector<double> cf(S.geo_coefs, S.geo_coefs + P.ngeo_total * dim);
+        if ((rc = upload(&P.d_dofmap, dm, a->stream))) break;
+        if ((rc = upload(&P.d_coefs, cf, a->stream))) break;
+        if (S.geo_weights) { std::vector<double> wv(S.geo_weights, S.geo_weights + P.ngeo_total); if ((rc = upload(&P.d_weights, wv, a->stream))) break; }
+        const int L = dim - 1;
+        P.nrun = 1; for (int k = 1; k < dim; ++k) P.nrun *= 2 * P.dir[k].p + 1;
+        if ((rc = dev_malloc((void **)&P.d_colflag, (size_t)P.nb * pb->ncomp))) break;
+        if ((rc = dev_memset(P.d_colflag, 0, (size_t)P.nb * pb->ncomp, a->stream))) break;
+        if (pb->ncomp == 1) { if ((rc = dev_malloc((void **)&P.d_st, sizeof(unsigned) * (size_t)P.nb * P.nrun))) break; }
+        // ownership: one patch -> slabs along the last direction; several -> round robin by patch
+        const int nL = P.dir[L].nfun;
+        if (pb->npatches == 1) { P.own_lo = (int)((i64)nL * pb->rank / pb->nranks); P.own_hi = (int)((i64)nL * (pb->rank + 1) / pb->nranks); }
+        else { P.own_lo = 0; P.own_hi = (ip % pb->nranks == pb->rank) ? nL : 0; }
+    }
+    if (!rc && pb->fixed) { std::vector<double> fx(pb->fixed, pb->fixed + (size_t)pb->nfixed * pb->nrhs); rc = upload(&a->d_fixed, fx, a->stream); }
+    if (!rc && pb->rhs_kind == GSB200_RHS_PROGRAM) {
+        const int np = pb->form == GSB200_FORM_ELASTICITY ? pb->ncomp : pb->nrhs;
+        if (!pb->rhs_programs) { set_error("rhs_kind=PROGRAM but no programs"); rc = GSB200_EINVAL; }
+        for (int c = 0; c < np && !rc; ++c) {
+            const gsb200_program &pr = pb->rhs_programs[c];
+            if (pr.nops < 1 || pr.nops > GSB200_PROGRAM_MAX_OPS) { set_error("rhs program %d has bad length", c); rc = GSB200_EINVAL; break; }
+            std::vector<int> ops(pr.ops, pr.ops + pr.nops); std::vector<double> cs(pr.consts, pr.consts + pr.nconsts);
+            int *d_ops = 0; double *d_cs = 0;
+            if ((rc = upload(&d_ops, ops, a->stream))) break;
+            if ((rc = upload(&d_cs, cs, a->stream))) break;
+            a->prog_bufs.push_back(d_ops); a->prog_bufs.push_back(d_cs);
+            DevProgram dp; dp.ops = d_ops; dp.consts = d_cs; dp.nops = pr.nops; a->progs.push_back(dp);
+        }
+    }
+    if (!rc) rc = dev_malloc((void **)&a->d_rhs, sizeof(double) * (size_t)std::max(1, pb->nfree) * pb->nrhs);
+    if (!rc) rc = dev_malloc((void **)&a->d_npre, sizeof(int) * (size_t)(pb->nfree + 1));
+    if (!rc) rc = dev_memset(a->d_npre, 0, sizeof(int) * (size_t)(pb->nfree + 1), a->stream);
+    if (!rc) for (auto &P : a->patches) {
+        const i64 nt = P.nb * pb->ncomp;
+        GSB_LAUNCH(k_pat_preimages, dim3((unsigned)((nt + 127) / 128)), dim3(128), a->stream, P.d_dofmap, nt, pb->nfree, a->d_npre);
+    }
+    a->seg_cap = 1 << 16;
+    if (!rc) rc = dev_malloc((void **)&a->d_seg, a->seg_cap * sizeof(int));
+    if (!rc) rc = dev_sync(a->stream);
+    if (rc) { delete a; return rc; }
+    *out = a;
+    return GSB200_OK;
+}
+
+void gsb200_destroy(gsb200_assembler *a) { delete a; }
+
+int gsb200_set_stream(gsb200_assembler *a, void *cuda_stream)
+{
+    if (!a) return GSB200_EINVAL;
+#ifndef GSB200_EMULATE
+    a->stream = (cudaStream_t)cuda_stream;
+#else
+    (void)cuda_stream;
+#endif
+    return GSB200_OK;
+}
+
+int gsb200_set_workspace_limit(gsb200_assembler *a, int64_t bytes) { if (!a) return GSB200_EINVAL; a->ws_limit = bytes; return GSB200_OK; }
+
+int gsb200_build_pattern(gsb200_assembler *a)
+{
+    if (!a) { set_error("null assembler"); return GSB200_EINVAL; }
+    GSB_TRY(select_device(a->device));
+    return build_pattern(a);
+}
+
+int gsb200_assemble(gsb200_assembler *a)
+{
+    if (!a) { set_error("null assembler"); return GSB200_EINVAL; }
+    if (!a->pattern_built) { set_error("gsb200_assemble called before gsb200_build_pattern"); return GSB200_ESTATE; }
+    GSB_TRY(select_device(a->device));
+    return assemble(a);
+}
+
+int gsb200_synchronize(gsb200_assembler *a)
+{
+    if (!a) return GSB200_EINVAL;
+    GSB_TRY(dev_sync(a->stream));
+    finish_timings(a);
+    return GSB200_OK;
+}
+
+int gsb200_nnz(const gsb200_assembler *a, int64_t *nnz)
+{
+    if (!a || !nnz) return GSB200_EINVAL;
+    if (!a->pattern_built) { set_error("pattern not built"); return GSB200_ESTATE; }
+    *nnz = a->nnz; return GSB200_OK;
+}
+
+int gsb200_device_view_get(const gsb200_assembler *a, gsb200_device_view *v)
+{
+    if (!a || !v) return GSB200_EINVAL;
+    if (!a->pattern_built) { set_error("pattern not built"); return GSB200_ESTATE; }
+    v->nnz = a->nnz; v->ncols = a->nfree; v->col_begin = 0; v->col_end = a->nfree;
+    v->outer = (const int64_t *)a->d_colptr; v->inner = a->d_inner; v->values = a->d_values; v->rhs = a->d_rhs;
+    return GSB200_OK;
+}
+
+int gsb200_timings_get(const gsb200_assembler *a, gsb200_timings *t)
+{
+    if (!a || !t) return GSB200_EINVAL;
+    *t = a->tm; return GSB200_OK;
+}
+
+int gsb200_download_csc(gsb200_assembler *a, int32_t *outer, int32_t *inner, double *values)
+{
+    if (!a || !outer || !inner || !values) { set_error("download: null argument"); return GSB200_EINVAL; }
+    if (!a->assembled) { set_error("download before assemble"); return GSB200_ESTATE; }
+    if (a->nnz > 2147483647LL) { set_error("nnz = %lld exceeds the 32-bit index_t of gsSparseMatrix; use the device view", (long long)a->nnz); return GSB200_ERANGE; }
+    std::vector<i64> ptr((size_t)a->nfree + 1);
+    GSB_TRY(dev_d2h(ptr.data(), a->d_colptr, ptr.size() * sizeof(i64), a->stream));
+    for (size_t i = 0; i < ptr.size(); ++i) outer[i] = (int32_t)ptr[i];
+    GSB_TRY(dev_d2h(inner, a->d_inner, sizeof(int) * (size_t)a->nnz, a->stream));
+    GSB_TRY(dev_d2h(values, a->d_values, sizeof(double) * (size_t)a->nnz, a->stream));
+    finish_timings(a);
+    return GSB200_OK;
+}
+
+int gsb200_download_rhs(gsb200_assembler *a, double *rhs)
+{
+    if (!a || !rhs) { set_error("download: null argument"); return GSB200_EINVAL; }
+    if (!a->assembled) { set_error("download before assemble"); return GSB200_ESTATE; }
+    return dev_d2h(rhs, a->d_rhs, sizeof(double) * (size_t)a->nfree * a->nrhs, a->stream);
+}
+
+int gsb200_assemble_host(const gsb200_problem *pb, int device, int64_t *nnz, int32_t *outer, int32_t *inner, double *values, double *rhs)
+{
+    static const gsb200_problem *pending_pb = 0; static gsb200_assembler *pending = 0;
+    if (!pb || !nnz) { set_error("assemble_host: null argument"); return GSB200_EINVAL; }
+    gsb200_assembler *a = 0;
+    if (pending && pending_pb == pb) { a = pending; pending = 0; pending_pb = 0; }
+    else {
+        if (pending) { gsb200_destroy(pending); pending = 0; pending_pb = 0; }
+        GSB_TRY(gsb200_create(pb, device, &a));
+        int rc = gsb200_build_pattern(a);
+        if (!rc) rc = gsb200_assemble(a);
+        if (!rc) rc = gsb200_synchronize(a);
+        if (rc) { gsb200_destroy(a); return rc; }
+    }
+    *nnz = a->nnz;
+    if (!outer || !inner || !values) { pending = a; pending_pb = pb; return GSB200_OK; }   // size query: keep the result
+    int rc = gsb200_download_csc(a, outer, inner, values);
+    if (!rc && rhs) rc = gsb200_download_rhs(a, rhs);
+    gsb200_destroy(a);
+    return rc;
+}
+
+// ---------------------------------------------------------------- consumer: SpMV + Jacobi-CG
+static int cg_alloc(gsb200_assembler *a)
+{
+    for (int k = 0; k < 6; ++k) if (!a->cg[k]) GSB_TRY(dev_malloc((void **)&a->cg[k], sizeof(double) * (size_t)(a->nfree + 1)));
+    return 0;
+}
+
+int gsb200_spmv_host(gsb200_assembler *a, const double *x, double *y)
+{
+    if (!a || !x || !y) return GSB200_EINVAL;
+    if (!a->assembled) { set_error("spmv before assemble"); return GSB200_ESTATE; }
+    GSB_TRY(select_device(a->device));
+    GSB_TRY(cg_alloc(a));
+    const int n = a->nfree;
+    GSB_TRY(dev_h2d(a->cg[0], x, sizeof(double) * (size_t)n, a->stream));
+    GSB_LAUNCH(k_spmv, dim3((n + 127) / 128), dim3(128), a->stream, n, a->d_colptr, a->d_inner, a->d_values, a->cg[0], a->cg[1]);
+    return dev_d2h(y, a->cg[1], sizeof(double) * (size_t)n, a->stream);
+}
+
+static int dev_dot(gsb200_assembler *a, const double *u, const double *v, double *out)
+{
+    double *d = a->cg[5] + a->nfree;   // scalar slot after the vector
+    GSB_TRY(dev_memset(d, 0, sizeof(double), a->stream));
+    GSB_LAUNCH(k_dot, dim3(296), dim3(256), a->stream, a->nfree, u, v, d);
+    return dev_d2h(out, d, sizeof(double), a->stream);
+}
+
+int gsb200_cg_host(gsb200_assembler *a, const double *b, double *x, int max_iter, double tol, int *iters, double *rel_residual)
+{
+    if (!a || !b || !x) return GSB200_EINVAL;
+    if (!a->assembled) { set_error("cg before assemble"); return GSB200_ESTATE; }
+    GSB_TRY(select_device(a->device));
+    GSB_TRY(cg_alloc(a));
+    const int n = a->nfree; stream_t s = a->stream; const dim3 g((n + 127) / 128), t(128);
+    double *X = a->cg[0], *R = a->cg[1], *Z = a->cg[2], *Pv = a->cg[3], *Q = a->cg[4], *Dg = a->cg[5];
+    GSB_TRY(dev_memset(X, 0, sizeof(double) * (size_t)n, s));
+    GSB_TRY(dev_h2d(R, b, sizeof(double) * (size_t)n, s));
+    GSB_LAUNCH(k_diag, g, t, s, n, a->d_colptr, a->d_inner, a->d_values, Dg);
+    GSB_LAUNCH(k_div, g, t, s, n, R, Dg, Z);
+    GSB_TRY(dev_d2d(Pv, Z, sizeof(double) * (size_t)n, s));
+    double rz = 0, bb = 0, rr = 0;
+    GSB_TRY(dev_dot(a, R, Z, &rz)); GSB_TRY(dev_dot(a, R, R, &bb));
+    rr = bb; int it = 0;
+    const double thr = tol * tol * bb;
+    while (it < max_iter && rr > thr) {
+        GSB_LAUNCH(k_spmv, g, t, s, n, a->d_colptr, a->d_inner, a->d_values, Pv, Q);
+        double pq = 0; GSB_TRY(dev_dot(a, Pv, Q, &pq));
+        const double alpha = rz / pq;
+        GSB_LAUNCH(k_axpy, g, t, s, n, X, alpha, Pv, X);
+        GSB_LAUNCH(k_axpy, g, t, s, n, R, -alpha, Q, R);
+        GSB_LAUNCH(k_div, g, t, s, n, R, Dg, Z);
+        double rz2 = 0; GSB_TRY(dev_dot(a, R, Z, &rz2)); GSB_TRY(dev_dot(a, R, R, &rr));
+        const double beta = rz2 / rz; rz = rz2;
+        GSB_LAUNCH(k_axpy, g, t, s, n, Z, beta, Pv, Pv);
+        ++it;
+    }
+    if (iters) *iters = it;
+    if (rel_residual) *rel_residual = bb > 0 ? sqrt(rr / bb) : 0.0;
+    return dev_d2h(x, X, sizeof(double) * (size_t)n, s);
+}
+
+int gsb200_expr_eval_host(const gsb200_program *prog, double x, double y, double z, double *out)
+{
+    if (!prog || !out) return GSB200_EINVAL;
+    // same interpreter source as the device (program_eval is host+device)
+    DevProgram dp; dp.ops = prog->ops; dp.consts = prog->consts; dp.nops = prog->nops;
+#ifndef GSB200_EMULATE
+    *out = program_eval(dp, x, y, z);
+#else
+    *out = program_eval(dp, x, y, z);
+#endif
+    return GSB200_OK;
+}
+
+} // extern "C"
+
+#ifndef GSB200_EMULATE
+#include "peaks.cuh"
+#else
+extern "C" int gsb200_measure_peaks(int, double *, double *, double *) { gsb::set_error("no device in the interpreter build"); return GSB200_ENODEVICE; }
+#endif

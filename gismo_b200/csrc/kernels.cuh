@@ -1,0 +1,688 @@
+// kernels.cuh — device kernels of the B200 assembly path (sm_100a).
+//
+// Algorithm: GLOBAL sum factorisation with row (here: CSC-column) ownership.
+//   K_{j,i} = sum_q sum_{ab} D_ab(q) d_a N_j(q) d_b N_i(q)  with  N_i = prod_k B_{i_k}(xi_k)
+// is contracted one parametric direction at a time over the whole patch:
+//   K0  geometry:   D_ab(q) = w_q |det J| (J^-1 J^-T)_ab  (+ load density w|J|f)   [a6,a7,a8,a18]
+//   S1  sweep dir 0: A1[o][(i0,d0)][q1,q2] = sum_{q0} B^a_{i0} B^b_{i0+d0} D_c
+//   S2  sweep dir 1: A2[g][(i1,d1)][(i0,d0)][q2]
+//   S3  sweep dir 2: K[(i0,i1,i2),(d0,d1,d2)] -> written straight into its CSC slot
+// Each sweep thread owns one "column" of the remaining index space and marches along the
+// swept direction keeping, in registers, the (p+1)^2 partial sums of the function pairs
+// alive on the current knot span; a pair is complete when its older function leaves the
+// span window, and is then emitted exactly once.  No atomics, no element-local matrices,
+// every matrix entry is produced by exactly one thread (its column owner).
+// 1-D basis values/derivatives come from de Boor / A2.3 recursion evaluated in registers
+// once per 1-D quadrature point (k_basis_table) and are broadcast from L1.
+//
+// Reference functions replaced: a2 gsBSplineBasis.hpp:863-1041, a3
+// gsTensorBSplineBasis.hpp:166-205, a4 gsTensorBasis.hpp:634-728, a6 gsGeometry.hpp:539-597,
+// a7 gsFunction.hpp:604-862, a8 gsQuadRule.h:177-201, a10 gsVisitorPoisson.h:62-118,
+// a11 gsExpressions.h (igrad/ijac/idiv/meas), a14/a15 gsSparseSystem.h:972-1010 /
+// gsExprAssembler.h:553-630, a16 SparseMatrix.h:208-225,1366-1396, a18 gsFunctionExpr.hpp:513.
+#pragma once
+#include "platform.cuh"
+#include "../../include/gsb200.h"
+#include <type_traits>
+#include <utility>
+
+namespace gsb {
+
+#define GSB_MAXP 7            // max degree of the 1-D table kernels
+#ifdef GSB200_EMULATE
+#define GSB_CX constexpr
+#else
+#define GSB_CX __host__ __device__ constexpr
+#endif
+
+template <int I, int N, class F>
+GSB_DEVICE void static_for(F &&f)
+{
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Term tables.  A term (o, c, a, b) adds  B^(a)_owner(q) * B^(b)_partner(q) * in_c(q)  to out_o.
+// a/b = 0: value, 1: first derivative in the swept direction.
+#define GSB_PK(o, c, a, b) (((o) << 8) | ((c) << 2) | ((a) << 1) | (b))
+template <class D>
+struct TermOps {
+    static GSB_CX int o(int k) { return D::pk(k) >> 8; }
+    static GSB_CX int c(int k) { return (D::pk(k) >> 2) & 63; }
+    static GSB_CX int a(int k) { return (D::pk(k) >> 1) & 1; }
+    static GSB_CX int b(int k) { return D::pk(k) & 1; }
+    // first term contributing to z[o][b] ?
+    static GSB_CX bool first(int k) { for (int j = 0; j < k; ++j) if (o(j) == o(k) && b(j) == b(k)) return false; return true; }
+    static GSB_CX bool has(int oo, int bb) { for (int j = 0; j < D::NT; ++j) if (o(j) == oo && b(j) == bb) return true; return false; }
+};
+// symmetric coefficient tensor, 3-D (Poisson): D = {00,01,02,11,12,22}
+struct T3SymS1 : TermOps<T3SymS1> { enum { NIN = 6, NOUT = 8, NT = 8 };
+    static GSB_CX int pk(int k) { const int v[8] = {GSB_PK(0,0,1,1), GSB_PK(1,1,1,0), GSB_PK(2,1,0,1), GSB_PK(3,3,0,0),
+                                                    GSB_PK(4,2,1,0), GSB_PK(5,2,0,1), GSB_PK(6,4,0,0), GSB_PK(7,5,0,0)}; return v[k]; } };
+// outputs g = 2*(a==2)+(b==2): flags still needed in direction 2
+struct T3SymS2 : TermOps<T3SymS2> { enum { NIN = 8, NOUT = 4, NT = 9 };
+    static GSB_CX int pk(int k) { const int v[9] = {GSB_PK(0,0,0,0), GSB_PK(0,1,0,1), GSB_PK(0,2,1,0), GSB_PK(0,3,1,1),
+                                                    GSB_PK(1,4,0,0), GSB_PK(2,5,0,0), GSB_PK(1,6,1,0), GSB_PK(2,6,0,1),
+                                                    GSB_PK(3,7,0,0)}; return v[k]; } };
+// last direction of any gradient-gradient form: in_g, g = 2*a+b
+struct TLast : TermOps<TLast> { enum { NIN = 4, NOUT = 1, NT = 4 };
+    static GSB_CX int pk(int k) { const int v[4] = {GSB_PK(0,0,0,0), GSB_PK(0,1,0,1), GSB_PK(0,2,1,0), GSB_PK(0,3,1,1)}; return v[k]; } };
+// general (non-symmetric) tensor, 3-D: c = 3a+b
+struct T3GenS1 : TermOps<T3GenS1> { enum { NIN = 9, NOUT = 9, NT = 9 };
+    static GSB_CX int pk(int k) { const int v[9] = {GSB_PK(0,0,1,1), GSB_PK(1,1,1,0), GSB_PK(2,2,1,0), GSB_PK(3,3,0,1), GSB_PK(4,4,0,0),
+                                                    GSB_PK(5,5,0,0), GSB_PK(6,6,0,1), GSB_PK(7,7,0,0), GSB_PK(8,8,0,0)}; return v[k]; } };
+struct T3GenS2 : TermOps<T3GenS2> { enum { NIN = 9, NOUT = 4, NT = 9 };
+    static GSB_CX int pk(int k) { const int v[9] = {GSB_PK(0,0,0,0), GSB_PK(0,1,0,1), GSB_PK(1,2,0,0), GSB_PK(0,3,1,0), GSB_PK(0,4,1,1),
+                                                    GSB_PK(1,5,1,0), GSB_PK(2,6,0,0), GSB_PK(2,7,0,1), GSB_PK(3,8,0,0)}; return v[k]; } };
+// 2-D: symmetric D = {00,01,11}; general c = 2a+b.  Outputs g = 2*(a==1)+(b==1).
+struct T2SymS1 : TermOps<T2SymS1> { enum { NIN = 3, NOUT = 4, NT = 4 };
+    static GSB_CX int pk(int k) { const int v[4] = {GSB_PK(0,0,1,1), GSB_PK(1,1,1,0), GSB_PK(2,1,0,1), GSB_PK(3,2,0,0)}; return v[k]; } };
+struct T2GenS1 : TermOps<T2GenS1> { enum { NIN = 4, NOUT = 4, NT = 4 };
+    static GSB_CX int pk(int k) { const int v[4] = {GSB_PK(0,0,1,1), GSB_PK(1,1,1,0), GSB_PK(2,2,0,1), GSB_PK(3,3,0,0)}; return v[k]; } };
+// mass-type form: one scalar density, no derivatives, every direction
+struct TMass : TermOps<TMass> { enum { NIN = 1, NOUT = 1, NT = 1 };
+    static GSB_CX int pk(int) { return GSB_PK(0,0,0,0); } };
+
+// ------------------------------------------------------------------------------------
+// 1-D B-spline values + first derivatives on knot span s at u: Cox-de Boor triangle kept
+// in registers, derivative from the degree p-1 row (NURBS-book A2.3 with n=1).
+GSB_HD void bspline_ders(const double *kn, int p, int s, double u, double *val, double *der)
+{
+    double ndu[(GSB_MAXP + 1) * (GSB_MAXP + 1)], left[GSB_MAXP + 1], right[GSB_MAXP + 1];
+    const int p1 = p + 1;
+    ndu[0] = 1.0;
+    for (int j = 1; j <= p; ++j) {
+        left[j] = u - kn[s + 1 - j];
+        right[j] = kn[s + j] - u;
+        double saved = 0.0;
+        for (int r = 0; r < j; ++r) {
+            ndu[j * p1 + r] = right[r + 1] + left[j - r];
+            const double temp = ndu[r * p1 + j - 1] / ndu[j * p1 + r];
+            ndu[r * p1 + j] = saved + right[r + 1] * temp;
+            saved = left[j - r] * temp;
+        }
+        ndu[j * p1 + j] = saved;
+    }
+    for (int j = 0; j <= p; ++j) val[j] = ndu[j * p1 + p];
+    for (int r = 0; r <= p; ++r) {
+        double d = 0.0;
+        if (r >= 1) d = (1.0 / ndu[p * p1 + r - 1]) * ndu[(r - 1) * p1 + p - 1];
+        if (r <= p - 1) d += (-1.0 / ndu[p * p1 + r]) * ndu[r * p1 + p - 1];
+        der[r] = d * (double)p;
+    }
+}
+
+// One thread per 1-D quadrature point (e,t) of the solution basis: mapped Gauss node
+// (gsQuadRule.h:177-201), basis values/derivatives stored in SLOT order (slot = function
+// index mod (p+1)) so that the sweep kernels index their register accumulators statically.
+struct BasisTableArgs {
+    const double *knots; const int *span; const double *gnodes;
+    int p, nel, q;
+    double2 *tab;      // [nel*q][p+1]
+    double *upt;       // [nel*q] point coordinate
+    double *hpt;       // [nel*q] half element width h
+};
+GSB_GLOBAL void k_basis_table(const BasisTableArgs A)
+{
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= A.nel * A.q) return;
+    const int e = id / A.q, t = id - e * A.q, s = A.span[e], p1 = A.p + 1;
+    const double lower = A.knots[s], h = (A.knots[s + 1] - lower) / 2.0;
+    const double u = h * (A.gnodes[t] + 1.0) + lower;
+    double val[GSB_MAXP + 1], der[GSB_MAXP + 1];
+    bspline_ders(A.knots, A.p, s, u, val, der);
+    const int first = s - A.p;
+    for (int a = 0; a < p1; ++a) A.tab[(i64)id * p1 + (first + a) % p1] = make_double2(val[a], der[a]);
+    A.upt[id] = u;
+    A.hpt[id] = h;
+}
+
+// Geometry basis (its own, usually coarse, knot vector) at the same 1-D points.
+struct GeoTableArgs {
+    const double *knots; int nknots, p, npts;
+    const double *upt;
+    double2 *gtab;     // [npts][p+1] in local order
+    int *gfirst;       // [npts] first active geometry function
+};
+GSB_GLOBAL void k_geo_table(const GeoTableArgs A)
+{
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= A.npts) return;
+    const double u = A.upt[id];
+    int lo = A.p, hi = A.nknots - A.p - 1;   // span search: upper_bound - 1 (gsKnotVector.hpp:747-783)
+    if (u >= A.knots[hi]) { lo = hi - 1; while (A.knots[lo] == A.knots[lo + 1]) --lo; }
+    else while (hi - lo > 1) { const int mid = (lo + hi) / 2; if (A.knots[mid] <= u) lo = mid; else hi = mid; }
+    double val[GSB_MAXP + 1], der[GSB_MAXP + 1];
+    bspline_ders(A.knots, A.p, lo, u, val, der);
+    for (int a = 0; a <= A.p; ++a) A.gtab[(i64)id * (A.p + 1) + a] = make_double2(val[a], der[a]);
+    A.gfirst[id] = lo - A.p;
+}
+
+// ------------------------------------------------------------------------------------
+// Source-term stack machine (exprtk replacement).
+struct DevProgram { const int *ops; const double *consts; int nops; };
+GSB_HD double program_eval(const DevProgram &pr, double x, double y, double z)
+{
+    double st[GSB200_PROGRAM_MAX_STACK];
+    int sp = 0;
+    for (int i = 0; i < pr.nops; ++i) {
+        const int op = pr.ops[i];
+        switch (op) {
+        case GSB200_OP_CONST: st[sp++] = pr.consts[pr.ops[++i]]; break;
+        case GSB200_OP_X: st[sp++] = x; break;
+        case GSB200_OP_Y: st[sp++] = y; break;
+        case GSB200_OP_Z: st[sp++] = z; break;
+        case GSB200_OP_ADD: --sp; st[sp - 1] = st[sp - 1] + st[sp]; break;
+        case GSB200_OP_SUB: --sp; st[sp - 1] = st[sp - 1] - st[sp]; break;
+        case GSB200_OP_MUL: --sp; st[sp - 1] = st[sp - 1] * st[sp]; break;
+        case GSB200_OP_DIV: --sp; st[sp - 1] = st[sp - 1] / st[sp]; break;
+        case GSB200_OP_POW: --sp; st[sp - 1] = pow(st[sp - 1], st[sp]); break;
+        case GSB200_OP_NEG: st[sp - 1] = -st[sp - 1]; break;
+        case GSB200_OP_SIN: st[sp - 1] = sin(st[sp - 1]); break;
+        case GSB200_OP_COS: st[sp - 1] = cos(st[sp - 1]); break;
+        case GSB200_OP_TAN: st[sp - 1] = tan(st[sp - 1]); break;
+        case GSB200_OP_EXP: st[sp - 1] = exp(st[sp - 1]); break;
+        case GSB200_OP_LOG: st[sp - 1] = log(st[sp - 1]); break;
+        case GSB200_OP_SQRT: st[sp - 1] = sqrt(st[sp - 1]); break;
+        case GSB200_OP_ABS: st[sp - 1] = fabs(st[sp - 1]); break;
+        case GSB200_OP_TANH: st[sp - 1] = tanh(st[sp - 1]); break;
+        case GSB200_OP_SINH: st[sp - 1] = sinh(st[sp - 1]); break;
+        case GSB200_OP_COSH: st[sp - 1] = cosh(st[sp - 1]); break;
+        default: return NAN;
+        }
+    }
+    return st[0];
+}
+
+// ------------------------------------------------------------------------------------
+// K0: geometry map data at every quadrature point of the (chunk of the) patch:
+// x, Jacobian (gsGeometry.hpp:557-564, rational quotient rule gsRationalBasis.h:481-520),
+// measure and inverse (gsFunction.hpp:702-751), quadrature weight (gsQuadRule.h:190-200)
+// folded into the form's coefficient tensor; and the load density w|J|f(x).
+// Output layout: comp-major, then q0, q1, (q2) with the LAST direction fastest.
+struct GeoArgs {
+    int dim;
+    int qn[3], qoff[3];            // window of 1-D points handled (count, first)
+    const double2 *gtab[3]; const int *gfirst[3]; int pg1[3], ngeo[3];
+    const double *hpt[3]; const double *gw[3]; int q1d[3];   // h per point, Gauss weights, points/element
+    const double *coefs; const double *weights; i64 ngeo_total;
+    int form, brow, bcol; double lambda, mu;
+    int symD;                      // 1: write the 3/6 unique components, 0: all dim*dim
+    double *D; i64 dstride;        // may be NULL (load only)
+    double *F; i64 fstride; int nf; DevProgram prog[3];
+};
+template <int DIM>
+GSB_GLOBAL void k_geometry(const GeoArgs A)
+{
+    i64 total = 1;
+    for (int k = 0; k < DIM; ++k) total *= A.qn[k];
+    const i64 id = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= total) return;
+    int ql[DIM];   // global 1-D point index per direction
+    { i64 r = id; for (int k = DIM - 1; k >= 0; --k) { ql[k] = (int)(r % A.qn[k]) + A.qoff[k]; r /= A.qn[k]; } }
+    // tensor-product sum over the (pg+1)^d active control points
+    double W = 0.0, dW[DIM], xn[DIM], dxn[DIM][DIM];   // dxn[a][c] = d(x_c numerator)/d xi_a
+    for (int a = 0; a < DIM; ++a) { dW[a] = 0.0; xn[a] = 0.0; for (int c = 0; c < DIM; ++c) dxn[a][c] = 0.0; }
+    int cnt[DIM];
+    for (int k = 0; k < DIM; ++k) cnt[k] = 0;
+    for (;;) {
+        i64 idx = 0; double v = 1.0, dv[DIM];
+        for (int k = DIM - 1; k >= 0; --k) idx = idx * A.ngeo[k] + (A.gfirst[k][ql[k]] + cnt[k]);
+        double2 b[DIM];
+        for (int k = 0; k < DIM; ++k) { b[k] = A.gtab[k][(i64)ql[k] * A.pg1[k] + cnt[k]]; v *= b[k].x; }
+        for (int k = 0; k < DIM; ++k) { dv[k] = b[k].y; for (int i = 0; i < DIM; ++i) if (i != k) dv[k] *= b[i].x; }
+        const double wt = A.weights ? A.weights[idx] : 1.0;
+        W += wt * v;
+        for (int k = 0; k < DIM; ++k) dW[k] += wt * dv[k];
+        for (int c = 0; c < DIM; ++c) {
+            const double C = A.coefs[(i64)c * A.ngeo_total + idx];
+            xn[c] += wt * v * C;
+            for (int k = 0; k < DIM; ++k) dxn[k][c] += wt * dv[k] * C;
+        }
+        int k = 0;
+        while (k < DIM && ++cnt[k] >= A.pg1[k]) { cnt[k] = 0; ++k; }
+        if (k == DIM) break;
+    }
+    double x[3] = {0.0, 0.0, 0.0}, J[DIM][DIM];   // J[c][a] = d x_c / d xi_a
+    for (int c = 0; c < DIM; ++c) {
+        x[c] = xn[c] / W;
+        for (int a = 0; a < DIM; ++a) J[c][a] = (dxn[a][c] * W - xn[c] * dW[a]) / (W * W);
+    }
+    double Ji[DIM][DIM], det;   // Ji[a][c] = (J^-1)[a][c]
+    if (DIM == 2) {
+        det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+        Ji[0][0] = J[1][1] / det; Ji[0][1] = -J[0][1] / det; Ji[1][0] = -J[1][0] / det; Ji[1][1] = J[0][0] / det;
+    } else {
+        const int X = DIM == 3 ? 2 : 0;  // keeps the 2-D instantiation in bounds
+        const double c00 = J[1][1] * J[X][X] - J[1][X] * J[X][1], c01 = J[1][X] * J[X][0] - J[1][0] * J[X][X],
+                     c02 = J[1][0] * J[X][1] - J[1][1] * J[X][0];
+        det = J[0][0] * c00 + J[0][1] * c01 + J[0][X] * c02;
+        const double id_ = 1.0 / det;
+        Ji[0][0] = c00 * id_; Ji[0][1] = (J[0][X] * J[X][1] - J[0][1] * J[X][X]) * id_; Ji[0][X] = (J[0][1] * J[1][X] - J[0][X] * J[1][1]) * id_;
+        Ji[1][0] = c01 * id_; Ji[1][1] = (J[0][0] * J[X][X] - J[0][X] * J[X][0]) * id_; Ji[1][X] = (J[0][X] * J[1][0] - J[0][0] * J[1][X]) * id_;
+        Ji[X][0] = c02 * id_; Ji[X][1] = (J[0][1] * J[X][0] - J[0][0] * J[X][1]) * id_; Ji[X][X] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * id_;
+    }
+    // quadrature weight: hprod * (w_0 w_1 w_2), same association as the reference
+    double hprod = 1.0, wp = 1.0;
+    for (int k = 0; k < DIM; ++k) {
+        const double h = A.hpt[k][ql[k]];
+        hprod *= (h == 0.0 ? 0.5 : h);
+        const double g = A.gw[k][ql[k] % A.q1d[k]];
+        wp = (k == 0) ? g : wp * g;
+    }
+    const double weight = hprod * wp * fabs(det);
+    if (A.F) for (int c = 0; c < A.nf; ++c) A.F[c * A.fstride + id] = weight * program_eval(A.prog[c], x[0], x[1], x[2]);
+    if (!A.D) return;
+    if (A.form == GSB200_FORM_MASS) { A.D[id] = weight; return; }
+    double G[DIM][DIM];   // (J^-1 J^-T)_ab
+    for (int a = 0; a < DIM; ++a) for (int b = 0; b < DIM; ++b) {
+        double s = 0.0;
+        for (int c = 0; c < DIM; ++c) s += Ji[a][c] * Ji[b][c];
+        G[a][b] = s;
+    }
+    if (A.form == GSB200_FORM_POISSON) {
+        if (A.symD) { int c = 0; for (int a = 0; a < DIM; ++a) for (int b = a; b < DIM; ++b) A.D[(c++) * A.dstride + id] = weight * G[a][b]; }
+        else for (int a = 0; a < DIM; ++a) for (int b = 0; b < DIM; ++b) A.D[(a * DIM + b) * A.dstride + id] = weight * G[a][b];
+        return;
+    }
+    // elasticity block (row comp r = brow carried by the partner/test function, col comp c = bcol by the owner):
+    // E_{a'b'} = w ( lambda Ji[a'][r] Ji[b'][c] + mu ( Ji[a'][c] Ji[b'][r] + delta_rc G[a'][b'] ) ), a' on the row function.
+    // The sweeps put the FIRST tensor index on the owner, hence the transpose when storing.
+    const int r = A.brow, cc = A.bcol;
+    for (int a = 0; a < DIM; ++a) for (int b = 0; b < DIM; ++b) {
+        const double E = A.lambda * Ji[b][r] * Ji[a][cc] + A.mu * (Ji[b][cc] * Ji[a][r] + (r == cc ? G[b][a] : 0.0));
+        A.D[(a * DIM + b) * A.dstride + id] = weight * E;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Final-stage scatter context: where an owner/partner pair lands in the CSC arrays.
+struct FinalArgs {
+    int dim, L;                    // L = last (swept) direction
+    int n[3], p[3];                // functions / degree per direction
+    const int *plo[3]; const int *phi[3];   // co-occurring partner range per function, per direction
+    const int *dofmap; i64 nb;     // ncomp blocks of nb global indices
+    int brow, bcol;
+    const unsigned char *colflag;  // per (comp, local fn): 0 skip, 1 canonical, 2 generic
+    const unsigned *st; int nrun;  // canonical slot table: per (fn, run) start | mask<<16
+    const i64 *colptr; const int *inner; double *values;
+    double *rhs; const double *fixed; int nfree, nfixed, nrhs;
+};
+struct FinalCtx { i64 li_low, dj_low, nlow; int r_low, bit0; };
+
+GSB_HD bool final_init(const FinalArgs &F, i64 outer, i64 inner, FinalCtx &c)
+{
+    const int W0 = 2 * F.p[0] + 1;
+    const int i0 = (int)(inner / W0), d0 = (int)(inner % W0) - F.p[0];
+    const int j0 = i0 + d0;
+    if (j0 < F.plo[0][i0] || j0 > F.phi[0][i0]) return false;
+    c.bit0 = d0 + F.p[0];
+    if (F.dim == 2) { c.li_low = i0; c.dj_low = d0; c.nlow = F.n[0]; c.r_low = 0; return true; }
+    const int W1 = 2 * F.p[1] + 1;
+    const int i1 = (int)(outer / W1), d1 = (int)(outer % W1) - F.p[1];
+    const int j1 = i1 + d1;
+    if (j1 < F.plo[1][i1] || j1 > F.phi[1][i1]) return false;
+    c.li_low = (i64)i1 * F.n[0] + i0; c.dj_low = (i64)d1 * F.n[0] + d0; c.nlow = (i64)F.n[0] * F.n[1];
+    c.r_low = d1 + F.p[1];
+    return true;
+}
+
+GSB_HD void final_emit(const FinalArgs &F, const FinalCtx &c, int iL, int dL, double val)
+{
+    const i64 li = (i64)iL * c.nlow + c.li_low;
+    const i64 lj = li + (i64)dL * c.nlow + c.dj_low;
+    const int gi = F.dofmap[F.bcol * F.nb + li];
+    if (gi >= F.nfree) return;                       // eliminated column: nothing stored
+    const unsigned char flag = F.colflag[F.bcol * F.nb + li];
+    if (!flag) return;                               // column not owned by this rank
+    const int gj = F.dofmap[F.brow * F.nb + lj];
+    if (gj >= F.nfree) {                             // eliminated row: by symmetry of the form this is the
+        if (F.fixed)                                 // -K(i,j) g_j term of gsSparseSystem.h:1004
+            for (int r = 0; r < F.nrhs; ++r) atomic_add(F.rhs + (i64)r * F.nfree + gi, -val * F.fixed[(i64)r * F.nfixed + (gj - F.nfree)]);
+        return;
+    }
+    const i64 base = F.colptr[gi];
+    if (flag == 1) {
+        const int run = (F.dim == 2) ? (dL + F.p[1]) : ((dL + F.p[2]) * (2 * F.p[1] + 1) + c.r_low);
+        const unsigned w = F.st[li * F.nrun + run];
+        const unsigned mask = w >> 16;
+        const int rank = (int)(w & 0xffffu) + popc(mask & ((1u << c.bit0) - 1u));
+        F.values[base + rank] = val;
+    } else {
+        int lo = 0, hi = (int)(F.colptr[gi + 1] - base) - 1;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (F.inner[base + mid] < gj) lo = mid + 1; else hi = mid; }
+        atomic_add(F.values + base + lo, val);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// The sweep kernel (S1/S2/S3).  Thread = one column of the non-swept index space (lanes run
+// along the contiguous dimension of both input and output), blockIdx.y = group of owner
+// slots handled, blockIdx.z = sweep segment.
+struct SweepArgs {
+    const int *first, *nexit; const double2 *tab; int q, p;     // swept direction tables
+    const int *seg;                                            // [nseg][4] e_begin,e_end,x_min,x_max
+    const double *in; double *out;
+    i64 in_cs, in_es, in_ts, in_os, in_is; int e_in0;          // input strides: comp, element, point, outer, inner
+    i64 out_cs, out_ps, out_os, out_bs, out_is; int out_bq;    // output: comp, pair, outer, block, inner
+    i64 ncol; i64 ninner;
+    FinalArgs fin;
+};
+
+template <int P1, class T, int IS, bool FINAL>
+GSB_GLOBAL void k_sweep(const SweepArgs A)
+{
+    const i64 col = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= A.ncol) return;
+    const int grp = blockIdx.y, sg = blockIdx.z;
+    const int e_begin = A.seg[4 * sg + 0], e_end = A.seg[4 * sg + 1], x_min = A.seg[4 * sg + 2], x_max = A.seg[4 * sg + 3];
+    const i64 outer = col / A.ninner, inner = col - outer * A.ninner;
+    const double *inp = A.in + outer * A.in_os + inner * A.in_is;
+    FinalCtx fc;
+    i64 obase = 0;
+    if (FINAL) { if (!final_init(A.fin, outer, inner, fc)) return; }
+    else obase = outer * A.out_os + (inner / A.out_bq) * A.out_bs + (inner % A.out_bq) * A.out_is;
+    constexpr int NOUT = T::NOUT, NIN = T::NIN, NT = T::NT;
+    const int W = 2 * A.p + 1;
+
+    double acc[IS][P1][NOUT];
+#pragma unroll
+    for (int is = 0; is < IS; ++is)
+#pragma unroll
+        for (int js = 0; js < P1; ++js)
+#pragma unroll
+            for (int o = 0; o < NOUT; ++o) acc[is][js][o] = 0.0;
+
+    const int q = A.q;
+    for (int e = e_begin; e < e_end; ++e) {
+        const int f0 = A.first[e];
+        const int ph = f0 % P1;
+        const double *ine = inp + (i64)(e - A.e_in0) * A.in_es;
+        const double2 *tbe = A.tab + (i64)e * q * P1;
+        for (int t = 0; t < q; ++t) {
+            double v[NIN];
+#pragma unroll
+            for (int c = 0; c < NIN; ++c) v[c] = ld_keep(ine + c * A.in_cs + t * A.in_ts);
+            const double2 *tb = tbe + t * P1;
+            double2 bj[P1];
+#pragma unroll
+            for (int js = 0; js < P1; ++js) bj[js] = ld_keep2(tb + js);
+#pragma unroll
+            for (int is = 0; is < IS; ++is) {
+                double2 bi;
+                if (IS == P1) bi = bj[is]; else bi = ld_keep2(tb + grp * IS + is);
+                // z[o][b] = sum over terms with that (o,b) of B^(a)_owner * in_c
+                double z[NOUT][2];
+                static_for<0, NT>([&](auto kc) {
+                    constexpr int k = decltype(kc)::value;
+                    const double bo = T::a(k) ? bi.y : bi.x;
+                    if constexpr (T::first(k)) z[T::o(k)][T::b(k)] = bo * v[T::c(k)];
+                    else z[T::o(k)][T::b(k)] = fma(bo, v[T::c(k)], z[T::o(k)][T::b(k)]);
+                });
+#pragma unroll
+                for (int js = 0; js < P1; ++js)
+                    static_for<0, NOUT>([&](auto oc) {
+                        constexpr int o = decltype(oc)::value;
+                        if constexpr (T::has(o, 0)) acc[is][js][o] = fma(bj[js].x, z[o][0], acc[is][js][o]);
+                        if constexpr (T::has(o, 1)) acc[is][js][o] = fma(bj[js].y, z[o][1], acc[is][js][o]);
+                    });
+            }
+        }
+        // functions leaving the span window after this element complete their pairs
+        const int nx = A.nexit[e];
+        for (int k = 0; k < nx; ++k) {
+            const int x = f0 + k;
+            if (x >= x_max) break;
+            const bool wr = (x >= x_min);
+            const int sx = (ph + k) % P1;
+#pragma unroll
+            for (int is = 0; is < IS; ++is) {
+                const int so = grp * IS + is;
+                const int fi = f0 + ((so - ph + P1) % P1);
+                if (fi == x) {
+#pragma unroll
+                    for (int js = 0; js < P1; ++js) {
+                        const int fj = f0 + ((js - ph + P1) % P1);
+                        if (wr && fj >= x) {
+                            if (FINAL) final_emit(A.fin, fc, fi, fj - fi, acc[is][js][0]);
+                            else {
+                                const i64 o0 = ((i64)fi * W + (fj - fi + A.p)) * A.out_ps + obase;
+#pragma unroll
+                                for (int o = 0; o < NOUT; ++o) A.out[o * A.out_cs + o0] = acc[is][js][o];
+                            }
+                        }
+#pragma unroll
+                        for (int o = 0; o < NOUT; ++o) acc[is][js][o] = 0.0;
+                    }
+                } else if (fi > x) {
+#pragma unroll
+                    for (int js = 0; js < P1; ++js)
+                        if (js == sx) {
+                            if (wr) {
+                                if (FINAL) final_emit(A.fin, fc, fi, x - fi, acc[is][js][0]);
+                                else {
+                                    const i64 o0 = ((i64)fi * W + (x - fi + A.p)) * A.out_ps + obase;
+#pragma unroll
+                                    for (int o = 0; o < NOUT; ++o) A.out[o * A.out_cs + o0] = acc[is][js][o];
+                                }
+                            }
+#pragma unroll
+                            for (int o = 0; o < NOUT; ++o) acc[is][js][o] = 0.0;
+                        }
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// K3: load vector, one direction at a time: out[i][col] = sum_{q in supp(i)} B_i(q) in[q][col].
+struct VSweepArgs {
+    const int *ffirst, *flast;    // per function: first/last element of its support
+    const int *first; const double2 *tab; int q, p1;
+    int x_lo, x_hi;               // functions produced
+    int e_in0;                    // first element present in `in`
+    const double *in; i64 in_qs, in_os, in_is;    // point stride, column strides
+    double *out; i64 out_fs, out_os, out_is;      // function stride, column strides
+    i64 ncol, ninner;
+    // final: scatter into rhs through the dof map
+    int final_; int n0, n1, dimlow; const int *dofmap; double *rhs; int nfree;
+};
+GSB_GLOBAL void k_vsweep(const VSweepArgs A)
+{
+    const i64 col = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= A.ncol) return;
+    const int x = A.x_lo + blockIdx.y;
+    if (x >= A.x_hi) return;
+    const i64 outer = col / A.ninner, inner = col - outer * A.ninner;
+    const double *inp = A.in + outer * A.in_os + inner * A.in_is;
+    double s = 0.0;
+    const int slot = x % A.p1;
+    for (int e = A.ffirst[x]; e <= A.flast[x]; ++e)
+        for (int t = 0; t < A.q; ++t)
+            s = fma(A.tab[((i64)e * A.q + t) * A.p1 + slot].x, inp[(i64)((e - A.e_in0) * A.q + t) * A.in_qs], s);
+    if (!A.final_) { A.out[(i64)x * A.out_fs + outer * A.out_os + inner * A.out_is] = s; return; }
+    // column = (i1, i0) [3-D] or i0 [2-D]; local index = (x*n1 + i1)*n0 + i0
+    const i64 li = (A.dimlow == 2) ? ((i64)x * A.n1 + outer) * A.n0 + inner : (i64)x * A.n0 + inner;
+    const int g = A.dofmap[li];
+    if (g < A.nfree) atomic_add(A.rhs + g, s);
+}
+
+// ------------------------------------------------------------------------------------
+// K1: sparsity pattern.  Column gi of the CSC matrix = union over the (patch, local fn)
+// pre-images of gi of the free members of the tensor-product stencil of that function.
+struct PatArgs {
+    int dim, ncomp;
+    int n[3], p[3];
+    const int *plo[3]; const int *phi[3];
+    const int *dofmap; i64 nb;
+    int nfree;
+    int own_lo, own_hi;            // owner range in the last direction (multi-rank slabs)
+    const int *npre;               // per global dof: number of pre-images
+    unsigned long long *len;       // per global column: entry count (upper bound for coupled columns)
+    const i64 *colptr; int *inner; int *cursor;
+    unsigned char *colflag; unsigned *st; int nrun;
+    unsigned char *gneed;          // per global column: 1 sort, 2 sort+unique
+};
+
+GSB_HD void pat_decode(const PatArgs &A, i64 li, int *i)
+{
+    for (int k = 0; k < A.dim; ++k) { i[k] = (int)(li % A.n[k]); li /= A.n[k]; }
+}
+
+GSB_GLOBAL void k_pat_preimages(const int *dofmap, i64 n, int nfree, int *npre)
+{
+    const i64 id = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n) return;
+    const int g = dofmap[id];
+    if (g < nfree) atomic_add(npre + g, 1);
+}
+
+// pass 0: count; pass 1: fill
+template <int PASS>
+GSB_GLOBAL void k_pattern(const PatArgs A)
+{
+    const i64 id = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= A.nb * A.ncomp) return;
+    const int cc = (int)(id / A.nb);
+    const i64 li = id - (i64)cc * A.nb;
+    const int gi = A.dofmap[id];
+    if (PASS == 1) A.colflag[id] = 0;
+    if (gi >= A.nfree) return;
+    int i[3] = {0, 0, 0};
+    pat_decode(A, li, i);
+    const bool multi = A.npre[gi] > 1;
+    // columns shared by several patches are patterned on every rank (their values are
+    // all-reduced afterwards); all others only by the rank that owns the function
+    if (!multi && (i[A.dim - 1] < A.own_lo || i[A.dim - 1] >= A.own_hi)) return;
+    int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+    for (int k = 0; k < A.dim; ++k) { lo[k] = A.plo[k][i[k]]; hi[k] = A.phi[k][i[k]]; }
+    if (PASS == 0) {
+        unsigned long long cnt = 0;
+        for (int cr = 0; cr < A.ncomp; ++cr)
+            for (int j2 = lo[2]; j2 <= hi[2]; ++j2) for (int j1 = lo[1]; j1 <= hi[1]; ++j1) for (int j0 = lo[0]; j0 <= hi[0]; ++j0) {
+                const i64 lj = ((i64)j2 * A.n[1] + j1) * A.n[0] + j0;
+                if (A.dofmap[(i64)cr * A.nb + lj] < A.nfree) ++cnt;
+            }
+        if (multi) {
+#ifdef GSB200_EMULATE
+            A.len[gi] += cnt;
+#else
+            atomicAdd(A.len + gi, cnt);
+#endif
+        } else A.len[gi] = cnt;
+        return;
+    }
+    // fill
+    const i64 base = A.colptr[gi];
+    if (multi) {
+        // coupled column: append at an atomic cursor, sorted + deduplicated afterwards
+        int cnt = 0;
+        for (int cr = 0; cr < A.ncomp; ++cr)
+            for (int j2 = lo[2]; j2 <= hi[2]; ++j2) for (int j1 = lo[1]; j1 <= hi[1]; ++j1) for (int j0 = lo[0]; j0 <= hi[0]; ++j0)
+                if (A.dofmap[(i64)cr * A.nb + ((i64)j2 * A.n[1] + j1) * A.n[0] + j0] < A.nfree) ++cnt;
+        i64 pos = base + atomic_add(A.cursor + gi, cnt);
+        for (int cr = 0; cr < A.ncomp; ++cr)
+            for (int j2 = lo[2]; j2 <= hi[2]; ++j2) for (int j1 = lo[1]; j1 <= hi[1]; ++j1) for (int j0 = lo[0]; j0 <= hi[0]; ++j0) {
+                const int gj = A.dofmap[(i64)cr * A.nb + ((i64)j2 * A.n[1] + j1) * A.n[0] + j0];
+                if (gj < A.nfree) A.inner[pos++] = gj;
+            }
+        A.colflag[id] = 2; A.gneed[gi] = 2;
+        return;
+    }
+    i64 pos = base;
+    int prev = -1; bool mono = true;
+    for (int cr = 0; cr < A.ncomp; ++cr)
+        for (int j2 = lo[2]; j2 <= hi[2]; ++j2) for (int j1 = lo[1]; j1 <= hi[1]; ++j1) {
+            unsigned mask = 0; const int start = (int)(pos - base);
+            for (int j0 = lo[0]; j0 <= hi[0]; ++j0) {
+                const int gj = A.dofmap[(i64)cr * A.nb + ((i64)j2 * A.n[1] + j1) * A.n[0] + j0];
+                if (gj < A.nfree) {
+                    A.inner[pos++] = gj;
+                    if (gj <= prev) mono = false;
+                    prev = gj;
+                    mask |= 1u << (j0 - i[0] + A.p[0]);
+                }
+            }
+            if (A.ncomp == 1) {
+                const int run = (A.dim == 2) ? (j1 - i[1] + A.p[1]) : ((j2 - i[2] + A.p[2]) * (2 * A.p[1] + 1) + (j1 - i[1] + A.p[1]));
+                A.st[li * A.nrun + run] = (unsigned)start | (mask << 16);
+            }
+        }
+    if (mono && A.ncomp == 1) A.colflag[id] = 1;
+    else { A.colflag[id] = 2; if (!mono) A.gneed[gi] = 1; }
+}
+
+// sort (and for coupled columns deduplicate) the row indices of the flagged columns
+GSB_GLOBAL void k_pat_sort(int ncols, const unsigned char *gneed, const i64 *colptr, int *inner, unsigned long long *len)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ncols || !gneed[g]) return;
+    int *a = inner + colptr[g];
+    const int n = (int)len[g];
+    for (int i = 1; i < n; ++i) { const int v = a[i]; int j = i - 1; while (j >= 0 && a[j] > v) { a[j + 1] = a[j]; --j; } a[j + 1] = v; }
+    if (gneed[g] == 2) {
+        int m = 0;
+        for (int i = 0; i < n; ++i) if (i == 0 || a[i] != a[m - 1]) a[m++] = a[i];
+        len[g] = (unsigned long long)m;
+    }
+}
+
+GSB_GLOBAL void k_pat_compact(int ncols, const i64 *oldptr, const i64 *newptr, const int *oldinner, int *newinner)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ncols) return;
+    const i64 n = newptr[g + 1] - newptr[g];
+    for (i64 k = 0; k < n; ++k) newinner[newptr[g] + k] = oldinner[oldptr[g] + k];
+}
+
+// single-thread exclusive scan used by the interpreter build; the product build uses cub
+GSB_GLOBAL void k_scan_serial(const unsigned long long *len, i64 *ptr, int n)
+{
+    if (blockIdx.x || threadIdx.x) return;
+    i64 s = 0;
+    for (int i = 0; i < n; ++i) { ptr[i] = s; s += (i64)len[i]; }
+    ptr[n] = s;
+}
+
+// ------------------------------------------------------------------------------------
+// Consumer kernels: y = A x on the CSC arrays read as CSR of the (symmetric) matrix.
+GSB_GLOBAL void k_spmv(int n, const i64 *ptr, const int *idx, const double *val, const double *x, double *y)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    double s = 0.0;
+    for (i64 k = ptr[r]; k < ptr[r + 1]; ++k) s = fma(val[k], x[idx[k]], s);
+    y[r] = s;
+}
+GSB_GLOBAL void k_diag(int n, const i64 *ptr, const int *idx, const double *val, double *d)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    double s = 1.0;
+    for (i64 k = ptr[r]; k < ptr[r + 1]; ++k) if (idx[k] == r) s = val[k];
+    d[r] = s;
+}
+GSB_GLOBAL void k_dot(int n, const double *a, const double *b, double *out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double s = 0.0;
+    for (int k = i; k < n; k += gridDim.x * blockDim.x) s = fma(a[k], b[k], s);
+    if (s != 0.0) atomic_add(out, s);
+}
+// z = a + alpha * b  (element-wise)  and  z = a / d
+GSB_GLOBAL void k_axpy(int n, const double *a, double alpha, const double *b, double *z)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) z[i] = fma(alpha, b[i], a[i]);
+}
+GSB_GLOBAL void k_div(int n, const double *a, const double *d, double *z)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) z[i] = a[i] / d[i];
+}
+
+} // namespace gsb
