@@ -1,0 +1,142 @@
+"""Python face of the device assembler: same verbs as the reference's assembler objects
+(gsAssembler.h:415,614,618 — assemble(), matrix(), rhs(), numDofs()), driving the C ABI.
+
+Every call goes through gismo_b200/csrc/libgsb200.so; if that extension or a CUDA device is
+missing the calls raise (there is no CPU path in the package).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import capi
+from .capi import Problem, Timings, DeviceView, check
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+
+class DeviceAssembler:
+    """Handle on a device-resident problem (gsb200_create ... gsb200_destroy)."""
+
+    def __init__(self, problem: Problem, device: int = 0, stream: Optional[int] = None,
+                 workspace_limit: int = 0):
+        self.lib = capi.load_library()
+        self.problem = problem
+        self._h = C.c_void_p()
+        check(self.lib.gsb200_create(C.byref(problem.struct), device, C.byref(self._h)))
+        if stream is not None:
+            check(self.lib.gsb200_set_stream(self._h, C.c_void_p(stream)))
+        if workspace_limit:
+            check(self.lib.gsb200_set_workspace_limit(self._h, workspace_limit))
+        self._pattern = False
+
+    def close(self):
+        if self._h:
+            self.lib.gsb200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- reference-facing verbs -------------------------------------------------------
+    def numDofs(self) -> int:
+        return self.problem.nfree
+
+    def buildPattern(self) -> int:
+        check(self.lib.gsb200_build_pattern(self._h))
+        self._pattern = True
+        return self.nnz()
+
+    def assemble(self, sync: bool = True) -> None:
+        if not self._pattern:
+            self.buildPattern()
+        check(self.lib.gsb200_assemble(self._h))
+        if sync:
+            self.synchronize()
+
+    def synchronize(self) -> None:
+        check(self.lib.gsb200_synchronize(self._h))
+
+    def nnz(self) -> int:
+        n = C.c_int64(0)
+        check(self.lib.gsb200_nnz(self._h, C.byref(n)))
+        return n.value
+
+    def matrix(self) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """(outer, inner, values) exactly as Eigen's compressed gsSparseMatrix stores them."""
+        nnz = self.nnz()
+        outer = np.zeros(self.problem.nfree + 1, np.int32)
+        inner = np.zeros(nnz, np.int32)
+        values = np.zeros(nnz, np.float64)
+        check(self.lib.gsb200_download_csc(self._h, outer.ctypes.data_as(_ip), inner.ctypes.data_as(_ip),
+                                           values.ctypes.data_as(_dp)))
+        return outer, inner, values
+
+    def matrix_into(self, outer: np.ndarray, inner: np.ndarray, values: np.ndarray) -> None:
+        check(self.lib.gsb200_download_csc(self._h, outer.ctypes.data_as(_ip), inner.ctypes.data_as(_ip),
+                                           values.ctypes.data_as(_dp)))
+
+    def rhs(self) -> np.ndarray:
+        r = np.zeros((self.problem.nfree, self.problem.nrhs), np.float64, order="F")
+        check(self.lib.gsb200_download_rhs(self._h, r.ctypes.data_as(_dp)))
+        return r
+
+    def scipy_matrix(self):
+        import scipy.sparse as sp
+        o, i, v = self.matrix()
+        n = self.problem.nfree
+        return sp.csc_matrix((v, i, o), shape=(n, n))
+
+    # --- device-side access -----------------------------------------------------------
+    def device_view(self) -> DeviceView:
+        v = DeviceView()
+        check(self.lib.gsb200_device_view_get(self._h, C.byref(v)))
+        return v
+
+    def timings(self) -> Timings:
+        t = Timings()
+        check(self.lib.gsb200_timings_get(self._h, C.byref(t)))
+        return t
+
+    # --- consumer -------------------------------------------------------
+    def spmv(self, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.zeros_like(x)
+        check(self.lib.gsb200_spmv_host(self._h, x.ctypes.data_as(_dp), y.ctypes.data_as(_dp)))
+        return y
+
+    def cg(self, b: np.ndarray, max_iter: int = 1000, tol: float = 1e-10):
+        b = np.ascontiguousarray(b, dtype=np.float64).ravel()
+        x = np.zeros_like(b)
+        it, res = C.c_int(0), C.c_double(0)
+        check(self.lib.gsb200_cg_host(self._h, b.ctypes.data_as(_dp), x.ctypes.data_as(_dp), max_iter, tol,
+                                      C.byref(it), C.byref(res)))
+        return x, it.value, res.value
+
+
+def assemble_host(problem: Problem, device: int = 0):
+    """gsb200_assemble_host: host buffers in, host buffers out — what the C++ shim
+    gsPoissonAssemblerB200::assemble() calls."""
+    lib = capi.load_library()
+    nnz = C.c_int64(0)
+    check(lib.gsb200_assemble_host(C.byref(problem.struct), device, C.byref(nnz), None, None, None, None))
+    outer = np.zeros(problem.nfree + 1, np.int32)
+    inner = np.zeros(nnz.value, np.int32)
+    values = np.zeros(nnz.value)
+    rhs = np.zeros((problem.nfree, problem.nrhs), order="F")
+    check(lib.gsb200_assemble_host(C.byref(problem.struct), device, C.byref(nnz), outer.ctypes.data_as(_ip),
+                                   inner.ctypes.data_as(_ip), values.ctypes.data_as(_dp), rhs.ctypes.data_as(_dp)))
+    return outer, inner, values, rhs
+
+
+def measure_peaks(device: int = 0):
+    lib = capi.load_library()
+    a, b, c = C.c_double(0), C.c_double(0), C.c_double(0)
+    check(lib.gsb200_measure_peaks(device, C.byref(a), C.byref(b), C.byref(c)))
+    return {"fp64_tflops": a.value, "dmma_tflops": b.value, "hbm_gbs": c.value}

@@ -313,7 +313,7 @@ struct FinalArgs {
 };
 struct FinalCtx { i64 li_low, dj_low, nlow; int r_low, bit0; };
 
-GSB_HD bool final_init(const FinalArgs &F, i64 outer, i64 inner, FinalCtx &c)
+GSB_DEVICE bool final_init(const FinalArgs &F, i64 outer, i64 inner, FinalCtx &c)
 {
     const int W0 = 2 * F.p[0] + 1;
     const int i0 = (int)(inner / W0), d0 = (int)(inner % W0) - F.p[0];
@@ -330,7 +330,7 @@ GSB_HD bool final_init(const FinalArgs &F, i64 outer, i64 inner, FinalCtx &c)
     return true;
 }
 
-GSB_HD void final_emit(const FinalArgs &F, const FinalCtx &c, int iL, int dL, double val)
+GSB_DEVICE void final_emit(const FinalArgs &F, const FinalCtx &c, int iL, int dL, double val)
 {
     const i64 li = (i64)iL * c.nlow + c.li_low;
     const i64 lj = li + (i64)dL * c.nlow + c.dj_low;
@@ -528,7 +528,7 @@ struct PatArgs {
     unsigned char *gneed;          // per global column: 1 sort, 2 sort+unique
 };
 
-GSB_HD void pat_decode(const PatArgs &A, i64 li, int *i)
+GSB_DEVICE void pat_decode(const PatArgs &A, i64 li, int *i)
 {
     for (int k = 0; k < A.dim; ++k) { i[k] = (int)(li % A.n[k]); li /= A.n[k]; }
 }
