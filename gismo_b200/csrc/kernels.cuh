@@ -435,13 +435,13 @@ GSB_GLOBAL void k_sweep(const SweepArgs A)
         const int nx = A.nexit[e];
         for (int k = 0; k < nx; ++k) {
             const int x = f0 + k;
-            if (x >= x_max) break;
-            const bool wr = (x >= x_min);
+            if (x >= x_max) break;                 // later exits only involve owners >= x_max
             const int sx = (ph + k) % P1;
 #pragma unroll
             for (int is = 0; is < IS; ++is) {
                 const int so = grp * IS + is;
                 const int fi = f0 + ((so - ph + P1) % P1);
+                const bool wr = (fi >= x_min) && (fi < x_max);   // a pair is emitted by the segment owning its OWNER
                 if (fi == x) {
 #pragma unroll
                     for (int js = 0; js < P1; ++js) {

@@ -1,0 +1,95 @@
+"""Regenerates tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref/libgsref.so, built
+from /root/reference by oracle/Makefile).  Run here (build container) only:
+
+    python tests/golden/make_golden.py
+
+Each fixture stores the flattened inputs (what gsB200Flatten.h extracts) and the reference's own
+assembled CSC matrix / right-hand side, so that the GPU box — which has no /root/reference —
+can check both the C restatement and the CUDA path against the real thing.  Large cases store
+only fingerprints (nnz, sum K_ij, ||rhs||_2, probes K*x for a fixed x).
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import refutil as R  # noqa: E402
+
+PI2 = "2*pi^2*sin(pi*x)*sin(pi*y)"
+PI3 = "3*pi^2*sin(pi*x)*sin(pi*y)*sin(pi*z)"
+
+FULL = {
+    # name: reference configuration (see oracle/ref_driver.cpp)
+    "sq_p2_m8_visitor": dict(dim=2, degree=2, nelem=8, geometry=0, rhs=[PI2], dir_values=100),
+    "sq_p2_m8_expr_l2proj": dict(dim=2, degree=2, nelem=8, geometry=0, path=1, rhs=[PI2], dirichlet=["x+y"], dir_values=102),
+    "cube_p3_curved_m4": dict(dim=3, degree=3, nelem=4, geometry=1, rhs=[PI3], dirichlet=["x+y*z"]),
+    "cube_p2_m5": dict(dim=3, degree=2, nelem=5, geometry=0, rhs=[PI3], dir_values=100),
+    "cube_p1_m5": dict(dim=3, degree=1, nelem=5, geometry=0, rhs=[PI3], dirichlet=["x+y*z"]),
+    "cube_p4_curved_m2": dict(dim=3, degree=4, nelem=2, geometry=1, rhs=[PI3], dirichlet=["x*y"]),
+    "annulus_nurbs_p3_m6": dict(dim=2, degree=3, nelem=6, geometry=2, rhs=["sin(x)*y"], dirichlet=["x*y"]),
+    "grid2x2_p2_m4": dict(dim=2, degree=2, nelem=4, geometry=3, grid=(2, 2, 1), rhs=[PI2], dirichlet=["x*y"]),
+    "grid2x2x2_p2_m3": dict(dim=3, degree=2, nelem=3, geometry=3, grid=(2, 2, 2), rhs=[PI3], dirichlet=["x"]),
+    "yeti_mp2_p2_m2": dict(dim=2, degree=2, nelem=2, geometry=4, xml="domain2d/yeti_mp2.xml", rhs=["1"]),
+    "elasticity_2cubes_p2": dict(dim=3, degree=2, nelem=2, geometry=3, grid=(2, 1, 1), path=1, form=1, lam=2.0, mu=1.5,
+                                 rhs=["x", "y*z", "1"], dirichlet=["0.1*x", "0", "y"], dir_values=101),
+    "elasticity_sq_p2": dict(dim=2, degree=2, nelem=4, geometry=1, path=1, form=1, lam=80000.0, mu=80000.0,
+                             rhs=["1", "x"], dirichlet=["0", "0.01*x"], dir_values=101),
+}
+FINGERPRINT = {
+    "cube_p3_m16": dict(dim=3, degree=3, nelem=16, geometry=0, rhs=[PI3], dir_values=100, threads=8),
+    "sq_p2_m64": dict(dim=2, degree=2, nelem=64, geometry=0, rhs=[PI2], dir_values=100, threads=8),
+    "cube_p4_m8": dict(dim=3, degree=4, nelem=8, geometry=0, rhs=[PI3], dir_values=100, threads=8),
+    "cube_p2_m16_expr": dict(dim=3, degree=2, nelem=16, geometry=0, path=1, rhs=[PI3], dirichlet=["x*y*z"], dir_values=101, threads=1),
+}
+
+
+def pack_inputs(ref):
+    d = {"nfree": ref.nfree, "nfixed": ref.nfixed, "ncomp": ref.ncomp, "dim": ref.dim, "form": ref.form,
+         "coef": np.asarray(ref.coef), "quA": ref.quA, "quB": ref.quB, "npatches": len(ref.patches),
+         "rhs_text": np.asarray(ref.rhs_text), "fixed": ref.fixed}
+    for k, p in enumerate(ref.patches):
+        d[f"p{k}_sdeg"] = np.asarray(p.space_degree)
+        d[f"p{k}_gdeg"] = np.asarray(p.geo_degree)
+        for i in range(p.dim):
+            d[f"p{k}_sk{i}"] = p.space_knots[i]
+            d[f"p{k}_gk{i}"] = p.geo_knots[i]
+        d[f"p{k}_coefs"] = p.geo_coefs
+        d[f"p{k}_dofmap"] = p.dofmap
+        if p.geo_weights is not None:
+            d[f"p{k}_weights"] = p.geo_weights
+    return d
+
+
+def probe_vector(n):
+    return np.cos(0.37 * np.arange(n) + 0.11)
+
+
+def main():
+    for name, cfg in FULL.items():
+        ref = R.ref_run(**cfg)
+        d = pack_inputs(ref)
+        d.update(outer=ref.outer, inner=ref.inner, values=ref.values, rhs=ref.rhs, kind="full", config=repr(cfg))
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
+        print(name, "N", ref.nfree, "nnz", len(ref.values))
+    for name, cfg in FINGERPRINT.items():
+        ref = R.ref_run(**cfg)
+        d = pack_inputs(ref)
+        import scipy.sparse as sp
+        K = sp.csc_matrix((ref.values, ref.inner, ref.outer), shape=(ref.nfree, ref.nfree))
+        x = probe_vector(ref.nfree)
+        d.update(kind="fingerprint", config=repr(cfg), nnz=len(ref.values), sumK=ref.values.sum(),
+                 rhs_norm=np.linalg.norm(ref.rhs), Kx=K @ x, maxK=np.abs(ref.values).max(), rhs=ref.rhs,
+                 outer=ref.outer, inner_checksum=np.int64(ref.inner.astype(np.int64).sum()),
+                 diag=K.diagonal())
+        # dof maps of fingerprint cases are large; they are rebuilt by gismo_b200.host in the tests
+        for k in list(d):
+            if k.endswith("_dofmap"):
+                del d[k]
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
+        print(name, "N", ref.nfree, "nnz", len(ref.values), repr(ref.values.sum()), repr(np.linalg.norm(ref.rhs)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,79 @@
+"""Load tests/golden/*.npz (made by make_golden.py from the reference) into C-ABI problems."""
+import glob
+import os
+
+import numpy as np
+
+from gismo_b200.capi import PatchData, Problem
+from gismo_b200 import host
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = os.path.join(HERE, "golden")
+
+
+def names(kind):
+    out = []
+    for f in sorted(glob.glob(os.path.join(GOLDEN, "*.npz"))):
+        with np.load(f) as z:
+            if str(z["kind"]) == kind:
+                out.append(os.path.splitext(os.path.basename(f))[0])
+    return out
+
+
+def load(name, compile_fn, with_rhs=True):
+    """-> (Problem, dict of expected arrays)."""
+    z = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    dim, ncomp, npatches = int(z["dim"]), int(z["ncomp"]), int(z["npatches"])
+    patches = []
+    for k in range(npatches):
+        sdeg = [int(v) for v in z[f"p{k}_sdeg"]]
+        sk = [z[f"p{k}_sk{i}"] for i in range(dim)]
+        if f"p{k}_dofmap" in z:
+            dofmap = z[f"p{k}_dofmap"]
+        else:  # fingerprint cases: single patch, all sides eliminated -> rebuilt by the host builder
+            nfun = [len(sk[i]) - sdeg[i] - 1 for i in range(dim)]
+            m = host.DofMapper([int(np.prod(nfun))])
+            m.eliminate(0, host.boundary_indices(nfun))
+            m.finalize()
+            dofmap = m.patch_map(0)
+        patches.append(PatchData(sdeg, sk, [int(v) for v in z[f"p{k}_gdeg"]], [z[f"p{k}_gk{i}"] for i in range(dim)],
+                                 z[f"p{k}_coefs"], dofmap, z.get(f"p{k}_weights")))
+    progs = [compile_fn(str(t)) for t in z["rhs_text"]] if with_rhs else None
+    nfixed = int(z["nfixed"])
+    pb = Problem(patches, int(z["nfree"]), nfixed, form=int(z["form"]), ncomp=ncomp,
+                 fixed=z["fixed"] if nfixed else None, nrhs=1, coef=tuple(z["coef"]), quA=float(z["quA"]),
+                 quB=int(z["quB"]), rhs_programs=progs)
+    return pb, z
+
+
+def probe_vector(n):
+    return np.cos(0.37 * np.arange(n) + 0.11)
+
+
+def check_against(result, z, tol):
+    """result = (outer, inner, values, rhs) from any implementation; z = golden dict."""
+    import scipy.sparse as sp
+    outer, inner, values, rhs = result[:4]
+    if str(z["kind"]) == "full":
+        assert np.array_equal(outer, z["outer"]), "outer index array differs from the reference"
+        assert np.array_equal(inner, z["inner"]), "inner index array differs from the reference"
+        scale = np.abs(z["values"]).max()
+        ev = np.abs(values - z["values"]).max() / scale
+        rs = max(np.abs(z["rhs"]).max(), 1e-300)
+        er = np.abs(rhs - z["rhs"]).max() / rs
+        assert ev <= tol, f"matrix values differ: {ev:.3e}"
+        assert er <= tol, f"rhs differs: {er:.3e}"
+        return ev, er
+    n = int(z["nfree"])
+    assert len(values) == int(z["nnz"])
+    assert np.array_equal(outer, z["outer"])
+    assert int(inner.astype(np.int64).sum()) == int(z["inner_checksum"])
+    K = sp.csc_matrix((values, inner, outer), shape=(n, n))
+    scale = float(z["maxK"])
+    e1 = np.abs(K @ probe_vector(n) - z["Kx"]).max() / (scale * 50)
+    e2 = np.abs(K.diagonal() - z["diag"]).max() / scale
+    e3 = abs(values.sum() - float(z["sumK"])) / (scale * np.sqrt(len(values)))
+    er = np.abs(rhs - z["rhs"]).max() / np.abs(z["rhs"]).max()
+    assert max(e1, e2, e3) <= tol, f"fingerprints differ: Kx {e1:.2e} diag {e2:.2e} sum {e3:.2e}"
+    assert er <= tol, f"rhs differs: {er:.3e}"
+    return max(e1, e2, e3), er

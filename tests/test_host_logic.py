@@ -1,0 +1,105 @@
+"""Host side: C-ABI library surface, expression compiler, problem builders (no GPU needed)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import goldenutil as G
+import refutil as R
+import gismo_b200 as g
+from gismo_b200 import capi, host
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "gsb200.h")).read()
+    declared = set(re.findall(r"\b(gsb200_[a-z0-9_]+)\s*\(", hdr))
+    lib = capi.load_library()
+    for sym in sorted(declared):
+        assert hasattr(lib, sym), f"{sym} declared in include/gsb200.h but not exported"
+    assert lib.gsb200_abi_version() == capi.ABI_VERSION
+
+
+def test_struct_layout_matches_header():
+    # sizes computed by the C compiler for the same header
+    src = '#include "gsb200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n",sizeof(gsb200_basis),sizeof(gsb200_patch),sizeof(gsb200_program),sizeof(gsb200_problem),sizeof(gsb200_device_view),sizeof(gsb200_timings));}'
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "s.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "s.c"), "-o", os.path.join(d, "s")])
+        sizes = [int(v) for v in subprocess.check_output([os.path.join(d, "s")]).split()]
+    assert sizes == [C.sizeof(capi.Basis), C.sizeof(capi.Patch), C.sizeof(capi.Program), C.sizeof(capi.ProblemStruct),
+                     C.sizeof(capi.DeviceView), C.sizeof(capi.Timings)]
+
+
+def test_no_cpu_fallback_without_device():
+    lib = capi.load_library()
+    n = C.c_int(0)
+    lib.gsb200_device_count(C.byref(n))
+    if n.value > 0:
+        pytest.skip("a device is present")
+    pb = host.poisson_box_problem(2, 2, 4)
+    with pytest.raises(g.Gsb200Error, match="no CUDA device"):
+        g.DeviceAssembler(pb)
+    with pytest.raises(g.Gsb200Error, match="no CUDA device"):
+        g.assemble_host(pb)
+
+
+@pytest.mark.parametrize("text,pt,val", [
+    ("2*pi^2*sin(pi*x)*sin(pi*y)", (0.3, 0.7, 0.0), 2 * np.pi ** 2 * np.sin(np.pi * 0.3) * np.sin(np.pi * 0.7)),
+    ("-x^2 + 3*(y - z)/2", (1.5, 2.0, 0.5), -2.25 + 2.25),
+    ("exp(-x)*cos(y)+sqrt(abs(z))", (0.2, 1.0, -4.0), np.exp(-0.2) * np.cos(1.0) + 2.0),
+    ("1e-3*x + .5", (2.0, 0, 0), 0.502),
+    ("tanh(x)-sinh(y)*cosh(z)+log(2)+tan(0.1)", (0.3, 0.2, 0.1), np.tanh(0.3) - np.sinh(0.2) * np.cosh(0.1) + np.log(2) + np.tan(0.1)),
+])
+def test_expression_compiler(text, pt, val):
+    prog = g.expr_compile(text)
+    assert abs(capi.expr_eval(prog, *pt) - val) < 1e-14 * max(1, abs(val))
+
+
+@pytest.mark.parametrize("bad", ["foo(x)", "x +", "(x", "x y", "w"])
+def test_expression_compiler_rejects(bad):
+    with pytest.raises(g.Gsb200Error):
+        g.expr_compile(bad)
+
+
+def test_uniform_refine_matches_reference_expression():
+    kv = host.KnotVector.open_uniform(0, 1, 0, 2)
+    kv.setDegree(3)
+    kv.uniformRefine(124)
+    assert kv.size == 128 and len(np.unique(kv.knots)) == 126
+    z = dict(np.load(G.GOLDEN + "/cube_p3_m16.npz"))
+    kv = host.KnotVector.open_uniform(0, 1, 0, 2); kv.setDegree(3); kv.uniformRefine(15)
+    assert np.array_equal(kv.knots, z["p0_sk0"])      # bit-identical to gsKnotVector::uniformRefine
+    if R.have_ref():
+        lib = R.ref_lib()
+        base = np.array([0, 0, 0, 0.3, 0.3, 1, 1, 1.0])
+        out = np.zeros(64); n = C.c_int(0)
+        lib.gsref_uniform_refine(base.ctypes.data_as(C.POINTER(C.c_double)), len(base), 2, 3, out.ctypes.data_as(C.POINTER(C.c_double)), C.byref(n))
+        kv = host.KnotVector(2, base); kv.uniformRefine(3)
+        assert np.array_equal(kv.knots, out[:n.value])
+
+
+@pytest.mark.parametrize("name,dim,p,m", [("cube_p2_m5", 3, 2, 5), ("sq_p2_m8_visitor", 2, 2, 8), ("cube_p1_m5", 3, 1, 5)])
+def test_box_builder_reproduces_reference_flattening(name, dim, p, m):
+    z = dict(np.load(G.GOLDEN + f"/{name}.npz"))
+    pb = host.poisson_box_problem(dim, p, m)
+    assert pb.nfree == int(z["nfree"]) and pb.nfixed == int(z["nfixed"])
+    assert np.array_equal(pb.patches[0].dofmap, z["p0_dofmap"])
+    for i in range(dim):
+        assert np.array_equal(pb.patches[0].space_knots[i], z[f"p0_sk{i}"])
+    assert np.array_equal(pb.patches[0].geo_coefs, z["p0_coefs"])
+
+
+def test_dof_mapper_coupling_order():
+    # two 1-D "patches" of 4 functions glued end to start, ends eliminated (gsDofMapper.cpp:281-323)
+    m = host.DofMapper([4, 4])
+    m.match(0, 3, 1, 0)
+    m.eliminate(0, [0]); m.eliminate(1, [3])
+    m.finalize()
+    assert m.nfree == 5 and m.nfixed == 2
+    assert list(m.patch_map(0)) == [5, 0, 1, 4] and list(m.patch_map(1)) == [4, 2, 3, 6]

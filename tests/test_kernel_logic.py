@@ -1,0 +1,85 @@
+"""Index logic of the CUDA kernels, validated without a GPU.
+
+tests/emul builds the very kernel bodies of gismo_b200/csrc with -DGSB200_EMULATE (a single-
+threaded interpreter of the launch grid; test harness only, never loaded by the package) and
+the same host orchestration.  These tests pin: pattern build, slot tables, sweep segments,
+chunking under a workspace cap, slab partitioning across ranks, all against the reference's
+fixtures.  The same cases run on the real device in test_gpu_parity.py.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import goldenutil as G
+import refutil as R
+
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def emul():
+    return R.emul_lib()
+
+
+@pytest.mark.parametrize("name", G.names("full") + ["sq_p2_m64", "cube_p2_m16_expr"])
+def test_interpreted_kernels_match_reference(emul, name):
+    pb, z = G.load(name, R.emul_compile)
+    G.check_against(R.lib_assemble(emul, pb), z, TOL)
+
+
+@pytest.mark.parametrize("name,limit", [("cube_p3_curved_m4", 9_000_000), ("sq_p2_m64", 400_000), ("grid2x2_p2_m4", 14_000)])
+def test_chunked_assembly_under_workspace_cap(emul, name, limit):
+    pb, z = G.load(name, R.emul_compile)
+    res = R.lib_assemble(emul, pb, workspace_limit=limit)
+    assert res[4].nchunks > len(pb.patches), "cap did not force chunking"
+    G.check_against(res, z, TOL)
+
+
+def test_workspace_cap_too_small_is_an_error(emul):
+    pb, _ = G.load("cube_p2_m5", R.emul_compile)
+    with pytest.raises(RuntimeError, match="workspace limit"):
+        R.lib_assemble(emul, pb, workspace_limit=1000)
+
+
+@pytest.mark.parametrize("name,nranks", [("cube_p3_curved_m4", 2), ("cube_p2_m5", 3), ("sq_p2_m8_visitor", 4)])
+def test_slab_partition_over_ranks(emul, name, nranks):
+    """Each rank owns a slab of CSC columns; the union is the reference matrix, no overlap."""
+    pb0, z = G.load(name, R.emul_compile)
+    n = pb0.nfree
+    outer = np.zeros(n + 1, np.int64); cols = [None] * n; rhs = np.zeros((n, 1))
+    for r in range(nranks):
+        pb, _ = G.load(name, R.emul_compile)
+        pb.struct.rank, pb.struct.nranks = r, nranks
+        o, i, v, b, _ = R.lib_assemble(emul, pb)
+        for c in range(n):
+            if o[c + 1] > o[c]:
+                assert cols[c] is None, "column owned twice"
+                cols[c] = (i[o[c]:o[c + 1]], v[o[c]:o[c + 1]])
+        rhs += b
+    assert all(c is not None for c in cols)
+    inner = np.concatenate([c[0] for c in cols]); values = np.concatenate([c[1] for c in cols])
+    outer[1:] = np.cumsum([len(c[0]) for c in cols])
+    G.check_against((outer.astype(np.int32), inner, values, rhs), z, TOL)
+
+
+def test_bad_inputs_are_rejected(emul):
+    pb, _ = G.load("cube_p2_m5", R.emul_compile)
+    h = C.c_void_p()
+    pb.struct.abi_version = 99
+    assert emul.gsb200_create(C.byref(pb.struct), 0, C.byref(h)) == -1
+    pb.struct.abi_version = 1
+    pb.struct.form = 7
+    assert emul.gsb200_create(C.byref(pb.struct), 0, C.byref(h)) == -2
+    pb.struct.form = 0
+    pb.patches[0].dofmap[3] = 10 ** 6
+    assert emul.gsb200_create(C.byref(pb.struct), 0, C.byref(h)) == -1
+    assert b"out of range" in emul.gsb200_last_error()
+
+
+def test_assemble_before_pattern_is_a_state_error(emul):
+    pb, _ = G.load("cube_p2_m5", R.emul_compile)
+    h = C.c_void_p()
+    assert emul.gsb200_create(C.byref(pb.struct), 0, C.byref(h)) == 0
+    assert emul.gsb200_assemble(h) == -7
+    emul.gsb200_destroy(h)
