@@ -1,0 +1,13 @@
+"""Small driver for ncu captures: config-2 problem (or --nelem), pattern + N assemblies."""
+import argparse, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import gismo_b200 as g
+ap = argparse.ArgumentParser(); ap.add_argument("--nelem", type=int, default=125); ap.add_argument("--degree", type=int, default=3)
+ap.add_argument("--reps", type=int, default=2); ap.add_argument("--dim", type=int, default=3)
+a = ap.parse_args()
+prog = g.expr_compile("3*pi^2*sin(pi*x)*sin(pi*y)*sin(pi*z)" if a.dim == 3 else "2*pi^2*sin(pi*x)*sin(pi*y)")
+pb = g.host.poisson_box_problem(a.dim, a.degree, a.nelem, prog)
+A = g.DeviceAssembler(pb); A.buildPattern()
+for _ in range(a.reps):
+    A.assemble()
+t = A.timings(); print("ms:", t.geometry_ms, list(t.sweep_ms), t.rhs_ms, t.total_ms)
