@@ -295,26 +295,58 @@ constexpr int pick_is(int P1, int NOUT)
 template <class T> constexpr int n_has() { int n = 0; for (int o = 0; o < T::NOUT; ++o) for (int b = 0; b < 2; ++b) if (T::has(o, b)) ++n; return n; }
 template <class T> constexpr int n_first() { int n = 0; for (int k = 0; k < T::NT; ++k) if (T::first(k)) ++n; return n; }
 
+// Can the TMA-pipelined variant serve this sweep?  cp.async.bulk needs 16-byte aligned
+// addresses and sizes, i.e. even strides/extents in doubles; otherwise the generic kernel runs.
+static bool tma_ok(const SweepArgs &A, bool final_stage)
+{
+#ifdef GSB200_EMULATE
+    (void)A; (void)final_stage; return false;
+#else
+    static const bool disabled = getenv("GSB200_NO_TMA") != 0;
+    if (disabled) return false;
+    auto even = [](i64 v) { return (v & 1) == 0; };
+    if (!even(A.in_cs) || !even(A.in_es) || !even(A.in_os) || ((size_t)A.in & 15)) return false;
+    if (final_stage) return A.in_ts == 1 && A.in_is == A.q && (even(A.q) || even(A.ninner));
+    return A.in_is == 1 && even(A.in_ts) && even(A.ninner);
+#endif
+}
+
 template <int P1, class T, bool FINAL>
-static void launch_sweep_t(const SweepArgs &A, int nseg, stream_t s, i64 *flops_per_point)
+static int launch_sweep_t(const SweepArgs &A, int nseg, stream_t s, i64 *flops_per_point)
 {
     constexpr int IS = pick_is(P1, T::NOUT);
+    *flops_per_point = (i64)P1 * (2 * T::NT - n_first<T>() + 2 * P1 * n_has<T>());
+#ifndef GSB200_EMULATE
+    if (tma_ok(A, FINAL)) {
+        constexpr int G = P1 / IS, TC = (G <= 2) ? 128 : 64, NST = 3;
+        const size_t smem = (size_t)NST * A.q * T::NIN * TC * sizeof(double) + 2 * NST * sizeof(unsigned long long);
+        if (smem <= 200 * 1024) {
+            const int tiles = (int)((A.ninner + TC - 1) / TC);
+            const i64 nouter = A.ncol / A.ninner;
+            auto kfn = k_sweep_tma<P1, T, IS, FINAL, TC, NST, FINAL>;
+            static bool attr_done = false;
+            if (!attr_done) { GSB_TRY(dev_check(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "cudaFuncSetAttribute")); attr_done = true; }
+            kfn<<<dim3((unsigned)(nouter * tiles), 1, nseg), dim3(TC * G), smem, s>>>(A, tiles);
+            note_launch();
+            return 0;
+        }
+    }
+#endif
     dim3 grid((unsigned)((A.ncol + 127) / 128), P1 / IS, nseg);
     auto kfn = k_sweep<P1, T, IS, FINAL>;
     GSB_LAUNCH(kfn, grid, dim3(128), s, A);
-    *flops_per_point = (i64)P1 * (2 * T::NT - n_first<T>() + 2 * P1 * n_has<T>());
+    return 0;
 }
 template <class T, bool FINAL>
 static int launch_sweep(int P1, const SweepArgs &A, int nseg, stream_t s, i64 *fpp)
 {
     switch (P1) {
-    case 2: launch_sweep_t<2, T, FINAL>(A, nseg, s, fpp); break;
-    case 3: launch_sweep_t<3, T, FINAL>(A, nseg, s, fpp); break;
-    case 4: launch_sweep_t<4, T, FINAL>(A, nseg, s, fpp); break;
-    case 5: launch_sweep_t<5, T, FINAL>(A, nseg, s, fpp); break;
+    case 2: return launch_sweep_t<2, T, FINAL>(A, nseg, s, fpp);
+    case 3: return launch_sweep_t<3, T, FINAL>(A, nseg, s, fpp);
+    case 4: return launch_sweep_t<4, T, FINAL>(A, nseg, s, fpp);
+    case 5: return launch_sweep_t<5, T, FINAL>(A, nseg, s, fpp);
     default: set_error("degree %d not supported by the sweep kernels (1..4)", P1 - 1); return GSB200_EUNSUPPORTED;
     }
-    return 0;
 }
 
 enum { KIND_SYM = 0, KIND_GEN = 1, KIND_MASS = 2 };
@@ -413,18 +445,19 @@ static int assemble(gsb200_assembler *a)
             while (x_hi < P.own_hi && (i64)(dL.flast[x_hi] - dL.ffirst[x_lo] + 1) * dL.q <= maxpts) ++x_hi;
             const int eL0 = dL.ffirst[x_lo], eL1 = dL.flast[x_hi - 1] + 1, ELc = eL1 - eL0;
             const i64 QLc = (i64)ELc * dL.q;
-            const size_t need = (size_t)(perq * QLc) * 8;
+            const size_t need = (size_t)(perq * QLc) * 8 + 6 * 256;
             if (need > a->ws_size) {
                 dev_free(a->ws); a->ws = 0; a->ws_size = 0;
                 GSB_TRY(dev_malloc(&a->ws, need)); a->ws_size = need;
             }
             double *w = (double *)a->ws;
-            double *D = w; w += ncD * Q0 * Q1 * QLc;
-            double *A1 = w; w += no1 * NI0 * Q1 * QLc;
-            double *A2 = w; if (dim == 3) w += no2 * NI1 * NI0 * QLc;
-            double *F = w; w += nf * Q0 * Q1 * QLc;
-            double *V1 = w; w += n0 * Q1 * QLc;
-            double *V2 = w;
+            auto carve = [&](i64 count) { double *p = w; w += (count + 31) / 32 * 32; return p; };   // 256-byte aligned pieces
+            double *D = carve(ncD * Q0 * Q1 * QLc);
+            double *A1 = carve(no1 * NI0 * Q1 * QLc);
+            double *A2 = carve(dim == 3 ? no2 * NI1 * NI0 * QLc : 0);
+            double *F = carve(nf * Q0 * Q1 * QLc);
+            double *V1 = carve(n0 * Q1 * QLc);
+            double *V2 = carve(dim == 3 ? n1 * n0 * QLc : 0);
             const i64 npts = Q0 * Q1 * QLc;
             size_t segoff = 0;
             ++a->tm.nchunks;

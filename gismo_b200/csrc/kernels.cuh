@@ -372,6 +372,99 @@ struct SweepArgs {
     FinalArgs fin;
 };
 
+// Register-resident state of one sweep thread: partial sums of the (owner slot, partner slot)
+// pairs alive on the current knot span, for every output component.
+template <int P1, class T, int IS, bool FINAL>
+struct SweepCore {
+    static constexpr int NOUT = T::NOUT, NIN = T::NIN, NT = T::NT;
+    double acc[IS][P1][NOUT];
+
+    GSB_MEMBER void zero()
+    {
+#pragma unroll
+        for (int is = 0; is < IS; ++is)
+#pragma unroll
+            for (int js = 0; js < P1; ++js)
+#pragma unroll
+                for (int o = 0; o < NOUT; ++o) acc[is][js][o] = 0.0;
+    }
+
+    // one quadrature point: v = the NIN input components, tb = slot-ordered (value, derivative) table row
+    GSB_MEMBER void point(const double (&v)[NIN], const double2 *tb, int grp)
+    {
+        double2 bj[P1];
+#pragma unroll
+        for (int js = 0; js < P1; ++js) bj[js] = ld_keep2(tb + js);
+#pragma unroll
+        for (int is = 0; is < IS; ++is) {
+            double2 bi;
+            if (IS == P1) bi = bj[is]; else bi = ld_keep2(tb + grp * IS + is);
+            // z[o][b] = sum over the terms with that (o,b) of B^(a)_owner * in_c
+            double z[NOUT][2];
+            static_for<0, NT>([&](auto kc) {
+                constexpr int k = decltype(kc)::value;
+                const double bo = T::a(k) ? bi.y : bi.x;
+                if constexpr (T::first(k)) z[T::o(k)][T::b(k)] = bo * v[T::c(k)];
+                else z[T::o(k)][T::b(k)] = fma(bo, v[T::c(k)], z[T::o(k)][T::b(k)]);
+            });
+#pragma unroll
+            for (int js = 0; js < P1; ++js)
+                static_for<0, NOUT>([&](auto oc) {
+                    constexpr int o = decltype(oc)::value;
+                    if constexpr (T::has(o, 0)) acc[is][js][o] = fma(bj[js].x, z[o][0], acc[is][js][o]);
+                    if constexpr (T::has(o, 1)) acc[is][js][o] = fma(bj[js].y, z[o][1], acc[is][js][o]);
+                });
+        }
+    }
+
+    GSB_MEMBER void emit(const SweepArgs &A, const FinalCtx &fc, i64 obase, int is, int js, int fi, int d)
+    {
+        if (FINAL) final_emit(A.fin, fc, fi, d, acc[is][js][0]);
+        else {
+            const i64 o0 = ((i64)fi * (2 * A.p + 1) + (d + A.p)) * A.out_ps + obase;
+#pragma unroll
+            for (int o = 0; o < NOUT; ++o) A.out[o * A.out_cs + o0] = acc[is][js][o];
+        }
+    }
+
+    // functions leaving the span window after element e complete their pairs; a pair is emitted
+    // by the segment that owns its OWNER function (x_min <= owner < x_max)
+    GSB_MEMBER void exits(const SweepArgs &A, const FinalCtx &fc, i64 obase, int e, int f0, int grp, int x_min, int x_max)
+    {
+        const int ph = f0 % P1;
+        const int nx = A.nexit[e];
+        for (int k = 0; k < nx; ++k) {
+            const int x = f0 + k;
+            if (x >= x_max) break;                 // later exits only involve owners >= x_max
+            const int sx = (ph + k) % P1;
+#pragma unroll
+            for (int is = 0; is < IS; ++is) {
+                const int so = grp * IS + is;
+                const int fi = f0 + ((so - ph + P1) % P1);
+                const bool wr = (fi >= x_min) && (fi < x_max);
+                if (fi == x) {
+#pragma unroll
+                    for (int js = 0; js < P1; ++js) {
+                        const int fj = f0 + ((js - ph + P1) % P1);
+                        if (wr && fj >= x) emit(A, fc, obase, is, js, fi, fj - fi);
+#pragma unroll
+                        for (int o = 0; o < NOUT; ++o) acc[is][js][o] = 0.0;
+                    }
+                } else if (fi > x) {
+#pragma unroll
+                    for (int js = 0; js < P1; ++js)
+                        if (js == sx) {
+                            if (wr) emit(A, fc, obase, is, js, fi, x - fi);
+#pragma unroll
+                            for (int o = 0; o < NOUT; ++o) acc[is][js][o] = 0.0;
+                        }
+                }
+            }
+        }
+    }
+};
+
+// Generic variant: inputs straight from global memory (any strides / alignment).
 template <int P1, class T, int IS, bool FINAL>
 GSB_GLOBAL void k_sweep(const SweepArgs A)
 {
@@ -385,98 +478,122 @@ GSB_GLOBAL void k_sweep(const SweepArgs A)
     i64 obase = 0;
     if (FINAL) { if (!final_init(A.fin, outer, inner, fc)) return; }
     else obase = outer * A.out_os + (inner / A.out_bq) * A.out_bs + (inner % A.out_bq) * A.out_is;
-    constexpr int NOUT = T::NOUT, NIN = T::NIN, NT = T::NT;
-    const int W = 2 * A.p + 1;
-
-    double acc[IS][P1][NOUT];
-#pragma unroll
-    for (int is = 0; is < IS; ++is)
-#pragma unroll
-        for (int js = 0; js < P1; ++js)
-#pragma unroll
-            for (int o = 0; o < NOUT; ++o) acc[is][js][o] = 0.0;
-
+    constexpr int NIN = T::NIN;
+    SweepCore<P1, T, IS, FINAL> core;
+    core.zero();
     const int q = A.q;
     for (int e = e_begin; e < e_end; ++e) {
         const int f0 = A.first[e];
-        const int ph = f0 % P1;
         const double *ine = inp + (i64)(e - A.e_in0) * A.in_es;
         const double2 *tbe = A.tab + (i64)e * q * P1;
         for (int t = 0; t < q; ++t) {
             double v[NIN];
 #pragma unroll
             for (int c = 0; c < NIN; ++c) v[c] = ld_keep(ine + c * A.in_cs + t * A.in_ts);
-            const double2 *tb = tbe + t * P1;
-            double2 bj[P1];
-#pragma unroll
-            for (int js = 0; js < P1; ++js) bj[js] = ld_keep2(tb + js);
-#pragma unroll
-            for (int is = 0; is < IS; ++is) {
-                double2 bi;
-                if (IS == P1) bi = bj[is]; else bi = ld_keep2(tb + grp * IS + is);
-                // z[o][b] = sum over terms with that (o,b) of B^(a)_owner * in_c
-                double z[NOUT][2];
-                static_for<0, NT>([&](auto kc) {
-                    constexpr int k = decltype(kc)::value;
-                    const double bo = T::a(k) ? bi.y : bi.x;
-                    if constexpr (T::first(k)) z[T::o(k)][T::b(k)] = bo * v[T::c(k)];
-                    else z[T::o(k)][T::b(k)] = fma(bo, v[T::c(k)], z[T::o(k)][T::b(k)]);
-                });
-#pragma unroll
-                for (int js = 0; js < P1; ++js)
-                    static_for<0, NOUT>([&](auto oc) {
-                        constexpr int o = decltype(oc)::value;
-                        if constexpr (T::has(o, 0)) acc[is][js][o] = fma(bj[js].x, z[o][0], acc[is][js][o]);
-                        if constexpr (T::has(o, 1)) acc[is][js][o] = fma(bj[js].y, z[o][1], acc[is][js][o]);
-                    });
-            }
+            core.point(v, tbe + t * P1, grp);
         }
-        // functions leaving the span window after this element complete their pairs
-        const int nx = A.nexit[e];
-        for (int k = 0; k < nx; ++k) {
-            const int x = f0 + k;
-            if (x >= x_max) break;                 // later exits only involve owners >= x_max
-            const int sx = (ph + k) % P1;
-#pragma unroll
-            for (int is = 0; is < IS; ++is) {
-                const int so = grp * IS + is;
-                const int fi = f0 + ((so - ph + P1) % P1);
-                const bool wr = (fi >= x_min) && (fi < x_max);   // a pair is emitted by the segment owning its OWNER
-                if (fi == x) {
-#pragma unroll
-                    for (int js = 0; js < P1; ++js) {
-                        const int fj = f0 + ((js - ph + P1) % P1);
-                        if (wr && fj >= x) {
-                            if (FINAL) final_emit(A.fin, fc, fi, fj - fi, acc[is][js][0]);
-                            else {
-                                const i64 o0 = ((i64)fi * W + (fj - fi + A.p)) * A.out_ps + obase;
-#pragma unroll
-                                for (int o = 0; o < NOUT; ++o) A.out[o * A.out_cs + o0] = acc[is][js][o];
-                            }
-                        }
-#pragma unroll
-                        for (int o = 0; o < NOUT; ++o) acc[is][js][o] = 0.0;
-                    }
-                } else if (fi > x) {
-#pragma unroll
-                    for (int js = 0; js < P1; ++js)
-                        if (js == sx) {
-                            if (wr) {
-                                if (FINAL) final_emit(A.fin, fc, fi, x - fi, acc[is][js][0]);
-                                else {
-                                    const i64 o0 = ((i64)fi * W + (x - fi + A.p)) * A.out_ps + obase;
-#pragma unroll
-                                    for (int o = 0; o < NOUT; ++o) A.out[o * A.out_cs + o0] = acc[is][js][o];
-                                }
-                            }
-#pragma unroll
-                            for (int o = 0; o < NOUT; ++o) acc[is][js][o] = 0.0;
-                        }
-                }
-            }
-        }
+        core.exits(A, fc, obase, e, f0, grp, x_min, x_max);
     }
 }
+
+#ifndef GSB200_EMULATE
+// ------------------------------------------------------------------------------------
+// Blackwell variant: the input tile of every knot span is brought into shared memory by the
+// TMA engine (cp.async.bulk, completion on an mbarrier) through an NSTAGE-deep ring, so the
+// HBM latency is hidden behind the FP64 work of the previous spans instead of stalling each
+// warp on its own global loads; all owner-slot groups of a column tile live in ONE CTA and
+// share the tile (the generic variant re-reads it once per group).
+GSB_DEVICE unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+GSB_DEVICE void mbar_init(unsigned long long *bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
+GSB_DEVICE void mbar_expect_tx(unsigned long long *bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+GSB_DEVICE void mbar_arrive(unsigned long long *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+GSB_DEVICE void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+GSB_DEVICE void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// TC columns per CTA, G = P1/IS groups; blockDim.x = TC*G (group = threadIdx.x / TC, warp-uniform).
+// ROWB = true when the q points of a column are contiguous in memory (in_ts == 1, in_is == q):
+// one bulk copy per component; otherwise one per (point, component) row of TC contiguous columns.
+template <int P1, class T, int IS, bool FINAL, int TC, int NSTAGE, bool ROWB>
+GSB_GLOBAL void k_sweep_tma(const SweepArgs A, const int tiles_per_outer)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int NIN = T::NIN, G = P1 / IS;
+    const int q = A.q;
+    const int stage_doubles = q * NIN * TC;
+    double *sdata = reinterpret_cast<double *>(smem_raw);
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(sdata + (size_t)NSTAGE * stage_doubles);
+    unsigned long long *empty = full + NSTAGE;
+    const int tid = threadIdx.x, grp = tid / TC, lcol = tid - grp * TC, warp = tid >> 5, lane = tid & 31;
+    constexpr int NWARP = TC * G / 32;
+    const int sg = blockIdx.z;
+    const int e_begin = A.seg[4 * sg + 0], e_end = A.seg[4 * sg + 1], x_min = A.seg[4 * sg + 2], x_max = A.seg[4 * sg + 3];
+    const i64 outer = blockIdx.x / tiles_per_outer;
+    const i64 inner0 = (i64)(blockIdx.x - outer * tiles_per_outer) * TC;
+    const int ncols = (int)((A.ninner - inner0) < TC ? (A.ninner - inner0) : TC);
+    const i64 inner = inner0 + lcol;
+    const bool active_col = lcol < ncols;
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, NWARP); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const double *tile = A.in + outer * A.in_os + inner0 * A.in_is;
+    const unsigned row_bytes = (unsigned)(ncols * (ROWB ? q : 1) * sizeof(double));
+    const int nrows = ROWB ? NIN : q * NIN;
+    auto issue = [&](int e) {   // executed by warp 0: fill stage (e - e_begin) % NSTAGE with span e
+        const int s = (e - e_begin) % NSTAGE;
+        double *dst = sdata + (size_t)s * stage_doubles;
+        const double *src = tile + (i64)(e - A.e_in0) * A.in_es;
+        if (lane == 0) mbar_expect_tx(full + s, row_bytes * nrows);
+        __syncwarp();
+        for (int r = lane; r < nrows; r += 32) {
+            if (ROWB) bulk_g2s(dst + (size_t)r * TC * q, src + (i64)r * A.in_cs, row_bytes, full + s);
+            else { const int t = r / NIN, c = r - t * NIN; bulk_g2s(dst + (size_t)r * TC, src + (i64)c * A.in_cs + (i64)t * A.in_ts, row_bytes, full + s); }
+        }
+    };
+    if (warp == 0)
+        for (int e = e_begin; e < e_end && e < e_begin + NSTAGE; ++e) issue(e);
+
+    FinalCtx fc;
+    i64 obase = 0;
+    bool live = active_col;
+    if (FINAL) { if (live) live = final_init(A.fin, outer, inner, fc); }
+    else obase = outer * A.out_os + (inner / A.out_bq) * A.out_bs + (inner % A.out_bq) * A.out_is;
+    SweepCore<P1, T, IS, FINAL> core;
+    core.zero();
+    for (int e = e_begin; e < e_end; ++e) {
+        const int it = e - e_begin, s = it % NSTAGE;
+        const unsigned par = (unsigned)((it / NSTAGE) & 1);
+        mbar_wait(full + s, par);
+        if (live) {
+            const double *sd = sdata + (size_t)s * stage_doubles;
+            const double2 *tbe = A.tab + (i64)e * q * P1;
+            for (int t = 0; t < q; ++t) {
+                double v[NIN];
+#pragma unroll
+                for (int c = 0; c < NIN; ++c) v[c] = ROWB ? sd[((size_t)c * TC + lcol) * q + t] : sd[((size_t)t * NIN + c) * TC + lcol];
+                core.point(v, tbe + t * P1, grp);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);
+        if (warp == 0 && e + NSTAGE < e_end) {     // refill this stage once every warp has released it
+            mbar_wait(empty + s, par);
+            issue(e + NSTAGE);
+        }
+        if (live) core.exits(A, fc, obase, e, A.first[e], grp, x_min, x_max);
+    }
+}
+#endif
 
 // ------------------------------------------------------------------------------------
 // K3: load vector, one direction at a time: out[i][col] = sum_{q in supp(i)} B_i(q) in[q][col].

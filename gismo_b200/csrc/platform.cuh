@@ -24,6 +24,7 @@ void set_error(const char *fmt, ...);
 #define GSB_GLOBAL __global__
 #define GSB_DEVICE __device__ __forceinline__
 #define GSB_HD __host__ __device__ __forceinline__
+#define GSB_MEMBER __device__ __forceinline__
 #define GSB_LAUNCH(kernel, grid, block, stream, ...) \
     do { kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__); gsb::note_launch(); } while (0)
 namespace gsb {
@@ -59,6 +60,7 @@ GSB_DEVICE int popc(unsigned v) { return __popc(v); }
 #define GSB_GLOBAL static
 #define GSB_DEVICE static inline
 #define GSB_HD static inline
+#define GSB_MEMBER inline
 struct gsb_dim3 { unsigned x, y, z; gsb_dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 typedef gsb_dim3 dim3;
 struct double2 { double x, y; };
