@@ -27,16 +27,55 @@ struct Parser {
     std::vector<double> consts;
     std::string err;
     int depth, maxdepth;
+    // one entry per value currently on the evaluation stack: where its code starts and, if it
+    // is a compile-time constant, its value (constant sub-expressions such as 3*pi^2 are folded
+    // so the device interpreter does not evaluate pow() at every quadrature point)
+    struct Item { size_t start; bool is_const; double value; };
+    std::vector<Item> items;
 
     explicit Parser(const char *str) : s(str), depth(0), maxdepth(0) {}
     void skip() { while (*s && std::isspace((unsigned char)*s)) ++s; }
     void push(int d) { depth += d; if (depth > maxdepth) maxdepth = depth; }
-    void emit(int op) { ops.push_back(op); }
-    void emit_const(double v) {
+    static double apply1(int op, double a) {
+        switch (op) {
+        case GSB200_OP_NEG: return -a; case GSB200_OP_SIN: return std::sin(a); case GSB200_OP_COS: return std::cos(a);
+        case GSB200_OP_TAN: return std::tan(a); case GSB200_OP_EXP: return std::exp(a); case GSB200_OP_LOG: return std::log(a);
+        case GSB200_OP_SQRT: return std::sqrt(a); case GSB200_OP_ABS: return std::fabs(a); case GSB200_OP_TANH: return std::tanh(a);
+        case GSB200_OP_SINH: return std::sinh(a); case GSB200_OP_COSH: return std::cosh(a); case GSB200_OP_SQR: return a * a;
+        }
+        return NAN;
+    }
+    static double apply2(int op, double a, double b) {
+        switch (op) {
+        case GSB200_OP_ADD: return a + b; case GSB200_OP_SUB: return a - b; case GSB200_OP_MUL: return a * b;
+        case GSB200_OP_DIV: return a / b; case GSB200_OP_POW: return std::pow(a, b);
+        }
+        return NAN;
+    }
+    void raw_const(double v) {
         size_t k = 0;
         for (; k < consts.size(); ++k) if (std::memcmp(&consts[k], &v, sizeof v) == 0) break;
         if (k == consts.size()) consts.push_back(v);
-        ops.push_back(GSB200_OP_CONST); ops.push_back((int32_t)k); push(1);
+        ops.push_back(GSB200_OP_CONST); ops.push_back((int32_t)k);
+    }
+    void emit(int op) {
+        const bool leaf = op == GSB200_OP_X || op == GSB200_OP_Y || op == GSB200_OP_Z;
+        const bool binary = op == GSB200_OP_ADD || op == GSB200_OP_SUB || op == GSB200_OP_MUL || op == GSB200_OP_DIV || op == GSB200_OP_POW;
+        if (leaf) { Item it = {ops.size(), false, 0.0}; items.push_back(it); ops.push_back(op); return; }
+        if (binary) {
+            Item b = items.back(); items.pop_back();
+            Item &a = items.back();
+            if (a.is_const && b.is_const) { a.value = apply2(op, a.value, b.value); ops.resize(a.start); raw_const(a.value); return; }
+            if (op == GSB200_OP_POW && b.is_const && b.value == 2.0) { ops.resize(b.start); ops.push_back(GSB200_OP_SQR); a.is_const = false; return; }
+            a.is_const = false; ops.push_back(op); return;
+        }
+        Item &a = items.back();   // unary
+        if (a.is_const) { a.value = apply1(op, a.value); ops.resize(a.start); raw_const(a.value); return; }
+        ops.push_back(op);
+    }
+    void emit_const(double v) {
+        Item it = {ops.size(), true, v}; items.push_back(it);
+        raw_const(v); push(1);
     }
     bool expr() {
         if (!term()) return false;

@@ -60,11 +60,11 @@ struct Dir1D {
     int p = 0, q = 0, nfun = 0, nel = 0, Q = 0;
     std::vector<int> span, first, nexit, plo, phi, ffirst, flast;
     int *d_first = 0, *d_nexit = 0, *d_plo = 0, *d_phi = 0, *d_ffirst = 0, *d_flast = 0;
-    double2 *d_tab = 0; double *d_upt = 0, *d_hpt = 0, *d_gw = 0;
+    double2 *d_tab = 0; double *d_upt = 0, *d_hpt = 0, *d_gw = 0, *d_gwp = 0;
     double2 *d_gtab = 0; int *d_gfirst = 0; int pg1 = 0, ngeo = 0;
     void release() {
         dev_free(d_first); dev_free(d_nexit); dev_free(d_plo); dev_free(d_phi); dev_free(d_ffirst); dev_free(d_flast);
-        dev_free(d_tab); dev_free(d_upt); dev_free(d_hpt); dev_free(d_gw); dev_free(d_gtab); dev_free(d_gfirst);
+        dev_free(d_tab); dev_free(d_upt); dev_free(d_hpt); dev_free(d_gw); dev_free(d_gwp); dev_free(d_gtab); dev_free(d_gfirst);
     }
 };
 
@@ -102,8 +102,9 @@ static int build_dir(Dir1D &d, const double *kn, int nk, int p, int q, const dou
     GSB_TRY(dev_malloc((void **)&d.d_tab, sizeof(double2) * (size_t)d.Q * p1));
     GSB_TRY(dev_malloc((void **)&d.d_upt, sizeof(double) * (size_t)d.Q));
     GSB_TRY(dev_malloc((void **)&d.d_hpt, sizeof(double) * (size_t)d.Q));
-    BasisTableArgs B; B.knots = d_kn; B.span = d_span; B.gnodes = d_gx; B.p = p; B.nel = d.nel; B.q = q;
-    B.tab = d.d_tab; B.upt = d.d_upt; B.hpt = d.d_hpt;
+    GSB_TRY(dev_malloc((void **)&d.d_gwp, sizeof(double) * (size_t)d.Q));
+    BasisTableArgs B; B.knots = d_kn; B.span = d_span; B.gnodes = d_gx; B.gweights = d.d_gw; B.p = p; B.nel = d.nel; B.q = q;
+    B.tab = d.d_tab; B.upt = d.d_upt; B.hpt = d.d_hpt; B.gwp = d.d_gwp;
     GSB_LAUNCH(k_basis_table, dim3((d.Q + 127) / 128), dim3(128), s, B);
     d.pg1 = gp + 1; d.ngeo = gnk - gp - 1;
     GSB_TRY(dev_malloc((void **)&d.d_gtab, sizeof(double2) * (size_t)d.Q * d.pg1));
@@ -302,7 +303,7 @@ static bool tma_ok(const SweepArgs &A, bool final_stage)
 #ifdef GSB200_EMULATE
     (void)A; (void)final_stage; return false;
 #else
-    static const bool disabled = getenv("GSB200_NO_TMA") != 0;
+    const bool disabled = getenv("GSB200_NO_TMA") != 0;
     if (disabled) return false;
     auto even = [](i64 v) { return (v & 1) == 0; };
     if (!even(A.in_cs) || !even(A.in_es) || !even(A.in_os) || ((size_t)A.in & 15)) return false;
@@ -471,7 +472,7 @@ static int assemble(gsb200_assembler *a)
                     const Dir1D &d = P.dir[k];
                     G.qn[k] = (k == L) ? (int)QLc : d.Q; G.qoff[k] = (k == L) ? eL0 * d.q : 0;
                     G.gtab[k] = d.d_gtab; G.gfirst[k] = d.d_gfirst; G.pg1[k] = d.pg1; G.ngeo[k] = d.ngeo;
-                    G.hpt[k] = d.d_hpt; G.gw[k] = d.d_gw; G.q1d[k] = d.q;
+                    G.hpt[k] = d.d_hpt; G.gwp[k] = d.d_gwp;
                 }
                 G.coefs = P.d_coefs; G.weights = P.d_weights; G.ngeo_total = P.ngeo_total;
                 G.form = a->form; G.brow = brow; G.bcol = bcol; G.lambda = a->coef[0]; G.mu = a->coef[1];
@@ -479,8 +480,17 @@ static int assemble(gsb200_assembler *a)
                 G.D = D; G.dstride = npts;
                 if (blk == 0 && nf) { G.F = F; G.fstride = npts; G.nf = nf; for (int c = 0; c < nf; ++c) G.prog[c] = a->progs[c]; }
                 mark(a, 0);
-                if (dim == 2) { GSB_LAUNCH(k_geometry<2>, dim3((unsigned)((npts + 127) / 128)), dim3(128), s, G); }
-                else { GSB_LAUNCH(k_geometry<3>, dim3((unsigned)((npts + 127) / 128)), dim3(128), s, G); }
+                {
+                    int pgu = P.dir[0].pg1;                                   // uniform geometry degree -> unrolled kernel
+                    for (int k = 1; k < dim; ++k) if (P.dir[k].pg1 != pgu) pgu = 0;
+                    if (pgu > 4) pgu = 0;
+                    const dim3 gg((unsigned)((QLc + 127) / 128), dim == 3 ? (unsigned)Q1 : (unsigned)Q0, dim == 3 ? (unsigned)Q0 : 1u);
+                    if (gg.y > 65535u || gg.z > 65535u) { set_error("more than 65535 quadrature points per direction"); return GSB200_EUNSUPPORTED; }
+#define GSB_GEO(D_, P_) { auto kfn = k_geometry<D_, P_>; GSB_LAUNCH(kfn, gg, dim3(128), s, G); }
+                    if (dim == 2) { switch (pgu) { case 2: GSB_GEO(2, 2) break; case 3: GSB_GEO(2, 3) break; case 4: GSB_GEO(2, 4) break; default: GSB_GEO(2, 0) } }
+                    else { switch (pgu) { case 2: GSB_GEO(3, 2) break; case 3: GSB_GEO(3, 3) break; case 4: GSB_GEO(3, 4) break; default: GSB_GEO(3, 0) } }
+#undef GSB_GEO
+                }
 
                 // ---------------- sweeps
                 FinalArgs Fa; memset(&Fa, 0, sizeof Fa);

@@ -119,11 +119,12 @@ GSB_HD void bspline_ders(const double *kn, int p, int s, double u, double *val, 
 // (gsQuadRule.h:177-201), basis values/derivatives stored in SLOT order (slot = function
 // index mod (p+1)) so that the sweep kernels index their register accumulators statically.
 struct BasisTableArgs {
-    const double *knots; const int *span; const double *gnodes;
+    const double *knots; const int *span; const double *gnodes; const double *gweights;
     int p, nel, q;
     double2 *tab;      // [nel*q][p+1]
     double *upt;       // [nel*q] point coordinate
     double *hpt;       // [nel*q] half element width h
+    double *gwp;       // [nel*q] reference Gauss weight of the point
 };
 GSB_GLOBAL void k_basis_table(const BasisTableArgs A)
 {
@@ -138,6 +139,7 @@ GSB_GLOBAL void k_basis_table(const BasisTableArgs A)
     for (int a = 0; a < p1; ++a) A.tab[(i64)id * p1 + (first + a) % p1] = make_double2(val[a], der[a]);
     A.upt[id] = u;
     A.hpt[id] = h;
+    A.gwp[id] = A.gweights[t];
 }
 
 // Geometry basis (its own, usually coarse, knot vector) at the same 1-D points.
@@ -191,6 +193,7 @@ GSB_HD double program_eval(const DevProgram &pr, double x, double y, double z)
         case GSB200_OP_TANH: st[sp - 1] = tanh(st[sp - 1]); break;
         case GSB200_OP_SINH: st[sp - 1] = sinh(st[sp - 1]); break;
         case GSB200_OP_COSH: st[sp - 1] = cosh(st[sp - 1]); break;
+        case GSB200_OP_SQR: st[sp - 1] = st[sp - 1] * st[sp - 1]; break;
         default: return NAN;
         }
     }
@@ -207,49 +210,88 @@ struct GeoArgs {
     int dim;
     int qn[3], qoff[3];            // window of 1-D points handled (count, first)
     const double2 *gtab[3]; const int *gfirst[3]; int pg1[3], ngeo[3];
-    const double *hpt[3]; const double *gw[3]; int q1d[3];   // h per point, Gauss weights, points/element
+    const double *hpt[3]; const double *gwp[3];              // per 1-D point: half element width, reference Gauss weight
     const double *coefs; const double *weights; i64 ngeo_total;
     int form, brow, bcol; double lambda, mu;
     int symD;                      // 1: write the 3/6 unique components, 0: all dim*dim
     double *D; i64 dstride;        // may be NULL (load only)
     double *F; i64 fstride; int nf; DevProgram prog[3];
 };
-template <int DIM>
+// Thread = one point of the last direction (fastest in memory), blockIdx.y/z = the other
+// directions.  PG = geometry degree + 1 when equal in all directions (loops unrolled, 1-D values
+// in registers) or 0 for the generic run-time loop.
+template <int DIM, int PG>
 GSB_GLOBAL void k_geometry(const GeoArgs A)
 {
-    i64 total = 1;
-    for (int k = 0; k < DIM; ++k) total *= A.qn[k];
-    const i64 id = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= total) return;
+    const int qlast = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qlast >= A.qn[DIM - 1]) return;
     int ql[DIM];   // global 1-D point index per direction
-    { i64 r = id; for (int k = DIM - 1; k >= 0; --k) { ql[k] = (int)(r % A.qn[k]) + A.qoff[k]; r /= A.qn[k]; } }
+    i64 id;
+    ql[DIM - 1] = qlast + A.qoff[DIM - 1];
+    if (DIM == 3) { ql[1] = blockIdx.y + A.qoff[1]; ql[0] = blockIdx.z + A.qoff[0]; id = ((i64)blockIdx.z * A.qn[1] + blockIdx.y) * A.qn[DIM - 1] + qlast; }
+    else { ql[0] = blockIdx.y + A.qoff[0]; id = (i64)blockIdx.y * A.qn[DIM - 1] + qlast; }
+    constexpr int PGM = PG ? PG : (GSB_MAXP + 1);
+    int pg1[DIM], gf[DIM];
+    double2 b[DIM][PGM];
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) {
+        pg1[k] = PG ? PG : A.pg1[k];
+        gf[k] = A.gfirst[k][ql[k]];
+#pragma unroll
+        for (int a = 0; a < PGM; ++a) if (a < pg1[k]) b[k][a] = ld_keep2(A.gtab[k] + (i64)ql[k] * pg1[k] + a);
+    }
     // tensor-product sum over the (pg+1)^d active control points
     double W = 0.0, dW[DIM], xn[DIM], dxn[DIM][DIM];   // dxn[a][c] = d(x_c numerator)/d xi_a
-    for (int a = 0; a < DIM; ++a) { dW[a] = 0.0; xn[a] = 0.0; for (int c = 0; c < DIM; ++c) dxn[a][c] = 0.0; }
-    int cnt[DIM];
-    for (int k = 0; k < DIM; ++k) cnt[k] = 0;
-    for (;;) {
-        i64 idx = 0; double v = 1.0, dv[DIM];
-        for (int k = DIM - 1; k >= 0; --k) idx = idx * A.ngeo[k] + (A.gfirst[k][ql[k]] + cnt[k]);
-        double2 b[DIM];
-        for (int k = 0; k < DIM; ++k) { b[k] = A.gtab[k][(i64)ql[k] * A.pg1[k] + cnt[k]]; v *= b[k].x; }
-        for (int k = 0; k < DIM; ++k) { dv[k] = b[k].y; for (int i = 0; i < DIM; ++i) if (i != k) dv[k] *= b[i].x; }
-        const double wt = A.weights ? A.weights[idx] : 1.0;
-        W += wt * v;
-        for (int k = 0; k < DIM; ++k) dW[k] += wt * dv[k];
-        for (int c = 0; c < DIM; ++c) {
-            const double C = A.coefs[(i64)c * A.ngeo_total + idx];
-            xn[c] += wt * v * C;
-            for (int k = 0; k < DIM; ++k) dxn[k][c] += wt * dv[k] * C;
+#pragma unroll
+    for (int a = 0; a < DIM; ++a) { dW[a] = 0.0; xn[a] = 0.0;
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) dxn[a][c] = 0.0; }
+    const bool rational = A.weights != 0;
+    const int n2 = DIM == 3 ? pg1[DIM - 1] : 1;
+#pragma unroll
+    for (int a2 = 0; a2 < (DIM == 3 ? PGM : 1); ++a2) {
+        if (a2 >= n2) break;
+#pragma unroll
+        for (int a1 = 0; a1 < PGM; ++a1) {
+            if (a1 >= pg1[1]) break;
+            const double2 b1 = b[1][a1];
+            const double2 b2 = DIM == 3 ? b[DIM - 1][a2] : make_double2(1.0, 0.0);
+            const double v12 = b1.x * b2.x, d1 = b1.y * b2.x, d2 = b1.x * b2.y;
+            const i64 row = DIM == 3 ? ((i64)(gf[DIM - 1] + a2) * A.ngeo[1] + (gf[1] + a1)) * A.ngeo[0] + gf[0]
+                                     : (i64)(gf[1] + a1) * A.ngeo[0] + gf[0];
+#pragma unroll
+            for (int a0 = 0; a0 < PGM; ++a0) {
+                if (a0 >= pg1[0]) break;
+                const i64 idx = row + a0;
+                double dv[3];
+                double v = b[0][a0].x * v12;
+                dv[0] = b[0][a0].y * v12; dv[1] = b[0][a0].x * d1; dv[2] = b[0][a0].x * d2;
+                if (rational) {
+                    const double wt = A.weights[idx];
+                    v *= wt; dv[0] *= wt; dv[1] *= wt; dv[2] *= wt;
+                    W += v;
+#pragma unroll
+                    for (int kk = 0; kk < DIM; ++kk) dW[kk] += dv[kk];
+                }
+#pragma unroll
+                for (int c = 0; c < DIM; ++c) {
+                    const double C = ld_keep(A.coefs + (i64)c * A.ngeo_total + idx);
+                    xn[c] = fma(v, C, xn[c]);
+#pragma unroll
+                    for (int kk = 0; kk < DIM; ++kk) dxn[kk][c] = fma(dv[kk], C, dxn[kk][c]);
+                }
+            }
         }
-        int k = 0;
-        while (k < DIM && ++cnt[k] >= A.pg1[k]) { cnt[k] = 0; ++k; }
-        if (k == DIM) break;
     }
+    if (!rational) W = 1.0;
     double x[3] = {0.0, 0.0, 0.0}, J[DIM][DIM];   // J[c][a] = d x_c / d xi_a
-    for (int c = 0; c < DIM; ++c) {
-        x[c] = xn[c] / W;
-        for (int a = 0; a < DIM; ++a) J[c][a] = (dxn[a][c] * W - xn[c] * dW[a]) / (W * W);
+    if (rational) {
+        for (int c = 0; c < DIM; ++c) {
+            x[c] = xn[c] / W;
+            for (int a = 0; a < DIM; ++a) J[c][a] = (dxn[a][c] * W - xn[c] * dW[a]) / (W * W);
+        }
+    } else {
+        for (int c = 0; c < DIM; ++c) { x[c] = xn[c]; for (int a = 0; a < DIM; ++a) J[c][a] = dxn[a][c]; }
     }
     double Ji[DIM][DIM], det;   // Ji[a][c] = (J^-1)[a][c]
     if (DIM == 2) {
@@ -267,10 +309,11 @@ GSB_GLOBAL void k_geometry(const GeoArgs A)
     }
     // quadrature weight: hprod * (w_0 w_1 w_2), same association as the reference
     double hprod = 1.0, wp = 1.0;
+#pragma unroll
     for (int k = 0; k < DIM; ++k) {
         const double h = A.hpt[k][ql[k]];
         hprod *= (h == 0.0 ? 0.5 : h);
-        const double g = A.gw[k][ql[k] % A.q1d[k]];
+        const double g = A.gwp[k][ql[k]];
         wp = (k == 0) ? g : wp * g;
     }
     const double weight = hprod * wp * fabs(det);
@@ -330,32 +373,43 @@ GSB_DEVICE bool final_init(const FinalArgs &F, i64 outer, i64 inner, FinalCtx &c
     return true;
 }
 
-GSB_DEVICE void final_emit(const FinalArgs &F, const FinalCtx &c, int iL, int dL, double val)
+// Per-owner data (global column, its flag and CSC offset) is loaded once per function and
+// kept in registers; only the slot-table word is fetched per emitted entry.
+struct OwnerCache { int fun; int gi; int flag; i64 base; i64 li; };
+
+GSB_DEVICE void owner_load(const FinalArgs &F, const FinalCtx &c, int iL, OwnerCache &oc)
 {
-    const i64 li = (i64)iL * c.nlow + c.li_low;
-    const i64 lj = li + (i64)dL * c.nlow + c.dj_low;
-    const int gi = F.dofmap[F.bcol * F.nb + li];
-    if (gi >= F.nfree) return;                       // eliminated column: nothing stored
-    const unsigned char flag = F.colflag[F.bcol * F.nb + li];
-    if (!flag) return;                               // column not owned by this rank
+    oc.fun = iL;
+    oc.li = (i64)iL * c.nlow + c.li_low;
+    oc.gi = F.dofmap[F.bcol * F.nb + oc.li];
+    oc.flag = (oc.gi < F.nfree) ? (int)F.colflag[F.bcol * F.nb + oc.li] : 0;   // eliminated or foreign column: nothing stored
+    oc.base = oc.flag ? F.colptr[oc.gi] : 0;
+}
+
+GSB_DEVICE void final_emit(const FinalArgs &F, const FinalCtx &c, const OwnerCache &oc, int dL, double val)
+{
+    if (!oc.flag) return;
+    const i64 lj = oc.li + (i64)dL * c.nlow + c.dj_low;
+    if (oc.flag == 1) {
+        const int run = (F.dim == 2) ? (dL + F.p[1]) : ((dL + F.p[2]) * (2 * F.p[1] + 1) + c.r_low);
+        const unsigned w = F.st[oc.li * F.nrun + run];
+        const unsigned mask = w >> 16;
+        if ((mask >> c.bit0) & 1u) {                 // partner row is free: its rank in the column is known
+            const int rank = (int)(w & 0xffffu) + popc(mask & ((1u << c.bit0) - 1u));
+            F.values[oc.base + rank] = val;
+            return;
+        }
+        if (!F.fixed) return;
+    }
     const int gj = F.dofmap[F.brow * F.nb + lj];
     if (gj >= F.nfree) {                             // eliminated row: by symmetry of the form this is the
         if (F.fixed)                                 // -K(i,j) g_j term of gsSparseSystem.h:1004
-            for (int r = 0; r < F.nrhs; ++r) atomic_add(F.rhs + (i64)r * F.nfree + gi, -val * F.fixed[(i64)r * F.nfixed + (gj - F.nfree)]);
+            for (int r = 0; r < F.nrhs; ++r) atomic_add(F.rhs + (i64)r * F.nfree + oc.gi, -val * F.fixed[(i64)r * F.nfixed + (gj - F.nfree)]);
         return;
     }
-    const i64 base = F.colptr[gi];
-    if (flag == 1) {
-        const int run = (F.dim == 2) ? (dL + F.p[1]) : ((dL + F.p[2]) * (2 * F.p[1] + 1) + c.r_low);
-        const unsigned w = F.st[li * F.nrun + run];
-        const unsigned mask = w >> 16;
-        const int rank = (int)(w & 0xffffu) + popc(mask & ((1u << c.bit0) - 1u));
-        F.values[base + rank] = val;
-    } else {
-        int lo = 0, hi = (int)(F.colptr[gi + 1] - base) - 1;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (F.inner[base + mid] < gj) lo = mid + 1; else hi = mid; }
-        atomic_add(F.values + base + lo, val);
-    }
+    int lo = 0, hi = (int)(F.colptr[oc.gi + 1] - oc.base) - 1;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (F.inner[oc.base + mid] < gj) lo = mid + 1; else hi = mid; }
+    atomic_add(F.values + oc.base + lo, val);
 }
 
 // ------------------------------------------------------------------------------------
@@ -378,9 +432,12 @@ template <int P1, class T, int IS, bool FINAL>
 struct SweepCore {
     static constexpr int NOUT = T::NOUT, NIN = T::NIN, NT = T::NT;
     double acc[IS][P1][NOUT];
+    OwnerCache oc[FINAL ? IS : 1];
 
     GSB_MEMBER void zero()
     {
+#pragma unroll
+        for (int is = 0; is < (FINAL ? IS : 1); ++is) { oc[is].fun = -1; oc[is].flag = 0; }
 #pragma unroll
         for (int is = 0; is < IS; ++is)
 #pragma unroll
@@ -419,8 +476,11 @@ struct SweepCore {
 
     GSB_MEMBER void emit(const SweepArgs &A, const FinalCtx &fc, i64 obase, int is, int js, int fi, int d)
     {
-        if (FINAL) final_emit(A.fin, fc, fi, d, acc[is][js][0]);
-        else {
+        if (FINAL) {
+            OwnerCache &c = oc[FINAL ? is : 0];
+            if (c.fun != fi) owner_load(A.fin, fc, fi, c);
+            final_emit(A.fin, fc, c, d, acc[is][js][0]);
+        } else {
             const i64 o0 = ((i64)fi * (2 * A.p + 1) + (d + A.p)) * A.out_ps + obase;
 #pragma unroll
             for (int o = 0; o < NOUT; ++o) A.out[o * A.out_cs + o0] = acc[is][js][o];
@@ -523,7 +583,7 @@ GSB_DEVICE void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned lo
 // ROWB = true when the q points of a column are contiguous in memory (in_ts == 1, in_is == q):
 // one bulk copy per component; otherwise one per (point, component) row of TC contiguous columns.
 template <int P1, class T, int IS, bool FINAL, int TC, int NSTAGE, bool ROWB>
-GSB_GLOBAL void k_sweep_tma(const SweepArgs A, const int tiles_per_outer)
+GSB_GLOBAL void __launch_bounds__(TC * (P1 / IS)) k_sweep_tma(const SweepArgs A, const int tiles_per_outer)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int NIN = T::NIN, G = P1 / IS;

@@ -67,7 +67,8 @@ enum {
     GSB200_OP_ADD = 4, GSB200_OP_SUB = 5, GSB200_OP_MUL = 6, GSB200_OP_DIV = 7,
     GSB200_OP_POW = 8, GSB200_OP_NEG = 9, GSB200_OP_SIN = 10, GSB200_OP_COS = 11,
     GSB200_OP_TAN = 12, GSB200_OP_EXP = 13, GSB200_OP_LOG = 14, GSB200_OP_SQRT = 15,
-    GSB200_OP_ABS = 16, GSB200_OP_TANH = 17, GSB200_OP_SINH = 18, GSB200_OP_COSH = 19
+    GSB200_OP_ABS = 16, GSB200_OP_TANH = 17, GSB200_OP_SINH = 18, GSB200_OP_COSH = 19,
+    GSB200_OP_SQR = 20
 };
 #define GSB200_PROGRAM_MAX_OPS 256
 #define GSB200_PROGRAM_MAX_STACK 32

@@ -186,6 +186,7 @@ static double prog_eval(const gsb200_program *pr, const double *x)
         case GSB200_OP_TANH: st[sp - 1] = tanh(st[sp - 1]); break;
         case GSB200_OP_SINH: st[sp - 1] = sinh(st[sp - 1]); break;
         case GSB200_OP_COSH: st[sp - 1] = cosh(st[sp - 1]); break;
+        case GSB200_OP_SQR: st[sp - 1] = st[sp - 1] * st[sp - 1]; break;
         default: return NAN;
         }
     }
