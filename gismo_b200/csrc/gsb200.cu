@@ -18,6 +18,8 @@ void set_error(const char *fmt, ...)
     va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
 }
 void note_launch() { ++g_launches; }
+static bool g_dry = false;
+bool dry_run() { return g_dry; }
 
 #define GSB_TRY(expr) do { int rc_ = (expr); if (rc_) return rc_; } while (0)
 
@@ -156,7 +158,8 @@ struct gsb200_assembler {
     bool pattern_built = false, assembled = false, any_generic = false;
     i64 ws_limit = 0; void *ws = 0; size_t ws_size = 0;
     gsb200_timings tm;
-    int *d_seg = 0; size_t seg_cap = 0;
+    int *d_seg = 0; size_t seg_cap = 0; std::vector<int> seg_host; size_t seg_used = 0;
+    bool plan_valid = false; i64 plan_limit = 0; size_t ev_used = 0;
 #ifndef GSB200_EMULATE
     std::vector<cudaEvent_t> ev; std::vector<int> ev_tag;   // tag: 0 geometry, 1..3 sweeps, 4 rhs, 5 total-begin, 6 total-end
 #endif
@@ -319,16 +322,27 @@ static int launch_sweep_t(const SweepArgs &A, int nseg, stream_t s, i64 *flops_p
     *flops_per_point = (i64)P1 * (2 * T::NT - n_first<T>() + 2 * P1 * n_has<T>());
 #ifndef GSB200_EMULATE
     if (tma_ok(A, FINAL)) {
-        constexpr int G = P1 / IS, TC = (G <= 2) ? 128 : 64, NST = 3;
-        const size_t smem = (size_t)NST * A.q * T::NIN * TC * sizeof(double) + 2 * NST * sizeof(unsigned long long);
-        if (smem <= 200 * 1024) {
+        constexpr int G = P1 / IS, TC = (G <= 2) ? 128 : 64, NQ = P1;
+        constexpr int MINB_HI = (TC * G <= 128) ? 4 : (TC * G <= 256 ? 2 : 1);
+        const size_t stage = (size_t)(NQ * T::NIN * TC + NQ * P1 * 2) * sizeof(double);
+        const char *env = getenv("GSB200_MINB");
+        const bool hi = env ? atoi(env) > 1 : (TC * G <= 128);
+        // ring depth: as many spans in flight as the shared memory left per resident CTA allows
+        const size_t budget = (size_t)200 * 1024 / (hi ? MINB_HI : 1);
+        const char *envs = getenv("GSB200_NSTAGE");
+        int nstage = (int)std::min<size_t>(envs ? (size_t)atoi(envs) : 8, budget / stage);
+        if (A.q == NQ && nstage >= 2) {
+            const size_t smem = nstage * stage + 2 * nstage * sizeof(unsigned long long);
             const int tiles = (int)((A.ninner + TC - 1) / TC);
             const i64 nouter = A.ncol / A.ninner;
-            auto kfn = k_sweep_tma<P1, T, IS, FINAL, TC, NST, FINAL>;
-            static bool attr_done = false;
-            if (!attr_done) { GSB_TRY(dev_check(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "cudaFuncSetAttribute")); attr_done = true; }
-            kfn<<<dim3((unsigned)(nouter * tiles), 1, nseg), dim3(TC * G), smem, s>>>(A, tiles);
-            note_launch();
+            void (*kfn)(const SweepArgs, const int, const int) = hi ? k_sweep_tma<P1, T, IS, FINAL, TC, FINAL, NQ, MINB_HI>
+                                                                    : k_sweep_tma<P1, T, IS, FINAL, TC, FINAL, NQ, 1>;
+            static std::vector<const void *> attributed;
+            if (std::find(attributed.begin(), attributed.end(), (const void *)kfn) == attributed.end()) {
+                GSB_TRY(dev_check(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "cudaFuncSetAttribute"));
+                attributed.push_back((const void *)kfn);
+            }
+            if (!dry_run()) { kfn<<<dim3((unsigned)(nouter * tiles), 1, nseg), dim3(TC * G), smem, s>>>(A, tiles, nstage); note_launch(); }
             return 0;
         }
     }
@@ -373,7 +387,10 @@ static int upload_segments(gsb200_assembler *a, const std::vector<int> &seg, siz
 {
     // segments of all sweeps of one chunk live in one small device buffer, appended
     if ((*offset_ints + seg.size()) > a->seg_cap) { set_error("segment buffer overflow"); return GSB200_EINVAL; }
-    GSB_TRY(dev_h2d(a->d_seg + *offset_ints, seg.data(), seg.size() * sizeof(int), a->stream));
+    if (dry_run()) {
+        if (a->seg_host.size() < *offset_ints + seg.size()) a->seg_host.resize(*offset_ints + seg.size());
+        std::copy(seg.begin(), seg.end(), a->seg_host.begin() + *offset_ints);
+    }
     *offset_ints += seg.size();
     return 0;
 }
@@ -381,7 +398,10 @@ static int upload_segments(gsb200_assembler *a, const std::vector<int> &seg, siz
 #ifndef GSB200_EMULATE
 static void mark(gsb200_assembler *a, int tag)
 {
-    cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, a->stream); a->ev.push_back(e); a->ev_tag.push_back(tag);
+    if (dry_run()) return;
+    if (a->ev_used == a->ev.size()) { cudaEvent_t e; cudaEventCreate(&e); a->ev.push_back(e); a->ev_tag.push_back(tag); }
+    a->ev_tag[a->ev_used] = tag;
+    cudaEventRecord(a->ev[a->ev_used++], a->stream);
 }
 #else
 static void mark(gsb200_assembler *, int) {}
@@ -396,20 +416,19 @@ static int nseg_for(i64 threads_per_seg, int nfun, int p1)
     return (int)std::max<i64>(1, n);
 }
 
-static int assemble(gsb200_assembler *a)
+static int assemble_pass(gsb200_assembler *a)
 {
     stream_t s = a->stream;
     const int N = a->nfree;
     g_launches = 0;
-#ifndef GSB200_EMULATE
-    for (auto e : a->ev) cudaEventDestroy(e);
-    a->ev.clear(); a->ev_tag.clear();
-#endif
+    a->ev_used = 0;
     memset(a->tm.sweep_bytes, 0, sizeof a->tm.sweep_bytes); memset(a->tm.sweep_flops, 0, sizeof a->tm.sweep_flops);
     a->tm.nchunks = 0;
     mark(a, 5);
-    GSB_TRY(dev_memset(a->d_rhs, 0, sizeof(double) * (size_t)N * a->nrhs, s));
-    if (a->any_generic) GSB_TRY(dev_memset(a->d_values, 0, sizeof(double) * (size_t)std::max<i64>(a->nnz, 1), s));
+    if (!dry_run()) {
+        GSB_TRY(dev_memset(a->d_rhs, 0, sizeof(double) * (size_t)N * a->nrhs, s));
+        if (a->any_generic) GSB_TRY(dev_memset(a->d_values, 0, sizeof(double) * (size_t)std::max<i64>(a->nnz, 1), s));
+    }
 
     const int dim = a->dim, L = dim - 1;
     const int kind = a->form == GSB200_FORM_MASS ? KIND_MASS : (a->form == GSB200_FORM_POISSON ? KIND_SYM : KIND_GEN);
@@ -420,13 +439,15 @@ static int assemble(gsb200_assembler *a)
     else stage_io(kind, 3, &ncD, &no1);
 
     // workspace budget
-    i64 limit = a->ws_limit;
+    i64 limit = a->plan_valid ? a->plan_limit : a->ws_limit;
 #ifndef GSB200_EMULATE
     if (limit <= 0) { size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot); limit = (i64)((fr + a->ws_size) * 0.85); }
 #else
     if (limit <= 0) limit = (i64)1 << 30;
 #endif
+    a->plan_limit = limit;
 
+    size_t segoff = 0;   // every sweep of every chunk gets its own slice of the segment buffer
     for (size_t ip = 0; ip < a->patches.size(); ++ip) {
         PatchDev &P = a->patches[ip];
         if (P.own_hi <= P.own_lo) continue;
@@ -460,7 +481,6 @@ static int assemble(gsb200_assembler *a)
             double *V1 = carve(n0 * Q1 * QLc);
             double *V2 = carve(dim == 3 ? n1 * n0 * QLc : 0);
             const i64 npts = Q0 * Q1 * QLc;
-            size_t segoff = 0;
             ++a->tm.nchunks;
 
             for (int blk = 0; blk < nblocks; ++blk) {
@@ -615,10 +635,29 @@ static int assemble(gsb200_assembler *a)
         }
     }
     mark(a, 6);
+    if (dry_run()) return 0;
     GSB_TRY(dev_last_error("assembly kernels"));
     a->tm.launches = g_launches;
     a->assembled = true;
     return 0;
+}
+
+// The launch sequence (chunks, segments, workspace) is static for a built pattern: the first
+// call walks it once without launching to size the workspace and upload every segment table in
+// one copy; afterwards assemble() only enqueues kernels, so the stream never waits on the host.
+static int assemble(gsb200_assembler *a)
+{
+    if (!a->plan_valid) {
+        g_dry = true;
+        a->seg_host.clear();
+        const int rc = assemble_pass(a);
+        g_dry = false;
+        if (rc) return rc;
+        if (!a->seg_host.empty()) GSB_TRY(dev_h2d(a->d_seg, a->seg_host.data(), a->seg_host.size() * sizeof(int), a->stream));
+        GSB_TRY(dev_sync(a->stream));
+        a->plan_valid = true;
+    }
+    return assemble_pass(a);
 }
 
 static void finish_timings(gsb200_assembler *a)
@@ -626,12 +665,12 @@ static void finish_timings(gsb200_assembler *a)
 #ifndef GSB200_EMULATE
     gsb200_timings &t = a->tm;
     t.geometry_ms = t.rhs_ms = t.total_ms = 0; for (int k = 0; k < 3; ++k) t.sweep_ms[k] = 0;
-    for (size_t i = 0; i + 1 < a->ev.size(); ++i) {
+    for (size_t i = 0; i + 1 < a->ev_used; ++i) {
         float ms = 0; cudaEventElapsedTime(&ms, a->ev[i], a->ev[i + 1]);
         const int tag = a->ev_tag[i];
         if (tag == 0) t.geometry_ms += ms; else if (tag >= 1 && tag <= 3) t.sweep_ms[tag - 1] += ms; else if (tag == 4) t.rhs_ms += ms;
     }
-    if (a->ev.size() >= 2) cudaEventElapsedTime(&t.total_ms, a->ev.front(), a->ev.back());
+    if (a->ev_used >= 2) cudaEventElapsedTime(&t.total_ms, a->ev.front(), a->ev[a->ev_used - 1]);
 #else
     (void)a;
 #endif
@@ -736,7 +775,7 @@ int gsb200_create(const gsb200_problem *pb, int device, gsb200_assembler **out)
         const i64 nt = P.nb * pb->ncomp;
         GSB_LAUNCH(k_pat_preimages, dim3((unsigned)((nt + 127) / 128)), dim3(128), a->stream, P.d_dofmap, nt, pb->nfree, a->d_npre);
     }
-    a->seg_cap = 1 << 16;
+    a->seg_cap = 1 << 20;
     if (!rc) rc = dev_malloc((void **)&a->d_seg, a->seg_cap * sizeof(int));
     if (!rc) rc = dev_sync(a->stream);
     if (rc) { delete a; return rc; }
@@ -757,7 +796,7 @@ int gsb200_set_stream(gsb200_assembler *a, void *cuda_stream)
     return GSB200_OK;
 }
 
-int gsb200_set_workspace_limit(gsb200_assembler *a, int64_t bytes) { if (!a) return GSB200_EINVAL; a->ws_limit = bytes; return GSB200_OK; }
+int gsb200_set_workspace_limit(gsb200_assembler *a, int64_t bytes) { if (!a) return GSB200_EINVAL; a->ws_limit = bytes; a->plan_valid = false; return GSB200_OK; }
 
 int gsb200_build_pattern(gsb200_assembler *a)
 {

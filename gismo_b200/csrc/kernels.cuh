@@ -386,9 +386,11 @@ GSB_DEVICE void owner_load(const FinalArgs &F, const FinalCtx &c, int iL, OwnerC
     oc.base = oc.flag ? F.colptr[oc.gi] : 0;
 }
 
-GSB_DEVICE void final_emit(const FinalArgs &F, const FinalCtx &c, const OwnerCache &oc, int dL, double val)
+// -> position in `values` for the common case (canonical column, free row); slow paths
+// (eliminated row, generic column) are completed here and -1 is returned.
+GSB_DEVICE i64 final_prepare(const FinalArgs &F, const FinalCtx &c, const OwnerCache &oc, int dL, double val)
 {
-    if (!oc.flag) return;
+    if (!oc.flag) return -1;
     const i64 lj = oc.li + (i64)dL * c.nlow + c.dj_low;
     if (oc.flag == 1) {
         const int run = (F.dim == 2) ? (dL + F.p[1]) : ((dL + F.p[2]) * (2 * F.p[1] + 1) + c.r_low);
@@ -396,20 +398,20 @@ GSB_DEVICE void final_emit(const FinalArgs &F, const FinalCtx &c, const OwnerCac
         const unsigned mask = w >> 16;
         if ((mask >> c.bit0) & 1u) {                 // partner row is free: its rank in the column is known
             const int rank = (int)(w & 0xffffu) + popc(mask & ((1u << c.bit0) - 1u));
-            F.values[oc.base + rank] = val;
-            return;
+            return oc.base + rank;
         }
-        if (!F.fixed) return;
+        if (!F.fixed) return -1;
     }
     const int gj = F.dofmap[F.brow * F.nb + lj];
     if (gj >= F.nfree) {                             // eliminated row: by symmetry of the form this is the
         if (F.fixed)                                 // -K(i,j) g_j term of gsSparseSystem.h:1004
             for (int r = 0; r < F.nrhs; ++r) atomic_add(F.rhs + (i64)r * F.nfree + oc.gi, -val * F.fixed[(i64)r * F.nfixed + (gj - F.nfree)]);
-        return;
+        return -1;
     }
     int lo = 0, hi = (int)(F.colptr[oc.gi + 1] - oc.base) - 1;
     while (lo < hi) { const int mid = (lo + hi) >> 1; if (F.inner[oc.base + mid] < gj) lo = mid + 1; else hi = mid; }
     atomic_add(F.values + oc.base + lo, val);
+    return -1;
 }
 
 // ------------------------------------------------------------------------------------
@@ -447,15 +449,16 @@ struct SweepCore {
     }
 
     // one quadrature point: v = the NIN input components, tb = slot-ordered (value, derivative) table row
+    template <bool TBS = false>   // TBS: the table row is in shared memory (plain loads) instead of global/L1
     GSB_MEMBER void point(const double (&v)[NIN], const double2 *tb, int grp)
     {
         double2 bj[P1];
 #pragma unroll
-        for (int js = 0; js < P1; ++js) bj[js] = ld_keep2(tb + js);
+        for (int js = 0; js < P1; ++js) bj[js] = TBS ? tb[js] : ld_keep2(tb + js);
 #pragma unroll
         for (int is = 0; is < IS; ++is) {
             double2 bi;
-            if (IS == P1) bi = bj[is]; else bi = ld_keep2(tb + grp * IS + is);
+            if (IS == P1) bi = bj[is]; else bi = TBS ? tb[grp * IS + is] : ld_keep2(tb + grp * IS + is);
             // z[o][b] = sum over the terms with that (o,b) of B^(a)_owner * in_c
             double z[NOUT][2];
             static_for<0, NT>([&](auto kc) {
@@ -479,7 +482,8 @@ struct SweepCore {
         if (FINAL) {
             OwnerCache &c = oc[FINAL ? is : 0];
             if (c.fun != fi) owner_load(A.fin, fc, fi, c);
-            final_emit(A.fin, fc, c, d, acc[is][js][0]);
+            const i64 pos = final_prepare(A.fin, fc, c, d, acc[is][js][0]);
+            if (pos >= 0) A.fin.values[pos] = acc[is][js][0];
         } else {
             const i64 o0 = ((i64)fi * (2 * A.p + 1) + (d + A.p)) * A.out_ps + obase;
 #pragma unroll
@@ -489,10 +493,9 @@ struct SweepCore {
 
     // functions leaving the span window after element e complete their pairs; a pair is emitted
     // by the segment that owns its OWNER function (x_min <= owner < x_max)
-    GSB_MEMBER void exits(const SweepArgs &A, const FinalCtx &fc, i64 obase, int e, int f0, int grp, int x_min, int x_max)
+    GSB_MEMBER void exits(const SweepArgs &A, const FinalCtx &fc, i64 obase, int nx, int f0, int grp, int x_min, int x_max)
     {
         const int ph = f0 % P1;
-        const int nx = A.nexit[e];
         for (int k = 0; k < nx; ++k) {
             const int x = f0 + k;
             if (x >= x_max) break;                 // later exits only involve owners >= x_max
@@ -503,12 +506,29 @@ struct SweepCore {
                 const int fi = f0 + ((so - ph + P1) % P1);
                 const bool wr = (fi >= x_min) && (fi < x_max);
                 if (fi == x) {
+                    if (FINAL) {
+                        // all slot-table words of the owner's P1 entries are fetched before the first store
+                        OwnerCache &c = oc[FINAL ? is : 0];
+                        if (wr && c.fun != fi) owner_load(A.fin, fc, fi, c);
+                        i64 pos[P1];
 #pragma unroll
-                    for (int js = 0; js < P1; ++js) {
-                        const int fj = f0 + ((js - ph + P1) % P1);
-                        if (wr && fj >= x) emit(A, fc, obase, is, js, fi, fj - fi);
+                        for (int js = 0; js < P1; ++js) {
+                            const int fj = f0 + ((js - ph + P1) % P1);
+                            pos[js] = (wr && fj >= x) ? final_prepare(A.fin, fc, c, fj - fi, acc[is][js][0]) : -1;
+                        }
 #pragma unroll
-                        for (int o = 0; o < NOUT; ++o) acc[is][js][o] = 0.0;
+                        for (int js = 0; js < P1; ++js) {
+                            if (pos[js] >= 0) A.fin.values[pos[js]] = acc[is][js][0];
+                            acc[is][js][0] = 0.0;
+                        }
+                    } else {
+#pragma unroll
+                        for (int js = 0; js < P1; ++js) {
+                            const int fj = f0 + ((js - ph + P1) % P1);
+                            if (wr && fj >= x) emit(A, fc, obase, is, js, fi, fj - fi);
+#pragma unroll
+                            for (int o = 0; o < NOUT; ++o) acc[is][js][o] = 0.0;
+                        }
                     }
                 } else if (fi > x) {
 #pragma unroll
@@ -552,7 +572,7 @@ GSB_GLOBAL void k_sweep(const SweepArgs A)
             for (int c = 0; c < NIN; ++c) v[c] = ld_keep(ine + c * A.in_cs + t * A.in_ts);
             core.point(v, tbe + t * P1, grp);
         }
-        core.exits(A, fc, obase, e, f0, grp, x_min, x_max);
+        core.exits(A, fc, obase, A.nexit[e], f0, grp, x_min, x_max);
     }
 }
 
@@ -580,17 +600,19 @@ GSB_DEVICE void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned lo
 }
 
 // TC columns per CTA, G = P1/IS groups; blockDim.x = TC*G (group = threadIdx.x / TC, warp-uniform).
-// ROWB = true when the q points of a column are contiguous in memory (in_ts == 1, in_is == q):
-// one bulk copy per component; otherwise one per (point, component) row of TC contiguous columns.
-template <int P1, class T, int IS, bool FINAL, int TC, int NSTAGE, bool ROWB>
-GSB_GLOBAL void __launch_bounds__(TC * (P1 / IS)) k_sweep_tma(const SweepArgs A, const int tiles_per_outer)
+// NQ = quadrature points per span (compile time).  ROWB = true when the NQ points of a column are
+// contiguous in memory (in_ts == 1, in_is == NQ): one bulk copy per component; otherwise one per
+// (point, component) row of TC contiguous columns.  Each stage also receives the span's slot-
+// ordered basis table (NQ*P1 double2), so the inner loop touches shared memory only.
+template <int P1, class T, int IS, bool FINAL, int TC, bool ROWB, int NQ, int MINB>
+GSB_GLOBAL void __launch_bounds__(TC * (P1 / IS), MINB) k_sweep_tma(const SweepArgs A, const int tiles_per_outer, const int NSTAGE)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int NIN = T::NIN, G = P1 / IS;
-    const int q = A.q;
-    const int stage_doubles = q * NIN * TC;
+    constexpr int TAB_DOUBLES = NQ * P1 * 2;
+    constexpr int STAGE_DOUBLES = NQ * NIN * TC + TAB_DOUBLES;
     double *sdata = reinterpret_cast<double *>(smem_raw);
-    unsigned long long *full = reinterpret_cast<unsigned long long *>(sdata + (size_t)NSTAGE * stage_doubles);
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(sdata + (size_t)NSTAGE * STAGE_DOUBLES);
     unsigned long long *empty = full + NSTAGE;
     const int tid = threadIdx.x, grp = tid / TC, lcol = tid - grp * TC, warp = tid >> 5, lane = tid & 31;
     constexpr int NWARP = TC * G / 32;
@@ -600,23 +622,25 @@ GSB_GLOBAL void __launch_bounds__(TC * (P1 / IS)) k_sweep_tma(const SweepArgs A,
     const i64 inner0 = (i64)(blockIdx.x - outer * tiles_per_outer) * TC;
     const int ncols = (int)((A.ninner - inner0) < TC ? (A.ninner - inner0) : TC);
     const i64 inner = inner0 + lcol;
-    const bool active_col = lcol < ncols;
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, NWARP); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     const double *tile = A.in + outer * A.in_os + inner0 * A.in_is;
-    const unsigned row_bytes = (unsigned)(ncols * (ROWB ? q : 1) * sizeof(double));
-    const int nrows = ROWB ? NIN : q * NIN;
+    const unsigned row_bytes = (unsigned)(ncols * (ROWB ? NQ : 1) * sizeof(double));
+    constexpr int NROWS = ROWB ? NIN : NQ * NIN;
     auto issue = [&](int e) {   // executed by warp 0: fill stage (e - e_begin) % NSTAGE with span e
         const int s = (e - e_begin) % NSTAGE;
-        double *dst = sdata + (size_t)s * stage_doubles;
+        double *dst = sdata + (size_t)s * STAGE_DOUBLES;
         const double *src = tile + (i64)(e - A.e_in0) * A.in_es;
-        if (lane == 0) mbar_expect_tx(full + s, row_bytes * nrows);
+        if (lane == 0) {
+            mbar_expect_tx(full + s, row_bytes * NROWS + TAB_DOUBLES * 8);
+            bulk_g2s(dst + NQ * NIN * TC, A.tab + (i64)e * NQ * P1, TAB_DOUBLES * 8, full + s);
+        }
         __syncwarp();
-        for (int r = lane; r < nrows; r += 32) {
-            if (ROWB) bulk_g2s(dst + (size_t)r * TC * q, src + (i64)r * A.in_cs, row_bytes, full + s);
+        for (int r = lane; r < NROWS; r += 32) {
+            if (ROWB) bulk_g2s(dst + (size_t)r * TC * NQ, src + (i64)r * A.in_cs, row_bytes, full + s);
             else { const int t = r / NIN, c = r - t * NIN; bulk_g2s(dst + (size_t)r * TC, src + (i64)c * A.in_cs + (i64)t * A.in_ts, row_bytes, full + s); }
         }
     };
@@ -625,23 +649,44 @@ GSB_GLOBAL void __launch_bounds__(TC * (P1 / IS)) k_sweep_tma(const SweepArgs A,
 
     FinalCtx fc;
     i64 obase = 0;
-    bool live = active_col;
+    bool live = lcol < ncols;
     if (FINAL) { if (live) live = final_init(A.fin, outer, inner, fc); }
     else obase = outer * A.out_os + (inner / A.out_bq) * A.out_bs + (inner % A.out_bq) * A.out_is;
     SweepCore<P1, T, IS, FINAL> core;
     core.zero();
+    int f0 = A.first[e_begin], nx = A.nexit[e_begin];
     for (int e = e_begin; e < e_end; ++e) {
         const int it = e - e_begin, s = it % NSTAGE;
         const unsigned par = (unsigned)((it / NSTAGE) & 1);
+        // next span's window data: fetched now, consumed one iteration later
+        const int f0n = (e + 1 < e_end) ? A.first[e + 1] : 0, nxn = (e + 1 < e_end) ? A.nexit[e + 1] : 0;
         mbar_wait(full + s, par);
         if (live) {
-            const double *sd = sdata + (size_t)s * stage_doubles;
-            const double2 *tbe = A.tab + (i64)e * q * P1;
-            for (int t = 0; t < q; ++t) {
-                double v[NIN];
+            const double *sd = sdata + (size_t)s * STAGE_DOUBLES;
+            const double2 *tbs = reinterpret_cast<const double2 *>(sd + NQ * NIN * TC);
+            if (ROWB && (NQ % 2 == 0)) {
+                double vv[NIN][NQ];       // all points of the span in two-double shared-memory loads
 #pragma unroll
-                for (int c = 0; c < NIN; ++c) v[c] = ROWB ? sd[((size_t)c * TC + lcol) * q + t] : sd[((size_t)t * NIN + c) * TC + lcol];
-                core.point(v, tbe + t * P1, grp);
+                for (int c = 0; c < NIN; ++c) {
+                    const double2 *p2 = reinterpret_cast<const double2 *>(sd + ((size_t)c * TC + lcol) * NQ);
+#pragma unroll
+                    for (int h = 0; h < NQ / 2; ++h) { const double2 w2 = p2[h]; vv[c][2 * h] = w2.x; vv[c][2 * h + 1] = w2.y; }
+                }
+#pragma unroll
+                for (int t = 0; t < NQ; ++t) {
+                    double v[NIN];
+#pragma unroll
+                    for (int c = 0; c < NIN; ++c) v[c] = vv[c][t];
+                    core.template point<true>(v, tbs + t * P1, grp);
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < NQ; ++t) {
+                    double v[NIN];
+#pragma unroll
+                    for (int c = 0; c < NIN; ++c) v[c] = ROWB ? sd[((size_t)c * TC + lcol) * NQ + t] : sd[((size_t)t * NIN + c) * TC + lcol];
+                    core.template point<true>(v, tbs + t * P1, grp);
+                }
             }
         }
         __syncwarp();
@@ -650,7 +695,8 @@ GSB_GLOBAL void __launch_bounds__(TC * (P1 / IS)) k_sweep_tma(const SweepArgs A,
             mbar_wait(empty + s, par);
             issue(e + NSTAGE);
         }
-        if (live) core.exits(A, fc, obase, e, A.first[e], grp, x_min, x_max);
+        if (live) core.exits(A, fc, obase, nx, f0, grp, x_min, x_max);
+        f0 = f0n; nx = nxn;
     }
 }
 #endif

@@ -26,9 +26,10 @@ void set_error(const char *fmt, ...);
 #define GSB_HD __host__ __device__ __forceinline__
 #define GSB_MEMBER __device__ __forceinline__
 #define GSB_LAUNCH(kernel, grid, block, stream, ...) \
-    do { kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__); gsb::note_launch(); } while (0)
+    do { if (!gsb::dry_run()) { kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__); gsb::note_launch(); } } while (0)
 namespace gsb {
 void note_launch();
+bool dry_run();   // planning pass of assemble(): walk the launch sequence without launching
 typedef cudaStream_t stream_t;
 typedef cudaEvent_t event_t;
 inline int dev_check(cudaError_t e, const char *what) {
@@ -67,7 +68,7 @@ struct double2 { double x, y; };
 static inline double2 make_double2(double a, double b) { double2 r; r.x = a; r.y = b; return r; }
 static gsb_dim3 blockIdx, threadIdx, blockDim, gridDim;
 #define GSB_LAUNCH(kernel, grid, block, stream, ...)                                         \
-    do { gridDim = gsb_dim3(grid); blockDim = gsb_dim3(block);                               \
+    do { if (gsb::dry_run()) break; gridDim = gsb_dim3(grid); blockDim = gsb_dim3(block);     \
          for (unsigned bz_ = 0; bz_ < gridDim.z; ++bz_) for (unsigned by_ = 0; by_ < gridDim.y; ++by_) \
          for (unsigned bx_ = 0; bx_ < gridDim.x; ++bx_) for (unsigned tz_ = 0; tz_ < blockDim.z; ++tz_) \
          for (unsigned ty_ = 0; ty_ < blockDim.y; ++ty_) for (unsigned tx_ = 0; tx_ < blockDim.x; ++tx_) { \
@@ -75,6 +76,7 @@ static gsb_dim3 blockIdx, threadIdx, blockDim, gridDim;
          gsb::note_launch(); } while (0)
 namespace gsb {
 void note_launch();
+bool dry_run();
 typedef int stream_t;
 typedef int event_t;
 inline int dev_malloc(void **p, size_t n) { *p = std::calloc(n ? n : 1, 1); return *p ? 0 : -5; }
