@@ -7,6 +7,7 @@
 #include <vector>
 #ifndef GSB200_EMULATE
 #include <cub/device/device_scan.cuh>
+#include <cuda.h>   // CUtensorMap + enums only; the encoder is fetched with cudaGetDriverEntryPoint
 #endif
 
 namespace gsb {
@@ -299,6 +300,39 @@ constexpr int pick_is(int P1, int NOUT)
 template <class T> constexpr int n_has() { int n = 0; for (int o = 0; o < T::NOUT; ++o) for (int b = 0; b < 2; ++b) if (T::has(o, b)) ++n; return n; }
 template <class T> constexpr int n_first() { int n = 0; for (int k = 0; k < T::NT; ++k) if (T::first(k)) ++n; return n; }
 
+// Host description of a sweep's input array as a (<=5-D) tensor for tiled TMA; dims fastest first.
+// box_kind per dim: 0 -> 1, 1 -> TC (column tile), 2 -> NQ (points of a span), 3 -> NIN (all components)
+struct TmapDesc { int rank; unsigned long long dims[5]; unsigned long long strides[4]; int box_kind[5]; bool valid; };
+
+#ifndef GSB200_EMULATE
+static bool encode_tmap(TensorMapBlob *out, const void *base, const TmapDesc &d, int TC, int NQ, int NIN)
+{
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn fn = 0; static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = 0; cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess) fn = (encode_fn)p;
+    }
+    if (!fn || !d.valid || ((size_t)base & 15)) return false;
+    cuuint64_t dims[5], strides[4]; cuuint32_t box[5], estr[5];
+    for (int i = 0; i < d.rank; ++i) {
+        dims[i] = d.dims[i]; estr[i] = 1;
+        box[i] = d.box_kind[i] == 1 ? TC : d.box_kind[i] == 2 ? NQ : d.box_kind[i] == 3 ? NIN : 1;
+        if (box[i] > 256 || dims[i] == 0 || dims[i] > 0xffffffffull) return false;
+        if (i && ((d.strides[i - 1] & 15) || d.strides[i - 1] >= (1ull << 40))) return false;
+        if (i) strides[i - 1] = d.strides[i - 1];
+    }
+    if ((box[0] * 8) & 15) return false;
+    static_assert(sizeof(CUtensorMap) == sizeof(TensorMapBlob), "tensor map size");
+    return fn((CUtensorMap *)out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, d.rank, const_cast<void *>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+#endif
+
 // Can the TMA-pipelined variant serve this sweep?  cp.async.bulk needs 16-byte aligned
 // addresses and sizes, i.e. even strides/extents in doubles; otherwise the generic kernel runs.
 static bool tma_ok(const SweepArgs &A, bool final_stage)
@@ -316,15 +350,19 @@ static bool tma_ok(const SweepArgs &A, bool final_stage)
 }
 
 template <int P1, class T, bool FINAL>
-static int launch_sweep_t(const SweepArgs &A, int nseg, stream_t s, i64 *flops_per_point)
+static int launch_sweep_t(const SweepArgs &A, int nseg, stream_t s, i64 *flops_per_point, const TmapDesc &td)
 {
     constexpr int IS = pick_is(P1, T::NOUT);
     *flops_per_point = (i64)P1 * (2 * T::NT - n_first<T>() + 2 * P1 * n_has<T>());
 #ifndef GSB200_EMULATE
-    if (tma_ok(A, FINAL)) {
+    constexpr int G0 = P1 / IS, TC0 = (G0 <= 2) ? 128 : 64;
+    TensorMapBlob tmap; memset(&tmap, 0, sizeof tmap);
+    const bool no_tmap = getenv("GSB200_NO_TMAP") != 0 || getenv("GSB200_NO_TMA") != 0;
+    const bool use_tmap = !no_tmap && A.q == P1 && encode_tmap(&tmap, A.in, td, TC0, P1, T::NIN);
+    if (use_tmap || tma_ok(A, FINAL)) {
         constexpr int G = P1 / IS, TC = (G <= 2) ? 128 : 64, NQ = P1;
         constexpr int MINB_HI = (TC * G <= 128) ? 4 : (TC * G <= 256 ? 2 : 1);
-        const size_t stage = (size_t)(NQ * T::NIN * TC + NQ * P1 * 2) * sizeof(double);
+        const size_t stage = (size_t)((NQ * T::NIN * TC + NQ * P1 * 2 + 15) / 16 * 16) * sizeof(double);
         const char *env = getenv("GSB200_MINB");
         const bool hi = env ? atoi(env) > 1 : (TC * G <= 128);
         // ring depth: as many spans in flight as the shared memory left per resident CTA allows
@@ -335,14 +373,14 @@ static int launch_sweep_t(const SweepArgs &A, int nseg, stream_t s, i64 *flops_p
             const size_t smem = nstage * stage + 2 * nstage * sizeof(unsigned long long);
             const int tiles = (int)((A.ninner + TC - 1) / TC);
             const i64 nouter = A.ncol / A.ninner;
-            void (*kfn)(const SweepArgs, const int, const int) = hi ? k_sweep_tma<P1, T, IS, FINAL, TC, FINAL, NQ, MINB_HI>
+            void (*kfn)(const SweepArgs, const int, const int, const TensorMapBlob, const int) = hi ? k_sweep_tma<P1, T, IS, FINAL, TC, FINAL, NQ, MINB_HI>
                                                                     : k_sweep_tma<P1, T, IS, FINAL, TC, FINAL, NQ, 1>;
             static std::vector<const void *> attributed;
             if (std::find(attributed.begin(), attributed.end(), (const void *)kfn) == attributed.end()) {
                 GSB_TRY(dev_check(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "cudaFuncSetAttribute"));
                 attributed.push_back((const void *)kfn);
             }
-            if (!dry_run()) { kfn<<<dim3((unsigned)(nouter * tiles), 1, nseg), dim3(TC * G), smem, s>>>(A, tiles, nstage); note_launch(); }
+            if (!dry_run()) { kfn<<<dim3((unsigned)(nouter * tiles), 1, nseg), dim3(TC * G), smem, s>>>(A, tiles, nstage, tmap, use_tmap ? 1 : 0); note_launch(); }
             return 0;
         }
     }
@@ -353,26 +391,26 @@ static int launch_sweep_t(const SweepArgs &A, int nseg, stream_t s, i64 *flops_p
     return 0;
 }
 template <class T, bool FINAL>
-static int launch_sweep(int P1, const SweepArgs &A, int nseg, stream_t s, i64 *fpp)
+static int launch_sweep(int P1, const SweepArgs &A, int nseg, stream_t s, i64 *fpp, const TmapDesc &td)
 {
     switch (P1) {
-    case 2: return launch_sweep_t<2, T, FINAL>(A, nseg, s, fpp);
-    case 3: return launch_sweep_t<3, T, FINAL>(A, nseg, s, fpp);
-    case 4: return launch_sweep_t<4, T, FINAL>(A, nseg, s, fpp);
-    case 5: return launch_sweep_t<5, T, FINAL>(A, nseg, s, fpp);
+    case 2: return launch_sweep_t<2, T, FINAL>(A, nseg, s, fpp, td);
+    case 3: return launch_sweep_t<3, T, FINAL>(A, nseg, s, fpp, td);
+    case 4: return launch_sweep_t<4, T, FINAL>(A, nseg, s, fpp, td);
+    case 5: return launch_sweep_t<5, T, FINAL>(A, nseg, s, fpp, td);
     default: set_error("degree %d not supported by the sweep kernels (1..4)", P1 - 1); return GSB200_EUNSUPPORTED;
     }
 }
 
 enum { KIND_SYM = 0, KIND_GEN = 1, KIND_MASS = 2 };
 // stage: 0 = first of 3-D, 1 = middle of 3-D, 2 = last; 3 = first of 2-D
-static int dispatch_sweep(int kind, int stage, int P1, const SweepArgs &A, int nseg, stream_t s, i64 *fpp)
+static int dispatch_sweep(int kind, int stage, int P1, const SweepArgs &A, int nseg, stream_t s, i64 *fpp, const TmapDesc &td)
 {
-    if (kind == KIND_MASS) return stage == 2 ? launch_sweep<TMass, true>(P1, A, nseg, s, fpp) : launch_sweep<TMass, false>(P1, A, nseg, s, fpp);
-    if (stage == 2) return launch_sweep<TLast, true>(P1, A, nseg, s, fpp);
-    if (stage == 0) return kind == KIND_SYM ? launch_sweep<T3SymS1, false>(P1, A, nseg, s, fpp) : launch_sweep<T3GenS1, false>(P1, A, nseg, s, fpp);
-    if (stage == 1) return kind == KIND_SYM ? launch_sweep<T3SymS2, false>(P1, A, nseg, s, fpp) : launch_sweep<T3GenS2, false>(P1, A, nseg, s, fpp);
-    return kind == KIND_SYM ? launch_sweep<T2SymS1, false>(P1, A, nseg, s, fpp) : launch_sweep<T2GenS1, false>(P1, A, nseg, s, fpp);
+    if (kind == KIND_MASS) return stage == 2 ? launch_sweep<TMass, true>(P1, A, nseg, s, fpp, td) : launch_sweep<TMass, false>(P1, A, nseg, s, fpp, td);
+    if (stage == 2) return launch_sweep<TLast, true>(P1, A, nseg, s, fpp, td);
+    if (stage == 0) return kind == KIND_SYM ? launch_sweep<T3SymS1, false>(P1, A, nseg, s, fpp, td) : launch_sweep<T3GenS1, false>(P1, A, nseg, s, fpp, td);
+    if (stage == 1) return kind == KIND_SYM ? launch_sweep<T3SymS2, false>(P1, A, nseg, s, fpp, td) : launch_sweep<T3GenS2, false>(P1, A, nseg, s, fpp, td);
+    return kind == KIND_SYM ? launch_sweep<T2SymS1, false>(P1, A, nseg, s, fpp, td) : launch_sweep<T2GenS1, false>(P1, A, nseg, s, fpp, td);
 }
 static void stage_io(int kind, int stage, int *nin, int *nout)
 {
@@ -546,7 +584,8 @@ static int assemble_pass(gsb200_assembler *a)
                         std::vector<int> seg = make_segments(d0, 0, d0.nfun, nseg);
                         A.seg = a->d_seg + segoff; GSB_TRY(upload_segments(a, seg, &segoff));
                         mark(a, 1);
-                        GSB_TRY(dispatch_sweep(kind, 0, d0.p + 1, A, (int)seg.size() / 4, s, &fpp));
+                        { TmapDesc td; memset(&td, 0, sizeof td); td.valid = true; td.rank = 3; td.dims[0] = (unsigned long long)(Q1 * QLc); td.dims[1] = (unsigned long long)(Q0); td.dims[2] = (unsigned long long)(ncD); td.strides[0] = 8ull * (unsigned long long)(Q1 * QLc); td.strides[1] = 8ull * (unsigned long long)(npts); td.box_kind[0] = 1; td.box_kind[1] = 2; td.box_kind[2] = 3; A.tm_rank = 3; A.tm_dim_inner = 0; A.tm_dim_e = 1; A.tm_e_mul = d0.q; A.tm_dim_outer = -1;
+                        GSB_TRY(dispatch_sweep(kind, 0, d0.p + 1, A, (int)seg.size() / 4, s, &fpp, td)); }
                         stage_io(kind, 0, &nin, &nout); account(0, A, seg, fpp, nin, nout, NI0);
                     }
                     {   // S2: direction 1
@@ -558,7 +597,8 @@ static int assemble_pass(gsb200_assembler *a)
                         std::vector<int> seg = make_segments(d1, 0, d1.nfun, nseg);
                         A.seg = a->d_seg + segoff; GSB_TRY(upload_segments(a, seg, &segoff));
                         mark(a, 2);
-                        GSB_TRY(dispatch_sweep(kind, 1, d1.p + 1, A, (int)seg.size() / 4, s, &fpp));
+                        { TmapDesc td; memset(&td, 0, sizeof td); td.valid = true; td.rank = 4; td.dims[0] = (unsigned long long)(QLc); td.dims[1] = (unsigned long long)(Q1); td.dims[2] = (unsigned long long)(NI0); td.dims[3] = (unsigned long long)(no1); td.strides[0] = 8ull * (unsigned long long)(QLc); td.strides[1] = 8ull * (unsigned long long)(Q1 * QLc); td.strides[2] = 8ull * (unsigned long long)(NI0 * Q1 * QLc); td.box_kind[0] = 1; td.box_kind[1] = 2; td.box_kind[2] = 0; td.box_kind[3] = 3; A.tm_rank = 4; A.tm_dim_inner = 0; A.tm_dim_e = 1; A.tm_e_mul = d1.q; A.tm_dim_outer = 2;
+                        GSB_TRY(dispatch_sweep(kind, 1, d1.p + 1, A, (int)seg.size() / 4, s, &fpp, td)); }
                         stage_io(kind, 1, &nin, &nout); account(1, A, seg, fpp, nin, nout, NI1);
                     }
                     {   // S3: direction 2, scatter into the CSC arrays
@@ -569,7 +609,8 @@ static int assemble_pass(gsb200_assembler *a)
                         std::vector<int> seg = make_segments(dL, x_lo, x_hi, nseg);
                         A.seg = a->d_seg + segoff; GSB_TRY(upload_segments(a, seg, &segoff));
                         mark(a, 3);
-                        GSB_TRY(dispatch_sweep(kind, 2, dL.p + 1, A, (int)seg.size() / 4, s, &fpp));
+                        { TmapDesc td; memset(&td, 0, sizeof td); td.valid = true; td.rank = 5; td.dims[0] = (unsigned long long)(dL.q); td.dims[1] = (unsigned long long)(NI0); td.dims[2] = (unsigned long long)(ELc); td.dims[3] = (unsigned long long)(NI1); td.dims[4] = (unsigned long long)(no2); td.strides[0] = 8ull * (unsigned long long)(dL.q); td.strides[1] = 8ull * (unsigned long long)(NI0 * dL.q); td.strides[2] = 8ull * (unsigned long long)((i64)ELc * NI0 * dL.q); td.strides[3] = 8ull * (unsigned long long)(NI1 * ELc * NI0 * dL.q); td.box_kind[0] = 2; td.box_kind[1] = 1; td.box_kind[2] = 0; td.box_kind[3] = 0; td.box_kind[4] = 3; A.tm_rank = 5; A.tm_dim_inner = 1; A.tm_dim_e = 2; A.tm_e_mul = 1; A.tm_dim_outer = 3;
+                        GSB_TRY(dispatch_sweep(kind, 2, dL.p + 1, A, (int)seg.size() / 4, s, &fpp, td)); }
                         stage_io(kind, 2, &nin, &nout); account(2, A, seg, fpp, nin, nout, (i64)(x_hi - x_lo) * (2 * dL.p + 1));
                     }
                 } else {
@@ -582,7 +623,8 @@ static int assemble_pass(gsb200_assembler *a)
                         std::vector<int> seg = make_segments(d0, 0, d0.nfun, nseg);
                         A.seg = a->d_seg + segoff; GSB_TRY(upload_segments(a, seg, &segoff));
                         mark(a, 1);
-                        GSB_TRY(dispatch_sweep(kind, 3, d0.p + 1, A, (int)seg.size() / 4, s, &fpp));
+                        { TmapDesc td; memset(&td, 0, sizeof td); td.valid = true; td.rank = 3; td.dims[0] = (unsigned long long)(QLc); td.dims[1] = (unsigned long long)(Q0); td.dims[2] = (unsigned long long)(ncD); td.strides[0] = 8ull * (unsigned long long)(QLc); td.strides[1] = 8ull * (unsigned long long)(npts); td.box_kind[0] = 1; td.box_kind[1] = 2; td.box_kind[2] = 3; A.tm_rank = 3; A.tm_dim_inner = 0; A.tm_dim_e = 1; A.tm_e_mul = d0.q; A.tm_dim_outer = -1;
+                        GSB_TRY(dispatch_sweep(kind, 3, d0.p + 1, A, (int)seg.size() / 4, s, &fpp, td)); }
                         stage_io(kind, 3, &nin, &nout); account(0, A, seg, fpp, nin, nout, NI0);
                     }
                     {   // S2: direction 1, scatter
@@ -593,7 +635,8 @@ static int assemble_pass(gsb200_assembler *a)
                         std::vector<int> seg = make_segments(dL, x_lo, x_hi, nseg);
                         A.seg = a->d_seg + segoff; GSB_TRY(upload_segments(a, seg, &segoff));
                         mark(a, 2);
-                        GSB_TRY(dispatch_sweep(kind, 2, dL.p + 1, A, (int)seg.size() / 4, s, &fpp));
+                        { TmapDesc td; memset(&td, 0, sizeof td); td.valid = true; td.rank = 4; td.dims[0] = (unsigned long long)(dL.q); td.dims[1] = (unsigned long long)(NI0); td.dims[2] = (unsigned long long)(ELc); td.dims[3] = (unsigned long long)(no1); td.strides[0] = 8ull * (unsigned long long)(dL.q); td.strides[1] = 8ull * (unsigned long long)(NI0 * dL.q); td.strides[2] = 8ull * (unsigned long long)((i64)ELc * NI0 * dL.q); td.box_kind[0] = 2; td.box_kind[1] = 1; td.box_kind[2] = 0; td.box_kind[3] = 3; A.tm_rank = 4; A.tm_dim_inner = 1; A.tm_dim_e = 2; A.tm_e_mul = 1; A.tm_dim_outer = -1;
+                        GSB_TRY(dispatch_sweep(kind, 2, dL.p + 1, A, (int)seg.size() / 4, s, &fpp, td)); }
                         stage_io(kind, 2, &nin, &nout); account(1, A, seg, fpp, nin, nout, (i64)(x_hi - x_lo) * (2 * dL.p + 1));
                     }
                 }

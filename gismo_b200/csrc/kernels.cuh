@@ -425,6 +425,8 @@ struct SweepArgs {
     i64 in_cs, in_es, in_ts, in_os, in_is; int e_in0;          // input strides: comp, element, point, outer, inner
     i64 out_cs, out_ps, out_os, out_bs, out_is; int out_bq;    // output: comp, pair, outer, block, inner
     i64 ncol; i64 ninner;
+    // tensor-map TMA variant: which box coordinate carries the tile start, the span, the outer index
+    int tm_rank, tm_dim_inner, tm_dim_e, tm_e_mul, tm_dim_outer;
     FinalArgs fin;
 };
 
@@ -599,18 +601,35 @@ GSB_DEVICE void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned lo
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// One tiled-TMA operation (cp.async.bulk.tensor) brings the whole [NIN x NQ x TC] box of a span.
+GSB_DEVICE void tma_box_g2s(void *dst, const void *tmap, const int (&c)[5], int rank, unsigned long long *bar)
+{
+    const unsigned d = smem_u32(dst), b = smem_u32(bar);
+    if (rank == 3)
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                     ::"r"(d), "l"(tmap), "r"(b), "r"(c[0]), "r"(c[1]), "r"(c[2]) : "memory");
+    else if (rank == 4)
+        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                     ::"r"(d), "l"(tmap), "r"(b), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]) : "memory");
+    else
+        asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                     ::"r"(d), "l"(tmap), "r"(b), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]) : "memory");
+}
+struct alignas(64) TensorMapBlob { unsigned char bytes[128]; };   // CUtensorMap, passed by value (__grid_constant__)
+
 // TC columns per CTA, G = P1/IS groups; blockDim.x = TC*G (group = threadIdx.x / TC, warp-uniform).
 // NQ = quadrature points per span (compile time).  ROWB = true when the NQ points of a column are
 // contiguous in memory (in_ts == 1, in_is == NQ): one bulk copy per component; otherwise one per
 // (point, component) row of TC contiguous columns.  Each stage also receives the span's slot-
 // ordered basis table (NQ*P1 double2), so the inner loop touches shared memory only.
 template <int P1, class T, int IS, bool FINAL, int TC, bool ROWB, int NQ, int MINB>
-GSB_GLOBAL void __launch_bounds__(TC * (P1 / IS), MINB) k_sweep_tma(const SweepArgs A, const int tiles_per_outer, const int NSTAGE)
+GSB_GLOBAL void __launch_bounds__(TC * (P1 / IS), MINB) k_sweep_tma(const SweepArgs A, const int tiles_per_outer, const int NSTAGE,
+                                                                    const __grid_constant__ TensorMapBlob tmap, const int use_tmap)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int NIN = T::NIN, G = P1 / IS;
     constexpr int TAB_DOUBLES = NQ * P1 * 2;
-    constexpr int STAGE_DOUBLES = NQ * NIN * TC + TAB_DOUBLES;
+    constexpr int STAGE_DOUBLES = (NQ * NIN * TC + TAB_DOUBLES + 15) / 16 * 16;   // 128-byte multiple (TMA destination alignment)
     double *sdata = reinterpret_cast<double *>(smem_raw);
     unsigned long long *full = reinterpret_cast<unsigned long long *>(sdata + (size_t)NSTAGE * STAGE_DOUBLES);
     unsigned long long *empty = full + NSTAGE;
@@ -634,6 +653,18 @@ GSB_GLOBAL void __launch_bounds__(TC * (P1 / IS), MINB) k_sweep_tma(const SweepA
         const int s = (e - e_begin) % NSTAGE;
         double *dst = sdata + (size_t)s * STAGE_DOUBLES;
         const double *src = tile + (i64)(e - A.e_in0) * A.in_es;
+        if (use_tmap) {       // one box per span (out-of-range columns are zero-filled and still counted)
+            if (lane == 0) {
+                mbar_expect_tx(full + s, NQ * NIN * TC * 8 + TAB_DOUBLES * 8);
+                bulk_g2s(dst + NQ * NIN * TC, A.tab + (i64)e * NQ * P1, TAB_DOUBLES * 8, full + s);
+                int c[5] = {0, 0, 0, 0, 0};
+                c[A.tm_dim_inner] = (int)inner0;
+                c[A.tm_dim_e] = (e - A.e_in0) * A.tm_e_mul;
+                if (A.tm_dim_outer >= 0) c[A.tm_dim_outer] = (int)outer;
+                tma_box_g2s(dst, &tmap, c, A.tm_rank, full + s);
+            }
+            return;
+        }
         if (lane == 0) {
             mbar_expect_tx(full + s, row_bytes * NROWS + TAB_DOUBLES * 8);
             bulk_g2s(dst + NQ * NIN * TC, A.tab + (i64)e * NQ * P1, TAB_DOUBLES * 8, full + s);
@@ -641,7 +672,7 @@ GSB_GLOBAL void __launch_bounds__(TC * (P1 / IS), MINB) k_sweep_tma(const SweepA
         __syncwarp();
         for (int r = lane; r < NROWS; r += 32) {
             if (ROWB) bulk_g2s(dst + (size_t)r * TC * NQ, src + (i64)r * A.in_cs, row_bytes, full + s);
-            else { const int t = r / NIN, c = r - t * NIN; bulk_g2s(dst + (size_t)r * TC, src + (i64)c * A.in_cs + (i64)t * A.in_ts, row_bytes, full + s); }
+            else { const int c = r / NQ, t = r - c * NQ; bulk_g2s(dst + (size_t)r * TC, src + (i64)c * A.in_cs + (i64)t * A.in_ts, row_bytes, full + s); }
         }
     };
     if (warp == 0)
@@ -684,7 +715,7 @@ GSB_GLOBAL void __launch_bounds__(TC * (P1 / IS), MINB) k_sweep_tma(const SweepA
                 for (int t = 0; t < NQ; ++t) {
                     double v[NIN];
 #pragma unroll
-                    for (int c = 0; c < NIN; ++c) v[c] = ROWB ? sd[((size_t)c * TC + lcol) * NQ + t] : sd[((size_t)t * NIN + c) * TC + lcol];
+                    for (int c = 0; c < NIN; ++c) v[c] = ROWB ? sd[((size_t)c * TC + lcol) * NQ + t] : sd[((size_t)c * NQ + t) * TC + lcol];
                     core.template point<true>(v, tbs + t * P1, grp);
                 }
             }
