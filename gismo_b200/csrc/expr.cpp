@@ -30,7 +30,7 @@ struct Parser {
     // one entry per value currently on the evaluation stack: where its code starts and, if it
     // is a compile-time constant, its value (constant sub-expressions such as 3*pi^2 are folded
     // so the device interpreter does not evaluate pow() at every quadrature point)
-    struct Item { size_t start; bool is_const; double value; };
+    struct Item { size_t start; bool is_const; double value; bool pi_scaled; size_t pi_mul_at; std::vector<int32_t> rest; };
     std::vector<Item> items;
 
     explicit Parser(const char *str) : s(str), depth(0), maxdepth(0) {}
@@ -42,6 +42,7 @@ struct Parser {
         case GSB200_OP_TAN: return std::tan(a); case GSB200_OP_EXP: return std::exp(a); case GSB200_OP_LOG: return std::log(a);
         case GSB200_OP_SQRT: return std::sqrt(a); case GSB200_OP_ABS: return std::fabs(a); case GSB200_OP_TANH: return std::tanh(a);
         case GSB200_OP_SINH: return std::sinh(a); case GSB200_OP_COSH: return std::cosh(a); case GSB200_OP_SQR: return a * a;
+        case GSB200_OP_SINPI: return std::sin(3.14159265358979323846 * a); case GSB200_OP_COSPI: return std::cos(3.14159265358979323846 * a);
         }
         return NAN;
     }
@@ -61,20 +62,38 @@ struct Parser {
     void emit(int op) {
         const bool leaf = op == GSB200_OP_X || op == GSB200_OP_Y || op == GSB200_OP_Z;
         const bool binary = op == GSB200_OP_ADD || op == GSB200_OP_SUB || op == GSB200_OP_MUL || op == GSB200_OP_DIV || op == GSB200_OP_POW;
-        if (leaf) { Item it = {ops.size(), false, 0.0}; items.push_back(it); ops.push_back(op); return; }
+        if (leaf) { Item it = {ops.size(), false, 0.0, false, 0, std::vector<int32_t>()}; items.push_back(it); ops.push_back(op); return; }
         if (binary) {
             Item b = items.back(); items.pop_back();
             Item &a = items.back();
             if (a.is_const && b.is_const) { a.value = apply2(op, a.value, b.value); ops.resize(a.start); raw_const(a.value); return; }
-            if (op == GSB200_OP_POW && b.is_const && b.value == 2.0) { ops.resize(b.start); ops.push_back(GSB200_OP_SQR); a.is_const = false; return; }
-            a.is_const = false; ops.push_back(op); return;
+            if (op == GSB200_OP_POW && b.is_const && b.value == 2.0) { ops.resize(b.start); ops.push_back(GSB200_OP_SQR); a.is_const = false; a.pi_scaled = false; return; }
+            const double PI = 3.14159265358979323846264338328;
+            if (op == GSB200_OP_MUL && (a.is_const != b.is_const) && (a.is_const ? a.value : b.value) == PI) {
+                // remember how to strip the factor pi again should sin()/cos() be applied to this product
+                std::vector<int32_t> rest;
+                if (a.is_const) rest.assign(ops.begin() + b.start, ops.end());       // pi * E : E follows the constant
+                else rest.assign(ops.begin() + a.start, ops.begin() + b.start);       // E * pi
+                a.pi_scaled = true; a.pi_mul_at = a.start; a.rest = rest;
+                a.is_const = false; ops.push_back(op); return;
+            }
+            a.is_const = false; a.pi_scaled = false; ops.push_back(op); return;
         }
         Item &a = items.back();   // unary
         if (a.is_const) { a.value = apply1(op, a.value); ops.resize(a.start); raw_const(a.value); return; }
+        if ((op == GSB200_OP_SIN || op == GSB200_OP_COS) && a.pi_scaled) {
+            // sin(pi*E): drop the multiplication by pi and use the range-reduction-free sinpi/cospi
+            ops.resize(a.pi_mul_at);
+            ops.insert(ops.end(), a.rest.begin(), a.rest.end());
+            ops.push_back(op == GSB200_OP_SIN ? GSB200_OP_SINPI : GSB200_OP_COSPI);
+            a.pi_scaled = false;
+            return;
+        }
+        a.pi_scaled = false;
         ops.push_back(op);
     }
     void emit_const(double v) {
-        Item it = {ops.size(), true, v}; items.push_back(it);
+        Item it = {ops.size(), true, v, false, 0, std::vector<int32_t>()}; items.push_back(it);
         raw_const(v); push(1);
     }
     bool expr() {

@@ -357,7 +357,11 @@ static int launch_sweep_t(const SweepArgs &A, int nseg, stream_t s, i64 *flops_p
 #ifndef GSB200_EMULATE
     constexpr int G0 = P1 / IS, TC0 = (G0 <= 2) ? 128 : 64;
     TensorMapBlob tmap; memset(&tmap, 0, sizeof tmap);
-    const bool no_tmap = getenv("GSB200_NO_TMAP") != 0 || getenv("GSB200_NO_TMA") != 0;
+    // measured on B200 (profiles/): one tiled-TMA box per span wins for the first sweep (long contiguous
+    // rows, 4.3 vs 6.2 ms) but loses to per-row bulk copies for the strided later sweeps; GSB200_TMAP=all|none overrides
+    const char *pol = getenv("GSB200_TMAP");
+    const bool want_tmap = pol ? !strcmp(pol, "all") : (td.rank == 3);
+    const bool no_tmap = !want_tmap || getenv("GSB200_NO_TMA") != 0;
     const bool use_tmap = !no_tmap && A.q == P1 && encode_tmap(&tmap, A.in, td, TC0, P1, T::NIN);
     if (use_tmap || tma_ok(A, FINAL)) {
         constexpr int G = P1 / IS, TC = (G <= 2) ? 128 : 64, NQ = P1;
@@ -808,7 +812,13 @@ int gsb200_create(const gsb200_problem *pb, int device, gsb200_assembler **out)
             if ((rc = upload(&d_ops, ops, a->stream))) break;
             if ((rc = upload(&d_cs, cs, a->stream))) break;
             a->prog_bufs.push_back(d_ops); a->prog_bufs.push_back(d_cs);
-            DevProgram dp; dp.ops = d_ops; dp.consts = d_cs; dp.nops = pr.nops; a->progs.push_back(dp);
+            DevProgram dp; memset(&dp, 0, sizeof dp); dp.ops = d_ops; dp.consts = d_cs; dp.nops = pr.nops;
+            if (pr.nops <= GSB_INLINE_OPS && pr.nconsts <= GSB_INLINE_CONSTS) {
+                dp.inl = 1;
+                for (int k = 0; k < pr.nops; ++k) dp.iops[k] = (signed char)pr.ops[k];
+                for (int k = 0; k < pr.nconsts; ++k) dp.iconsts[k] = pr.consts[k];
+            }
+            a->progs.push_back(dp);
         }
     }
     if (!rc) rc = dev_malloc((void **)&a->d_rhs, sizeof(double) * (size_t)std::max(1, pb->nfree) * pb->nrhs);
@@ -994,7 +1004,7 @@ int gsb200_expr_eval_host(const gsb200_program *prog, double x, double y, double
 {
     if (!prog || !out) return GSB200_EINVAL;
     // same interpreter source as the device (program_eval is host+device)
-    DevProgram dp; dp.ops = prog->ops; dp.consts = prog->consts; dp.nops = prog->nops;
+    DevProgram dp; memset(&dp, 0, sizeof dp); dp.ops = prog->ops; dp.consts = prog->consts; dp.nops = prog->nops;
 #ifndef GSB200_EMULATE
     *out = program_eval(dp, x, y, z);
 #else

@@ -165,39 +165,56 @@ GSB_GLOBAL void k_geo_table(const GeoTableArgs A)
 
 // ------------------------------------------------------------------------------------
 // Source-term stack machine (exprtk replacement).
-struct DevProgram { const int *ops; const double *consts; int nops; };
+// Short programs travel inside the kernel arguments (constant bank: no dependent global loads
+// in the interpreter loop); long ones stay in global memory.
+#define GSB_INLINE_OPS 48
+#define GSB_INLINE_CONSTS 12
+struct DevProgram {
+    const int *ops; const double *consts; int nops;
+    int inl;                                   // 1: use the inline copies below
+    signed char iops[GSB_INLINE_OPS]; double iconsts[GSB_INLINE_CONSTS];
+};
 GSB_HD double program_eval(const DevProgram &pr, double x, double y, double z)
 {
+    // stack machine with the top of stack cached in a register (t); st[] holds the rest
     double st[GSB200_PROGRAM_MAX_STACK];
+    double t = 0.0;
     int sp = 0;
     for (int i = 0; i < pr.nops; ++i) {
-        const int op = pr.ops[i];
+        const int op = pr.inl ? (int)pr.iops[i] : pr.ops[i];
         switch (op) {
-        case GSB200_OP_CONST: st[sp++] = pr.consts[pr.ops[++i]]; break;
-        case GSB200_OP_X: st[sp++] = x; break;
-        case GSB200_OP_Y: st[sp++] = y; break;
-        case GSB200_OP_Z: st[sp++] = z; break;
-        case GSB200_OP_ADD: --sp; st[sp - 1] = st[sp - 1] + st[sp]; break;
-        case GSB200_OP_SUB: --sp; st[sp - 1] = st[sp - 1] - st[sp]; break;
-        case GSB200_OP_MUL: --sp; st[sp - 1] = st[sp - 1] * st[sp]; break;
-        case GSB200_OP_DIV: --sp; st[sp - 1] = st[sp - 1] / st[sp]; break;
-        case GSB200_OP_POW: --sp; st[sp - 1] = pow(st[sp - 1], st[sp]); break;
-        case GSB200_OP_NEG: st[sp - 1] = -st[sp - 1]; break;
-        case GSB200_OP_SIN: st[sp - 1] = sin(st[sp - 1]); break;
-        case GSB200_OP_COS: st[sp - 1] = cos(st[sp - 1]); break;
-        case GSB200_OP_TAN: st[sp - 1] = tan(st[sp - 1]); break;
-        case GSB200_OP_EXP: st[sp - 1] = exp(st[sp - 1]); break;
-        case GSB200_OP_LOG: st[sp - 1] = log(st[sp - 1]); break;
-        case GSB200_OP_SQRT: st[sp - 1] = sqrt(st[sp - 1]); break;
-        case GSB200_OP_ABS: st[sp - 1] = fabs(st[sp - 1]); break;
-        case GSB200_OP_TANH: st[sp - 1] = tanh(st[sp - 1]); break;
-        case GSB200_OP_SINH: st[sp - 1] = sinh(st[sp - 1]); break;
-        case GSB200_OP_COSH: st[sp - 1] = cosh(st[sp - 1]); break;
-        case GSB200_OP_SQR: st[sp - 1] = st[sp - 1] * st[sp - 1]; break;
+        case GSB200_OP_CONST: { ++i; const int ci = pr.inl ? (int)pr.iops[i] : pr.ops[i]; st[sp++] = t; t = pr.inl ? pr.iconsts[ci] : pr.consts[ci]; break; }
+        case GSB200_OP_X: st[sp++] = t; t = x; break;
+        case GSB200_OP_Y: st[sp++] = t; t = y; break;
+        case GSB200_OP_Z: st[sp++] = t; t = z; break;
+        case GSB200_OP_ADD: t = st[--sp] + t; break;
+        case GSB200_OP_SUB: t = st[--sp] - t; break;
+        case GSB200_OP_MUL: t = st[--sp] * t; break;
+        case GSB200_OP_DIV: t = st[--sp] / t; break;
+        case GSB200_OP_POW: t = pow(st[--sp], t); break;
+        case GSB200_OP_NEG: t = -t; break;
+        case GSB200_OP_SIN: t = sin(t); break;
+        case GSB200_OP_COS: t = cos(t); break;
+        case GSB200_OP_TAN: t = tan(t); break;
+        case GSB200_OP_EXP: t = exp(t); break;
+        case GSB200_OP_LOG: t = log(t); break;
+        case GSB200_OP_SQRT: t = sqrt(t); break;
+        case GSB200_OP_ABS: t = fabs(t); break;
+        case GSB200_OP_TANH: t = tanh(t); break;
+        case GSB200_OP_SINH: t = sinh(t); break;
+        case GSB200_OP_COSH: t = cosh(t); break;
+        case GSB200_OP_SQR: t = t * t; break;
+#ifdef GSB200_EMULATE
+        case GSB200_OP_SINPI: t = sin(3.14159265358979323846 * t); break;
+        case GSB200_OP_COSPI: t = cos(3.14159265358979323846 * t); break;
+#else
+        case GSB200_OP_SINPI: t = sinpi(t); break;
+        case GSB200_OP_COSPI: t = cospi(t); break;
+#endif
         default: return NAN;
         }
     }
-    return st[0];
+    return t;
 }
 
 // ------------------------------------------------------------------------------------
@@ -391,6 +408,8 @@ GSB_DEVICE void owner_load(const FinalArgs &F, const FinalCtx &c, int iL, OwnerC
 GSB_DEVICE i64 final_prepare(const FinalArgs &F, const FinalCtx &c, const OwnerCache &oc, int dL, double val)
 {
     if (!oc.flag) return -1;
+    if (oc.flag == 3)       // full interior stencil: every partner is free, rank is the lexicographic stencil index
+        return oc.base + ((F.dim == 2) ? (dL + F.p[1]) : ((dL + F.p[2]) * (2 * F.p[1] + 1) + c.r_low)) * (2 * F.p[0] + 1) + c.bit0;
     const i64 lj = oc.li + (i64)dL * c.nlow + c.dj_low;
     if (oc.flag == 1) {
         const int run = (F.dim == 2) ? (dL + F.p[1]) : ((dL + F.p[2]) * (2 * F.p[1] + 1) + c.r_low);
@@ -483,7 +502,7 @@ struct SweepCore {
     {
         if (FINAL) {
             OwnerCache &c = oc[FINAL ? is : 0];
-            if (c.fun != fi) owner_load(A.fin, fc, fi, c);
+            if (c.fun != fi) owner_load(A.fin, fc, fi, c);      // only at a segment start
             const i64 pos = final_prepare(A.fin, fc, c, d, acc[is][js][0]);
             if (pos >= 0) A.fin.values[pos] = acc[is][js][0];
         } else {
@@ -508,30 +527,15 @@ struct SweepCore {
                 const int fi = f0 + ((so - ph + P1) % P1);
                 const bool wr = (fi >= x_min) && (fi < x_max);
                 if (fi == x) {
-                    if (FINAL) {
-                        // all slot-table words of the owner's P1 entries are fetched before the first store
-                        OwnerCache &c = oc[FINAL ? is : 0];
-                        if (wr && c.fun != fi) owner_load(A.fin, fc, fi, c);
-                        i64 pos[P1];
 #pragma unroll
-                        for (int js = 0; js < P1; ++js) {
-                            const int fj = f0 + ((js - ph + P1) % P1);
-                            pos[js] = (wr && fj >= x) ? final_prepare(A.fin, fc, c, fj - fi, acc[is][js][0]) : -1;
-                        }
+                    for (int js = 0; js < P1; ++js) {
+                        const int fj = f0 + ((js - ph + P1) % P1);
+                        if (wr && fj >= x) emit(A, fc, obase, is, js, fi, fj - fi);
 #pragma unroll
-                        for (int js = 0; js < P1; ++js) {
-                            if (pos[js] >= 0) A.fin.values[pos[js]] = acc[is][js][0];
-                            acc[is][js][0] = 0.0;
-                        }
-                    } else {
-#pragma unroll
-                        for (int js = 0; js < P1; ++js) {
-                            const int fj = f0 + ((js - ph + P1) % P1);
-                            if (wr && fj >= x) emit(A, fc, obase, is, js, fi, fj - fi);
-#pragma unroll
-                            for (int o = 0; o < NOUT; ++o) acc[is][js][o] = 0.0;
-                        }
+                        for (int o = 0; o < NOUT; ++o) acc[is][js][o] = 0.0;
                     }
+                    // the function that takes over this slot is known now: fetch its column data early
+                    if (FINAL) { const int fn = x + P1; if (fn >= x_min && fn < x_max) owner_load(A.fin, fc, fn, oc[FINAL ? is : 0]); else oc[FINAL ? is : 0].fun = -1; }
                 } else if (fi > x) {
 #pragma unroll
                     for (int js = 0; js < P1; ++js)
@@ -866,8 +870,11 @@ GSB_GLOBAL void k_pattern(const PatArgs A)
                 A.st[li * A.nrun + run] = (unsigned)start | (mask << 16);
             }
         }
-    if (mono && A.ncomp == 1) A.colflag[id] = 1;
-    else { A.colflag[id] = 2; if (!mono) A.gneed[gi] = 1; }
+    if (mono && A.ncomp == 1) {
+        i64 full = 1;
+        for (int k = 0; k < A.dim; ++k) full *= 2 * A.p[k] + 1;
+        A.colflag[id] = (pos - base == full) ? 3 : 1;     // 3: whole (2p+1)^d stencil present -> closed-form slots
+    } else { A.colflag[id] = 2; if (!mono) A.gneed[gi] = 1; }
 }
 
 // sort (and for coupled columns deduplicate) the row indices of the flagged columns

@@ -68,7 +68,9 @@ enum {
     GSB200_OP_POW = 8, GSB200_OP_NEG = 9, GSB200_OP_SIN = 10, GSB200_OP_COS = 11,
     GSB200_OP_TAN = 12, GSB200_OP_EXP = 13, GSB200_OP_LOG = 14, GSB200_OP_SQRT = 15,
     GSB200_OP_ABS = 16, GSB200_OP_TANH = 17, GSB200_OP_SINH = 18, GSB200_OP_COSH = 19,
-    GSB200_OP_SQR = 20
+    GSB200_OP_SQR = 20,   /* x*x            (emitted for x^2)        */
+    GSB200_OP_SINPI = 21, /* sin(pi*x)      (emitted for sin(pi*E))  */
+    GSB200_OP_COSPI = 22  /* cos(pi*x)                                 */
 };
 #define GSB200_PROGRAM_MAX_OPS 256
 #define GSB200_PROGRAM_MAX_STACK 32

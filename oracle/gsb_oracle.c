@@ -187,6 +187,8 @@ static double prog_eval(const gsb200_program *pr, const double *x)
         case GSB200_OP_SINH: st[sp - 1] = sinh(st[sp - 1]); break;
         case GSB200_OP_COSH: st[sp - 1] = cosh(st[sp - 1]); break;
         case GSB200_OP_SQR: st[sp - 1] = st[sp - 1] * st[sp - 1]; break;
+        case GSB200_OP_SINPI: st[sp - 1] = sin(3.14159265358979323846 * st[sp - 1]); break;
+        case GSB200_OP_COSPI: st[sp - 1] = cos(3.14159265358979323846 * st[sp - 1]); break;
         default: return NAN;
         }
     }
