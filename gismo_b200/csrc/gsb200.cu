@@ -497,6 +497,7 @@ static int assemble_pass(gsb200_assembler *a)
         const i64 Q0 = d0.Q, Q1 = dim == 3 ? d1.Q : 1;
         const i64 NI0 = (i64)d0.nfun * (2 * d0.p + 1), NI1 = dim == 3 ? (i64)d1.nfun * (2 * d1.p + 1) : 1;
         const i64 n0 = d0.nfun, n1 = dim == 3 ? d1.nfun : 1;
+        const i64 W0 = 2 * d0.p + 1, W1 = dim == 3 ? 2 * d1.p + 1 : 1;
         // doubles of workspace per last-direction quadrature point
         i64 perq = ncD * Q0 * Q1 + no1 * NI0 * Q1 + (dim == 3 ? no2 * NI1 * NI0 : 0) + nf * Q0 * Q1 + n0 * Q1 + (dim == 3 ? n1 * n0 : 0);
         i64 maxpts = limit / (perq * 8);
@@ -569,7 +570,7 @@ static int assemble_pass(gsb200_assembler *a)
                 auto base_args = [&](const Dir1D &d) {
                     SweepArgs A; memset(&A, 0, sizeof A);
                     A.first = d.d_first; A.nexit = d.d_nexit; A.tab = d.d_tab; A.q = d.q; A.p = d.p; A.fin = Fa;
-                    A.out_bq = 1; return A;
+                    A.out_bq = 1; A.out_od = 1; return A;
                 };
                 auto account = [&](int slot, const SweepArgs &A, const std::vector<int> &seg, i64 fpp, int nin, int nout, i64 npairs_out) {
                     i64 pts = 0;
@@ -583,7 +584,7 @@ static int assemble_pass(gsb200_assembler *a)
                         SweepArgs A = base_args(d0);
                         A.in = D; A.in_cs = npts; A.in_es = (i64)d0.q * Q1 * QLc; A.in_ts = Q1 * QLc; A.in_os = 0; A.in_is = 1; A.e_in0 = 0;
                         A.ncol = Q1 * QLc; A.ninner = A.ncol;
-                        A.out = A1; A.out_cs = NI0 * Q1 * QLc; A.out_ps = Q1 * QLc; A.out_os = 0; A.out_bq = A.ncol + 1; A.out_bs = 0; A.out_is = 1;
+                        A.out = A1; A.out_cs = NI0 * Q1 * QLc; A.out_fs = (2 * d0.p + 1) * Q1 * QLc; A.out_ds = Q1 * QLc; A.out_os = 0; A.out_bq = A.ncol + 1; A.out_bs = 0; A.out_is = 1;
                         const int nseg = nseg_for(A.ncol * (d0.p + 1), d0.nfun, d0.p + 1);
                         std::vector<int> seg = make_segments(d0, 0, d0.nfun, nseg);
                         A.seg = a->d_seg + segoff; GSB_TRY(upload_segments(a, seg, &segoff));
@@ -596,7 +597,9 @@ static int assemble_pass(gsb200_assembler *a)
                         SweepArgs A = base_args(d1);
                         A.in = A1; A.in_cs = NI0 * Q1 * QLc; A.in_es = (i64)d1.q * QLc; A.in_ts = QLc; A.in_os = Q1 * QLc; A.in_is = 1; A.e_in0 = 0;
                         A.ncol = NI0 * QLc; A.ninner = QLc;
-                        A.out = A2; A.out_cs = NI1 * ELc * NI0 * dL.q; A.out_ps = (i64)ELc * NI0 * dL.q; A.out_os = dL.q; A.out_bq = dL.q; A.out_bs = NI0 * dL.q; A.out_is = 1;
+                        // A2[g][i1][e2][i0][d1][d0][t]: the last sweep then writes (d1,d0)-contiguous runs of each CSC column
+                        A.out = A2; A.out_cs = NI1 * ELc * NI0 * dL.q; A.out_fs = (i64)ELc * NI0 * W1 * dL.q; A.out_ds = (i64)W0 * dL.q;
+                        A.out_od = W0; A.out_os = (i64)W1 * W0 * dL.q; A.out_os2 = dL.q; A.out_bq = dL.q; A.out_bs = NI0 * W1 * dL.q; A.out_is = 1;
                         const int nseg = nseg_for(A.ncol * (d1.p + 1), d1.nfun, d1.p + 1);
                         std::vector<int> seg = make_segments(d1, 0, d1.nfun, nseg);
                         A.seg = a->d_seg + segoff; GSB_TRY(upload_segments(a, seg, &segoff));
@@ -607,13 +610,13 @@ static int assemble_pass(gsb200_assembler *a)
                     }
                     {   // S3: direction 2, scatter into the CSC arrays
                         SweepArgs A = base_args(dL);
-                        A.in = A2; A.in_cs = NI1 * ELc * NI0 * dL.q; A.in_es = NI0 * dL.q; A.in_ts = 1; A.in_os = (i64)ELc * NI0 * dL.q; A.in_is = dL.q; A.e_in0 = eL0;
-                        A.ncol = NI1 * NI0; A.ninner = NI0;
+                        A.in = A2; A.in_cs = NI1 * ELc * NI0 * dL.q; A.in_es = NI0 * W1 * dL.q; A.in_ts = 1; A.in_os = (i64)ELc * NI0 * W1 * dL.q; A.in_is = dL.q; A.e_in0 = eL0;
+                        A.ncol = NI1 * NI0; A.ninner = NI0 * W1;     // outer = i1, inner = (i0, d1, d0)
                         const int nseg = nseg_for(A.ncol, x_hi - x_lo, dL.p + 1);
                         std::vector<int> seg = make_segments(dL, x_lo, x_hi, nseg);
                         A.seg = a->d_seg + segoff; GSB_TRY(upload_segments(a, seg, &segoff));
                         mark(a, 3);
-                        { TmapDesc td; memset(&td, 0, sizeof td); td.valid = true; td.rank = 5; td.dims[0] = (unsigned long long)(dL.q); td.dims[1] = (unsigned long long)(NI0); td.dims[2] = (unsigned long long)(ELc); td.dims[3] = (unsigned long long)(NI1); td.dims[4] = (unsigned long long)(no2); td.strides[0] = 8ull * (unsigned long long)(dL.q); td.strides[1] = 8ull * (unsigned long long)(NI0 * dL.q); td.strides[2] = 8ull * (unsigned long long)((i64)ELc * NI0 * dL.q); td.strides[3] = 8ull * (unsigned long long)(NI1 * ELc * NI0 * dL.q); td.box_kind[0] = 2; td.box_kind[1] = 1; td.box_kind[2] = 0; td.box_kind[3] = 0; td.box_kind[4] = 3; A.tm_rank = 5; A.tm_dim_inner = 1; A.tm_dim_e = 2; A.tm_e_mul = 1; A.tm_dim_outer = 3;
+                        { TmapDesc td; memset(&td, 0, sizeof td); td.valid = true; td.rank = 5; td.dims[0] = (unsigned long long)(dL.q); td.dims[1] = (unsigned long long)(NI0 * W1); td.dims[2] = (unsigned long long)(ELc); td.dims[3] = (unsigned long long)(n1); td.dims[4] = (unsigned long long)(no2); td.strides[0] = 8ull * (unsigned long long)(dL.q); td.strides[1] = 8ull * (unsigned long long)(NI0 * W1 * dL.q); td.strides[2] = 8ull * (unsigned long long)((i64)ELc * NI0 * W1 * dL.q); td.strides[3] = 8ull * (unsigned long long)(NI1 * ELc * NI0 * dL.q); td.box_kind[0] = 2; td.box_kind[1] = 1; td.box_kind[2] = 0; td.box_kind[3] = 0; td.box_kind[4] = 3; A.tm_rank = 5; A.tm_dim_inner = 1; A.tm_dim_e = 2; A.tm_e_mul = 1; A.tm_dim_outer = 3;
                         GSB_TRY(dispatch_sweep(kind, 2, dL.p + 1, A, (int)seg.size() / 4, s, &fpp, td)); }
                         stage_io(kind, 2, &nin, &nout); account(2, A, seg, fpp, nin, nout, (i64)(x_hi - x_lo) * (2 * dL.p + 1));
                     }
@@ -622,7 +625,7 @@ static int assemble_pass(gsb200_assembler *a)
                         SweepArgs A = base_args(d0);
                         A.in = D; A.in_cs = npts; A.in_es = (i64)d0.q * QLc; A.in_ts = QLc; A.in_os = 0; A.in_is = 1; A.e_in0 = 0;
                         A.ncol = QLc; A.ninner = QLc;
-                        A.out = A1; A.out_cs = (i64)ELc * NI0 * dL.q; A.out_ps = dL.q; A.out_os = 0; A.out_bq = dL.q; A.out_bs = NI0 * dL.q; A.out_is = 1;
+                        A.out = A1; A.out_cs = (i64)ELc * NI0 * dL.q; A.out_fs = (i64)(2 * d0.p + 1) * dL.q; A.out_ds = dL.q; A.out_os = 0; A.out_bq = dL.q; A.out_bs = NI0 * dL.q; A.out_is = 1;
                         const int nseg = nseg_for(A.ncol * (d0.p + 1), d0.nfun, d0.p + 1);
                         std::vector<int> seg = make_segments(d0, 0, d0.nfun, nseg);
                         A.seg = a->d_seg + segoff; GSB_TRY(upload_segments(a, seg, &segoff));

@@ -375,16 +375,25 @@ struct FinalCtx { i64 li_low, dj_low, nlow; int r_low, bit0; };
 
 GSB_DEVICE bool final_init(const FinalArgs &F, i64 outer, i64 inner, FinalCtx &c)
 {
+    // 2-D: inner = (i0, d0).  3-D: outer = i1, inner = (i0, d1, d0) so that consecutive lanes hit
+    // consecutive slots (d1, d0) of one CSC column.
     const int W0 = 2 * F.p[0] + 1;
-    const int i0 = (int)(inner / W0), d0 = (int)(inner % W0) - F.p[0];
-    const int j0 = i0 + d0;
-    if (j0 < F.plo[0][i0] || j0 > F.phi[0][i0]) return false;
-    c.bit0 = d0 + F.p[0];
-    if (F.dim == 2) { c.li_low = i0; c.dj_low = d0; c.nlow = F.n[0]; c.r_low = 0; return true; }
+    if (F.dim == 2) {
+        const int i0 = (int)(inner / W0), d0 = (int)(inner % W0) - F.p[0];
+        const int j0 = i0 + d0;
+        if (j0 < F.plo[0][i0] || j0 > F.phi[0][i0]) return false;
+        c.bit0 = d0 + F.p[0];
+        c.li_low = i0; c.dj_low = d0; c.nlow = F.n[0]; c.r_low = 0;
+        return true;
+    }
     const int W1 = 2 * F.p[1] + 1;
-    const int i1 = (int)(outer / W1), d1 = (int)(outer % W1) - F.p[1];
-    const int j1 = i1 + d1;
+    const int i0 = (int)(inner / (W1 * W0)), r = (int)(inner % (W1 * W0));
+    const int d1 = r / W0 - F.p[1], d0 = r % W0 - F.p[0];
+    const int i1 = (int)outer;
+    const int j0 = i0 + d0, j1 = i1 + d1;
+    if (j0 < F.plo[0][i0] || j0 > F.phi[0][i0]) return false;
     if (j1 < F.plo[1][i1] || j1 > F.phi[1][i1]) return false;
+    c.bit0 = d0 + F.p[0];
     c.li_low = (i64)i1 * F.n[0] + i0; c.dj_low = (i64)d1 * F.n[0] + d0; c.nlow = (i64)F.n[0] * F.n[1];
     c.r_low = d1 + F.p[1];
     return true;
@@ -442,7 +451,7 @@ struct SweepArgs {
     const int *seg;                                            // [nseg][4] e_begin,e_end,x_min,x_max
     const double *in; double *out;
     i64 in_cs, in_es, in_ts, in_os, in_is; int e_in0;          // input strides: comp, element, point, outer, inner
-    i64 out_cs, out_ps, out_os, out_bs, out_is; int out_bq;    // output: comp, pair, outer, block, inner
+    i64 out_cs, out_fs, out_ds, out_os, out_os2, out_od, out_bs, out_is, out_bq;   // output strides: comp, owner fn, delta, outer (split at out_od), block, inner
     i64 ncol; i64 ninner;
     // tensor-map TMA variant: which box coordinate carries the tile start, the span, the outer index
     int tm_rank, tm_dim_inner, tm_dim_e, tm_e_mul, tm_dim_outer;
@@ -506,7 +515,7 @@ struct SweepCore {
             const i64 pos = final_prepare(A.fin, fc, c, d, acc[is][js][0]);
             if (pos >= 0) A.fin.values[pos] = acc[is][js][0];
         } else {
-            const i64 o0 = ((i64)fi * (2 * A.p + 1) + (d + A.p)) * A.out_ps + obase;
+            const i64 o0 = (i64)fi * A.out_fs + (i64)(d + A.p) * A.out_ds + obase;
 #pragma unroll
             for (int o = 0; o < NOUT; ++o) A.out[o * A.out_cs + o0] = acc[is][js][o];
         }
@@ -563,7 +572,7 @@ GSB_GLOBAL void k_sweep(const SweepArgs A)
     FinalCtx fc;
     i64 obase = 0;
     if (FINAL) { if (!final_init(A.fin, outer, inner, fc)) return; }
-    else obase = outer * A.out_os + (inner / A.out_bq) * A.out_bs + (inner % A.out_bq) * A.out_is;
+    else obase = (outer / A.out_od) * A.out_os + (outer % A.out_od) * A.out_os2 + (inner / A.out_bq) * A.out_bs + (inner % A.out_bq) * A.out_is;
     constexpr int NIN = T::NIN;
     SweepCore<P1, T, IS, FINAL> core;
     core.zero();
@@ -686,7 +695,7 @@ GSB_GLOBAL void __launch_bounds__(TC * (P1 / IS), MINB) k_sweep_tma(const SweepA
     i64 obase = 0;
     bool live = lcol < ncols;
     if (FINAL) { if (live) live = final_init(A.fin, outer, inner, fc); }
-    else obase = outer * A.out_os + (inner / A.out_bq) * A.out_bs + (inner % A.out_bq) * A.out_is;
+    else obase = (outer / A.out_od) * A.out_os + (outer % A.out_od) * A.out_os2 + (inner / A.out_bq) * A.out_bs + (inner % A.out_bq) * A.out_is;
     SweepCore<P1, T, IS, FINAL> core;
     core.zero();
     int f0 = A.first[e_begin], nx = A.nexit[e_begin];
