@@ -138,9 +138,9 @@ struct PatchDev {
     Dir1D dir[3];
     i64 nb = 0, ngeo_total = 0;
     int *d_dofmap = 0; double *d_coefs = 0, *d_weights = 0;
-    unsigned char *d_colflag = 0; unsigned *d_st = 0; int nrun = 1;
+    unsigned char *d_colflag = 0; unsigned *d_st = 0; int nrun = 1; i64 *d_ownrec = 0;
     int own_lo = 0, own_hi = 0;     // owner range along the last direction on this rank
-    void release() { for (int k = 0; k < 3; ++k) dir[k].release(); dev_free(d_dofmap); dev_free(d_coefs); dev_free(d_weights); dev_free(d_colflag); dev_free(d_st); }
+    void release() { for (int k = 0; k < 3; ++k) dir[k].release(); dev_free(d_dofmap); dev_free(d_coefs); dev_free(d_weights); dev_free(d_colflag); dev_free(d_st); dev_free(d_ownrec); }
 };
 
 } // namespace gsb
@@ -277,6 +277,12 @@ static int build_pattern(gsb200_assembler *a)
         GSB_TRY(dev_d2h(fl.data(), P.d_colflag, fl.size(), s));
         for (unsigned char f : fl) if (f == 2) { a->any_generic = true; break; }
     }
+    for (auto &P : a->patches) {       // packed owner records for the final sweep
+        const i64 nt = P.nb * a->ncomp;
+        dev_free(P.d_ownrec); P.d_ownrec = 0;
+        GSB_TRY(dev_malloc((void **)&P.d_ownrec, sizeof(i64) * (size_t)nt));
+        GSB_LAUNCH(k_owner_records, dim3((unsigned)((nt + 127) / 128)), dim3(128), s, nt, N, P.d_dofmap, P.d_colflag, a->d_colptr, P.d_ownrec);
+    }
     GSB_TRY(dev_malloc((void **)&a->d_values, sizeof(double) * (size_t)std::max<i64>(a->nnz, 1)));
     GSB_TRY(dev_memset(a->d_values, 0, sizeof(double) * (size_t)std::max<i64>(a->nnz, 1), s));
     GSB_TRY(dev_last_error("pattern kernels"));
@@ -286,7 +292,7 @@ static int build_pattern(gsb200_assembler *a)
     cudaEventRecord(e1, s); cudaEventSynchronize(e1); cudaEventElapsedTime(&a->tm.pattern_ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
 #endif
-    a->pattern_built = true;
+    a->pattern_built = true; a->plan_valid = false;
     return 0;
 }
 
@@ -563,7 +569,7 @@ static int assemble_pass(gsb200_assembler *a)
                     Fa.plo[k] = k < dim ? P.dir[k].d_plo : 0; Fa.phi[k] = k < dim ? P.dir[k].d_phi : 0;
                 }
                 Fa.dofmap = P.d_dofmap; Fa.nb = P.nb; Fa.brow = brow; Fa.bcol = bcol;
-                Fa.colflag = P.d_colflag; Fa.st = P.d_st; Fa.nrun = P.nrun;
+                Fa.colflag = P.d_colflag; Fa.ownrec = P.d_ownrec; Fa.st = P.d_st; Fa.nrun = P.nrun;
                 Fa.colptr = a->d_colptr; Fa.inner = a->d_inner; Fa.values = a->d_values;
                 Fa.rhs = a->d_rhs; Fa.fixed = a->d_fixed; Fa.nfree = N; Fa.nfixed = a->nfixed; Fa.nrhs = a->nrhs;
 

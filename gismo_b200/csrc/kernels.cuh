@@ -366,7 +366,8 @@ struct FinalArgs {
     const int *plo[3]; const int *phi[3];   // co-occurring partner range per function, per direction
     const int *dofmap; i64 nb;     // ncomp blocks of nb global indices
     int brow, bcol;
-    const unsigned char *colflag;  // per (comp, local fn): 0 skip, 1 canonical, 2 generic
+    const unsigned char *colflag;  // per (comp, local fn): 0 skip, 1 canonical, 2 generic, 3 canonical + full stencil
+    const i64 *ownrec;             // per (comp, local fn): (colptr << 2) | flag
     const unsigned *st; int nrun;  // canonical slot table: per (fn, run) start | mask<<16
     const i64 *colptr; const int *inner; double *values;
     double *rhs; const double *fixed; int nfree, nfixed, nrhs;
@@ -399,46 +400,55 @@ GSB_DEVICE bool final_init(const FinalArgs &F, i64 outer, i64 inner, FinalCtx &c
     return true;
 }
 
-// Per-owner data (global column, its flag and CSC offset) is loaded once per function and
-// kept in registers; only the slot-table word is fetched per emitted entry.
-struct OwnerCache { int fun; int gi; int flag; i64 base; i64 li; };
+// Per-owner data: ONE packed word per (component, local function) prepared after the pattern
+// build (k_owner_records): (colptr[gi] << 2) | flag, 0 for eliminated / foreign columns.  The
+// sweep fetches it one span before the owner's first emit and keeps it in registers.
+struct OwnerCache { int fun; i64 rec; };
 
 GSB_DEVICE void owner_load(const FinalArgs &F, const FinalCtx &c, int iL, OwnerCache &oc)
 {
     oc.fun = iL;
-    oc.li = (i64)iL * c.nlow + c.li_low;
-    oc.gi = F.dofmap[F.bcol * F.nb + oc.li];
-    oc.flag = (oc.gi < F.nfree) ? (int)F.colflag[F.bcol * F.nb + oc.li] : 0;   // eliminated or foreign column: nothing stored
-    oc.base = oc.flag ? F.colptr[oc.gi] : 0;
+    oc.rec = F.ownrec[F.bcol * F.nb + (i64)iL * c.nlow + c.li_low];
+}
+
+GSB_GLOBAL void k_owner_records(i64 n, int nfree, const int *dofmap, const unsigned char *colflag, const i64 *colptr, i64 *ownrec)
+{
+    const i64 id = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n) return;
+    const int g = dofmap[id];
+    const int flag = g < nfree ? (int)colflag[id] : 0;
+    ownrec[id] = flag ? ((colptr[g] << 2) | flag) : 0;
 }
 
 // -> position in `values` for the common case (canonical column, free row); slow paths
 // (eliminated row, generic column) are completed here and -1 is returned.
 GSB_DEVICE i64 final_prepare(const FinalArgs &F, const FinalCtx &c, const OwnerCache &oc, int dL, double val)
 {
-    if (!oc.flag) return -1;
-    if (oc.flag == 3)       // full interior stencil: every partner is free, rank is the lexicographic stencil index
-        return oc.base + ((F.dim == 2) ? (dL + F.p[1]) : ((dL + F.p[2]) * (2 * F.p[1] + 1) + c.r_low)) * (2 * F.p[0] + 1) + c.bit0;
-    const i64 lj = oc.li + (i64)dL * c.nlow + c.dj_low;
-    if (oc.flag == 1) {
+    const int flag = (int)(oc.rec & 3);
+    if (!flag) return -1;
+    const i64 base = oc.rec >> 2;
+    if (flag == 3)          // full interior stencil: every partner is free, rank is the lexicographic stencil index
+        return base + ((F.dim == 2) ? (dL + F.p[1]) : ((dL + F.p[2]) * (2 * F.p[1] + 1) + c.r_low)) * (2 * F.p[0] + 1) + c.bit0;
+    const i64 li = (i64)oc.fun * c.nlow + c.li_low;
+    const i64 lj = li + (i64)dL * c.nlow + c.dj_low;
+    if (flag == 1) {
         const int run = (F.dim == 2) ? (dL + F.p[1]) : ((dL + F.p[2]) * (2 * F.p[1] + 1) + c.r_low);
-        const unsigned w = F.st[oc.li * F.nrun + run];
+        const unsigned w = F.st[li * F.nrun + run];
         const unsigned mask = w >> 16;
-        if ((mask >> c.bit0) & 1u) {                 // partner row is free: its rank in the column is known
-            const int rank = (int)(w & 0xffffu) + popc(mask & ((1u << c.bit0) - 1u));
-            return oc.base + rank;
-        }
+        if ((mask >> c.bit0) & 1u)                   // partner row is free: its rank in the column is known
+            return base + (int)(w & 0xffffu) + popc(mask & ((1u << c.bit0) - 1u));
         if (!F.fixed) return -1;
     }
+    const int gi = F.dofmap[F.bcol * F.nb + li];
     const int gj = F.dofmap[F.brow * F.nb + lj];
     if (gj >= F.nfree) {                             // eliminated row: by symmetry of the form this is the
         if (F.fixed)                                 // -K(i,j) g_j term of gsSparseSystem.h:1004
-            for (int r = 0; r < F.nrhs; ++r) atomic_add(F.rhs + (i64)r * F.nfree + oc.gi, -val * F.fixed[(i64)r * F.nfixed + (gj - F.nfree)]);
+            for (int r = 0; r < F.nrhs; ++r) atomic_add(F.rhs + (i64)r * F.nfree + gi, -val * F.fixed[(i64)r * F.nfixed + (gj - F.nfree)]);
         return -1;
     }
-    int lo = 0, hi = (int)(F.colptr[oc.gi + 1] - oc.base) - 1;
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (F.inner[oc.base + mid] < gj) lo = mid + 1; else hi = mid; }
-    atomic_add(F.values + oc.base + lo, val);
+    int lo = 0, hi = (int)(F.colptr[gi + 1] - base) - 1;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (F.inner[base + mid] < gj) lo = mid + 1; else hi = mid; }
+    atomic_add(F.values + base + lo, val);
     return -1;
 }
 
@@ -469,7 +479,7 @@ struct SweepCore {
     GSB_MEMBER void zero()
     {
 #pragma unroll
-        for (int is = 0; is < (FINAL ? IS : 1); ++is) { oc[is].fun = -1; oc[is].flag = 0; }
+        for (int is = 0; is < (FINAL ? IS : 1); ++is) { oc[is].fun = -1; oc[is].rec = 0; }
 #pragma unroll
         for (int is = 0; is < IS; ++is)
 #pragma unroll
@@ -662,8 +672,7 @@ GSB_GLOBAL void __launch_bounds__(TC * (P1 / IS), MINB) k_sweep_tma(const SweepA
     const double *tile = A.in + outer * A.in_os + inner0 * A.in_is;
     const unsigned row_bytes = (unsigned)(ncols * (ROWB ? NQ : 1) * sizeof(double));
     constexpr int NROWS = ROWB ? NIN : NQ * NIN;
-    auto issue = [&](int e) {   // executed by warp 0: fill stage (e - e_begin) % NSTAGE with span e
-        const int s = (e - e_begin) % NSTAGE;
+    auto issue = [&](int e, int s) {   // executed by warp 0: fill stage s (= (e - e_begin) % NSTAGE) with span e
         double *dst = sdata + (size_t)s * STAGE_DOUBLES;
         const double *src = tile + (i64)(e - A.e_in0) * A.in_es;
         if (use_tmap) {       // one box per span (out-of-range columns are zero-filled and still counted)
@@ -689,7 +698,7 @@ GSB_GLOBAL void __launch_bounds__(TC * (P1 / IS), MINB) k_sweep_tma(const SweepA
         }
     };
     if (warp == 0)
-        for (int e = e_begin; e < e_end && e < e_begin + NSTAGE; ++e) issue(e);
+        for (int e = e_begin; e < e_end && e < e_begin + NSTAGE; ++e) issue(e, e - e_begin);
 
     FinalCtx fc;
     i64 obase = 0;
@@ -699,9 +708,8 @@ GSB_GLOBAL void __launch_bounds__(TC * (P1 / IS), MINB) k_sweep_tma(const SweepA
     SweepCore<P1, T, IS, FINAL> core;
     core.zero();
     int f0 = A.first[e_begin], nx = A.nexit[e_begin];
+    int s = 0; unsigned par = 0;
     for (int e = e_begin; e < e_end; ++e) {
-        const int it = e - e_begin, s = it % NSTAGE;
-        const unsigned par = (unsigned)((it / NSTAGE) & 1);
         // next span's window data: fetched now, consumed one iteration later
         const int f0n = (e + 1 < e_end) ? A.first[e + 1] : 0, nxn = (e + 1 < e_end) ? A.nexit[e + 1] : 0;
         mbar_wait(full + s, par);
@@ -737,10 +745,11 @@ GSB_GLOBAL void __launch_bounds__(TC * (P1 / IS), MINB) k_sweep_tma(const SweepA
         if (lane == 0) mbar_arrive(empty + s);
         if (warp == 0 && e + NSTAGE < e_end) {     // refill this stage once every warp has released it
             mbar_wait(empty + s, par);
-            issue(e + NSTAGE);
+            issue(e + NSTAGE, s);
         }
         if (live) core.exits(A, fc, obase, nx, f0, grp, x_min, x_max);
         f0 = f0n; nx = nxn;
+        if (++s == NSTAGE) { s = 0; par ^= 1u; }
     }
 }
 #endif
