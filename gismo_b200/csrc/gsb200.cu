@@ -355,10 +355,9 @@ static bool tma_ok(const SweepArgs &A, bool final_stage)
 #endif
 }
 
-template <int P1, class T, bool FINAL>
-static int launch_sweep_t(const SweepArgs &A, int nseg, stream_t s, i64 *flops_per_point, const TmapDesc &td)
+template <int P1, class T, bool FINAL, int IS>
+static int launch_sweep_i(const SweepArgs &A, int nseg, stream_t s, i64 *flops_per_point, const TmapDesc &td)
 {
-    constexpr int IS = pick_is(P1, T::NOUT);
     *flops_per_point = (i64)P1 * (2 * T::NT - n_first<T>() + 2 * P1 * n_has<T>());
 #ifndef GSB200_EMULATE
     constexpr int G0 = P1 / IS, TC0 = (G0 <= 2) ? 128 : 64;
@@ -399,6 +398,18 @@ static int launch_sweep_t(const SweepArgs &A, int nseg, stream_t s, i64 *flops_p
     auto kfn = k_sweep<P1, T, IS, FINAL>;
     GSB_LAUNCH(kfn, grid, dim3(128), s, A);
     return 0;
+}
+// owner slots per thread: the largest that keeps the accumulators in registers, or (GSB200_ISDIV=1)
+// half of it: twice the threads per column tile, half the accumulators each -> more resident warps
+template <int P1, class T, bool FINAL>
+static int launch_sweep_t(const SweepArgs &A, int nseg, stream_t s, i64 *fpp, const TmapDesc &td)
+{
+    constexpr int IS = pick_is(P1, T::NOUT);
+    if constexpr (!FINAL && IS % 2 == 0 && IS > 1) {
+        static const char *env = getenv("GSB200_ISDIV");
+        if (env && atoi(env) > 0) return launch_sweep_i<P1, T, FINAL, IS / 2>(A, nseg, s, fpp, td);
+    }
+    return launch_sweep_i<P1, T, FINAL, IS>(A, nseg, s, fpp, td);
 }
 template <class T, bool FINAL>
 static int launch_sweep(int P1, const SweepArgs &A, int nseg, stream_t s, i64 *fpp, const TmapDesc &td)

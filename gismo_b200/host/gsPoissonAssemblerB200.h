@@ -23,7 +23,7 @@
 namespace gismo
 {
 
-template <class T>
+template <class T = real_t>
 class gsPoissonAssemblerB200 : public gsPoissonAssembler<T>
 {
 public:
@@ -96,7 +96,7 @@ protected:
         A.assembleElasticity(lambda, mu, f);
         A.matrix(); A.rhs();
 */
-template <class T>
+template <class T = real_t>
 class gsExprAssemblerB200
 {
 public:

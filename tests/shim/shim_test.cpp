@@ -1,0 +1,90 @@
+// shim_test.cpp — drop-in proof (test infrastructure): the UNMODIFIED reference assemblers next to the
+// B200 shims of gismo_b200/host/, on identical gismo objects.  Built header-only against /root/reference
+// by tests/shim/Makefile; runs on the GPU box (needs libgsb200.so + a CUDA device).
+#include <gismo.h>
+#include <gsAssembler/gsVisitorPoisson.h>
+#include <gsPoissonAssemblerB200.h>
+
+using namespace gismo;
+
+static int compare(const char *what, const gsSparseMatrix<real_t> &A, const gsMatrix<real_t> &ra,
+                   const gsSparseMatrix<real_t> &B, const gsMatrix<real_t> &rb)
+{
+    gsSparseMatrix<real_t> Ac = A; Ac.makeCompressed();
+    bool pattern = Ac.rows() == B.rows() && Ac.nonZeros() == B.nonZeros() && B.isCompressed();
+    if (pattern) {
+        pattern = std::equal(Ac.outerIndexPtr(), Ac.outerIndexPtr() + Ac.cols() + 1, B.outerIndexPtr()) &&
+                  std::equal(Ac.innerIndexPtr(), Ac.innerIndexPtr() + Ac.nonZeros(), B.innerIndexPtr());
+    }
+    real_t dv = 0, mv = 0;
+    if (pattern) for (index_t k = 0; k < Ac.nonZeros(); ++k) { dv = std::max(dv, std::abs(Ac.valuePtr()[k] - B.valuePtr()[k])); mv = std::max(mv, std::abs(Ac.valuePtr()[k])); }
+    const real_t dr = (ra - rb).cwiseAbs().maxCoeff(), mr = std::max<real_t>(ra.cwiseAbs().maxCoeff(), 1e-300);
+    const bool ok = pattern && dv <= 1e-12 * mv && dr <= 1e-12 * mr;
+    gsInfo << "SHIM " << what << ": dofs " << B.rows() << " nnz " << B.nonZeros() << " pattern " << (pattern ? "identical" : "DIFFERENT")
+           << " dK " << dv / std::max<real_t>(mv, 1e-300) << " drhs " << dr / mr << (ok ? " OK" : " FAIL") << "\n";
+    return ok ? 0 : 1;
+}
+
+int main()
+{
+    int bad = 0;
+    {   // visitor path, multi-patch, non-homogeneous Dirichlet by interpolation
+        gsMultiPatch<> mp = gsNurbsCreator<>::BSplineSquareGrid(2, 2, 1.0);
+        mp.computeTopology();
+        gsMultiBasis<> mb(mp, true); mb.setDegree(3); mb.uniformRefine(7);
+        gsFunctionExpr<> f("2*pi^2*sin(pi*x)*sin(pi*y)", 2), g("x*y+1", 2);
+        gsBoundaryConditions<> bc;
+        for (gsMultiPatch<>::const_biterator it = mp.bBegin(); it != mp.bEnd(); ++it) bc.addCondition(*it, condition_type::dirichlet, &g);
+        bc.setGeoMap(mp);
+        gsPoissonAssembler<> R(mp, mb, bc, f, dirichlet::elimination, iFace::glue);
+        R.assemble();
+        gsPoissonAssemblerB200<> D(mp, mb, bc, f, dirichlet::elimination, iFace::glue);
+        D.assemble();
+        bad += compare("gsPoissonAssemblerB200 2x2 patches p=3", R.matrix(), R.rhs(), D.matrix(), D.rhs());
+        // the reference's own solver consumes the device-built matrix
+        gsSparseSolver<>::CGDiagonal solver; solver.compute(D.matrix());
+        gsMatrix<> x = solver.solve(D.rhs());
+        gsSparseSolver<>::CGDiagonal solver2; solver2.compute(R.matrix());
+        gsMatrix<> y = solver2.solve(R.rhs());
+        const real_t ds = (x - y).norm() / y.norm();
+        gsInfo << "SHIM solve difference " << ds << (ds < 1e-8 ? " OK" : " FAIL") << "\n";
+        bad += !(ds < 1e-8);
+    }
+    {   // visitor path, 3-D NURBS-free curved cube, homogeneous
+        gsMultiPatch<> mp(*gsNurbsCreator<>::BSplineCube(1, 0, 0, 0));
+        gsMultiBasis<> mb(mp, true); mb.setDegree(2); mb.uniformRefine(5);
+        gsFunctionExpr<> f("3*pi^2*sin(pi*x)*sin(pi*y)*sin(pi*z)", 3), g("0", 3);
+        gsBoundaryConditions<> bc;
+        for (gsMultiPatch<>::const_biterator it = mp.bBegin(); it != mp.bEnd(); ++it) bc.addCondition(*it, condition_type::dirichlet, &g);
+        bc.setGeoMap(mp);
+        gsPoissonAssembler<> R(mp, mb, bc, f, dirichlet::elimination, iFace::glue);
+        R.assemble();
+        gsPoissonAssemblerB200<> D(mp, mb, bc, f, dirichlet::elimination, iFace::glue);
+        D.assemble();
+        bad += compare("gsPoissonAssemblerB200 cube p=2", R.matrix(), R.rhs(), D.matrix(), D.rhs());
+    }
+    {   // expression path on the NURBS quarter annulus, L2-projected Dirichlet data
+        gsMultiPatch<> mp(*gsNurbsCreator<>::NurbsQuarterAnnulus(1, 2));
+        mp.computeTopology();
+        gsMultiBasis<> mb(mp, true); mb.setDegree(2); mb.uniformRefine(7);
+        gsFunctionExpr<> f("sin(x)*y", 2), g("x+y", 2);
+        gsBoundaryConditions<> bc;
+        for (gsMultiPatch<>::const_biterator it = mp.bBegin(); it != mp.bEnd(); ++it) bc.addCondition(*it, condition_type::dirichlet, &g);
+        bc.setGeoMap(mp);
+        gsExprAssembler<> A(1, 1);
+        A.setIntegrationElements(mb);
+        gsExprAssembler<>::geometryMap G = A.getMap(mp);
+        gsExprAssembler<>::space u = A.getSpace(mb);
+        auto ff = A.getCoeff(f, G);
+        u.setup(bc, dirichlet::l2Projection, 0);
+        A.initSystem();
+        A.assemble(igrad(u, G) * igrad(u, G).tr() * meas(G), u * ff * meas(G));
+        gsExprAssemblerB200<> B;
+        B.setIntegrationElements(mb); B.setGeometry(mp);
+        B.setup(bc, 1, dirichlet::l2Projection);
+        B.assemblePoisson(f);
+        bad += compare("gsExprAssemblerB200 NURBS annulus p=2", A.matrix(), A.rhs(), B.matrix(), B.rhs());
+    }
+    gsInfo << (bad ? "SHIM RESULT FAIL\n" : "SHIM RESULT PASS\n");
+    return bad;
+}

@@ -180,3 +180,16 @@ def test_consumer_spmv_and_cg(lib):
 def test_measured_peaks_are_plausible(lib):
     pk = g.measure_peaks(0)
     assert 5 < pk["fp64_tflops"] < 100 and 500 < pk["hbm_gbs"] < 10000
+
+
+def test_gismo_shim_dropin(lib):
+    """The C++ drop-in shims (gismo_b200/host/*.h) on real gismo objects next to the unmodified reference
+    assemblers: tests/shim/shim_test.cpp, built here against /root/reference, executed on the GPU box."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shim", "_build", "shim_test")
+    if not os.path.exists(exe):
+        pytest.skip("tests/shim/_build/shim_test not built (needs /root/reference at build time)")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    print(out.stdout[-2000:], out.stderr[-2000:])
+    assert out.returncode == 0 and "SHIM RESULT PASS" in out.stdout
