@@ -303,7 +303,11 @@ constexpr int pick_is(int P1, int NOUT)
     for (int d = 1; d <= P1; ++d) if (P1 % d == 0 && d * P1 * NOUT <= 40) best = d;
     return best;
 }
-constexpr int tc_for(int P1, int NOUT) { return (P1 / pick_is(P1, NOUT) <= 2) ? 128 : 64; }   // columns per CTA of a sweep
+// columns per CTA of a sweep: 64 when several owner-slot groups share the tile; for 1-2 groups 128, or 64
+// (GSB200_TC=64) to fit two CTAs per SM
+static int g_tc_small = -1;
+static bool tc_small() { if (g_tc_small < 0) { const char *e = getenv("GSB200_TC"); g_tc_small = (e && atoi(e) == 64) ? 1 : 0; } return g_tc_small == 1; }
+static int tc_for(int P1, int NOUT) { return (P1 / pick_is(P1, NOUT) <= 2 && !tc_small()) ? 128 : 64; }
 template <class T> constexpr int n_has() { int n = 0; for (int o = 0; o < T::NOUT; ++o) for (int b = 0; b < 2; ++b) if (T::has(o, b)) ++n; return n; }
 template <class T> constexpr int n_first() { int n = 0; for (int k = 0; k < T::NT; ++k) if (T::first(k)) ++n; return n; }
 
@@ -357,31 +361,28 @@ static bool tma_ok(const SweepArgs &A, bool final_stage)
 #endif
 }
 
-template <int P1, class T, bool FINAL, int IS>
-static int launch_sweep_i(const SweepArgs &A, int nseg, stream_t s, i64 *flops_per_point, const TmapDesc &td)
+template <int P1, class T, bool FINAL, int IS, int TC>
+static int launch_sweep_tc(const SweepArgs &A, int nseg, stream_t s, const TmapDesc &td, bool *launched)
 {
-    *flops_per_point = (i64)P1 * (2 * T::NT - n_first<T>() + 2 * P1 * n_has<T>());
+    *launched = false;
 #ifndef GSB200_EMULATE
-    constexpr int TC0 = tc_for(P1, T::NOUT);
-    static_assert(IS == pick_is(P1, T::NOUT) || true, "");
     TensorMapBlob tmap; memset(&tmap, 0, sizeof tmap);
-    // measured on B200 (profiles/): one tiled-TMA box per span wins for the first sweep (long contiguous
-    // rows, 4.3 vs 6.2 ms) but loses to per-row bulk copies for the strided later sweeps; GSB200_TMAP=all|none overrides
+    // measured on B200 (profiles/): tiled-TMA boxes only pay off for long contiguous rows; GSB200_TMAP=all|none overrides
     const char *pol = getenv("GSB200_TMAP");
-    const bool want_tmap = pol ? !strcmp(pol, "all") : (td.rank == 3);
-    const bool no_tmap = !want_tmap || getenv("GSB200_NO_TMA") != 0;
-    const bool use_tmap = !no_tmap && A.q == P1 && encode_tmap(&tmap, A.in, td, TC0, P1, T::NIN);
-    if (A.in_blk_tc && A.in_blk_tc != TC0) { set_error("internal: blocked layout tile %d != kernel tile %d", A.in_blk_tc, TC0); return GSB200_EINVAL; }
+    const bool want_tmap = pol ? !strcmp(pol, "all") : false;
+    const bool no_tmap = !want_tmap || getenv("GSB200_NO_TMA") != 0 || A.in_blk_tc;
+    const bool use_tmap = !no_tmap && A.q == P1 && encode_tmap(&tmap, A.in, td, TC, P1, T::NIN);
+    if (A.in_blk_tc && A.in_blk_tc != TC) { set_error("internal: blocked layout tile %d != kernel tile %d", A.in_blk_tc, TC); return GSB200_EINVAL; }
     if (use_tmap || tma_ok(A, FINAL)) {
-        constexpr int G = P1 / IS, TC = tc_for(P1, T::NOUT), NQ = P1;
-        constexpr int MINB_HI = (TC * G <= 128) ? 4 : (TC * G <= 256 ? 2 : 1);
+        constexpr int G = P1 / IS, NQ = P1;
+        constexpr int MINB_HI = (TC * G <= 128) ? (FINAL ? 4 : 2) : (TC * G <= 256 ? 2 : 1);
         const size_t stage = (size_t)((NQ * T::NIN * TC + NQ * P1 * 2 + 15) / 16 * 16) * sizeof(double);
         const char *env = getenv("GSB200_MINB");
         const bool hi = env ? atoi(env) > 1 : (TC * G <= 128);
         // ring depth: as many spans in flight as the shared memory left per resident CTA allows
         const size_t budget = (size_t)200 * 1024 / (hi ? MINB_HI : 1);
         const char *envs = getenv("GSB200_NSTAGE");
-        int nstage = (int)std::min<size_t>(envs ? (size_t)atoi(envs) : 8, budget / stage);
+        int nstage = (int)std::min<size_t>(envs ? (size_t)atoi(envs) : 6, budget / stage);
         if (A.q == NQ && nstage >= 2) {
             const size_t smem = nstage * stage + 2 * nstage * sizeof(unsigned long long);
             const int tiles = (int)((A.ninner + TC - 1) / TC);
@@ -394,10 +395,21 @@ static int launch_sweep_i(const SweepArgs &A, int nseg, stream_t s, i64 *flops_p
                 attributed.push_back((const void *)kfn);
             }
             if (!dry_run()) { kfn<<<dim3((unsigned)(nouter * tiles), 1, nseg), dim3(TC * G), smem, s>>>(A, tiles, nstage, tmap, use_tmap ? 1 : 0); note_launch(); }
-            return 0;
+            *launched = true;
         }
     }
 #endif
+    return 0;
+}
+
+template <int P1, class T, bool FINAL, int IS>
+static int launch_sweep_i(const SweepArgs &A, int nseg, stream_t s, i64 *flops_per_point, const TmapDesc &td)
+{
+    *flops_per_point = (i64)P1 * (2 * T::NT - n_first<T>() + 2 * P1 * n_has<T>());
+    bool launched = false;
+    if (P1 / IS <= 2 && !tc_small()) GSB_TRY((launch_sweep_tc<P1, T, FINAL, IS, 128>(A, nseg, s, td, &launched)));
+    else GSB_TRY((launch_sweep_tc<P1, T, FINAL, IS, 64>(A, nseg, s, td, &launched)));
+    if (launched) return 0;
     dim3 grid((unsigned)((A.ncol + 127) / 128), P1 / IS, nseg);
     auto kfn = k_sweep<P1, T, IS, FINAL>;
     GSB_LAUNCH(kfn, grid, dim3(128), s, A);

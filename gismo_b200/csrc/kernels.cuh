@@ -674,11 +674,11 @@ GSB_GLOBAL void __launch_bounds__(TC * (P1 / IS), MINB) k_sweep_tma(const SweepA
     constexpr int NIN = T::NIN, G = P1 / IS;
     constexpr int TAB_DOUBLES = NQ * P1 * 2;
     constexpr int STAGE_DOUBLES = (NQ * NIN * TC + TAB_DOUBLES + 15) / 16 * 16;   // 128-byte multiple (TMA destination alignment)
+    constexpr int NWARP = TC * G / 32;
     double *sdata = reinterpret_cast<double *>(smem_raw);
     unsigned long long *full = reinterpret_cast<unsigned long long *>(sdata + (size_t)NSTAGE * STAGE_DOUBLES);
     unsigned long long *empty = full + NSTAGE;
     const int tid = threadIdx.x, grp = tid / TC, lcol = tid - grp * TC, warp = tid >> 5, lane = tid & 31;
-    constexpr int NWARP = TC * G / 32;
     const int sg = blockIdx.z;
     const int e_begin = A.seg[4 * sg + 0], e_end = A.seg[4 * sg + 1], x_min = A.seg[4 * sg + 2], x_max = A.seg[4 * sg + 3];
     const i64 outer = blockIdx.x / tiles_per_outer;
@@ -695,8 +695,7 @@ GSB_GLOBAL void __launch_bounds__(TC * (P1 / IS), MINB) k_sweep_tma(const SweepA
     constexpr int NROWS = ROWB ? NIN : NQ * NIN;
     auto issue = [&](int e, int s) {   // executed by warp 0: fill stage s (= (e - e_begin) % NSTAGE) with span e
         double *dst = sdata + (size_t)s * STAGE_DOUBLES;
-        const double *src = tile + (i64)(e - A.e_in0) * A.in_es;
-        if (!ROWB && A.in_blk_tc) {   // tile-blocked input: the whole stage is one contiguous chunk
+        if (!ROWB && A.in_blk_tc) {       // tile-blocked input: the whole stage is one contiguous chunk
             if (lane == 0) {
                 mbar_expect_tx(full + s, NQ * NIN * TC * 8 + TAB_DOUBLES * 8);
                 bulk_g2s(dst + NQ * NIN * TC, A.tab + (i64)e * NQ * P1, TAB_DOUBLES * 8, full + s);
@@ -704,7 +703,7 @@ GSB_GLOBAL void __launch_bounds__(TC * (P1 / IS), MINB) k_sweep_tma(const SweepA
             }
             return;
         }
-        if (use_tmap) {       // one box per span (out-of-range columns are zero-filled and still counted)
+        if (use_tmap) {                   // one box per span (out-of-range columns are zero-filled and still counted)
             if (lane == 0) {
                 mbar_expect_tx(full + s, NQ * NIN * TC * 8 + TAB_DOUBLES * 8);
                 bulk_g2s(dst + NQ * NIN * TC, A.tab + (i64)e * NQ * P1, TAB_DOUBLES * 8, full + s);
@@ -716,6 +715,7 @@ GSB_GLOBAL void __launch_bounds__(TC * (P1 / IS), MINB) k_sweep_tma(const SweepA
             }
             return;
         }
+        const double *src = tile + (i64)(e - A.e_in0) * A.in_es;
         if (lane == 0) {
             mbar_expect_tx(full + s, row_bytes * NROWS + TAB_DOUBLES * 8);
             bulk_g2s(dst + NQ * NIN * TC, A.tab + (i64)e * NQ * P1, TAB_DOUBLES * 8, full + s);
@@ -738,10 +738,17 @@ GSB_GLOBAL void __launch_bounds__(TC * (P1 / IS), MINB) k_sweep_tma(const SweepA
     core.zero();
     const bool blk = !ROWB && A.in_blk_tc != 0;
     int f0 = A.first[e_begin], nx = A.nexit[e_begin];
-    int s = 0; unsigned par = 0;
+    int s = 0; unsigned par = 0;          // stage / phase parity of span e
+    int sp = 0; unsigned parp = 0;        // stage / parity of span e-1 (refilled with one span of lag)
     for (int e = e_begin; e < e_end; ++e) {
         // next span's window data: fetched now, consumed one iteration later
         const int f0n = (e + 1 < e_end) ? A.first[e + 1] : 0, nxn = (e + 1 < e_end) ? A.nexit[e + 1] : 0;
+        // warp 0 re-arms the stage of the PREVIOUS span: the other warps had a whole span of time to
+        // release it, so this wait is normally already satisfied and nobody is serialised behind it
+        if (warp == 0 && e > e_begin) {
+            if (e - 1 + NSTAGE < e_end) { mbar_wait(empty + sp, parp); issue(e - 1 + NSTAGE, sp); }
+            if (++sp == NSTAGE) { sp = 0; parp ^= 1u; }
+        }
         mbar_wait(full + s, par);
         if (live) {
             const double *sd = sdata + (size_t)s * STAGE_DOUBLES;
@@ -772,11 +779,7 @@ GSB_GLOBAL void __launch_bounds__(TC * (P1 / IS), MINB) k_sweep_tma(const SweepA
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(empty + s);
-        if (warp == 0 && e + NSTAGE < e_end) {     // refill this stage once every warp has released it
-            mbar_wait(empty + s, par);
-            issue(e + NSTAGE, s);
-        }
+        if (lane == 0) mbar_arrive(empty + s);       // this warp is done with the stage
         if (live) core.exits(A, fc, obase, nx, f0, grp, x_min, x_max);
         f0 = f0n; nx = nxn;
         if (++s == NSTAGE) { s = 0; par ^= 1u; }
