@@ -303,11 +303,6 @@ constexpr int pick_is(int P1, int NOUT)
     for (int d = 1; d <= P1; ++d) if (P1 % d == 0 && d * P1 * NOUT <= 40) best = d;
     return best;
 }
-// columns per CTA of a sweep: 64 when several owner-slot groups share the tile; for 1-2 groups 128, or 64
-// (GSB200_TC=64) to fit two CTAs per SM
-static int g_tc_small = -1;
-static bool tc_small() { if (g_tc_small < 0) { const char *e = getenv("GSB200_TC"); g_tc_small = (e && atoi(e) == 64) ? 1 : 0; } return g_tc_small == 1; }
-static int tc_for(int P1, int NOUT) { return (P1 / pick_is(P1, NOUT) <= 2 && !tc_small()) ? 128 : 64; }
 template <class T> constexpr int n_has() { int n = 0; for (int o = 0; o < T::NOUT; ++o) for (int b = 0; b < 2; ++b) if (T::has(o, b)) ++n; return n; }
 template <class T> constexpr int n_first() { int n = 0; for (int k = 0; k < T::NT; ++k) if (T::first(k)) ++n; return n; }
 
@@ -354,35 +349,35 @@ static bool tma_ok(const SweepArgs &A, bool final_stage)
     const bool disabled = getenv("GSB200_NO_TMA") != 0;
     if (disabled) return false;
     auto even = [](i64 v) { return (v & 1) == 0; };
-    if (A.in_blk_tc && !final_stage) return ((size_t)A.in & 15) == 0;
     if (!even(A.in_cs) || !even(A.in_es) || !even(A.in_os) || ((size_t)A.in & 15)) return false;
     if (final_stage) return A.in_ts == 1 && A.in_is == A.q && (even(A.q) || even(A.ninner));
     return A.in_is == 1 && even(A.in_ts) && even(A.ninner);
 #endif
 }
 
-template <int P1, class T, bool FINAL, int IS, int TC>
-static int launch_sweep_tc(const SweepArgs &A, int nseg, stream_t s, const TmapDesc &td, bool *launched)
+template <int P1, class T, bool FINAL, int IS>
+static int launch_sweep_i(const SweepArgs &A, int nseg, stream_t s, i64 *flops_per_point, const TmapDesc &td)
 {
-    *launched = false;
+    *flops_per_point = (i64)P1 * (2 * T::NT - n_first<T>() + 2 * P1 * n_has<T>());
 #ifndef GSB200_EMULATE
+    constexpr int G0 = P1 / IS, TC0 = (G0 <= 2) ? 128 : 64;
     TensorMapBlob tmap; memset(&tmap, 0, sizeof tmap);
-    // measured on B200 (profiles/): tiled-TMA boxes only pay off for long contiguous rows; GSB200_TMAP=all|none overrides
+    // measured on B200 (profiles/): one tiled-TMA box per span wins for the first sweep (long contiguous
+    // rows, 4.3 vs 6.2 ms) but loses to per-row bulk copies for the strided later sweeps; GSB200_TMAP=all|none overrides
     const char *pol = getenv("GSB200_TMAP");
-    const bool want_tmap = pol ? !strcmp(pol, "all") : false;
-    const bool no_tmap = !want_tmap || getenv("GSB200_NO_TMA") != 0 || A.in_blk_tc;
-    const bool use_tmap = !no_tmap && A.q == P1 && encode_tmap(&tmap, A.in, td, TC, P1, T::NIN);
-    if (A.in_blk_tc && A.in_blk_tc != TC) { set_error("internal: blocked layout tile %d != kernel tile %d", A.in_blk_tc, TC); return GSB200_EINVAL; }
+    const bool want_tmap = pol ? !strcmp(pol, "all") : (td.rank == 3);
+    const bool no_tmap = !want_tmap || getenv("GSB200_NO_TMA") != 0;
+    const bool use_tmap = !no_tmap && A.q == P1 && encode_tmap(&tmap, A.in, td, TC0, P1, T::NIN);
     if (use_tmap || tma_ok(A, FINAL)) {
-        constexpr int G = P1 / IS, NQ = P1;
-        constexpr int MINB_HI = (TC * G <= 128) ? (FINAL ? 4 : 2) : (TC * G <= 256 ? 2 : 1);
+        constexpr int G = P1 / IS, TC = (G <= 2) ? 128 : 64, NQ = P1;
+        constexpr int MINB_HI = (TC * G <= 128) ? 4 : (TC * G <= 256 ? 2 : 1);
         const size_t stage = (size_t)((NQ * T::NIN * TC + NQ * P1 * 2 + 15) / 16 * 16) * sizeof(double);
         const char *env = getenv("GSB200_MINB");
         const bool hi = env ? atoi(env) > 1 : (TC * G <= 128);
         // ring depth: as many spans in flight as the shared memory left per resident CTA allows
         const size_t budget = (size_t)200 * 1024 / (hi ? MINB_HI : 1);
         const char *envs = getenv("GSB200_NSTAGE");
-        int nstage = (int)std::min<size_t>(envs ? (size_t)atoi(envs) : 6, budget / stage);
+        int nstage = (int)std::min<size_t>(envs ? (size_t)atoi(envs) : 8, budget / stage);
         if (A.q == NQ && nstage >= 2) {
             const size_t smem = nstage * stage + 2 * nstage * sizeof(unsigned long long);
             const int tiles = (int)((A.ninner + TC - 1) / TC);
@@ -395,30 +390,26 @@ static int launch_sweep_tc(const SweepArgs &A, int nseg, stream_t s, const TmapD
                 attributed.push_back((const void *)kfn);
             }
             if (!dry_run()) { kfn<<<dim3((unsigned)(nouter * tiles), 1, nseg), dim3(TC * G), smem, s>>>(A, tiles, nstage, tmap, use_tmap ? 1 : 0); note_launch(); }
-            *launched = true;
+            return 0;
         }
     }
 #endif
-    return 0;
-}
-
-template <int P1, class T, bool FINAL, int IS>
-static int launch_sweep_i(const SweepArgs &A, int nseg, stream_t s, i64 *flops_per_point, const TmapDesc &td)
-{
-    *flops_per_point = (i64)P1 * (2 * T::NT - n_first<T>() + 2 * P1 * n_has<T>());
-    bool launched = false;
-    if (P1 / IS <= 2 && !tc_small()) GSB_TRY((launch_sweep_tc<P1, T, FINAL, IS, 128>(A, nseg, s, td, &launched)));
-    else GSB_TRY((launch_sweep_tc<P1, T, FINAL, IS, 64>(A, nseg, s, td, &launched)));
-    if (launched) return 0;
     dim3 grid((unsigned)((A.ncol + 127) / 128), P1 / IS, nseg);
     auto kfn = k_sweep<P1, T, IS, FINAL>;
     GSB_LAUNCH(kfn, grid, dim3(128), s, A);
     return 0;
 }
+// owner slots per thread: the largest that keeps the accumulators in registers, or (GSB200_ISDIV=1)
+// half of it: twice the threads per column tile, half the accumulators each -> more resident warps
 template <int P1, class T, bool FINAL>
 static int launch_sweep_t(const SweepArgs &A, int nseg, stream_t s, i64 *fpp, const TmapDesc &td)
 {
-    return launch_sweep_i<P1, T, FINAL, pick_is(P1, T::NOUT)>(A, nseg, s, fpp, td);
+    constexpr int IS = pick_is(P1, T::NOUT);
+    if constexpr (!FINAL && IS % 2 == 0 && IS > 1) {
+        static const char *env = getenv("GSB200_ISDIV");
+        if (env && atoi(env) > 0) return launch_sweep_i<P1, T, FINAL, IS / 2>(A, nseg, s, fpp, td);
+    }
+    return launch_sweep_i<P1, T, FINAL, IS>(A, nseg, s, fpp, td);
 }
 template <class T, bool FINAL>
 static int launch_sweep(int P1, const SweepArgs &A, int nseg, stream_t s, i64 *fpp, const TmapDesc &td)
@@ -524,42 +515,31 @@ static int assemble_pass(gsb200_assembler *a)
         const i64 NI0 = (i64)d0.nfun * (2 * d0.p + 1), NI1 = dim == 3 ? (i64)d1.nfun * (2 * d1.p + 1) : 1;
         const i64 n0 = d0.nfun, n1 = dim == 3 ? d1.nfun : 1;
         const i64 W0 = 2 * d0.p + 1, W1 = dim == 3 ? 2 * d1.p + 1 : 1;
-        // tile widths of the consumers: D is blocked for the first sweep, A1 (3-D) for the second
-        const int TC1 = tc_for(d0.p + 1, no1), TC2 = dim == 3 ? tc_for(d1.p + 1, no2) : 0;
-        auto sizes = [&](i64 QLc, i64 *sD, i64 *sA1, i64 *sA2, i64 *sF, i64 *sV1, i64 *sV2) {
-            const i64 NT1 = (Q1 * QLc + TC1 - 1) / TC1;                     // column tiles of sweep 1 (columns = (q1, qL) or qL)
-            *sD = NT1 * Q0 * ncD * TC1;
-            *sA1 = dim == 3 ? NI0 * ((QLc + TC2 - 1) / TC2) * Q1 * no1 * TC2 : no1 * NI0 * QLc;
-            *sA2 = dim == 3 ? no2 * NI1 * NI0 * QLc : 0;
-            *sF = nf * Q0 * Q1 * QLc; *sV1 = n0 * Q1 * QLc; *sV2 = dim == 3 ? n1 * n0 * QLc : 0;
-        };
-        auto need_bytes = [&](i64 QLc) { i64 s[6]; sizes(QLc, s, s + 1, s + 2, s + 3, s + 4, s + 5); i64 t = 0; for (int k = 0; k < 6; ++k) t += (s[k] + 31) / 32 * 32; return (size_t)t * 8; };
-        const i64 minpts = (i64)(dL.flast[P.own_lo] - dL.ffirst[P.own_lo] + 1) * dL.q;
-        if ((i64)need_bytes(minpts) > limit) { set_error("workspace limit %lld B too small: one slab of patch %zu needs %lld B", (long long)limit, ip, (long long)need_bytes(minpts)); return GSB200_ENOMEM; }
+        // doubles of workspace per last-direction quadrature point
+        i64 perq = ncD * Q0 * Q1 + no1 * NI0 * Q1 + (dim == 3 ? no2 * NI1 * NI0 : 0) + nf * Q0 * Q1 + n0 * Q1 + (dim == 3 ? n1 * n0 : 0);
+        i64 maxpts = limit / (perq * 8);
+        const i64 minpts = (i64)(dL.p + 1) * dL.q;
+        if (maxpts < minpts) { set_error("workspace limit %lld B too small: one slab of patch %zu needs %lld B", (long long)limit, ip, (long long)(perq * 8 * minpts)); return GSB200_ENOMEM; }
         int x_lo = P.own_lo;
         while (x_lo < P.own_hi) {
             // largest chunk [x_lo,x_hi) whose element footprint fits
             int x_hi = x_lo + 1;
-            while (x_hi < P.own_hi && (i64)need_bytes((i64)(dL.flast[x_hi] - dL.ffirst[x_lo] + 1) * dL.q) <= limit) ++x_hi;
+            while (x_hi < P.own_hi && (i64)(dL.flast[x_hi] - dL.ffirst[x_lo] + 1) * dL.q <= maxpts) ++x_hi;
             const int eL0 = dL.ffirst[x_lo], eL1 = dL.flast[x_hi - 1] + 1, ELc = eL1 - eL0;
             const i64 QLc = (i64)ELc * dL.q;
-            const size_t need = need_bytes(QLc);
-            if ((i64)need > limit) { set_error("workspace limit %lld B too small: a slab of patch %zu needs %lld B", (long long)limit, ip, (long long)need); return GSB200_ENOMEM; }
+            const size_t need = (size_t)(perq * QLc) * 8 + 6 * 256;
             if (need > a->ws_size) {
                 dev_free(a->ws); a->ws = 0; a->ws_size = 0;
                 GSB_TRY(dev_malloc(&a->ws, need)); a->ws_size = need;
             }
             double *w = (double *)a->ws;
             auto carve = [&](i64 count) { double *p = w; w += (count + 31) / 32 * 32; return p; };   // 256-byte aligned pieces
-            i64 sD, sA1, sA2, sF, sV1, sV2;
-            sizes(QLc, &sD, &sA1, &sA2, &sF, &sV1, &sV2);
-            double *D = carve(sD);
-            double *A1 = carve(sA1);
-            double *A2 = carve(sA2);
-            double *F = carve(sF);
-            double *V1 = carve(sV1);
-            double *V2 = carve(sV2);
-            const i64 NT1 = (Q1 * QLc + TC1 - 1) / TC1, NT2 = dim == 3 ? (QLc + TC2 - 1) / TC2 : 0;
+            double *D = carve(ncD * Q0 * Q1 * QLc);
+            double *A1 = carve(no1 * NI0 * Q1 * QLc);
+            double *A2 = carve(dim == 3 ? no2 * NI1 * NI0 * QLc : 0);
+            double *F = carve(nf * Q0 * Q1 * QLc);
+            double *V1 = carve(n0 * Q1 * QLc);
+            double *V2 = carve(dim == 3 ? n1 * n0 * QLc : 0);
             const i64 npts = Q0 * Q1 * QLc;
             ++a->tm.nchunks;
 
@@ -577,7 +557,7 @@ static int assemble_pass(gsb200_assembler *a)
                 G.coefs = P.d_coefs; G.weights = P.d_weights; G.ngeo_total = P.ngeo_total;
                 G.form = a->form; G.brow = brow; G.bcol = bcol; G.lambda = a->coef[0]; G.mu = a->coef[1];
                 G.symD = kind == KIND_SYM;
-                G.D = D; G.dstride = npts; G.d_tc = TC1; G.d_ncomp = ncD;
+                G.D = D; G.dstride = npts;
                 if (blk == 0 && nf) { G.F = F; G.fstride = npts; G.nf = nf; for (int c = 0; c < nf; ++c) G.prog[c] = a->progs[c]; }
                 mark(a, 0);
                 {
@@ -607,7 +587,7 @@ static int assemble_pass(gsb200_assembler *a)
                 auto base_args = [&](const Dir1D &d) {
                     SweepArgs A; memset(&A, 0, sizeof A);
                     A.first = d.d_first; A.nexit = d.d_nexit; A.tab = d.d_tab; A.q = d.q; A.p = d.p; A.fin = Fa;
-                    A.out_bq = 1; A.out_od = 1; A.out_bq2 = (i64)1 << 62; return A;
+                    A.out_bq = 1; A.out_od = 1; return A;
                 };
                 auto account = [&](int slot, const SweepArgs &A, const std::vector<int> &seg, i64 fpp, int nin, int nout, i64 npairs_out) {
                     i64 pts = 0;
@@ -619,12 +599,9 @@ static int assemble_pass(gsb200_assembler *a)
                 if (dim == 3) {
                     {   // S1: direction 0
                         SweepArgs A = base_args(d0);
-                        // D blocked [tile][q0][c][TC1]; A1 blocked for sweep 2: [(i0,d0)][q2 tile][q1][o][TC2]
-                        A.in = D; A.in_blk_tc = TC1; A.in_tiles = NT1; A.in_tile_stride = Q0 * ncD * TC1;
-                        A.in_cs = TC1; A.in_ts = (i64)ncD * TC1; A.in_es = (i64)d0.q * ncD * TC1; A.in_os = 0; A.in_is = 1; A.e_in0 = 0;
+                        A.in = D; A.in_cs = npts; A.in_es = (i64)d0.q * Q1 * QLc; A.in_ts = Q1 * QLc; A.in_os = 0; A.in_is = 1; A.e_in0 = 0;
                         A.ncol = Q1 * QLc; A.ninner = A.ncol;
-                        A.out = A1; A.out_cs = TC2; A.out_ds = NT2 * Q1 * no1 * TC2; A.out_fs = W0 * A.out_ds; A.out_os = 0;
-                        A.out_bq = QLc; A.out_bs = (i64)no1 * TC2; A.out_bq2 = TC2; A.out_bs2 = Q1 * no1 * TC2; A.out_is = 1;
+                        A.out = A1; A.out_cs = NI0 * Q1 * QLc; A.out_fs = (2 * d0.p + 1) * Q1 * QLc; A.out_ds = Q1 * QLc; A.out_os = 0; A.out_bq = A.ncol + 1; A.out_bs = 0; A.out_is = 1;
                         const int nseg = nseg_for(A.ncol * (d0.p + 1), d0.nfun, d0.p + 1);
                         std::vector<int> seg = make_segments(d0, 0, d0.nfun, nseg);
                         A.seg = a->d_seg + segoff; GSB_TRY(upload_segments(a, seg, &segoff));
@@ -635,8 +612,7 @@ static int assemble_pass(gsb200_assembler *a)
                     }
                     {   // S2: direction 1
                         SweepArgs A = base_args(d1);
-                        A.in = A1; A.in_blk_tc = TC2; A.in_tiles = NT2; A.in_tile_stride = Q1 * no1 * TC2;
-                        A.in_cs = TC2; A.in_ts = (i64)no1 * TC2; A.in_es = (i64)d1.q * no1 * TC2; A.in_os = 0; A.in_is = 1; A.e_in0 = 0;
+                        A.in = A1; A.in_cs = NI0 * Q1 * QLc; A.in_es = (i64)d1.q * QLc; A.in_ts = QLc; A.in_os = Q1 * QLc; A.in_is = 1; A.e_in0 = 0;
                         A.ncol = NI0 * QLc; A.ninner = QLc;
                         // A2[g][i1][e2][i0][d1][d0][t]: the last sweep then writes (d1,d0)-contiguous runs of each CSC column
                         A.out = A2; A.out_cs = NI1 * ELc * NI0 * dL.q; A.out_fs = (i64)ELc * NI0 * W1 * dL.q; A.out_ds = (i64)W0 * dL.q;
@@ -664,8 +640,7 @@ static int assemble_pass(gsb200_assembler *a)
                 } else {
                     {   // S1: direction 0
                         SweepArgs A = base_args(d0);
-                        A.in = D; A.in_blk_tc = TC1; A.in_tiles = NT1; A.in_tile_stride = Q0 * ncD * TC1;
-                        A.in_cs = TC1; A.in_ts = (i64)ncD * TC1; A.in_es = (i64)d0.q * ncD * TC1; A.in_os = 0; A.in_is = 1; A.e_in0 = 0;
+                        A.in = D; A.in_cs = npts; A.in_es = (i64)d0.q * QLc; A.in_ts = QLc; A.in_os = 0; A.in_is = 1; A.e_in0 = 0;
                         A.ncol = QLc; A.ninner = QLc;
                         A.out = A1; A.out_cs = (i64)ELc * NI0 * dL.q; A.out_fs = (i64)(2 * d0.p + 1) * dL.q; A.out_ds = dL.q; A.out_os = 0; A.out_bq = dL.q; A.out_bs = NI0 * dL.q; A.out_is = 1;
                         const int nseg = nseg_for(A.ncol * (d0.p + 1), d0.nfun, d0.p + 1);

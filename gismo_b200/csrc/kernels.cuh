@@ -231,8 +231,7 @@ struct GeoArgs {
     const double *coefs; const double *weights; i64 ngeo_total;
     int form, brow, bcol; double lambda, mu;
     int symD;                      // 1: write the 3/6 unique components, 0: all dim*dim
-    double *D; i64 dstride;        // may be NULL (load only); blocked as [tile][q0][comp][d_tc] when d_tc > 0
-    int d_tc, d_ncomp; i64 d_colstride;   // column = (middle dirs, last dir) flattened with pitch d_colstride per q0 plane row
+    double *D; i64 dstride;        // may be NULL (load only)
     double *F; i64 fstride; int nf; DevProgram prog[3];
 };
 // Thread = one point of the last direction (fastest in memory), blockIdx.y/z = the other
@@ -337,16 +336,7 @@ GSB_GLOBAL void k_geometry(const GeoArgs A)
     const double weight = hprod * wp * fabs(det);
     if (A.F) for (int c = 0; c < A.nf; ++c) A.F[c * A.fstride + id] = weight * program_eval(A.prog[c], x[0], x[1], x[2]);
     if (!A.D) return;
-    // destination of component c: plain [c][point] or tile-blocked [tile][q0][c][d_tc] (one contiguous chunk
-    // per span and column tile for the first sweep's TMA stage)
-    i64 dbase = id, dcs = A.dstride;
-    if (A.d_tc) {
-        const i64 col = (DIM == 3) ? (i64)blockIdx.y * A.qn[DIM - 1] + qlast : (i64)qlast;
-        const i64 q0 = (DIM == 3) ? blockIdx.z : blockIdx.y;
-        dbase = ((col / A.d_tc) * A.qn[0] + q0) * A.d_ncomp * A.d_tc + col % A.d_tc;
-        dcs = A.d_tc;
-    }
-    if (A.form == GSB200_FORM_MASS) { A.D[dbase] = weight; return; }
+    if (A.form == GSB200_FORM_MASS) { A.D[id] = weight; return; }
     double G[DIM][DIM];   // (J^-1 J^-T)_ab
     for (int a = 0; a < DIM; ++a) for (int b = 0; b < DIM; ++b) {
         double s = 0.0;
@@ -354,8 +344,8 @@ GSB_GLOBAL void k_geometry(const GeoArgs A)
         G[a][b] = s;
     }
     if (A.form == GSB200_FORM_POISSON) {
-        if (A.symD) { int c = 0; for (int a = 0; a < DIM; ++a) for (int b = a; b < DIM; ++b) A.D[(c++) * dcs + dbase] = weight * G[a][b]; }
-        else for (int a = 0; a < DIM; ++a) for (int b = 0; b < DIM; ++b) A.D[(a * DIM + b) * dcs + dbase] = weight * G[a][b];
+        if (A.symD) { int c = 0; for (int a = 0; a < DIM; ++a) for (int b = a; b < DIM; ++b) A.D[(c++) * A.dstride + id] = weight * G[a][b]; }
+        else for (int a = 0; a < DIM; ++a) for (int b = 0; b < DIM; ++b) A.D[(a * DIM + b) * A.dstride + id] = weight * G[a][b];
         return;
     }
     // elasticity block (row comp r = brow carried by the partner/test function, col comp c = bcol by the owner):
@@ -364,7 +354,7 @@ GSB_GLOBAL void k_geometry(const GeoArgs A)
     const int r = A.brow, cc = A.bcol;
     for (int a = 0; a < DIM; ++a) for (int b = 0; b < DIM; ++b) {
         const double E = A.lambda * Ji[b][r] * Ji[a][cc] + A.mu * (Ji[b][cc] * Ji[a][r] + (r == cc ? G[b][a] : 0.0));
-        A.D[(a * DIM + b) * dcs + dbase] = weight * E;
+        A.D[(a * DIM + b) * A.dstride + id] = weight * E;
     }
 }
 
@@ -471,10 +461,7 @@ struct SweepArgs {
     const int *seg;                                            // [nseg][4] e_begin,e_end,x_min,x_max
     const double *in; double *out;
     i64 in_cs, in_es, in_ts, in_os, in_is; int e_in0;          // input strides: comp, element, point, outer, inner
-    // tile-blocked input ([tile][point][comp][TC], one contiguous chunk per span and column tile): in_blk_tc = TC (0 = plain strides)
-    int in_blk_tc; i64 in_tiles, in_tile_stride;
     i64 out_cs, out_fs, out_ds, out_os, out_os2, out_od, out_bs, out_is, out_bq;   // output strides: comp, owner fn, delta, outer (split at out_od), block, inner
-    i64 out_bq2, out_bs2;          // second split of (inner % out_bq): (r / out_bq2) * out_bs2 + (r % out_bq2) * out_is
     i64 ncol; i64 ninner;
     // tensor-map TMA variant: which box coordinate carries the tile start, the span, the outer index
     int tm_rank, tm_dim_inner, tm_dim_e, tm_e_mul, tm_dim_outer;
@@ -582,13 +569,6 @@ struct SweepCore {
     }
 };
 
-GSB_DEVICE i64 sweep_obase(const SweepArgs &A, i64 outer, i64 inner)
-{
-    const i64 r = inner % A.out_bq;
-    return (outer / A.out_od) * A.out_os + (outer % A.out_od) * A.out_os2 + (inner / A.out_bq) * A.out_bs +
-           (r / A.out_bq2) * A.out_bs2 + (r % A.out_bq2) * A.out_is;
-}
-
 // Generic variant: inputs straight from global memory (any strides / alignment).
 template <int P1, class T, int IS, bool FINAL>
 GSB_GLOBAL void k_sweep(const SweepArgs A)
@@ -598,12 +578,11 @@ GSB_GLOBAL void k_sweep(const SweepArgs A)
     const int grp = blockIdx.y, sg = blockIdx.z;
     const int e_begin = A.seg[4 * sg + 0], e_end = A.seg[4 * sg + 1], x_min = A.seg[4 * sg + 2], x_max = A.seg[4 * sg + 3];
     const i64 outer = col / A.ninner, inner = col - outer * A.ninner;
-    const double *inp = A.in_blk_tc ? A.in + (outer * A.in_tiles + inner / A.in_blk_tc) * A.in_tile_stride + inner % A.in_blk_tc
-                                    : A.in + outer * A.in_os + inner * A.in_is;
+    const double *inp = A.in + outer * A.in_os + inner * A.in_is;
     FinalCtx fc;
     i64 obase = 0;
     if (FINAL) { if (!final_init(A.fin, outer, inner, fc)) return; }
-    else obase = sweep_obase(A, outer, inner);
+    else obase = (outer / A.out_od) * A.out_os + (outer % A.out_od) * A.out_os2 + (inner / A.out_bq) * A.out_bs + (inner % A.out_bq) * A.out_is;
     constexpr int NIN = T::NIN;
     SweepCore<P1, T, IS, FINAL> core;
     core.zero();
@@ -674,11 +653,11 @@ GSB_GLOBAL void __launch_bounds__(TC * (P1 / IS), MINB) k_sweep_tma(const SweepA
     constexpr int NIN = T::NIN, G = P1 / IS;
     constexpr int TAB_DOUBLES = NQ * P1 * 2;
     constexpr int STAGE_DOUBLES = (NQ * NIN * TC + TAB_DOUBLES + 15) / 16 * 16;   // 128-byte multiple (TMA destination alignment)
-    constexpr int NWARP = TC * G / 32;
     double *sdata = reinterpret_cast<double *>(smem_raw);
     unsigned long long *full = reinterpret_cast<unsigned long long *>(sdata + (size_t)NSTAGE * STAGE_DOUBLES);
     unsigned long long *empty = full + NSTAGE;
     const int tid = threadIdx.x, grp = tid / TC, lcol = tid - grp * TC, warp = tid >> 5, lane = tid & 31;
+    constexpr int NWARP = TC * G / 32;
     const int sg = blockIdx.z;
     const int e_begin = A.seg[4 * sg + 0], e_end = A.seg[4 * sg + 1], x_min = A.seg[4 * sg + 2], x_max = A.seg[4 * sg + 3];
     const i64 outer = blockIdx.x / tiles_per_outer;
@@ -695,15 +674,8 @@ GSB_GLOBAL void __launch_bounds__(TC * (P1 / IS), MINB) k_sweep_tma(const SweepA
     constexpr int NROWS = ROWB ? NIN : NQ * NIN;
     auto issue = [&](int e, int s) {   // executed by warp 0: fill stage s (= (e - e_begin) % NSTAGE) with span e
         double *dst = sdata + (size_t)s * STAGE_DOUBLES;
-        if (!ROWB && A.in_blk_tc) {       // tile-blocked input: the whole stage is one contiguous chunk
-            if (lane == 0) {
-                mbar_expect_tx(full + s, NQ * NIN * TC * 8 + TAB_DOUBLES * 8);
-                bulk_g2s(dst + NQ * NIN * TC, A.tab + (i64)e * NQ * P1, TAB_DOUBLES * 8, full + s);
-                bulk_g2s(dst, A.in + (i64)blockIdx.x * A.in_tile_stride + (i64)(e - A.e_in0) * A.in_es, NQ * NIN * TC * 8, full + s);
-            }
-            return;
-        }
-        if (use_tmap) {                   // one box per span (out-of-range columns are zero-filled and still counted)
+        const double *src = tile + (i64)(e - A.e_in0) * A.in_es;
+        if (use_tmap) {       // one box per span (out-of-range columns are zero-filled and still counted)
             if (lane == 0) {
                 mbar_expect_tx(full + s, NQ * NIN * TC * 8 + TAB_DOUBLES * 8);
                 bulk_g2s(dst + NQ * NIN * TC, A.tab + (i64)e * NQ * P1, TAB_DOUBLES * 8, full + s);
@@ -715,7 +687,6 @@ GSB_GLOBAL void __launch_bounds__(TC * (P1 / IS), MINB) k_sweep_tma(const SweepA
             }
             return;
         }
-        const double *src = tile + (i64)(e - A.e_in0) * A.in_es;
         if (lane == 0) {
             mbar_expect_tx(full + s, row_bytes * NROWS + TAB_DOUBLES * 8);
             bulk_g2s(dst + NQ * NIN * TC, A.tab + (i64)e * NQ * P1, TAB_DOUBLES * 8, full + s);
@@ -733,22 +704,14 @@ GSB_GLOBAL void __launch_bounds__(TC * (P1 / IS), MINB) k_sweep_tma(const SweepA
     i64 obase = 0;
     bool live = lcol < ncols;
     if (FINAL) { if (live) live = final_init(A.fin, outer, inner, fc); }
-    else obase = sweep_obase(A, outer, inner);
+    else obase = (outer / A.out_od) * A.out_os + (outer % A.out_od) * A.out_os2 + (inner / A.out_bq) * A.out_bs + (inner % A.out_bq) * A.out_is;
     SweepCore<P1, T, IS, FINAL> core;
     core.zero();
-    const bool blk = !ROWB && A.in_blk_tc != 0;
     int f0 = A.first[e_begin], nx = A.nexit[e_begin];
-    int s = 0; unsigned par = 0;          // stage / phase parity of span e
-    int sp = 0; unsigned parp = 0;        // stage / parity of span e-1 (refilled with one span of lag)
+    int s = 0; unsigned par = 0;
     for (int e = e_begin; e < e_end; ++e) {
         // next span's window data: fetched now, consumed one iteration later
         const int f0n = (e + 1 < e_end) ? A.first[e + 1] : 0, nxn = (e + 1 < e_end) ? A.nexit[e + 1] : 0;
-        // warp 0 re-arms the stage of the PREVIOUS span: the other warps had a whole span of time to
-        // release it, so this wait is normally already satisfied and nobody is serialised behind it
-        if (warp == 0 && e > e_begin) {
-            if (e - 1 + NSTAGE < e_end) { mbar_wait(empty + sp, parp); issue(e - 1 + NSTAGE, sp); }
-            if (++sp == NSTAGE) { sp = 0; parp ^= 1u; }
-        }
         mbar_wait(full + s, par);
         if (live) {
             const double *sd = sdata + (size_t)s * STAGE_DOUBLES;
@@ -773,13 +736,17 @@ GSB_GLOBAL void __launch_bounds__(TC * (P1 / IS), MINB) k_sweep_tma(const SweepA
                 for (int t = 0; t < NQ; ++t) {
                     double v[NIN];
 #pragma unroll
-                    for (int c = 0; c < NIN; ++c) v[c] = ROWB ? sd[((size_t)c * TC + lcol) * NQ + t] : (blk ? sd[((size_t)t * NIN + c) * TC + lcol] : sd[((size_t)c * NQ + t) * TC + lcol]);
+                    for (int c = 0; c < NIN; ++c) v[c] = ROWB ? sd[((size_t)c * TC + lcol) * NQ + t] : sd[((size_t)c * NQ + t) * TC + lcol];
                     core.template point<true>(v, tbs + t * P1, grp);
                 }
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(empty + s);       // this warp is done with the stage
+        if (lane == 0) mbar_arrive(empty + s);
+        if (warp == 0 && e + NSTAGE < e_end) {     // refill this stage once every warp has released it
+            mbar_wait(empty + s, par);
+            issue(e + NSTAGE, s);
+        }
         if (live) core.exits(A, fc, obase, nx, f0, grp, x_min, x_max);
         f0 = f0n; nx = nxn;
         if (++s == NSTAGE) { s = 0; par ^= 1u; }
