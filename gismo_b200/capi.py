@@ -14,7 +14,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 MAX_DIM = 3
-ABI_VERSION = 1
+ABI_VERSION = 2
 FORM_POISSON, FORM_ELASTICITY, FORM_MASS = 0, 1, 2
 RHS_NONE, RHS_PROGRAM, RHS_SAMPLES = 0, 1, 2
 
@@ -35,13 +35,17 @@ class Program(C.Structure):
     _fields_ = [("nops", C.c_int32), ("ops", _ip), ("nconsts", C.c_int32), ("consts", _dp)]
 
 
+class Neumann(C.Structure):
+    _fields_ = [("patch", C.c_int32), ("side", C.c_int32), ("ndata", C.c_int32), ("data", Program * MAX_DIM)]
+
+
 class ProblemStruct(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("form", C.c_int32), ("npatches", C.c_int32),
                 ("patches", C.POINTER(Patch)), ("ncomp", C.c_int32), ("nfree", C.c_int32),
                 ("nfixed", C.c_int32), ("fixed", _dp), ("nrhs", C.c_int32), ("coef", C.c_double * 4),
                 ("quA", C.c_double), ("quB", C.c_int32), ("rhs_kind", C.c_int32),
                 ("rhs_programs", C.POINTER(Program)), ("rhs_samples", C.POINTER(_dp)),
-                ("rank", C.c_int32), ("nranks", C.c_int32)]
+                ("rank", C.c_int32), ("nranks", C.c_int32), ("nneumann", C.c_int32), ("neumann", C.POINTER(Neumann))]
 
 
 class DeviceView(C.Structure):
@@ -95,7 +99,8 @@ class Problem:
     def __init__(self, patches: List[PatchData], nfree: int, nfixed: int, form: int = FORM_POISSON,
                  ncomp: int = 1, fixed: Optional[np.ndarray] = None, nrhs: int = 1,
                  coef: Sequence[float] = (0.0, 0.0), quA: float = 1.0, quB: int = 1,
-                 rhs_programs: Optional[List["CompiledProgram"]] = None, rank: int = 0, nranks: int = 1):
+                 rhs_programs: Optional[List["CompiledProgram"]] = None, rank: int = 0, nranks: int = 1,
+                 neumann: Optional[List[tuple]] = None):
         self.patches = patches
         self.nfree, self.nfixed, self.form, self.ncomp, self.nrhs = int(nfree), int(nfixed), form, ncomp, nrhs
         self.fixed = None if fixed is None else np.asfortranarray(np.asarray(fixed, dtype=np.float64).reshape(nfixed, -1))
@@ -136,6 +141,20 @@ class Problem:
         else:
             s.rhs_kind = RHS_NONE
         s.rank, s.nranks = rank, nranks
+        # neumann: list of (patch, side, [CompiledProgram, ...])
+        self.neumann = neumann or []
+        if self.neumann:
+            nm = (Neumann * len(self.neumann))()
+            for i, (patch, side, progs) in enumerate(self.neumann):
+                nm[i].patch, nm[i].side, nm[i].ndata = int(patch), int(side), len(progs)
+                for k, cp in enumerate(progs):
+                    nm[i].data[k].nops = len(cp.ops)
+                    nm[i].data[k].ops = cp.ops.ctypes.data_as(_ip)
+                    nm[i].data[k].nconsts = len(cp.consts)
+                    nm[i].data[k].consts = cp.consts.ctypes.data_as(_dp)
+            self._nm = nm
+            s.nneumann = len(self.neumann)
+            s.neumann = nm
         self.struct = s
 
     @property

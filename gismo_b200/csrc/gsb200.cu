@@ -65,6 +65,8 @@ struct Dir1D {
     int *d_first = 0, *d_nexit = 0, *d_plo = 0, *d_phi = 0, *d_ffirst = 0, *d_flast = 0;
     double2 *d_tab = 0; double *d_upt = 0, *d_hpt = 0, *d_gw = 0, *d_gwp = 0;
     double2 *d_gtab = 0; int *d_gfirst = 0; int pg1 = 0, ngeo = 0;
+    // basis values at the two ends of the parameter interval (Neumann sides): [0] lower, [1] upper
+    double bval[2][GSB_MAXP + 1]; int bfirst[2]; double2 bgeo[2][GSB_MAXP + 1]; int bgfirst[2];
     void release() {
         dev_free(d_first); dev_free(d_nexit); dev_free(d_plo); dev_free(d_phi); dev_free(d_ffirst); dev_free(d_flast);
         dev_free(d_tab); dev_free(d_upt); dev_free(d_hpt); dev_free(d_gw); dev_free(d_gwp); dev_free(d_gtab); dev_free(d_gfirst);
@@ -92,6 +94,19 @@ static int build_dir(Dir1D &d, const double *kn, int nk, int p, int q, const dou
     for (int f = 0; f < d.nfun; ++f) {
         if (d.flast[f] < 0) { set_error("basis function %d has empty support (knot multiplicity > degree+1?)", f); return GSB200_EINVAL; }
         d.plo[f] = d.first[d.ffirst[f]]; d.phi[f] = d.first[d.flast[f]] + p;
+    }
+    for (int side = 0; side < 2; ++side) {      // boundary evaluations for the Neumann load
+        const double ub = side ? kn[nk - p - 1] : kn[p];
+        const int s = side ? d.span.back() : d.span.front();
+        double val[GSB_MAXP + 1], der[GSB_MAXP + 1];
+        bspline_ders(kn, p, s, ub, val, der);
+        for (int a = 0; a <= p; ++a) d.bval[side][a] = val[a];
+        d.bfirst[side] = s - p;
+        int gs = gp;                              // geometry span containing ub
+        if (side) { gs = gnk - gp - 2; while (gkn[gs] == gkn[gs + 1]) --gs; } else { while (gkn[gs] == gkn[gs + 1]) ++gs; }
+        bspline_ders(gkn, gp, gs, ub, val, der);
+        for (int a = 0; a <= gp; ++a) d.bgeo[side][a] = make_double2(val[a], der[a]);
+        d.bgfirst[side] = gs - gp;
     }
     std::vector<double> gx, gw;
     gauss_rule(q, gx, gw);
@@ -155,6 +170,8 @@ struct gsb200_assembler {
     i64 *d_colptr = 0; int *d_inner = 0; int *d_npre = 0;
     i64 nnz = 0;
     std::vector<DevProgram> progs; std::vector<void *> prog_bufs;
+    struct NeumannSide { int patch, side, ndata; DevProgram prog[3]; };
+    std::vector<NeumannSide> neumann; double *d_face = 0; size_t face_cap = 0;
     stream_t stream = 0;
     bool pattern_built = false, assembled = false, any_generic = false;
     i64 ws_limit = 0; void *ws = 0; size_t ws_size = 0;
@@ -170,7 +187,7 @@ struct gsb200_assembler {
         for (auto &p : patches) p.release();
         dev_free(d_fixed); dev_free(d_rhs); dev_free(d_values); dev_free(d_colptr); dev_free(d_inner); dev_free(d_npre);
         for (void *b : prog_bufs) dev_free(b);
-        dev_free(ws); dev_free(d_seg);
+        dev_free(ws); dev_free(d_seg); dev_free(d_face);
         for (int k = 0; k < 6; ++k) dev_free(cg[k]);
 #ifndef GSB200_EMULATE
         for (auto e : ev) cudaEventDestroy(e);
@@ -701,6 +718,36 @@ static int assemble_pass(gsb200_assembler *a)
             x_lo = x_hi;
         }
     }
+    // ---------------- Neumann boundary load (rank 0 of a multi-rank run adds it once per side it owns)
+    for (const auto &ns : a->neumann) {
+        PatchDev &P = a->patches[ns.patch];
+        const int dir = (ns.side - 1) / 2, upper = (ns.side - 1) % 2;
+        // the side belongs to the rank owning the boundary function layer (last direction) or, for other
+        // directions, it is split by the same slab ownership through the dof rows: keep it simple and exact:
+        // only the rank that owns the patch's first slab assembles side loads
+        if (!(P.own_lo == 0 && P.own_hi > 0)) continue;
+        FaceArgs F; memset(&F, 0, sizeof F);
+        FaceLoadArgs Lg; memset(&Lg, 0, sizeof Lg);
+        F.dim = dim; F.dir = dir; F.upper = upper; Lg.dim = dim; Lg.dir = dir;
+        i64 npt = 1, nfn = 1;
+        for (int k = 0; k < dim; ++k) {
+            const Dir1D &d = P.dir[k];
+            F.qn[k] = d.Q; F.gtab[k] = d.d_gtab; F.gfirst[k] = d.d_gfirst; F.pg1[k] = d.pg1; F.ngeo[k] = d.ngeo; F.hpt[k] = d.d_hpt; F.gwp[k] = d.d_gwp;
+            Lg.nfun[k] = d.nfun; Lg.p1[k] = d.p + 1; Lg.q[k] = d.q; Lg.Q[k] = d.Q; Lg.ffirst[k] = d.d_ffirst; Lg.flast[k] = d.d_flast; Lg.tab[k] = d.d_tab;
+            if (k != dir) { npt *= d.Q; nfn *= d.nfun; }
+        }
+        const Dir1D &dd = P.dir[dir];
+        for (int k2 = 0; k2 < dd.pg1; ++k2) F.bgeo[k2] = dd.bgeo[upper][k2];
+        F.bgfirst = dd.bgfirst[upper];
+        for (int k2 = 0; k2 <= dd.p; ++k2) Lg.bval[k2] = dd.bval[upper][k2];
+        Lg.bfirst = dd.bfirst[upper]; Lg.nb1 = dd.p + 1;
+        F.coefs = P.d_coefs; F.weights = P.d_weights; F.ngeo_total = P.ngeo_total;
+        F.ndata = ns.ndata; for (int c = 0; c < ns.ndata; ++c) F.prog[c] = ns.prog[c];
+        if ((size_t)npt > a->face_cap) { dev_free(a->d_face); a->d_face = 0; GSB_TRY(dev_malloc((void **)&a->d_face, sizeof(double) * (size_t)npt)); a->face_cap = (size_t)npt; }
+        F.Fb = a->d_face; Lg.Fb = a->d_face; Lg.dofmap = P.d_dofmap; Lg.rhs = a->d_rhs; Lg.nfree = N;
+        if (dim == 2) { GSB_LAUNCH(k_face_geometry<2>, dim3((unsigned)((npt + 127) / 128)), dim3(128), s, F); GSB_LAUNCH(k_face_load<2>, dim3((unsigned)((nfn + 127) / 128)), dim3(128), s, Lg); }
+        else { GSB_LAUNCH(k_face_geometry<3>, dim3((unsigned)((npt + 127) / 128)), dim3(128), s, F); GSB_LAUNCH(k_face_load<3>, dim3((unsigned)((nfn + 127) / 128)), dim3(128), s, Lg); }
+    }
     mark(a, 6);
     if (dry_run()) return 0;
     GSB_TRY(dev_last_error("assembly kernels"));
@@ -821,24 +868,35 @@ int gsb200_create(const gsb200_problem *pb, int device, gsb200_assembler **out)
         else { P.own_lo = 0; P.own_hi = (ip % pb->nranks == pb->rank) ? nL : 0; }
     }
     if (!rc && pb->fixed) { std::vector<double> fx(pb->fixed, pb->fixed + (size_t)pb->nfixed * pb->nrhs); rc = upload(&a->d_fixed, fx, a->stream); }
+    auto upload_program = [&](const gsb200_program &pr, DevProgram *out) -> int {
+        if (pr.nops < 1 || pr.nops > GSB200_PROGRAM_MAX_OPS || !pr.ops) { set_error("source/boundary program has bad length %d", pr.nops); return GSB200_EINVAL; }
+        std::vector<int> ops(pr.ops, pr.ops + pr.nops); std::vector<double> cs(pr.consts, pr.consts + pr.nconsts);
+        int *d_ops = 0; double *d_cs = 0;
+        GSB_TRY(upload(&d_ops, ops, a->stream)); a->prog_bufs.push_back(d_ops);
+        GSB_TRY(upload(&d_cs, cs, a->stream)); a->prog_bufs.push_back(d_cs);
+        DevProgram dp; memset(&dp, 0, sizeof dp); dp.ops = d_ops; dp.consts = d_cs; dp.nops = pr.nops;
+        if (pr.nops <= GSB_INLINE_OPS && pr.nconsts <= GSB_INLINE_CONSTS) {
+            dp.inl = 1;
+            for (int k = 0; k < pr.nops; ++k) dp.iops[k] = (signed char)pr.ops[k];
+            for (int k = 0; k < pr.nconsts; ++k) dp.iconsts[k] = pr.consts[k];
+        }
+        *out = dp;
+        return 0;
+    };
     if (!rc && pb->rhs_kind == GSB200_RHS_PROGRAM) {
         const int np = pb->form == GSB200_FORM_ELASTICITY ? pb->ncomp : pb->nrhs;
         if (!pb->rhs_programs) { set_error("rhs_kind=PROGRAM but no programs"); rc = GSB200_EINVAL; }
-        for (int c = 0; c < np && !rc; ++c) {
-            const gsb200_program &pr = pb->rhs_programs[c];
-            if (pr.nops < 1 || pr.nops > GSB200_PROGRAM_MAX_OPS) { set_error("rhs program %d has bad length", c); rc = GSB200_EINVAL; break; }
-            std::vector<int> ops(pr.ops, pr.ops + pr.nops); std::vector<double> cs(pr.consts, pr.consts + pr.nconsts);
-            int *d_ops = 0; double *d_cs = 0;
-            if ((rc = upload(&d_ops, ops, a->stream))) break;
-            if ((rc = upload(&d_cs, cs, a->stream))) break;
-            a->prog_bufs.push_back(d_ops); a->prog_bufs.push_back(d_cs);
-            DevProgram dp; memset(&dp, 0, sizeof dp); dp.ops = d_ops; dp.consts = d_cs; dp.nops = pr.nops;
-            if (pr.nops <= GSB_INLINE_OPS && pr.nconsts <= GSB_INLINE_CONSTS) {
-                dp.inl = 1;
-                for (int k = 0; k < pr.nops; ++k) dp.iops[k] = (signed char)pr.ops[k];
-                for (int k = 0; k < pr.nconsts; ++k) dp.iconsts[k] = pr.consts[k];
-            }
-            a->progs.push_back(dp);
+        for (int c = 0; c < np && !rc; ++c) { DevProgram dp; rc = upload_program(pb->rhs_programs[c], &dp); if (!rc) a->progs.push_back(dp); }
+    }
+    if (!rc && pb->nneumann > 0) {
+        if (pb->ncomp != 1 || pb->nrhs != 1 || !pb->neumann) { set_error("Neumann sides need a scalar problem with one right-hand side"); rc = GSB200_EUNSUPPORTED; }
+        for (int i = 0; i < pb->nneumann && !rc; ++i) {
+            const gsb200_neumann &nm = pb->neumann[i];
+            if (nm.patch < 0 || nm.patch >= pb->npatches || nm.side < 1 || nm.side > 2 * dim || (nm.ndata != 1 && nm.ndata != dim)) {
+                set_error("Neumann side %d malformed (patch %d, side %d, ndata %d)", i, nm.patch, nm.side, nm.ndata); rc = GSB200_EINVAL; break; }
+            gsb200_assembler::NeumannSide ns; ns.patch = nm.patch; ns.side = nm.side; ns.ndata = nm.ndata;
+            for (int c = 0; c < nm.ndata && !rc; ++c) rc = upload_program(nm.data[c], &ns.prog[c]);
+            if (!rc) a->neumann.push_back(ns);
         }
     }
     if (!rc) rc = dev_malloc((void **)&a->d_rhs, sizeof(double) * (size_t)std::max(1, pb->nfree) * pb->nrhs);

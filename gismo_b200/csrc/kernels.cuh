@@ -359,6 +359,122 @@ GSB_GLOBAL void k_geometry(const GeoArgs A)
 }
 
 // ------------------------------------------------------------------------------------
+// Neumann boundary load (gsVisitorNeumann.h:83-136, gsExprAssembler.h:835-895): flux density at the
+// boundary quadrature points of one patch side.  The fixed direction contributes one node at the
+// boundary parameter (its basis values come pre-evaluated from the host), the outer normal is built
+// from the first minors of the Jacobian (gsFunction.hpp:613-699).
+struct FaceArgs {
+    int dim, dir, upper;
+    int qn[3];                                   // points per face direction (qn[dir] unused)
+    const double2 *gtab[3]; const int *gfirst[3]; int pg1[3], ngeo[3];
+    const double *hpt[3]; const double *gwp[3];
+    double2 bgeo[GSB_MAXP + 1]; int bgfirst;       // geometry basis (value, derivative) of `dir` at the boundary parameter
+    const double *coefs; const double *weights; i64 ngeo_total;
+    int ndata; DevProgram prog[3];
+    double *Fb;                                  // [qa][qb], last face direction fastest
+};
+template <int DIM>
+GSB_GLOBAL void k_face_geometry(const FaceArgs A)
+{
+    int fd[2] = {0, 0}, nf = 0;                  // the face's own directions, ascending
+    for (int k = 0; k < DIM; ++k) if (k != A.dir) fd[nf++] = k;
+    const i64 total = (DIM == 3) ? (i64)A.qn[fd[0]] * A.qn[fd[1]] : (i64)A.qn[fd[0]];
+    const i64 id = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= total) return;
+    int ql[3] = {0, 0, 0};
+    if (DIM == 3) { ql[fd[1]] = (int)(id % A.qn[fd[1]]); ql[fd[0]] = (int)(id / A.qn[fd[1]]); } else ql[fd[0]] = (int)id;
+    double W = 0.0, dW[3] = {0, 0, 0}, xn[3] = {0, 0, 0}, dxn[3][3];
+    for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) dxn[a][c] = 0.0;
+    int cnt[3] = {0, 0, 0}, gf[3];
+    for (int k = 0; k < DIM; ++k) gf[k] = (k == A.dir) ? A.bgfirst : A.gfirst[k][ql[k]];
+    for (;;) {
+        i64 idx = 0; double v = 1.0, dv[3]; double2 b[3];
+        for (int k = DIM - 1; k >= 0; --k) idx = idx * A.ngeo[k] + (gf[k] + cnt[k]);
+        for (int k = 0; k < DIM; ++k) { b[k] = (k == A.dir) ? A.bgeo[cnt[k]] : A.gtab[k][(i64)ql[k] * A.pg1[k] + cnt[k]]; v *= b[k].x; }
+        for (int k = 0; k < DIM; ++k) { dv[k] = b[k].y; for (int i = 0; i < DIM; ++i) if (i != k) dv[k] *= b[i].x; }
+        const double wt = A.weights ? A.weights[idx] : 1.0;
+        W += wt * v;
+        for (int k = 0; k < DIM; ++k) dW[k] += wt * dv[k];
+        for (int c = 0; c < DIM; ++c) {
+            const double C = A.coefs[(i64)c * A.ngeo_total + idx];
+            xn[c] += wt * v * C;
+            for (int k = 0; k < DIM; ++k) dxn[k][c] += wt * dv[k] * C;
+        }
+        int k = 0;
+        while (k < DIM && ++cnt[k] >= A.pg1[k]) { cnt[k] = 0; ++k; }
+        if (k == DIM) break;
+    }
+    double x[3] = {0, 0, 0}, Jt[3][3];           // Jt[a][c] = d x_c / d xi_a
+    for (int c = 0; c < DIM; ++c) { x[c] = xn[c] / W; for (int a = 0; a < DIM; ++a) Jt[a][c] = (dxn[a][c] * W - xn[c] * dW[a]) / (W * W); }
+    double nrm[3] = {0, 0, 0}, det;
+    if (DIM == 2) {
+        det = Jt[0][0] * Jt[1][1] - Jt[0][1] * Jt[1][0];
+        const int o = 1 - A.dir;
+        nrm[0] = Jt[o][1]; nrm[1] = -Jt[o][0];
+    } else {
+        det = Jt[0][0] * (Jt[1][1] * Jt[2][2] - Jt[1][2] * Jt[2][1]) - Jt[0][1] * (Jt[1][0] * Jt[2][2] - Jt[1][2] * Jt[2][0]) +
+              Jt[0][2] * (Jt[1][0] * Jt[2][1] - Jt[1][1] * Jt[2][0]);
+        const int r0 = A.dir == 0 ? 1 : 0, r1 = A.dir == 2 ? 1 : 2;
+        nrm[0] = Jt[r0][1] * Jt[r1][2] - Jt[r0][2] * Jt[r1][1];
+        nrm[1] = -(Jt[r0][0] * Jt[r1][2] - Jt[r0][2] * Jt[r1][0]);
+        nrm[2] = Jt[r0][0] * Jt[r1][1] - Jt[r0][1] * Jt[r1][0];
+    }
+    const int side = 2 * A.dir + A.upper + 1;     // sideOrientation(s), gsBoundary.h:1029-1035
+    const double sgn = (((side + (side + 1) / 2) % 2) ? 1.0 : -1.0) * (det < 0 ? -1.0 : 1.0);
+    double nn = 0.0;
+    for (int c = 0; c < DIM; ++c) { nrm[c] *= sgn; nn += nrm[c] * nrm[c]; }
+    double flux;
+    if (A.ndata == 1) flux = program_eval(A.prog[0], x[0], x[1], x[2]) * sqrt(nn);
+    else { flux = 0.0; for (int c = 0; c < DIM; ++c) flux += program_eval(A.prog[c], x[0], x[1], x[2]) * nrm[c]; }
+    double w = 1.0;                               // the fixed direction contributes h=0 -> 0.5 and weight 2
+    for (int k = 0; k < DIM; ++k) if (k != A.dir) w *= A.hpt[k][ql[k]] * A.gwp[k][ql[k]];
+    A.Fb[id] = w * flux;
+}
+
+// One thread per face basis function: contracts the flux density with the tensor basis over the
+// function's support and adds the result to the rhs rows of the (<= p+1) functions alive at the boundary.
+struct FaceLoadArgs {
+    int dim, dir;
+    int nfun[3], p1[3], q[3], Q[3];
+    const int *ffirst[3], *flast[3]; const double2 *tab[3];
+    double bval[GSB_MAXP + 1]; int bfirst, nb1;   // solution basis values of `dir` at the boundary parameter
+    const double *Fb; const int *dofmap; double *rhs; int nfree;
+};
+template <int DIM>
+GSB_GLOBAL void k_face_load(const FaceLoadArgs A)
+{
+    int fd[2] = {0, 0}, nf = 0;
+    for (int k = 0; k < DIM; ++k) if (k != A.dir) fd[nf++] = k;
+    const i64 total = (DIM == 3) ? (i64)A.nfun[fd[0]] * A.nfun[fd[1]] : (i64)A.nfun[fd[0]];
+    const i64 id = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= total) return;
+    int fi[3] = {0, 0, 0};
+    if (DIM == 3) { fi[fd[1]] = (int)(id % A.nfun[fd[1]]); fi[fd[0]] = (int)(id / A.nfun[fd[1]]); } else fi[fd[0]] = (int)id;
+    const int a = fd[0], b = fd[1];
+    double s = 0.0;
+    for (int ea = A.ffirst[a][fi[a]]; ea <= A.flast[a][fi[a]]; ++ea)
+        for (int ta = 0; ta < A.q[a]; ++ta) {
+            const int qa = ea * A.q[a] + ta;
+            const double va = A.tab[a][(i64)qa * A.p1[a] + fi[a] % A.p1[a]].x;
+            if (DIM == 2) { s = fma(va, A.Fb[qa], s); continue; }
+            double sb = 0.0;
+            for (int eb = A.ffirst[b][fi[b]]; eb <= A.flast[b][fi[b]]; ++eb)
+                for (int tb = 0; tb < A.q[b]; ++tb) {
+                    const int qb = eb * A.q[b] + tb;
+                    sb = fma(A.tab[b][(i64)qb * A.p1[b] + fi[b] % A.p1[b]].x, A.Fb[(i64)qa * A.Q[b] + qb], sb);
+                }
+            s = fma(va, sb, s);
+        }
+    for (int k = 0; k < A.nb1; ++k) {
+        fi[A.dir] = A.bfirst + k;
+        const i64 li = ((i64)(DIM == 3 ? fi[2] : 0) * A.nfun[1] + fi[1]) * A.nfun[0] + fi[0];
+        const int g = A.dofmap[li];
+        const double v = s * A.bval[k];
+        if (g < A.nfree && v != 0.0) atomic_add(A.rhs + g, v);
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // Final-stage scatter context: where an owner/partner pair lands in the CSC arrays.
 struct FinalArgs {
     int dim, L;                    // L = last (swept) direction

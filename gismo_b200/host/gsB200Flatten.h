@@ -38,6 +38,7 @@ struct gsB200Problem
     std::deque<std::vector<int32_t> > idx;   // dof maps, program opcodes
     std::vector<double> fixed;
     std::vector<gsb200_program> programs;
+    std::vector<gsb200_neumann> neumann;
 
     gsB200Problem() { std::memset(&pb, 0, sizeof(pb)); pb.abi_version = GSB200_ABI_VERSION; pb.nranks = 1; }
 private:
@@ -117,6 +118,47 @@ void flattenSource(const gsFunction<T> & f, index_t ncompExpected, gsB200Problem
     }
     st.pb.rhs_kind = GSB200_RHS_PROGRAM;
     st.pb.rhs_programs = st.programs.data();
+}
+
+namespace internal
+{
+template <class T>
+gsb200_program compileExpr(const std::string & text, gsB200Problem & st)
+{
+    std::vector<int32_t> ops(GSB200_PROGRAM_MAX_OPS);
+    std::vector<double>  cst(GSB200_PROGRAM_MAX_OPS);
+    int32_t nops = 0, ncst = 0;
+    if (gsb200_expr_compile(text.c_str(), ops.data(), (int32_t)ops.size(), &nops,
+                            cst.data(), (int32_t)cst.size(), &ncst) != GSB200_OK)
+        GISMO_ERROR("gsB200: cannot compile '" << text << "': " << gsb200_last_error());
+    ops.resize(nops); cst.resize(ncst);
+    st.idx.push_back(ops); st.dbl.push_back(cst);
+    gsb200_program pr;
+    pr.nops = nops; pr.ops = st.idx.back().data(); pr.nconsts = ncst; pr.consts = st.dbl.back().data();
+    return pr;
+}
+} // namespace internal
+
+/// Neumann sides of a gsBoundaryConditions (bc.neumannSides(), gsBoundaryConditions.h:439): one entry per
+/// (patch, side) with its gsFunctionExpr data: 1 component = scalar flux (gsVisitorNeumann), dim components =
+/// vector dotted with the outer normal (u*g_N.tr()*nv(G), poisson2_example.cpp:153).
+template <class T>
+void flattenNeumann(const gsBoundaryConditions<T> & bc, short_t dim, gsB200Problem & st)
+{
+    st.neumann.clear();
+    for (typename gsBoundaryConditions<T>::const_iterator it = bc.neumannSides().begin(); it != bc.neumannSides().end(); ++it)
+    {
+        const gsFunctionExpr<T> * fe = dynamic_cast<const gsFunctionExpr<T>*>(it->function().get());
+        GISMO_ENSURE(fe, "gsB200: Neumann data must be a gsFunctionExpr");
+        GISMO_ENSURE(fe->targetDim() == 1 || fe->targetDim() == dim, "gsB200: Neumann data must have 1 or dim components");
+        gsb200_neumann nm;
+        std::memset(&nm, 0, sizeof(nm));
+        nm.patch = it->patch(); nm.side = it->side().index(); nm.ndata = fe->targetDim();
+        for (short_t c = 0; c != fe->targetDim(); ++c) nm.data[c] = internal::compileExpr<T>(fe->expression(c), st);
+        st.neumann.push_back(nm);
+    }
+    st.pb.nneumann = static_cast<int32_t>(st.neumann.size());
+    st.pb.neumann = st.neumann.empty() ? NULL : st.neumann.data();
 }
 
 /** Flatten a whole (multi-patch) discretisation.

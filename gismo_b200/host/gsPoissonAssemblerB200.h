@@ -53,8 +53,6 @@ public:
                      "gsB200: only DirichletStrategy=elimination (11) is supported");
         GISMO_ENSURE(m_options.getInt("InterfaceStrategy") == iFace::glue,
                      "gsB200: only InterfaceStrategy=glue (1) is supported");
-        GISMO_ENSURE(m_pde_ptr->bc().neumannSides().empty(),
-                     "gsB200: Neumann sides are not handled by the device path yet");
 
         // Dirichlet values stay on the reference's host code: they are inputs.
         Base::computeDirichletDofs();
@@ -64,6 +62,7 @@ public:
                       m_options, GSB200_FORM_POISSON, st);
         const gsPoissonPde<T> & ppde = static_cast<const gsPoissonPde<T>&>(*m_pde_ptr);
         b200::flattenSource(*ppde.rhs(), st.pb.nrhs, st);
+        b200::flattenNeumann(m_pde_ptr->bc(), m_pde_ptr->domain().parDim(), st);   // gsVisitorNeumann on the device
 
         int64_t nnz = 0;
         if (gsb200_assemble_host(&st.pb, m_device, &nnz, NULL, NULL, NULL, NULL) != GSB200_OK)
@@ -100,7 +99,7 @@ template <class T = real_t>
 class gsExprAssemblerB200
 {
 public:
-    gsExprAssemblerB200() : m_ref(1,1), m_mp(NULL), m_mb(NULL), m_dim(1), m_device(0) { }
+    gsExprAssemblerB200() : m_ref(1,1), m_mp(NULL), m_mb(NULL), m_bc(NULL), m_dim(1), m_device(0) { }
 
     void setOptions(const gsOptionList & o) { m_ref.setOptions(o); }
     gsOptionList & options() { return m_ref.options(); }
@@ -130,6 +129,8 @@ public:
     const gsMatrix<T> & fixedPart() const { return m_fixed; }
 
     void assemblePoisson(const gsFunction<T> & f) { run(GSB200_FORM_POISSON, 0, 0, f); }
+    /// Poisson + assembleBdr(bc.get("Neumann"), u * g_N.tr() * nv(G))  (poisson2_example.cpp:145-153)
+    void assemblePoisson(const gsFunction<T> & f, const gsBoundaryConditions<T> & bc) { m_bc = &bc; run(GSB200_FORM_POISSON, 0, 0, f); m_bc = NULL; }
     void assembleElasticity(T lambda, T mu, const gsFunction<T> & f) { run(GSB200_FORM_ELASTICITY, lambda, mu, f); }
 
 private:
@@ -140,6 +141,7 @@ private:
         st.pb.coef[0] = c0; st.pb.coef[1] = c1;
         st.pb.nrhs = 1;
         b200::flattenSource(f, form == GSB200_FORM_ELASTICITY ? m_dim : 1, st);
+        if (m_bc) b200::flattenNeumann(*m_bc, m_mp->parDim(), st);
         int64_t nnz = 0;
         if (gsb200_assemble_host(&st.pb, m_device, &nnz, NULL, NULL, NULL, NULL) != GSB200_OK)
             GISMO_ERROR("gsB200: " << gsb200_last_error());
@@ -156,6 +158,7 @@ private:
     gsExprAssembler<T> m_ref;      // used for set-up only (mapper, Dirichlet values)
     const gsMultiPatch<T> * m_mp;
     const gsMultiBasis<T> * m_mb;
+    const gsBoundaryConditions<T> * m_bc;
     index_t m_dim;
     int m_device;
     gsDofMapper m_mapper;

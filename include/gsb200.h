@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define GSB200_ABI_VERSION 1
+#define GSB200_ABI_VERSION 2
 #define GSB200_MAX_DIM 3
 
 enum {
@@ -101,6 +101,16 @@ typedef struct gsb200_program {
     const double *consts;    /* literal pool                          */
 } gsb200_program;
 
+/* Neumann boundary load on one patch side (gsVisitorNeumann.h:83-136 / assembleBdr
+ * gsExprAssembler.h:835-895).  side: 1 west, 2 east, 3 south, 4 north, 5 front, 6 back
+ * (gsBoundary.h:58-60).  ndata == 1: rhs_i += int N_i g |n|  (visitor convention, scalar flux);
+ * ndata == dim: rhs_i += int N_i (g . n)  with n the unnormalised outer normal
+ * (expression u*g_N.tr()*nv(G), poisson2_example.cpp:153). */
+typedef struct gsb200_neumann {
+    int32_t patch, side, ndata;
+    gsb200_program data[GSB200_MAX_DIM];
+} gsb200_neumann;
+
 typedef struct gsb200_problem {
     int32_t abi_version;       /* must be GSB200_ABI_VERSION                                  */
     int32_t form;              /* GSB200_FORM_*                                               */
@@ -122,6 +132,8 @@ typedef struct gsb200_problem {
     /* Partition of the work over ranks.  Rank r integrates and owns the
        matrix columns/rows of its share; nranks==1 means everything. */
     int32_t rank, nranks;
+    int32_t nneumann;                   /* Neumann sides (scalar problems)                     */
+    const gsb200_neumann *neumann;
 } gsb200_problem;
 
 typedef struct gsb200_assembler gsb200_assembler; /* opaque device-side state */

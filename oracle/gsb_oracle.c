@@ -408,6 +408,85 @@ int gsbo_assemble(const gsb200_problem *pb, int64_t *nnz_out, int32_t *outer, in
                 while (k < d && ++el[k] >= ks[k].nel) { el[k] = 0; ++k; }
                 if (k == d) break;
             }
+            /* ---- Neumann sides of this patch: gsVisitorNeumann.h:83-136 (scalar data * |n|) or the
+                    expression u*g_N.tr()*nv(G) (vector data . outer normal), boundary quadrature with one
+                    node in the fixed direction (gsGaussRule.hpp:28-36, gsQuadRule.h:190-197), outer normal
+                    from the first minors of the Jacobian (gsFunction.hpp:613-699), pushToRhs
+                    (gsSparseSystem.h:884-899) ---- */
+            for (int in = 0; in < pb->nneumann; ++in) {
+                const gsb200_neumann *nm = &pb->neumann[in];
+                if (nm->patch != ip) continue;
+                const int dir = (nm->side - 1) / 2, upper = (nm->side - 1) % 2;
+                const double ub = upper ? ks[dir].kn[ks[dir].nk - ks[dir].p - 1] : ks[dir].kn[ks[dir].p];
+                const int eb = upper ? ks[dir].nel - 1 : 0;
+                int el2[3] = {0, 0, 0};
+                el2[dir] = eb;
+                for (;;) {
+                    double lower[3], h[3], hprod = 1.0, u1[3][MAXQ], v1[3][MAXQ][MAXP + 1], d1[3][MAXQ][MAXP + 1];
+                    int qq[3];
+                    for (int k = 0; k < d; ++k) {
+                        const int s = ks[k].span[el2[k]];
+                        qq[k] = (k == dir) ? 1 : q[k];
+                        if (k == dir) { h[k] = 0.0; hprod *= 0.5; u1[k][0] = ub; bspline_ders(ks[k].kn, ks[k].p, s, ub, v1[k][0], d1[k][0]); continue; }
+                        lower[k] = ks[k].kn[s]; h[k] = (ks[k].kn[s + 1] - lower[k]) / 2.0; hprod *= h[k];
+                        for (int t = 0; t < q[k]; ++t) { u1[k][t] = h[k] * (gn[k][t] + 1.0) + lower[k]; bspline_ders(ks[k].kn, ks[k].p, s, u1[k][t], v1[k][t], d1[k][t]); }
+                    }
+                    { int r = 0, a[3] = {0, 0, 0};
+                      for (;;) { int idx = 0; for (int k = d - 1; k >= 0; --k) idx = idx * ks[k].nfun + (ks[k].span[el2[k]] - ks[k].p + a[k]); act[r++] = idx;
+                                 int k = 0; while (k < d && ++a[k] > ks[k].p) { a[k] = 0; ++k; } if (k == d) break; } }
+                    memset(lr, 0, sizeof(double) * (size_t)nloc * nrhs);
+                    int t[3] = {0, 0, 0};
+                    const int nqb = qq[0] * qq[1] * (d == 3 ? qq[2] : 1);
+                    for (int kq = 0; kq < nqb; ++kq) {
+                        double u[3] = {0, 0, 0}, wp = 1.0;
+                        for (int k = 0; k < d; ++k) { u[k] = u1[k][t[k]]; const double wk = (k == dir) ? 2.0 : gw[k][t[k]]; wp = (k == 0) ? wk : wp * wk; }
+                        const double w = hprod * wp;
+                        { int r = 0, a[3] = {0, 0, 0};
+                          for (;;) { double v = 1.0; for (int k = 0; k < d; ++k) v *= v1[k][t[k]][a[k]]; bv[r++] = v;
+                                     int k = 0; while (k < d && ++a[k] > ks[k].p) { a[k] = 0; ++k; } if (k == d) break; } }
+                        double x[3] = {0, 0, 0}, Jt[9];
+                        { int sg[3]; double gv1[3][MAXP + 1], gd1[3][MAXP + 1]; int ngeo = 1;
+                          for (int k = 0; k < d; ++k) { sg[k] = kv_find(&kg[k], u[k]); bspline_ders(kg[k].kn, kg[k].p, sg[k], u[k], gv1[k], gd1[k]); ngeo *= kg[k].nfun; }
+                          double W = 0.0, dW[3] = {0, 0, 0}, xn[3] = {0, 0, 0}, dxn[9] = {0};
+                          int a[3] = {0, 0, 0};
+                          for (;;) {
+                              int idx = 0; for (int k = d - 1; k >= 0; --k) idx = idx * kg[k].nfun + (sg[k] - kg[k].p + a[k]);
+                              double v = 1.0, dv[3]; for (int k = 0; k < d; ++k) v *= gv1[k][a[k]];
+                              for (int k = 0; k < d; ++k) { dv[k] = gd1[k][a[k]]; for (int i = 0; i < d; ++i) if (i != k) dv[k] *= gv1[i][a[i]]; }
+                              const double wt = pa->geo_weights ? pa->geo_weights[idx] : 1.0;
+                              W += wt * v; for (int k = 0; k < d; ++k) dW[k] += wt * dv[k];
+                              for (int c = 0; c < d; ++c) { const double C = pa->geo_coefs[(size_t)c * ngeo + idx]; xn[c] += wt * v * C; for (int k = 0; k < d; ++k) dxn[k * d + c] += wt * dv[k] * C; }
+                              int k = 0; while (k < d && ++a[k] > kg[k].p) { a[k] = 0; ++k; } if (k == d) break;
+                          }
+                          for (int c = 0; c < d; ++c) { x[c] = xn[c] / W; for (int k = 0; k < d; ++k) Jt[k * d + c] = (dxn[k * d + c] * W - xn[c] * dW[k]) / (W * W); } }
+                        /* outer normal: n_i = sgn * det_sgn * (-1)^i * det(first minor (dir, i) of Jt) */
+                        double nrm[3] = {0, 0, 0}, detJ;
+                        if (d == 2) {
+                            detJ = Jt[0] * Jt[3] - Jt[1] * Jt[2];
+                            const int o = 1 - dir;
+                            nrm[0] = Jt[o * 2 + 1]; nrm[1] = -Jt[o * 2 + 0];
+                        } else {
+                            detJ = Jt[0] * (Jt[4] * Jt[8] - Jt[5] * Jt[7]) - Jt[1] * (Jt[3] * Jt[8] - Jt[5] * Jt[6]) + Jt[2] * (Jt[3] * Jt[7] - Jt[4] * Jt[6]);
+                            const int r0 = dir == 0 ? 1 : 0, r1 = dir == 2 ? 1 : 2;
+                            const double *A = &Jt[r0 * 3], *B = &Jt[r1 * 3];
+                            nrm[0] = A[1] * B[2] - A[2] * B[1]; nrm[1] = -(A[0] * B[2] - A[2] * B[0]); nrm[2] = A[0] * B[1] - A[1] * B[0];
+                        }
+                        /* sideOrientation(s) = ((s + (s+1)/2) % 2) ? +1 : -1   (gsBoundary.h:1029-1035) */
+                        const double sgn = (((nm->side + (nm->side + 1) / 2) % 2) ? 1.0 : -1.0) * (detJ < 0 ? -1.0 : 1.0);
+                        double nn = 0.0; for (int c = 0; c < d; ++c) { nrm[c] *= sgn; nn += nrm[c] * nrm[c]; }
+                        nn = sqrt(nn);
+                        double flux;
+                        if (nm->ndata == 1) flux = prog_eval(&nm->data[0], x) * nn;
+                        else { flux = 0.0; for (int c = 0; c < d; ++c) flux += prog_eval(&nm->data[c], x) * nrm[c]; }
+                        for (int i = 0; i < nact; ++i) lr[i] += w * bv[i] * flux;
+                        { int k = 0; while (k < d && ++t[k] >= qq[k]) { t[k] = 0; ++k; } }
+                    }
+                    for (int i = 0; i < nact; ++i) { const int ii = pa->dofmap[act[i]]; if (ii < N) rhs_acc[ii] += lr[i]; }
+                    int k = 0;
+                    for (;;) { if (k == dir) { ++k; continue; } if (k >= d) break; if (++el2[k] < ks[k].nel) break; el2[k] = 0; ++k; }
+                    if (k >= d) break;
+                }
+            }
             free(bv); free(bd); free(pg); free(lm); free(lr); free(act); free(gv); free(gd);
             for (int k = 0; k < d; ++k) { free(ks[k].span); free(kg[k].span); }
         }

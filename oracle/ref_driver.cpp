@@ -27,7 +27,9 @@ typedef struct gsref_config {
     int32_t degree;       /* setDegree(degree) on the solution basis                        */
     int32_t nelem;        /* uniformRefine(nelem-1): elements per original span/direction   */
     int32_t geometry;     /* 0 unit box, 1 curved box, 2 NURBS quarter annulus (2D),
-                             3 grid of boxes (multi-patch), 4 XML multipatch file           */
+                             3 grid of boxes (multi-patch), 4 XML multipatch file,
+                             5 complete BVP file as read by examples/poisson2_example.cpp:43-64
+                               (geometry id 0, source id 1, boundary conditions id 2), nelem = #refinements */
     int32_t grid[3];      /* patches per direction for geometry 3                           */
     int32_t path;         /* 0 visitor (gsPoissonAssembler), 1 expression (gsExprAssembler)  */
     int32_t form;         /* 0 Poisson, 1 linear elasticity (path 1 only)                   */
@@ -38,6 +40,9 @@ typedef struct gsref_config {
     const char *dir[3];   /* Dirichlet data component expressions                           */
     const char *xml;      /* geometry 4: file with a gsMultiPatch                           */
     double lambda, mu;
+    int32_t neumann_mask; /* bit s set: boundary sides with index s (1..6) carry Neumann data `neu`  */
+    int32_t neu_n;        /* 1: scalar flux (visitor path), dim: vector data dotted with the outer normal */
+    const char *neu[3];
 } gsref_config;
 
 struct gsref_result {
@@ -46,6 +51,8 @@ struct gsref_result {
     gsMatrix<real_t> rhs;
     double assemble_seconds;
     int64_t elements, qpoints;
+    std::vector<int32_t> neumann;   // (patch, side) pairs
+    std::vector<std::string> rhs_text, neu_text;
     std::string err;
 };
 
@@ -88,6 +95,11 @@ static gsMultiPatch<real_t> make_geometry(const gsref_config &c)
         gsFileData<real_t> fd(c.xml);
         fd.getFirst(mp);
         break; }
+    case 5: {
+        gsFileData<real_t> fd(c.xml);
+        fd.getId(0, mp);
+        return mp;   // topology comes from the file
+    }
     default: GISMO_ERROR("unknown geometry kind");
     }
     mp.computeTopology();
@@ -105,18 +117,42 @@ void *gsref_run(const gsref_config *cfg)
         gsMultiPatch<real_t> mp = make_geometry(c);
         const int d = mp.parDim();
         gsMultiBasis<real_t> mb(mp, true);
-        if (c.geometry == 4 && c.degree_elevate > 0) mb.degreeElevate(c.degree_elevate);
+        if (c.geometry == 5) {           // poisson2_example.cpp:69-81: setDegree(max + elevate), r x uniformRefine()
+            mb.setDegree(mb.maxCwiseDegree() + c.degree_elevate);
+            for (int r = 0; r < c.nelem; ++r) mb.uniformRefine();
+        }
+        else if (c.geometry == 4 && c.degree_elevate > 0) mb.degreeElevate(c.degree_elevate);
         else mb.setDegree(c.degree);
-        if (c.nelem > 1) mb.uniformRefine(c.nelem - 1);
+        if (c.geometry != 5 && c.nelem > 1) mb.uniformRefine(c.nelem - 1);
 
         const int ncomp = c.form == 1 ? d : 1;
         std::vector<std::string> fs, gs;
         for (int k = 0; k < ncomp; ++k) { fs.push_back(c.rhs[k] ? c.rhs[k] : "0"); gs.push_back(c.dir[k] ? c.dir[k] : "0"); }
         gsFunctionExpr<real_t> f(fs, d), g(gs, d);
 
+        std::vector<std::string> ns;
+        for (int k = 0; k < std::max(1, c.neu_n); ++k) ns.push_back(c.neu[k] ? c.neu[k] : "0");
+        gsFunctionExpr<real_t> gN(ns, d);
         gsBoundaryConditions<real_t> bc;
-        for (gsMultiPatch<real_t>::const_biterator it = mp.bBegin(); it != mp.bEnd(); ++it)
-            bc.addCondition(*it, condition_type::dirichlet, &g, 0, false, -1);
+        for (gsMultiPatch<real_t>::const_biterator it = mp.bBegin(); it != mp.bEnd(); ++it) {
+            if ((c.neumann_mask >> it->side().index()) & 1) {
+                bc.addCondition(*it, condition_type::neumann, &gN, 0, false, -1);
+                R->neumann.push_back(it->patch); R->neumann.push_back(it->side().index());
+            } else bc.addCondition(*it, condition_type::dirichlet, &g, 0, false, -1);
+        }
+        if (c.geometry == 5) {           // source term and boundary conditions from the file
+            gsFileData<real_t> fd(c.xml);
+            fd.getId(1, f);
+            bc = gsBoundaryConditions<real_t>();
+            fd.getId(2, bc);
+            R->neumann.clear();
+            for (gsBoundaryConditions<real_t>::const_iterator it = bc.neumannSides().begin(); it != bc.neumannSides().end(); ++it) {
+                R->neumann.push_back(it->patch()); R->neumann.push_back(it->side().index());
+                const gsFunctionExpr<real_t> *fe = dynamic_cast<const gsFunctionExpr<real_t> *>(it->function().get());
+                if (R->neu_text.empty() && fe) for (short_t k = 0; k < fe->targetDim(); ++k) R->neu_text.push_back(fe->expression(k));
+            }
+        } else if (c.neumann_mask) for (size_t k = 0; k < ns.size(); ++k) R->neu_text.push_back(ns[k]);
+        for (short_t k = 0; k < f.targetDim(); ++k) R->rhs_text.push_back(f.expression(k));
         bc.setGeoMap(mp);
 
         gsStopwatch timer;
@@ -144,8 +180,10 @@ void *gsref_run(const gsref_config *cfg)
             A.initSystem();
             timer.restart();
             if (c.form == 0)
+            {
                 A.assemble(igrad(u, G) * igrad(u, G).tr() * meas(G), u * ff * meas(G));
-            else {
+                if (c.neumann_mask || c.geometry == 5) { auto g_N = A.getBdrFunction(G); A.assembleBdr(bc.get("Neumann"), u * g_N.tr() * nv(G)); }
+            } else {
                 auto pj = ijac(u, G);
                 auto bl = c.lambda * idiv(u, G) * idiv(u, G).tr() * meas(G);
                 auto bm = c.mu * ((pj.cwisetr() + pj) % pj.tr()) * meas(G);
@@ -255,6 +293,25 @@ int gsref_uniform_refine(const double *knots, int nknots, int degree, int numKno
     std::copy(kv.data(), kv.data() + kv.size(), out);
     *nout = (int)kv.size();
     return 0;
+}
+
+/* which = 0: source-term component idx, 1: Neumann data component idx; returns the length (0 = none) */
+int gsref_text(void *h, int which, int idx, char *buf, int cap)
+{
+    gsref_result *R = static_cast<gsref_result *>(h);
+    const std::vector<std::string> &v = which ? R->neu_text : R->rhs_text;
+    if (idx < 0 || idx >= (int)v.size()) return 0;
+    snprintf(buf, cap, "%s", v[idx].c_str());
+    return (int)v[idx].size();
+}
+
+/* (patch, side) pairs of the Neumann sides, in the order the reference visits them */
+int gsref_neumann(void *h, int32_t *pairs, int32_t cap)
+{
+    gsref_result *R = static_cast<gsref_result *>(h);
+    const int n = (int)R->neumann.size() / 2;
+    for (int i = 0; i < 2 * n && i < cap; ++i) pairs[i] = R->neumann[i];
+    return n;
 }
 
 int gsref_max_threads(void)

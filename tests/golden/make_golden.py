@@ -34,6 +34,16 @@ FULL = {
     "yeti_mp2_p2_m2": dict(dim=2, degree=2, nelem=2, geometry=4, xml="domain2d/yeti_mp2.xml", rhs=["1"]),
     "elasticity_2cubes_p2": dict(dim=3, degree=2, nelem=2, geometry=3, grid=(2, 1, 1), path=1, form=1, lam=2.0, mu=1.5,
                                  rhs=["x", "y*z", "1"], dirichlet=["0.1*x", "0", "y"], dir_values=101),
+    # Neumann sides: gsVisitorNeumann (scalar flux) and assembleBdr(u*g_N.tr()*nv(G)) (vector data)
+    "sq_p2_neumann_visitor": dict(dim=2, degree=2, nelem=5, geometry=0, rhs=[PI2], dirichlet=["x*y"], neumann_mask=(1 << 2) | (1 << 4), neu=["1+x*y"]),
+    "annulus_p3_neumann_expr": dict(dim=2, degree=3, nelem=4, geometry=2, path=1, rhs=["sin(x)*y"], dirichlet=["x+y"], dir_values=102,
+                                    neumann_mask=(1 << 1) | (1 << 3), neu=["x-y", "cos(x)"]),
+    "cube_p2_curved_neumann": dict(dim=3, degree=2, nelem=3, geometry=1, rhs=["x*y*z"], dirichlet=["x"], neumann_mask=(1 << 2) | (1 << 3) | (1 << 5), neu=["1+x*z"]),
+    "cubes2_p2_neumann_expr": dict(dim=3, degree=2, nelem=2, geometry=3, grid=(2, 1, 1), path=1, rhs=["1"], dirichlet=["z"],
+                                   neumann_mask=(1 << 6) | (1 << 1), neu=["x", "y*z", "1"]),
+    # the stock input of examples/poisson2_example.cpp (BASELINE config 1): 2-patch NURBS quarter annulus,
+    # mixed Dirichlet (L2-projected) / Neumann, read by the reference from its own XML file
+    "poisson2d_bvp_stock_r2": dict(dim=2, degree=0, nelem=2, geometry=5, xml="pde/poisson2d_bvp.xml", path=1, dir_values=102),
     "elasticity_sq_p2": dict(dim=2, degree=2, nelem=4, geometry=1, path=1, form=1, lam=80000.0, mu=80000.0,
                              rhs=["1", "x"], dirichlet=["0", "0.01*x"], dir_values=101),
 }
@@ -48,7 +58,8 @@ FINGERPRINT = {
 def pack_inputs(ref):
     d = {"nfree": ref.nfree, "nfixed": ref.nfixed, "ncomp": ref.ncomp, "dim": ref.dim, "form": ref.form,
          "coef": np.asarray(ref.coef), "quA": ref.quA, "quB": ref.quB, "npatches": len(ref.patches),
-         "rhs_text": np.asarray(ref.rhs_text), "fixed": ref.fixed}
+         "rhs_text": np.asarray(ref.rhs_text), "fixed": ref.fixed,
+         "neumann_sides": np.asarray(ref.neumann_sides, dtype=np.int32).reshape(-1, 2), "neu_text": np.asarray(ref.neu_text)}
     for k, p in enumerate(ref.patches):
         d[f"p{k}_sdeg"] = np.asarray(p.space_degree)
         d[f"p{k}_gdeg"] = np.asarray(p.geo_degree)

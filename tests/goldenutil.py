@@ -40,9 +40,13 @@ def load(name, compile_fn, with_rhs=True):
                                  z[f"p{k}_coefs"], dofmap, z.get(f"p{k}_weights")))
     progs = [compile_fn(str(t)) for t in z["rhs_text"]] if with_rhs else None
     nfixed = int(z["nfixed"])
+    neumann = []
+    if "neumann_sides" in z and len(z["neumann_sides"]):
+        neu = [compile_fn(str(t)) for t in z["neu_text"]]
+        neumann = [(int(p), int(s), neu) for p, s in z["neumann_sides"]]
     pb = Problem(patches, int(z["nfree"]), nfixed, form=int(z["form"]), ncomp=ncomp,
                  fixed=z["fixed"] if nfixed else None, nrhs=1, coef=tuple(z["coef"]), quA=float(z["quA"]),
-                 quB=int(z["quB"]), rhs_programs=progs)
+                 quB=int(z["quB"]), rhs_programs=progs, neumann=neumann)
     return pb, z
 
 

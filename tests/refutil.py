@@ -82,7 +82,8 @@ class RefConfig(C.Structure):
     _fields_ = [("dim", C.c_int32), ("degree", C.c_int32), ("nelem", C.c_int32), ("geometry", C.c_int32),
                 ("grid", C.c_int32 * 3), ("path", C.c_int32), ("form", C.c_int32), ("dir_values", C.c_int32),
                 ("threads", C.c_int32), ("degree_elevate", C.c_int32), ("rhs", C.c_char_p * 3),
-                ("dir", C.c_char_p * 3), ("xml", C.c_char_p), ("lambda_", C.c_double), ("mu", C.c_double)]
+                ("dir", C.c_char_p * 3), ("xml", C.c_char_p), ("lambda_", C.c_double), ("mu", C.c_double),
+                ("neumann_mask", C.c_int32), ("neu_n", C.c_int32), ("neu", C.c_char_p * 3)]
 
 
 _ref = None
@@ -106,6 +107,8 @@ def ref_lib():
         lib.gsref_last_error.restype = C.c_char_p
         lib.gsref_gauss.argtypes = [C.c_int, _dp, _dp]
         lib.gsref_uniform_refine.argtypes = [_dp, C.c_int, C.c_int, C.c_int, _dp, C.POINTER(C.c_int)]
+        lib.gsref_neumann.argtypes = [C.c_void_p, _ip, C.c_int32]
+        lib.gsref_text.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_int]
         _ref = lib
     return _ref
 
@@ -123,19 +126,24 @@ class RefResult:
         self.form = 0
         self.coef = (0.0, 0.0)
         self.rhs_text: List[str] = []
+        self.neumann_sides: List[Tuple[int, int]] = []
+        self.neu_text: List[str] = []
 
     def problem(self, with_rhs: bool = True, compile_fn=None) -> Problem:
         progs = None
         if with_rhs and self.rhs_text:
             compile_fn = compile_fn or capi.expr_compile
             progs = [compile_fn(t) for t in self.rhs_text]
+        compile_fn = compile_fn or capi.expr_compile
+        neumann = [(p, s, [compile_fn(t) for t in self.neu_text]) for p, s in self.neumann_sides]
         return Problem(self.patches, self.nfree, self.nfixed, form=self.form, ncomp=self.ncomp,
                        fixed=self.fixed if self.nfixed else None, nrhs=1, coef=self.coef, quA=self.quA,
-                       quB=self.quB, rhs_programs=progs)
+                       quB=self.quB, rhs_programs=progs, neumann=neumann)
 
 
 def ref_run(dim=3, degree=2, nelem=4, geometry=0, grid=(1, 1, 1), path=0, form=0, dir_values=101,
-            threads=1, rhs=None, dirichlet=None, xml=None, lam=0.0, mu=0.0, degree_elevate=0) -> RefResult:
+            threads=1, rhs=None, dirichlet=None, xml=None, lam=0.0, mu=0.0, degree_elevate=0,
+            neumann_mask=0, neu=None) -> RefResult:
     lib = ref_lib()
     cfg = RefConfig()
     cfg.dim, cfg.degree, cfg.nelem, cfg.geometry = dim, degree, nelem, geometry
@@ -150,6 +158,10 @@ def ref_run(dim=3, degree=2, nelem=4, geometry=0, grid=(1, 1, 1), path=0, form=0
         cfg.dir[k] = dirichlet[k].encode()
     cfg.xml = xml.encode() if xml else None
     cfg.lambda_, cfg.mu = lam, mu
+    neu = list(neu or [])
+    cfg.neumann_mask, cfg.neu_n = neumann_mask, len(neu)
+    for k, t in enumerate(neu):
+        cfg.neu[k] = t.encode()
     h = lib.gsref_run(C.byref(cfg))
     if not h:
         raise RuntimeError("reference failed: " + lib.gsref_last_error().decode())
@@ -161,6 +173,17 @@ def ref_run(dim=3, degree=2, nelem=4, geometry=0, grid=(1, 1, 1), path=0, form=0
         R.nfree, R.nfixed, nnz, npatches, R.ncomp, R.dim, R.elements, R.qpoints = [int(v) for v in sizes]
         R.seconds, R.quA, R.quB = sec.value, quA.value, quB.value
         R.form, R.coef, R.rhs_text = form, (lam, mu), rhs
+        pairs = (C.c_int32 * 128)()
+        nn = lib.gsref_neumann(h, pairs, 128)
+        R.neumann_sides = [(pairs[2 * i], pairs[2 * i + 1]) for i in range(nn)]
+        def texts(which):
+            out = []
+            buf = C.create_string_buffer(1024)
+            k = 0
+            while lib.gsref_text(h, which, k, buf, 1024) > 0:
+                out.append(buf.value.decode()); k += 1
+            return out
+        R.rhs_text, R.neu_text = texts(0), texts(1)
         R.outer = np.zeros(R.nfree + 1, np.int32)
         R.inner = np.zeros(nnz, np.int32)
         R.values = np.zeros(nnz)

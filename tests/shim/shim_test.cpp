@@ -53,23 +53,29 @@ int main()
     {   // visitor path, 3-D NURBS-free curved cube, homogeneous
         gsMultiPatch<> mp(*gsNurbsCreator<>::BSplineCube(1, 0, 0, 0));
         gsMultiBasis<> mb(mp, true); mb.setDegree(2); mb.uniformRefine(5);
-        gsFunctionExpr<> f("3*pi^2*sin(pi*x)*sin(pi*y)*sin(pi*z)", 3), g("0", 3);
-        gsBoundaryConditions<> bc;
-        for (gsMultiPatch<>::const_biterator it = mp.bBegin(); it != mp.bEnd(); ++it) bc.addCondition(*it, condition_type::dirichlet, &g);
+        gsFunctionExpr<> f("3*pi^2*sin(pi*x)*sin(pi*y)*sin(pi*z)", 3), g("0", 3), gN("1+x*z", 3);
+        gsBoundaryConditions<> bc;     // east and back sides: Neumann (gsVisitorNeumann, scalar flux)
+        for (gsMultiPatch<>::const_biterator it = mp.bBegin(); it != mp.bEnd(); ++it) {
+            if (it->side().index() == 2 || it->side().index() == 6) bc.addCondition(*it, condition_type::neumann, &gN);
+            else bc.addCondition(*it, condition_type::dirichlet, &g);
+        }
         bc.setGeoMap(mp);
         gsPoissonAssembler<> R(mp, mb, bc, f, dirichlet::elimination, iFace::glue);
         R.assemble();
         gsPoissonAssemblerB200<> D(mp, mb, bc, f, dirichlet::elimination, iFace::glue);
         D.assemble();
-        bad += compare("gsPoissonAssemblerB200 cube p=2", R.matrix(), R.rhs(), D.matrix(), D.rhs());
+        bad += compare("gsPoissonAssemblerB200 cube p=2 + Neumann", R.matrix(), R.rhs(), D.matrix(), D.rhs());
     }
     {   // expression path on the NURBS quarter annulus, L2-projected Dirichlet data
         gsMultiPatch<> mp(*gsNurbsCreator<>::NurbsQuarterAnnulus(1, 2));
         mp.computeTopology();
         gsMultiBasis<> mb(mp, true); mb.setDegree(2); mb.uniformRefine(7);
-        gsFunctionExpr<> f("sin(x)*y", 2), g("x+y", 2);
-        gsBoundaryConditions<> bc;
-        for (gsMultiPatch<>::const_biterator it = mp.bBegin(); it != mp.bEnd(); ++it) bc.addCondition(*it, condition_type::dirichlet, &g);
+        gsFunctionExpr<> f("sin(x)*y", 2), g("x+y", 2), gN("x-y", "cos(x)", 2);
+        gsBoundaryConditions<> bc;     // west and south sides carry Neumann data (vector . outer normal), the rest Dirichlet
+        for (gsMultiPatch<>::const_biterator it = mp.bBegin(); it != mp.bEnd(); ++it) {
+            if (it->side().index() == 1 || it->side().index() == 3) bc.addCondition(*it, condition_type::neumann, &gN);
+            else bc.addCondition(*it, condition_type::dirichlet, &g);
+        }
         bc.setGeoMap(mp);
         gsExprAssembler<> A(1, 1);
         A.setIntegrationElements(mb);
@@ -79,11 +85,13 @@ int main()
         u.setup(bc, dirichlet::l2Projection, 0);
         A.initSystem();
         A.assemble(igrad(u, G) * igrad(u, G).tr() * meas(G), u * ff * meas(G));
+        auto g_N = A.getBdrFunction(G);
+        A.assembleBdr(bc.get("Neumann"), u * g_N.tr() * nv(G));
         gsExprAssemblerB200<> B;
         B.setIntegrationElements(mb); B.setGeometry(mp);
         B.setup(bc, 1, dirichlet::l2Projection);
-        B.assemblePoisson(f);
-        bad += compare("gsExprAssemblerB200 NURBS annulus p=2", A.matrix(), A.rhs(), B.matrix(), B.rhs());
+        B.assemblePoisson(f, bc);
+        bad += compare("gsExprAssemblerB200 NURBS annulus p=2 + Neumann", A.matrix(), A.rhs(), B.matrix(), B.rhs());
     }
     gsInfo << (bad ? "SHIM RESULT FAIL\n" : "SHIM RESULT PASS\n");
     return bad;

@@ -13,6 +13,7 @@ import pytest
 
 import goldenutil as G
 import refutil as R
+from gismo_b200 import capi
 
 TOL = 1e-12
 
@@ -68,7 +69,7 @@ def test_bad_inputs_are_rejected(emul):
     h = C.c_void_p()
     pb.struct.abi_version = 99
     assert emul.gsb200_create(C.byref(pb.struct), 0, C.byref(h)) == -1
-    pb.struct.abi_version = 1
+    pb.struct.abi_version = capi.ABI_VERSION
     pb.struct.form = 7
     assert emul.gsb200_create(C.byref(pb.struct), 0, C.byref(h)) == -2
     pb.struct.form = 0
