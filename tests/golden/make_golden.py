@@ -52,7 +52,13 @@ FINGERPRINT = {
     "sq_p2_m64": dict(dim=2, degree=2, nelem=64, geometry=0, rhs=[PI2], dir_values=100, threads=8),
     "cube_p4_m8": dict(dim=3, degree=4, nelem=8, geometry=0, rhs=[PI3], dir_values=100, threads=8),
     "cube_p2_m16_expr": dict(dim=3, degree=2, nelem=16, geometry=0, path=1, rhs=[PI3], dirichlet=["x*y*z"], dir_values=101, threads=1),
+    # BASELINE config 3 shape: the 21-patch yeti footprint, p=2, 16x16 elements per patch, glued interfaces
+    "yeti_mp2_p2_m8": dict(dim=2, degree=2, nelem=8, geometry=4, xml="domain2d/yeti_mp2.xml", rhs=["1+x"], dirichlet=["0.1*y"], threads=8),
+    # BASELINE config 4 shape: 2x2x2 patches, p=2, vector-valued linear elasticity through the expression path
+    "elasticity_8cubes_p2_m5": dict(dim=3, degree=2, nelem=5, geometry=3, grid=(2, 2, 2), path=1, form=1, lam=80000.0, mu=80000.0,
+                                    rhs=["0", "0", "-1000"], dirichlet=["0", "0", "0.001*x"], dir_values=101, threads=1),
 }
+KEEP_DOFMAP = {"yeti_mp2_p2_m8", "elasticity_8cubes_p2_m5"}
 
 
 def pack_inputs(ref):
@@ -96,7 +102,7 @@ def main():
                  diag=K.diagonal())
         # dof maps of fingerprint cases are large; they are rebuilt by gismo_b200.host in the tests
         for k in list(d):
-            if k.endswith("_dofmap"):
+            if k.endswith("_dofmap") and name not in KEEP_DOFMAP:
                 del d[k]
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
         print(name, "N", ref.nfree, "nnz", len(ref.values), repr(ref.values.sum()), repr(np.linalg.norm(ref.rhs)))

@@ -24,7 +24,7 @@ def test_oracle_matches_reference_fixture(name):
     G.check_against(R.oracle_assemble(pb), z, TOL)
 
 
-@pytest.mark.parametrize("name", ["sq_p2_m64", "cube_p4_m8", "cube_p2_m16_expr"])
+@pytest.mark.parametrize("name", ["sq_p2_m64", "cube_p4_m8", "cube_p2_m16_expr", "yeti_mp2_p2_m8", "elasticity_8cubes_p2_m5"])
 def test_oracle_matches_reference_fingerprint(name):
     pb, z = G.load(name, _compile)
     G.check_against(R.oracle_assemble(pb), z, TOL)
