@@ -532,8 +532,11 @@ static int assemble_pass(gsb200_assembler *a)
         const i64 NI0 = (i64)d0.nfun * (2 * d0.p + 1), NI1 = dim == 3 ? (i64)d1.nfun * (2 * d1.p + 1) : 1;
         const i64 n0 = d0.nfun, n1 = dim == 3 ? d1.nfun : 1;
         const i64 W0 = 2 * d0.p + 1, W1 = dim == 3 ? 2 * d1.p + 1 : 1;
+        // symmetric forms in 3-D: the first sweep keeps only delta0 >= 0, the second one mirrors its output
+        const bool half = dim == 3 && kind != KIND_GEN && !getenv("GSB200_NOSYM");
+        const i64 NI0h = half ? (i64)d0.nfun * (d0.p + 1) : NI0;     // (i0, delta0) pairs stored in A1
         // doubles of workspace per last-direction quadrature point
-        i64 perq = ncD * Q0 * Q1 + no1 * NI0 * Q1 + (dim == 3 ? no2 * NI1 * NI0 : 0) + nf * Q0 * Q1 + n0 * Q1 + (dim == 3 ? n1 * n0 : 0);
+        i64 perq = ncD * Q0 * Q1 + no1 * NI0h * Q1 + (dim == 3 ? no2 * NI1 * NI0 : 0) + nf * Q0 * Q1 + n0 * Q1 + (dim == 3 ? n1 * n0 : 0);
         i64 maxpts = limit / (perq * 8);
         const i64 minpts = (i64)(dL.p + 1) * dL.q;
         if (maxpts < minpts) { set_error("workspace limit %lld B too small: one slab of patch %zu needs %lld B", (long long)limit, ip, (long long)(perq * 8 * minpts)); return GSB200_ENOMEM; }
@@ -552,7 +555,7 @@ static int assemble_pass(gsb200_assembler *a)
             double *w = (double *)a->ws;
             auto carve = [&](i64 count) { double *p = w; w += (count + 31) / 32 * 32; return p; };   // 256-byte aligned pieces
             double *D = carve(ncD * Q0 * Q1 * QLc);
-            double *A1 = carve(no1 * NI0 * Q1 * QLc);
+            double *A1 = carve(no1 * NI0h * Q1 * QLc);
             double *A2 = carve(dim == 3 ? no2 * NI1 * NI0 * QLc : 0);
             double *F = carve(nf * Q0 * Q1 * QLc);
             double *V1 = carve(n0 * Q1 * QLc);
@@ -604,7 +607,7 @@ static int assemble_pass(gsb200_assembler *a)
                 auto base_args = [&](const Dir1D &d) {
                     SweepArgs A; memset(&A, 0, sizeof A);
                     A.first = d.d_first; A.nexit = d.d_nexit; A.tab = d.d_tab; A.q = d.q; A.p = d.p; A.fin = Fa;
-                    A.out_bq = 1; A.out_od = 1; return A;
+                    A.out_bq = 1; A.out_od = 1; A.d_off = d.p; return A;
                 };
                 auto account = [&](int slot, const SweepArgs &A, const std::vector<int> &seg, i64 fpp, int nin, int nout, i64 npairs_out) {
                     i64 pts = 0;
@@ -618,27 +621,29 @@ static int assemble_pass(gsb200_assembler *a)
                         SweepArgs A = base_args(d0);
                         A.in = D; A.in_cs = npts; A.in_es = (i64)d0.q * Q1 * QLc; A.in_ts = Q1 * QLc; A.in_os = 0; A.in_is = 1; A.e_in0 = 0;
                         A.ncol = Q1 * QLc; A.ninner = A.ncol;
-                        A.out = A1; A.out_cs = NI0 * Q1 * QLc; A.out_fs = (2 * d0.p + 1) * Q1 * QLc; A.out_ds = Q1 * QLc; A.out_os = 0; A.out_bq = A.ncol + 1; A.out_bs = 0; A.out_is = 1;
+                        A.out = A1; A.out_cs = NI0h * Q1 * QLc; A.out_fs = (half ? d0.p + 1 : 2 * d0.p + 1) * Q1 * QLc; A.out_ds = Q1 * QLc; A.out_os = 0; A.out_bq = A.ncol + 1; A.out_bs = 0; A.out_is = 1;
+                        if (half) { A.half_out = 1; A.d_off = 0; }
                         const int nseg = nseg_for(A.ncol * (d0.p + 1), d0.nfun, d0.p + 1);
                         std::vector<int> seg = make_segments(d0, 0, d0.nfun, nseg);
                         A.seg = a->d_seg + segoff; GSB_TRY(upload_segments(a, seg, &segoff));
                         mark(a, 1);
                         { TmapDesc td; memset(&td, 0, sizeof td); td.valid = true; td.rank = 3; td.dims[0] = (unsigned long long)(Q1 * QLc); td.dims[1] = (unsigned long long)(Q0); td.dims[2] = (unsigned long long)(ncD); td.strides[0] = 8ull * (unsigned long long)(Q1 * QLc); td.strides[1] = 8ull * (unsigned long long)(npts); td.box_kind[0] = 1; td.box_kind[1] = 2; td.box_kind[2] = 3; A.tm_rank = 3; A.tm_dim_inner = 0; A.tm_dim_e = 1; A.tm_e_mul = d0.q; A.tm_dim_outer = -1;
                         GSB_TRY(dispatch_sweep(kind, 0, d0.p + 1, A, (int)seg.size() / 4, s, &fpp, td)); }
-                        stage_io(kind, 0, &nin, &nout); account(0, A, seg, fpp, nin, nout, NI0);
+                        stage_io(kind, 0, &nin, &nout); account(0, A, seg, fpp, nin, nout, NI0h);
                     }
                     {   // S2: direction 1
                         SweepArgs A = base_args(d1);
-                        A.in = A1; A.in_cs = NI0 * Q1 * QLc; A.in_es = (i64)d1.q * QLc; A.in_ts = QLc; A.in_os = Q1 * QLc; A.in_is = 1; A.e_in0 = 0;
-                        A.ncol = NI0 * QLc; A.ninner = QLc;
+                        A.in = A1; A.in_cs = NI0h * Q1 * QLc; A.in_es = (i64)d1.q * QLc; A.in_ts = QLc; A.in_os = Q1 * QLc; A.in_is = 1; A.e_in0 = 0;
+                        A.ncol = NI0h * QLc; A.ninner = QLc;
                         // A2[g][i1][e2][i0][d1][d0][t]: the last sweep then writes (d1,d0)-contiguous runs of each CSC column
                         A.out = A2; A.out_cs = NI1 * ELc * NI0 * dL.q; A.out_fs = (i64)ELc * NI0 * W1 * dL.q; A.out_ds = (i64)W0 * dL.q;
-                        A.out_od = W0; A.out_os = (i64)W1 * W0 * dL.q; A.out_os2 = dL.q; A.out_bq = dL.q; A.out_bs = NI0 * W1 * dL.q; A.out_is = 1;
+                        A.out_od = half ? d0.p + 1 : W0; A.out_dshift = half ? d0.p : 0; A.mirror = half ? 1 : 0; A.out_nprev = d0.nfun;
+                        A.out_os = (i64)W1 * W0 * dL.q; A.out_os2 = dL.q; A.out_bq = dL.q; A.out_bs = NI0 * W1 * dL.q; A.out_is = 1;
                         const int nseg = nseg_for(A.ncol * (d1.p + 1), d1.nfun, d1.p + 1);
                         std::vector<int> seg = make_segments(d1, 0, d1.nfun, nseg);
                         A.seg = a->d_seg + segoff; GSB_TRY(upload_segments(a, seg, &segoff));
                         mark(a, 2);
-                        { TmapDesc td; memset(&td, 0, sizeof td); td.valid = true; td.rank = 4; td.dims[0] = (unsigned long long)(QLc); td.dims[1] = (unsigned long long)(Q1); td.dims[2] = (unsigned long long)(NI0); td.dims[3] = (unsigned long long)(no1); td.strides[0] = 8ull * (unsigned long long)(QLc); td.strides[1] = 8ull * (unsigned long long)(Q1 * QLc); td.strides[2] = 8ull * (unsigned long long)(NI0 * Q1 * QLc); td.box_kind[0] = 1; td.box_kind[1] = 2; td.box_kind[2] = 0; td.box_kind[3] = 3; A.tm_rank = 4; A.tm_dim_inner = 0; A.tm_dim_e = 1; A.tm_e_mul = d1.q; A.tm_dim_outer = 2;
+                        { TmapDesc td; memset(&td, 0, sizeof td); td.valid = true; td.rank = 4; td.dims[0] = (unsigned long long)(QLc); td.dims[1] = (unsigned long long)(Q1); td.dims[2] = (unsigned long long)(NI0h); td.dims[3] = (unsigned long long)(no1); td.strides[0] = 8ull * (unsigned long long)(QLc); td.strides[1] = 8ull * (unsigned long long)(Q1 * QLc); td.strides[2] = 8ull * (unsigned long long)(NI0h * Q1 * QLc); td.box_kind[0] = 1; td.box_kind[1] = 2; td.box_kind[2] = 0; td.box_kind[3] = 3; A.tm_rank = 4; A.tm_dim_inner = 0; A.tm_dim_e = 1; A.tm_e_mul = d1.q; A.tm_dim_outer = 2;
                         GSB_TRY(dispatch_sweep(kind, 1, d1.p + 1, A, (int)seg.size() / 4, s, &fpp, td)); }
                         stage_io(kind, 1, &nin, &nout); account(1, A, seg, fpp, nin, nout, NI1);
                     }

@@ -57,6 +57,9 @@ struct TermOps {
     // first term contributing to z[o][b] ?
     static GSB_CX bool first(int k) { for (int j = 0; j < k; ++j) if (o(j) == o(k) && b(j) == b(k)) return false; return true; }
     static GSB_CX bool has(int oo, int bb) { for (int j = 0; j < D::NT; ++j) if (o(j) == oo && b(j) == bb) return true; return false; }
+    // output that holds the same number when owner and partner swap roles (symmetric coefficient tensor):
+    // identity unless the table overrides it
+    static GSB_CX int omirror(int oo) { return oo; }
 };
 // symmetric coefficient tensor, 3-D (Poisson): D = {00,01,02,11,12,22}
 struct T3SymS1 : TermOps<T3SymS1> { enum { NIN = 6, NOUT = 8, NT = 8 };
@@ -66,7 +69,8 @@ struct T3SymS1 : TermOps<T3SymS1> { enum { NIN = 6, NOUT = 8, NT = 8 };
 struct T3SymS2 : TermOps<T3SymS2> { enum { NIN = 8, NOUT = 4, NT = 9 };
     static GSB_CX int pk(int k) { const int v[9] = {GSB_PK(0,0,0,0), GSB_PK(0,1,0,1), GSB_PK(0,2,1,0), GSB_PK(0,3,1,1),
                                                     GSB_PK(1,4,0,0), GSB_PK(2,5,0,0), GSB_PK(1,6,1,0), GSB_PK(2,6,0,1),
-                                                    GSB_PK(3,7,0,0)}; return v[k]; } };
+                                                    GSB_PK(3,7,0,0)}; return v[k]; }
+    static GSB_CX int omirror(int oo) { return oo == 1 ? 2 : (oo == 2 ? 1 : oo); } };   // g = 2*alpha2 + beta2: swap the flags
 // last direction of any gradient-gradient form: in_g, g = 2*a+b
 struct TLast : TermOps<TLast> { enum { NIN = 4, NOUT = 1, NT = 4 };
     static GSB_CX int pk(int k) { const int v[4] = {GSB_PK(0,0,0,0), GSB_PK(0,1,0,1), GSB_PK(0,2,1,0), GSB_PK(0,3,1,1)}; return v[k]; } };
@@ -578,6 +582,9 @@ struct SweepArgs {
     const double *in; double *out;
     i64 in_cs, in_es, in_ts, in_os, in_is; int e_in0;          // input strides: comp, element, point, outer, inner
     i64 out_cs, out_fs, out_ds, out_os, out_os2, out_od, out_bs, out_is, out_bq;   // output strides: comp, owner fn, delta, outer (split at out_od), block, inner
+    // symmetry of the form (D symmetric): the first sweep may emit only delta >= 0 (half_out, delta index offset
+    // d_off instead of p) and the second sweep then writes every value to its mirrored slot as well (mirror)
+    int half_out, d_off, mirror; i64 out_dshift, out_nprev;
     i64 ncol; i64 ninner;
     // tensor-map TMA variant: which box coordinate carries the tile start, the span, the outer index
     int tm_rank, tm_dim_inner, tm_dim_e, tm_e_mul, tm_dim_outer;
@@ -591,11 +598,13 @@ struct SweepCore {
     static constexpr int NOUT = T::NOUT, NIN = T::NIN, NT = T::NT;
     double acc[IS][P1][NOUT];
     OwnerCache oc[FINAL ? IS : 1];
+    i64 obase_m;                                  // output base of the mirrored column, or -1
 
     GSB_MEMBER void zero()
     {
 #pragma unroll
         for (int is = 0; is < (FINAL ? IS : 1); ++is) { oc[is].fun = -1; oc[is].rec = 0; }
+        obase_m = -1;
 #pragma unroll
         for (int is = 0; is < IS; ++is)
 #pragma unroll
@@ -641,9 +650,17 @@ struct SweepCore {
             const i64 pos = final_prepare(A.fin, fc, c, d, acc[is][js][0]);
             if (pos >= 0) A.fin.values[pos] = acc[is][js][0];
         } else {
-            const i64 o0 = (i64)fi * A.out_fs + (i64)(d + A.p) * A.out_ds + obase;
+            if (A.half_out && d < 0) return;      // the mirrored pair (partner, -d) carries this value
+            const i64 o0 = (i64)fi * A.out_fs + (i64)(d + A.d_off) * A.out_ds + obase;
 #pragma unroll
             for (int o = 0; o < NOUT; ++o) A.out[o * A.out_cs + o0] = acc[is][js][o];
+            if (obase_m >= 0) {                   // same number, roles of owner and partner exchanged
+                const i64 om = (i64)(fi + d) * A.out_fs + (i64)(A.d_off - d) * A.out_ds + obase_m;
+                static_for<0, NOUT>([&](auto oc_) {
+                    constexpr int o = decltype(oc_)::value;
+                    A.out[T::omirror(o) * A.out_cs + om] = acc[is][js][o];
+                });
+            }
         }
     }
 
@@ -685,6 +702,16 @@ struct SweepCore {
     }
 };
 
+// Output base of a thread's column; *mirror receives the base of the column with owner and partner exchanged in
+// the previous direction ((i0,d0) -> (i0+d0,-d0)) when the sweep has to write mirrored values, else -1.
+GSB_DEVICE i64 sweep_obase(const SweepArgs &A, i64 outer, i64 inner, i64 *mirror)
+{
+    const i64 i0 = outer / A.out_od, d0 = outer % A.out_od;
+    const i64 in_part = (inner / A.out_bq) * A.out_bs + (inner % A.out_bq) * A.out_is;
+    *mirror = (A.mirror && d0 > 0 && i0 + d0 < A.out_nprev) ? (i0 + d0) * A.out_os + (A.out_dshift - d0) * A.out_os2 + in_part : -1;
+    return i0 * A.out_os + (d0 + A.out_dshift) * A.out_os2 + in_part;
+}
+
 // Generic variant: inputs straight from global memory (any strides / alignment).
 template <int P1, class T, int IS, bool FINAL>
 GSB_GLOBAL void k_sweep(const SweepArgs A)
@@ -696,12 +723,13 @@ GSB_GLOBAL void k_sweep(const SweepArgs A)
     const i64 outer = col / A.ninner, inner = col - outer * A.ninner;
     const double *inp = A.in + outer * A.in_os + inner * A.in_is;
     FinalCtx fc;
-    i64 obase = 0;
+    i64 obase = 0, obase_mirror = -1;
     if (FINAL) { if (!final_init(A.fin, outer, inner, fc)) return; }
-    else obase = (outer / A.out_od) * A.out_os + (outer % A.out_od) * A.out_os2 + (inner / A.out_bq) * A.out_bs + (inner % A.out_bq) * A.out_is;
+    else obase = sweep_obase(A, outer, inner, &obase_mirror);
     constexpr int NIN = T::NIN;
     SweepCore<P1, T, IS, FINAL> core;
     core.zero();
+    core.obase_m = obase_mirror;
     const int q = A.q;
     for (int e = e_begin; e < e_end; ++e) {
         const int f0 = A.first[e];
@@ -817,12 +845,13 @@ GSB_GLOBAL void __launch_bounds__(TC * (P1 / IS), MINB) k_sweep_tma(const SweepA
         for (int e = e_begin; e < e_end && e < e_begin + NSTAGE; ++e) issue(e, e - e_begin);
 
     FinalCtx fc;
-    i64 obase = 0;
+    i64 obase = 0, obase_mirror = -1;
     bool live = lcol < ncols;
     if (FINAL) { if (live) live = final_init(A.fin, outer, inner, fc); }
-    else obase = (outer / A.out_od) * A.out_os + (outer % A.out_od) * A.out_os2 + (inner / A.out_bq) * A.out_bs + (inner % A.out_bq) * A.out_is;
+    else obase = sweep_obase(A, outer, inner, &obase_mirror);
     SweepCore<P1, T, IS, FINAL> core;
     core.zero();
+    core.obase_m = obase_mirror;
     int f0 = A.first[e_begin], nx = A.nexit[e_begin];
     int s = 0; unsigned par = 0;
     for (int e = e_begin; e < e_end; ++e) {
