@@ -63,13 +63,13 @@ struct Dir1D {
     int p = 0, q = 0, nfun = 0, nel = 0, Q = 0;
     std::vector<int> span, first, nexit, plo, phi, ffirst, flast;
     int *d_first = 0, *d_nexit = 0, *d_plo = 0, *d_phi = 0, *d_ffirst = 0, *d_flast = 0;
-    double2 *d_tab = 0; double *d_upt = 0, *d_hpt = 0, *d_gw = 0, *d_gwp = 0;
+    double2 *d_tab = 0, *d_tabl = 0; double *d_upt = 0, *d_hpt = 0, *d_gw = 0, *d_gwp = 0;
     double2 *d_gtab = 0; int *d_gfirst = 0; int pg1 = 0, ngeo = 0;
     // basis values at the two ends of the parameter interval (Neumann sides): [0] lower, [1] upper
     double bval[2][GSB_MAXP + 1]; int bfirst[2]; double2 bgeo[2][GSB_MAXP + 1]; int bgfirst[2];
     void release() {
         dev_free(d_first); dev_free(d_nexit); dev_free(d_plo); dev_free(d_phi); dev_free(d_ffirst); dev_free(d_flast);
-        dev_free(d_tab); dev_free(d_upt); dev_free(d_hpt); dev_free(d_gw); dev_free(d_gwp); dev_free(d_gtab); dev_free(d_gfirst);
+        dev_free(d_tab); dev_free(d_tabl); dev_free(d_upt); dev_free(d_hpt); dev_free(d_gw); dev_free(d_gwp); dev_free(d_gtab); dev_free(d_gfirst);
     }
 };
 
@@ -118,11 +118,12 @@ static int build_dir(Dir1D &d, const double *kn, int nk, int p, int q, const dou
     GSB_TRY(upload(&d.d_plo, d.plo, s)); GSB_TRY(upload(&d.d_phi, d.phi, s));
     GSB_TRY(upload(&d.d_ffirst, d.ffirst, s)); GSB_TRY(upload(&d.d_flast, d.flast, s));
     GSB_TRY(dev_malloc((void **)&d.d_tab, sizeof(double2) * (size_t)d.Q * p1));
+    GSB_TRY(dev_malloc((void **)&d.d_tabl, sizeof(double2) * (size_t)d.Q * p1));
     GSB_TRY(dev_malloc((void **)&d.d_upt, sizeof(double) * (size_t)d.Q));
     GSB_TRY(dev_malloc((void **)&d.d_hpt, sizeof(double) * (size_t)d.Q));
     GSB_TRY(dev_malloc((void **)&d.d_gwp, sizeof(double) * (size_t)d.Q));
     BasisTableArgs B; B.knots = d_kn; B.span = d_span; B.gnodes = d_gx; B.gweights = d.d_gw; B.p = p; B.nel = d.nel; B.q = q;
-    B.tab = d.d_tab; B.upt = d.d_upt; B.hpt = d.d_hpt; B.gwp = d.d_gwp;
+    B.tab = d.d_tab; B.tabl = d.d_tabl; B.upt = d.d_upt; B.hpt = d.d_hpt; B.gwp = d.d_gwp;
     GSB_LAUNCH(k_basis_table, dim3((d.Q + 127) / 128), dim3(128), s, B);
     d.pg1 = gp + 1; d.ngeo = gnk - gp - 1;
     GSB_TRY(dev_malloc((void **)&d.d_gtab, sizeof(double2) * (size_t)d.Q * d.pg1));
@@ -416,12 +417,56 @@ static int launch_sweep_i(const SweepArgs &A, int nseg, stream_t s, i64 *flops_p
     GSB_LAUNCH(kfn, grid, dim3(128), s, A);
     return 0;
 }
+// Window kernel (default): one launch per group of output components; a group is as many outputs as keep the
+// (p+1)^2 * NG accumulators in registers.  GSB200_SWEEP=ring selects the shared-memory ring kernels instead.
+constexpr int window_ng(int P1, int NOUT) { int ng = 36 / (P1 * P1); if (ng < 1) ng = 1; return ng < NOUT ? ng : NOUT; }
+#ifndef GSB200_EMULATE
+template <class K> static int window_launch(K kfn, dim3 grid, size_t smem, stream_t s, const SweepArgs &A)
+{
+    static std::vector<const void *> attributed;
+    if (std::find(attributed.begin(), attributed.end(), (const void *)kfn) == attributed.end()) {
+        GSB_TRY(dev_check(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute"));
+        attributed.push_back((const void *)kfn);
+    }
+    if (!dry_run()) { kfn<<<grid, dim3(128), smem, s>>>(A); note_launch(); }
+    return 0;
+}
+#endif
+template <int P1, class T, bool FINAL, int NG, int GI>
+static int launch_window_groups(const SweepArgs &A, int nseg, stream_t s)
+{
+    if constexpr (GI * NG < T::NOUT) {
+        constexpr unsigned OMASK = group_mask<T, NG>(GI);
+        const dim3 grid((unsigned)((A.ncol + 127) / 128), 1, nseg);
+#ifndef GSB200_EMULATE
+        static const int ns = [] { const char *e = getenv("GSB200_WSTAGES"); return e ? atoi(e) : 3; }();
+        if (ns == 0) GSB_TRY(window_launch(k_sweepw<P1, T, OMASK, FINAL, 0>, grid, 0, s, A));
+        else if (ns >= 4) GSB_TRY(window_launch(k_sweepw<P1, T, OMASK, FINAL, 4>, grid, window_smem<P1, T, OMASK, 4>(), s, A));
+        else if (ns == 3) GSB_TRY(window_launch(k_sweepw<P1, T, OMASK, FINAL, 3>, grid, window_smem<P1, T, OMASK, 3>(), s, A));
+        else GSB_TRY(window_launch(k_sweepw<P1, T, OMASK, FINAL, 2>, grid, window_smem<P1, T, OMASK, 2>(), s, A));
+#else
+        { auto kfn = k_sweepw<P1, T, OMASK, FINAL, 3>; GSB_LAUNCH(kfn, grid, dim3(128), s, A); }
+#endif
+        return launch_window_groups<P1, T, FINAL, NG, GI + 1>(A, nseg, s);
+    }
+    return 0;
+}
+static bool use_window(const SweepArgs &A, int P1)
+{
+    static const bool ring = [] { const char *e = getenv("GSB200_SWEEP"); return e && !strcmp(e, "ring"); }();
+    return !ring && A.q == P1;
+}
+
 // owner slots per thread: the largest that keeps the accumulators in registers, or (GSB200_ISDIV=1)
 // half of it: twice the threads per column tile, half the accumulators each -> more resident warps
 template <int P1, class T, bool FINAL>
 static int launch_sweep_t(const SweepArgs &A, int nseg, stream_t s, i64 *fpp, const TmapDesc &td)
 {
     constexpr int IS = pick_is(P1, T::NOUT);
+    if (use_window(A, P1)) {
+        *fpp = (i64)P1 * (2 * T::NT - n_first<T>() + 2 * P1 * n_has<T>());
+        return launch_window_groups<P1, T, FINAL, window_ng(P1, T::NOUT), 0>(A, nseg, s);
+    }
     if constexpr (!FINAL && IS % 2 == 0 && IS > 1) {
         static const char *env = getenv("GSB200_ISDIV");
         if (env && atoi(env) > 0) return launch_sweep_i<P1, T, FINAL, IS / 2>(A, nseg, s, fpp, td);
@@ -533,7 +578,11 @@ static int assemble_pass(gsb200_assembler *a)
         const i64 n0 = d0.nfun, n1 = dim == 3 ? d1.nfun : 1;
         const i64 W0 = 2 * d0.p + 1, W1 = dim == 3 ? 2 * d1.p + 1 : 1;
         // symmetric forms in 3-D: the first sweep keeps only delta0 >= 0, the second one mirrors its output
-        const bool half = dim == 3 && kind != KIND_GEN && !getenv("GSB200_NOSYM");
+        const bool half = dim == 3 && kind != KIND_GEN && getenv("GSB200_SYM") && getenv("GSB200_SWEEP");   // experiment, ring kernels only
+        static const bool a2_rows_env = [] { const char *e = getenv("GSB200_A2ROWS"); return e && atoi(e) > 0; }();
+        static const bool a1_blk_env = [] { const char *e = getenv("GSB200_A1BLK"); return !e || atoi(e) > 0; }();   // default on
+        const bool a1_blk = a1_blk_env && !half && dim == 3 && !getenv("GSB200_SWEEP");
+        const bool a2_rows = a2_rows_env && !half && dim == 3 && !a1_blk;
         const i64 NI0h = half ? (i64)d0.nfun * (d0.p + 1) : NI0;     // (i0, delta0) pairs stored in A1
         // doubles of workspace per last-direction quadrature point
         i64 perq = ncD * Q0 * Q1 + no1 * NI0h * Q1 + (dim == 3 ? no2 * NI1 * NI0 : 0) + nf * Q0 * Q1 + n0 * Q1 + (dim == 3 ? n1 * n0 : 0);
@@ -586,6 +635,10 @@ static int assemble_pass(gsb200_assembler *a)
                     if (pgu > 4) pgu = 0;
                     const dim3 gg((unsigned)((QLc + 127) / 128), dim == 3 ? (unsigned)Q1 : (unsigned)Q0, dim == 3 ? (unsigned)Q0 : 1u);
                     if (gg.y > 65535u || gg.z > 65535u) { set_error("more than 65535 quadrature points per direction"); return GSB200_EUNSUPPORTED; }
+                    static const bool geo_point = [] { const char *e = getenv("GSB200_GEO"); return e && !strcmp(e, "point"); }();
+                    if (!geo_point) {
+                        if (dim == 2) { GSB_LAUNCH(k_geometry_line<2>, gg, dim3(128), s, G); } else { GSB_LAUNCH(k_geometry_line<3>, gg, dim3(128), s, G); }
+                    } else
 #define GSB_GEO(D_, P_) { auto kfn = k_geometry<D_, P_>; GSB_LAUNCH(kfn, gg, dim3(128), s, G); }
                     if (dim == 2) { switch (pgu) { case 2: GSB_GEO(2, 2) break; case 3: GSB_GEO(2, 3) break; case 4: GSB_GEO(2, 4) break; default: GSB_GEO(2, 0) } }
                     else { switch (pgu) { case 2: GSB_GEO(3, 2) break; case 3: GSB_GEO(3, 3) break; case 4: GSB_GEO(3, 4) break; default: GSB_GEO(3, 0) } }
@@ -606,8 +659,10 @@ static int assemble_pass(gsb200_assembler *a)
 
                 auto base_args = [&](const Dir1D &d) {
                     SweepArgs A; memset(&A, 0, sizeof A);
-                    A.first = d.d_first; A.nexit = d.d_nexit; A.tab = d.d_tab; A.q = d.q; A.p = d.p; A.fin = Fa;
-                    A.out_bq = 1; A.out_od = 1; A.d_off = d.p; return A;
+                    A.first = d.d_first; A.nexit = d.d_nexit; A.tab = d.d_tab; A.tabl = d.d_tabl; A.q = d.q; A.p = d.p; A.fin = Fa;
+                    A.out_bq = 1; A.out_od = 1; A.d_off = d.p;
+                    { static const int pf = [] { const char *e = getenv("GSB200_PF"); return e ? atoi(e) : 0; }(); A.pf_dist = pf; }
+                    return A;
                 };
                 auto account = [&](int slot, const SweepArgs &A, const std::vector<int> &seg, i64 fpp, int nin, int nout, i64 npairs_out) {
                     i64 pts = 0;
@@ -623,6 +678,9 @@ static int assemble_pass(gsb200_assembler *a)
                         A.ncol = Q1 * QLc; A.ninner = A.ncol;
                         A.out = A1; A.out_cs = NI0h * Q1 * QLc; A.out_fs = (half ? d0.p + 1 : 2 * d0.p + 1) * Q1 * QLc; A.out_ds = Q1 * QLc; A.out_os = 0; A.out_bq = A.ncol + 1; A.out_bs = 0; A.out_is = 1;
                         if (half) { A.half_out = 1; A.d_off = 0; }
+                        if (a1_blk) {    // A1[o][i0][q1][e2][d0][t]: the second sweep then reads AND writes whole (d0, t) runs
+                            A.out_fs = Q1 * ELc * W0 * dL.q; A.out_ds = dL.q; A.out_bq = dL.q; A.out_bs = W0 * dL.q; A.out_is = 1;
+                        }
                         const int nseg = nseg_for(A.ncol * (d0.p + 1), d0.nfun, d0.p + 1);
                         std::vector<int> seg = make_segments(d0, 0, d0.nfun, nseg);
                         A.seg = a->d_seg + segoff; GSB_TRY(upload_segments(a, seg, &segoff));
@@ -639,6 +697,15 @@ static int assemble_pass(gsb200_assembler *a)
                         A.out = A2; A.out_cs = NI1 * ELc * NI0 * dL.q; A.out_fs = (i64)ELc * NI0 * W1 * dL.q; A.out_ds = (i64)W0 * dL.q;
                         A.out_od = half ? d0.p + 1 : W0; A.out_dshift = half ? d0.p : 0; A.mirror = half ? 1 : 0; A.out_nprev = d0.nfun;
                         A.out_os = (i64)W1 * W0 * dL.q; A.out_os2 = dL.q; A.out_bq = dL.q; A.out_bs = NI0 * W1 * dL.q; A.out_is = 1;
+                        if (a1_blk) {    // thread = (i0; e2, d0, t): contiguous in A1 and, per element, in A2
+                            A.in_os = Q1 * ELc * W0 * dL.q; A.in_is = 1; A.in_ts = ELc * W0 * dL.q; A.in_es = (i64)d1.q * A.in_ts;
+                            A.ncol = n0 * ELc * W0 * dL.q; A.ninner = ELc * W0 * dL.q;
+                            A.out_od = 1; A.out_dshift = 0; A.out_os = W1 * W0 * dL.q; A.out_os2 = 0; A.out_bq = W0 * dL.q; A.out_bs = NI0 * W1 * dL.q; A.out_is = 1;
+                        }
+                        if (a2_rows) {   // A2[g][i1][i0][d1][d0][q2]: rows of the last direction (coalesced S2 stores, row-strided S3 loads)
+                            A.out_cs = NI1 * NI0 * QLc; A.out_fs = NI0 * W1 * QLc; A.out_ds = W0 * QLc; A.out_os = W1 * W0 * QLc; A.out_os2 = QLc;
+                            A.out_bq = QLc + 1; A.out_bs = 0; A.out_is = 1;
+                        }
                         const int nseg = nseg_for(A.ncol * (d1.p + 1), d1.nfun, d1.p + 1);
                         std::vector<int> seg = make_segments(d1, 0, d1.nfun, nseg);
                         A.seg = a->d_seg + segoff; GSB_TRY(upload_segments(a, seg, &segoff));
@@ -651,6 +718,7 @@ static int assemble_pass(gsb200_assembler *a)
                         SweepArgs A = base_args(dL);
                         A.in = A2; A.in_cs = NI1 * ELc * NI0 * dL.q; A.in_es = NI0 * W1 * dL.q; A.in_ts = 1; A.in_os = (i64)ELc * NI0 * W1 * dL.q; A.in_is = dL.q; A.e_in0 = eL0;
                         A.ncol = NI1 * NI0; A.ninner = NI0 * W1;     // outer = i1, inner = (i0, d1, d0)
+                        if (a2_rows) { A.in_cs = NI1 * NI0 * QLc; A.in_es = dL.q; A.in_ts = 1; A.in_os = NI0 * W1 * QLc; A.in_is = QLc; A.e_in0 = eL0; }
                         const int nseg = nseg_for(A.ncol, x_hi - x_lo, dL.p + 1);
                         std::vector<int> seg = make_segments(dL, x_lo, x_hi, nseg);
                         A.seg = a->d_seg + segoff; GSB_TRY(upload_segments(a, seg, &segoff));

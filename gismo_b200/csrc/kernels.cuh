@@ -60,17 +60,22 @@ struct TermOps {
     // output that holds the same number when owner and partner swap roles (symmetric coefficient tensor):
     // identity unless the table overrides it
     static GSB_CX int omirror(int oo) { return oo; }
+    // output order in which the window kernel forms its groups: consecutive outputs of this order share inputs
+    static GSB_CX int order(int i) { return i; }
+    static GSB_CX bool uses_c(unsigned omask, int cc) { for (int j = 0; j < D::NT; ++j) if (((omask >> o(j)) & 1u) && c(j) == cc) return true; return false; }
 };
 // symmetric coefficient tensor, 3-D (Poisson): D = {00,01,02,11,12,22}
 struct T3SymS1 : TermOps<T3SymS1> { enum { NIN = 6, NOUT = 8, NT = 8 };
     static GSB_CX int pk(int k) { const int v[8] = {GSB_PK(0,0,1,1), GSB_PK(1,1,1,0), GSB_PK(2,1,0,1), GSB_PK(3,3,0,0),
-                                                    GSB_PK(4,2,1,0), GSB_PK(5,2,0,1), GSB_PK(6,4,0,0), GSB_PK(7,5,0,0)}; return v[k]; } };
+                                                    GSB_PK(4,2,1,0), GSB_PK(5,2,0,1), GSB_PK(6,4,0,0), GSB_PK(7,5,0,0)}; return v[k]; }
+    static GSB_CX int order(int i) { const int v[8] = {1, 2, 0, 3, 4, 5, 6, 7}; return v[i]; } };
 // outputs g = 2*(a==2)+(b==2): flags still needed in direction 2
 struct T3SymS2 : TermOps<T3SymS2> { enum { NIN = 8, NOUT = 4, NT = 9 };
     static GSB_CX int pk(int k) { const int v[9] = {GSB_PK(0,0,0,0), GSB_PK(0,1,0,1), GSB_PK(0,2,1,0), GSB_PK(0,3,1,1),
                                                     GSB_PK(1,4,0,0), GSB_PK(2,5,0,0), GSB_PK(1,6,1,0), GSB_PK(2,6,0,1),
                                                     GSB_PK(3,7,0,0)}; return v[k]; }
-    static GSB_CX int omirror(int oo) { return oo == 1 ? 2 : (oo == 2 ? 1 : oo); } };   // g = 2*alpha2 + beta2: swap the flags
+    static GSB_CX int omirror(int oo) { return oo == 1 ? 2 : (oo == 2 ? 1 : oo); }      // g = 2*alpha2 + beta2: swap the flags
+    static GSB_CX int order(int i) { const int v[4] = {0, 3, 1, 2}; return v[i]; } };
 // last direction of any gradient-gradient form: in_g, g = 2*a+b
 struct TLast : TermOps<TLast> { enum { NIN = 4, NOUT = 1, NT = 4 };
     static GSB_CX int pk(int k) { const int v[4] = {GSB_PK(0,0,0,0), GSB_PK(0,1,0,1), GSB_PK(0,2,1,0), GSB_PK(0,3,1,1)}; return v[k]; } };
@@ -83,7 +88,8 @@ struct T3GenS2 : TermOps<T3GenS2> { enum { NIN = 9, NOUT = 4, NT = 9 };
                                                     GSB_PK(1,5,1,0), GSB_PK(2,6,0,0), GSB_PK(2,7,0,1), GSB_PK(3,8,0,0)}; return v[k]; } };
 // 2-D: symmetric D = {00,01,11}; general c = 2a+b.  Outputs g = 2*(a==1)+(b==1).
 struct T2SymS1 : TermOps<T2SymS1> { enum { NIN = 3, NOUT = 4, NT = 4 };
-    static GSB_CX int pk(int k) { const int v[4] = {GSB_PK(0,0,1,1), GSB_PK(1,1,1,0), GSB_PK(2,1,0,1), GSB_PK(3,2,0,0)}; return v[k]; } };
+    static GSB_CX int pk(int k) { const int v[4] = {GSB_PK(0,0,1,1), GSB_PK(1,1,1,0), GSB_PK(2,1,0,1), GSB_PK(3,2,0,0)}; return v[k]; }
+    static GSB_CX int order(int i) { const int v[4] = {1, 2, 0, 3}; return v[i]; } };
 struct T2GenS1 : TermOps<T2GenS1> { enum { NIN = 4, NOUT = 4, NT = 4 };
     static GSB_CX int pk(int k) { const int v[4] = {GSB_PK(0,0,1,1), GSB_PK(1,1,1,0), GSB_PK(2,2,0,1), GSB_PK(3,3,0,0)}; return v[k]; } };
 // mass-type form: one scalar density, no derivatives, every direction
@@ -125,7 +131,8 @@ GSB_HD void bspline_ders(const double *kn, int p, int s, double u, double *val, 
 struct BasisTableArgs {
     const double *knots; const int *span; const double *gnodes; const double *gweights;
     int p, nel, q;
-    double2 *tab;      // [nel*q][p+1]
+    double2 *tab;      // [nel*q][p+1] slot order
+    double2 *tabl;     // [nel*q][p+1] local order (a-th active function of the span)
     double *upt;       // [nel*q] point coordinate
     double *hpt;       // [nel*q] half element width h
     double *gwp;       // [nel*q] reference Gauss weight of the point
@@ -141,6 +148,7 @@ GSB_GLOBAL void k_basis_table(const BasisTableArgs A)
     bspline_ders(A.knots, A.p, s, u, val, der);
     const int first = s - A.p;
     for (int a = 0; a < p1; ++a) A.tab[(i64)id * p1 + (first + a) % p1] = make_double2(val[a], der[a]);
+    for (int a = 0; a < p1; ++a) A.tabl[(i64)id * p1 + a] = make_double2(val[a], der[a]);
     A.upt[id] = u;
     A.hpt[id] = h;
     A.gwp[id] = A.gweights[t];
@@ -238,6 +246,64 @@ struct GeoArgs {
     double *D; i64 dstride;        // may be NULL (load only)
     double *F; i64 fstride; int nf; DevProgram prog[3];
 };
+// Common tail of the geometry kernels: inverse/measure of the Jacobian, quadrature weight, coefficient tensor of
+// the form and load density at one point.
+template <int DIM>
+GSB_DEVICE void geo_finish(const GeoArgs &A, i64 id, const int (&ql)[DIM], const double (&x)[3], const double (&J)[DIM][DIM])
+{
+    double Ji[DIM][DIM], det;   // Ji[a][c] = (J^-1)[a][c]
+    if (DIM == 2) {
+        det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+        Ji[0][0] = J[1][1] / det; Ji[0][1] = -J[0][1] / det; Ji[1][0] = -J[1][0] / det; Ji[1][1] = J[0][0] / det;
+    } else {
+        const int X = DIM == 3 ? 2 : 0;  // keeps the 2-D instantiation in bounds
+        const double c00 = J[1][1] * J[X][X] - J[1][X] * J[X][1], c01 = J[1][X] * J[X][0] - J[1][0] * J[X][X],
+                     c02 = J[1][0] * J[X][1] - J[1][1] * J[X][0];
+        det = J[0][0] * c00 + J[0][1] * c01 + J[0][X] * c02;
+        const double id_ = 1.0 / det;
+        Ji[0][0] = c00 * id_; Ji[0][1] = (J[0][X] * J[X][1] - J[0][1] * J[X][X]) * id_; Ji[0][X] = (J[0][1] * J[1][X] - J[0][X] * J[1][1]) * id_;
+        Ji[1][0] = c01 * id_; Ji[1][1] = (J[0][0] * J[X][X] - J[0][X] * J[X][0]) * id_; Ji[1][X] = (J[0][X] * J[1][0] - J[0][0] * J[1][X]) * id_;
+        Ji[X][0] = c02 * id_; Ji[X][1] = (J[0][1] * J[X][0] - J[0][0] * J[X][1]) * id_; Ji[X][X] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * id_;
+    }
+    // quadrature weight: hprod * (w_0 w_1 w_2), same association as the reference
+    double hprod = 1.0, wp = 1.0;
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) {
+        const double h = A.hpt[k][ql[k]];
+        hprod *= (h == 0.0 ? 0.5 : h);
+        const double g = A.gwp[k][ql[k]];
+        wp = (k == 0) ? g : wp * g;
+    }
+    const double weight = hprod * wp * fabs(det);
+    if (A.F) for (int c = 0; c < A.nf; ++c) A.F[c * A.fstride + id] = weight * program_eval(A.prog[c], x[0], x[1], x[2]);
+    if (!A.D) return;
+    if (A.form == GSB200_FORM_MASS) { A.D[id] = weight; return; }
+    double G[DIM][DIM];   // (J^-1 J^-T)_ab
+#pragma unroll
+    for (int a = 0; a < DIM; ++a)
+#pragma unroll
+        for (int b = a; b < DIM; ++b) {       // symmetric: the products commute, so the mirrored entry is the same number
+            double s = 0.0;
+#pragma unroll
+            for (int c = 0; c < DIM; ++c) s += Ji[a][c] * Ji[b][c];
+            G[a][b] = s; G[b][a] = s;
+        }
+    if (A.form == GSB200_FORM_POISSON) {
+        if (A.symD) { int c = 0; for (int a = 0; a < DIM; ++a) for (int b = a; b < DIM; ++b) A.D[(c++) * A.dstride + id] = weight * G[a][b]; }
+        else for (int a = 0; a < DIM; ++a) for (int b = 0; b < DIM; ++b) A.D[(a * DIM + b) * A.dstride + id] = weight * G[a][b];
+        return;
+    }
+    // elasticity block (row comp r = brow carried by the partner/test function, col comp c = bcol by the owner):
+    // E_{a'b'} = w ( lambda Ji[a'][r] Ji[b'][c] + mu ( Ji[a'][c] Ji[b'][r] + delta_rc G[a'][b'] ) ), a' on the row function.
+    // The sweeps put the FIRST tensor index on the owner, hence the transpose when storing.
+    const int r = A.brow, cc = A.bcol;
+    for (int a = 0; a < DIM; ++a) for (int b = 0; b < DIM; ++b) {
+        const double E = A.lambda * Ji[b][r] * Ji[a][cc] + A.mu * (Ji[b][cc] * Ji[a][r] + (r == cc ? G[b][a] : 0.0));
+        A.D[(a * DIM + b) * A.dstride + id] = weight * E;
+    }
+}
+
+
 // Thread = one point of the last direction (fastest in memory), blockIdx.y/z = the other
 // directions.  PG = geometry degree + 1 when equal in all directions (loops unrolled, 1-D values
 // in registers) or 0 for the generic run-time loop.
@@ -314,52 +380,109 @@ GSB_GLOBAL void k_geometry(const GeoArgs A)
     } else {
         for (int c = 0; c < DIM; ++c) { x[c] = xn[c]; for (int a = 0; a < DIM; ++a) J[c][a] = dxn[a][c]; }
     }
-    double Ji[DIM][DIM], det;   // Ji[a][c] = (J^-1)[a][c]
-    if (DIM == 2) {
-        det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
-        Ji[0][0] = J[1][1] / det; Ji[0][1] = -J[0][1] / det; Ji[1][0] = -J[1][0] / det; Ji[1][1] = J[0][0] / det;
-    } else {
-        const int X = DIM == 3 ? 2 : 0;  // keeps the 2-D instantiation in bounds
-        const double c00 = J[1][1] * J[X][X] - J[1][X] * J[X][1], c01 = J[1][X] * J[X][0] - J[1][0] * J[X][X],
-                     c02 = J[1][0] * J[X][1] - J[1][1] * J[X][0];
-        det = J[0][0] * c00 + J[0][1] * c01 + J[0][X] * c02;
-        const double id_ = 1.0 / det;
-        Ji[0][0] = c00 * id_; Ji[0][1] = (J[0][X] * J[X][1] - J[0][1] * J[X][X]) * id_; Ji[0][X] = (J[0][1] * J[1][X] - J[0][X] * J[1][1]) * id_;
-        Ji[1][0] = c01 * id_; Ji[1][1] = (J[0][0] * J[X][X] - J[0][X] * J[X][0]) * id_; Ji[1][X] = (J[0][X] * J[1][0] - J[0][0] * J[1][X]) * id_;
-        Ji[X][0] = c02 * id_; Ji[X][1] = (J[0][1] * J[X][0] - J[0][0] * J[X][1]) * id_; Ji[X][X] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * id_;
-    }
-    // quadrature weight: hprod * (w_0 w_1 w_2), same association as the reference
-    double hprod = 1.0, wp = 1.0;
+    geo_finish<DIM>(A, id, ql, x, J);
+}
+
+// K0, line-factorised (default).  All threads of a block share the quadrature indices of the leading
+// directions and differ only in the LAST one, so the tensor-product sum over the geometry's control points is
+// split: the block first contracts the leading directions into "line coefficients"
+//   E[a_L][field][kind] = sum_{a_0(,a_1)} B^(kind)(q_0(,q_1)) C_field[a_0(,a_1), a_L],  kind = value, d/dxi_0 (, d/dxi_1)
+// (shared memory, a few hundred FMAs per block), then every thread finishes with a short 1-D sum over the
+// (geometry degree + 1) functions of the last direction.  Fields = the geoDim coordinates (times the weight
+// for a rational geometry) and the weight itself.  Same map data as k_geometry (gsGeometry.hpp:557-564,
+// gsRationalBasis.h:481-520, gsFunction.hpp:702-751), ~5x fewer FP64 operations per point at degree 1-3.
+#define GSB_GEO_MAXA 48
+#ifndef GSB200_EMULATE
+#define GSB_SHARED __shared__
+#define GSB_SYNCTHREADS() __syncthreads()
+#define GSB_COOP_FIRST ((int)threadIdx.x)
+#define GSB_COOP_STEP ((int)blockDim.x)
+#else
+#define GSB_SHARED
+#define GSB_SYNCTHREADS()
+#define GSB_COOP_FIRST 0
+#define GSB_COOP_STEP 1
+#endif
+template <int DIM>
+GSB_GLOBAL void k_geometry_line(const GeoArgs A)
+{
+    constexpr int L = DIM - 1, NFM = DIM + 1;
+    GSB_SHARED double E[GSB_GEO_MAXA][NFM][DIM];
+    const int q0blk = blockIdx.x * blockDim.x, qlast = q0blk + threadIdx.x;
+    const bool active = qlast < A.qn[L];
+    int ql[DIM];
+    i64 id;
+    ql[L] = (active ? qlast : A.qn[L] - 1) + A.qoff[L];
+    if (DIM == 3) { ql[1] = blockIdx.y + A.qoff[1]; ql[0] = blockIdx.z + A.qoff[0]; id = ((i64)blockIdx.z * A.qn[1] + blockIdx.y) * A.qn[L] + qlast; }
+    else { ql[0] = blockIdx.y + A.qoff[0]; id = (i64)blockIdx.y * A.qn[L] + qlast; }
+    const bool rational = A.weights != 0;
+    const int nf = rational ? DIM + 1 : DIM;
+    // range of last-direction control points touched by the block (gfirst is non-decreasing along the points)
+    const int qb_first = q0blk + A.qoff[L];
+    const int qb_last = (q0blk + (int)blockDim.x - 1 < A.qn[L] ? q0blk + (int)blockDim.x - 1 : A.qn[L] - 1) + A.qoff[L];
+    const int pgL = A.pg1[L];
+    const int lo = A.gfirst[L][qb_first], hi = A.gfirst[L][qb_last] + pgL;
+    const int gfL = A.gfirst[L][ql[L]];
+    int gf[DIM];
 #pragma unroll
-    for (int k = 0; k < DIM; ++k) {
-        const double h = A.hpt[k][ql[k]];
-        hprod *= (h == 0.0 ? 0.5 : h);
-        const double g = A.gwp[k][ql[k]];
-        wp = (k == 0) ? g : wp * g;
+    for (int k = 0; k < DIM; ++k) gf[k] = A.gfirst[k][ql[k]];
+    double val[NFM], dd[NFM][DIM];      // dd[f][k] = d field_f / d xi_k
+#pragma unroll
+    for (int f = 0; f < NFM; ++f) { val[f] = 0.0;
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) dd[f][k] = 0.0; }
+    for (int abase = lo; abase < hi; abase += GSB_GEO_MAXA) {
+        const int cnt = hi - abase < GSB_GEO_MAXA ? hi - abase : GSB_GEO_MAXA;
+        GSB_SYNCTHREADS();
+        for (int item = GSB_COOP_FIRST; item < cnt * nf; item += GSB_COOP_STEP) {
+            const int aa = item / nf, f = item - aa * nf, aL = abase + aa;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+            const int n1 = DIM == 3 ? A.pg1[1] : 1;
+            for (int a1 = 0; a1 < n1; ++a1) {
+                const double2 b1 = DIM == 3 ? A.gtab[1][(i64)ql[1] * A.pg1[1] + a1] : make_double2(1.0, 0.0);
+                const i64 row = DIM == 3 ? ((i64)aL * A.ngeo[1] + (gf[1] + a1)) * A.ngeo[0] + gf[0] : (i64)aL * A.ngeo[0] + gf[0];
+                for (int a0 = 0; a0 < A.pg1[0]; ++a0) {
+                    const double2 b0 = A.gtab[0][(i64)ql[0] * A.pg1[0] + a0];
+                    const i64 idx = row + a0;
+                    double C = f < DIM ? A.coefs[(i64)f * A.ngeo_total + idx] : 1.0;
+                    if (rational) C *= A.weights[idx];
+                    s0 = fma(b0.x * b1.x, C, s0); s1 = fma(b0.y * b1.x, C, s1); s2 = fma(b0.x * b1.y, C, s2);
+                }
+            }
+            E[aa][f][0] = s0; E[aa][f][1] = s1; if (DIM == 3) E[aa][f][DIM - 1] = s2;
+        }
+        GSB_SYNCTHREADS();
+        for (int k = 0; k < pgL; ++k) {
+            const int aa = gfL + k - abase;
+            if (aa < 0 || aa >= cnt) continue;
+            const double2 bL = A.gtab[L][(i64)ql[L] * pgL + k];
+#pragma unroll
+            for (int f = 0; f < NFM; ++f) {
+                if (f >= nf) break;
+                val[f] = fma(bL.x, E[aa][f][0], val[f]);
+                dd[f][0] = fma(bL.x, E[aa][f][1], dd[f][0]);
+                if (DIM == 3) dd[f][1] = fma(bL.x, E[aa][f][DIM - 1], dd[f][1]);
+                dd[f][L] = fma(bL.y, E[aa][f][0], dd[f][L]);
+            }
+        }
     }
-    const double weight = hprod * wp * fabs(det);
-    if (A.F) for (int c = 0; c < A.nf; ++c) A.F[c * A.fstride + id] = weight * program_eval(A.prog[c], x[0], x[1], x[2]);
-    if (!A.D) return;
-    if (A.form == GSB200_FORM_MASS) { A.D[id] = weight; return; }
-    double G[DIM][DIM];   // (J^-1 J^-T)_ab
-    for (int a = 0; a < DIM; ++a) for (int b = 0; b < DIM; ++b) {
-        double s = 0.0;
-        for (int c = 0; c < DIM; ++c) s += Ji[a][c] * Ji[b][c];
-        G[a][b] = s;
+    if (!active) return;
+    double x[3] = {0.0, 0.0, 0.0}, J[DIM][DIM];   // J[c][a] = d x_c / d xi_a
+    if (rational) {
+        const double W = val[DIM];
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) {
+            x[c] = val[c] / W;
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) J[c][a] = (dd[c][a] * W - val[c] * dd[DIM][a]) / (W * W);
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) { x[c] = val[c];
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) J[c][a] = dd[c][a]; }
     }
-    if (A.form == GSB200_FORM_POISSON) {
-        if (A.symD) { int c = 0; for (int a = 0; a < DIM; ++a) for (int b = a; b < DIM; ++b) A.D[(c++) * A.dstride + id] = weight * G[a][b]; }
-        else for (int a = 0; a < DIM; ++a) for (int b = 0; b < DIM; ++b) A.D[(a * DIM + b) * A.dstride + id] = weight * G[a][b];
-        return;
-    }
-    // elasticity block (row comp r = brow carried by the partner/test function, col comp c = bcol by the owner):
-    // E_{a'b'} = w ( lambda Ji[a'][r] Ji[b'][c] + mu ( Ji[a'][c] Ji[b'][r] + delta_rc G[a'][b'] ) ), a' on the row function.
-    // The sweeps put the FIRST tensor index on the owner, hence the transpose when storing.
-    const int r = A.brow, cc = A.bcol;
-    for (int a = 0; a < DIM; ++a) for (int b = 0; b < DIM; ++b) {
-        const double E = A.lambda * Ji[b][r] * Ji[a][cc] + A.mu * (Ji[b][cc] * Ji[a][r] + (r == cc ? G[b][a] : 0.0));
-        A.D[(a * DIM + b) * A.dstride + id] = weight * E;
-    }
+    geo_finish<DIM>(A, id, ql, x, J);
 }
 
 // ------------------------------------------------------------------------------------
@@ -577,7 +700,7 @@ GSB_DEVICE i64 final_prepare(const FinalArgs &F, const FinalCtx &c, const OwnerC
 // along the contiguous dimension of both input and output), blockIdx.y = group of owner
 // slots handled, blockIdx.z = sweep segment.
 struct SweepArgs {
-    const int *first, *nexit; const double2 *tab; int q, p;     // swept direction tables
+    const int *first, *nexit; const double2 *tab; const double2 *tabl; int q, p;     // swept direction tables (slot / local order)
     const int *seg;                                            // [nseg][4] e_begin,e_end,x_min,x_max
     const double *in; double *out;
     i64 in_cs, in_es, in_ts, in_os, in_is; int e_in0;          // input strides: comp, element, point, outer, inner
@@ -585,6 +708,7 @@ struct SweepArgs {
     // symmetry of the form (D symmetric): the first sweep may emit only delta >= 0 (half_out, delta index offset
     // d_off instead of p) and the second sweep then writes every value to its mirrored slot as well (mirror)
     int half_out, d_off, mirror; i64 out_dshift, out_nprev;
+    int pf_dist;                 // window kernel: spans of L2 prefetch distance (0 = none)
     i64 ncol; i64 ninner;
     // tensor-map TMA variant: which box coordinate carries the tile start, the span, the outer index
     int tm_rank, tm_dim_inner, tm_dim_e, tm_e_mul, tm_dim_outer;
@@ -743,6 +867,254 @@ GSB_GLOBAL void k_sweep(const SweepArgs A)
         }
         core.exits(A, fc, obase, A.nexit[e], f0, grp, x_min, x_max);
     }
+}
+
+// ------------------------------------------------------------------------------------
+// Window variant of the sweep (default).  A thread owns one column of the non-swept index space AND one
+// group of output components (OMASK), and keeps the partial sums of ALL (p+1)^2 function pairs alive on
+// the current knot span in WINDOW order: acc[a][b] belongs to the pair (f0+a, f0+b), f0 = first function
+// of the span.  When f0 leaves the window its 2p+1 pairs are complete, are written once, and the window
+// shifts by one (register renaming after unrolling, no slot arithmetic, no cross-thread sharing, no
+// barriers).  The inputs of span e+1 are requested while span e is being integrated (register double
+// buffer) and lines further ahead are pulled into L2 with prefetch hints, so the HBM latency hides behind
+// the FP64 work without a shared-memory ring.  Knot multiplicities > 1 simply exit several functions.
+#ifndef GSB200_EMULATE
+#define GSB_GRID_CONSTANT __grid_constant__
+#define GSB_NOINLINE __device__ __noinline__
+GSB_DEVICE void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#else
+#define GSB_GRID_CONSTANT
+#define GSB_NOINLINE static
+static inline void prefetch_l2(const void *) {}
+#endif
+
+// boundary-adjacent, coupled and eliminated entries of the final scatter: out of line, the hot loop stays small
+GSB_NOINLINE void final_slow(const FinalArgs &F, const FinalCtx &c, int fun, i64 rec, int dL, double val)
+{
+    OwnerCache oc; oc.fun = fun; oc.rec = rec;
+    const i64 pos = final_prepare(F, c, oc, dL, val);
+    if (pos >= 0) F.values[pos] = val;
+}
+
+template <class T, int NG> GSB_CX unsigned group_mask(int gi)
+{
+    unsigned m = 0;
+    for (int i = gi * NG; i < (gi + 1) * NG && i < T::NOUT; ++i) m |= 1u << T::order(i);
+    return m;
+}
+GSB_CX int mask_rank(unsigned m, int o) { int r = 0; for (int i = 0; i < o; ++i) if ((m >> i) & 1u) ++r; return r; }
+GSB_CX int mask_count(unsigned m) { int r = 0; for (int i = 0; i < 32; ++i) if ((m >> i) & 1u) ++r; return r; }
+
+template <class T> GSB_CX int used_count(unsigned m) { int n = 0; for (int c = 0; c < T::NIN; ++c) if (T::uses_c(m, c)) ++n; return n; }
+template <class T> GSB_CX int used_rank(unsigned m, int cc) { int n = 0; for (int c = 0; c < cc; ++c) if (T::uses_c(m, c)) ++n; return n; }
+#ifndef GSB200_EMULATE
+GSB_DEVICE void cp_async8(double *dst_smem, const double *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+GSB_DEVICE void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> GSB_DEVICE void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#else
+static inline void cp_async8(double *dst, const double *src) { *dst = *src; }
+static inline void cp_async_commit() {}
+template <int N> static inline void cp_async_wait() {}
+#endif
+// shared memory per CTA of 128 threads and resident CTAs per SM the window kernel is built for
+template <int P1, class T, unsigned OMASK, int NS> GSB_CX int window_smem() { return NS * P1 * used_count<T>(OMASK) * 128 * 8; }
+template <int P1, class T, unsigned OMASK, int NS> GSB_CX int window_minb() { if (NS == 0) return 3; int n = 220 * 1024 / window_smem<P1, T, OMASK, NS>(); return n > 4 ? 4 : (n < 1 ? 1 : n); }
+
+template <int P1, class T, unsigned OMASK, bool FINAL, int NS>
+GSB_GLOBAL void
+#ifndef GSB200_EMULATE
+__launch_bounds__(128, (window_minb<P1, T, OMASK, NS>()))
+#endif
+k_sweepw(const GSB_GRID_CONSTANT SweepArgs A)
+{
+    constexpr int NIN = T::NIN, NT = T::NT, NOUT = T::NOUT, NG = mask_count(OMASK), NQ = P1;
+    const i64 col = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= A.ncol) return;
+    const int sg = blockIdx.z;
+    const int e_begin = A.seg[4 * sg + 0], e_end = A.seg[4 * sg + 1], x_min = A.seg[4 * sg + 2], x_max = A.seg[4 * sg + 3];
+    const i64 outer = col / A.ninner, inner = col - outer * A.ninner;
+    const double *inp = A.in + outer * A.in_os + inner * A.in_is - (i64)A.e_in0 * A.in_es;
+    FinalCtx fc;
+    i64 obase = 0, unused_mirror = -1;
+    i64 fin_c0 = 0, fin_ww = 0; int fin_pl = 0;
+    if (FINAL) {
+        if (!final_init(A.fin, outer, inner, fc)) return;
+        const int W0 = 2 * A.fin.p[0] + 1;
+        if (A.fin.dim == 2) { fin_ww = W0; fin_c0 = fc.bit0; fin_pl = A.fin.p[1]; }
+        else { fin_ww = (i64)(2 * A.fin.p[1] + 1) * W0; fin_c0 = (i64)fc.r_low * W0 + fc.bit0; fin_pl = A.fin.p[2]; }
+    } else obase = sweep_obase(A, outer, inner, &unused_mirror);
+
+    double acc[P1][P1][NG];
+#pragma unroll
+    for (int a = 0; a < P1; ++a)
+#pragma unroll
+        for (int b = 0; b < P1; ++b)
+#pragma unroll
+            for (int g = 0; g < NG; ++g) acc[a][b][g] = 0.0;
+    int f0 = A.first[e_begin];
+    i64 rec[P1];      // FINAL: packed (colptr << 2 | flag) of the window's functions as owners, 0 = not ours
+#pragma unroll
+    for (int k = 0; k < P1; ++k) {
+        rec[k] = 0;
+        if (FINAL) { const int fn = f0 + k; if (fn >= x_min && fn < x_max) rec[k] = A.fin.ownrec[A.fin.bcol * A.fin.nb + (i64)fn * fc.nlow + fc.li_low]; }
+    }
+    // thread-constant output strides of the two families of completed pairs
+    const i64 st_b = A.out_ds, st_a = A.out_fs - A.out_ds, base_d = (i64)A.d_off * A.out_ds + obase;
+
+    // NS >= 2: thread-private ring in shared memory filled by cp.async (LDGSTS): [stage][row = (t, used component)][tid];
+    // NS == 0: register double buffer (the loads of span e+1 are in flight while span e is integrated)
+    constexpr int NINg = used_count<T>(OMASK), NR = NQ * NINg, NSR = NS > 0 ? NS : 1;
+#ifndef GSB200_EMULATE
+    extern __shared__ __align__(16) double ring_smem[];
+    double *ring = ring_smem + threadIdx.x;
+#define GSB_RING(s_, r_) ring[((s_) * NR + (r_)) * 128]
+#else
+    double ring[NSR * NR];
+#define GSB_RING(s_, r_) ring[(s_) * NR + (r_)]
+#endif
+    double vc[NS == 0 ? NR : 1], vn[NS == 0 ? NR : 1];
+    auto issue = [&](int e, int st) {
+        const double *pe = inp + (i64)e * A.in_es;
+#pragma unroll
+        for (int t = 0; t < NQ; ++t)
+            static_for<0, NIN>([&](auto cc) {
+                constexpr int c = decltype(cc)::value;
+                if constexpr (T::uses_c(OMASK, c)) {
+                    constexpr int r = used_rank<T>(OMASK, c);
+                    if constexpr (NS == 0) vn[t * NINg + r] = ld_stream(pe + c * A.in_cs + t * A.in_ts);
+                    else cp_async8(&GSB_RING(st, t * NINg + r), pe + c * A.in_cs + t * A.in_ts);
+                }
+            });
+    };
+    if constexpr (NS == 0) {
+        issue(e_begin, 0);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) vc[r] = vn[r];
+    } else {
+#pragma unroll
+        for (int k = 0; k < NS - 1; ++k) { if (e_begin + k < e_end) issue(e_begin + k, k); cp_async_commit(); }
+    }
+    int stg = 0;
+    const int pf = A.pf_dist;
+    for (int e = e_begin; e < e_end; ++e) {
+        const int nx = A.nexit[e];
+        if constexpr (NS == 0) { if (e + 1 < e_end) issue(e + 1, 0); }
+        else {
+            const int sn = stg == 0 ? NS - 1 : stg - 1;
+            if (e + NS - 1 < e_end) issue(e + NS - 1, sn);
+            cp_async_commit();
+            cp_async_wait<(NS > 0 ? NS - 1 : 0)>();
+        }
+        if (pf > 0 && e + pf < e_end) {
+            const double *pe = inp + (i64)(e + pf) * A.in_es;
+#pragma unroll
+            for (int t = 0; t < NQ; ++t)
+                static_for<0, NIN>([&](auto cc) {
+                    constexpr int c = decltype(cc)::value;
+                    if constexpr (T::uses_c(OMASK, c)) prefetch_l2(pe + c * A.in_cs + t * A.in_ts);
+                });
+        }
+        const double2 *tb = A.tabl + (i64)e * NQ * P1;
+#pragma unroll
+        for (int t = 0; t < NQ; ++t) {
+            double2 bw[P1];
+#pragma unroll
+            for (int k = 0; k < P1; ++k) bw[k] = ld_keep2(tb + t * P1 + k);
+            double v[NIN];
+            static_for<0, NIN>([&](auto cc) {
+                constexpr int c = decltype(cc)::value;
+                if constexpr (T::uses_c(OMASK, c)) {
+                    if constexpr (NS == 0) v[c] = vc[t * NINg + used_rank<T>(OMASK, c)];
+                    else v[c] = GSB_RING(stg, t * NINg + used_rank<T>(OMASK, c));
+                }
+            });
+#pragma unroll
+            for (int a = 0; a < P1; ++a) {
+                double z[NOUT][2];
+                static_for<0, NT>([&](auto kc) {
+                    constexpr int k = decltype(kc)::value;
+                    if constexpr ((OMASK >> T::o(k)) & 1u) {
+                        const double bo = T::a(k) ? bw[a].y : bw[a].x;
+                        if constexpr (T::first(k)) z[T::o(k)][T::b(k)] = bo * v[T::c(k)];
+                        else z[T::o(k)][T::b(k)] = fma(bo, v[T::c(k)], z[T::o(k)][T::b(k)]);
+                    }
+                });
+#pragma unroll
+                for (int b = 0; b < P1; ++b)
+                    static_for<0, NOUT>([&](auto oc_) {
+                        constexpr int o = decltype(oc_)::value;
+                        if constexpr ((OMASK >> o) & 1u) {
+                            constexpr int g = mask_rank(OMASK, o);
+                            if constexpr (T::has(o, 0)) acc[a][b][g] = fma(bw[b].x, z[o][0], acc[a][b][g]);
+                            if constexpr (T::has(o, 1)) acc[a][b][g] = fma(bw[b].y, z[o][1], acc[a][b][g]);
+                        }
+                    });
+            }
+        }
+        // exits: f0 leaves the window, its pairs are complete
+        for (int x = 0; x < nx; ++x) {
+            if (FINAL) {
+                if (rec[0]) {          // owner f0, partners f0+b
+#pragma unroll
+                    for (int b = 0; b < P1; ++b) {
+                        if (b + x >= P1) break;        // x-th exit of one span: f0+b entered later, the pair never co-occurs
+                        const int flag = (int)(rec[0] & 3);
+                        if (flag == 3) st_stream(A.fin.values + (rec[0] >> 2) + (i64)(b + fin_pl) * fin_ww + fin_c0, acc[0][b][0]);
+                        else final_slow(A.fin, fc, f0, rec[0], b, acc[0][b][0]);
+                    }
+                }
+#pragma unroll
+                for (int a = 1; a < P1; ++a) {   // owner f0+a, partner f0
+                    if (rec[a] && a + x < P1) {
+                        const int flag = (int)(rec[a] & 3);
+                        if (flag == 3) st_stream(A.fin.values + (rec[a] >> 2) + (i64)(fin_pl - a) * fin_ww + fin_c0, acc[a][0][0]);
+                        else final_slow(A.fin, fc, f0 + a, rec[a], -a, acc[a][0][0]);
+                    }
+                }
+            } else {
+                const i64 o0 = (i64)f0 * A.out_fs + base_d;
+                if (f0 >= x_min && f0 < x_max) {
+#pragma unroll
+                    for (int b = 0; b < P1; ++b)
+                        if (b + x < P1)
+                            static_for<0, NOUT>([&](auto oc_) {
+                                constexpr int o = decltype(oc_)::value;
+                                if constexpr ((OMASK >> o) & 1u) st_stream(A.out + o * A.out_cs + o0 + b * st_b, acc[0][b][mask_rank(OMASK, o)]);
+                            });
+                }
+#pragma unroll
+                for (int a = 1; a < P1; ++a) {
+                    if (f0 + a >= x_min && f0 + a < x_max && a + x < P1)
+                        static_for<0, NOUT>([&](auto oc_) {
+                            constexpr int o = decltype(oc_)::value;
+                            if constexpr ((OMASK >> o) & 1u) st_stream(A.out + o * A.out_cs + o0 + a * st_a, acc[a][0][mask_rank(OMASK, o)]);
+                        });
+                }
+            }
+            // shift the window by one function
+#pragma unroll
+            for (int a = 0; a < P1; ++a)
+#pragma unroll
+                for (int b = 0; b < P1; ++b)
+#pragma unroll
+                    for (int g = 0; g < NG; ++g) acc[a][b][g] = (a + 1 < P1 && b + 1 < P1) ? acc[(a + 1) % P1][(b + 1) % P1][g] : 0.0;
+            ++f0;
+            if (FINAL) {
+#pragma unroll
+                for (int k = 0; k + 1 < P1; ++k) rec[k] = rec[k + 1];
+                const int fn = f0 + P1 - 1;
+                rec[P1 - 1] = (fn >= x_min && fn < x_max) ? A.fin.ownrec[A.fin.bcol * A.fin.nb + (i64)fn * fc.nlow + fc.li_low] : 0;
+            }
+        }
+        if constexpr (NS == 0) {
+#pragma unroll
+            for (int r = 0; r < NR; ++r) vc[r] = vn[r];
+        } else stg = (stg + 1 == NS) ? 0 : stg + 1;
+    }
+#undef GSB_RING
 }
 
 #ifndef GSB200_EMULATE
