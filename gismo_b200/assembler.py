@@ -82,6 +82,14 @@ class DeviceAssembler:
         check(self.lib.gsb200_download_csc(self._h, outer.ctypes.data_as(_ip), inner.ctypes.data_as(_ip),
                                            values.ctypes.data_as(_dp)))
 
+    def assemble_into(self, outer: np.ndarray, inner: np.ndarray, values: np.ndarray, rhs: Optional[np.ndarray] = None) -> None:
+        """gsb200_assemble_to_host: assemble and deliver into caller buffers (pattern arrays travel while
+        the values are integrated).  What gsPoissonAssemblerB200::assemble() does after sizing the matrix."""
+        if not self._pattern:
+            self.buildPattern()
+        check(self.lib.gsb200_assemble_to_host(self._h, outer.ctypes.data_as(_ip), inner.ctypes.data_as(_ip), values.ctypes.data_as(_dp),
+                                               rhs.ctypes.data_as(_dp) if rhs is not None else None))
+
     def rhs(self) -> np.ndarray:
         r = np.zeros((self.problem.nfree, self.problem.nrhs), np.float64, order="F")
         check(self.lib.gsb200_download_rhs(self._h, r.ctypes.data_as(_dp)))

@@ -199,6 +199,7 @@ def load_library():
     lib.gsb200_timings_get.argtypes = [C.c_void_p, C.POINTER(Timings)]
     lib.gsb200_download_csc.argtypes = [C.c_void_p, _ip, _ip, _dp]
     lib.gsb200_download_rhs.argtypes = [C.c_void_p, _dp]
+    lib.gsb200_assemble_to_host.argtypes = [C.c_void_p, _ip, _ip, _dp, _dp]
     lib.gsb200_assemble_host.argtypes = [C.POINTER(ProblemStruct), C.c_int, C.POINTER(C.c_int64), _ip, _ip, _dp, _dp]
     lib.gsb200_spmv_host.argtypes = [C.c_void_p, _dp, _dp]
     lib.gsb200_cg_host.argtypes = [C.c_void_p, _dp, _dp, C.c_int, C.c_double, C.POINTER(C.c_int), _dp]

@@ -182,13 +182,22 @@ struct gsb200_assembler {
 #ifndef GSB200_EMULATE
     std::vector<cudaEvent_t> ev; std::vector<int> ev_tag;   // tag: 0 geometry, 1..3 sweeps, 4 rhs, 5 total-begin, 6 total-end
 #endif
+    int *d_outer32 = 0;                 // narrowed column pointers for the host-side gsSparseMatrix
+#ifndef GSB200_EMULATE
+    cudaStream_t copy_stream = 0; cudaEvent_t ev_done = 0;
+#endif
     // CG work vectors
     double *cg[6] = {0, 0, 0, 0, 0, 0};
     ~gsb200_assembler() {
+        dev_sync(stream);                  // frees below are not ordered behind this stream's kernels
         for (auto &p : patches) p.release();
         dev_free(d_fixed); dev_free(d_rhs); dev_free(d_values); dev_free(d_colptr); dev_free(d_inner); dev_free(d_npre);
         for (void *b : prog_bufs) dev_free(b);
-        dev_free(ws); dev_free(d_seg); dev_free(d_face);
+        dev_free(ws); dev_free(d_seg); dev_free(d_face); dev_free(d_outer32);
+#ifndef GSB200_EMULATE
+        if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
+        if (ev_done) cudaEventDestroy(ev_done);
+#endif
         for (int k = 0; k < 6; ++k) dev_free(cg[k]);
 #ifndef GSB200_EMULATE
         for (auto e : ev) cudaEventDestroy(e);
@@ -255,6 +264,7 @@ static int build_pattern(gsb200_assembler *a)
     GSB_TRY(dev_memset(d_cursor, 0, sizeof(int) * (size_t)(N + 1), s));
     GSB_TRY(dev_malloc((void **)&d_gneed, (size_t)N + 1));
     GSB_TRY(dev_memset(d_gneed, 0, (size_t)N + 1, s));
+    GSB_TRY(dev_sync(s));
     dev_free(a->d_colptr); dev_free(a->d_inner); dev_free(a->d_values); a->d_colptr = 0; a->d_inner = 0; a->d_values = 0;
     GSB_TRY(dev_malloc((void **)&a->d_colptr, sizeof(i64) * (size_t)(N + 1)));
     for (auto &P : a->patches) {
@@ -439,7 +449,7 @@ static int launch_window_groups(const SweepArgs &A, int nseg, stream_t s)
         constexpr unsigned OMASK = group_mask<T, NG>(GI);
         const dim3 grid((unsigned)((A.ncol + 127) / 128), 1, nseg);
 #ifndef GSB200_EMULATE
-        static const int ns = [] { const char *e = getenv("GSB200_WSTAGES"); return e ? atoi(e) : 3; }();
+        static const int ns = [] { const char *e = getenv("GSB200_WSTAGES"); return e ? atoi(e) : 2; }();
         if (ns == 0) GSB_TRY(window_launch(k_sweepw<P1, T, OMASK, FINAL, 0>, grid, 0, s, A));
         else if (ns >= 4) GSB_TRY(window_launch(k_sweepw<P1, T, OMASK, FINAL, 4>, grid, window_smem<P1, T, OMASK, 4>(), s, A));
         else if (ns == 3) GSB_TRY(window_launch(k_sweepw<P1, T, OMASK, FINAL, 3>, grid, window_smem<P1, T, OMASK, 3>(), s, A));
@@ -598,6 +608,7 @@ static int assemble_pass(gsb200_assembler *a)
             const i64 QLc = (i64)ELc * dL.q;
             const size_t need = (size_t)(perq * QLc) * 8 + 6 * 256;
             if (need > a->ws_size) {
+                GSB_TRY(dev_sync(s));
                 dev_free(a->ws); a->ws = 0; a->ws_size = 0;
                 GSB_TRY(dev_malloc(&a->ws, need)); a->ws_size = need;
             }
@@ -816,7 +827,7 @@ static int assemble_pass(gsb200_assembler *a)
         Lg.bfirst = dd.bfirst[upper]; Lg.nb1 = dd.p + 1;
         F.coefs = P.d_coefs; F.weights = P.d_weights; F.ngeo_total = P.ngeo_total;
         F.ndata = ns.ndata; for (int c = 0; c < ns.ndata; ++c) F.prog[c] = ns.prog[c];
-        if ((size_t)npt > a->face_cap) { dev_free(a->d_face); a->d_face = 0; GSB_TRY(dev_malloc((void **)&a->d_face, sizeof(double) * (size_t)npt)); a->face_cap = (size_t)npt; }
+        if ((size_t)npt > a->face_cap) { GSB_TRY(dev_sync(s)); dev_free(a->d_face); a->d_face = 0; GSB_TRY(dev_malloc((void **)&a->d_face, sizeof(double) * (size_t)npt)); a->face_cap = (size_t)npt; }
         F.Fb = a->d_face; Lg.Fb = a->d_face; Lg.dofmap = P.d_dofmap; Lg.rhs = a->d_rhs; Lg.nfree = N;
         if (dim == 2) { GSB_LAUNCH(k_face_geometry<2>, dim3((unsigned)((npt + 127) / 128)), dim3(128), s, F); GSB_LAUNCH(k_face_load<2>, dim3((unsigned)((nfn + 127) / 128)), dim3(128), s, Lg); }
         else { GSB_LAUNCH(k_face_geometry<3>, dim3((unsigned)((npt + 127) / 128)), dim3(128), s, F); GSB_LAUNCH(k_face_load<3>, dim3((unsigned)((nfn + 127) / 128)), dim3(128), s, Lg); }
@@ -1068,6 +1079,38 @@ int gsb200_download_rhs(gsb200_assembler *a, double *rhs)
     return dev_d2h(rhs, a->d_rhs, sizeof(double) * (size_t)a->nfree * a->nrhs, a->stream);
 }
 
+int gsb200_assemble_to_host(gsb200_assembler *a, int32_t *outer, int32_t *inner, double *values, double *rhs)
+{
+    if (!a || !outer || !inner || !values) { set_error("assemble_to_host: null argument"); return GSB200_EINVAL; }
+    if (!a->pattern_built) { set_error("gsb200_assemble_to_host called before gsb200_build_pattern"); return GSB200_ESTATE; }
+    if (a->nnz > 2147483647LL) { set_error("nnz = %lld exceeds the 32-bit index_t of gsSparseMatrix; use the device view", (long long)a->nnz); return GSB200_ERANGE; }
+    GSB_TRY(select_device(a->device));
+#ifndef GSB200_EMULATE
+    const int N = a->nfree;
+    if (!a->copy_stream) GSB_TRY(dev_check(cudaStreamCreateWithFlags(&a->copy_stream, cudaStreamNonBlocking), "copy stream"));
+    if (!a->ev_done) GSB_TRY(dev_check(cudaEventCreateWithFlags(&a->ev_done, cudaEventDisableTiming), "event"));
+    if (!a->d_outer32) GSB_TRY(dev_malloc((void **)&a->d_outer32, sizeof(int) * (size_t)(N + 1)));
+    cudaStream_t cs = a->copy_stream;
+    // pattern arrays are final since gsb200_build_pattern returned: ship them while the values are integrated
+    k_narrow_outer<<<(N + 1 + 255) / 256, 256, 0, cs>>>(N + 1, a->d_colptr, a->d_outer32); note_launch();
+    GSB_TRY(dev_check(cudaMemcpyAsync(outer, a->d_outer32, sizeof(int) * (size_t)(N + 1), cudaMemcpyDeviceToHost, cs), "D2H outer"));
+    GSB_TRY(dev_check(cudaMemcpyAsync(inner, a->d_inner, sizeof(int) * (size_t)a->nnz, cudaMemcpyDeviceToHost, cs), "D2H inner"));
+    GSB_TRY(assemble(a));
+    GSB_TRY(dev_check(cudaEventRecord(a->ev_done, a->stream), "event record"));
+    GSB_TRY(dev_check(cudaStreamWaitEvent(cs, a->ev_done, 0), "stream wait"));
+    GSB_TRY(dev_check(cudaMemcpyAsync(values, a->d_values, sizeof(double) * (size_t)a->nnz, cudaMemcpyDeviceToHost, cs), "D2H values"));
+    if (rhs) GSB_TRY(dev_check(cudaMemcpyAsync(rhs, a->d_rhs, sizeof(double) * (size_t)N * a->nrhs, cudaMemcpyDeviceToHost, cs), "D2H rhs"));
+    GSB_TRY(dev_check(cudaStreamSynchronize(cs), "copy stream sync"));
+    GSB_TRY(dev_sync(a->stream));
+    finish_timings(a);
+    return GSB200_OK;
+#else
+    GSB_TRY(assemble(a));
+    GSB_TRY(gsb200_download_csc(a, outer, inner, values));
+    return rhs ? gsb200_download_rhs(a, rhs) : GSB200_OK;
+#endif
+}
+
 int gsb200_assemble_host(const gsb200_problem *pb, int device, int64_t *nnz, int32_t *outer, int32_t *inner, double *values, double *rhs)
 {
     static const gsb200_problem *pending_pb = 0; static gsb200_assembler *pending = 0;
@@ -1077,15 +1120,12 @@ int gsb200_assemble_host(const gsb200_problem *pb, int device, int64_t *nnz, int
     else {
         if (pending) { gsb200_destroy(pending); pending = 0; pending_pb = 0; }
         GSB_TRY(gsb200_create(pb, device, &a));
-        int rc = gsb200_build_pattern(a);
-        if (!rc) rc = gsb200_assemble(a);
-        if (!rc) rc = gsb200_synchronize(a);
+        const int rc = gsb200_build_pattern(a);
         if (rc) { gsb200_destroy(a); return rc; }
     }
     *nnz = a->nnz;
-    if (!outer || !inner || !values) { pending = a; pending_pb = pb; return GSB200_OK; }   // size query: keep the result
-    int rc = gsb200_download_csc(a, outer, inner, values);
-    if (!rc && rhs) rc = gsb200_download_rhs(a, rhs);
+    if (!outer || !inner || !values) { pending = a; pending_pb = pb; return GSB200_OK; }   // size query: keep the pattern
+    const int rc = gsb200_assemble_to_host(a, outer, inner, values, rhs);
     gsb200_destroy(a);
     return rc;
 }

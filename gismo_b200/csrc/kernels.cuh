@@ -912,15 +912,21 @@ GSB_DEVICE void cp_async8(double *dst_smem, const double *src)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
 }
+GSB_DEVICE void cp_async16(double2 *dst_smem, const double2 *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+GSB_DEVICE void warp_sync() { __syncwarp(); }
 GSB_DEVICE void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> GSB_DEVICE void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 #else
 static inline void cp_async8(double *dst, const double *src) { *dst = *src; }
+static inline void warp_sync() {}
 static inline void cp_async_commit() {}
 template <int N> static inline void cp_async_wait() {}
 #endif
 // shared memory per CTA of 128 threads and resident CTAs per SM the window kernel is built for
-template <int P1, class T, unsigned OMASK, int NS> GSB_CX int window_smem() { return NS * P1 * used_count<T>(OMASK) * 128 * 8; }
+template <int P1, class T, unsigned OMASK, int NS> GSB_CX int window_smem() { return NS * P1 * used_count<T>(OMASK) * 128 * 8 + NS * 4 * P1 * P1 * 16; }
 template <int P1, class T, unsigned OMASK, int NS> GSB_CX int window_minb() { if (NS == 0) return 3; int n = 220 * 1024 / window_smem<P1, T, OMASK, NS>(); return n > 4 ? 4 : (n < 1 ? 1 : n); }
 
 template <int P1, class T, unsigned OMASK, bool FINAL, int NS>
@@ -931,21 +937,25 @@ __launch_bounds__(128, (window_minb<P1, T, OMASK, NS>()))
 k_sweepw(const GSB_GRID_CONSTANT SweepArgs A)
 {
     constexpr int NIN = T::NIN, NT = T::NT, NOUT = T::NOUT, NG = mask_count(OMASK), NQ = P1;
-    const i64 col = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (col >= A.ncol) return;
+    // every thread of a warp stays in the loop (the warp shares the staged basis table); threads without a column
+    // work on a clamped one and own nothing
+    const i64 col_raw = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    bool live = col_raw < A.ncol;
+    const i64 col = live ? col_raw : A.ncol - 1;
     const int sg = blockIdx.z;
-    const int e_begin = A.seg[4 * sg + 0], e_end = A.seg[4 * sg + 1], x_min = A.seg[4 * sg + 2], x_max = A.seg[4 * sg + 3];
+    const int e_begin = A.seg[4 * sg + 0], e_end = A.seg[4 * sg + 1];
     const i64 outer = col / A.ninner, inner = col - outer * A.ninner;
     const double *inp = A.in + outer * A.in_os + inner * A.in_is - (i64)A.e_in0 * A.in_es;
     FinalCtx fc;
     i64 obase = 0, unused_mirror = -1;
     i64 fin_c0 = 0, fin_ww = 0; int fin_pl = 0;
     if (FINAL) {
-        if (!final_init(A.fin, outer, inner, fc)) return;
+        live = final_init(A.fin, outer, inner, fc) && live;
         const int W0 = 2 * A.fin.p[0] + 1;
         if (A.fin.dim == 2) { fin_ww = W0; fin_c0 = fc.bit0; fin_pl = A.fin.p[1]; }
         else { fin_ww = (i64)(2 * A.fin.p[1] + 1) * W0; fin_c0 = (i64)fc.r_low * W0 + fc.bit0; fin_pl = A.fin.p[2]; }
     } else obase = sweep_obase(A, outer, inner, &unused_mirror);
+    const int x_min = live ? A.seg[4 * sg + 2] : 0, x_max = live ? A.seg[4 * sg + 3] : 0;    // empty owner range: nothing is written
 
     double acc[P1][P1][NG];
 #pragma unroll
@@ -975,9 +985,21 @@ k_sweepw(const GSB_GRID_CONSTANT SweepArgs A)
     double ring[NSR * NR];
 #define GSB_RING(s_, r_) ring[(s_) * NR + (r_)]
 #endif
+    // the span's basis table (NQ x P1 value/derivative pairs, local order) travels with the stage: one copy per warp
+    constexpr int NTAB = NQ * P1;
+#if !defined(GSB200_EMULATE)
+    constexpr bool STAGE_TAB = NS > 0 && NTAB <= 32;
+    double2 *tabring = reinterpret_cast<double2 *>(ring_smem + (size_t)NSR * NR * 128) + (threadIdx.x >> 5) * NTAB;   // [stage][warp][NTAB]
+    const int lane = threadIdx.x & 31;
+#else
+    constexpr bool STAGE_TAB = false;
+#endif
     double vc[NS == 0 ? NR : 1], vn[NS == 0 ? NR : 1];
     auto issue = [&](int e, int st) {
         const double *pe = inp + (i64)e * A.in_es;
+#if !defined(GSB200_EMULATE)
+        if constexpr (STAGE_TAB) { if (lane < NTAB) cp_async16(tabring + (size_t)st * 4 * NTAB + lane, A.tabl + (i64)e * NTAB + lane); }
+#endif
 #pragma unroll
         for (int t = 0; t < NQ; ++t)
             static_for<0, NIN>([&](auto cc) {
@@ -1004,9 +1026,11 @@ k_sweepw(const GSB_GRID_CONSTANT SweepArgs A)
         if constexpr (NS == 0) { if (e + 1 < e_end) issue(e + 1, 0); }
         else {
             const int sn = stg == 0 ? NS - 1 : stg - 1;
+            if constexpr (STAGE_TAB) warp_sync();      // every lane is done with the stage about to be refilled
             if (e + NS - 1 < e_end) issue(e + NS - 1, sn);
             cp_async_commit();
             cp_async_wait<(NS > 0 ? NS - 1 : 0)>();
+            if constexpr (STAGE_TAB) warp_sync();      // ... and sees the table entries the other lanes copied
         }
         if (pf > 0 && e + pf < e_end) {
             const double *pe = inp + (i64)(e + pf) * A.in_es;
@@ -1018,11 +1042,19 @@ k_sweepw(const GSB_GRID_CONSTANT SweepArgs A)
                 });
         }
         const double2 *tb = A.tabl + (i64)e * NQ * P1;
+#if !defined(GSB200_EMULATE)
+        const double2 *tbs = tabring + (size_t)stg * 4 * NTAB;
+#endif
 #pragma unroll
         for (int t = 0; t < NQ; ++t) {
             double2 bw[P1];
 #pragma unroll
-            for (int k = 0; k < P1; ++k) bw[k] = ld_keep2(tb + t * P1 + k);
+            for (int k = 0; k < P1; ++k) {
+#if !defined(GSB200_EMULATE)
+                if constexpr (STAGE_TAB) bw[k] = tbs[t * P1 + k]; else
+#endif
+                bw[k] = ld_keep2(tb + t * P1 + k);
+            }
             double v[NIN];
             static_for<0, NIN>([&](auto cc) {
                 constexpr int c = decltype(cc)::value;
@@ -1433,6 +1465,13 @@ GSB_GLOBAL void k_pat_compact(int ncols, const i64 *oldptr, const i64 *newptr, c
     if (g >= ncols) return;
     const i64 n = newptr[g + 1] - newptr[g];
     for (i64 k = 0; k < n; ++k) newinner[newptr[g] + k] = oldinner[oldptr[g] + k];
+}
+
+// 64-bit device column pointers -> the 32-bit outerIndexPtr of gsSparseMatrix<T,0,index_t>
+GSB_GLOBAL void k_narrow_outer(int n, const i64 *ptr, int *out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (int)ptr[i];
 }
 
 // single-thread exclusive scan used by the interpreter build; the product build uses cub

@@ -195,6 +195,14 @@ int gsb200_timings_get(const gsb200_assembler *a, gsb200_timings *t);
 int gsb200_download_csc(gsb200_assembler *a, int32_t *outer, int32_t *inner, double *values);
 int gsb200_download_rhs(gsb200_assembler *a, double *rhs);
 
+/* Assemble and deliver in one pipelined step (pattern must be built): the column pointers and row
+   indices travel to the host on a copy stream WHILE the values are being integrated, the values and
+   the right-hand side follow as soon as the last sweep is done.  Buffers as for gsb200_download_*
+   (pinned host memory gives the full PCIe rate).  This is the data path of
+   gsPoissonAssemblerB200::assemble() after m_system.matrix().resizeNonZeros(nnz)
+   (SparseMatrix.h:626,649; valuePtr/innerIndexPtr/outerIndexPtr :150-172). */
+int gsb200_assemble_to_host(gsb200_assembler *a, int32_t *outer, int32_t *inner, double *values, double *rhs);
+
 /* One call, host buffers in, host buffers out: what gsPoissonAssemblerB200::assemble()
    does.  Pass outer/inner/values/rhs = NULL first to query *nnz. */
 int gsb200_assemble_host(const gsb200_problem *problem, int device, int64_t *nnz,
