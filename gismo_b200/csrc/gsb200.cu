@@ -648,7 +648,15 @@ static int assemble_pass(gsb200_assembler *a)
                     if (gg.y > 65535u || gg.z > 65535u) { set_error("more than 65535 quadrature points per direction"); return GSB200_EUNSUPPORTED; }
                     static const bool geo_point = [] { const char *e = getenv("GSB200_GEO"); return e && !strcmp(e, "point"); }();
                     if (!geo_point) {
-                        if (dim == 2) { GSB_LAUNCH(k_geometry_line<2>, gg, dim3(128), s, G); } else { GSB_LAUNCH(k_geometry_line<3>, gg, dim3(128), s, G); }
+                        const int pgl = P.dir[L].pg1;
+                        const bool rat = P.d_weights != 0, hot = a->form == GSB200_FORM_POISSON && G.symD;
+#define GSB_GEOL(D_, PG_, R_, F_) { auto kfn = k_geometry_line<D_, PG_, R_, F_>; GSB_LAUNCH(kfn, gg, dim3(128), s, G); }
+#define GSB_GEOL_D(D_) { if (hot && !rat && pgl == 2) GSB_GEOL(D_, 2, false, 1) else if (hot && !rat && pgl == 3) GSB_GEOL(D_, 3, false, 1) \
+                         else if (hot && !rat && pgl == 4) GSB_GEOL(D_, 4, false, 1) else if (hot && rat && pgl == 3) GSB_GEOL(D_, 3, true, 1) \
+                         else if (rat) GSB_GEOL(D_, 0, true, 0) else GSB_GEOL(D_, 0, false, 0) }
+                        if (dim == 2) GSB_GEOL_D(2) else GSB_GEOL_D(3)
+#undef GSB_GEOL_D
+#undef GSB_GEOL
                     } else
 #define GSB_GEO(D_, P_) { auto kfn = k_geometry<D_, P_>; GSB_LAUNCH(kfn, gg, dim3(128), s, G); }
                     if (dim == 2) { switch (pgu) { case 2: GSB_GEO(2, 2) break; case 3: GSB_GEO(2, 3) break; case 4: GSB_GEO(2, 4) break; default: GSB_GEO(2, 0) } }

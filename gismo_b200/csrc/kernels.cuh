@@ -248,7 +248,7 @@ struct GeoArgs {
 };
 // Common tail of the geometry kernels: inverse/measure of the Jacobian, quadrature weight, coefficient tensor of
 // the form and load density at one point.
-template <int DIM>
+template <int DIM, int FSPEC>      // FSPEC 1: Poisson with the symmetric coefficient tensor only (no run-time form dispatch)
 GSB_DEVICE void geo_finish(const GeoArgs &A, i64 id, const int (&ql)[DIM], const double (&x)[3], const double (&J)[DIM][DIM])
 {
     double Ji[DIM][DIM], det;   // Ji[a][c] = (J^-1)[a][c]
@@ -275,9 +275,9 @@ GSB_DEVICE void geo_finish(const GeoArgs &A, i64 id, const int (&ql)[DIM], const
         wp = (k == 0) ? g : wp * g;
     }
     const double weight = hprod * wp * fabs(det);
-    if (A.F) for (int c = 0; c < A.nf; ++c) A.F[c * A.fstride + id] = weight * program_eval(A.prog[c], x[0], x[1], x[2]);
+    if (A.F) for (int c = 0; c < A.nf; ++c) st_stream(A.F + c * A.fstride + id, weight * program_eval(A.prog[c], x[0], x[1], x[2]));
     if (!A.D) return;
-    if (A.form == GSB200_FORM_MASS) { A.D[id] = weight; return; }
+    if (FSPEC != 1 && A.form == GSB200_FORM_MASS) { A.D[id] = weight; return; }
     double G[DIM][DIM];   // (J^-1 J^-T)_ab
 #pragma unroll
     for (int a = 0; a < DIM; ++a)
@@ -288,21 +288,40 @@ GSB_DEVICE void geo_finish(const GeoArgs &A, i64 id, const int (&ql)[DIM], const
             for (int c = 0; c < DIM; ++c) s += Ji[a][c] * Ji[b][c];
             G[a][b] = s; G[b][a] = s;
         }
+    if (FSPEC == 1 || (A.form == GSB200_FORM_POISSON && A.symD)) {
+        int c = 0;
+#pragma unroll
+        for (int a = 0; a < DIM; ++a)
+#pragma unroll
+            for (int b = a; b < DIM; ++b) st_stream(A.D + (c++) * A.dstride + id, weight * G[a][b]);
+        return;
+    }
     if (A.form == GSB200_FORM_POISSON) {
-        if (A.symD) { int c = 0; for (int a = 0; a < DIM; ++a) for (int b = a; b < DIM; ++b) A.D[(c++) * A.dstride + id] = weight * G[a][b]; }
-        else for (int a = 0; a < DIM; ++a) for (int b = 0; b < DIM; ++b) A.D[(a * DIM + b) * A.dstride + id] = weight * G[a][b];
+#pragma unroll
+        for (int a = 0; a < DIM; ++a)
+#pragma unroll
+            for (int b = 0; b < DIM; ++b) A.D[(a * DIM + b) * A.dstride + id] = weight * G[a][b];
         return;
     }
     // elasticity block (row comp r = brow carried by the partner/test function, col comp c = bcol by the owner):
     // E_{a'b'} = w ( lambda Ji[a'][r] Ji[b'][c] + mu ( Ji[a'][c] Ji[b'][r] + delta_rc G[a'][b'] ) ), a' on the row function.
     // The sweeps put the FIRST tensor index on the owner, hence the transpose when storing.
     const int r = A.brow, cc = A.bcol;
-    for (int a = 0; a < DIM; ++a) for (int b = 0; b < DIM; ++b) {
-        const double E = A.lambda * Ji[b][r] * Ji[a][cc] + A.mu * (Ji[b][cc] * Ji[a][r] + (r == cc ? G[b][a] : 0.0));
-        A.D[(a * DIM + b) * A.dstride + id] = weight * E;
+    double Jr[DIM], Jc[DIM];          // columns r and cc of J^-1, selected without indexing registers dynamically
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) {
+        Jr[k] = Ji[k][0]; Jc[k] = Ji[k][0];
+#pragma unroll
+        for (int m = 1; m < DIM; ++m) { if (r == m) Jr[k] = Ji[k][m]; if (cc == m) Jc[k] = Ji[k][m]; }
     }
+#pragma unroll
+    for (int a = 0; a < DIM; ++a)
+#pragma unroll
+        for (int b = 0; b < DIM; ++b) {
+            const double E = A.lambda * Jr[b] * Jc[a] + A.mu * (Jc[b] * Jr[a] + (r == cc ? G[b][a] : 0.0));
+            A.D[(a * DIM + b) * A.dstride + id] = weight * E;
+        }
 }
-
 
 // Thread = one point of the last direction (fastest in memory), blockIdx.y/z = the other
 // directions.  PG = geometry degree + 1 when equal in all directions (loops unrolled, 1-D values
@@ -380,7 +399,7 @@ GSB_GLOBAL void k_geometry(const GeoArgs A)
     } else {
         for (int c = 0; c < DIM; ++c) { x[c] = xn[c]; for (int a = 0; a < DIM; ++a) J[c][a] = dxn[a][c]; }
     }
-    geo_finish<DIM>(A, id, ql, x, J);
+    geo_finish<DIM, 0>(A, id, ql, x, J);
 }
 
 // K0, line-factorised (default).  All threads of a block share the quadrature indices of the leading
@@ -403,7 +422,9 @@ GSB_GLOBAL void k_geometry(const GeoArgs A)
 #define GSB_COOP_FIRST 0
 #define GSB_COOP_STEP 1
 #endif
-template <int DIM>
+// PGL = (geometry degree + 1) of the last direction (0 = run time), RATIONAL = NURBS weights present,
+// FSPEC = 1 for the Poisson form with symmetric coefficient storage (the hot configuration)
+template <int DIM, int PGL, bool RATIONAL, int FSPEC>
 GSB_GLOBAL void k_geometry_line(const GeoArgs A)
 {
     constexpr int L = DIM - 1, NFM = DIM + 1;
@@ -415,12 +436,12 @@ GSB_GLOBAL void k_geometry_line(const GeoArgs A)
     ql[L] = (active ? qlast : A.qn[L] - 1) + A.qoff[L];
     if (DIM == 3) { ql[1] = blockIdx.y + A.qoff[1]; ql[0] = blockIdx.z + A.qoff[0]; id = ((i64)blockIdx.z * A.qn[1] + blockIdx.y) * A.qn[L] + qlast; }
     else { ql[0] = blockIdx.y + A.qoff[0]; id = (i64)blockIdx.y * A.qn[L] + qlast; }
-    const bool rational = A.weights != 0;
-    const int nf = rational ? DIM + 1 : DIM;
+    constexpr bool rational = RATIONAL;
+    constexpr int nf = rational ? DIM + 1 : DIM;
     // range of last-direction control points touched by the block (gfirst is non-decreasing along the points)
     const int qb_first = q0blk + A.qoff[L];
     const int qb_last = (q0blk + (int)blockDim.x - 1 < A.qn[L] ? q0blk + (int)blockDim.x - 1 : A.qn[L] - 1) + A.qoff[L];
-    const int pgL = A.pg1[L];
+    const int pgL = PGL ? PGL : A.pg1[L];
     const int lo = A.gfirst[L][qb_first], hi = A.gfirst[L][qb_last] + pgL;
     const int gfL = A.gfirst[L][ql[L]];
     int gf[DIM];
@@ -452,7 +473,9 @@ GSB_GLOBAL void k_geometry_line(const GeoArgs A)
             E[aa][f][0] = s0; E[aa][f][1] = s1; if (DIM == 3) E[aa][f][DIM - 1] = s2;
         }
         GSB_SYNCTHREADS();
-        for (int k = 0; k < pgL; ++k) {
+#pragma unroll
+        for (int k = 0; k < (PGL ? PGL : GSB_MAXP + 1); ++k) {
+            if (k >= pgL) break;
             const int aa = gfL + k - abase;
             if (aa < 0 || aa >= cnt) continue;
             const double2 bL = A.gtab[L][(i64)ql[L] * pgL + k];
@@ -482,7 +505,7 @@ GSB_GLOBAL void k_geometry_line(const GeoArgs A)
 #pragma unroll
             for (int a = 0; a < DIM; ++a) J[c][a] = dd[c][a]; }
     }
-    geo_finish<DIM>(A, id, ql, x, J);
+    geo_finish<DIM, FSPEC>(A, id, ql, x, J);
 }
 
 // ------------------------------------------------------------------------------------
@@ -896,6 +919,16 @@ GSB_NOINLINE void final_slow(const FinalArgs &F, const FinalCtx &c, int fun, i64
     if (pos >= 0) F.values[pos] = val;
 }
 
+// canonical column whose stencil is cut by eliminated functions: slot from the per-run (start, mask) word; an
+// eliminated partner goes the slow way (right-hand-side contribution)
+GSB_DEVICE void final_canonical(const FinalArgs &F, const FinalCtx &c, int fun, i64 rec, int dL, int run, double val)
+{
+    const unsigned w = F.st[((i64)fun * c.nlow + c.li_low) * F.nrun + run];
+    const unsigned mask = w >> 16;
+    if ((mask >> c.bit0) & 1u) st_stream(F.values + (rec >> 2) + (int)(w & 0xffffu) + popc(mask & ((1u << c.bit0) - 1u)), val);
+    else if (F.fixed) final_slow(F, c, fun, rec, dL, val);
+}
+
 template <class T, int NG> GSB_CX unsigned group_mask(int gi)
 {
     unsigned m = 0;
@@ -948,12 +981,12 @@ k_sweepw(const GSB_GRID_CONSTANT SweepArgs A)
     const double *inp = A.in + outer * A.in_os + inner * A.in_is - (i64)A.e_in0 * A.in_es;
     FinalCtx fc;
     i64 obase = 0, unused_mirror = -1;
-    i64 fin_c0 = 0, fin_ww = 0; int fin_pl = 0;
+    i64 fin_c0 = 0, fin_ww = 0; int fin_pl = 0, fin_w1 = 1;
     if (FINAL) {
         live = final_init(A.fin, outer, inner, fc) && live;
         const int W0 = 2 * A.fin.p[0] + 1;
-        if (A.fin.dim == 2) { fin_ww = W0; fin_c0 = fc.bit0; fin_pl = A.fin.p[1]; }
-        else { fin_ww = (i64)(2 * A.fin.p[1] + 1) * W0; fin_c0 = (i64)fc.r_low * W0 + fc.bit0; fin_pl = A.fin.p[2]; }
+        if (A.fin.dim == 2) { fin_ww = W0; fin_c0 = fc.bit0; fin_pl = A.fin.p[1]; fin_w1 = 1; }
+        else { fin_ww = (i64)(2 * A.fin.p[1] + 1) * W0; fin_c0 = (i64)fc.r_low * W0 + fc.bit0; fin_pl = A.fin.p[2]; fin_w1 = 2 * A.fin.p[1] + 1; }
     } else obase = sweep_obase(A, outer, inner, &unused_mirror);
     const int x_min = live ? A.seg[4 * sg + 2] : 0, x_max = live ? A.seg[4 * sg + 3] : 0;    // empty owner range: nothing is written
 
@@ -1095,6 +1128,7 @@ k_sweepw(const GSB_GRID_CONSTANT SweepArgs A)
                         if (b + x >= P1) break;        // x-th exit of one span: f0+b entered later, the pair never co-occurs
                         const int flag = (int)(rec[0] & 3);
                         if (flag == 3) st_stream(A.fin.values + (rec[0] >> 2) + (i64)(b + fin_pl) * fin_ww + fin_c0, acc[0][b][0]);
+                        else if (flag == 1) final_canonical(A.fin, fc, f0, rec[0], b, (b + fin_pl) * fin_w1 + fc.r_low, acc[0][b][0]);
                         else final_slow(A.fin, fc, f0, rec[0], b, acc[0][b][0]);
                     }
                 }
@@ -1103,6 +1137,7 @@ k_sweepw(const GSB_GRID_CONSTANT SweepArgs A)
                     if (rec[a] && a + x < P1) {
                         const int flag = (int)(rec[a] & 3);
                         if (flag == 3) st_stream(A.fin.values + (rec[a] >> 2) + (i64)(fin_pl - a) * fin_ww + fin_c0, acc[a][0][0]);
+                        else if (flag == 1) final_canonical(A.fin, fc, f0 + a, rec[a], -a, (fin_pl - a) * fin_w1 + fc.r_low, acc[a][0][0]);
                         else final_slow(A.fin, fc, f0 + a, rec[a], -a, acc[a][0][0]);
                     }
                 }
