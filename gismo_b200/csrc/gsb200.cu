@@ -590,9 +590,13 @@ static int assemble_pass(gsb200_assembler *a)
         // symmetric forms in 3-D: the first sweep keeps only delta0 >= 0, the second one mirrors its output
         const bool half = dim == 3 && kind != KIND_GEN && getenv("GSB200_SYM") && getenv("GSB200_SWEEP");   // experiment, ring kernels only
         static const bool a2_rows_env = [] { const char *e = getenv("GSB200_A2ROWS"); return e && atoi(e) > 0; }();
-        static const bool a1_blk_env = [] { const char *e = getenv("GSB200_A1BLK"); return !e || atoi(e) > 0; }();   // default on
-        const bool a1_blk = a1_blk_env && !half && dim == 3 && !getenv("GSB200_SWEEP");
-        const bool a2_rows = a2_rows_env && !half && dim == 3 && !a1_blk;
+        // layout of A1 (3-D): 1 = blocked by last-direction element (A1[o][i0][q1][e2][d0][t]: the second sweep reads whole runs, but the
+        // first one stores q-point pieces, which only pays when those are whole 32-byte sectors), 2 = A1[o][i0][d0][q1][q2] (coalesced first-
+        // sweep stores, the second sweep gathers q-point pieces), 0 = legacy mapping of the ring kernels.  GSB200_A1BLK overrides.
+        static const int a1_env = [] { const char *e = getenv("GSB200_A1BLK"); return e ? atoi(e) : -1; }();
+        const int a1_mode = (half || dim != 3 || getenv("GSB200_SWEEP")) ? 0 : (a1_env >= 0 ? a1_env : ((dL.q * 8) % 32 == 0 ? 1 : 2));
+        const bool a1_blk = a1_mode == 1, a1_gather = a1_mode == 2;
+        const bool a2_rows = a2_rows_env && a1_mode == 0 && dim == 3 && !half;
         const i64 NI0h = half ? (i64)d0.nfun * (d0.p + 1) : NI0;     // (i0, delta0) pairs stored in A1
         // doubles of workspace per last-direction quadrature point
         i64 perq = ncD * Q0 * Q1 + no1 * NI0h * Q1 + (dim == 3 ? no2 * NI1 * NI0 : 0) + nf * Q0 * Q1 + n0 * Q1 + (dim == 3 ? n1 * n0 : 0);
@@ -718,6 +722,12 @@ static int assemble_pass(gsb200_assembler *a)
                         A.out_os = (i64)W1 * W0 * dL.q; A.out_os2 = dL.q; A.out_bq = dL.q; A.out_bs = NI0 * W1 * dL.q; A.out_is = 1;
                         if (a1_blk) {    // thread = (i0; e2, d0, t): contiguous in A1 and, per element, in A2
                             A.in_os = Q1 * ELc * W0 * dL.q; A.in_is = 1; A.in_ts = ELc * W0 * dL.q; A.in_es = (i64)d1.q * A.in_ts;
+                            A.ncol = n0 * ELc * W0 * dL.q; A.ninner = ELc * W0 * dL.q;
+                            A.out_od = 1; A.out_dshift = 0; A.out_os = W1 * W0 * dL.q; A.out_os2 = 0; A.out_bq = W0 * dL.q; A.out_bs = NI0 * W1 * dL.q; A.out_is = 1;
+                        }
+                        if (a1_gather) { // thread = (i0; e2, d0, t) as above, but A1 keeps whole q2 rows per (i0, d0)
+                            A.in_os = W0 * Q1 * QLc; A.in_is = 1; A.in_ts = QLc; A.in_es = (i64)d1.q * QLc;
+                            A.in_bq2 = W0 * dL.q; A.in_bs2 = dL.q; A.in_bq = dL.q; A.in_bs = Q1 * QLc;
                             A.ncol = n0 * ELc * W0 * dL.q; A.ninner = ELc * W0 * dL.q;
                             A.out_od = 1; A.out_dshift = 0; A.out_os = W1 * W0 * dL.q; A.out_os2 = 0; A.out_bq = W0 * dL.q; A.out_bs = NI0 * W1 * dL.q; A.out_is = 1;
                         }

@@ -732,6 +732,9 @@ struct SweepArgs {
     // d_off instead of p) and the second sweep then writes every value to its mirrored slot as well (mirror)
     int half_out, d_off, mirror; i64 out_dshift, out_nprev;
     int pf_dist;                 // window kernel: spans of L2 prefetch distance (0 = none)
+    // window kernel: optional 3-level decomposition of the inner column index for the INPUT address
+    // (inner = (x, y, z) with z fastest: x * in_bs2 + y * in_bs + z * in_is), in_bq = 0: plain inner * in_is
+    i64 in_bq, in_bs, in_bq2, in_bs2;
     i64 ncol; i64 ninner;
     // tensor-map TMA variant: which box coordinate carries the tile start, the span, the outer index
     int tm_rank, tm_dim_inner, tm_dim_e, tm_e_mul, tm_dim_outer;
@@ -978,7 +981,9 @@ k_sweepw(const GSB_GRID_CONSTANT SweepArgs A)
     const int sg = blockIdx.z;
     const int e_begin = A.seg[4 * sg + 0], e_end = A.seg[4 * sg + 1];
     const i64 outer = col / A.ninner, inner = col - outer * A.ninner;
-    const double *inp = A.in + outer * A.in_os + inner * A.in_is - (i64)A.e_in0 * A.in_es;
+    i64 in_part = inner * A.in_is;
+    if (A.in_bq > 0) { const i64 r = inner % A.in_bq2; in_part = (inner / A.in_bq2) * A.in_bs2 + (r / A.in_bq) * A.in_bs + (r % A.in_bq) * A.in_is; }
+    const double *inp = A.in + outer * A.in_os + in_part - (i64)A.e_in0 * A.in_es;
     FinalCtx fc;
     i64 obase = 0, unused_mirror = -1;
     i64 fin_c0 = 0, fin_ww = 0; int fin_pl = 0, fin_w1 = 1;
