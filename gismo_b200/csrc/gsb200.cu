@@ -495,12 +495,14 @@ static int launch_sweep(int P1, const SweepArgs &A, int nseg, stream_t s, i64 *f
     }
 }
 
-enum { KIND_SYM = 0, KIND_GEN = 1, KIND_MASS = 2 };
+enum { KIND_SYM = 0, KIND_GEN = 1, KIND_MASS = 2, KIND_SYMH = 3 };   // SYMH: symmetric form with half-stored first-sweep output
 // stage: 0 = first of 3-D, 1 = middle of 3-D, 2 = last; 3 = first of 2-D
 static int dispatch_sweep(int kind, int stage, int P1, const SweepArgs &A, int nseg, stream_t s, i64 *fpp, const TmapDesc &td)
 {
     if (kind == KIND_MASS) return stage == 2 ? launch_sweep<TMass, true>(P1, A, nseg, s, fpp, td) : launch_sweep<TMass, false>(P1, A, nseg, s, fpp, td);
     if (stage == 2) return launch_sweep<TLast, true>(P1, A, nseg, s, fpp, td);
+    if (kind == KIND_SYMH && stage == 0) return launch_sweep<T3SymS1H, false>(P1, A, nseg, s, fpp, td);
+    if (kind == KIND_SYMH && stage == 1) return launch_sweep<T3SymS2H, false>(P1, A, nseg, s, fpp, td);
     if (stage == 0) return kind == KIND_SYM ? launch_sweep<T3SymS1, false>(P1, A, nseg, s, fpp, td) : launch_sweep<T3GenS1, false>(P1, A, nseg, s, fpp, td);
     if (stage == 1) return kind == KIND_SYM ? launch_sweep<T3SymS2, false>(P1, A, nseg, s, fpp, td) : launch_sweep<T3GenS2, false>(P1, A, nseg, s, fpp, td);
     return kind == KIND_SYM ? launch_sweep<T2SymS1, false>(P1, A, nseg, s, fpp, td) : launch_sweep<T2GenS1, false>(P1, A, nseg, s, fpp, td);
@@ -509,6 +511,8 @@ static void stage_io(int kind, int stage, int *nin, int *nout)
 {
     if (kind == KIND_MASS) { *nin = 1; *nout = 1; return; }
     if (stage == 2) { *nin = 4; *nout = 1; return; }
+    if (kind == KIND_SYMH && stage == 0) { *nin = 6; *nout = 6; return; }
+    if (kind == KIND_SYMH && stage == 1) { *nin = 6; *nout = 4; return; }
     if (stage == 0) { *nin = kind == KIND_SYM ? 6 : 9; *nout = kind == KIND_SYM ? 8 : 9; return; }
     if (stage == 1) { *nin = kind == KIND_SYM ? 8 : 9; *nout = 4; return; }
     *nin = kind == KIND_SYM ? 3 : 4; *nout = 4;
@@ -596,6 +600,10 @@ static int assemble_pass(gsb200_assembler *a)
         static const int a1_env = [] { const char *e = getenv("GSB200_A1BLK"); return e ? atoi(e) : -1; }();
         const int a1_mode = (half || dim != 3 || getenv("GSB200_SWEEP")) ? 0 : (a1_env >= 0 ? a1_env : ((dL.q * 8) % 32 == 0 ? 1 : 2));
         const bool a1_blk = a1_mode == 1, a1_gather = a1_mode == 2;
+        // experiment (GSB200_SYMH=1): symmetric form + blocked A1: store the symmetric first-sweep components for delta0 >= 0 only, read mirrored
+        static const bool symh_env = [] { const char *e = getenv("GSB200_SYMH"); return e && atoi(e) > 0; }();   // measured slower (profiles/): opt-in
+        const int kind01 = (kind == KIND_SYM && a1_blk && symh_env) ? KIND_SYMH : kind;
+        const double symh_frac = kind01 == KIND_SYMH ? (2.0 * W0 + 4.0 * (d0.p + 1)) / (double)W0 : 0.0;   // stored components per (i0, slot) on average
         const bool a2_rows = a2_rows_env && a1_mode == 0 && dim == 3 && !half;
         const i64 NI0h = half ? (i64)d0.nfun * (d0.p + 1) : NI0;     // (i0, delta0) pairs stored in A1
         // doubles of workspace per last-direction quadrature point
@@ -687,11 +695,11 @@ static int assemble_pass(gsb200_assembler *a)
                     { static const int pf = [] { const char *e = getenv("GSB200_PF"); return e ? atoi(e) : 0; }(); A.pf_dist = pf; }
                     return A;
                 };
-                auto account = [&](int slot, const SweepArgs &A, const std::vector<int> &seg, i64 fpp, int nin, int nout, i64 npairs_out) {
+                auto account = [&](int slot, const SweepArgs &A, const std::vector<int> &seg, i64 fpp, double nin, double nout, i64 npairs_out) {
                     i64 pts = 0;
                     for (size_t k = 0; k < seg.size(); k += 4) pts += (i64)(seg[k + 1] - seg[k]) * A.q;
                     a->tm.sweep_flops[slot] += fpp * A.ncol * pts;
-                    a->tm.sweep_bytes[slot] += 8 * ((i64)nin * A.ncol * pts + (i64)nout * npairs_out * A.ncol);
+                    a->tm.sweep_bytes[slot] += (i64)(8.0 * (nin * (double)A.ncol * (double)pts + nout * (double)npairs_out * (double)A.ncol));
                 };
                 i64 fpp = 0; int nin, nout;
                 if (dim == 3) {
@@ -709,8 +717,9 @@ static int assemble_pass(gsb200_assembler *a)
                         A.seg = a->d_seg + segoff; GSB_TRY(upload_segments(a, seg, &segoff));
                         mark(a, 1);
                         { TmapDesc td; memset(&td, 0, sizeof td); td.valid = true; td.rank = 3; td.dims[0] = (unsigned long long)(Q1 * QLc); td.dims[1] = (unsigned long long)(Q0); td.dims[2] = (unsigned long long)(ncD); td.strides[0] = 8ull * (unsigned long long)(Q1 * QLc); td.strides[1] = 8ull * (unsigned long long)(npts); td.box_kind[0] = 1; td.box_kind[1] = 2; td.box_kind[2] = 3; A.tm_rank = 3; A.tm_dim_inner = 0; A.tm_dim_e = 1; A.tm_e_mul = d0.q; A.tm_dim_outer = -1;
-                        GSB_TRY(dispatch_sweep(kind, 0, d0.p + 1, A, (int)seg.size() / 4, s, &fpp, td)); }
-                        stage_io(kind, 0, &nin, &nout); account(0, A, seg, fpp, nin, nout, NI0h);
+                        GSB_TRY(dispatch_sweep(kind01, 0, d0.p + 1, A, (int)seg.size() / 4, s, &fpp, td)); }
+                        stage_io(kind01, 0, &nin, &nout);
+                        if (kind01 == KIND_SYMH) account(0, A, seg, fpp, nin, symh_frac, NI0h); else account(0, A, seg, fpp, nin, nout, NI0h);
                     }
                     {   // S2: direction 1
                         SweepArgs A = base_args(d1);
@@ -740,8 +749,10 @@ static int assemble_pass(gsb200_assembler *a)
                         A.seg = a->d_seg + segoff; GSB_TRY(upload_segments(a, seg, &segoff));
                         mark(a, 2);
                         { TmapDesc td; memset(&td, 0, sizeof td); td.valid = true; td.rank = 4; td.dims[0] = (unsigned long long)(QLc); td.dims[1] = (unsigned long long)(Q1); td.dims[2] = (unsigned long long)(NI0h); td.dims[3] = (unsigned long long)(no1); td.strides[0] = 8ull * (unsigned long long)(QLc); td.strides[1] = 8ull * (unsigned long long)(Q1 * QLc); td.strides[2] = 8ull * (unsigned long long)(NI0h * Q1 * QLc); td.box_kind[0] = 1; td.box_kind[1] = 2; td.box_kind[2] = 0; td.box_kind[3] = 3; A.tm_rank = 4; A.tm_dim_inner = 0; A.tm_dim_e = 1; A.tm_e_mul = d1.q; A.tm_dim_outer = 2;
-                        GSB_TRY(dispatch_sweep(kind, 1, d1.p + 1, A, (int)seg.size() / 4, s, &fpp, td)); }
-                        stage_io(kind, 1, &nin, &nout); account(1, A, seg, fpp, nin, nout, NI1);
+                        if (kind01 == KIND_SYMH) { A.mir_q = dL.q; A.mir_w = (int)W0; A.mir_p = d0.p; A.mir_n = (int)n0; }
+                        GSB_TRY(dispatch_sweep(kind01, 1, d1.p + 1, A, (int)seg.size() / 4, s, &fpp, td)); }
+                        stage_io(kind01, 1, &nin, &nout);
+                        if (kind01 == KIND_SYMH) account(1, A, seg, fpp, symh_frac, nout, NI1); else account(1, A, seg, fpp, nin, nout, NI1);
                     }
                     {   // S3: direction 2, scatter into the CSC arrays
                         SweepArgs A = base_args(dL);
@@ -791,28 +802,48 @@ static int assemble_pass(gsb200_assembler *a)
                         const int comp = a->form == GSB200_FORM_ELASTICITY ? c : 0;   // dof component
                         VSweepArgs V; memset(&V, 0, sizeof V);
                         auto vbase = [&](const Dir1D &d) { V.ffirst = d.d_ffirst; V.flast = d.d_flast; V.first = d.d_first; V.tab = d.d_tab; V.q = d.q; V.p1 = d.p + 1; };
+                        // window kernel when the rule has p+1 points (reads its input once), else one thread per (column, function)
+                        auto vlaunch = [&](const Dir1D &d) -> int {
+                            static const bool vold = getenv("GSB200_VSWEEP_OLD") != 0;
+                            const int P1 = d.p + 1, nx = V.x_hi - V.x_lo;
+                            if (vold || d.q != P1 || P1 < 2 || P1 > 5) {
+                                GSB_LAUNCH(k_vsweep, dim3((unsigned)((V.ncol + 127) / 128), nx), dim3(128), s, V);
+                                return 0;
+                            }
+                            const int nseg = std::min(nseg_for(V.ncol, nx, P1), 65535);
+                            std::vector<int> seg = make_segments(d, V.x_lo, V.x_hi, nseg);
+                            const int *dseg = a->d_seg + segoff; GSB_TRY(upload_segments(a, seg, &segoff));
+                            const dim3 grid((unsigned)((V.ncol + 127) / 128), (unsigned)(seg.size() / 4));
+                            switch (P1) {
+                            case 2: GSB_LAUNCH(k_vsweepw<2>, grid, dim3(128), s, V, d.d_tabl, d.d_nexit, dseg); break;
+                            case 3: GSB_LAUNCH(k_vsweepw<3>, grid, dim3(128), s, V, d.d_tabl, d.d_nexit, dseg); break;
+                            case 4: GSB_LAUNCH(k_vsweepw<4>, grid, dim3(128), s, V, d.d_tabl, d.d_nexit, dseg); break;
+                            default: GSB_LAUNCH(k_vsweepw<5>, grid, dim3(128), s, V, d.d_tabl, d.d_nexit, dseg); break;
+                            }
+                            return 0;
+                        };
                         if (dim == 3) {
                             vbase(d0); V.final_ = 0; V.x_lo = 0; V.x_hi = d0.nfun; V.e_in0 = 0;
                             V.in = F + c * npts; V.in_qs = Q1 * QLc; V.in_os = 0; V.in_is = 1; V.ncol = Q1 * QLc; V.ninner = V.ncol;
                             V.out = V1; V.out_fs = Q1 * QLc; V.out_os = 0; V.out_is = 1;
-                            GSB_LAUNCH(k_vsweep, dim3((unsigned)((V.ncol + 127) / 128), d0.nfun), dim3(128), s, V);
+                            GSB_TRY(vlaunch(d0));
                             vbase(d1); V.x_lo = 0; V.x_hi = d1.nfun;
                             V.in = V1; V.in_qs = QLc; V.in_os = Q1 * QLc; V.in_is = 1; V.ncol = n0 * QLc; V.ninner = QLc;
                             V.out = V2; V.out_fs = n0 * QLc; V.out_os = QLc; V.out_is = 1;
-                            GSB_LAUNCH(k_vsweep, dim3((unsigned)((V.ncol + 127) / 128), d1.nfun), dim3(128), s, V);
+                            GSB_TRY(vlaunch(d1));
                             vbase(dL); V.x_lo = x_lo; V.x_hi = x_hi; V.e_in0 = eL0; V.final_ = 1;
                             V.in = V2; V.in_qs = 1; V.in_os = n0 * QLc; V.in_is = QLc; V.ncol = n1 * n0; V.ninner = n0;
                             V.n0 = (int)n0; V.n1 = (int)n1; V.dimlow = 2; V.dofmap = P.d_dofmap + (i64)comp * P.nb; V.rhs = a->d_rhs + (i64)rcol * N; V.nfree = N;
-                            GSB_LAUNCH(k_vsweep, dim3((unsigned)((V.ncol + 127) / 128), x_hi - x_lo), dim3(128), s, V);
+                            GSB_TRY(vlaunch(dL));
                         } else {
                             vbase(d0); V.final_ = 0; V.x_lo = 0; V.x_hi = d0.nfun; V.e_in0 = 0;
                             V.in = F + c * npts; V.in_qs = QLc; V.in_os = 0; V.in_is = 1; V.ncol = QLc; V.ninner = QLc;
                             V.out = V1; V.out_fs = QLc; V.out_os = 0; V.out_is = 1;
-                            GSB_LAUNCH(k_vsweep, dim3((unsigned)((V.ncol + 127) / 128), d0.nfun), dim3(128), s, V);
+                            GSB_TRY(vlaunch(d0));
                             vbase(dL); V.x_lo = x_lo; V.x_hi = x_hi; V.e_in0 = eL0; V.final_ = 1;
                             V.in = V1; V.in_qs = 1; V.in_os = 0; V.in_is = QLc; V.ncol = n0; V.ninner = n0;
                             V.n0 = (int)n0; V.n1 = 1; V.dimlow = 1; V.dofmap = P.d_dofmap + (i64)comp * P.nb; V.rhs = a->d_rhs + (i64)rcol * N; V.nfree = N;
-                            GSB_LAUNCH(k_vsweep, dim3((unsigned)((V.ncol + 127) / 128), x_hi - x_lo), dim3(128), s, V);
+                            GSB_TRY(vlaunch(dL));
                         }
                     }
                 }

@@ -62,6 +62,12 @@ struct TermOps {
     static GSB_CX int omirror(int oo) { return oo; }
     // output order in which the window kernel forms its groups: consecutive outputs of this order share inputs
     static GSB_CX int order(int i) { return i; }
+    // symmetry of the form (window kernels): an output that is symmetric under the exchange of owner and partner is stored for
+    // delta >= 0 only; a (virtual) input c is backed by the stored component in_src(c) and read directly (mode 1), at the mirrored
+    // pair (i + delta, -delta) (mode 2), or mirrored only where delta < 0 (mode 0, symmetric component)
+    static GSB_CX bool out_sym(int) { return false; }
+    static GSB_CX int in_src(int cc) { return cc; }
+    static GSB_CX int in_mode(int) { return 1; }
     static GSB_CX bool uses_c(unsigned omask, int cc) { for (int j = 0; j < D::NT; ++j) if (((omask >> o(j)) & 1u) && c(j) == cc) return true; return false; }
 };
 // symmetric coefficient tensor, 3-D (Poisson): D = {00,01,02,11,12,22}
@@ -76,6 +82,18 @@ struct T3SymS2 : TermOps<T3SymS2> { enum { NIN = 8, NOUT = 4, NT = 9 };
                                                     GSB_PK(3,7,0,0)}; return v[k]; }
     static GSB_CX int omirror(int oo) { return oo == 1 ? 2 : (oo == 2 ? 1 : oo); }      // g = 2*alpha2 + beta2: swap the flags
     static GSB_CX int order(int i) { const int v[4] = {0, 3, 1, 2}; return v[i]; } };
+// The same two sweeps exploiting the symmetry of D (blocked A1 layout, window kernels): the first sweep stores 6 components
+// {D00(1,1), D01(1,0), D11(0,0), D02(1,0), D12(0,0), D22(0,0)}, the symmetric ones for delta0 >= 0 only; the (0,1) companions
+// of D01 and D02 are the (1,0) values of the mirrored pair.  46 % fewer bytes between the two sweeps.
+struct T3SymS1H : TermOps<T3SymS1H> { enum { NIN = 6, NOUT = 6, NT = 6 };
+    static GSB_CX int pk(int k) { const int v[6] = {GSB_PK(0,0,1,1), GSB_PK(1,1,1,0), GSB_PK(2,3,0,0), GSB_PK(3,2,1,0), GSB_PK(4,4,0,0), GSB_PK(5,5,0,0)}; return v[k]; }
+    static GSB_CX bool out_sym(int oo) { return oo != 1 && oo != 3; }
+    static GSB_CX int order(int i) { const int v[6] = {0, 2, 1, 3, 4, 5}; return v[i]; } };
+struct T3SymS2H : TermOps<T3SymS2H> { enum { NIN = 8, NOUT = 4, NT = 9 };
+    static GSB_CX int pk(int k) { return T3SymS2::pk(k); }
+    static GSB_CX int order(int i) { return T3SymS2::order(i); }
+    static GSB_CX int in_src(int cc) { const int v[8] = {0, 1, 1, 2, 3, 3, 4, 5}; return v[cc]; }
+    static GSB_CX int in_mode(int cc) { const int v[8] = {0, 1, 2, 0, 1, 2, 0, 0}; return v[cc]; } };
 // last direction of any gradient-gradient form: in_g, g = 2*a+b
 struct TLast : TermOps<TLast> { enum { NIN = 4, NOUT = 1, NT = 4 };
     static GSB_CX int pk(int k) { const int v[4] = {GSB_PK(0,0,0,0), GSB_PK(0,1,0,1), GSB_PK(0,2,1,0), GSB_PK(0,3,1,1)}; return v[k]; } };
@@ -735,6 +753,9 @@ struct SweepArgs {
     // window kernel: optional 3-level decomposition of the inner column index for the INPUT address
     // (inner = (x, y, z) with z fastest: x * in_bs2 + y * in_bs + z * in_is), in_bq = 0: plain inner * in_is
     i64 in_bq, in_bs, in_bq2, in_bs2;
+    // window kernel, mirrored reads: inner = (.., delta slot, t) with mir_q points per slot and mir_w slots; the mirrored pair of
+    // (outer, slot) is (outer + slot - mir_p, 2 mir_p - slot), valid while 0 <= outer + slot - mir_p < mir_n
+    int mir_q, mir_w, mir_p, mir_n;
     i64 ncol; i64 ninner;
     // tensor-map TMA variant: which box coordinate carries the tile start, the span, the outer index
     int tm_rank, tm_dim_inner, tm_dim_e, tm_e_mul, tm_dim_outer;
@@ -984,6 +1005,14 @@ k_sweepw(const GSB_GRID_CONSTANT SweepArgs A)
     i64 in_part = inner * A.in_is;
     if (A.in_bq > 0) { const i64 r = inner % A.in_bq2; in_part = (inner / A.in_bq2) * A.in_bs2 + (r / A.in_bq) * A.in_bs + (r % A.in_bq) * A.in_is; }
     const double *inp = A.in + outer * A.in_os + in_part - (i64)A.e_in0 * A.in_es;
+    const double *inp_m = inp; bool mir_neg = false;      // same column of the mirrored pair; delta < 0 ?
+    if (A.mir_w > 0) {
+        const int di = (int)((inner / A.mir_q) % A.mir_w);
+        const i64 om = outer + di - A.mir_p;
+        mir_neg = di < A.mir_p;
+        if (om >= 0 && om < A.mir_n) inp_m = A.in + om * A.in_os + in_part + (i64)(2 * (A.mir_p - di)) * A.mir_q * A.in_is - (i64)A.e_in0 * A.in_es;
+        else mir_neg = false;
+    }
     FinalCtx fc;
     i64 obase = 0, unused_mirror = -1;
     i64 fin_c0 = 0, fin_ww = 0; int fin_pl = 0, fin_w1 = 1;
@@ -1033,8 +1062,16 @@ k_sweepw(const GSB_GRID_CONSTANT SweepArgs A)
     constexpr bool STAGE_TAB = false;
 #endif
     double vc[NS == 0 ? NR : 1], vn[NS == 0 ? NR : 1];
+    const double *pin[NIN];       // per (virtual) input component: where this thread's column starts
+    static_for<0, NIN>([&](auto cc) {
+        constexpr int c = decltype(cc)::value;
+        if constexpr (T::uses_c(OMASK, c)) {
+            constexpr int mode = T::in_mode(c);
+            pin[c] = ((mode == 2 || (mode == 0 && mir_neg)) ? inp_m : inp) + T::in_src(c) * A.in_cs;
+        }
+    });
     auto issue = [&](int e, int st) {
-        const double *pe = inp + (i64)e * A.in_es;
+        const i64 pe = (i64)e * A.in_es;
 #if !defined(GSB200_EMULATE)
         if constexpr (STAGE_TAB) { if (lane < NTAB) cp_async16(tabring + (size_t)st * 4 * NTAB + lane, A.tabl + (i64)e * NTAB + lane); }
 #endif
@@ -1044,8 +1081,8 @@ k_sweepw(const GSB_GRID_CONSTANT SweepArgs A)
                 constexpr int c = decltype(cc)::value;
                 if constexpr (T::uses_c(OMASK, c)) {
                     constexpr int r = used_rank<T>(OMASK, c);
-                    if constexpr (NS == 0) vn[t * NINg + r] = ld_stream(pe + c * A.in_cs + t * A.in_ts);
-                    else cp_async8(&GSB_RING(st, t * NINg + r), pe + c * A.in_cs + t * A.in_ts);
+                    if constexpr (NS == 0) vn[t * NINg + r] = ld_stream(pin[c] + pe + t * A.in_ts);
+                    else cp_async8(&GSB_RING(st, t * NINg + r), pin[c] + pe + t * A.in_ts);
                 }
             });
     };
@@ -1071,12 +1108,12 @@ k_sweepw(const GSB_GRID_CONSTANT SweepArgs A)
             if constexpr (STAGE_TAB) warp_sync();      // ... and sees the table entries the other lanes copied
         }
         if (pf > 0 && e + pf < e_end) {
-            const double *pe = inp + (i64)(e + pf) * A.in_es;
+            const i64 pe = (i64)(e + pf) * A.in_es;
 #pragma unroll
             for (int t = 0; t < NQ; ++t)
                 static_for<0, NIN>([&](auto cc) {
                     constexpr int c = decltype(cc)::value;
-                    if constexpr (T::uses_c(OMASK, c)) prefetch_l2(pe + c * A.in_cs + t * A.in_ts);
+                    if constexpr (T::uses_c(OMASK, c)) prefetch_l2(pin[c] + pe + t * A.in_ts);
                 });
         }
         const double2 *tb = A.tabl + (i64)e * NQ * P1;
@@ -1162,7 +1199,7 @@ k_sweepw(const GSB_GRID_CONSTANT SweepArgs A)
                     if (f0 + a >= x_min && f0 + a < x_max && a + x < P1)
                         static_for<0, NOUT>([&](auto oc_) {
                             constexpr int o = decltype(oc_)::value;
-                            if constexpr ((OMASK >> o) & 1u) st_stream(A.out + o * A.out_cs + o0 + a * st_a, acc[a][0][mask_rank(OMASK, o)]);
+                            if constexpr (((OMASK >> o) & 1u) && !T::out_sym(o)) st_stream(A.out + o * A.out_cs + o0 + a * st_a, acc[a][0][mask_rank(OMASK, o)]);
                         });
                 }
             }
@@ -1374,6 +1411,56 @@ GSB_GLOBAL void k_vsweep(const VSweepArgs A)
     const i64 li = (A.dimlow == 2) ? ((i64)x * A.n1 + outer) * A.n0 + inner : (i64)x * A.n0 + inner;
     const int g = A.dofmap[li];
     if (g < A.nfree) atomic_add(A.rhs + g, s);
+}
+
+// Window variant of the load-vector sweep: one thread per column marches along the swept direction with the (p+1)
+// partial sums of the functions alive on the current span (window order); the function leaving the window is complete.
+// Reads the load density once (the kernel above reads every point once per overlapping function).
+template <int P1>
+GSB_GLOBAL void k_vsweepw(const VSweepArgs A, const double2 *tabl, const int *nexit, const int *seg)
+{
+    constexpr int NQ = P1;
+    const i64 col = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= A.ncol) return;
+    const int sg = blockIdx.y;
+    const int e_begin = seg[4 * sg + 0], e_end = seg[4 * sg + 1], x_min = seg[4 * sg + 2], x_max = seg[4 * sg + 3];
+    const i64 outer = col / A.ninner, inner = col - outer * A.ninner;
+    const double *inp = A.in + outer * A.in_os + inner * A.in_is - (i64)A.e_in0 * NQ * A.in_qs;
+    double acc[P1];
+#pragma unroll
+    for (int k = 0; k < P1; ++k) acc[k] = 0.0;
+    int f0 = A.first[e_begin];
+    double vc[NQ], vn[NQ];
+#pragma unroll
+    for (int t = 0; t < NQ; ++t) vc[t] = ld_stream(inp + (i64)(e_begin * NQ + t) * A.in_qs);
+    for (int e = e_begin; e < e_end; ++e) {
+        const int nx = nexit[e];
+        if (e + 1 < e_end) {
+#pragma unroll
+            for (int t = 0; t < NQ; ++t) vn[t] = ld_stream(inp + (i64)((e + 1) * NQ + t) * A.in_qs);
+        }
+        const double2 *tb = tabl + (i64)e * NQ * P1;
+#pragma unroll
+        for (int t = 0; t < NQ; ++t)
+#pragma unroll
+            for (int k = 0; k < P1; ++k) acc[k] = fma(ld_keep2(tb + t * P1 + k).x, vc[t], acc[k]);
+        for (int x = 0; x < nx; ++x) {
+            if (f0 >= x_min && f0 < x_max) {
+                if (!A.final_) A.out[(i64)f0 * A.out_fs + outer * A.out_os + inner * A.out_is] = acc[0];
+                else {
+                    const i64 li = (A.dimlow == 2) ? ((i64)f0 * A.n1 + outer) * A.n0 + inner : (i64)f0 * A.n0 + inner;
+                    const int g = A.dofmap[li];
+                    if (g < A.nfree) atomic_add(A.rhs + g, acc[0]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k + 1 < P1; ++k) acc[k] = acc[k + 1];
+            acc[P1 - 1] = 0.0;
+            ++f0;
+        }
+#pragma unroll
+        for (int t = 0; t < NQ; ++t) vc[t] = vn[t];
+    }
 }
 
 // ------------------------------------------------------------------------------------
