@@ -1180,6 +1180,17 @@ int gsb200_assemble_host(const gsb200_problem *pb, int device, int64_t *nnz, int
 }
 
 // ---------------------------------------------------------------- consumer: SpMV + Jacobi-CG
+static int launch_spmv(gsb200_assembler *a, const double *x, double *y)
+{
+    const int n = a->nfree;
+#ifndef GSB200_EMULATE
+    if (!dry_run()) { k_spmv_warp<<<148 * 8, 256, 0, a->stream>>>(n, a->d_colptr, a->d_inner, a->d_values, x, y); note_launch(); }
+#else
+    GSB_LAUNCH(k_spmv, dim3((n + 127) / 128), dim3(128), a->stream, n, a->d_colptr, a->d_inner, a->d_values, x, y);
+#endif
+    return 0;
+}
+
 static int cg_alloc(gsb200_assembler *a)
 {
     for (int k = 0; k < 6; ++k) if (!a->cg[k]) GSB_TRY(dev_malloc((void **)&a->cg[k], sizeof(double) * (size_t)(a->nfree + 1)));
@@ -1194,7 +1205,7 @@ int gsb200_spmv_host(gsb200_assembler *a, const double *x, double *y)
     GSB_TRY(cg_alloc(a));
     const int n = a->nfree;
     GSB_TRY(dev_h2d(a->cg[0], x, sizeof(double) * (size_t)n, a->stream));
-    GSB_LAUNCH(k_spmv, dim3((n + 127) / 128), dim3(128), a->stream, n, a->d_colptr, a->d_inner, a->d_values, a->cg[0], a->cg[1]);
+    GSB_TRY(launch_spmv(a, a->cg[0], a->cg[1]));
     return dev_d2h(y, a->cg[1], sizeof(double) * (size_t)n, a->stream);
 }
 
@@ -1224,7 +1235,7 @@ int gsb200_cg_host(gsb200_assembler *a, const double *b, double *x, int max_iter
     rr = bb; int it = 0;
     const double thr = tol * tol * bb;
     while (it < max_iter && rr > thr) {
-        GSB_LAUNCH(k_spmv, g, t, s, n, a->d_colptr, a->d_inner, a->d_values, Pv, Q);
+        GSB_TRY(launch_spmv(a, Pv, Q));
         double pq = 0; GSB_TRY(dev_dot(a, Pv, Q, &pq));
         const double alpha = rz / pq;
         GSB_LAUNCH(k_axpy, g, t, s, n, X, alpha, Pv, X);

@@ -1620,6 +1620,23 @@ GSB_GLOBAL void k_spmv(int n, const i64 *ptr, const int *idx, const double *val,
     for (i64 k = ptr[r]; k < ptr[r + 1]; ++k) s = fma(val[k], x[idx[k]], s);
     y[r] = s;
 }
+#ifndef GSB200_EMULATE
+// One warp per row: the lanes stride over the row's entries (values and indices are read as whole 256/128-byte
+// segments), partial sums meet in a shuffle tree.  HBM-bound: 12 B per stored entry.
+GSB_GLOBAL void __launch_bounds__(256) k_spmv_warp(int n, const i64 *ptr, const int *idx, const double *val, const double *x, double *y)
+{
+    const int lane = threadIdx.x & 31;
+    const i64 warp0 = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = ((i64)gridDim.x * blockDim.x) >> 5;
+    for (i64 r = warp0; r < n; r += nwarp) {
+        const i64 b = ptr[r], e = ptr[r + 1];
+        double s = 0.0;
+        for (i64 k = b + lane; k < e; k += 32) s = fma(__ldcs(val + k), __ldg(x + __ldcs(idx + k)), s);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) y[r] = s;
+    }
+}
+#endif
 GSB_GLOBAL void k_diag(int n, const i64 *ptr, const int *idx, const double *val, double *d)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1633,6 +1650,11 @@ GSB_GLOBAL void k_dot(int n, const double *a, const double *b, double *out)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double s = 0.0;
     for (int k = i; k < n; k += gridDim.x * blockDim.x) s = fma(a[k], b[k], s);
+#ifndef GSB200_EMULATE
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) != 0) return;
+#endif
     if (s != 0.0) atomic_add(out, s);
 }
 // z = a + alpha * b  (element-wise)  and  z = a / d

@@ -11,3 +11,9 @@ A = g.DeviceAssembler(pb); A.buildPattern()
 for _ in range(a.reps):
     A.assemble()
 t = A.timings(); print("ms:", t.geometry_ms, list(t.sweep_ms), t.rhs_ms, t.total_ms)
+if os.environ.get("PROF_CG"):
+    import time, numpy as np
+    b = A.rhs()[:, 0]
+    n = int(os.environ["PROF_CG"])
+    t0 = time.time(); u, it, res = A.cg(b, max_iter=n, tol=1e-30); dt = time.time() - t0
+    print(f"cg: {it} iterations in {dt*1e3:.1f} ms = {dt/it*1e3:.3f} ms/iter, rel.res {res:.3e}")
