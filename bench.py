@@ -216,9 +216,16 @@ def main():
     except Exception:
         pass
     ach = tm.sweep_bytes[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-    roofline = {"kernel": f"k_sweep direction {dom}", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+    # a sweep is one launch per group of output components (k_sweepw<P1, table, output mask, final, stages>); bytes and time are
+    # those of the whole sweep (all its group launches, CUDA events on the launching stream inside the timed region)
+    groups = {0: 4, 1: 2, 2: 1}.get(dom, 1) if p == 3 else None
+    roofline = {"kernel": f"k_sweepw, sum-factorisation sweep of direction {dom}" + (" (final: CSC scatter)" if dom == 2 else ""),
+                "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                 "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": int(tm.sweep_bytes[dom]), "ms_per_launch": dom_ms / max(tm.nchunks, 1)}
+                "algorithmic_bytes_per_launch": int(tm.sweep_bytes[dom]), "ms_per_launch": dom_ms / max(tm.nchunks, 1),
+                "launches_per_sweep": groups,
+                "note": "achieved = algorithmic bytes of the sweep (inputs read once + outputs written once, DESIGN.md 3) / its event-timed "
+                        "duration; traffic = measured dram read+write bytes of the same launches (profiles/traffic.json)"}
     stages = {"geometry_ms": tm.geometry_ms, "sweep_ms": [tm.sweep_ms[k] for k in range(3)], "rhs_ms": tm.rhs_ms,
               "total_ms_last_step": tm.total_ms, "pattern_ms": tm_cold.pattern_ms, "chunks": tm.nchunks,
               "sweep_gbs": [tm.sweep_bytes[k] / (tm.sweep_ms[k] * 1e-3) / 1e9 if tm.sweep_ms[k] > 0 else 0 for k in range(3)],
@@ -261,7 +268,7 @@ def main():
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "qp_per_sec": qp / sec_per_step,
                 "config": {"workload": f"3D unit-cube tensor B-spline, degree {p}, {m}x{m}x{m * world} elements ({m}^3 per GPU slab), "
                                        f"{n_dofs} DOFs, nnz/GPU {nnz_local}, Poisson stiffness + RHS",
-                           "l2": "no flush needed: every step streams ~35 GB of intermediates per GPU, far larger than the 126 MB L2",
+                           "l2": "no flush needed: every step streams ~73 GB through HBM per GPU (34 GB of intermediates written and re-read), far larger than the 126 MB L2",
                            "parallelism": f"column slabs x{world}, no collective"},
                 "e2e": {"value": e2e_val, "unit": "DOFs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "steps": args.e2e_steps, "ms_per_step": float(e2e_s.item()) * 1e3,
