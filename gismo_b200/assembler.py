@@ -112,6 +112,12 @@ class DeviceAssembler:
         check(self.lib.gsb200_timings_get(self._h, C.byref(t)))
         return t
 
+    def jit_launches(self) -> int:
+        """Geometry launches of the last assemble() that ran the NVRTC-compiled source term."""
+        n = C.c_int(0)
+        check(self.lib.gsb200_jit_launches(self._h, C.byref(n)))
+        return n.value
+
     # --- consumer (SURVEY 8f-1) -------------------------------------------------------
     def spmv(self, x: np.ndarray) -> np.ndarray:
         x = np.ascontiguousarray(x, dtype=np.float64)

@@ -204,6 +204,8 @@ def load_library():
     lib.gsb200_spmv_host.argtypes = [C.c_void_p, _dp, _dp]
     lib.gsb200_cg_host.argtypes = [C.c_void_p, _dp, _dp, C.c_int, C.c_double, C.POINTER(C.c_int), _dp]
     lib.gsb200_expr_compile.argtypes = [C.c_char_p, _ip, C.c_int32, _ip, _dp, C.c_int32, _ip]
+    lib.gsb200_jit_launches.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+    lib.gsb200_jit_compile_check.argtypes = [C.POINTER(Program), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
     lib.gsb200_expr_eval_host.argtypes = [C.POINTER(Program), C.c_double, C.c_double, C.c_double, _dp]
     lib.gsb200_measure_peaks.argtypes = [C.c_int, _dp, _dp, _dp]
     lib.gsb200_device_count.argtypes = [C.POINTER(C.c_int)]

@@ -10,6 +10,12 @@
 #include <cuda.h>   // CUtensorMap + enums only; the encoder is fetched with cudaGetDriverEntryPoint
 #endif
 
+#ifndef GSB200_EMULATE
+#include "jit.cuh"
+#else
+namespace gsb { struct HostProgram { std::vector<int> ops; std::vector<double> consts; }; }
+#endif
+
 namespace gsb {
 
 static thread_local char g_err[1024] = "";
@@ -171,6 +177,8 @@ struct gsb200_assembler {
     i64 *d_colptr = 0; int *d_inner = 0; int *d_npre = 0;
     i64 nnz = 0;
     std::vector<DevProgram> progs; std::vector<void *> prog_bufs;
+    std::vector<HostProgram> progs_host;   // the same source-term programs, for the NVRTC path (jit.cuh)
+    int jit_launches = 0;                  // geometry launches of the last assemble() that ran the compiled source term
     struct NeumannSide { int patch, side, ndata; DevProgram prog[3]; };
     std::vector<NeumannSide> neumann; double *d_face = 0; size_t face_cap = 0;
     stream_t stream = 0;
@@ -556,6 +564,7 @@ static int assemble_pass(gsb200_assembler *a)
     stream_t s = a->stream;
     const int N = a->nfree;
     g_launches = 0;
+    a->jit_launches = 0;
     a->ev_used = 0;
     memset(a->tm.sweep_bytes, 0, sizeof a->tm.sweep_bytes); memset(a->tm.sweep_flops, 0, sizeof a->tm.sweep_flops);
     a->tm.nchunks = 0;
@@ -662,7 +671,13 @@ static int assemble_pass(gsb200_assembler *a)
                     if (!geo_point) {
                         const int pgl = P.dir[L].pg1;
                         const bool rat = P.d_weights != 0, hot = a->form == GSB200_FORM_POISSON && G.symD;
+#ifndef GSB200_EMULATE
+#define GSB_GEOL(D_, PG_, R_, F_) { cudaKernel_t jk = (G.F && !dry_run()) ? jit_geometry_kernel(a->progs_host, a->device, D_, PG_, R_, F_) : 0; \
+                                    if (jk) { void *kargs[] = {(void *)&G}; GSB_TRY(dev_check(cudaLaunchKernel((const void *)jk, gg, dim3(128), kargs, 0, s), "launch of the compiled geometry kernel")); note_launch(); ++a->jit_launches; } \
+                                    else { auto kfn = k_geometry_line<D_, PG_, R_, F_>; GSB_LAUNCH(kfn, gg, dim3(128), s, G); } }
+#else
 #define GSB_GEOL(D_, PG_, R_, F_) { auto kfn = k_geometry_line<D_, PG_, R_, F_>; GSB_LAUNCH(kfn, gg, dim3(128), s, G); }
+#endif
 #define GSB_GEOL_D(D_) { if (hot && !rat && pgl == 2) GSB_GEOL(D_, 2, false, 1) else if (hot && !rat && pgl == 3) GSB_GEOL(D_, 3, false, 1) \
                          else if (hot && !rat && pgl == 4) GSB_GEOL(D_, 4, false, 1) else if (hot && rat && pgl == 3) GSB_GEOL(D_, 3, true, 1) \
                          else if (rat) GSB_GEOL(D_, 0, true, 0) else GSB_GEOL(D_, 0, false, 0) }
@@ -1019,7 +1034,15 @@ int gsb200_create(const gsb200_problem *pb, int device, gsb200_assembler **out)
     if (!rc && pb->rhs_kind == GSB200_RHS_PROGRAM) {
         const int np = pb->form == GSB200_FORM_ELASTICITY ? pb->ncomp : pb->nrhs;
         if (!pb->rhs_programs) { set_error("rhs_kind=PROGRAM but no programs"); rc = GSB200_EINVAL; }
-        for (int c = 0; c < np && !rc; ++c) { DevProgram dp; rc = upload_program(pb->rhs_programs[c], &dp); if (!rc) a->progs.push_back(dp); }
+        for (int c = 0; c < np && !rc; ++c) {
+            DevProgram dp; rc = upload_program(pb->rhs_programs[c], &dp);
+            if (!rc) {
+                a->progs.push_back(dp);
+                HostProgram hp; hp.ops.assign(pb->rhs_programs[c].ops, pb->rhs_programs[c].ops + pb->rhs_programs[c].nops);
+                hp.consts.assign(pb->rhs_programs[c].consts, pb->rhs_programs[c].consts + pb->rhs_programs[c].nconsts);
+                a->progs_host.push_back(hp);
+            }
+        }
     }
     if (!rc && pb->nneumann > 0) {
         if (pb->ncomp != 1 || pb->nrhs != 1 || !pb->neumann) { set_error("Neumann sides need a scalar problem with one right-hand side"); rc = GSB200_EUNSUPPORTED; }
@@ -1249,6 +1272,30 @@ int gsb200_cg_host(gsb200_assembler *a, const double *b, double *x, int max_iter
     if (iters) *iters = it;
     if (rel_residual) *rel_residual = bb > 0 ? sqrt(rr / bb) : 0.0;
     return dev_d2h(x, X, sizeof(double) * (size_t)n, s);
+}
+
+int gsb200_jit_launches(const gsb200_assembler *a, int *count)
+{
+    if (!a || !count) return GSB200_EINVAL;
+    *count = a->jit_launches; return GSB200_OK;
+}
+
+int gsb200_jit_compile_check(const gsb200_program *progs, int nprogs, int dim, int pgl, int rational, int fspec, char *log, int log_cap)
+{
+    if (!progs || nprogs < 1 || nprogs > 3) { set_error("jit check: bad arguments"); return GSB200_EINVAL; }
+#ifndef GSB200_EMULATE
+    std::vector<HostProgram> hp(nprogs);
+    for (int c = 0; c < nprogs; ++c) { hp[c].ops.assign(progs[c].ops, progs[c].ops + progs[c].nops); hp[c].consts.assign(progs[c].consts, progs[c].consts + progs[c].nconsts); }
+    std::string src, clog; std::vector<char> cubin;
+    if (!jit_build_source(hp, dim, pgl, rational != 0, fspec, src)) { set_error("jit check: program not translatable"); return GSB200_EUNSUPPORTED; }
+    const bool ok = jit_compile(src, cubin, clog);
+    if (log && log_cap > 0) { snprintf(log, (size_t)log_cap, "%s", clog.c_str()); }
+    if (!ok) { set_error("jit check: NVRTC compile failed: %.800s", clog.c_str()); return GSB200_EUNSUPPORTED; }
+    return GSB200_OK;
+#else
+    (void)dim; (void)pgl; (void)rational; (void)fspec; (void)log; (void)log_cap;
+    set_error("no NVRTC in the interpreter build"); return GSB200_EUNSUPPORTED;
+#endif
 }
 
 int gsb200_expr_eval_host(const gsb200_program *prog, double x, double y, double z, double *out)

@@ -221,6 +221,14 @@ int gsb200_cg_host(gsb200_assembler *a, const double *b, double *x, int max_iter
    numeric literals, sin cos tan exp log sqrt abs tanh sinh cosh. */
 int gsb200_expr_compile(const char *expr, int32_t *ops, int32_t ops_cap, int32_t *nops,
                         double *consts, int32_t consts_cap, int32_t *nconsts);
+/* Geometry-kernel launches of the last gsb200_assemble() that ran the NVRTC-compiled source term (csrc/jit.cuh;
+   policy GSB200_JIT=0|1|2: never, from the third use of a program in the process (default), at first use). */
+int gsb200_jit_launches(const gsb200_assembler *a, int *count);
+/* Diagnostic: translate `nprogs` source-term programs to CUDA and compile them with NVRTC together with the
+   geometry kernel <dim, pgl, rational, fspec> exactly as repeated assemblies do (csrc/jit.cuh; needs libnvrtc,
+   no device).  The compiler log is copied to `log` (may be NULL). */
+int gsb200_jit_compile_check(const gsb200_program *progs, int nprogs, int dim, int pgl, int rational, int fspec,
+                             char *log, int log_cap);
 /* Host evaluation of a compiled program (used by tests to pin the device VM). */
 int gsb200_expr_eval_host(const gsb200_program *prog, double x, double y, double z, double *out);
 

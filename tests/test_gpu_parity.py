@@ -9,6 +9,8 @@ Bars: sparsity pattern and DOF mapping bit-exact; values/rhs within 1e-12 of max
 """
 import ctypes as C
 
+import os
+
 import numpy as np
 import pytest
 
@@ -175,6 +177,25 @@ def test_consumer_spmv_and_cg(lib):
     # manufactured solution u = sin(pi x) sin(pi y) sin(pi z) on the cube centred at 0 -> cos products; just sanity
     assert np.all(np.isfinite(u))
     A.close()
+
+
+def test_compiled_source_term_equals_interpreter_bitwise(lib):
+    """Repeated assemblies switch the geometry kernel to the NVRTC-compiled source term (csrc/jit.cuh): same numbers, bit for bit."""
+    pb, z = G.load("cube_p3_curved_m4", g.expr_compile)
+    A = g.DeviceAssembler(pb)
+    A.assemble()
+    first = A.matrix() + (A.rhs(),)
+    used_first = A.jit_launches()
+    for _ in range(3):
+        A.assemble()
+    last = A.matrix() + (A.rhs(),)
+    used_last = A.jit_launches()
+    A.close()
+    G.check_against(last + (None,), z, TOL)
+    if os.environ.get("GSB200_JIT", "1") == "0" or used_last == 0:
+        pytest.skip("NVRTC path not active (GSB200_JIT=0 or libnvrtc missing)")
+    assert used_last > 0
+    assert np.array_equal(first[2], last[2]) and np.array_equal(first[3], last[3]), (used_first, used_last)
 
 
 def test_measured_peaks_are_plausible(lib):

@@ -103,3 +103,31 @@ def test_dof_mapper_coupling_order():
     m.finalize()
     assert m.nfree == 5 and m.nfixed == 2
     assert list(m.patch_map(0)) == [5, 0, 1, 4] and list(m.patch_map(1)) == [4, 2, 3, 6]
+
+
+def test_embedded_geometry_source_is_in_sync():
+    """csrc/geometry_src.inc (what NVRTC compiles) must be the text of csrc/geometry.cuh."""
+    import os
+    csrc = os.path.join(R.ROOT, "gismo_b200", "csrc")
+    src = open(os.path.join(csrc, "geometry.cuh")).read()
+    inc = open(os.path.join(csrc, "geometry_src.inc")).read()
+    assert src in inc, "run __graft_entry__.build() to regenerate geometry_src.inc"
+
+
+@pytest.mark.parametrize("text,dim,pgl,rational,fspec", [("3*pi^2*sin(pi*x)*sin(pi*y)*sin(pi*z)", 3, 2, 0, 1), ("2*pi^2*sin(pi*x)*sin(pi*y)", 2, 0, 1, 0),
+                                                        ("x^2+exp(-y)/(1+z*z)-sqrt(abs(x))+cos(x)^3", 3, 3, 0, 0)])
+def test_source_term_translates_and_compiles_with_nvrtc(text, dim, pgl, rational, fspec):
+    """The NVRTC path of repeated assemblies (csrc/jit.cuh): program -> straight-line CUDA + geometry.cuh -> sm_100a cubin.
+    Needs libnvrtc only (no device)."""
+    import ctypes as C
+    import gismo_b200 as g
+    from gismo_b200 import capi
+    lib = capi.load_library()
+    pr = g.expr_compile(text)
+    ip, dp = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+    P = (capi.Program * 1)(capi.Program(len(pr.ops), pr.ops.ctypes.data_as(ip), len(pr.consts), pr.consts.ctypes.data_as(dp)))
+    log = C.create_string_buffer(8000)
+    rc = lib.gsb200_jit_compile_check(P, 1, dim, pgl, rational, fspec, log, 8000)
+    if rc and b"libnvrtc not available" in lib.gsb200_last_error():
+        pytest.skip("libnvrtc not found")
+    assert rc == 0, lib.gsb200_last_error().decode() + log.value.decode()
