@@ -159,6 +159,7 @@ def main():
     sampler.stop_flag = True
     ms_total = float(ms.item())
     tm = A.timings()
+    jit_used = A.jit_launches()
     dview = A.device_view()
     n_dofs = pb.nfree                                   # global free DOFs = all ranks' columns
     n_elem = m * m * m * world
@@ -269,7 +270,9 @@ def main():
                 "config": {"workload": f"3D unit-cube tensor B-spline, degree {p}, {m}x{m}x{m * world} elements ({m}^3 per GPU slab), "
                                        f"{n_dofs} DOFs, nnz/GPU {nnz_local}, Poisson stiffness + RHS",
                            "l2": "no flush needed: every step streams ~73 GB through HBM per GPU (34 GB of intermediates written and re-read), far larger than the 126 MB L2",
-                           "parallelism": f"column slabs x{world}, no collective"},
+                           "parallelism": f"column slabs x{world}, no collective",
+                           "source_term": ("compiled into the geometry kernel with NVRTC (repeated assemblies, from the 3rd use on; bitwise the "
+                                           "interpreter's operations)" if jit_used else "interpreted stack machine")},
                 "e2e": {"value": e2e_val, "unit": "DOFs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "steps": args.e2e_steps, "ms_per_step": float(e2e_s.item()) * 1e3,
                         "phases_ms": {k: float(np.mean([p[i] for p in e2e_phases]) * 1e3) for i, k in enumerate(("create", "pattern", "assemble_to_host", "destroy"))},

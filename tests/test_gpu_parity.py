@@ -179,9 +179,12 @@ def test_consumer_spmv_and_cg(lib):
     A.close()
 
 
-def test_compiled_source_term_equals_interpreter_bitwise(lib):
-    """Repeated assemblies switch the geometry kernel to the NVRTC-compiled source term (csrc/jit.cuh): same numbers, bit for bit."""
-    pb, z = G.load("cube_p3_curved_m4", g.expr_compile)
+def test_compiled_source_term_equals_interpreter(lib):
+    """Repeated assemblies switch the geometry kernel to the NVRTC-compiled source term (csrc/jit.cuh).  The compiled term uses
+    the interpreter's operations one by one (__dmul_rn, ... : nothing is contracted), so the load vector agrees to the rounding
+    of its atomic accumulation order; the matrix does not depend on the source term and stays bit-identical."""
+    text = "3*pi^2*sin(pi*x)*sin(pi*y)*sin(pi*z)+0.125*x*y-exp(-z*z)/7"        # a program no other test uses: its first launches interpret
+    pb = host.poisson_box_problem(3, 3, 9, g.expr_compile(text))
     A = g.DeviceAssembler(pb)
     A.assemble()
     first = A.matrix() + (A.rhs(),)
@@ -191,11 +194,13 @@ def test_compiled_source_term_equals_interpreter_bitwise(lib):
     last = A.matrix() + (A.rhs(),)
     used_last = A.jit_launches()
     A.close()
-    G.check_against(last + (None,), z, TOL)
-    if os.environ.get("GSB200_JIT", "1") == "0" or used_last == 0:
-        pytest.skip("NVRTC path not active (GSB200_JIT=0 or libnvrtc missing)")
-    assert used_last > 0
-    assert np.array_equal(first[2], last[2]) and np.array_equal(first[3], last[3]), (used_first, used_last)
+    ok, msg = R.compare_csc(last, R.oracle_assemble(pb), TOL)
+    assert ok, msg
+    if os.environ.get("GSB200_JIT", "1") != "1" or used_last == 0:
+        pytest.skip("NVRTC path not active (GSB200_JIT set or libnvrtc missing)")
+    assert used_first == 0 and used_last > 0
+    assert np.array_equal(first[2], last[2])
+    assert np.abs(first[3] - last[3]).max() <= 1e-14 * np.abs(first[3]).max()
 
 
 def test_measured_peaks_are_plausible(lib):
