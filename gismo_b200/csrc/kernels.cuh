@@ -380,8 +380,10 @@ GSB_DEVICE i64 final_prepare(const FinalArgs &F, const FinalCtx &c, const OwnerC
     const int flag = (int)(oc.rec & 3);
     if (!flag) return -1;
     const i64 base = oc.rec >> 2;
-    if (flag == 3)          // full interior stencil: every partner is free, rank is the lexicographic stencil index
-        return base + ((F.dim == 2) ? (dL + F.p[1]) : ((dL + F.p[2]) * (2 * F.p[1] + 1) + c.r_low)) * (2 * F.p[0] + 1) + c.bit0;
+    if (flag == 3) {        // full interior stencil: every partner is free, rank is the lexicographic stencil index (per row component)
+        const i64 full = (i64)(2 * F.p[0] + 1) * (2 * F.p[1] + 1) * (F.dim == 3 ? 2 * F.p[2] + 1 : 1);
+        return base + F.brow * full + ((F.dim == 2) ? (dL + F.p[1]) : ((dL + F.p[2]) * (2 * F.p[1] + 1) + c.r_low)) * (2 * F.p[0] + 1) + c.bit0;
+    }
     const i64 li = (i64)oc.fun * c.nlow + c.li_low;
     const i64 lj = li + (i64)dL * c.nlow + c.dj_low;
     if (flag == 1) {
@@ -690,6 +692,7 @@ k_sweepw(const GSB_GRID_CONSTANT SweepArgs A)
         const int W0 = 2 * A.fin.p[0] + 1;
         if (A.fin.dim == 2) { fin_ww = W0; fin_c0 = fc.bit0; fin_pl = A.fin.p[1]; fin_w1 = 1; }
         else { fin_ww = (i64)(2 * A.fin.p[1] + 1) * W0; fin_c0 = (i64)fc.r_low * W0 + fc.bit0; fin_pl = A.fin.p[2]; fin_w1 = 2 * A.fin.p[1] + 1; }
+        fin_c0 += (i64)A.fin.brow * (2 * fin_pl + 1) * fin_ww;        // rows of a vector-valued space: component-major blocks of the stencil
     } else obase = sweep_obase(A, outer, inner, &unused_mirror);
     const int x_min = live ? A.seg[4 * sg + 2] : 0, x_max = live ? A.seg[4 * sg + 3] : 0;    // empty owner range: nothing is written
 
@@ -1216,7 +1219,11 @@ GSB_GLOBAL void k_pattern(const PatArgs A)
     }
     i64 pos = base;
     int prev = -1; bool mono = true;
-    for (int cr = 0; cr < A.ncomp; ++cr)
+    i64 full = 1;
+    for (int k = 0; k < A.dim; ++k) full *= 2 * A.p[k] + 1;
+    bool all_full = true;            // every row component contributes the whole (2p+1)^d stencil
+    for (int cr = 0; cr < A.ncomp; ++cr) {
+        const i64 pos_cr = pos;
         for (int j2 = lo[2]; j2 <= hi[2]; ++j2) for (int j1 = lo[1]; j1 <= hi[1]; ++j1) {
             unsigned mask = 0; const int start = (int)(pos - base);
             for (int j0 = lo[0]; j0 <= hi[0]; ++j0) {
@@ -1233,11 +1240,12 @@ GSB_GLOBAL void k_pattern(const PatArgs A)
                 A.st[li * A.nrun + run] = (unsigned)start | (mask << 16);
             }
         }
-    if (mono && A.ncomp == 1) {
-        i64 full = 1;
-        for (int k = 0; k < A.dim; ++k) full *= 2 * A.p[k] + 1;
-        A.colflag[id] = (pos - base == full) ? 3 : 1;     // 3: whole (2p+1)^d stencil present -> closed-form slots
-    } else { A.colflag[id] = 2; if (!mono) A.gneed[gi] = 1; }
+        if (pos - pos_cr != full) all_full = false;
+    }
+    // 3: whole (2p+1)^d stencil present (per row component, component-major rows) -> closed-form slots; 1: canonical scalar column
+    if (mono && all_full) A.colflag[id] = 3;
+    else if (mono && A.ncomp == 1) A.colflag[id] = 1;
+    else { A.colflag[id] = 2; if (!mono) A.gneed[gi] = 1; }
 }
 
 // sort (and for coupled columns deduplicate) the row indices of the flagged columns

@@ -40,14 +40,29 @@ def device_tensor(ptr: int, n: int, dtype: torch.dtype, device: int) -> torch.Te
     return torch.as_tensor(_CudaView(ptr, n, typestr), device=torch.device("cuda", device))
 
 
-def reduce_coupled_columns(values: torch.Tensor, rhs: torch.Tensor, outer: np.ndarray, c0: int,
+def coupled_column_ranges(problem: Problem):
+    """Contiguous runs [a, b) of global columns shared by more than one (patch, local) pre-image: one tail run for a scalar
+    space, one per component block for a vector-valued one (component-major numbering, gsDofMapper.cpp:255-265)."""
+    counts = np.zeros(problem.nfree + 1, dtype=np.int32)
+    for p in problem.patches:
+        g = p.dofmap[p.dofmap < problem.nfree]
+        np.add.at(counts, g, 1)
+    multi = np.concatenate([[False], counts[:problem.nfree] > 1, [False]])
+    edges = np.flatnonzero(multi[1:] != multi[:-1])
+    return [(int(edges[k]), int(edges[k + 1])) for k in range(0, len(edges), 2)]
+
+
+def reduce_coupled_columns(values: torch.Tensor, rhs: torch.Tensor, outer: np.ndarray, c0,
                            group: Optional[dist.ProcessGroup] = None) -> None:
-    """In place: sum the value block of columns [c0, n) and the whole rhs over all ranks."""
+    """In place: sum the value blocks of the coupled columns (c0 = first coupled column of a scalar space, or the list of
+    runs from coupled_column_ranges) and the whole rhs over all ranks."""
     n = len(outer) - 1
+    runs = [(int(c0), n)] if np.isscalar(c0) else list(c0)
     if dist.is_initialized() and dist.get_world_size(group) > 1:
-        if c0 < n:
-            block = values[int(outer[c0]):int(outer[n])]
-            dist.all_reduce(block, op=dist.ReduceOp.SUM, group=group)
+        for a, b in runs:
+            if a < b and int(outer[b]) > int(outer[a]):
+                block = values[int(outer[a]):int(outer[b])]
+                dist.all_reduce(block, op=dist.ReduceOp.SUM, group=group)
         dist.all_reduce(rhs, op=dist.ReduceOp.SUM, group=group)
 
 

@@ -12,7 +12,7 @@ from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from .capi import PatchData, Problem, FORM_POISSON, CompiledProgram
+from .capi import PatchData, Problem, FORM_POISSON, FORM_ELASTICITY, CompiledProgram
 
 
 class KnotVector:
@@ -218,3 +218,69 @@ def poisson_box_problem(dim: int, degree: int, nelem: Sequence[int] | int, rhs_p
                       mapper.patch_map(0))
     return Problem([patch], mapper.nfree, mapper.nfixed, form=form, ncomp=1,
                    rhs_programs=[rhs_program] if rhs_program is not None else None, rank=rank, nranks=nranks)
+
+
+def multipatch_grid_problem(dim: int, degree: int, grid: Sequence[int], nelem: int, rhs_programs=None, form: int = FORM_POISSON,
+                            coef=(0.0, 0.0), rank: int = 0, nranks: int = 1) -> Problem:
+    """SURVEY 8(d) configs 3/4 in synthetic form: a conforming grid of unit boxes (gsNurbsCreator::BSplineSquareGrid /
+    BSplineCubeGrid patch order: LAST direction fastest), every patch with its own degree-p basis of `nelem` elements per
+    direction, C0 gluing of all interfaces (iFace::glue), homogeneous Dirichlet on the outer boundary (elimination).
+    The numbering is gsDofMapper's (gsDofMapper.cpp:240-344): standard free DOFs in patch-then-local order, then the
+    coupled interface DOFs in first-appearance order, then the eliminated ones; vector-valued forms get component-major
+    blocks.  Built with array operations on the global lattice of glued functions (DofMapper.match is per DOF)."""
+    grid = [int(g) for g in grid][:dim]
+    ncomp = dim if form == FORM_ELASTICITY else 1
+    nf1 = nelem + degree                                   # functions per direction and patch
+    lat = [g * (nf1 - 1) + 1 for g in grid]                 # glued lattice per direction
+    patches_abc = []
+    for a in np.ndindex(*grid):                             # last index fastest = reference order
+        patches_abc.append(a)
+    npatch = len(patches_abc)
+    nloc = nf1 ** dim
+    # node id of every (patch, local function); local index has direction 0 fastest
+    loc = np.arange(nloc)
+    lk = [(loc // (nf1 ** k)) % nf1 for k in range(dim)]
+    node = np.empty((npatch, nloc), dtype=np.int64)
+    outer_b = np.zeros((npatch, nloc), dtype=bool)
+    for ip, abc in enumerate(patches_abc):
+        nid = np.zeros(nloc, dtype=np.int64); stride = 1; ob = np.zeros(nloc, dtype=bool)
+        for k in range(dim):
+            gk = abc[k] * (nf1 - 1) + lk[k]
+            nid += gk * stride; stride *= lat[k]
+            ob |= (gk == 0) | (gk == lat[k] - 1)
+        node[ip] = nid; outer_b[ip] = ob
+    flat_node = node.ravel(); flat_ob = outer_b.ravel()
+    counts = np.bincount(flat_node, minlength=int(np.prod(lat)))
+    multi = counts[flat_node] > 1
+    std = ~flat_ob & ~multi
+    cpl = ~flat_ob & multi
+    nstd = int(std.sum())
+    index1 = np.zeros(npatch * nloc, dtype=np.int64)
+    index1[std] = np.arange(nstd)
+
+    def first_appearance_rank(sel):
+        ids, first_pos, inv = np.unique(flat_node[sel], return_index=True, return_inverse=True)
+        order = np.argsort(first_pos, kind="stable")
+        rk = np.empty(len(ids), dtype=np.int64); rk[order] = np.arange(len(ids))
+        return rk[inv], len(ids)
+    ncpl = nelim = 0
+    if cpl.any():
+        r, ncpl = first_appearance_rank(cpl); index1[cpl] = nstd + r
+    if flat_ob.any():
+        r, nelim = first_appearance_rank(flat_ob); index1[flat_ob] = r       # offset added below
+    nfree1 = nstd + ncpl
+    nfree, nfixed = nfree1 * ncomp, nelim * ncomp
+    patches = []
+    for ip, abc in enumerate(patches_abc):
+        gkv, C = bspline_box(dim, 1.0, [float(v) + (0.5 if dim == 3 else 0.0) for v in abc] + [0.0] * (3 - dim))
+        skv = []
+        for k in range(dim):
+            kv = gkv[k].copy(); kv.setDegree(degree)
+            if nelem > 1:
+                kv.uniformRefine(nelem - 1)
+            skv.append(kv)
+        i1 = index1[ip * nloc:(ip + 1) * nloc]; ob = flat_ob[ip * nloc:(ip + 1) * nloc]
+        dm = np.concatenate([np.where(ob, i1 + nfree + c * nelim, i1 + c * nfree1) for c in range(ncomp)]).astype(np.int32)
+        patches.append(PatchData([degree] * dim, [kv.knots for kv in skv], [kv.degree for kv in gkv], [kv.knots for kv in gkv], C, dm))
+    return Problem(patches, nfree, nfixed, form=form, ncomp=ncomp, coef=tuple(coef) + (0.0,) * (4 - len(coef)),
+                   rhs_programs=rhs_programs, rank=rank, nranks=nranks)

@@ -131,3 +131,30 @@ def test_source_term_translates_and_compiles_with_nvrtc(text, dim, pgl, rational
     if rc and b"libnvrtc not available" in lib.gsb200_last_error():
         pytest.skip("libnvrtc not found")
     assert rc == 0, lib.gsb200_last_error().decode() + log.value.decode()
+
+
+@pytest.mark.parametrize("name,dim,p,grid,m,form", [("grid2x2x2_p2_m3", 3, 2, (2, 2, 2), 3, 0), ("grid2x2_p2_m4", 2, 2, (2, 2), 4, 0),
+                                                    ("elasticity_8cubes_p2_m5", 3, 2, (2, 2, 2), 5, 1)])
+def test_multipatch_grid_builder_reproduces_the_reference_numbering(name, dim, p, grid, m, form):
+    """host.multipatch_grid_problem (array operations on the glued lattice) against the flattened inputs the reference produced
+    for the same grids: gsDofMapper numbering, knots after setDegree/uniformRefine, control points, patch order."""
+    import os
+    from gismo_b200 import host
+    z = np.load(os.path.join(R.ROOT, "tests", "golden", name + ".npz"), allow_pickle=True)
+    pb = host.multipatch_grid_problem(dim, p, grid, m, form=form)
+    assert (pb.nfree, pb.nfixed) == (int(z["nfree"]), int(z["nfixed"]))
+    for ip, pa in enumerate(pb.patches):
+        assert np.array_equal(pa.dofmap, z[f"p{ip}_dofmap"])
+        assert np.allclose(np.asarray(pa.geo_coefs), np.asarray(z[f"p{ip}_coefs"]))
+        for k in range(dim):
+            assert np.array_equal(pa.space_knots[k], z[f"p{ip}_sk{k}"])
+
+
+def test_coupled_column_ranges_scalar_and_vector():
+    from gismo_b200 import host, distributed as D
+    pb = host.multipatch_grid_problem(2, 2, (2, 2), 4)
+    assert D.coupled_column_ranges(pb) == [(D.first_coupled_column(pb), pb.nfree)]
+    pe = host.multipatch_grid_problem(3, 2, (2, 2, 2), 3, form=1)
+    runs = D.coupled_column_ranges(pe)
+    n1 = pe.nfree // 3
+    assert len(runs) == 3 and all(b == (c + 1) * n1 for c, (a, b) in enumerate(runs)) and len({b - a for a, b in runs}) == 1
