@@ -437,7 +437,13 @@ static int launch_sweep_i(const SweepArgs &A, int nseg, stream_t s, i64 *flops_p
 }
 // Window kernel (default): one launch per group of output components; a group is as many outputs as keep the
 // (p+1)^2 * NG accumulators in registers.  GSB200_SWEEP=ring selects the shared-memory ring kernels instead.
-constexpr int window_ng(int P1, int NOUT) { int ng = 36 / (P1 * P1); if (ng < 1) ng = 1; return ng < NOUT ? ng : NOUT; }
+constexpr int window_ng(int P1, int NOUT)
+{
+    const int per_out = P1 * P1 + (GSB_WINDOW_HOLD(P1) ? P1 * (P1 - 1) / 2 : 0);     // accumulators (+ held pairs) per output component
+    int ng = 36 / per_out; if (ng < 1) ng = 1; if (ng > NOUT) ng = NOUT;
+    if (NOUT % ng != 0 && ng > 1 && NOUT % (ng - 1) == 0) --ng;                       // balanced groups
+    return ng;
+}
 #ifndef GSB200_EMULATE
 template <class K> static int window_launch(K kfn, dim3 grid, size_t smem, stream_t s, const SweepArgs &A)
 {
@@ -603,11 +609,12 @@ static int assemble_pass(gsb200_assembler *a)
         // symmetric forms in 3-D: the first sweep keeps only delta0 >= 0, the second one mirrors its output
         const bool half = dim == 3 && kind != KIND_GEN && getenv("GSB200_SYM") && getenv("GSB200_SWEEP");   // experiment, ring kernels only
         static const bool a2_rows_env = [] { const char *e = getenv("GSB200_A2ROWS"); return e && atoi(e) > 0; }();
-        // layout of A1 (3-D): 1 = blocked by last-direction element (A1[o][i0][q1][e2][d0][t]: the second sweep reads whole runs, but the
-        // first one stores q-point pieces, which only pays when those are whole 32-byte sectors), 2 = A1[o][i0][d0][q1][q2] (coalesced first-
-        // sweep stores, the second sweep gathers q-point pieces), 0 = legacy mapping of the ring kernels.  GSB200_A1BLK overrides.
+        // layout of A1 (3-D): 1 (default) = blocked by last-direction element (A1[o][i0][q1][e2][d0][t]: the second sweep reads whole runs; the
+        // first one stores q-point pieces, whole rows of deltas at a time when q points do not fill a sector, GSB_WINDOW_HOLD),
+        // 2 = A1[o][i0][d0][q1][q2] (coalesced first-sweep stores, the second sweep gathers q-point pieces), 0 = legacy mapping of the ring
+        // kernels.  GSB200_A1BLK overrides.
         static const int a1_env = [] { const char *e = getenv("GSB200_A1BLK"); return e ? atoi(e) : -1; }();
-        const int a1_mode = (half || dim != 3 || getenv("GSB200_SWEEP")) ? 0 : (a1_env >= 0 ? a1_env : ((dL.q * 8) % 32 == 0 ? 1 : 2));
+        const int a1_mode = (half || dim != 3 || getenv("GSB200_SWEEP")) ? 0 : (a1_env >= 0 ? a1_env : 1);
         const bool a1_blk = a1_mode == 1, a1_gather = a1_mode == 2;
         // experiment (GSB200_SYMH=1): symmetric form + blocked A1: store the symmetric first-sweep components for delta0 >= 0 only, read mirrored
         static const bool symh_env = [] { const char *e = getenv("GSB200_SYMH"); return e && atoi(e) > 0; }();   // measured slower (profiles/): opt-in
@@ -708,6 +715,8 @@ static int assemble_pass(gsb200_assembler *a)
                     A.first = d.d_first; A.nexit = d.d_nexit; A.tab = d.d_tab; A.tabl = d.d_tabl; A.q = d.q; A.p = d.p; A.fin = Fa;
                     A.out_bq = 1; A.out_od = 1; A.d_off = d.p;
                     { static const int pf = [] { const char *e = getenv("GSB200_PF"); return e ? atoi(e) : 0; }(); A.pf_dist = pf; }
+                    { static const int wb = [] { const char *e = getenv("GSB200_WB"); return e ? atoi(e) : -1; }();
+                      A.wb_stores = wb >= 0 ? wb : ((dL.q * 8) % 32 != 0); }
                     return A;
                 };
                 auto account = [&](int slot, const SweepArgs &A, const std::vector<int> &seg, i64 fpp, double nin, double nout, i64 npairs_out) {

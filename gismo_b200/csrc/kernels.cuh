@@ -427,6 +427,8 @@ struct SweepArgs {
     // window kernel, mirrored reads: inner = (.., delta slot, t) with mir_q points per slot and mir_w slots; the mirrored pair of
     // (outer, slot) is (outer + slot - mir_p, 2 mir_p - slot), valid while 0 <= outer + slot - mir_p < mir_n
     int mir_q, mir_w, mir_p, mir_n;
+    int wb_stores;               // window kernel: plain write-back stores instead of streaming ones (pieces that do not fill 32-byte sectors
+                                 // must wait in L2 for their neighbours, else DRAM read-modify-writes them)
     i64 ncol; i64 ninner;
     // tensor-map TMA variant: which box coordinate carries the tile start, the span, the outer index
     int tm_rank, tm_dim_inner, tm_dim_e, tm_e_mul, tm_dim_outer;
@@ -624,6 +626,8 @@ GSB_DEVICE void final_canonical(const FinalArgs &F, const FinalCtx &c, int fun, 
     else if (F.fixed) final_slow(F, c, fun, rec, dL, val);
 }
 
+GSB_DEVICE void st_out(double *p, double v, int wb) { if (wb) *p = v; else st_stream(p, v); }
+
 template <class T, int NG> GSB_CX unsigned group_mask(int gi)
 {
     unsigned m = 0;
@@ -657,6 +661,9 @@ template <int N> static inline void cp_async_wait() {}
 template <int P1, class T, unsigned OMASK, int NS> GSB_CX int window_smem() { return NS * P1 * used_count<T>(OMASK) * 128 * 8 + NS * 4 * P1 * P1 * 16; }
 template <int P1, class T, unsigned OMASK, int NS> GSB_CX int window_minb() { if (NS == 0) return 3; int n = 220 * 1024 / window_smem<P1, T, OMASK, NS>(); return n > 4 ? 4 : (n < 1 ? 1 : n); }
 
+#ifndef GSB_WINDOW_HOLD
+#define GSB_WINDOW_HOLD(P1_) (((P1_) * 8) % 32 != 0)
+#endif
 template <int P1, class T, unsigned OMASK, bool FINAL, int NS>
 GSB_GLOBAL void
 #ifndef GSB200_EMULATE
@@ -703,6 +710,17 @@ k_sweepw(const GSB_GRID_CONSTANT SweepArgs A)
         for (int b = 0; b < P1; ++b)
 #pragma unroll
             for (int g = 0; g < NG; ++g) acc[a][b][g] = 0.0;
+    // HOLD: completed pairs with a negative delta wait for their owner's exit (hold[k][j]: window position k, delta -j) so that a
+    // whole row of 2p+1 deltas is stored at once.  Needed when a span's q points do not fill 32-byte sectors: pieces stored one
+    // span apart outlive the L2 and are read-modify-written in DRAM (profiles/r01b_layout_experiments.txt)
+    constexpr bool HOLD = GSB_WINDOW_HOLD(P1);
+    double hold[HOLD ? P1 : 1][HOLD ? P1 : 1][NG];
+#pragma unroll
+    for (int k = 0; k < (HOLD ? P1 : 1); ++k)
+#pragma unroll
+        for (int j = 0; j < (HOLD ? P1 : 1); ++j)
+#pragma unroll
+            for (int g = 0; g < NG; ++g) hold[k][j][g] = 0.0;
     int f0 = A.first[e_begin];
     i64 rec[P1];      // FINAL: packed (colptr << 2 | flag) of the window's functions as owners, 0 = not ours
 #pragma unroll
@@ -835,6 +853,58 @@ k_sweepw(const GSB_GRID_CONSTANT SweepArgs A)
         }
         // exits: f0 leaves the window, its pairs are complete
         for (int x = 0; x < nx; ++x) {
+            if constexpr (HOLD) {
+                // whole-row emission: the pairs (f0, f0-j) completed at earlier exits wait in hold[0][j]; together with (f0, f0+b)
+                // they are the owner's complete row of 2p+1 deltas, written in one go (contiguous across the warp's lanes)
+                if (FINAL) {
+                    if (rec[0]) {
+                        const int flag = (int)(rec[0] & 3);
+                        if (flag == 3) {
+#pragma unroll
+                            for (int j = 1; j < P1; ++j) st_stream(A.fin.values + (rec[0] >> 2) + (i64)(fin_pl - j) * fin_ww + fin_c0, hold[0][j][0]);
+#pragma unroll
+                            for (int b = 0; b < P1; ++b) st_stream(A.fin.values + (rec[0] >> 2) + (i64)(b + fin_pl) * fin_ww + fin_c0, acc[0][b][0]);
+                        } else {
+                            const int dlo = A.fin.plo[A.fin.L][f0] - f0, dhi = A.fin.phi[A.fin.L][f0] - f0;     // co-occurring partners only
+#pragma unroll
+                            for (int j = 1; j < P1; ++j)
+                                if (-j >= dlo) {
+                                    if (flag == 1) final_canonical(A.fin, fc, f0, rec[0], -j, (fin_pl - j) * fin_w1 + fc.r_low, hold[0][j][0]);
+                                    else final_slow(A.fin, fc, f0, rec[0], -j, hold[0][j][0]);
+                                }
+#pragma unroll
+                            for (int b = 0; b < P1; ++b)
+                                if (b <= dhi) {
+                                    if (flag == 1) final_canonical(A.fin, fc, f0, rec[0], b, (b + fin_pl) * fin_w1 + fc.r_low, acc[0][b][0]);
+                                    else final_slow(A.fin, fc, f0, rec[0], b, acc[0][b][0]);
+                                }
+                        }
+                    }
+                } else if (f0 >= x_min && f0 < x_max) {
+                    const i64 o0 = (i64)f0 * A.out_fs + base_d;
+                    static_for<0, NOUT>([&](auto oc_) {
+                        constexpr int o = decltype(oc_)::value;
+                        if constexpr ((OMASK >> o) & 1u) {
+                            constexpr int g = mask_rank(OMASK, o);
+#pragma unroll
+                            for (int j = P1 - 1; j >= 1; --j) st_out(A.out + o * A.out_cs + o0 - j * st_b, hold[0][j][g], A.wb_stores);
+#pragma unroll
+                            for (int b = 0; b < P1; ++b) st_out(A.out + o * A.out_cs + o0 + b * st_b, acc[0][b][g], A.wb_stores);
+                        }
+                    });
+                }
+                // (f0+a, f0) is complete now: it waits for its owner; then everything moves one window position down
+#pragma unroll
+                for (int k = 1; k < P1; ++k)
+#pragma unroll
+                    for (int g = 0; g < NG; ++g) hold[k][k][g] = acc[k][0][g];
+#pragma unroll
+                for (int k = 0; k < P1; ++k)
+#pragma unroll
+                    for (int j = 1; j < P1; ++j)
+#pragma unroll
+                        for (int g = 0; g < NG; ++g) hold[k][j][g] = (k + 1 < P1) ? hold[(k + 1) % P1][j][g] : 0.0;
+            } else
             if (FINAL) {
                 if (rec[0]) {          // owner f0, partners f0+b
 #pragma unroll
@@ -863,7 +933,7 @@ k_sweepw(const GSB_GRID_CONSTANT SweepArgs A)
                         if (b + x < P1)
                             static_for<0, NOUT>([&](auto oc_) {
                                 constexpr int o = decltype(oc_)::value;
-                                if constexpr ((OMASK >> o) & 1u) st_stream(A.out + o * A.out_cs + o0 + b * st_b, acc[0][b][mask_rank(OMASK, o)]);
+                                if constexpr ((OMASK >> o) & 1u) st_out(A.out + o * A.out_cs + o0 + b * st_b, acc[0][b][mask_rank(OMASK, o)], A.wb_stores);
                             });
                 }
 #pragma unroll
@@ -871,7 +941,7 @@ k_sweepw(const GSB_GRID_CONSTANT SweepArgs A)
                     if (f0 + a >= x_min && f0 + a < x_max && a + x < P1)
                         static_for<0, NOUT>([&](auto oc_) {
                             constexpr int o = decltype(oc_)::value;
-                            if constexpr (((OMASK >> o) & 1u) && !T::out_sym(o)) st_stream(A.out + o * A.out_cs + o0 + a * st_a, acc[a][0][mask_rank(OMASK, o)]);
+                            if constexpr (((OMASK >> o) & 1u) && !T::out_sym(o)) st_out(A.out + o * A.out_cs + o0 + a * st_a, acc[a][0][mask_rank(OMASK, o)], A.wb_stores);
                         });
                 }
             }
