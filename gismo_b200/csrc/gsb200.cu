@@ -1229,6 +1229,14 @@ static int cg_alloc(gsb200_assembler *a)
     return 0;
 }
 
+int gsb200_spmv_device(gsb200_assembler *a, const double *x_dev, double *y_dev)
+{
+    if (!a || !x_dev || !y_dev) return GSB200_EINVAL;
+    if (!a->assembled) { set_error("spmv before assemble"); return GSB200_ESTATE; }
+    GSB_TRY(select_device(a->device));
+    return launch_spmv(a, x_dev, y_dev);
+}
+
 int gsb200_spmv_host(gsb200_assembler *a, const double *x, double *y)
 {
     if (!a || !x || !y) return GSB200_EINVAL;

@@ -85,3 +85,58 @@ def merge_rank_matrices(parts, c0: int, n: int) -> Tuple[np.ndarray, np.ndarray,
             values[new_outer[c]:new_outer[c + 1]] = val[a:b]
             done[c] = True
     return new_outer.astype(np.int32), inner, values
+
+
+class DistributedCG:
+    """Jacobi-preconditioned CG on the device-resident, column-partitioned matrix (mirrors
+    gsSparseSolver<>::CGDiagonal, gsSparseSolver.h:71-72).  Every rank keeps full-length vectors; the matrix product is the
+    library's warp-per-row SpMV over the columns the rank owns (gsb200_spmv_device) followed by ONE all_reduce of y, dot products
+    are local (replicated vectors).  world_size 1 works without a process group."""
+
+    def __init__(self, assembler, device: int, group: Optional[dist.ProcessGroup] = None, reduced: bool = True):
+        """reduced: the coupled columns (multi-patch) already hold the all-reduced values on every rank that stores them
+        (reduce_coupled_columns was called); irrelevant for single-patch slabs."""
+        self.A, self.device, self.group = assembler, device, group
+        self.n = assembler.problem.nfree
+        self.multi = dist.is_initialized() and dist.get_world_size(group) > 1
+        v = assembler.device_view()
+        outer = device_tensor(v.outer, self.n + 1, torch.int64, device)
+        inner = device_tensor(v.inner, int(v.nnz), torch.int32, device)
+        vals = device_tensor(v.values, int(v.nnz), torch.float64, device)
+        # diagonal: entry (c, c) of every owned column; summed over ranks (coupled columns hold partial sums before the exchange,
+        # full sums after it on every rank that patterns them: divide by the number of ranks storing the column)
+        cols = torch.repeat_interleave(torch.arange(self.n, device=outer.device), (outer[1:] - outer[:-1]))
+        on_diag = inner.to(torch.int64) == cols
+        diag = torch.zeros(self.n, dtype=torch.float64, device=outer.device)
+        diag.index_add_(0, cols[on_diag], vals[on_diag])
+        holders = ((outer[1:] - outer[:-1]) > 0).to(torch.float64)
+        if self.multi:
+            dist.all_reduce(diag, group=group); dist.all_reduce(holders, group=group)
+        self.holders = torch.clamp(holders, min=1.0) if reduced else torch.ones_like(holders)
+        self.diag = diag / self.holders
+        del cols, on_diag
+
+    def matvec(self, x: torch.Tensor) -> torch.Tensor:
+        from .capi import check
+        y = torch.empty_like(x)
+        check(self.A.lib.gsb200_spmv_device(self.A._h, x.data_ptr(), y.data_ptr()))
+        if self.multi:
+            y /= self.holders                     # columns patterned on several ranks carry the same (already reduced) values
+            dist.all_reduce(y, group=self.group)
+        return y
+
+    def solve(self, b: torch.Tensor, max_iter: int = 1000, tol: float = 1e-10):
+        x = torch.zeros_like(b); r = b.clone(); z = r / self.diag; p = z.clone()
+        rz = torch.dot(r, z); bb = torch.dot(b, b); it = 0
+        while it < max_iter:
+            q = self.matvec(p)
+            alpha = rz / torch.dot(p, q)
+            x += alpha * p; r -= alpha * q
+            rr = torch.dot(r, r)
+            it += 1
+            if float(rr) <= tol * tol * float(bb):
+                break
+            z = r / self.diag
+            rz2 = torch.dot(r, z)
+            p = z + (rz2 / rz) * p; rz = rz2
+        return x, it, float(torch.sqrt(torch.dot(r, r) / bb))

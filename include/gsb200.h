@@ -212,6 +212,10 @@ int gsb200_assemble_host(const gsb200_problem *problem, int device, int64_t *nnz
    preconditioned CG mirroring gsSparseSolver<>::CGDiagonal (gsSparseSolver.h:71-72).
    x/y/b are host pointers of length nfree. */
 int gsb200_spmv_host(gsb200_assembler *a, const double *x, double *y);
+/* Same product on DEVICE vectors of length nfree, asynchronously on the assembler's stream: y[c] = sum over the stored entries
+   of column c (= row c, the forms are symmetric), 0 for columns this rank does not own.  With one rank per GPU the full
+   product is the sum of the ranks' y (one all_reduce, gismo_b200/distributed.py::DistributedCG; SURVEY 8e "CG consumer"). */
+int gsb200_spmv_device(gsb200_assembler *a, const double *x_dev, double *y_dev);
 int gsb200_cg_host(gsb200_assembler *a, const double *b, double *x, int max_iter,
                    double tol, int *iters, double *rel_residual);
 
