@@ -1237,6 +1237,16 @@ int gsb200_spmv_device(gsb200_assembler *a, const double *x_dev, double *y_dev)
     return launch_spmv(a, x_dev, y_dev);
 }
 
+int gsb200_diag_device(gsb200_assembler *a, double *d_dev)
+{
+    if (!a || !d_dev) return GSB200_EINVAL;
+    if (!a->assembled) { set_error("diag before assemble"); return GSB200_ESTATE; }
+    GSB_TRY(select_device(a->device));
+    const int n = a->nfree;
+    GSB_LAUNCH(k_diag, dim3((n + 127) / 128), dim3(128), a->stream, n, a->d_colptr, a->d_inner, a->d_values, d_dev);
+    return GSB200_OK;
+}
+
 int gsb200_spmv_host(gsb200_assembler *a, const double *x, double *y)
 {
     if (!a || !x || !y) return GSB200_EINVAL;

@@ -99,22 +99,21 @@ class DistributedCG:
         self.A, self.device, self.group = assembler, device, group
         self.n = assembler.problem.nfree
         self.multi = dist.is_initialized() and dist.get_world_size(group) > 1
+        from .capi import check
         v = assembler.device_view()
         outer = device_tensor(v.outer, self.n + 1, torch.int64, device)
-        inner = device_tensor(v.inner, int(v.nnz), torch.int32, device)
-        vals = device_tensor(v.values, int(v.nnz), torch.float64, device)
-        # diagonal: entry (c, c) of every owned column; summed over ranks (coupled columns hold partial sums before the exchange,
-        # full sums after it on every rank that patterns them: divide by the number of ranks storing the column)
-        cols = torch.repeat_interleave(torch.arange(self.n, device=outer.device), (outer[1:] - outer[:-1]))
-        on_diag = inner.to(torch.int64) == cols
-        diag = torch.zeros(self.n, dtype=torch.float64, device=outer.device)
-        diag.index_add_(0, cols[on_diag], vals[on_diag])
-        holders = ((outer[1:] - outer[:-1]) > 0).to(torch.float64)
+        stored = (outer[1:] - outer[:-1]) > 0
+        # diagonal of the columns this rank stores (library kernel: no nnz-sized temporaries), summed over the ranks; coupled
+        # columns hold the full sums on every rank that patterns them after the exchange: divide by the number of holders
+        diag = torch.empty(self.n, dtype=torch.float64, device=outer.device)
+        check(assembler.lib.gsb200_diag_device(assembler._h, diag.data_ptr()))
+        diag = torch.where(stored, diag, torch.zeros_like(diag))
+        holders = stored.to(torch.float64)
         if self.multi:
             dist.all_reduce(diag, group=group); dist.all_reduce(holders, group=group)
         self.holders = torch.clamp(holders, min=1.0) if reduced else torch.ones_like(holders)
         self.diag = diag / self.holders
-        del cols, on_diag
+        self.diag = torch.where(self.diag == 0, torch.ones_like(self.diag), self.diag)
 
     def matvec(self, x: torch.Tensor) -> torch.Tensor:
         from .capi import check

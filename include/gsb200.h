@@ -216,6 +216,9 @@ int gsb200_spmv_host(gsb200_assembler *a, const double *x, double *y);
    of column c (= row c, the forms are symmetric), 0 for columns this rank does not own.  With one rank per GPU the full
    product is the sum of the ranks' y (one all_reduce, gismo_b200/distributed.py::DistributedCG; SURVEY 8e "CG consumer"). */
 int gsb200_spmv_device(gsb200_assembler *a, const double *x_dev, double *y_dev);
+/* Diagonal of the stored columns into a DEVICE vector of length nfree (1.0 where the rank stores no diagonal entry):
+   the Jacobi preconditioner of the CG consumer. */
+int gsb200_diag_device(gsb200_assembler *a, double *d_dev);
 int gsb200_cg_host(gsb200_assembler *a, const double *b, double *x, int max_iter,
                    double tol, int *iters, double *rel_residual);
 

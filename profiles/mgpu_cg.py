@@ -19,8 +19,20 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--check", action="store_true"); ap.add_argument("--degree", type=int, default=4); ap.add_argument("--nelem", type=int, default=96)
     ap.add_argument("--iters", type=int, default=50)
+    ap.add_argument("--cube", type=int, default=0, help="total elements per direction of ONE cube split over the ranks (strong); 0: nelem^3 per rank (weak)")
+    ap.add_argument("--as-rank", type=str, default="", help="debug: 'r/w' = build and assemble the share of rank r of w in this single process (no CG)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.as_rank:
+        r, w = (int(v) for v in a.as_rank.split("/"))
+        prog = g.expr_compile("3*pi^2*sin(pi*x)*sin(pi*y)*sin(pi*z)")
+        t0 = time.time(); pb = host.poisson_box_problem(3, a.degree, [a.cube] * 3, prog, rank=r, nranks=w); print("host problem", time.time() - t0, "s, dofs", pb.nfree, flush=True)
+        A = g.DeviceAssembler(pb, device=0); print("created", flush=True)
+        nnz = A.buildPattern(); print("pattern nnz", nnz, torch.cuda.mem_get_info(), flush=True)
+        for _ in range(4):
+            A.assemble()
+        tm = A.timings(); print("assemble ms", tm.total_ms, "chunks", tm.nchunks, [tm.geometry_ms, list(tm.sweep_ms), tm.rhs_ms], torch.cuda.mem_get_info(), flush=True)
+        return
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -54,7 +66,9 @@ def main():
     else:
         m = a.nelem
         t0 = time.time()
-        pb = host.poisson_box_problem(3, a.degree, [m, m, m * world], prog, rank=rank, nranks=world)
+        shape = [a.cube] * 3 if a.cube else [m, m, m * world]
+        pb = host.poisson_box_problem(3, a.degree, shape, prog, rank=rank, nranks=world)
+        t_host = time.time() - t0
         A = g.DeviceAssembler(pb, device=local, stream=stream)
         nnz = A.buildPattern()
         for _ in range(3):
@@ -73,7 +87,7 @@ def main():
         x, it, res = cg.solve(b, max_iter=a.iters, tol=1e-30)
         torch.cuda.synchronize(); t_cg = time.time() - t1
         if rank == 0:
-            print(json.dumps({"config": f"config5 shape: 3-D cube p={a.degree}, {m}x{m}x{m * world} elements", "n_gpus": world, "dofs": pb.nfree, "nnz_per_gpu": nnz,
+            print(json.dumps({"config": f"3-D cube p={a.degree}, {shape[0]}x{shape[1]}x{shape[2]} elements", "host_problem_s": t_host, "chunks": A.timings().nchunks, "n_gpus": world, "dofs": pb.nfree, "nnz_per_gpu": nnz,
                               "assemble_ms": float(ms.item()), "assembled_dofs_per_sec": pb.nfree / (float(ms.item()) * 1e-3),
                               "cg_iterations": it, "cg_ms_per_iteration": t_cg / it * 1e3, "cg_rel_residual": res}), flush=True)
         A.close()
