@@ -203,6 +203,15 @@ def test_compiled_source_term_equals_interpreter(lib):
     assert np.abs(first[3] - last[3]).max() <= 1e-14 * np.abs(first[3]).max()
 
 
+@pytest.mark.parametrize("dim,p,m,quA,quB", [(3, 2, 6, 1.0, 2), (3, 3, 5, 1.0, 2), (2, 2, 9, 2.0, 1), (3, 1, 7, 1.0, 2)])
+def test_other_quadrature_sizes(lib, dim, p, m, quA, quB):
+    """q != p+1 Gauss points per direction (quA/quB options): the generic / ring kernels on the layouts chosen for the window kernels."""
+    pb = host.poisson_box_problem(dim, p, m, g.expr_compile("1+x*y" if dim == 2 else "1+x*y-z"))
+    pb.struct.quA, pb.struct.quB = quA, quB
+    ok, msg = R.compare_csc(R.lib_assemble(lib, pb), R.oracle_assemble(pb), TOL)
+    assert ok, msg
+
+
 def test_measured_peaks_are_plausible(lib):
     pk = g.measure_peaks(0)
     assert 5 < pk["fp64_tflops"] < 100 and 500 < pk["hbm_gbs"] < 10000

@@ -84,3 +84,14 @@ def test_assemble_before_pattern_is_a_state_error(emul):
     assert emul.gsb200_create(C.byref(pb.struct), 0, C.byref(h)) == 0
     assert emul.gsb200_assemble(h) == -7
     emul.gsb200_destroy(h)
+
+
+@pytest.mark.parametrize("dim,p,m,quA,quB", [(3, 2, 4, 1.0, 2), (3, 3, 3, 1.0, 2), (2, 2, 6, 2.0, 1), (3, 1, 5, 1.0, 2)])
+def test_other_quadrature_sizes_take_the_generic_kernels(emul, dim, p, m, quA, quB):
+    """q != p+1 points per direction (gsQuadrature.h:152-171 with quA/quB options) leaves the window kernels' fast path: the generic
+    sweep must still honour the layouts chosen for them.  Checked against the C oracle (element loop)."""
+    from gismo_b200 import host
+    pb = host.poisson_box_problem(dim, p, m, R.emul_compile("1+x*y" if dim == 2 else "1+x*y-z"))
+    pb.struct.quA, pb.struct.quB = quA, quB
+    ok, msg = R.compare_csc(R.lib_assemble(emul, pb), R.oracle_assemble(pb), TOL)
+    assert ok, msg
