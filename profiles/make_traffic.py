@@ -11,11 +11,11 @@ for r in rows[hi + 1:]:
     d[r[mn]] = float(r[mv].replace(',', ''))
 L = list(launch.values())
 # one assembly = from a geometry kernel to the launch before the next geometry kernel
-starts = [i for i, d in enumerate(L) if 'k_geometry' in d['name']]
+starts = [i for i, d in enumerate(L) if 'k_geometry' in d['name'] or 'gsb_jit_geo' in d['name']]
 seq = L[starts[-1]:]
 def stage(d):
     n = d['name']
-    if 'k_geometry' in n: return 'geometry'
+    if 'k_geometry' in n or 'gsb_jit_geo' in n: return 'geometry'
     if 'k_vsweep' in n: return 'rhs'
     if 'TLast' in n or ', true' in n or ', 1, ' in n and 'TMass' in n: return 'sweep_last'
     if 'S1' in n: return 'sweep0'
