@@ -615,7 +615,9 @@ static int assemble_pass(gsb200_assembler *a)
         // kernels.  GSB200_A1BLK overrides.
         static const int a1_env = [] { const char *e = getenv("GSB200_A1BLK"); return e ? atoi(e) : -1; }();
         const int a1_mode = (half || dim != 3 || getenv("GSB200_SWEEP")) ? 0 : (a1_env >= 0 ? a1_env : 1);
-        const bool a1_blk = a1_mode == 1, a1_gather = a1_mode == 2;
+        // the gathered reads exist in the window kernel only (q = p+1 points); any other rule keeps the blocked layout, which the
+        // generic kernels address through the same strides
+        const bool a1_gather = a1_mode == 2 && dim == 3 && d1.q == d1.p + 1, a1_blk = a1_mode == 1 || (a1_mode == 2 && !a1_gather);
         // experiment (GSB200_SYMH=1): symmetric form + blocked A1: store the symmetric first-sweep components for delta0 >= 0 only, read mirrored
         static const bool symh_env = [] { const char *e = getenv("GSB200_SYMH"); return e && atoi(e) > 0; }();   // measured slower (profiles/): opt-in
         const int kind01 = (kind == KIND_SYM && a1_blk && symh_env) ? KIND_SYMH : kind;
