@@ -620,7 +620,7 @@ static int assemble_pass(gsb200_assembler *a)
         const bool a1_gather = a1_mode == 2 && dim == 3 && d1.q == d1.p + 1, a1_blk = a1_mode == 1 || (a1_mode == 2 && !a1_gather);
         // experiment (GSB200_SYMH=1): symmetric form + blocked A1: store the symmetric first-sweep components for delta0 >= 0 only, read mirrored
         static const bool symh_env = [] { const char *e = getenv("GSB200_SYMH"); return e && atoi(e) > 0; }();   // measured slower (profiles/): opt-in
-        const int kind01 = (kind == KIND_SYM && a1_blk && symh_env) ? KIND_SYMH : kind;
+        const int kind01 = (kind == KIND_SYM && a1_mode == 1 && symh_env && d0.q == d0.p + 1 && d1.q == d1.p + 1) ? KIND_SYMH : kind;   // window kernels only
         const double symh_frac = kind01 == KIND_SYMH ? (2.0 * W0 + 4.0 * (d0.p + 1)) / (double)W0 : 0.0;   // stored components per (i0, slot) on average
         const bool a2_rows = a2_rows_env && a1_mode == 0 && dim == 3 && !half;
         const i64 NI0h = half ? (i64)d0.nfun * (d0.p + 1) : NI0;     // (i0, delta0) pairs stored in A1
