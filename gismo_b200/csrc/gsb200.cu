@@ -287,6 +287,18 @@ static int build_pattern(gsb200_assembler *a)
     for (auto &P : a->patches) {
         PatArgs A; fill_pat_args(a, P, A); A.len = d_len; A.colptr = a->d_colptr; A.inner = a->d_inner; A.cursor = d_cursor; A.gneed = d_gneed;
         const i64 nt = P.nb * a->ncomp;
+#ifndef GSB200_EMULATE
+        int maxlen = a->ncomp;
+        for (int k = 0; k < P.dim; ++k) maxlen *= 2 * P.dir[k].p + 1;
+        const int stride = maxlen | 1;
+        const size_t smem = (size_t)32 * stride * sizeof(int);
+        static const bool pat_old = getenv("GSB200_PATTERN_OLD") != 0;
+        if (!pat_old && smem <= 200 * 1024) {      // coalesced fill through per-lane shared-memory rows
+            static size_t attributed = 0;
+            if (smem > attributed) { GSB_TRY(dev_check(cudaFuncSetAttribute(k_pattern_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "cudaFuncSetAttribute")); attributed = 200 * 1024; }
+            k_pattern_staged<<<(unsigned)((nt + 31) / 32), 32, smem, s>>>(A, stride); note_launch();
+        } else
+#endif
         GSB_LAUNCH(k_pattern<1>, dim3((unsigned)((nt + 127) / 128)), dim3(128), s, A);
     }
     GSB_LAUNCH(k_pat_sort, dim3((N + 127) / 128), dim3(128), s, N, d_gneed, a->d_colptr, a->d_inner, d_len);

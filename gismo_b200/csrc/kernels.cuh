@@ -1236,10 +1236,11 @@ GSB_GLOBAL void k_pat_preimages(const int *dofmap, i64 n, int nfree, int *npre)
 }
 
 // pass 0: count; pass 1: fill
+// Body of the pattern kernels for one (component, local function).  PASS 1 with `stage` != 0 writes the row indices of a column that
+// this thread owns alone into stage[0..n) (shared memory; flushed with coalesced stores by k_pattern_staged) and reports where they go.
 template <int PASS>
-GSB_GLOBAL void k_pattern(const PatArgs A)
+GSB_DEVICE void pattern_column(const PatArgs &A, i64 id, int *stage, i64 *stage_base, int *stage_n)
 {
-    const i64 id = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= A.nb * A.ncomp) return;
     const int cc = (int)(id / A.nb);
     const i64 li = id - (i64)cc * A.nb;
@@ -1299,7 +1300,8 @@ GSB_GLOBAL void k_pattern(const PatArgs A)
             for (int j0 = lo[0]; j0 <= hi[0]; ++j0) {
                 const int gj = A.dofmap[(i64)cr * A.nb + ((i64)j2 * A.n[1] + j1) * A.n[0] + j0];
                 if (gj < A.nfree) {
-                    A.inner[pos++] = gj;
+                    if (stage) stage[pos - base] = gj; else A.inner[pos] = gj;
+                    ++pos;
                     if (gj <= prev) mono = false;
                     prev = gj;
                     mask |= 1u << (j0 - i[0] + A.p[0]);
@@ -1316,7 +1318,33 @@ GSB_GLOBAL void k_pattern(const PatArgs A)
     if (mono && all_full) A.colflag[id] = 3;
     else if (mono && A.ncomp == 1) A.colflag[id] = 1;
     else { A.colflag[id] = 2; if (!mono) A.gneed[gi] = 1; }
+    if (stage) { *stage_base = base; *stage_n = (int)(pos - base); }
 }
+
+template <int PASS>
+GSB_GLOBAL void k_pattern(const PatArgs A)
+{
+    pattern_column<PASS>(A, (i64)blockIdx.x * blockDim.x + threadIdx.x, 0, 0, 0);
+}
+
+#ifndef GSB200_EMULATE
+// Fill pass with coalesced stores: one warp per block, every lane builds its column in a private shared-memory row (odd stride:
+// conflict-free), then the warp copies the 32 rows to their places in `inner` 128 bytes at a time.  The one-thread-per-column
+// version above stores 4 bytes per lane into 32 different lines per instruction (7.6 ms for 2.6 GB at config 2).
+GSB_GLOBAL void __launch_bounds__(32) k_pattern_staged(const PatArgs A, const int stride)
+{
+    extern __shared__ int pat_stage[];
+    const int lane = threadIdx.x;
+    i64 base = 0; int n = 0;
+    pattern_column<1>(A, (i64)blockIdx.x * 32 + lane, pat_stage + lane * stride, &base, &n);
+    __syncwarp();
+    for (int c = 0; c < 32; ++c) {
+        const i64 bc = __shfl_sync(0xffffffffu, base, c);
+        const int nc = __shfl_sync(0xffffffffu, n, c);
+        for (int k = lane; k < nc; k += 32) A.inner[bc + k] = pat_stage[c * stride + k];
+    }
+}
+#endif
 
 // sort (and for coupled columns deduplicate) the row indices of the flagged columns
 GSB_GLOBAL void k_pat_sort(int ncols, const unsigned char *gneed, const i64 *colptr, int *inner, unsigned long long *len)
