@@ -476,9 +476,10 @@ static int launch_window_groups(const SweepArgs &A, int nseg, stream_t s)
         const dim3 grid((unsigned)((A.ncol + 127) / 128), 1, nseg);
 #ifndef GSB200_EMULATE
         static const int ns = [] { const char *e = getenv("GSB200_WSTAGES"); return e ? atoi(e) : 2; }();
+        // ring depth: 2 stages (one span ahead) measured best, 3 kept for experiments (4 was never better: profiles/r01b_layout_experiments.txt);
+        // 0 = register double buffer
         if (ns == 0) GSB_TRY(window_launch(k_sweepw<P1, T, OMASK, FINAL, 0>, grid, 0, s, A));
-        else if (ns >= 4) GSB_TRY(window_launch(k_sweepw<P1, T, OMASK, FINAL, 4>, grid, window_smem<P1, T, OMASK, 4>(), s, A));
-        else if (ns == 3) GSB_TRY(window_launch(k_sweepw<P1, T, OMASK, FINAL, 3>, grid, window_smem<P1, T, OMASK, 3>(), s, A));
+        else if (ns >= 3) GSB_TRY(window_launch(k_sweepw<P1, T, OMASK, FINAL, 3>, grid, window_smem<P1, T, OMASK, 3>(), s, A));
         else GSB_TRY(window_launch(k_sweepw<P1, T, OMASK, FINAL, 2>, grid, window_smem<P1, T, OMASK, 2>(), s, A));
 #else
         { auto kfn = k_sweepw<P1, T, OMASK, FINAL, 3>; GSB_LAUNCH(kfn, grid, dim3(128), s, A); }
