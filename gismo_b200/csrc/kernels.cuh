@@ -713,7 +713,7 @@ k_sweepw(const GSB_GRID_CONSTANT SweepArgs A)
     // HOLD: completed pairs with a negative delta wait for their owner's exit (hold[k][j]: window position k, delta -j) so that a
     // whole row of 2p+1 deltas is stored at once.  Needed when a span's q points do not fill 32-byte sectors: pieces stored one
     // span apart outlive the L2 and are read-modify-written in DRAM (profiles/r01b_layout_experiments.txt)
-    constexpr bool HOLD = GSB_WINDOW_HOLD(P1);
+    constexpr bool HOLD = GSB_WINDOW_HOLD(P1) || FINAL;      // the final scatter always writes whole columns of deltas: one owner record per exit
     double hold[HOLD ? P1 : 1][HOLD ? P1 : 1][NG];
 #pragma unroll
     for (int k = 0; k < (HOLD ? P1 : 1); ++k)
