@@ -451,7 +451,10 @@ static int launch_sweep_i(const SweepArgs &A, int nseg, stream_t s, i64 *flops_p
 // (p+1)^2 * NG accumulators in registers.  GSB200_SWEEP=ring selects the shared-memory ring kernels instead.
 constexpr int window_ng(int P1, int NOUT)
 {
-    const int per_out = P1 * P1 + (GSB_WINDOW_HOLD(P1) ? P1 * (P1 - 1) / 2 : 0);     // accumulators (+ held pairs) per output component
+#ifndef GSB_WINDOW_NG_HOLD
+#define GSB_WINDOW_NG_HOLD(P1_) GSB_WINDOW_HOLD(P1_)
+#endif
+    const int per_out = P1 * P1 + (GSB_WINDOW_NG_HOLD(P1) ? P1 * (P1 - 1) / 2 : 0);     // accumulators (+ held pairs) per output component
     int ng = 36 / per_out; if (ng < 1) ng = 1; if (ng > NOUT) ng = NOUT;
     if (NOUT % ng != 0 && ng > 1 && NOUT % (ng - 1) == 0) --ng;                       // balanced groups
     return ng;

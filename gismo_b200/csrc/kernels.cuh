@@ -65,6 +65,9 @@ struct TermOps {
     // symmetry of the form (window kernels): an output that is symmetric under the exchange of owner and partner is stored for
     // delta >= 0 only; a (virtual) input c is backed by the stored component in_src(c) and read directly (mode 1), at the mirrored
     // pair (i + delta, -delta) (mode 2), or mirrored only where delta < 0 (mode 0, symmetric component)
+    // first sweeps store whole rows of deltas at the owner's exit for every degree (measured: S1 4.0 -> 3.55 ms at p=3; the second
+    // sweep loses as much through register pressure, so it holds pairs back only where the quadrature size demands it)
+    static GSB_CX bool whole_rows() { return false; }
     static GSB_CX bool out_sym(int) { return false; }
     static GSB_CX int in_src(int cc) { return cc; }
     static GSB_CX int in_mode(int) { return 1; }
@@ -72,6 +75,7 @@ struct TermOps {
 };
 // symmetric coefficient tensor, 3-D (Poisson): D = {00,01,02,11,12,22}
 struct T3SymS1 : TermOps<T3SymS1> { enum { NIN = 6, NOUT = 8, NT = 8 };
+    static GSB_CX bool whole_rows() { return true; }
     static GSB_CX int pk(int k) { const int v[8] = {GSB_PK(0,0,1,1), GSB_PK(1,1,1,0), GSB_PK(2,1,0,1), GSB_PK(3,3,0,0),
                                                     GSB_PK(4,2,1,0), GSB_PK(5,2,0,1), GSB_PK(6,4,0,0), GSB_PK(7,5,0,0)}; return v[k]; }
     static GSB_CX int order(int i) { const int v[8] = {1, 2, 0, 3, 4, 5, 6, 7}; return v[i]; } };
@@ -99,6 +103,7 @@ struct TLast : TermOps<TLast> { enum { NIN = 4, NOUT = 1, NT = 4 };
     static GSB_CX int pk(int k) { const int v[4] = {GSB_PK(0,0,0,0), GSB_PK(0,1,0,1), GSB_PK(0,2,1,0), GSB_PK(0,3,1,1)}; return v[k]; } };
 // general (non-symmetric) tensor, 3-D: c = 3a+b
 struct T3GenS1 : TermOps<T3GenS1> { enum { NIN = 9, NOUT = 9, NT = 9 };
+    static GSB_CX bool whole_rows() { return true; }
     static GSB_CX int pk(int k) { const int v[9] = {GSB_PK(0,0,1,1), GSB_PK(1,1,1,0), GSB_PK(2,2,1,0), GSB_PK(3,3,0,1), GSB_PK(4,4,0,0),
                                                     GSB_PK(5,5,0,0), GSB_PK(6,6,0,1), GSB_PK(7,7,0,0), GSB_PK(8,8,0,0)}; return v[k]; } };
 struct T3GenS2 : TermOps<T3GenS2> { enum { NIN = 9, NOUT = 4, NT = 9 };
@@ -106,9 +111,11 @@ struct T3GenS2 : TermOps<T3GenS2> { enum { NIN = 9, NOUT = 4, NT = 9 };
                                                     GSB_PK(1,5,1,0), GSB_PK(2,6,0,0), GSB_PK(2,7,0,1), GSB_PK(3,8,0,0)}; return v[k]; } };
 // 2-D: symmetric D = {00,01,11}; general c = 2a+b.  Outputs g = 2*(a==1)+(b==1).
 struct T2SymS1 : TermOps<T2SymS1> { enum { NIN = 3, NOUT = 4, NT = 4 };
+    static GSB_CX bool whole_rows() { return true; }
     static GSB_CX int pk(int k) { const int v[4] = {GSB_PK(0,0,1,1), GSB_PK(1,1,1,0), GSB_PK(2,1,0,1), GSB_PK(3,2,0,0)}; return v[k]; }
     static GSB_CX int order(int i) { const int v[4] = {1, 2, 0, 3}; return v[i]; } };
 struct T2GenS1 : TermOps<T2GenS1> { enum { NIN = 4, NOUT = 4, NT = 4 };
+    static GSB_CX bool whole_rows() { return true; }
     static GSB_CX int pk(int k) { const int v[4] = {GSB_PK(0,0,1,1), GSB_PK(1,1,1,0), GSB_PK(2,2,0,1), GSB_PK(3,3,0,0)}; return v[k]; } };
 // mass-type form: one scalar density, no derivatives, every direction
 struct TMass : TermOps<TMass> { enum { NIN = 1, NOUT = 1, NT = 1 };
@@ -713,7 +720,7 @@ k_sweepw(const GSB_GRID_CONSTANT SweepArgs A)
     // HOLD: completed pairs with a negative delta wait for their owner's exit (hold[k][j]: window position k, delta -j) so that a
     // whole row of 2p+1 deltas is stored at once.  Needed when a span's q points do not fill 32-byte sectors: pieces stored one
     // span apart outlive the L2 and are read-modify-written in DRAM (profiles/r01b_layout_experiments.txt)
-    constexpr bool HOLD = GSB_WINDOW_HOLD(P1) || FINAL;      // the final scatter always writes whole columns of deltas: one owner record per exit
+    constexpr bool HOLD = GSB_WINDOW_HOLD(P1) || FINAL || T::whole_rows();      // the final scatter always writes whole columns of deltas: one owner record per exit
     double hold[HOLD ? P1 : 1][HOLD ? P1 : 1][NG];
 #pragma unroll
     for (int k = 0; k < (HOLD ? P1 : 1); ++k)
