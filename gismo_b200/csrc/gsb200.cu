@@ -690,7 +690,8 @@ static int assemble_pass(gsb200_assembler *a)
                     int pgu = P.dir[0].pg1;                                   // uniform geometry degree -> unrolled kernel
                     for (int k = 1; k < dim; ++k) if (P.dir[k].pg1 != pgu) pgu = 0;
                     if (pgu > 4) pgu = 0;
-                    const dim3 gg((unsigned)((QLc + 127) / 128), dim == 3 ? (unsigned)Q1 : (unsigned)Q0, dim == 3 ? (unsigned)Q0 : 1u);
+                    static const int gblk = [] { const char *e = getenv("GSB200_GEO_BLOCK"); const int v = e ? atoi(e) : 128; return (v == 64 || v == 256) ? v : 128; }();
+                    const dim3 gg((unsigned)((QLc + gblk - 1) / gblk), dim == 3 ? (unsigned)Q1 : (unsigned)Q0, dim == 3 ? (unsigned)Q0 : 1u);
                     if (gg.y > 65535u || gg.z > 65535u) { set_error("more than 65535 quadrature points per direction"); return GSB200_EUNSUPPORTED; }
                     static const bool geo_point = [] { const char *e = getenv("GSB200_GEO"); return e && !strcmp(e, "point"); }();
                     if (!geo_point) {
@@ -698,10 +699,10 @@ static int assemble_pass(gsb200_assembler *a)
                         const bool rat = P.d_weights != 0, hot = a->form == GSB200_FORM_POISSON && G.symD;
 #ifndef GSB200_EMULATE
 #define GSB_GEOL(D_, PG_, R_, F_) { cudaKernel_t jk = (G.F && !dry_run()) ? jit_geometry_kernel(a->progs_host, a->device, D_, PG_, R_, F_) : 0; \
-                                    if (jk) { void *kargs[] = {(void *)&G}; GSB_TRY(dev_check(cudaLaunchKernel((const void *)jk, gg, dim3(128), kargs, 0, s), "launch of the compiled geometry kernel")); note_launch(); ++a->jit_launches; } \
-                                    else { auto kfn = k_geometry_line<D_, PG_, R_, F_>; GSB_LAUNCH(kfn, gg, dim3(128), s, G); } }
+                                    if (jk) { void *kargs[] = {(void *)&G}; GSB_TRY(dev_check(cudaLaunchKernel((const void *)jk, gg, dim3(gblk), kargs, 0, s), "launch of the compiled geometry kernel")); note_launch(); ++a->jit_launches; } \
+                                    else { auto kfn = k_geometry_line<D_, PG_, R_, F_>; GSB_LAUNCH(kfn, gg, dim3(gblk), s, G); } }
 #else
-#define GSB_GEOL(D_, PG_, R_, F_) { auto kfn = k_geometry_line<D_, PG_, R_, F_>; GSB_LAUNCH(kfn, gg, dim3(128), s, G); }
+#define GSB_GEOL(D_, PG_, R_, F_) { auto kfn = k_geometry_line<D_, PG_, R_, F_>; GSB_LAUNCH(kfn, gg, dim3(gblk), s, G); }
 #endif
 #define GSB_GEOL_D(D_) { if (hot && !rat && pgl == 2) GSB_GEOL(D_, 2, false, 1) else if (hot && !rat && pgl == 3) GSB_GEOL(D_, 3, false, 1) \
                          else if (hot && !rat && pgl == 4) GSB_GEOL(D_, 4, false, 1) else if (hot && rat && pgl == 3) GSB_GEOL(D_, 3, true, 1) \
@@ -710,7 +711,7 @@ static int assemble_pass(gsb200_assembler *a)
 #undef GSB_GEOL_D
 #undef GSB_GEOL
                     } else
-#define GSB_GEO(D_, P_) { auto kfn = k_geometry<D_, P_>; GSB_LAUNCH(kfn, gg, dim3(128), s, G); }
+#define GSB_GEO(D_, P_) { auto kfn = k_geometry<D_, P_>; GSB_LAUNCH(kfn, gg, dim3(gblk), s, G); }
                     if (dim == 2) { switch (pgu) { case 2: GSB_GEO(2, 2) break; case 3: GSB_GEO(2, 3) break; case 4: GSB_GEO(2, 4) break; default: GSB_GEO(2, 0) } }
                     else { switch (pgu) { case 2: GSB_GEO(3, 2) break; case 3: GSB_GEO(3, 3) break; case 4: GSB_GEO(3, 4) break; default: GSB_GEO(3, 0) } }
 #undef GSB_GEO
