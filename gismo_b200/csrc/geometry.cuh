@@ -78,8 +78,12 @@ struct GeoArgs {
 };
 // Common tail of the geometry kernels: inverse/measure of the Jacobian, quadrature weight, coefficient tensor of
 // the form and load density at one point.
-template <int DIM, int FSPEC>      // FSPEC 1: Poisson with the symmetric coefficient tensor only (no run-time form dispatch)
-GSB_DEVICE void geo_finish(const GeoArgs &A, i64 id, const int (&ql)[DIM], const double (&x)[3], const double (&J)[DIM][DIM])
+// SM = false: D / F live in global memory (streaming stores); SM = true: they are a shared-memory tile of the fused
+// geometry + first-sweep kernel (fused.cuh), plain stores.
+template <bool SM> GSB_DEVICE void geo_store(double *p, double v) { if (SM) *p = v; else st_stream(p, v); }
+GSB_DEVICE void st_out(double *p, double v, int wb) { if (wb) *p = v; else st_stream(p, v); }
+template <int DIM, int FSPEC, bool SM>      // FSPEC 1: Poisson with the symmetric coefficient tensor only (no run-time form dispatch)
+GSB_DEVICE void geo_finish_to(const GeoArgs &A, double *Dp, i64 dstride, double *Fp, i64 fstride, i64 id, const int (&ql)[DIM], const double (&x)[3], const double (&J)[DIM][DIM])
 {
     double Ji[DIM][DIM], det;   // Ji[a][c] = (J^-1)[a][c]
     if (DIM == 2) {
@@ -106,12 +110,12 @@ GSB_DEVICE void geo_finish(const GeoArgs &A, i64 id, const int (&ql)[DIM], const
     }
     const double weight = hprod * wp * fabs(det);
 #ifdef GSB_JIT_SOURCE       // the source term compiled for this problem (jit.cuh) instead of the stack machine
-    if (A.F) for (int c = 0; c < A.nf; ++c) st_stream(A.F + c * A.fstride + id, weight * gsb_jit_src(c, x[0], x[1], x[2]));
+    if (Fp) for (int c = 0; c < A.nf; ++c) geo_store<SM>(Fp + c * fstride + id, weight * gsb_jit_src(c, x[0], x[1], x[2]));
 #else
-    if (A.F) for (int c = 0; c < A.nf; ++c) st_stream(A.F + c * A.fstride + id, weight * program_eval(A.prog[c], x[0], x[1], x[2]));
+    if (Fp) for (int c = 0; c < A.nf; ++c) geo_store<SM>(Fp + c * fstride + id, weight * program_eval(A.prog[c], x[0], x[1], x[2]));
 #endif
-    if (!A.D) return;
-    if (FSPEC != 1 && A.form == GSB200_FORM_MASS) { A.D[id] = weight; return; }
+    if (!Dp) return;
+    if (FSPEC != 1 && A.form == GSB200_FORM_MASS) { Dp[id] = weight; return; }
     double G[DIM][DIM];   // (J^-1 J^-T)_ab
 #pragma unroll
     for (int a = 0; a < DIM; ++a)
@@ -127,14 +131,14 @@ GSB_DEVICE void geo_finish(const GeoArgs &A, i64 id, const int (&ql)[DIM], const
 #pragma unroll
         for (int a = 0; a < DIM; ++a)
 #pragma unroll
-            for (int b = a; b < DIM; ++b) st_stream(A.D + (c++) * A.dstride + id, weight * G[a][b]);
+            for (int b = a; b < DIM; ++b) geo_store<SM>(Dp + (c++) * dstride + id, weight * G[a][b]);
         return;
     }
     if (A.form == GSB200_FORM_POISSON) {
 #pragma unroll
         for (int a = 0; a < DIM; ++a)
 #pragma unroll
-            for (int b = 0; b < DIM; ++b) A.D[(a * DIM + b) * A.dstride + id] = weight * G[a][b];
+            for (int b = 0; b < DIM; ++b) Dp[(a * DIM + b) * dstride + id] = weight * G[a][b];
         return;
     }
     // elasticity block (row comp r = brow carried by the partner/test function, col comp c = bcol by the owner):
@@ -153,100 +157,24 @@ GSB_DEVICE void geo_finish(const GeoArgs &A, i64 id, const int (&ql)[DIM], const
 #pragma unroll
         for (int b = 0; b < DIM; ++b) {
             const double E = A.lambda * Jr[b] * Jc[a] + A.mu * (Jc[b] * Jr[a] + (r == cc ? G[b][a] : 0.0));
-            A.D[(a * DIM + b) * A.dstride + id] = weight * E;
+            Dp[(a * DIM + b) * dstride + id] = weight * E;
         }
 }
 
-#ifndef GSB_JIT_SOURCE
-// Thread = one point of the last direction (fastest in memory), blockIdx.y/z = the other
-// directions.  PG = geometry degree + 1 when equal in all directions (loops unrolled, 1-D values
-// in registers) or 0 for the generic run-time loop.
-template <int DIM, int PG>
-GSB_GLOBAL void k_geometry(const GeoArgs A)
+template <int DIM, int FSPEC>
+GSB_DEVICE void geo_finish(const GeoArgs &A, i64 id, const int (&ql)[DIM], const double (&x)[3], const double (&J)[DIM][DIM])
 {
-    const int qlast = blockIdx.x * blockDim.x + threadIdx.x;
-    if (qlast >= A.qn[DIM - 1]) return;
-    int ql[DIM];   // global 1-D point index per direction
-    i64 id;
-    ql[DIM - 1] = qlast + A.qoff[DIM - 1];
-    if (DIM == 3) { ql[1] = blockIdx.y + A.qoff[1]; ql[0] = blockIdx.z + A.qoff[0]; id = ((i64)blockIdx.z * A.qn[1] + blockIdx.y) * A.qn[DIM - 1] + qlast; }
-    else { ql[0] = blockIdx.y + A.qoff[0]; id = (i64)blockIdx.y * A.qn[DIM - 1] + qlast; }
-    constexpr int PGM = PG ? PG : (GSB_MAXP + 1);
-    int pg1[DIM], gf[DIM];
-    double2 b[DIM][PGM];
-#pragma unroll
-    for (int k = 0; k < DIM; ++k) {
-        pg1[k] = PG ? PG : A.pg1[k];
-        gf[k] = A.gfirst[k][ql[k]];
-#pragma unroll
-        for (int a = 0; a < PGM; ++a) if (a < pg1[k]) b[k][a] = ld_keep2(A.gtab[k] + (i64)ql[k] * pg1[k] + a);
-    }
-    // tensor-product sum over the (pg+1)^d active control points
-    double W = 0.0, dW[DIM], xn[DIM], dxn[DIM][DIM];   // dxn[a][c] = d(x_c numerator)/d xi_a
-#pragma unroll
-    for (int a = 0; a < DIM; ++a) { dW[a] = 0.0; xn[a] = 0.0;
-#pragma unroll
-        for (int c = 0; c < DIM; ++c) dxn[a][c] = 0.0; }
-    const bool rational = A.weights != 0;
-    const int n2 = DIM == 3 ? pg1[DIM - 1] : 1;
-#pragma unroll
-    for (int a2 = 0; a2 < (DIM == 3 ? PGM : 1); ++a2) {
-        if (a2 >= n2) break;
-#pragma unroll
-        for (int a1 = 0; a1 < PGM; ++a1) {
-            if (a1 >= pg1[1]) break;
-            const double2 b1 = b[1][a1];
-            const double2 b2 = DIM == 3 ? b[DIM - 1][a2] : make_double2(1.0, 0.0);
-            const double v12 = b1.x * b2.x, d1 = b1.y * b2.x, d2 = b1.x * b2.y;
-            const i64 row = DIM == 3 ? ((i64)(gf[DIM - 1] + a2) * A.ngeo[1] + (gf[1] + a1)) * A.ngeo[0] + gf[0]
-                                     : (i64)(gf[1] + a1) * A.ngeo[0] + gf[0];
-#pragma unroll
-            for (int a0 = 0; a0 < PGM; ++a0) {
-                if (a0 >= pg1[0]) break;
-                const i64 idx = row + a0;
-                double dv[3];
-                double v = b[0][a0].x * v12;
-                dv[0] = b[0][a0].y * v12; dv[1] = b[0][a0].x * d1; dv[2] = b[0][a0].x * d2;
-                if (rational) {
-                    const double wt = A.weights[idx];
-                    v *= wt; dv[0] *= wt; dv[1] *= wt; dv[2] *= wt;
-                    W += v;
-#pragma unroll
-                    for (int kk = 0; kk < DIM; ++kk) dW[kk] += dv[kk];
-                }
-#pragma unroll
-                for (int c = 0; c < DIM; ++c) {
-                    const double C = ld_keep(A.coefs + (i64)c * A.ngeo_total + idx);
-                    xn[c] = fma(v, C, xn[c]);
-#pragma unroll
-                    for (int kk = 0; kk < DIM; ++kk) dxn[kk][c] = fma(dv[kk], C, dxn[kk][c]);
-                }
-            }
-        }
-    }
-    if (!rational) W = 1.0;
-    double x[3] = {0.0, 0.0, 0.0}, J[DIM][DIM];   // J[c][a] = d x_c / d xi_a
-    if (rational) {
-        for (int c = 0; c < DIM; ++c) {
-            x[c] = xn[c] / W;
-            for (int a = 0; a < DIM; ++a) J[c][a] = (dxn[a][c] * W - xn[c] * dW[a]) / (W * W);
-        }
-    } else {
-        for (int c = 0; c < DIM; ++c) { x[c] = xn[c]; for (int a = 0; a < DIM; ++a) J[c][a] = dxn[a][c]; }
-    }
-    geo_finish<DIM, 0>(A, id, ql, x, J);
+    geo_finish_to<DIM, FSPEC, false>(A, A.D, A.dstride, A.F, A.fstride, id, ql, x, J);
 }
 
-#endif
-
-// K0, line-factorised (default).  All threads of a block share the quadrature indices of the leading
+// K0, line-factorised.  All threads of a block share the quadrature indices of the leading
 // directions and differ only in the LAST one, so the tensor-product sum over the geometry's control points is
 // split: the block first contracts the leading directions into "line coefficients"
 //   E[a_L][field][kind] = sum_{a_0(,a_1)} B^(kind)(q_0(,q_1)) C_field[a_0(,a_1), a_L],  kind = value, d/dxi_0 (, d/dxi_1)
 // (shared memory, a few hundred FMAs per block), then every thread finishes with a short 1-D sum over the
 // (geometry degree + 1) functions of the last direction.  Fields = the geoDim coordinates (times the weight
-// for a rational geometry) and the weight itself.  Same map data as k_geometry (gsGeometry.hpp:557-564,
-// gsRationalBasis.h:481-520, gsFunction.hpp:702-751), ~5x fewer FP64 operations per point at degree 1-3.
+// for a rational geometry) and the weight itself (gsGeometry.hpp:557-564, gsRationalBasis.h:481-520,
+// gsFunction.hpp:702-751), ~5x fewer FP64 operations per point at degree 1-3 than the per-point tensor sum.
 #define GSB_GEO_MAXA 48
 #ifndef GSB200_EMULATE
 #define GSB_SHARED __shared__

@@ -1,6 +1,6 @@
 // gsb200.cu — host orchestration + C ABI (include/gsb200.h) of the B200 assembly path.
 // Compiled by nvcc for sm_100a into gismo_b200/csrc/libgsb200.so.  No torch, no Eigen.
-#include "kernels.cuh"
+#include "launch.h"
 #include <algorithm>
 #include <cstdarg>
 #include <string>
@@ -12,23 +12,35 @@
 
 #ifndef GSB200_EMULATE
 #include "jit.cuh"
-#else
-namespace gsb { struct HostProgram { std::vector<int> ops; std::vector<double> consts; }; }
+#include <mutex>
+#include <set>
 #endif
 
 namespace gsb {
 
 static thread_local char g_err[1024] = "";
-static int g_launches = 0;
+static thread_local int g_launches = 0;      // per host thread: two threads driving two assemblers do not see each other's planning pass
 void set_error(const char *fmt, ...)
 {
     va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
 }
 void note_launch() { ++g_launches; }
-static bool g_dry = false;
+static thread_local bool g_dry = false;
 bool dry_run() { return g_dry; }
+#ifndef GSB200_EMULATE
+int grant_dynamic_smem(const void *kfn, size_t smem)
+{
+    if (smem <= 48 * 1024) return 0;
+    static std::mutex mu; static std::set<std::pair<int, const void *>> granted;       // per (device, kernel)
+    int dev = 0; cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    if (granted.count({dev, kfn})) return 0;
+    GSB_TRY(dev_check(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "cudaFuncSetAttribute"));
+    granted.insert({dev, kfn});
+    return 0;
+}
+#endif
 
-#define GSB_TRY(expr) do { int rc_ = (expr); if (rc_) return rc_; } while (0)
 
 // Gauss-Legendre rule on [-1,1] (the reference tabulates the same numbers to 30 digits,
 // gsGaussRule.hpp:218-547): Newton on P_n in long double, rounded to double.
@@ -162,7 +174,8 @@ struct PatchDev {
     int *d_dofmap = 0; double *d_coefs = 0, *d_weights = 0;
     unsigned char *d_colflag = 0; unsigned *d_st = 0; int nrun = 1; i64 *d_ownrec = 0;
     int own_lo = 0, own_hi = 0;     // owner range along the last direction on this rank
-    void release() { for (int k = 0; k < 3; ++k) dir[k].release(); dev_free(d_dofmap); dev_free(d_coefs); dev_free(d_weights); dev_free(d_colflag); dev_free(d_st); dev_free(d_ownrec); }
+    double *d_lc = 0;               // line coefficients of the geometry (fused.cuh, k_line_coefs), 0: fused first sweep not available
+    void release() { for (int k = 0; k < 3; ++k) dir[k].release(); dev_free(d_dofmap); dev_free(d_coefs); dev_free(d_weights); dev_free(d_colflag); dev_free(d_st); dev_free(d_ownrec); dev_free(d_lc); }
 };
 
 } // namespace gsb
@@ -294,8 +307,7 @@ static int build_pattern(gsb200_assembler *a)
         const size_t smem = (size_t)32 * stride * sizeof(int);
         static const bool pat_old = getenv("GSB200_PATTERN_OLD") != 0;
         if (!pat_old && smem <= 200 * 1024) {      // coalesced fill through per-lane shared-memory rows
-            static size_t attributed = 0;
-            if (smem > attributed) { GSB_TRY(dev_check(cudaFuncSetAttribute(k_pattern_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "cudaFuncSetAttribute")); attributed = 200 * 1024; }
+            GSB_TRY(grant_dynamic_smem((const void *)k_pattern_staged, 200 * 1024));
             k_pattern_staged<<<(unsigned)((nt + 31) / 32), 32, smem, s>>>(A, stride); note_launch();
         } else
 #endif
@@ -344,205 +356,10 @@ static int build_pattern(gsb200_assembler *a)
     return 0;
 }
 
-// ------------------------------------------------------------------ sweep dispatch
-constexpr int pick_is(int P1, int NOUT)
-{
-    int best = 1;
-    for (int d = 1; d <= P1; ++d) if (P1 % d == 0 && d * P1 * NOUT <= 40) best = d;
-    return best;
-}
-template <class T> constexpr int n_has() { int n = 0; for (int o = 0; o < T::NOUT; ++o) for (int b = 0; b < 2; ++b) if (T::has(o, b)) ++n; return n; }
-template <class T> constexpr int n_first() { int n = 0; for (int k = 0; k < T::NT; ++k) if (T::first(k)) ++n; return n; }
-
-// Host description of a sweep's input array as a (<=5-D) tensor for tiled TMA; dims fastest first.
-// box_kind per dim: 0 -> 1, 1 -> TC (column tile), 2 -> NQ (points of a span), 3 -> NIN (all components)
-struct TmapDesc { int rank; unsigned long long dims[5]; unsigned long long strides[4]; int box_kind[5]; bool valid; };
-
-#ifndef GSB200_EMULATE
-static bool encode_tmap(TensorMapBlob *out, const void *base, const TmapDesc &d, int TC, int NQ, int NIN)
-{
-    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static encode_fn fn = 0; static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void *p = 0; cudaDriverEntryPointQueryResult qr;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess) fn = (encode_fn)p;
-    }
-    if (!fn || !d.valid || ((size_t)base & 15)) return false;
-    cuuint64_t dims[5], strides[4]; cuuint32_t box[5], estr[5];
-    for (int i = 0; i < d.rank; ++i) {
-        dims[i] = d.dims[i]; estr[i] = 1;
-        box[i] = d.box_kind[i] == 1 ? TC : d.box_kind[i] == 2 ? NQ : d.box_kind[i] == 3 ? NIN : 1;
-        if (box[i] > 256 || dims[i] == 0 || dims[i] > 0xffffffffull) return false;
-        if (i && ((d.strides[i - 1] & 15) || d.strides[i - 1] >= (1ull << 40))) return false;
-        if (i) strides[i - 1] = d.strides[i - 1];
-    }
-    if ((box[0] * 8) & 15) return false;
-    static_assert(sizeof(CUtensorMap) == sizeof(TensorMapBlob), "tensor map size");
-    return fn((CUtensorMap *)out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, d.rank, const_cast<void *>(base), dims, strides, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-#endif
-
-// Can the TMA-pipelined variant serve this sweep?  cp.async.bulk needs 16-byte aligned
-// addresses and sizes, i.e. even strides/extents in doubles; otherwise the generic kernel runs.
-static bool tma_ok(const SweepArgs &A, bool final_stage)
-{
-#ifdef GSB200_EMULATE
-    (void)A; (void)final_stage; return false;
-#else
-    const bool disabled = getenv("GSB200_NO_TMA") != 0;
-    if (disabled) return false;
-    auto even = [](i64 v) { return (v & 1) == 0; };
-    if (!even(A.in_cs) || !even(A.in_es) || !even(A.in_os) || ((size_t)A.in & 15)) return false;
-    if (final_stage) return A.in_ts == 1 && A.in_is == A.q && (even(A.q) || even(A.ninner));
-    return A.in_is == 1 && even(A.in_ts) && even(A.ninner);
-#endif
-}
-
-template <int P1, class T, bool FINAL, int IS>
-static int launch_sweep_i(const SweepArgs &A, int nseg, stream_t s, i64 *flops_per_point, const TmapDesc &td)
-{
-    *flops_per_point = (i64)P1 * (2 * T::NT - n_first<T>() + 2 * P1 * n_has<T>());
-#ifndef GSB200_EMULATE
-    constexpr int G0 = P1 / IS, TC0 = (G0 <= 2) ? 128 : 64;
-    TensorMapBlob tmap; memset(&tmap, 0, sizeof tmap);
-    // measured on B200 (profiles/): one tiled-TMA box per span wins for the first sweep (long contiguous
-    // rows, 4.3 vs 6.2 ms) but loses to per-row bulk copies for the strided later sweeps; GSB200_TMAP=all|none overrides
-    const char *pol = getenv("GSB200_TMAP");
-    const bool want_tmap = pol ? !strcmp(pol, "all") : (td.rank == 3);
-    const bool no_tmap = !want_tmap || getenv("GSB200_NO_TMA") != 0;
-    const bool use_tmap = !no_tmap && A.q == P1 && encode_tmap(&tmap, A.in, td, TC0, P1, T::NIN);
-    if (use_tmap || tma_ok(A, FINAL)) {
-        constexpr int G = P1 / IS, TC = (G <= 2) ? 128 : 64, NQ = P1;
-        constexpr int MINB_HI = (TC * G <= 128) ? 4 : (TC * G <= 256 ? 2 : 1);
-        const size_t stage = (size_t)((NQ * T::NIN * TC + NQ * P1 * 2 + 15) / 16 * 16) * sizeof(double);
-        const char *env = getenv("GSB200_MINB");
-        const bool hi = env ? atoi(env) > 1 : (TC * G <= 128);
-        // ring depth: as many spans in flight as the shared memory left per resident CTA allows
-        const size_t budget = (size_t)200 * 1024 / (hi ? MINB_HI : 1);
-        const char *envs = getenv("GSB200_NSTAGE");
-        int nstage = (int)std::min<size_t>(envs ? (size_t)atoi(envs) : 8, budget / stage);
-        if (A.q == NQ && nstage >= 2) {
-            const size_t smem = nstage * stage + 2 * nstage * sizeof(unsigned long long);
-            const int tiles = (int)((A.ninner + TC - 1) / TC);
-            const i64 nouter = A.ncol / A.ninner;
-            void (*kfn)(const SweepArgs, const int, const int, const TensorMapBlob, const int) = hi ? k_sweep_tma<P1, T, IS, FINAL, TC, FINAL, NQ, MINB_HI>
-                                                                    : k_sweep_tma<P1, T, IS, FINAL, TC, FINAL, NQ, 1>;
-            static std::vector<const void *> attributed;
-            if (std::find(attributed.begin(), attributed.end(), (const void *)kfn) == attributed.end()) {
-                GSB_TRY(dev_check(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "cudaFuncSetAttribute"));
-                attributed.push_back((const void *)kfn);
-            }
-            if (!dry_run()) { kfn<<<dim3((unsigned)(nouter * tiles), 1, nseg), dim3(TC * G), smem, s>>>(A, tiles, nstage, tmap, use_tmap ? 1 : 0); note_launch(); }
-            return 0;
-        }
-    }
-#endif
-    dim3 grid((unsigned)((A.ncol + 127) / 128), P1 / IS, nseg);
-    auto kfn = k_sweep<P1, T, IS, FINAL>;
-    GSB_LAUNCH(kfn, grid, dim3(128), s, A);
-    return 0;
-}
-// Window kernel (default): one launch per group of output components; a group is as many outputs as keep the
-// (p+1)^2 * NG accumulators in registers.  GSB200_SWEEP=ring selects the shared-memory ring kernels instead.
-constexpr int window_ng(int P1, int NOUT)
-{
-#ifndef GSB_WINDOW_NG_HOLD
-#define GSB_WINDOW_NG_HOLD(P1_) GSB_WINDOW_HOLD(P1_)
-#endif
-    const int per_out = P1 * P1 + (GSB_WINDOW_NG_HOLD(P1) ? P1 * (P1 - 1) / 2 : 0);     // accumulators (+ held pairs) per output component
-    int ng = 36 / per_out; if (ng < 1) ng = 1; if (ng > NOUT) ng = NOUT;
-    if (NOUT % ng != 0 && ng > 1 && NOUT % (ng - 1) == 0) --ng;                       // balanced groups
-    return ng;
-}
-#ifndef GSB200_EMULATE
-template <class K> static int window_launch(K kfn, dim3 grid, size_t smem, stream_t s, const SweepArgs &A)
-{
-    static std::vector<const void *> attributed;
-    if (std::find(attributed.begin(), attributed.end(), (const void *)kfn) == attributed.end()) {
-        GSB_TRY(dev_check(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute"));
-        attributed.push_back((const void *)kfn);
-    }
-    if (!dry_run()) { kfn<<<grid, dim3(128), smem, s>>>(A); note_launch(); }
-    return 0;
-}
-#endif
-template <int P1, class T, bool FINAL, int NG, int GI>
-static int launch_window_groups(const SweepArgs &A, int nseg, stream_t s)
-{
-    if constexpr (GI * NG < T::NOUT) {
-        constexpr unsigned OMASK = group_mask<T, NG>(GI);
-        const dim3 grid((unsigned)((A.ncol + 127) / 128), 1, nseg);
-#ifndef GSB200_EMULATE
-        static const int ns = [] { const char *e = getenv("GSB200_WSTAGES"); return e ? atoi(e) : 2; }();
-        // ring depth: 2 stages (one span ahead) measured best, 3 kept for experiments (4 was never better: profiles/r01b_layout_experiments.txt);
-        // 0 = register double buffer
-        if (ns == 0) GSB_TRY(window_launch(k_sweepw<P1, T, OMASK, FINAL, 0>, grid, 0, s, A));
-        else if (ns >= 3) GSB_TRY(window_launch(k_sweepw<P1, T, OMASK, FINAL, 3>, grid, window_smem<P1, T, OMASK, 3>(), s, A));
-        else GSB_TRY(window_launch(k_sweepw<P1, T, OMASK, FINAL, 2>, grid, window_smem<P1, T, OMASK, 2>(), s, A));
-#else
-        { auto kfn = k_sweepw<P1, T, OMASK, FINAL, 3>; GSB_LAUNCH(kfn, grid, dim3(128), s, A); }
-#endif
-        return launch_window_groups<P1, T, FINAL, NG, GI + 1>(A, nseg, s);
-    }
-    return 0;
-}
-static bool use_window(const SweepArgs &A, int P1)
-{
-    static const bool ring = [] { const char *e = getenv("GSB200_SWEEP"); return e && !strcmp(e, "ring"); }();
-    return !ring && A.q == P1;
-}
-
-// owner slots per thread: the largest that keeps the accumulators in registers, or (GSB200_ISDIV=1)
-// half of it: twice the threads per column tile, half the accumulators each -> more resident warps
-template <int P1, class T, bool FINAL>
-static int launch_sweep_t(const SweepArgs &A, int nseg, stream_t s, i64 *fpp, const TmapDesc &td)
-{
-    constexpr int IS = pick_is(P1, T::NOUT);
-    if (use_window(A, P1)) {
-        *fpp = (i64)P1 * (2 * T::NT - n_first<T>() + 2 * P1 * n_has<T>());
-        return launch_window_groups<P1, T, FINAL, window_ng(P1, T::NOUT), 0>(A, nseg, s);
-    }
-    if constexpr (!FINAL && IS % 2 == 0 && IS > 1) {
-        static const char *env = getenv("GSB200_ISDIV");
-        if (env && atoi(env) > 0) return launch_sweep_i<P1, T, FINAL, IS / 2>(A, nseg, s, fpp, td);
-    }
-    return launch_sweep_i<P1, T, FINAL, IS>(A, nseg, s, fpp, td);
-}
-template <class T, bool FINAL>
-static int launch_sweep(int P1, const SweepArgs &A, int nseg, stream_t s, i64 *fpp, const TmapDesc &td)
-{
-    switch (P1) {
-    case 2: return launch_sweep_t<2, T, FINAL>(A, nseg, s, fpp, td);
-    case 3: return launch_sweep_t<3, T, FINAL>(A, nseg, s, fpp, td);
-    case 4: return launch_sweep_t<4, T, FINAL>(A, nseg, s, fpp, td);
-    case 5: return launch_sweep_t<5, T, FINAL>(A, nseg, s, fpp, td);
-    default: set_error("degree %d not supported by the sweep kernels (1..4)", P1 - 1); return GSB200_EUNSUPPORTED;
-    }
-}
-
-enum { KIND_SYM = 0, KIND_GEN = 1, KIND_MASS = 2, KIND_SYMH = 3 };   // SYMH: symmetric form with half-stored first-sweep output
-// stage: 0 = first of 3-D, 1 = middle of 3-D, 2 = last; 3 = first of 2-D
-static int dispatch_sweep(int kind, int stage, int P1, const SweepArgs &A, int nseg, stream_t s, i64 *fpp, const TmapDesc &td)
-{
-    if (kind == KIND_MASS) return stage == 2 ? launch_sweep<TMass, true>(P1, A, nseg, s, fpp, td) : launch_sweep<TMass, false>(P1, A, nseg, s, fpp, td);
-    if (stage == 2) return launch_sweep<TLast, true>(P1, A, nseg, s, fpp, td);
-    if (kind == KIND_SYMH && stage == 0) return launch_sweep<T3SymS1H, false>(P1, A, nseg, s, fpp, td);
-    if (kind == KIND_SYMH && stage == 1) return launch_sweep<T3SymS2H, false>(P1, A, nseg, s, fpp, td);
-    if (stage == 0) return kind == KIND_SYM ? launch_sweep<T3SymS1, false>(P1, A, nseg, s, fpp, td) : launch_sweep<T3GenS1, false>(P1, A, nseg, s, fpp, td);
-    if (stage == 1) return kind == KIND_SYM ? launch_sweep<T3SymS2, false>(P1, A, nseg, s, fpp, td) : launch_sweep<T3GenS2, false>(P1, A, nseg, s, fpp, td);
-    return kind == KIND_SYM ? launch_sweep<T2SymS1, false>(P1, A, nseg, s, fpp, td) : launch_sweep<T2GenS1, false>(P1, A, nseg, s, fpp, td);
-}
 static void stage_io(int kind, int stage, int *nin, int *nout)
 {
     if (kind == KIND_MASS) { *nin = 1; *nout = 1; return; }
     if (stage == 2) { *nin = 4; *nout = 1; return; }
-    if (kind == KIND_SYMH && stage == 0) { *nin = 6; *nout = 6; return; }
-    if (kind == KIND_SYMH && stage == 1) { *nin = 6; *nout = 4; return; }
     if (stage == 0) { *nin = kind == KIND_SYM ? 6 : 9; *nout = kind == KIND_SYM ? 8 : 9; return; }
     if (stage == 1) { *nin = kind == KIND_SYM ? 8 : 9; *nout = 4; return; }
     *nin = kind == KIND_SYM ? 3 : 4; *nout = 4;
@@ -622,26 +439,21 @@ static int assemble_pass(gsb200_assembler *a)
         const i64 NI0 = (i64)d0.nfun * (2 * d0.p + 1), NI1 = dim == 3 ? (i64)d1.nfun * (2 * d1.p + 1) : 1;
         const i64 n0 = d0.nfun, n1 = dim == 3 ? d1.nfun : 1;
         const i64 W0 = 2 * d0.p + 1, W1 = dim == 3 ? 2 * d1.p + 1 : 1;
-        // symmetric forms in 3-D: the first sweep keeps only delta0 >= 0, the second one mirrors its output
-        const bool half = dim == 3 && kind != KIND_GEN && getenv("GSB200_SYM") && getenv("GSB200_SWEEP");   // experiment, ring kernels only
-        static const bool a2_rows_env = [] { const char *e = getenv("GSB200_A2ROWS"); return e && atoi(e) > 0; }();
         // layout of A1 (3-D): 1 (default) = blocked by last-direction element (A1[o][i0][q1][e2][d0][t]: the second sweep reads whole runs; the
-        // first one stores q-point pieces, whole rows of deltas at a time when q points do not fill a sector, GSB_WINDOW_HOLD),
-        // 2 = A1[o][i0][d0][q1][q2] (coalesced first-sweep stores, the second sweep gathers q-point pieces), 0 = legacy mapping of the ring
-        // kernels.  GSB200_A1BLK overrides.
+        // first one stores whole rows of deltas at the owner's exit), 2 = A1[o][i0][d0][q1][q2] (coalesced first-sweep stores, the second
+        // sweep gathers q-point pieces; measured slower, profiles/r01b_layout_experiments.txt).  GSB200_A1BLK overrides.
         static const int a1_env = [] { const char *e = getenv("GSB200_A1BLK"); return e ? atoi(e) : -1; }();
-        const int a1_mode = (half || dim != 3 || getenv("GSB200_SWEEP")) ? 0 : (a1_env >= 0 ? a1_env : 1);
+        const int a1_mode = dim != 3 ? 0 : (a1_env >= 0 ? a1_env : 1);
         // the gathered reads exist in the window kernel only (q = p+1 points); any other rule keeps the blocked layout, which the
         // generic kernels address through the same strides
         const bool a1_gather = a1_mode == 2 && dim == 3 && d1.q == d1.p + 1, a1_blk = a1_mode == 1 || (a1_mode == 2 && !a1_gather);
-        // experiment (GSB200_SYMH=1): symmetric form + blocked A1: store the symmetric first-sweep components for delta0 >= 0 only, read mirrored
-        static const bool symh_env = [] { const char *e = getenv("GSB200_SYMH"); return e && atoi(e) > 0; }();   // measured slower (profiles/): opt-in
-        const int kind01 = (kind == KIND_SYM && a1_mode == 1 && symh_env && d0.q == d0.p + 1 && d1.q == d1.p + 1) ? KIND_SYMH : kind;   // window kernels only
-        const double symh_frac = kind01 == KIND_SYMH ? (2.0 * W0 + 4.0 * (d0.p + 1)) / (double)W0 : 0.0;   // stored components per (i0, slot) on average
-        const bool a2_rows = a2_rows_env && a1_mode == 0 && dim == 3 && !half;
-        const i64 NI0h = half ? (i64)d0.nfun * (d0.p + 1) : NI0;     // (i0, delta0) pairs stored in A1
+        // K0 fused into the first sweep (fused.cuh): D and F stay in shared memory.  Needs the p+1-point rule in direction 0 (window
+        // accumulators) and a geometry whose last-direction functions per column tile fit the line-coefficient buffer.
+        static const bool fuse_env = [] { const char *e = getenv("GSB200_FUSE"); return !e || atoi(e) > 0; }();
+        const bool fused = fuse_env && P.d_lc && d0.q == d0.p + 1 && dL.q == d0.q && d0.p >= 1 && d0.p <= 4 && nf <= GSB_FUSE_MAXF && (dim == 2 || a1_blk);
+        const int nfv = std::max(nf, 1);
         // doubles of workspace per last-direction quadrature point
-        i64 perq = ncD * Q0 * Q1 + no1 * NI0h * Q1 + (dim == 3 ? no2 * NI1 * NI0 : 0) + nf * Q0 * Q1 + n0 * Q1 + (dim == 3 ? n1 * n0 : 0);
+        i64 perq = (fused ? 0 : ncD * Q0 * Q1 + nf * Q0 * Q1) + no1 * NI0 * Q1 + (dim == 3 ? no2 * NI1 * NI0 : 0) + nfv * n0 * Q1 + (dim == 3 ? n1 * n0 : 0);
         i64 maxpts = limit / (perq * 8);
         const i64 minpts = (i64)(dL.p + 1) * dL.q;
         if (maxpts < minpts) { set_error("workspace limit %lld B too small: one slab of patch %zu needs %lld B", (long long)limit, ip, (long long)(perq * 8 * minpts)); return GSB200_ENOMEM; }
@@ -660,18 +472,18 @@ static int assemble_pass(gsb200_assembler *a)
             }
             double *w = (double *)a->ws;
             auto carve = [&](i64 count) { double *p = w; w += (count + 31) / 32 * 32; return p; };   // 256-byte aligned pieces
-            double *D = carve(ncD * Q0 * Q1 * QLc);
-            double *A1 = carve(no1 * NI0h * Q1 * QLc);
+            double *D = carve(fused ? 0 : ncD * Q0 * Q1 * QLc);
+            double *A1 = carve(no1 * NI0 * Q1 * QLc);
             double *A2 = carve(dim == 3 ? no2 * NI1 * NI0 * QLc : 0);
-            double *F = carve(nf * Q0 * Q1 * QLc);
-            double *V1 = carve(n0 * Q1 * QLc);
+            double *F = carve(fused ? 0 : nf * Q0 * Q1 * QLc);
+            double *V1 = carve(nfv * n0 * Q1 * QLc);
             double *V2 = carve(dim == 3 ? n1 * n0 * QLc : 0);
             const i64 npts = Q0 * Q1 * QLc;
             ++a->tm.nchunks;
 
             for (int blk = 0; blk < nblocks; ++blk) {
                 const int brow = nblocks == 1 ? 0 : blk / a->ncomp, bcol = nblocks == 1 ? 0 : blk % a->ncomp;
-                // ---------------- K0
+                // ---------------- K0 arguments
                 GeoArgs G; memset(&G, 0, sizeof G);
                 G.dim = dim;
                 for (int k = 0; k < dim; ++k) {
@@ -684,19 +496,15 @@ static int assemble_pass(gsb200_assembler *a)
                 G.form = a->form; G.brow = brow; G.bcol = bcol; G.lambda = a->coef[0]; G.mu = a->coef[1];
                 G.symD = kind == KIND_SYM;
                 G.D = D; G.dstride = npts;
-                if (blk == 0 && nf) { G.F = F; G.fstride = npts; G.nf = nf; for (int c = 0; c < nf; ++c) G.prog[c] = a->progs[c]; }
-                mark(a, 0);
-                {
-                    int pgu = P.dir[0].pg1;                                   // uniform geometry degree -> unrolled kernel
-                    for (int k = 1; k < dim; ++k) if (P.dir[k].pg1 != pgu) pgu = 0;
-                    if (pgu > 4) pgu = 0;
+                const bool with_load = blk == 0 && nf > 0;
+                if (with_load) { G.F = F; G.fstride = npts; G.nf = nf; for (int c = 0; c < nf; ++c) G.prog[c] = a->progs[c]; }
+                const int pgl = P.dir[L].pg1;
+                const bool rat = P.d_weights != 0, hot = a->form == GSB200_FORM_POISSON && G.symD;
+                if (!fused) {
+                    mark(a, 0);
                     static const int gblk = [] { const char *e = getenv("GSB200_GEO_BLOCK"); const int v = e ? atoi(e) : 128; return (v == 64 || v == 256) ? v : 128; }();
                     const dim3 gg((unsigned)((QLc + gblk - 1) / gblk), dim == 3 ? (unsigned)Q1 : (unsigned)Q0, dim == 3 ? (unsigned)Q0 : 1u);
                     if (gg.y > 65535u || gg.z > 65535u) { set_error("more than 65535 quadrature points per direction"); return GSB200_EUNSUPPORTED; }
-                    static const bool geo_point = [] { const char *e = getenv("GSB200_GEO"); return e && !strcmp(e, "point"); }();
-                    if (!geo_point) {
-                        const int pgl = P.dir[L].pg1;
-                        const bool rat = P.d_weights != 0, hot = a->form == GSB200_FORM_POISSON && G.symD;
 #ifndef GSB200_EMULATE
 #define GSB_GEOL(D_, PG_, R_, F_) { cudaKernel_t jk = (G.F && !dry_run()) ? jit_geometry_kernel(a->progs_host, a->device, D_, PG_, R_, F_) : 0; \
                                     if (jk) { void *kargs[] = {(void *)&G}; GSB_TRY(dev_check(cudaLaunchKernel((const void *)jk, gg, dim3(gblk), kargs, 0, s), "launch of the compiled geometry kernel")); note_launch(); ++a->jit_launches; } \
@@ -705,16 +513,10 @@ static int assemble_pass(gsb200_assembler *a)
 #define GSB_GEOL(D_, PG_, R_, F_) { auto kfn = k_geometry_line<D_, PG_, R_, F_>; GSB_LAUNCH(kfn, gg, dim3(gblk), s, G); }
 #endif
 #define GSB_GEOL_D(D_) { if (hot && !rat && pgl == 2) GSB_GEOL(D_, 2, false, 1) else if (hot && !rat && pgl == 3) GSB_GEOL(D_, 3, false, 1) \
-                         else if (hot && !rat && pgl == 4) GSB_GEOL(D_, 4, false, 1) else if (hot && rat && pgl == 3) GSB_GEOL(D_, 3, true, 1) \
                          else if (rat) GSB_GEOL(D_, 0, true, 0) else GSB_GEOL(D_, 0, false, 0) }
-                        if (dim == 2) GSB_GEOL_D(2) else GSB_GEOL_D(3)
+                    if (dim == 2) GSB_GEOL_D(2) else GSB_GEOL_D(3)
 #undef GSB_GEOL_D
 #undef GSB_GEOL
-                    } else
-#define GSB_GEO(D_, P_) { auto kfn = k_geometry<D_, P_>; GSB_LAUNCH(kfn, gg, dim3(gblk), s, G); }
-                    if (dim == 2) { switch (pgu) { case 2: GSB_GEO(2, 2) break; case 3: GSB_GEO(2, 3) break; case 4: GSB_GEO(2, 4) break; default: GSB_GEO(2, 0) } }
-                    else { switch (pgu) { case 2: GSB_GEO(3, 2) break; case 3: GSB_GEO(3, 3) break; case 4: GSB_GEO(3, 4) break; default: GSB_GEO(3, 0) } }
-#undef GSB_GEO
                 }
 
                 // ---------------- sweeps
@@ -744,33 +546,50 @@ static int assemble_pass(gsb200_assembler *a)
                     a->tm.sweep_flops[slot] += fpp * A.ncol * pts;
                     a->tm.sweep_bytes[slot] += (i64)(8.0 * (nin * (double)A.ncol * (double)pts + nout * (double)npairs_out * (double)A.ncol));
                 };
+                // first sweep (direction 0): fused with K0, or the window / generic kernel reading D
+                auto first_sweep = [&](SweepArgs &A, int stage, i64 ncolL, i64 nrows) -> int {
+                    const int nseg = nseg_for(A.ncol * (d0.p + 1), d0.nfun, d0.p + 1);
+                    std::vector<int> seg = make_segments(d0, 0, d0.nfun, nseg);
+                    A.seg = a->d_seg + segoff; GSB_TRY(upload_segments(a, seg, &segoff));
+                    mark(a, 1);
+                    i64 fpp = 0; int nin, nout;
+                    stage_io(kind, stage, &nin, &nout);
+                    if (fused) {
+                        FusedArgs FA; memset(&FA, 0, sizeof FA);
+                        FA.G = G; FA.G.D = 0; FA.G.F = 0;
+                        FA.first = d0.d_first; FA.nexit = d0.d_nexit; FA.tab = d0.d_tab; FA.seg = A.seg; FA.lc = P.d_lc; FA.lc_nL = dL.ngeo;
+                        FA.ncolL = (int)ncolL; FA.nrows = (int)nrows;
+                        FA.out = A.out; FA.out_cs = A.out_cs; FA.out_fs = A.out_fs; FA.out_bq = A.out_bq; FA.out_bs = A.out_bs; FA.out_is = A.out_is;
+                        FA.d_off = A.d_off;
+                        FA.nf = with_load ? nf : 0; FA.v1 = V1; FA.v1_fs = A.ncol; FA.v1_cs = n0 * A.ncol;
+                        { FusedCtx fc; fc.progs = &a->progs_host; fc.device = a->device; fc.jit_launches = &a->jit_launches;
+                          GSB_TRY(launch_fused(fc, kind, dim, d0.p + 1, FA, (int)seg.size() / 4, s, hot, rat, pgl, &fpp)); }
+                        account(0, A, seg, fpp, 0, nout, NI0);
+                    } else {
+                        GSB_TRY(dispatch_sweep(kind, stage, d0.p + 1, A, (int)seg.size() / 4, s, &fpp));
+                        account(0, A, seg, fpp, nin, nout, NI0);
+                    }
+                    return 0;
+                };
                 i64 fpp = 0; int nin, nout;
                 if (dim == 3) {
                     {   // S1: direction 0
                         SweepArgs A = base_args(d0);
                         A.in = D; A.in_cs = npts; A.in_es = (i64)d0.q * Q1 * QLc; A.in_ts = Q1 * QLc; A.in_os = 0; A.in_is = 1; A.e_in0 = 0;
                         A.ncol = Q1 * QLc; A.ninner = A.ncol;
-                        A.out = A1; A.out_cs = NI0h * Q1 * QLc; A.out_fs = (half ? d0.p + 1 : 2 * d0.p + 1) * Q1 * QLc; A.out_ds = Q1 * QLc; A.out_os = 0; A.out_bq = A.ncol + 1; A.out_bs = 0; A.out_is = 1;
-                        if (half) { A.half_out = 1; A.d_off = 0; }
+                        A.out = A1; A.out_cs = NI0 * Q1 * QLc; A.out_fs = (2 * d0.p + 1) * Q1 * QLc; A.out_ds = Q1 * QLc; A.out_os = 0; A.out_bq = A.ncol + 1; A.out_bs = 0; A.out_is = 1;
                         if (a1_blk) {    // A1[o][i0][q1][e2][d0][t]: the second sweep then reads AND writes whole (d0, t) runs
                             A.out_fs = Q1 * ELc * W0 * dL.q; A.out_ds = dL.q; A.out_bq = dL.q; A.out_bs = W0 * dL.q; A.out_is = 1;
                         }
-                        const int nseg = nseg_for(A.ncol * (d0.p + 1), d0.nfun, d0.p + 1);
-                        std::vector<int> seg = make_segments(d0, 0, d0.nfun, nseg);
-                        A.seg = a->d_seg + segoff; GSB_TRY(upload_segments(a, seg, &segoff));
-                        mark(a, 1);
-                        { TmapDesc td; memset(&td, 0, sizeof td); td.valid = true; td.rank = 3; td.dims[0] = (unsigned long long)(Q1 * QLc); td.dims[1] = (unsigned long long)(Q0); td.dims[2] = (unsigned long long)(ncD); td.strides[0] = 8ull * (unsigned long long)(Q1 * QLc); td.strides[1] = 8ull * (unsigned long long)(npts); td.box_kind[0] = 1; td.box_kind[1] = 2; td.box_kind[2] = 3; A.tm_rank = 3; A.tm_dim_inner = 0; A.tm_dim_e = 1; A.tm_e_mul = d0.q; A.tm_dim_outer = -1;
-                        GSB_TRY(dispatch_sweep(kind01, 0, d0.p + 1, A, (int)seg.size() / 4, s, &fpp, td)); }
-                        stage_io(kind01, 0, &nin, &nout);
-                        if (kind01 == KIND_SYMH) account(0, A, seg, fpp, nin, symh_frac, NI0h); else account(0, A, seg, fpp, nin, nout, NI0h);
+                        GSB_TRY(first_sweep(A, 0, QLc, Q1));
                     }
                     {   // S2: direction 1
                         SweepArgs A = base_args(d1);
-                        A.in = A1; A.in_cs = NI0h * Q1 * QLc; A.in_es = (i64)d1.q * QLc; A.in_ts = QLc; A.in_os = Q1 * QLc; A.in_is = 1; A.e_in0 = 0;
-                        A.ncol = NI0h * QLc; A.ninner = QLc;
+                        A.in = A1; A.in_cs = NI0 * Q1 * QLc; A.in_es = (i64)d1.q * QLc; A.in_ts = QLc; A.in_os = Q1 * QLc; A.in_is = 1; A.e_in0 = 0;
+                        A.ncol = NI0 * QLc; A.ninner = QLc;
                         // A2[g][i1][e2][i0][d1][d0][t]: the last sweep then writes (d1,d0)-contiguous runs of each CSC column
                         A.out = A2; A.out_cs = NI1 * ELc * NI0 * dL.q; A.out_fs = (i64)ELc * NI0 * W1 * dL.q; A.out_ds = (i64)W0 * dL.q;
-                        A.out_od = half ? d0.p + 1 : W0; A.out_dshift = half ? d0.p : 0; A.mirror = half ? 1 : 0; A.out_nprev = d0.nfun;
+                        A.out_od = W0; A.out_dshift = 0; A.mirror = 0; A.out_nprev = d0.nfun;
                         A.out_os = (i64)W1 * W0 * dL.q; A.out_os2 = dL.q; A.out_bq = dL.q; A.out_bs = NI0 * W1 * dL.q; A.out_is = 1;
                         if (a1_blk) {    // thread = (i0; e2, d0, t): contiguous in A1 and, per element, in A2
                             A.in_os = Q1 * ELc * W0 * dL.q; A.in_is = 1; A.in_ts = ELc * W0 * dL.q; A.in_es = (i64)d1.q * A.in_ts;
@@ -783,31 +602,23 @@ static int assemble_pass(gsb200_assembler *a)
                             A.ncol = n0 * ELc * W0 * dL.q; A.ninner = ELc * W0 * dL.q;
                             A.out_od = 1; A.out_dshift = 0; A.out_os = W1 * W0 * dL.q; A.out_os2 = 0; A.out_bq = W0 * dL.q; A.out_bs = NI0 * W1 * dL.q; A.out_is = 1;
                         }
-                        if (a2_rows) {   // A2[g][i1][i0][d1][d0][q2]: rows of the last direction (coalesced S2 stores, row-strided S3 loads)
-                            A.out_cs = NI1 * NI0 * QLc; A.out_fs = NI0 * W1 * QLc; A.out_ds = W0 * QLc; A.out_os = W1 * W0 * QLc; A.out_os2 = QLc;
-                            A.out_bq = QLc + 1; A.out_bs = 0; A.out_is = 1;
-                        }
                         const int nseg = nseg_for(A.ncol * (d1.p + 1), d1.nfun, d1.p + 1);
                         std::vector<int> seg = make_segments(d1, 0, d1.nfun, nseg);
                         A.seg = a->d_seg + segoff; GSB_TRY(upload_segments(a, seg, &segoff));
                         mark(a, 2);
-                        { TmapDesc td; memset(&td, 0, sizeof td); td.valid = true; td.rank = 4; td.dims[0] = (unsigned long long)(QLc); td.dims[1] = (unsigned long long)(Q1); td.dims[2] = (unsigned long long)(NI0h); td.dims[3] = (unsigned long long)(no1); td.strides[0] = 8ull * (unsigned long long)(QLc); td.strides[1] = 8ull * (unsigned long long)(Q1 * QLc); td.strides[2] = 8ull * (unsigned long long)(NI0h * Q1 * QLc); td.box_kind[0] = 1; td.box_kind[1] = 2; td.box_kind[2] = 0; td.box_kind[3] = 3; A.tm_rank = 4; A.tm_dim_inner = 0; A.tm_dim_e = 1; A.tm_e_mul = d1.q; A.tm_dim_outer = 2;
-                        if (kind01 == KIND_SYMH) { A.mir_q = dL.q; A.mir_w = (int)W0; A.mir_p = d0.p; A.mir_n = (int)n0; }
-                        GSB_TRY(dispatch_sweep(kind01, 1, d1.p + 1, A, (int)seg.size() / 4, s, &fpp, td)); }
-                        stage_io(kind01, 1, &nin, &nout);
-                        if (kind01 == KIND_SYMH) account(1, A, seg, fpp, symh_frac, nout, NI1); else account(1, A, seg, fpp, nin, nout, NI1);
+                        GSB_TRY(dispatch_sweep(kind, 1, d1.p + 1, A, (int)seg.size() / 4, s, &fpp));
+                        stage_io(kind, 1, &nin, &nout);
+                        account(1, A, seg, fpp, nin, nout, NI1);
                     }
                     {   // S3: direction 2, scatter into the CSC arrays
                         SweepArgs A = base_args(dL);
                         A.in = A2; A.in_cs = NI1 * ELc * NI0 * dL.q; A.in_es = NI0 * W1 * dL.q; A.in_ts = 1; A.in_os = (i64)ELc * NI0 * W1 * dL.q; A.in_is = dL.q; A.e_in0 = eL0;
                         A.ncol = NI1 * NI0; A.ninner = NI0 * W1;     // outer = i1, inner = (i0, d1, d0)
-                        if (a2_rows) { A.in_cs = NI1 * NI0 * QLc; A.in_es = dL.q; A.in_ts = 1; A.in_os = NI0 * W1 * QLc; A.in_is = QLc; A.e_in0 = eL0; }
                         const int nseg = nseg_for(A.ncol, x_hi - x_lo, dL.p + 1);
                         std::vector<int> seg = make_segments(dL, x_lo, x_hi, nseg);
                         A.seg = a->d_seg + segoff; GSB_TRY(upload_segments(a, seg, &segoff));
                         mark(a, 3);
-                        { TmapDesc td; memset(&td, 0, sizeof td); td.valid = true; td.rank = 5; td.dims[0] = (unsigned long long)(dL.q); td.dims[1] = (unsigned long long)(NI0 * W1); td.dims[2] = (unsigned long long)(ELc); td.dims[3] = (unsigned long long)(n1); td.dims[4] = (unsigned long long)(no2); td.strides[0] = 8ull * (unsigned long long)(dL.q); td.strides[1] = 8ull * (unsigned long long)(NI0 * W1 * dL.q); td.strides[2] = 8ull * (unsigned long long)((i64)ELc * NI0 * W1 * dL.q); td.strides[3] = 8ull * (unsigned long long)(NI1 * ELc * NI0 * dL.q); td.box_kind[0] = 2; td.box_kind[1] = 1; td.box_kind[2] = 0; td.box_kind[3] = 0; td.box_kind[4] = 3; A.tm_rank = 5; A.tm_dim_inner = 1; A.tm_dim_e = 2; A.tm_e_mul = 1; A.tm_dim_outer = 3;
-                        GSB_TRY(dispatch_sweep(kind, 2, dL.p + 1, A, (int)seg.size() / 4, s, &fpp, td)); }
+                        GSB_TRY(dispatch_sweep(kind, 2, dL.p + 1, A, (int)seg.size() / 4, s, &fpp));
                         stage_io(kind, 2, &nin, &nout); account(2, A, seg, fpp, nin, nout, (i64)(x_hi - x_lo) * (2 * dL.p + 1));
                     }
                 } else {
@@ -816,13 +627,7 @@ static int assemble_pass(gsb200_assembler *a)
                         A.in = D; A.in_cs = npts; A.in_es = (i64)d0.q * QLc; A.in_ts = QLc; A.in_os = 0; A.in_is = 1; A.e_in0 = 0;
                         A.ncol = QLc; A.ninner = QLc;
                         A.out = A1; A.out_cs = (i64)ELc * NI0 * dL.q; A.out_fs = (i64)(2 * d0.p + 1) * dL.q; A.out_ds = dL.q; A.out_os = 0; A.out_bq = dL.q; A.out_bs = NI0 * dL.q; A.out_is = 1;
-                        const int nseg = nseg_for(A.ncol * (d0.p + 1), d0.nfun, d0.p + 1);
-                        std::vector<int> seg = make_segments(d0, 0, d0.nfun, nseg);
-                        A.seg = a->d_seg + segoff; GSB_TRY(upload_segments(a, seg, &segoff));
-                        mark(a, 1);
-                        { TmapDesc td; memset(&td, 0, sizeof td); td.valid = true; td.rank = 3; td.dims[0] = (unsigned long long)(QLc); td.dims[1] = (unsigned long long)(Q0); td.dims[2] = (unsigned long long)(ncD); td.strides[0] = 8ull * (unsigned long long)(QLc); td.strides[1] = 8ull * (unsigned long long)(npts); td.box_kind[0] = 1; td.box_kind[1] = 2; td.box_kind[2] = 3; A.tm_rank = 3; A.tm_dim_inner = 0; A.tm_dim_e = 1; A.tm_e_mul = d0.q; A.tm_dim_outer = -1;
-                        GSB_TRY(dispatch_sweep(kind, 3, d0.p + 1, A, (int)seg.size() / 4, s, &fpp, td)); }
-                        stage_io(kind, 3, &nin, &nout); account(0, A, seg, fpp, nin, nout, NI0);
+                        GSB_TRY(first_sweep(A, 3, QLc, 1));
                     }
                     {   // S2: direction 1, scatter
                         SweepArgs A = base_args(dL);
@@ -832,15 +637,15 @@ static int assemble_pass(gsb200_assembler *a)
                         std::vector<int> seg = make_segments(dL, x_lo, x_hi, nseg);
                         A.seg = a->d_seg + segoff; GSB_TRY(upload_segments(a, seg, &segoff));
                         mark(a, 2);
-                        { TmapDesc td; memset(&td, 0, sizeof td); td.valid = true; td.rank = 4; td.dims[0] = (unsigned long long)(dL.q); td.dims[1] = (unsigned long long)(NI0); td.dims[2] = (unsigned long long)(ELc); td.dims[3] = (unsigned long long)(no1); td.strides[0] = 8ull * (unsigned long long)(dL.q); td.strides[1] = 8ull * (unsigned long long)(NI0 * dL.q); td.strides[2] = 8ull * (unsigned long long)((i64)ELc * NI0 * dL.q); td.box_kind[0] = 2; td.box_kind[1] = 1; td.box_kind[2] = 0; td.box_kind[3] = 3; A.tm_rank = 4; A.tm_dim_inner = 1; A.tm_dim_e = 2; A.tm_e_mul = 1; A.tm_dim_outer = -1;
-                        GSB_TRY(dispatch_sweep(kind, 2, dL.p + 1, A, (int)seg.size() / 4, s, &fpp, td)); }
+                        GSB_TRY(dispatch_sweep(kind, 2, dL.p + 1, A, (int)seg.size() / 4, s, &fpp));
                         stage_io(kind, 2, &nin, &nout); account(1, A, seg, fpp, nin, nout, (i64)(x_hi - x_lo) * (2 * dL.p + 1));
                     }
                 }
                 // ---------------- K3: load vector (once per chunk)
-                if (blk == 0 && nf) {
+                if (with_load) {
                     mark(a, 4);
                     for (int c = 0; c < nf; ++c) {
+                        double *V1c = V1 + (fused ? (i64)c * n0 * Q1 * QLc : 0);      // the fused first sweep produced all components at once
                         const int rcol = a->form == GSB200_FORM_ELASTICITY ? 0 : c;   // rhs column
                         const int comp = a->form == GSB200_FORM_ELASTICITY ? c : 0;   // dof component
                         VSweepArgs V; memset(&V, 0, sizeof V);
@@ -866,12 +671,14 @@ static int assemble_pass(gsb200_assembler *a)
                             return 0;
                         };
                         if (dim == 3) {
-                            vbase(d0); V.final_ = 0; V.x_lo = 0; V.x_hi = d0.nfun; V.e_in0 = 0;
-                            V.in = F + c * npts; V.in_qs = Q1 * QLc; V.in_os = 0; V.in_is = 1; V.ncol = Q1 * QLc; V.ninner = V.ncol;
-                            V.out = V1; V.out_fs = Q1 * QLc; V.out_os = 0; V.out_is = 1;
-                            GSB_TRY(vlaunch(d0));
-                            vbase(d1); V.x_lo = 0; V.x_hi = d1.nfun;
-                            V.in = V1; V.in_qs = QLc; V.in_os = Q1 * QLc; V.in_is = 1; V.ncol = n0 * QLc; V.ninner = QLc;
+                            if (!fused) {
+                                vbase(d0); V.final_ = 0; V.x_lo = 0; V.x_hi = d0.nfun; V.e_in0 = 0;
+                                V.in = F + c * npts; V.in_qs = Q1 * QLc; V.in_os = 0; V.in_is = 1; V.ncol = Q1 * QLc; V.ninner = V.ncol;
+                                V.out = V1c; V.out_fs = Q1 * QLc; V.out_os = 0; V.out_is = 1;
+                                GSB_TRY(vlaunch(d0));
+                            }
+                            vbase(d1); V.final_ = 0; V.e_in0 = 0; V.x_lo = 0; V.x_hi = d1.nfun;
+                            V.in = V1c; V.in_qs = QLc; V.in_os = Q1 * QLc; V.in_is = 1; V.ncol = n0 * QLc; V.ninner = QLc;
                             V.out = V2; V.out_fs = n0 * QLc; V.out_os = QLc; V.out_is = 1;
                             GSB_TRY(vlaunch(d1));
                             vbase(dL); V.x_lo = x_lo; V.x_hi = x_hi; V.e_in0 = eL0; V.final_ = 1;
@@ -879,12 +686,14 @@ static int assemble_pass(gsb200_assembler *a)
                             V.n0 = (int)n0; V.n1 = (int)n1; V.dimlow = 2; V.dofmap = P.d_dofmap + (i64)comp * P.nb; V.rhs = a->d_rhs + (i64)rcol * N; V.nfree = N;
                             GSB_TRY(vlaunch(dL));
                         } else {
-                            vbase(d0); V.final_ = 0; V.x_lo = 0; V.x_hi = d0.nfun; V.e_in0 = 0;
-                            V.in = F + c * npts; V.in_qs = QLc; V.in_os = 0; V.in_is = 1; V.ncol = QLc; V.ninner = QLc;
-                            V.out = V1; V.out_fs = QLc; V.out_os = 0; V.out_is = 1;
-                            GSB_TRY(vlaunch(d0));
+                            if (!fused) {
+                                vbase(d0); V.final_ = 0; V.x_lo = 0; V.x_hi = d0.nfun; V.e_in0 = 0;
+                                V.in = F + c * npts; V.in_qs = QLc; V.in_os = 0; V.in_is = 1; V.ncol = QLc; V.ninner = QLc;
+                                V.out = V1c; V.out_fs = QLc; V.out_os = 0; V.out_is = 1;
+                                GSB_TRY(vlaunch(d0));
+                            }
                             vbase(dL); V.x_lo = x_lo; V.x_hi = x_hi; V.e_in0 = eL0; V.final_ = 1;
-                            V.in = V1; V.in_qs = 1; V.in_os = 0; V.in_is = QLc; V.ncol = n0; V.ninner = n0;
+                            V.in = V1c; V.in_qs = 1; V.in_os = 0; V.in_is = QLc; V.ncol = n0; V.ninner = n0;
                             V.n0 = (int)n0; V.n1 = 1; V.dimlow = 1; V.dofmap = P.d_dofmap + (i64)comp * P.nb; V.rhs = a->d_rhs + (i64)rcol * N; V.nfree = N;
                             GSB_TRY(vlaunch(dL));
                         }
@@ -1035,6 +844,21 @@ int gsb200_create(const gsb200_problem *pb, int device, gsb200_assembler **out)
         if (S.geo_weights) { std::vector<double> wv(S.geo_weights, S.geo_weights + P.ngeo_total); if ((rc = upload(&P.d_weights, wv, a->stream))) break; }
         const int L = dim - 1;
         P.nrun = 1; for (int k = 1; k < dim; ++k) P.nrun *= 2 * P.dir[k].p + 1;
+        {   // fused first sweep (fused.cuh)
+            const Dir1D &dl = P.dir[L];
+            // leading directions of the geometry contracted once per patch (they do not depend on the last direction)
+            const int nfg = S.geo_weights ? dim + 1 : dim;
+            const i64 lc_count = (i64)(dim == 3 ? P.dir[1].Q : 1) * P.dir[0].Q * dl.ngeo * nfg * dim;
+            if (lc_count * 8 <= ((i64)1 << 30)) {      // a geometry as fine as the solution basis in the last direction would not pay: unfused path
+                if ((rc = dev_malloc((void **)&P.d_lc, sizeof(double) * (size_t)lc_count))) break;
+                LineCoefArgs LC; memset(&LC, 0, sizeof LC);
+                LC.dim = dim; LC.rational = S.geo_weights ? 1 : 0; LC.Q0 = P.dir[0].Q; LC.Q1 = dim == 3 ? P.dir[1].Q : 1; LC.nL = dl.ngeo;
+                for (int k = 0; k < dim - 1; ++k) { LC.gtab[k] = P.dir[k].d_gtab; LC.gfirst[k] = P.dir[k].d_gfirst; LC.pg1[k] = P.dir[k].pg1; LC.ngeo[k] = P.dir[k].ngeo; }
+                LC.coefs = P.d_coefs; LC.weights = P.d_weights; LC.ngeo_total = P.ngeo_total; LC.lc = P.d_lc;
+                const i64 nthreads = lc_count / dim;
+                GSB_LAUNCH(k_line_coefs, dim3((unsigned)((nthreads + 127) / 128)), dim3(128), a->stream, LC);
+            }
+        }
         if ((rc = dev_malloc((void **)&P.d_colflag, (size_t)P.nb * pb->ncomp))) break;
         if ((rc = dev_memset(P.d_colflag, 0, (size_t)P.nb * pb->ncomp, a->stream))) break;
         if (pb->ncomp == 1) { if ((rc = dev_malloc((void **)&P.d_st, sizeof(unsigned) * (size_t)P.nb * P.nrun))) break; }

@@ -23,8 +23,6 @@
 #pragma once
 #include "platform.cuh"
 #include "../../include/gsb200.h"
-#include <type_traits>
-#include <utility>
 
 namespace gsb {
 
@@ -35,91 +33,7 @@ namespace gsb {
 #define GSB_CX __host__ __device__ constexpr
 #endif
 
-template <int I, int N, class F>
-GSB_DEVICE void static_for(F &&f)
-{
-    if constexpr (I < N) {
-        f(std::integral_constant<int, I>{});
-        static_for<I + 1, N>(f);
-    }
-}
-
-// ------------------------------------------------------------------------------------
-// Term tables.  A term (o, c, a, b) adds  B^(a)_owner(q) * B^(b)_partner(q) * in_c(q)  to out_o.
-// a/b = 0: value, 1: first derivative in the swept direction.
-#define GSB_PK(o, c, a, b) (((o) << 8) | ((c) << 2) | ((a) << 1) | (b))
-template <class D>
-struct TermOps {
-    static GSB_CX int o(int k) { return D::pk(k) >> 8; }
-    static GSB_CX int c(int k) { return (D::pk(k) >> 2) & 63; }
-    static GSB_CX int a(int k) { return (D::pk(k) >> 1) & 1; }
-    static GSB_CX int b(int k) { return D::pk(k) & 1; }
-    // first term contributing to z[o][b] ?
-    static GSB_CX bool first(int k) { for (int j = 0; j < k; ++j) if (o(j) == o(k) && b(j) == b(k)) return false; return true; }
-    static GSB_CX bool has(int oo, int bb) { for (int j = 0; j < D::NT; ++j) if (o(j) == oo && b(j) == bb) return true; return false; }
-    // output that holds the same number when owner and partner swap roles (symmetric coefficient tensor):
-    // identity unless the table overrides it
-    static GSB_CX int omirror(int oo) { return oo; }
-    // output order in which the window kernel forms its groups: consecutive outputs of this order share inputs
-    static GSB_CX int order(int i) { return i; }
-    // symmetry of the form (window kernels): an output that is symmetric under the exchange of owner and partner is stored for
-    // delta >= 0 only; a (virtual) input c is backed by the stored component in_src(c) and read directly (mode 1), at the mirrored
-    // pair (i + delta, -delta) (mode 2), or mirrored only where delta < 0 (mode 0, symmetric component)
-    // first sweeps store whole rows of deltas at the owner's exit for every degree (measured: S1 4.0 -> 3.55 ms at p=3; the second
-    // sweep loses as much through register pressure, so it holds pairs back only where the quadrature size demands it)
-    static GSB_CX bool whole_rows() { return false; }
-    static GSB_CX bool out_sym(int) { return false; }
-    static GSB_CX int in_src(int cc) { return cc; }
-    static GSB_CX int in_mode(int) { return 1; }
-    static GSB_CX bool uses_c(unsigned omask, int cc) { for (int j = 0; j < D::NT; ++j) if (((omask >> o(j)) & 1u) && c(j) == cc) return true; return false; }
-};
-// symmetric coefficient tensor, 3-D (Poisson): D = {00,01,02,11,12,22}
-struct T3SymS1 : TermOps<T3SymS1> { enum { NIN = 6, NOUT = 8, NT = 8 };
-    static GSB_CX bool whole_rows() { return true; }
-    static GSB_CX int pk(int k) { const int v[8] = {GSB_PK(0,0,1,1), GSB_PK(1,1,1,0), GSB_PK(2,1,0,1), GSB_PK(3,3,0,0),
-                                                    GSB_PK(4,2,1,0), GSB_PK(5,2,0,1), GSB_PK(6,4,0,0), GSB_PK(7,5,0,0)}; return v[k]; }
-    static GSB_CX int order(int i) { const int v[8] = {1, 2, 0, 3, 4, 5, 6, 7}; return v[i]; } };
-// outputs g = 2*(a==2)+(b==2): flags still needed in direction 2
-struct T3SymS2 : TermOps<T3SymS2> { enum { NIN = 8, NOUT = 4, NT = 9 };
-    static GSB_CX int pk(int k) { const int v[9] = {GSB_PK(0,0,0,0), GSB_PK(0,1,0,1), GSB_PK(0,2,1,0), GSB_PK(0,3,1,1),
-                                                    GSB_PK(1,4,0,0), GSB_PK(2,5,0,0), GSB_PK(1,6,1,0), GSB_PK(2,6,0,1),
-                                                    GSB_PK(3,7,0,0)}; return v[k]; }
-    static GSB_CX int omirror(int oo) { return oo == 1 ? 2 : (oo == 2 ? 1 : oo); }      // g = 2*alpha2 + beta2: swap the flags
-    static GSB_CX int order(int i) { const int v[4] = {0, 3, 1, 2}; return v[i]; } };
-// The same two sweeps exploiting the symmetry of D (blocked A1 layout, window kernels): the first sweep stores 6 components
-// {D00(1,1), D01(1,0), D11(0,0), D02(1,0), D12(0,0), D22(0,0)}, the symmetric ones for delta0 >= 0 only; the (0,1) companions
-// of D01 and D02 are the (1,0) values of the mirrored pair.  46 % fewer bytes between the two sweeps.
-struct T3SymS1H : TermOps<T3SymS1H> { enum { NIN = 6, NOUT = 6, NT = 6 };
-    static GSB_CX int pk(int k) { const int v[6] = {GSB_PK(0,0,1,1), GSB_PK(1,1,1,0), GSB_PK(2,3,0,0), GSB_PK(3,2,1,0), GSB_PK(4,4,0,0), GSB_PK(5,5,0,0)}; return v[k]; }
-    static GSB_CX bool out_sym(int oo) { return oo != 1 && oo != 3; }
-    static GSB_CX int order(int i) { const int v[6] = {0, 2, 1, 3, 4, 5}; return v[i]; } };
-struct T3SymS2H : TermOps<T3SymS2H> { enum { NIN = 8, NOUT = 4, NT = 9 };
-    static GSB_CX int pk(int k) { return T3SymS2::pk(k); }
-    static GSB_CX int order(int i) { return T3SymS2::order(i); }
-    static GSB_CX int in_src(int cc) { const int v[8] = {0, 1, 1, 2, 3, 3, 4, 5}; return v[cc]; }
-    static GSB_CX int in_mode(int cc) { const int v[8] = {0, 1, 2, 0, 1, 2, 0, 0}; return v[cc]; } };
-// last direction of any gradient-gradient form: in_g, g = 2*a+b
-struct TLast : TermOps<TLast> { enum { NIN = 4, NOUT = 1, NT = 4 };
-    static GSB_CX int pk(int k) { const int v[4] = {GSB_PK(0,0,0,0), GSB_PK(0,1,0,1), GSB_PK(0,2,1,0), GSB_PK(0,3,1,1)}; return v[k]; } };
-// general (non-symmetric) tensor, 3-D: c = 3a+b
-struct T3GenS1 : TermOps<T3GenS1> { enum { NIN = 9, NOUT = 9, NT = 9 };
-    static GSB_CX bool whole_rows() { return true; }
-    static GSB_CX int pk(int k) { const int v[9] = {GSB_PK(0,0,1,1), GSB_PK(1,1,1,0), GSB_PK(2,2,1,0), GSB_PK(3,3,0,1), GSB_PK(4,4,0,0),
-                                                    GSB_PK(5,5,0,0), GSB_PK(6,6,0,1), GSB_PK(7,7,0,0), GSB_PK(8,8,0,0)}; return v[k]; } };
-struct T3GenS2 : TermOps<T3GenS2> { enum { NIN = 9, NOUT = 4, NT = 9 };
-    static GSB_CX int pk(int k) { const int v[9] = {GSB_PK(0,0,0,0), GSB_PK(0,1,0,1), GSB_PK(1,2,0,0), GSB_PK(0,3,1,0), GSB_PK(0,4,1,1),
-                                                    GSB_PK(1,5,1,0), GSB_PK(2,6,0,0), GSB_PK(2,7,0,1), GSB_PK(3,8,0,0)}; return v[k]; } };
-// 2-D: symmetric D = {00,01,11}; general c = 2a+b.  Outputs g = 2*(a==1)+(b==1).
-struct T2SymS1 : TermOps<T2SymS1> { enum { NIN = 3, NOUT = 4, NT = 4 };
-    static GSB_CX bool whole_rows() { return true; }
-    static GSB_CX int pk(int k) { const int v[4] = {GSB_PK(0,0,1,1), GSB_PK(1,1,1,0), GSB_PK(2,1,0,1), GSB_PK(3,2,0,0)}; return v[k]; }
-    static GSB_CX int order(int i) { const int v[4] = {1, 2, 0, 3}; return v[i]; } };
-struct T2GenS1 : TermOps<T2GenS1> { enum { NIN = 4, NOUT = 4, NT = 4 };
-    static GSB_CX bool whole_rows() { return true; }
-    static GSB_CX int pk(int k) { const int v[4] = {GSB_PK(0,0,1,1), GSB_PK(1,1,1,0), GSB_PK(2,2,0,1), GSB_PK(3,3,0,0)}; return v[k]; } };
-// mass-type form: one scalar density, no derivatives, every direction
-struct TMass : TermOps<TMass> { enum { NIN = 1, NOUT = 1, NT = 1 };
-    static GSB_CX int pk(int) { return GSB_PK(0,0,0,0); } };
+#include "terms.cuh"   // static_for, term tables, output-group helpers (also part of the text NVRTC compiles, jit.cuh)
 
 // ------------------------------------------------------------------------------------
 // 1-D B-spline values + first derivatives on knot span s at u: Cox-de Boor triangle kept
@@ -201,6 +115,7 @@ GSB_GLOBAL void k_geo_table(const GeoTableArgs A)
 }
 
 #include "geometry.cuh"   // K0: source-term machine, map data, coefficient tensor (also the text NVRTC compiles, jit.cuh)
+#include "fused.cuh"      // K0 + first sweep in one kernel (D stays in shared memory); NVRTC text as well
 
 // ------------------------------------------------------------------------------------
 // Neumann boundary load (gsVisitorNeumann.h:83-136, gsExprAssembler.h:835-895): flux density at the
@@ -437,8 +352,6 @@ struct SweepArgs {
     int wb_stores;               // window kernel: plain write-back stores instead of streaming ones (pieces that do not fill 32-byte sectors
                                  // must wait in L2 for their neighbours, else DRAM read-modify-writes them)
     i64 ncol; i64 ninner;
-    // tensor-map TMA variant: which box coordinate carries the tile start, the span, the outer index
-    int tm_rank, tm_dim_inner, tm_dim_e, tm_e_mul, tm_dim_outer;
     FinalArgs fin;
 };
 
@@ -606,11 +519,9 @@ GSB_GLOBAL void k_sweep(const SweepArgs A)
 // buffer) and lines further ahead are pulled into L2 with prefetch hints, so the HBM latency hides behind
 // the FP64 work without a shared-memory ring.  Knot multiplicities > 1 simply exit several functions.
 #ifndef GSB200_EMULATE
-#define GSB_GRID_CONSTANT __grid_constant__
-#define GSB_NOINLINE __device__ __noinline__
+#define GSB_NOINLINE static __device__ __noinline__
 GSB_DEVICE void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 #else
-#define GSB_GRID_CONSTANT
 #define GSB_NOINLINE static
 static inline void prefetch_l2(const void *) {}
 #endif
@@ -633,19 +544,7 @@ GSB_DEVICE void final_canonical(const FinalArgs &F, const FinalCtx &c, int fun, 
     else if (F.fixed) final_slow(F, c, fun, rec, dL, val);
 }
 
-GSB_DEVICE void st_out(double *p, double v, int wb) { if (wb) *p = v; else st_stream(p, v); }
 
-template <class T, int NG> GSB_CX unsigned group_mask(int gi)
-{
-    unsigned m = 0;
-    for (int i = gi * NG; i < (gi + 1) * NG && i < T::NOUT; ++i) m |= 1u << T::order(i);
-    return m;
-}
-GSB_CX int mask_rank(unsigned m, int o) { int r = 0; for (int i = 0; i < o; ++i) if ((m >> i) & 1u) ++r; return r; }
-GSB_CX int mask_count(unsigned m) { int r = 0; for (int i = 0; i < 32; ++i) if ((m >> i) & 1u) ++r; return r; }
-
-template <class T> GSB_CX int used_count(unsigned m) { int n = 0; for (int c = 0; c < T::NIN; ++c) if (T::uses_c(m, c)) ++n; return n; }
-template <class T> GSB_CX int used_rank(unsigned m, int cc) { int n = 0; for (int c = 0; c < cc; ++c) if (T::uses_c(m, c)) ++n; return n; }
 #ifndef GSB200_EMULATE
 GSB_DEVICE void cp_async8(double *dst_smem, const double *src)
 {
@@ -974,160 +873,6 @@ k_sweepw(const GSB_GRID_CONSTANT SweepArgs A)
     }
 #undef GSB_RING
 }
-
-#ifndef GSB200_EMULATE
-// ------------------------------------------------------------------------------------
-// Blackwell variant: the input tile of every knot span is brought into shared memory by the
-// TMA engine (cp.async.bulk, completion on an mbarrier) through an NSTAGE-deep ring, so the
-// HBM latency is hidden behind the FP64 work of the previous spans instead of stalling each
-// warp on its own global loads; all owner-slot groups of a column tile live in ONE CTA and
-// share the tile (the generic variant re-reads it once per group).
-GSB_DEVICE unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-GSB_DEVICE void mbar_init(unsigned long long *bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
-GSB_DEVICE void mbar_expect_tx(unsigned long long *bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory"); }
-GSB_DEVICE void mbar_arrive(unsigned long long *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
-GSB_DEVICE void mbar_wait(unsigned long long *bar, unsigned parity)
-{
-    unsigned ok;
-    do {
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!ok);
-}
-GSB_DEVICE void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-// One tiled-TMA operation (cp.async.bulk.tensor) brings the whole [NIN x NQ x TC] box of a span.
-GSB_DEVICE void tma_box_g2s(void *dst, const void *tmap, const int (&c)[5], int rank, unsigned long long *bar)
-{
-    const unsigned d = smem_u32(dst), b = smem_u32(bar);
-    if (rank == 3)
-        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                     ::"r"(d), "l"(tmap), "r"(b), "r"(c[0]), "r"(c[1]), "r"(c[2]) : "memory");
-    else if (rank == 4)
-        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                     ::"r"(d), "l"(tmap), "r"(b), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]) : "memory");
-    else
-        asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-                     ::"r"(d), "l"(tmap), "r"(b), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]) : "memory");
-}
-struct alignas(64) TensorMapBlob { unsigned char bytes[128]; };   // CUtensorMap, passed by value (__grid_constant__)
-
-// TC columns per CTA, G = P1/IS groups; blockDim.x = TC*G (group = threadIdx.x / TC, warp-uniform).
-// NQ = quadrature points per span (compile time).  ROWB = true when the NQ points of a column are
-// contiguous in memory (in_ts == 1, in_is == NQ): one bulk copy per component; otherwise one per
-// (point, component) row of TC contiguous columns.  Each stage also receives the span's slot-
-// ordered basis table (NQ*P1 double2), so the inner loop touches shared memory only.
-template <int P1, class T, int IS, bool FINAL, int TC, bool ROWB, int NQ, int MINB>
-GSB_GLOBAL void __launch_bounds__(TC * (P1 / IS), MINB) k_sweep_tma(const SweepArgs A, const int tiles_per_outer, const int NSTAGE,
-                                                                    const __grid_constant__ TensorMapBlob tmap, const int use_tmap)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int NIN = T::NIN, G = P1 / IS;
-    constexpr int TAB_DOUBLES = NQ * P1 * 2;
-    constexpr int STAGE_DOUBLES = (NQ * NIN * TC + TAB_DOUBLES + 15) / 16 * 16;   // 128-byte multiple (TMA destination alignment)
-    double *sdata = reinterpret_cast<double *>(smem_raw);
-    unsigned long long *full = reinterpret_cast<unsigned long long *>(sdata + (size_t)NSTAGE * STAGE_DOUBLES);
-    unsigned long long *empty = full + NSTAGE;
-    const int tid = threadIdx.x, grp = tid / TC, lcol = tid - grp * TC, warp = tid >> 5, lane = tid & 31;
-    constexpr int NWARP = TC * G / 32;
-    const int sg = blockIdx.z;
-    const int e_begin = A.seg[4 * sg + 0], e_end = A.seg[4 * sg + 1], x_min = A.seg[4 * sg + 2], x_max = A.seg[4 * sg + 3];
-    const i64 outer = blockIdx.x / tiles_per_outer;
-    const i64 inner0 = (i64)(blockIdx.x - outer * tiles_per_outer) * TC;
-    const int ncols = (int)((A.ninner - inner0) < TC ? (A.ninner - inner0) : TC);
-    const i64 inner = inner0 + lcol;
-    if (tid == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, NWARP); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    const double *tile = A.in + outer * A.in_os + inner0 * A.in_is;
-    const unsigned row_bytes = (unsigned)(ncols * (ROWB ? NQ : 1) * sizeof(double));
-    constexpr int NROWS = ROWB ? NIN : NQ * NIN;
-    auto issue = [&](int e, int s) {   // executed by warp 0: fill stage s (= (e - e_begin) % NSTAGE) with span e
-        double *dst = sdata + (size_t)s * STAGE_DOUBLES;
-        const double *src = tile + (i64)(e - A.e_in0) * A.in_es;
-        if (use_tmap) {       // one box per span (out-of-range columns are zero-filled and still counted)
-            if (lane == 0) {
-                mbar_expect_tx(full + s, NQ * NIN * TC * 8 + TAB_DOUBLES * 8);
-                bulk_g2s(dst + NQ * NIN * TC, A.tab + (i64)e * NQ * P1, TAB_DOUBLES * 8, full + s);
-                int c[5] = {0, 0, 0, 0, 0};
-                c[A.tm_dim_inner] = (int)inner0;
-                c[A.tm_dim_e] = (e - A.e_in0) * A.tm_e_mul;
-                if (A.tm_dim_outer >= 0) c[A.tm_dim_outer] = (int)outer;
-                tma_box_g2s(dst, &tmap, c, A.tm_rank, full + s);
-            }
-            return;
-        }
-        if (lane == 0) {
-            mbar_expect_tx(full + s, row_bytes * NROWS + TAB_DOUBLES * 8);
-            bulk_g2s(dst + NQ * NIN * TC, A.tab + (i64)e * NQ * P1, TAB_DOUBLES * 8, full + s);
-        }
-        __syncwarp();
-        for (int r = lane; r < NROWS; r += 32) {
-            if (ROWB) bulk_g2s(dst + (size_t)r * TC * NQ, src + (i64)r * A.in_cs, row_bytes, full + s);
-            else { const int c = r / NQ, t = r - c * NQ; bulk_g2s(dst + (size_t)r * TC, src + (i64)c * A.in_cs + (i64)t * A.in_ts, row_bytes, full + s); }
-        }
-    };
-    if (warp == 0)
-        for (int e = e_begin; e < e_end && e < e_begin + NSTAGE; ++e) issue(e, e - e_begin);
-
-    FinalCtx fc;
-    i64 obase = 0, obase_mirror = -1;
-    bool live = lcol < ncols;
-    if (FINAL) { if (live) live = final_init(A.fin, outer, inner, fc); }
-    else obase = sweep_obase(A, outer, inner, &obase_mirror);
-    SweepCore<P1, T, IS, FINAL> core;
-    core.zero();
-    core.obase_m = obase_mirror;
-    int f0 = A.first[e_begin], nx = A.nexit[e_begin];
-    int s = 0; unsigned par = 0;
-    for (int e = e_begin; e < e_end; ++e) {
-        // next span's window data: fetched now, consumed one iteration later
-        const int f0n = (e + 1 < e_end) ? A.first[e + 1] : 0, nxn = (e + 1 < e_end) ? A.nexit[e + 1] : 0;
-        mbar_wait(full + s, par);
-        if (live) {
-            const double *sd = sdata + (size_t)s * STAGE_DOUBLES;
-            const double2 *tbs = reinterpret_cast<const double2 *>(sd + NQ * NIN * TC);
-            if (ROWB && (NQ % 2 == 0)) {
-                double vv[NIN][NQ];       // all points of the span in two-double shared-memory loads
-#pragma unroll
-                for (int c = 0; c < NIN; ++c) {
-                    const double2 *p2 = reinterpret_cast<const double2 *>(sd + ((size_t)c * TC + lcol) * NQ);
-#pragma unroll
-                    for (int h = 0; h < NQ / 2; ++h) { const double2 w2 = p2[h]; vv[c][2 * h] = w2.x; vv[c][2 * h + 1] = w2.y; }
-                }
-#pragma unroll
-                for (int t = 0; t < NQ; ++t) {
-                    double v[NIN];
-#pragma unroll
-                    for (int c = 0; c < NIN; ++c) v[c] = vv[c][t];
-                    core.template point<true>(v, tbs + t * P1, grp);
-                }
-            } else {
-#pragma unroll
-                for (int t = 0; t < NQ; ++t) {
-                    double v[NIN];
-#pragma unroll
-                    for (int c = 0; c < NIN; ++c) v[c] = ROWB ? sd[((size_t)c * TC + lcol) * NQ + t] : sd[((size_t)c * NQ + t) * TC + lcol];
-                    core.template point<true>(v, tbs + t * P1, grp);
-                }
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty + s);
-        if (warp == 0 && e + NSTAGE < e_end) {     // refill this stage once every warp has released it
-            mbar_wait(empty + s, par);
-            issue(e + NSTAGE, s);
-        }
-        if (live) core.exits(A, fc, obase, nx, f0, grp, x_min, x_max);
-        f0 = f0n; nx = nxn;
-        if (++s == NSTAGE) { s = 0; par ^= 1u; }
-    }
-}
-#endif
 
 // ------------------------------------------------------------------------------------
 // K3: load vector, one direction at a time: out[i][col] = sum_{q in supp(i)} B_i(q) in[q][col].

@@ -21,12 +21,14 @@ void set_error(const char *fmt, ...);
 #ifndef GSB200_EMULATE
 // ------------------------------------------------------------------ real CUDA
 #include <cuda_runtime.h>
-#define GSB_GLOBAL __global__
+#define GSB_GLOBAL static __global__     // internal linkage: kernels.cuh is included by several translation units
 #define GSB_DEVICE __device__ __forceinline__
 #define GSB_HD __host__ __device__ __forceinline__
 #define GSB_MEMBER __device__ __forceinline__
 #define GSB_LAUNCH(kernel, grid, block, stream, ...) \
     do { if (!gsb::dry_run()) { kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__); gsb::note_launch(); } } while (0)
+// kernels whose CTA cooperates through shared memory (the interpreter build runs them block by block)
+#define GSB_LAUNCH_CTA(kernel, grid, block, stream, ...) GSB_LAUNCH(kernel, grid, block, stream, __VA_ARGS__)
 namespace gsb {
 void note_launch();
 bool dry_run();   // planning pass of assemble(): walk the launch sequence without launching
@@ -105,6 +107,12 @@ static gsb_dim3 blockIdx, threadIdx, blockDim, gridDim;
          for (unsigned bx_ = 0; bx_ < gridDim.x; ++bx_) for (unsigned tz_ = 0; tz_ < blockDim.z; ++tz_) \
          for (unsigned ty_ = 0; ty_ < blockDim.y; ++ty_) for (unsigned tx_ = 0; tx_ < blockDim.x; ++tx_) { \
              blockIdx = gsb_dim3(bx_, by_, bz_); threadIdx = gsb_dim3(tx_, ty_, tz_); kernel(__VA_ARGS__); } \
+         gsb::note_launch(); } while (0)
+// CTA-cooperative kernels: ONE call per block, the kernel body loops over its threads phase by phase (GSB_THREADS in fused.cuh)
+#define GSB_LAUNCH_CTA(kernel, grid, block, stream, ...)                                     \
+    do { if (gsb::dry_run()) break; gridDim = gsb_dim3(grid); blockDim = gsb_dim3(block);     \
+         for (unsigned bz_ = 0; bz_ < gridDim.z; ++bz_) for (unsigned by_ = 0; by_ < gridDim.y; ++by_) \
+         for (unsigned bx_ = 0; bx_ < gridDim.x; ++bx_) { blockIdx = gsb_dim3(bx_, by_, bz_); threadIdx = gsb_dim3(0, 0, 0); kernel(__VA_ARGS__); } \
          gsb::note_launch(); } while (0)
 namespace gsb {
 void note_launch();

@@ -34,7 +34,7 @@ def build_oracle():
 
 
 def build_emul():
-    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "emul")])
+    subprocess.check_call(["make", "-s", "-j4", "-C", os.path.join(ROOT, "tests", "emul")])
 
 
 _oracle = None
