@@ -31,6 +31,7 @@ struct FusedArgs {
     const int *seg;                                     // [gridDim.z][4] e_begin, e_end, x_min, x_max
     int ncolL, nrows;                                   // columns along the last direction (a tile never straddles a row); rows (3-D: Q1, 2-D: 1)
     double *out; i64 out_cs, out_fs, out_bq, out_bs, out_is; int d_off;      // A1 addressing (as SweepArgs); the delta stride is p+1 (blocked layouts)
+    i64 out_ds;                                         // ... or, ROWS layout A1[o][i0][d0][q1][q2]: the (runtime) stride of a delta row
     double *v1; i64 v1_cs, v1_fs; int nf;               // first load-vector sweep: V1[c][i0][column]
 };
 
@@ -130,7 +131,7 @@ template <int P1, class T> GSB_CX int fused_smem(int nb)
 }
 template <int P1, class T, int NG> GSB_CX int fused_threads() { return GSB_FUSE_TC * (P1 + (T::NOUT + NG - 1) / NG); }
 
-template <int DIM, int P1, class T, int NG, int PGL, bool RATIONAL, int FSPEC>
+template <int DIM, int P1, class T, int NG, int PGL, bool RATIONAL, int FSPEC, bool ROWS = false>
 GSB_DEVICE void geo_sweep_body(const FusedArgs &A)
 {
     static_assert(fused_one_term_per_output<T>(), "first-sweep tables have one term per output");
@@ -174,7 +175,7 @@ GSB_DEVICE void geo_sweep_body(const FusedArgs &A)
         if (tid < NCONS) {
             const int grp = tid / TC;
             const i64 inner = (i64)row * A.ncolL + colc;
-            const i64 obase = (inner / A.out_bq) * A.out_bs + (inner % A.out_bq) * A.out_is + (i64)A.d_off * DS + (i64)A.first[e_begin] * A.out_fs;
+            const i64 obase = (inner / A.out_bq) * A.out_bs + (inner % A.out_bq) * A.out_is + (i64)A.d_off * (ROWS ? A.out_ds : (i64)DS) + (i64)A.first[e_begin] * A.out_fs;
             th.ngv = 0;
 #pragma unroll
             for (int g = 0; g < NG; ++g) {
@@ -305,16 +306,32 @@ GSB_DEVICE void geo_sweep_body(const FusedArgs &A)
         const bool mine = th.live && x >= seg_xmin && x < seg_xmax;
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
-            if (mine && (FULLG || g < th.ngv)) {
-                double *po = th.pw[g];
+            if constexpr (ROWS) {
+                // every (function, delta) row of A1 is contiguous along the columns: a completed pair is stored at once, by owner
+                if (th.live && (FULLG || g < th.ngv)) {
+                    double *po = th.pw[g];
+                    if (x >= seg_xmin && x < seg_xmax) {
 #pragma unroll
-                for (int j = P1 - 1; j >= 1; --j) st_stream(po - j * DS, th.hold[S][j][g]);
+                        for (int b = 0; b < P1; ++b) { st_stream(po, th.acc[S][(S + b) % P1][g]); po += A.out_ds; }
+                    }
+                    const i64 sa = A.out_fs - A.out_ds;        // owner x + a, delta -a
+                    po = th.pw[g];
 #pragma unroll
-                for (int b = 0; b < P1; ++b) st_stream(po + b * DS, th.acc[S][(S + b) % P1][g]);
+                    for (int a = 1; a < P1; ++a) { po += sa; if (x + a >= seg_xmin && x + a < seg_xmax) st_stream(po, th.acc[(S + a) % P1][S][g]); }
+                }
+                th.pw[g] += A.out_fs;
+            } else {
+                if (mine && (FULLG || g < th.ngv)) {
+                    double *po = th.pw[g];
+#pragma unroll
+                    for (int j = P1 - 1; j >= 1; --j) st_stream(po - j * DS, th.hold[S][j][g]);
+#pragma unroll
+                    for (int b = 0; b < P1; ++b) st_stream(po + b * DS, th.acc[S][(S + b) % P1][g]);
+                }
+                th.pw[g] += A.out_fs;
+#pragma unroll
+                for (int a = 1; a < P1; ++a) th.hold[(S + a) % P1][a][g] = th.acc[(S + a) % P1][S][g];
             }
-            th.pw[g] += A.out_fs;
-#pragma unroll
-            for (int a = 1; a < P1; ++a) th.hold[(S + a) % P1][a][g] = th.acc[(S + a) % P1][S][g];
 #pragma unroll
             for (int k = 0; k < P1; ++k) { th.acc[S][k][g] = 0.0; th.acc[k][S][g] = 0.0; }
         }
@@ -394,9 +411,9 @@ GSB_DEVICE void geo_sweep_body(const FusedArgs &A)
 #undef GSB_TH
 }
 
-template <int DIM, int P1, class T, int NG, int PGL, bool RATIONAL, int FSPEC>
+template <int DIM, int P1, class T, int NG, int PGL, bool RATIONAL, int FSPEC, bool ROWS = false>
 GSB_GLOBAL void
 #ifndef GSB200_EMULATE
 __launch_bounds__((fused_threads<P1, T, NG>()), (512 / fused_threads<P1, T, NG>() > 0 ? 512 / fused_threads<P1, T, NG>() : 1))
 #endif
-k_geo_sweep(const GSB_GRID_CONSTANT FusedArgs A) { geo_sweep_body<DIM, P1, T, NG, PGL, RATIONAL, FSPEC>(A); }
+k_geo_sweep(const GSB_GRID_CONSTANT FusedArgs A) { geo_sweep_body<DIM, P1, T, NG, PGL, RATIONAL, FSPEC, ROWS>(A); }

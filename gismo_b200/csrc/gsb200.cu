@@ -35,7 +35,7 @@ int grant_dynamic_smem(const void *kfn, size_t smem)
     int dev = 0; cudaGetDevice(&dev);
     std::lock_guard<std::mutex> lock(mu);
     if (granted.count({dev, kfn})) return 0;
-    GSB_TRY(dev_check(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "cudaFuncSetAttribute"));
+    GSB_TRY(dev_check(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "cudaFuncSetAttribute"));
     granted.insert({dev, kfn});
     return 0;
 }
@@ -450,10 +450,12 @@ static int assemble_pass(gsb200_assembler *a)
         // K0 fused into the first sweep (fused.cuh): D and F stay in shared memory.  Needs the p+1-point rule in direction 0 (window
         // accumulators) and a geometry whose last-direction functions per column tile fit the line-coefficient buffer.
         static const bool fuse_env = [] { const char *e = getenv("GSB200_FUSE"); return !e || atoi(e) > 0; }();
-        const bool fused = fuse_env && P.d_lc && d0.q == d0.p + 1 && dL.q == d0.q && d0.p >= 1 && d0.p <= 4 && nf <= GSB_FUSE_MAXF && (dim == 2 || a1_blk);
+        const bool fused = fuse_env && P.d_lc && d0.q == d0.p + 1 && dL.q == d0.q && d0.p >= 1 && d0.p <= 4 && nf <= GSB_FUSE_MAXF;     // (the rows layout is chosen below when the next two sweeps are fused as well)
+        // second + last sweep fused (fused23.cuh): A1 in rows layout, A2 never exists.  3-D gradient forms, degrees 1..3, p+1-point rules.
+        const bool s23 = fused && dim == 3 && a1_env < 0 && d1.q == d1.p + 1 && dL.q == dL.p + 1 && d1.p == dL.p && s23_available(kind, d1.p + 1);
         const int nfv = std::max(nf, 1);
         // doubles of workspace per last-direction quadrature point
-        i64 perq = (fused ? 0 : ncD * Q0 * Q1 + nf * Q0 * Q1) + no1 * NI0 * Q1 + (dim == 3 ? no2 * NI1 * NI0 : 0) + nfv * n0 * Q1 + (dim == 3 ? n1 * n0 : 0);
+        i64 perq = (fused ? 0 : ncD * Q0 * Q1 + nf * Q0 * Q1) + no1 * NI0 * Q1 + (dim == 3 && !s23 ? no2 * NI1 * NI0 : 0) + nfv * n0 * Q1 + (dim == 3 ? n1 * n0 : 0);
         i64 maxpts = limit / (perq * 8);
         const i64 minpts = (i64)(dL.p + 1) * dL.q;
         if (maxpts < minpts) { set_error("workspace limit %lld B too small: one slab of patch %zu needs %lld B", (long long)limit, ip, (long long)(perq * 8 * minpts)); return GSB200_ENOMEM; }
@@ -474,7 +476,7 @@ static int assemble_pass(gsb200_assembler *a)
             auto carve = [&](i64 count) { double *p = w; w += (count + 31) / 32 * 32; return p; };   // 256-byte aligned pieces
             double *D = carve(fused ? 0 : ncD * Q0 * Q1 * QLc);
             double *A1 = carve(no1 * NI0 * Q1 * QLc);
-            double *A2 = carve(dim == 3 ? no2 * NI1 * NI0 * QLc : 0);
+            double *A2 = carve(dim == 3 && !s23 ? no2 * NI1 * NI0 * QLc : 0);
             double *F = carve(fused ? 0 : nf * Q0 * Q1 * QLc);
             double *V1 = carve(nfv * n0 * Q1 * QLc);
             double *V2 = carve(dim == 3 ? n1 * n0 * QLc : 0);
@@ -560,10 +562,10 @@ static int assemble_pass(gsb200_assembler *a)
                         FA.first = d0.d_first; FA.nexit = d0.d_nexit; FA.tab = d0.d_tab; FA.seg = A.seg; FA.lc = P.d_lc; FA.lc_nL = dL.ngeo;
                         FA.ncolL = (int)ncolL; FA.nrows = (int)nrows;
                         FA.out = A.out; FA.out_cs = A.out_cs; FA.out_fs = A.out_fs; FA.out_bq = A.out_bq; FA.out_bs = A.out_bs; FA.out_is = A.out_is;
-                        FA.d_off = A.d_off;
+                        FA.d_off = A.d_off; FA.out_ds = A.out_ds;
                         FA.nf = with_load ? nf : 0; FA.v1 = V1; FA.v1_fs = A.ncol; FA.v1_cs = n0 * A.ncol;
                         { FusedCtx fc; fc.progs = &a->progs_host; fc.device = a->device; fc.jit_launches = &a->jit_launches;
-                          GSB_TRY(launch_fused(fc, kind, dim, d0.p + 1, FA, (int)seg.size() / 4, s, hot, rat, pgl, &fpp)); }
+                          GSB_TRY(launch_fused(fc, kind, dim, d0.p + 1, FA, (int)seg.size() / 4, s, hot, rat, pgl, s23 || a1_gather, &fpp)); }
                         account(0, A, seg, fpp, 0, nout, NI0);
                     } else {
                         GSB_TRY(dispatch_sweep(kind, stage, d0.p + 1, A, (int)seg.size() / 4, s, &fpp));
@@ -578,11 +580,43 @@ static int assemble_pass(gsb200_assembler *a)
                         A.in = D; A.in_cs = npts; A.in_es = (i64)d0.q * Q1 * QLc; A.in_ts = Q1 * QLc; A.in_os = 0; A.in_is = 1; A.e_in0 = 0;
                         A.ncol = Q1 * QLc; A.ninner = A.ncol;
                         A.out = A1; A.out_cs = NI0 * Q1 * QLc; A.out_fs = (2 * d0.p + 1) * Q1 * QLc; A.out_ds = Q1 * QLc; A.out_os = 0; A.out_bq = A.ncol + 1; A.out_bs = 0; A.out_is = 1;
-                        if (a1_blk) {    // A1[o][i0][q1][e2][d0][t]: the second sweep then reads AND writes whole (d0, t) runs
+                        if (a1_blk && !s23) {    // A1[o][i0][q1][e2][d0][t]: the second sweep then reads AND writes whole (d0, t) runs
                             A.out_fs = Q1 * ELc * W0 * dL.q; A.out_ds = dL.q; A.out_bq = dL.q; A.out_bs = W0 * dL.q; A.out_is = 1;
                         }
                         GSB_TRY(first_sweep(A, 0, QLc, Q1));
                     }
+                    if (s23) {   // S2 + S3 in one kernel: rows of A2 go from the direction-1 warps to the direction-2 warps through shared memory
+                        S23Args SA; memset(&SA, 0, sizeof SA);
+                        SA.first1 = d1.d_first; SA.nexit1 = d1.d_nexit; SA.tab1 = d1.d_tab;
+                        SA.first2 = dL.d_first; SA.tabl2 = dL.d_tabl; SA.ffirst2 = dL.d_ffirst; SA.flast2 = dL.d_flast;
+                        SA.e_in0 = eL0; SA.a1 = A1; SA.a1_cs = NI0 * Q1 * QLc; SA.a1_row = Q1 * QLc; SA.a1_q1 = QLc;
+                        SA.n0 = (int)n0; SA.W0 = (int)W0; SA.fin = Fa;
+                        // tiles of the last direction: as few as keep every tile within S23_NEMAX spans
+                        std::vector<int> tiles; int ne_max = 0;
+                        for (int nt = 1;; ++nt) {
+                            tiles = make_segments(dL, x_lo, x_hi, nt);
+                            ne_max = 0;
+                            for (size_t k = 0; k < tiles.size(); k += 4) ne_max = std::max(ne_max, tiles[k + 1] - tiles[k]);
+                            if (ne_max <= S23_NEMAX || nt >= x_hi - x_lo) break;
+                        }
+                        if (ne_max > S23_NEMAX) { set_error("a function of the last direction spans more than %d elements", S23_NEMAX); return GSB200_EUNSUPPORTED; }
+                        const i64 ncta = NI0 * (i64)(tiles.size() / 4);
+                        int nseg1 = (int)std::max<i64>(1, std::min<i64>((2 * 148 + ncta - 1) / ncta, std::max(1, d1.nfun / (4 * (d1.p + 1)))));
+                        std::vector<int> seg1 = make_segments(d1, 0, d1.nfun, nseg1);
+                        SA.tiles = a->d_seg + segoff; GSB_TRY(upload_segments(a, tiles, &segoff));
+                        SA.seg1 = a->d_seg + segoff; GSB_TRY(upload_segments(a, seg1, &segoff));
+                        mark(a, 2);
+                        i64 fpp2 = 0, fpp3 = 0;
+                        const dim3 grid((unsigned)NI0, (unsigned)(tiles.size() / 4), (unsigned)(seg1.size() / 4));
+                        GSB_TRY(launch_s23(kind, d1.p + 1, SA, grid, ne_max, s, &fpp2, &fpp3));
+                        stage_io(kind, 1, &nin, &nout);
+                        {   // accounting: direction-1 work per tile point, direction-2 work per pair and span; bytes: A1 read once per tile span, K written once
+                            i64 pts2 = 0; for (size_t k = 0; k < tiles.size(); k += 4) pts2 += (i64)(tiles[k + 1] - tiles[k]) * dL.q;
+                            i64 pts1 = 0; for (size_t k = 0; k < seg1.size(); k += 4) pts1 += (i64)(seg1[k + 1] - seg1[k]) * d1.q;
+                            a->tm.sweep_flops[1] += fpp2 * NI0 * pts2 * pts1 + fpp3 * NI0 * NI1 * pts2;
+                            a->tm.sweep_bytes[1] += (i64)(8.0 * (nin * (double)NI0 * (double)pts2 * (double)pts1 + (double)NI0 * (double)NI1 * (double)(x_hi - x_lo) * (2 * dL.p + 1)));
+                        }
+                    } else {
                     {   // S2: direction 1
                         SweepArgs A = base_args(d1);
                         A.in = A1; A.in_cs = NI0 * Q1 * QLc; A.in_es = (i64)d1.q * QLc; A.in_ts = QLc; A.in_os = Q1 * QLc; A.in_is = 1; A.e_in0 = 0;
@@ -620,6 +654,7 @@ static int assemble_pass(gsb200_assembler *a)
                         mark(a, 3);
                         GSB_TRY(dispatch_sweep(kind, 2, dL.p + 1, A, (int)seg.size() / 4, s, &fpp));
                         stage_io(kind, 2, &nin, &nout); account(2, A, seg, fpp, nin, nout, (i64)(x_hi - x_lo) * (2 * dL.p + 1));
+                    }
                     }
                 } else {
                     {   // S1: direction 0

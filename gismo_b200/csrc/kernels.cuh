@@ -874,6 +874,8 @@ k_sweepw(const GSB_GRID_CONSTANT SweepArgs A)
 #undef GSB_RING
 }
 
+#include "fused23.cuh"    // second + last sweep of 3-D forms in one kernel (A2 stays in shared memory)
+
 // ------------------------------------------------------------------------------------
 // K3: load vector, one direction at a time: out[i][col] = sum_{q in supp(i)} B_i(q) in[q][col].
 struct VSweepArgs {

@@ -36,13 +36,17 @@ int dispatch_sweep(int kind, int stage, int P1, const SweepArgs &A, int nseg, st
 
 // K0 fused into the first sweep (fused.cuh)
 struct FusedCtx { const std::vector<HostProgram> *progs; int device; int *jit_launches; };
-int launch_fused(const FusedCtx &ctx, int kind, int dim, int P1, const FusedArgs &FA, int nseg, stream_t s, bool hot, bool rat, int pgl, i64 *fpp);
+int launch_fused(const FusedCtx &ctx, int kind, int dim, int P1, const FusedArgs &FA, int nseg, stream_t s, bool hot, bool rat, int pgl, bool rows, i64 *fpp);
+
+// second + last sweep of a 3-D form in one kernel (fused23.cuh); ne_max = longest tile (spans of the last direction)
+int launch_s23(int kind, int P1, const S23Args &A, dim3 grid, int ne_max, stream_t s, i64 *fpp2, i64 *fpp3);
+bool s23_available(int kind, int P1);
 
 #ifndef GSB200_EMULATE
 // more than 48 KB of dynamic shared memory has to be granted per kernel AND per device
 int grant_dynamic_smem(const void *kfn, size_t smem);
 cudaKernel_t jit_geometry_kernel(const std::vector<HostProgram> &progs, int device, int dim, int pgl, bool rational, int fspec);
-cudaKernel_t jit_fused_kernel(const std::vector<HostProgram> &progs, int device, int dim, int p1, const char *table, int ng, int nthr, int pgl, bool rational, int fspec);
+cudaKernel_t jit_fused_kernel(const std::vector<HostProgram> &progs, int device, int dim, int p1, const char *table, int ng, int nthr, int pgl, bool rational, int fspec, bool rows);
 #endif
 
 } // namespace gsb

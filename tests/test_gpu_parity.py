@@ -69,7 +69,7 @@ def test_cuda_matches_oracle_on_seeded_random_inputs(lib, dim, p, m, seed):
 def test_chunked_equals_unchunked_bitwise_and_deterministic(lib):
     pb, z = G.load("cube_p3_m16", g.expr_compile)
     a = R.lib_assemble(lib, pb)
-    b = R.lib_assemble(lib, pb, workspace_limit=40_000_000)
+    b = R.lib_assemble(lib, pb, workspace_limit=15_000_000)
     c = R.lib_assemble(lib, pb)
     assert b[4].nchunks > 1
     assert np.array_equal(a[2], b[2]) and np.array_equal(a[1], b[1])

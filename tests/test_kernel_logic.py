@@ -29,7 +29,7 @@ def test_interpreted_kernels_match_reference(emul, name):
     G.check_against(R.lib_assemble(emul, pb), z, TOL)
 
 
-@pytest.mark.parametrize("name,limit", [("cube_p3_curved_m4", 7_000_000), ("sq_p2_m64", 300_000), ("grid2x2_p2_m4", 11_000)])
+@pytest.mark.parametrize("name,limit", [("cube_p3_curved_m4", 3_000_000), ("sq_p2_m64", 300_000), ("grid2x2_p2_m4", 11_000)])
 def test_chunked_assembly_under_workspace_cap(emul, name, limit):
     pb, z = G.load(name, R.emul_compile)
     res = R.lib_assemble(emul, pb, workspace_limit=limit)
