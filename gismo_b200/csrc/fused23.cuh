@@ -18,12 +18,12 @@
 // Row sets go round a two-deep ring with full/empty mbarriers; the S3 warps use a named barrier between their two phases.
 // Every matrix entry is still produced exactly once, by one thread: no atomics for free rows, deterministic.
 #define S23_NS2T 256          // S2 threads (one per direction-2 quadrature point of the tile): two warpgroups
-#define S23_NS3T 128          // S3 threads: one warpgroup
-#define S23_NEMAX 52          // spans of direction 2 per tile; padded row length: = 4 or 12 (mod 16) keeps both access patterns conflict-free
+#define S23_NS3T 256          // S3 threads: two warpgroups (their work is as large as the S2 side's and has less instruction-level parallelism)
+#define S23_NEMAX 52          // spans of direction 2 per tile = row length of the shared-memory arrays: 4 (mod 16) keeps both access patterns conflict-free
 #define S23_NSTG 3            // cp.async ring: points of direction 1 in flight
 #ifndef S23_S2REG
-#define S23_S2REG 184         // registers per S2 / S3 thread after the split (setmaxnreg): 256 * 184 + 128 * 104 <= 64 K
-#define S23_S3REG 104
+#define S23_S2REG 184         // registers per S2 / S3 thread after the split (setmaxnreg): 256 * 184 + 256 * 72 = 64 K
+#define S23_S3REG 72
 #endif
 
 struct S23Args {
@@ -38,11 +38,10 @@ struct S23Args {
     FinalArgs fin;
 };
 
-GSB_CX int s23_nep(int ne) { return ne <= 4 ? 4 : (ne <= 12 ? 12 : (ne <= 20 ? 20 : (ne <= 28 ? 28 : (ne <= 36 ? 36 : (ne <= 44 ? 44 : 52))))); }
 // dynamic shared memory (doubles) for a tile of ne spans
-template <int P1, class T2> GSB_CX int s23_smem_doubles(int ne)
+template <int P1, class T2> GSB_CX int s23_smem_doubles()
 {
-    const int nep = s23_nep(ne), NP = 2 * P1 - 1;
+    const int nep = S23_NEMAX, NP = 2 * P1 - 1;
     return S23_NSTG * T2::NIN * S23_NS2T                  // A1 ring
          + 2 * NP * T2::NOUT * P1 * nep                   // row sets
          + NP * P1 * P1 * nep                             // local pair integrals
@@ -75,7 +74,8 @@ GSB_DEVICE void s23_body(const S23Args &A, double *smem)
     const int tl = blockIdx.y, sg = blockIdx.z;
     const int e2b = A.tiles[4 * tl + 0], e2e = A.tiles[4 * tl + 1], x2min = A.tiles[4 * tl + 2], x2max = A.tiles[4 * tl + 3];
     const int e1b = A.seg1[4 * sg + 0], e1e = A.seg1[4 * sg + 1], x1min = A.seg1[4 * sg + 2], x1max = A.seg1[4 * sg + 3];
-    const int NE = e2e - e2b, NEP = s23_nep(NE), NOWN = x2max - x2min;
+    constexpr int NEP = S23_NEMAX;
+    const int NE = e2e - e2b, NOWN = x2max - x2min;
     // ---- shared memory carve-up
     double *ring = smem;                                         // [stage][component][S2 thread]
     double *rows = ring + S23_NSTG * NIN * NS2T;                 // [buffer][pair][component][t2][span]
@@ -86,8 +86,9 @@ GSB_DEVICE void s23_body(const S23Args &A, double *smem)
     int *first2s = (int *)(bars + 8);                            // first function of every span of the tile
     int *ff2s = first2s + S23_NEMAX + 2;                         // first / last span of the functions [x2min - p, x2max + p) ...
     int *fl2s = ff2s + S23_NEMAX + 2 * GSB_MAXP + 2;
-    int *dlo2s = fl2s + S23_NEMAX + 2 * GSB_MAXP + 2;            // ... and, per owned function, the partner range dlo | dhi << 8 (+ 128 each)
-    const int ROWSET = NP * NOUT * P1 * NEP;
+    int *dlo2s = fl2s + S23_NEMAX + 2 * GSB_MAXP + 2;            // ... and, per owned function: partner range (dlo + 8) | (dhi + 8) << 4, first span in the tile << 8,
+                                                                 // number of spans << 16, local index of the function in span m at bits 20 + 3 m
+    constexpr int ROWSET = NP * NOUT * P1 * NEP;
 #ifdef GSB200_EMULATE
     static thread_local S23Thread<P1, T2> *states = 0; static thread_local int nstates = 0;
     if (nstates < NS2T) { delete[] states; states = new S23Thread<P1, T2>[NS2T]; nstates = NS2T; }
@@ -110,7 +111,12 @@ GSB_DEVICE void s23_body(const S23Args &A, double *smem)
             const bool ok = j2 >= 0 && j2 < F.n[2];
             ff2s[it] = ok ? A.ffirst2[j2] : 0; fl2s[it] = ok ? A.flast2[j2] : -1;
         }
-        for (int it = tid; it < NOWN; it += NTHR) { const int i2 = x2min + it; dlo2s[it] = (F.plo[2][i2] - i2 + 128) | ((F.phi[2][i2] - i2 + 128) << 8); }
+        for (int it = tid; it < NOWN; it += NTHR) {
+            const int i2 = x2min + it, ea = A.ffirst2[i2], eb = A.flast2[i2];
+            unsigned w = (unsigned)(F.plo[2][i2] - i2 + 8) | ((unsigned)(F.phi[2][i2] - i2 + 8) << 4) | ((unsigned)(ea - e2b) << 8) | ((unsigned)(eb - ea + 1) << 16);
+            for (int e = ea; e <= eb; ++e) w |= (unsigned)(i2 - A.first2[e]) << (20 + 3 * (e - ea));
+            dlo2s[it] = (int)w;
+        }
         if (tid < NS2T) {
             S23Thread<P1, T2> &th = S23_TH;
 #pragma unroll
@@ -197,10 +203,15 @@ GSB_DEVICE void s23_body(const S23Args &A, double *smem)
     };
 
     // ================================================================= S3 role
-    // (1) local pair integrals of one span for one pair: local[k][a * P1 + b][el] = sum_t2 sum_g B^(ag)_a B^(bg)_b row_g
+    // (1) local pair integrals of one span for one pair: local[k][a * P1 + b][el] = sum_t2 sum_g B^(ag)_a B^(bg)_b row_g.
+    // thread = (span el, quarter kq of the pairs): pairs kq and kq + 4
     auto s3_local = [&](int s3tid, int rb) {
-        for (int item = s3tid; item < NP * NE; item += NS3T) {
-            const int k = item / NE, el = item - k * NE;
+        const int el = s3tid % NEP, kq = s3tid / NEP;
+        if (el >= NE || kq >= 4) return;
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+            const int k = kq + 4 * kk;
+            if (k >= NP) break;
             double acc[P1][P1];
 #pragma unroll
             for (int a = 0; a < P1; ++a)
@@ -262,22 +273,34 @@ GSB_DEVICE void s23_body(const S23Args &A, double *smem)
             fc.li_low = (i64)i1 * F.n[0] + i0; fc.dj_low = (i64)d1 * F.n[0] + d0; fc.nlow = nlow;
             fc.r_low = d1 + F.p[1]; fc.bit0 = d0 + F.p[0];
             const int flag = (int)(rec[r] & 3);
-            const int dw = dlo2s[i2l], dlo = (dw & 255) - 128, dhi = (dw >> 8) - 128;
-            const int ea = ff2s[i2l + P1 - 1], eb = fl2s[i2l + P1 - 1];
-            const double *lk = local + (k * P1 * P1) * NEP;
+            const unsigned dw = (unsigned)dlo2s[i2l];
+            const int dlo = (int)(dw & 15u) - 8, dhi = (int)((dw >> 4) & 15u) - 8, el0 = (int)((dw >> 8) & 255u), ns = (int)((dw >> 16) & 15u);
+            const double *lk = local + (k * P1 * P1) * NEP + el0;
             double *vbase = F.values + (rec[r] >> 2) + F.brow * full + (i64)fc.r_low * W0 + fc.bit0;
-            for (int dd = dlo; dd <= dhi; ++dd) {
-                const int es = dd > 0 ? ff2s[i2l + P1 - 1 + dd] : ea, ee = dd < 0 ? fl2s[i2l + P1 - 1 + dd] : eb;     // spans shared by i2 and i2 + dd
-                double val = 0.0;
-                for (int e = es; e <= ee; ++e) {
-                    const int la = i2 - first2s[e - e2b];
-                    val += lk[(la * P1 + la + dd) * NEP + (e - e2b)];
+            // all (partner, span) combinations at once: independent shared-memory reads, no dependent index look-ups
+            double val[2 * P1 - 1];
+#pragma unroll
+            for (int q = 0; q < 2 * P1 - 1; ++q) val[q] = 0.0;
+#pragma unroll
+            for (int m = 0; m < P1; ++m) {
+                if (m < ns) {
+                    const int la = (int)((dw >> (20 + 3 * m)) & 7u);
+#pragma unroll
+                    for (int q = 0; q < 2 * P1 - 1; ++q) {
+                        const int lb = la + q - (P1 - 1);
+                        if (lb >= 0 && lb < P1) val[q] += lk[(la * P1 + lb) * NEP + m];
+                    }
                 }
-                if (flag == 3) st_stream(vbase + (i64)(dd + p2) * W1 * W0, val);
+            }
+#pragma unroll
+            for (int q = 0; q < 2 * P1 - 1; ++q) {
+                const int dd = q - (P1 - 1);
+                if (dd < dlo || dd > dhi) continue;
+                if (flag == 3) st_stream(vbase + (i64)(dd + p2) * W1 * W0, val[q]);
                 else {
                     const int run = (dd + p2) * W1 + fc.r_low;
-                    if (flag == 1) final_canonical(F, fc, i2, rec[r], dd, run, val);
-                    else final_slow(F, fc, i2, rec[r], dd, val);
+                    if (flag == 1) final_canonical(F, fc, i2, rec[r], dd, run, val[q]);
+                    else final_slow(F, fc, i2, rec[r], dd, val[q]);
                 }
             }
         }
@@ -390,7 +413,7 @@ template <int P1, class T2>
 GSB_GLOBAL void k_s23(const S23Args A)
 {
     static thread_local double *buf = 0;
-    const size_t n = (size_t)s23_smem_doubles<P1, T2>(S23_NEMAX);
+    const size_t n = (size_t)s23_smem_doubles<P1, T2>();
     if (!buf) buf = new double[n];
     for (size_t i = 0; i < n; ++i) buf[i] = 0.0;
     s23_body<P1, T2>(A, buf);

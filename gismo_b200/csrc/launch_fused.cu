@@ -59,7 +59,11 @@ int launch_fused(const FusedCtx &a, int kind, int dim, int P1, const FusedArgs &
 // ------------------------------------------------------------------ fused second + last sweep (fused23.cuh)
 bool s23_available(int kind, int P1)
 {
-    static const bool env = [] { const char *e = getenv("GSB200_S23"); return !e || atoi(e) > 0; }();
+    // opt-in (GSB200_S23=1): measured on B200 the fused kernel removes 25 GB of HBM traffic per assembly at config 2 but is bound by
+    // instruction issue / shared-memory latency of the direction-2 warps (23.8 ms against 8.8 ms for the two separate sweeps):
+    // profiles/r02_s23_experiment.txt
+    const char *e = getenv("GSB200_S23");      // read at every assembly: the tests switch it
+    const bool env = e && atoi(e) > 0;
     return env && kind != KIND_MASS && P1 >= 2 && P1 <= 4;
 }
 template <int P1, class T2>
@@ -69,7 +73,8 @@ static int launch_s23_t(const S23Args &A, dim3 grid, int ne_max, stream_t s, i64
     *fpp3 = (i64)P1 * (2 * TLast::NT - n_first<TLast>() + 2 * P1 * n_has<TLast>());
     auto kfn = k_s23<P1, T2>;
 #ifndef GSB200_EMULATE
-    const size_t smem = (size_t)s23_smem_doubles<P1, T2>(ne_max) * sizeof(double);
+    (void)ne_max;
+    const size_t smem = (size_t)s23_smem_doubles<P1, T2>() * sizeof(double);
     GSB_TRY(grant_dynamic_smem((const void *)kfn, smem));
     if (!dry_run()) { kfn<<<grid, dim3(S23_NS2T + S23_NS3T), smem, s>>>(A); note_launch(); }
 #else

@@ -69,7 +69,7 @@ def test_cuda_matches_oracle_on_seeded_random_inputs(lib, dim, p, m, seed):
 def test_chunked_equals_unchunked_bitwise_and_deterministic(lib):
     pb, z = G.load("cube_p3_m16", g.expr_compile)
     a = R.lib_assemble(lib, pb)
-    b = R.lib_assemble(lib, pb, workspace_limit=15_000_000)
+    b = R.lib_assemble(lib, pb, workspace_limit=30_000_000)
     c = R.lib_assemble(lib, pb)
     assert b[4].nchunks > 1
     assert np.array_equal(a[2], b[2]) and np.array_equal(a[1], b[1])
@@ -228,3 +228,11 @@ def test_gismo_shim_dropin(lib):
     out = subprocess.run([exe], capture_output=True, text=True, timeout=900)
     print(out.stdout[-2000:], out.stderr[-2000:])
     assert out.returncode == 0 and "SHIM RESULT PASS" in out.stdout
+
+
+@pytest.mark.parametrize("name", ["cube_p2_m5", "cube_p3_m16", "cube_p3_curved_m4", "elasticity_8cubes_p2_m5"])
+def test_fused_second_and_last_sweep_opt_in(lib, name, monkeypatch):
+    """GSB200_S23=1 (opt-in, profiles/r02_s23_experiment.txt): same matrix as the default path and the reference."""
+    monkeypatch.setenv("GSB200_S23", "1")
+    pb, z = G.load(name, g.expr_compile)
+    G.check_against(R.lib_assemble(lib, pb), z, TOL)

@@ -29,7 +29,7 @@ def test_interpreted_kernels_match_reference(emul, name):
     G.check_against(R.lib_assemble(emul, pb), z, TOL)
 
 
-@pytest.mark.parametrize("name,limit", [("cube_p3_curved_m4", 3_000_000), ("sq_p2_m64", 300_000), ("grid2x2_p2_m4", 11_000)])
+@pytest.mark.parametrize("name,limit", [("cube_p3_curved_m4", 7_000_000), ("sq_p2_m64", 300_000), ("grid2x2_p2_m4", 11_000)])
 def test_chunked_assembly_under_workspace_cap(emul, name, limit):
     pb, z = G.load(name, R.emul_compile)
     res = R.lib_assemble(emul, pb, workspace_limit=limit)
@@ -95,3 +95,11 @@ def test_other_quadrature_sizes_take_the_generic_kernels(emul, dim, p, m, quA, q
     pb.struct.quA, pb.struct.quB = quA, quB
     ok, msg = R.compare_csc(R.lib_assemble(emul, pb), R.oracle_assemble(pb), TOL)
     assert ok, msg
+
+
+@pytest.mark.parametrize("name", ["cube_p1_m5", "cube_p2_m5", "cube_p3_curved_m4", "grid2x2x2_p2_m3", "elasticity_2cubes_p2"])
+def test_fused_second_and_last_sweep(emul, name, monkeypatch):
+    """GSB200_S23=1: directions 1 and 2 contracted in one kernel (fused23.cuh), rows of A2 through shared memory."""
+    monkeypatch.setenv("GSB200_S23", "1")
+    pb, z = G.load(name, R.emul_compile)
+    G.check_against(R.lib_assemble(emul, pb), z, TOL)
