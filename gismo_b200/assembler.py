@@ -90,6 +90,27 @@ class DeviceAssembler:
         check(self.lib.gsb200_assemble_to_host(self._h, outer.ctypes.data_as(_ip), inner.ctypes.data_as(_ip), values.ctypes.data_as(_dp),
                                                rhs.ctypes.data_as(_dp) if rhs is not None else None))
 
+    def pattern_into(self, outer: np.ndarray, inner: np.ndarray) -> None:
+        """gsb200_download_pattern: the index arrays, once per mesh."""
+        if not self._pattern:
+            self.buildPattern()
+        check(self.lib.gsb200_download_pattern(self._h, outer.ctypes.data_as(_ip), inner.ctypes.data_as(_ip)))
+
+    def set_fixed(self, fixed: Optional[np.ndarray]) -> None:
+        """gsb200_set_fixed: new eliminated-DOF values (nfixed x nrhs, column-major) on the kept pattern."""
+        if fixed is None:
+            check(self.lib.gsb200_set_fixed(self._h, None))
+        else:
+            f = np.asfortranarray(fixed, dtype=np.float64)
+            check(self.lib.gsb200_set_fixed(self._h, f.ctypes.data_as(_dp)))
+
+    def assemble_values_into(self, values: np.ndarray, rhs: Optional[np.ndarray] = None) -> None:
+        """gsb200_assemble_values_to_host: re-assembly on the kept pattern, values (+ rhs) only travel."""
+        if not self._pattern:
+            self.buildPattern()
+        check(self.lib.gsb200_assemble_values_to_host(self._h, values.ctypes.data_as(_dp),
+                                                      rhs.ctypes.data_as(_dp) if rhs is not None else None))
+
     def rhs(self) -> np.ndarray:
         r = np.zeros((self.problem.nfree, self.problem.nrhs), np.float64, order="F")
         check(self.lib.gsb200_download_rhs(self._h, r.ctypes.data_as(_dp)))

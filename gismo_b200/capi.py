@@ -201,6 +201,11 @@ def load_library():
     lib.gsb200_download_rhs.argtypes = [C.c_void_p, _dp]
     lib.gsb200_assemble_to_host.argtypes = [C.c_void_p, _ip, _ip, _dp, _dp]
     lib.gsb200_assemble_host.argtypes = [C.POINTER(ProblemStruct), C.c_int, C.POINTER(C.c_int64), _ip, _ip, _dp, _dp]
+    lib.gsb200_download_pattern.argtypes = [C.c_void_p, _ip, _ip]
+    lib.gsb200_set_fixed.argtypes = [C.c_void_p, _dp]
+    lib.gsb200_assemble_values_to_host.argtypes = [C.c_void_p, _dp, _dp]
+    lib.gsb200_host_pin.argtypes = [C.c_void_p, C.c_int64]
+    lib.gsb200_host_unpin.argtypes = [C.c_void_p]
     lib.gsb200_spmv_host.argtypes = [C.c_void_p, _dp, _dp]
     lib.gsb200_spmv_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.gsb200_diag_device.argtypes = [C.c_void_p, C.c_void_p]

@@ -12,8 +12,11 @@
 
 #ifndef GSB200_EMULATE
 #include "jit.cuh"
+#include <atomic>
+#include <memory>
 #include <mutex>
 #include <set>
+#include <thread>
 #endif
 
 namespace gsb {
@@ -206,6 +209,7 @@ struct gsb200_assembler {
     int *d_outer32 = 0;                 // narrowed column pointers for the host-side gsSparseMatrix
 #ifndef GSB200_EMULATE
     cudaStream_t copy_stream = 0; cudaEvent_t ev_done = 0;
+    void *stage[4] = {0, 0, 0, 0}; cudaEvent_t stage_ev[4] = {0, 0, 0, 0};     // pinned staging ring for pageable destinations
 #endif
     // CG work vectors
     double *cg[6] = {0, 0, 0, 0, 0, 0};
@@ -218,6 +222,7 @@ struct gsb200_assembler {
 #ifndef GSB200_EMULATE
         if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
         if (ev_done) cudaEventDestroy(ev_done);
+        for (int k = 0; k < 4; ++k) { if (stage[k]) cudaFreeHost(stage[k]); if (stage_ev[k]) cudaEventDestroy(stage_ev[k]); }
 #endif
         for (int k = 0; k < 6; ++k) dev_free(cg[k]);
 #ifndef GSB200_EMULATE
@@ -810,6 +815,70 @@ static void finish_timings(gsb200_assembler *a)
 #endif
 }
 
+
+#ifndef GSB200_EMULATE
+// ------------------------------------------------------------------ device -> host delivery
+// Page-locked destinations (cudaHostAlloc / cudaHostRegister) are written by the copy engine directly.  Pageable ones (an Eigen
+// matrix: gsSparseMatrix::valuePtr()) go through a ring of pinned staging buffers that host threads drain while the next chunk is in
+// flight: PCIe rate instead of the driver's single-threaded bounce copy.
+static const size_t STAGE_CHUNK = (size_t)32 << 20;
+static bool host_is_pinned(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+static int staged_d2h(gsb200_assembler *a, void *dst_, const void *src_, size_t bytes, cudaStream_t cs)
+{
+    const int NB = 4;
+    for (int k = 0; k < NB; ++k) {
+        if (!a->stage[k]) GSB_TRY(dev_check(cudaHostAlloc(&a->stage[k], STAGE_CHUNK, cudaHostAllocDefault), "cudaHostAlloc (staging)"));
+        if (!a->stage_ev[k]) GSB_TRY(dev_check(cudaEventCreateWithFlags(&a->stage_ev[k], cudaEventDisableTiming), "event"));
+    }
+    char *dst = (char *)dst_; const char *src = (const char *)src_;
+    const size_t nchunk = (bytes + STAGE_CHUNK - 1) / STAGE_CHUNK;
+    const int T = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
+    std::unique_ptr<std::atomic<int>[]> ready(new std::atomic<int>[nchunk]), done(new std::atomic<int>[nchunk]);
+    for (size_t i = 0; i < nchunk; ++i) { ready[i].store(0); done[i].store(0); }
+    std::atomic<int> failed(0);
+    std::vector<std::thread> workers;
+    for (int t = 0; t < T; ++t)
+        workers.emplace_back([&, t] {
+            for (size_t i = 0; i < nchunk; ++i) {
+                while (!ready[i].load(std::memory_order_acquire)) { if (failed.load()) return; std::this_thread::yield(); }
+                const size_t off = i * STAGE_CHUNK, n = std::min(STAGE_CHUNK, bytes - off);
+                const size_t lo = n * t / T, hi = n * (t + 1) / T;
+                memcpy(dst + off + lo, (const char *)a->stage[i % NB] + lo, hi - lo);
+                done[i].fetch_add(1, std::memory_order_release);
+            }
+        });
+    size_t issued = 0, completed = 0; int rc = 0;
+    while (completed < nchunk && !rc) {
+        while (issued < nchunk && issued < completed + NB && (issued < (size_t)NB || done[issued - NB].load(std::memory_order_acquire) == T)) {
+            const size_t off = issued * STAGE_CHUNK, n = std::min(STAGE_CHUNK, bytes - off);
+            rc = dev_check(cudaMemcpyAsync(a->stage[issued % NB], src + off, n, cudaMemcpyDeviceToHost, cs), "D2H (staged)");
+            if (!rc) rc = dev_check(cudaEventRecord(a->stage_ev[issued % NB], cs), "event record");
+            if (rc) break;
+            ++issued;
+        }
+        if (rc) break;
+        if (issued == completed) { std::this_thread::yield(); continue; }       // the ring is full of chunks the workers still drain
+        rc = dev_check(cudaEventSynchronize(a->stage_ev[completed % NB]), "event sync");
+        if (!rc) { ready[completed].store(1, std::memory_order_release); ++completed; }
+    }
+    if (rc) failed.store(1);
+    for (auto &w : workers) w.join();
+    return rc;
+}
+// asynchronous for pinned destinations (caller synchronises `cs`), complete on return for pageable ones
+static int d2h_any(gsb200_assembler *a, void *dst, const void *src, size_t bytes, cudaStream_t cs)
+{
+    if (!bytes) return 0;
+    if (host_is_pinned(dst) || bytes < ((size_t)1 << 20)) return dev_check(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, cs), "D2H");
+    return staged_d2h(a, dst, src, bytes, cs);
+}
+#endif
+
 } // namespace gsb
 
 // ====================================================================== C ABI
@@ -1038,55 +1107,123 @@ int gsb200_download_rhs(gsb200_assembler *a, double *rhs)
     return dev_d2h(rhs, a->d_rhs, sizeof(double) * (size_t)a->nfree * a->nrhs, a->stream);
 }
 
-int gsb200_assemble_to_host(gsb200_assembler *a, int32_t *outer, int32_t *inner, double *values, double *rhs)
+int gsb200_download_pattern(gsb200_assembler *a, int32_t *outer, int32_t *inner)
 {
-    if (!a || !outer || !inner || !values) { set_error("assemble_to_host: null argument"); return GSB200_EINVAL; }
-    if (!a->pattern_built) { set_error("gsb200_assemble_to_host called before gsb200_build_pattern"); return GSB200_ESTATE; }
+    if (!a || !outer || !inner) { set_error("download_pattern: null argument"); return GSB200_EINVAL; }
+    if (!a->pattern_built) { set_error("pattern not built"); return GSB200_ESTATE; }
+    if (a->nnz > 2147483647LL) { set_error("nnz = %lld exceeds the 32-bit index_t of gsSparseMatrix; use the device view", (long long)a->nnz); return GSB200_ERANGE; }
+    GSB_TRY(select_device(a->device));
+#ifndef GSB200_EMULATE
+    const int N = a->nfree;
+    if (!a->copy_stream) GSB_TRY(dev_check(cudaStreamCreateWithFlags(&a->copy_stream, cudaStreamNonBlocking), "copy stream"));
+    if (!a->d_outer32) GSB_TRY(dev_malloc((void **)&a->d_outer32, sizeof(int) * (size_t)(N + 1)));
+    cudaStream_t cs = a->copy_stream;
+    k_narrow_outer<<<(N + 1 + 255) / 256, 256, 0, cs>>>(N + 1, a->d_colptr, a->d_outer32); note_launch();
+    GSB_TRY(d2h_any(a, outer, a->d_outer32, sizeof(int) * (size_t)(N + 1), cs));
+    GSB_TRY(d2h_any(a, inner, a->d_inner, sizeof(int) * (size_t)a->nnz, cs));
+    return dev_check(cudaStreamSynchronize(cs), "copy stream sync");
+#else
+    std::vector<i64> ptr((size_t)a->nfree + 1);
+    GSB_TRY(dev_d2h(ptr.data(), a->d_colptr, ptr.size() * sizeof(i64), a->stream));
+    for (size_t i = 0; i < ptr.size(); ++i) outer[i] = (int32_t)ptr[i];
+    return dev_d2h(inner, a->d_inner, sizeof(int) * (size_t)a->nnz, a->stream);
+#endif
+}
+
+int gsb200_set_fixed(gsb200_assembler *a, const double *fixed)
+{
+    if (!a) { set_error("null assembler"); return GSB200_EINVAL; }
+    GSB_TRY(select_device(a->device));
+    const size_t n = (size_t)a->nfixed * a->nrhs;
+    if (!fixed) { GSB_TRY(dev_sync(a->stream)); dev_free(a->d_fixed); a->d_fixed = 0; return GSB200_OK; }
+    if (!a->d_fixed) GSB_TRY(dev_malloc((void **)&a->d_fixed, sizeof(double) * std::max<size_t>(n, 1)));
+    if (n) GSB_TRY(dev_h2d(a->d_fixed, fixed, sizeof(double) * n, a->stream));
+    return dev_sync(a->stream);        // the caller's buffer may go away
+}
+
+// values (+ rhs) of a fresh assembly into host memory; with_pattern: the index arrays travel on the copy stream meanwhile
+static int assemble_deliver(gsb200_assembler *a, int32_t *outer, int32_t *inner, double *values, double *rhs)
+{
     if (a->nnz > 2147483647LL) { set_error("nnz = %lld exceeds the 32-bit index_t of gsSparseMatrix; use the device view", (long long)a->nnz); return GSB200_ERANGE; }
     GSB_TRY(select_device(a->device));
 #ifndef GSB200_EMULATE
     const int N = a->nfree;
     if (!a->copy_stream) GSB_TRY(dev_check(cudaStreamCreateWithFlags(&a->copy_stream, cudaStreamNonBlocking), "copy stream"));
     if (!a->ev_done) GSB_TRY(dev_check(cudaEventCreateWithFlags(&a->ev_done, cudaEventDisableTiming), "event"));
-    if (!a->d_outer32) GSB_TRY(dev_malloc((void **)&a->d_outer32, sizeof(int) * (size_t)(N + 1)));
     cudaStream_t cs = a->copy_stream;
-    // pattern arrays are final since gsb200_build_pattern returned: ship them while the values are integrated
-    k_narrow_outer<<<(N + 1 + 255) / 256, 256, 0, cs>>>(N + 1, a->d_colptr, a->d_outer32); note_launch();
-    GSB_TRY(dev_check(cudaMemcpyAsync(outer, a->d_outer32, sizeof(int) * (size_t)(N + 1), cudaMemcpyDeviceToHost, cs), "D2H outer"));
-    GSB_TRY(dev_check(cudaMemcpyAsync(inner, a->d_inner, sizeof(int) * (size_t)a->nnz, cudaMemcpyDeviceToHost, cs), "D2H inner"));
+    // the kernels are enqueued first (asynchronous), so the index arrays travel WHILE the values are being integrated
     GSB_TRY(assemble(a));
     GSB_TRY(dev_check(cudaEventRecord(a->ev_done, a->stream), "event record"));
+    if (outer && inner) {
+        if (!a->d_outer32) GSB_TRY(dev_malloc((void **)&a->d_outer32, sizeof(int) * (size_t)(N + 1)));
+        k_narrow_outer<<<(N + 1 + 255) / 256, 256, 0, cs>>>(N + 1, a->d_colptr, a->d_outer32); note_launch();
+        GSB_TRY(d2h_any(a, outer, a->d_outer32, sizeof(int) * (size_t)(N + 1), cs));
+        GSB_TRY(d2h_any(a, inner, a->d_inner, sizeof(int) * (size_t)a->nnz, cs));
+    }
     GSB_TRY(dev_check(cudaStreamWaitEvent(cs, a->ev_done, 0), "stream wait"));
-    GSB_TRY(dev_check(cudaMemcpyAsync(values, a->d_values, sizeof(double) * (size_t)a->nnz, cudaMemcpyDeviceToHost, cs), "D2H values"));
-    if (rhs) GSB_TRY(dev_check(cudaMemcpyAsync(rhs, a->d_rhs, sizeof(double) * (size_t)N * a->nrhs, cudaMemcpyDeviceToHost, cs), "D2H rhs"));
+    GSB_TRY(d2h_any(a, values, a->d_values, sizeof(double) * (size_t)a->nnz, cs));
+    if (rhs) GSB_TRY(d2h_any(a, rhs, a->d_rhs, sizeof(double) * (size_t)N * a->nrhs, cs));
     GSB_TRY(dev_check(cudaStreamSynchronize(cs), "copy stream sync"));
     GSB_TRY(dev_sync(a->stream));
     finish_timings(a);
     return GSB200_OK;
 #else
     GSB_TRY(assemble(a));
-    GSB_TRY(gsb200_download_csc(a, outer, inner, values));
+    if (outer && inner) GSB_TRY(gsb200_download_pattern(a, outer, inner));
+    GSB_TRY(dev_d2h(values, a->d_values, sizeof(double) * (size_t)a->nnz, a->stream));
     return rhs ? gsb200_download_rhs(a, rhs) : GSB200_OK;
 #endif
 }
 
+int gsb200_assemble_to_host(gsb200_assembler *a, int32_t *outer, int32_t *inner, double *values, double *rhs)
+{
+    if (!a || !outer || !inner || !values) { set_error("assemble_to_host: null argument"); return GSB200_EINVAL; }
+    if (!a->pattern_built) { set_error("gsb200_assemble_to_host called before gsb200_build_pattern"); return GSB200_ESTATE; }
+    return assemble_deliver(a, outer, inner, values, rhs);
+}
+
+int gsb200_assemble_values_to_host(gsb200_assembler *a, double *values, double *rhs)
+{
+    if (!a || !values) { set_error("assemble_values_to_host: null argument"); return GSB200_EINVAL; }
+    if (!a->pattern_built) { set_error("gsb200_assemble_values_to_host called before gsb200_build_pattern"); return GSB200_ESTATE; }
+    return assemble_deliver(a, 0, 0, values, rhs);
+}
+
 int gsb200_assemble_host(const gsb200_problem *pb, int device, int64_t *nnz, int32_t *outer, int32_t *inner, double *values, double *rhs)
 {
-    static const gsb200_problem *pending_pb = 0; static gsb200_assembler *pending = 0;
+    // stateless: the size query builds (and drops) the pattern; callers that want to keep it use an explicit handle
+    // (gsb200_create / gsb200_build_pattern / gsb200_nnz / gsb200_assemble_to_host / gsb200_destroy), as the gismo shims do
     if (!pb || !nnz) { set_error("assemble_host: null argument"); return GSB200_EINVAL; }
     gsb200_assembler *a = 0;
-    if (pending && pending_pb == pb) { a = pending; pending = 0; pending_pb = 0; }
-    else {
-        if (pending) { gsb200_destroy(pending); pending = 0; pending_pb = 0; }
-        GSB_TRY(gsb200_create(pb, device, &a));
-        const int rc = gsb200_build_pattern(a);
-        if (rc) { gsb200_destroy(a); return rc; }
+    GSB_TRY(gsb200_create(pb, device, &a));
+    int rc = gsb200_build_pattern(a);
+    if (!rc) {
+        const bool query = !outer || !inner || !values;
+        if (!query && *nnz != 0 && *nnz != a->nnz) { set_error("assemble_host: buffers sized for nnz = %lld, the problem has %lld", (long long)*nnz, (long long)a->nnz); rc = GSB200_EINVAL; }
+        *nnz = a->nnz;
+        if (!rc && !query) rc = gsb200_assemble_to_host(a, outer, inner, values, rhs);
     }
-    *nnz = a->nnz;
-    if (!outer || !inner || !values) { pending = a; pending_pb = pb; return GSB200_OK; }   // size query: keep the pattern
-    const int rc = gsb200_assemble_to_host(a, outer, inner, values, rhs);
     gsb200_destroy(a);
     return rc;
+}
+
+int gsb200_host_pin(void *p, int64_t bytes)
+{
+#ifndef GSB200_EMULATE
+    if (!p || bytes <= 0) return GSB200_EINVAL;
+    return dev_check(cudaHostRegister(p, (size_t)bytes, cudaHostRegisterDefault), "cudaHostRegister");
+#else
+    (void)p; (void)bytes; return GSB200_OK;
+#endif
+}
+int gsb200_host_unpin(void *p)
+{
+#ifndef GSB200_EMULATE
+    if (!p) return GSB200_EINVAL;
+    return dev_check(cudaHostUnregister(p), "cudaHostUnregister");
+#else
+    (void)p; return GSB200_OK;
+#endif
 }
 
 // ---------------------------------------------------------------- consumer: SpMV + Jacobi-CG

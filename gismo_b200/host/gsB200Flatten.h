@@ -16,6 +16,7 @@
       - source-term strings:         gsFunctionExpr::expression(i)  gsFunctionExpr.h:169
 */
 #pragma once
+#include <limits>
 
 #include <gismo.h>
 #include <gsb200.h>
@@ -205,19 +206,49 @@ void flatten(const gsMultiPatch<T> & mp, const gsMultiBasis<T> & mb, const gsDof
     pb.quA = opt.askReal("quA", 1.0);
     pb.quB = opt.askInt("quB", 1);
     GISMO_ENSURE(opt.askInt("quRule", 1) == 1, "gsB200: only Gauss-Legendre quadrature (quRule=1) is supported");
+    GISMO_ENSURE(!opt.askSwitch("overInt", false), "gsB200: overInt (boundary over-integration, quAb/quBb) is not supported");
 }
 
-/// Move the device result into a gsSparseMatrix exactly as Eigen stores a compressed matrix
-/// (SparseMatrix.h:150-177,626,649).
-template <class T>
-void fillSparse(gsSparseMatrix<T> & m, index_t n, int64_t nnz, const std::vector<int32_t> & outer,
-                const std::vector<int32_t> & inner, const std::vector<double> & values)
+/// RAII handle of a device assembler (gsb200_create ... gsb200_destroy): never leaks a device context when an
+/// exception unwinds between the calls.
+struct gsB200Handle
 {
+    gsb200_assembler * h;
+    gsB200Handle() : h(NULL) { }
+    ~gsB200Handle() { reset(); }
+    void reset() { if (h) gsb200_destroy(h); h = NULL; }
+private:
+    gsB200Handle(const gsB200Handle &); gsB200Handle & operator=(const gsB200Handle &);
+};
+
+inline void check(int rc) { if (rc != GSB200_OK) GISMO_ERROR("gsB200: " << gsb200_last_error()); }
+
+/** Assemble on the device and deliver straight into a gsSparseMatrix / gsMatrix: the matrix is sized like Eigen's
+    compressed form (SparseMatrix.h:150-177,626,649) and the library writes outerIndexPtr / innerIndexPtr / valuePtr /
+    rhs.data() itself (pinned staging ring, no intermediate std::vector).  \a handle keeps the device context: a second
+    call with keepPattern = true re-assembles values and right-hand side only (same mesh, new data). */
+template <class T>
+void assembleInto(gsB200Problem & st, int device, gsB200Handle & handle, bool keepPattern,
+                  gsSparseMatrix<T> & m, gsMatrix<T> & rhs)
+{
+    const index_t n = st.pb.nfree;
+    rhs.setZero(n, st.pb.nrhs);
+    if (handle.h && keepPattern && m.rows() == n && m.isCompressed())
+    {
+        if (st.pb.fixed) check(gsb200_set_fixed(handle.h, st.pb.fixed));
+        check(gsb200_assemble_values_to_host(handle.h, m.valuePtr(), rhs.data()));
+        return;
+    }
+    handle.reset();
+    check(gsb200_create(&st.pb, device, &handle.h));
+    check(gsb200_build_pattern(handle.h));
+    int64_t nnz = 0;
+    check(gsb200_nnz(handle.h, &nnz));
+    GISMO_ENSURE(nnz <= static_cast<int64_t>(std::numeric_limits<index_t>::max()),
+                 "gsB200: nnz exceeds index_t; use the device view (gsb200_device_view_get)");
     m.resize(n, n);
     m.resizeNonZeros(static_cast<index_t>(nnz));
-    std::copy(outer.begin(), outer.end(), m.outerIndexPtr());
-    std::copy(inner.begin(), inner.end(), m.innerIndexPtr());
-    std::copy(values.begin(), values.end(), m.valuePtr());
+    check(gsb200_assemble_to_host(handle.h, m.outerIndexPtr(), m.innerIndexPtr(), m.valuePtr(), rhs.data()));
 }
 
 } // namespace b200

@@ -30,19 +30,23 @@ public:
     typedef gsPoissonAssembler<T> Base;
 
     gsPoissonAssemblerB200(const gsPoissonPde<T> & pde, const gsMultiBasis<T> & bases)
-    : Base(pde, bases), m_device(0) { }
+    : Base(pde, bases), m_device(0), m_keepPattern(false) { }
 
     gsPoissonAssemblerB200(const gsPoissonPde<T> & pde, const gsMultiBasis<T> & bases,
                            dirichlet::strategy dirStrategy, iFace::strategy intStrategy = iFace::glue)
-    : Base(pde, bases, dirStrategy, intStrategy), m_device(0) { }
+    : Base(pde, bases, dirStrategy, intStrategy), m_device(0), m_keepPattern(false) { }
 
     gsPoissonAssemblerB200(gsMultiPatch<T> const & patches, gsMultiBasis<T> const & basis,
                            gsBoundaryConditions<T> const & bconditions, const gsFunction<T> & rhs,
                            dirichlet::strategy dirStrategy = dirichlet::elimination,
                            iFace::strategy intStrategy = iFace::glue)
-    : Base(patches, basis, bconditions, rhs, dirStrategy, intStrategy), m_device(0) { }
+    : Base(patches, basis, bconditions, rhs, dirStrategy, intStrategy), m_device(0), m_keepPattern(false) { }
 
     void setDevice(int device) { m_device = device; }
+    /// Re-use the sparsity pattern of the previous assemble() (same mesh and boundary conditions; new data): values and
+    /// right-hand side only are recomputed and transferred.  refresh() resets it.
+    void setKeepPattern(bool keep) { m_keepPattern = keep; }
+    virtual void refresh() { Base::refresh(); m_handle.reset(); }
 
     /// Main assembly routine: same contract as gsPoissonAssembler<T>::assemble().
     virtual void assemble()
@@ -61,20 +65,13 @@ public:
         b200::flatten(m_pde_ptr->domain(), m_bases[0], m_system.colMapper(0), 1, m_ddof[0],
                       m_options, GSB200_FORM_POISSON, st);
         const gsPoissonPde<T> & ppde = static_cast<const gsPoissonPde<T>&>(*m_pde_ptr);
+        st.pb.nrhs = ppde.numRhs();          // not inferred from the Dirichlet matrix (it is empty for a pure Neumann problem)
         b200::flattenSource(*ppde.rhs(), st.pb.nrhs, st);
         b200::flattenNeumann(m_pde_ptr->bc(), m_pde_ptr->domain().parDim(), st);   // gsVisitorNeumann on the device
 
-        int64_t nnz = 0;
-        if (gsb200_assemble_host(&st.pb, m_device, &nnz, NULL, NULL, NULL, NULL) != GSB200_OK)
-            GISMO_ERROR("gsB200: " << gsb200_last_error());
-        const index_t n = st.pb.nfree;
-        std::vector<int32_t> outer(n + 1), inner(nnz);
-        std::vector<double> values(nnz);
-        m_system.rhs().setZero(n, st.pb.nrhs);
-        if (gsb200_assemble_host(&st.pb, m_device, &nnz, outer.data(), inner.data(), values.data(),
-                                 m_system.rhs().data()) != GSB200_OK)
-            GISMO_ERROR("gsB200: " << gsb200_last_error());
-        b200::fillSparse(m_system.matrix(), n, nnz, outer, inner, values);
+        // explicit device handle: pattern + values straight into m_system (no static state, no staging vectors);
+        // a repeated assemble() on the same mesh re-assembles values and rhs only
+        b200::assembleInto(st, m_device, m_handle, m_keepPattern, m_system.matrix(), m_system.rhs());
     }
 
 protected:
@@ -84,6 +81,8 @@ protected:
     using Base::m_bases;
     using Base::m_ddof;
     int m_device;
+    bool m_keepPattern;
+    b200::gsB200Handle m_handle;
 };
 
 /** Sibling of gsExprAssembler<T> for the forms of the BASELINE configs.  Usage mirrors
@@ -99,13 +98,14 @@ template <class T = real_t>
 class gsExprAssemblerB200
 {
 public:
-    gsExprAssemblerB200() : m_ref(1,1), m_mp(NULL), m_mb(NULL), m_bc(NULL), m_dim(1), m_device(0) { }
+    gsExprAssemblerB200() : m_ref(1,1), m_mp(NULL), m_mb(NULL), m_bc(NULL), m_dim(1), m_device(0), m_keepPattern(false) { }
 
     void setOptions(const gsOptionList & o) { m_ref.setOptions(o); }
     gsOptionList & options() { return m_ref.options(); }
     void setIntegrationElements(const gsMultiBasis<T> & mb) { m_ref.setIntegrationElements(mb); m_mb = &mb; }
     void setGeometry(const gsMultiPatch<T> & mp) { m_mp = &mp; }
     void setDevice(int device) { m_device = device; }
+    void setKeepPattern(bool keep) { m_keepPattern = keep; }
 
     /// getSpace + space::setup (gsExprAssembler.h:166, gsExpressions.h:1091): the DOF
     /// mapper and the Dirichlet values are computed by the reference's own host code.
@@ -120,6 +120,7 @@ public:
         m_ref.initSystem();
         m_mapper = u.mapper();
         m_fixed = u.fixedPart();
+        m_handle.reset();
     }
 
     index_t numDofs() const { return m_mapper.freeSize(); }
@@ -142,17 +143,7 @@ private:
         st.pb.nrhs = 1;
         b200::flattenSource(f, form == GSB200_FORM_ELASTICITY ? m_dim : 1, st);
         if (m_bc) b200::flattenNeumann(*m_bc, m_mp->parDim(), st);
-        int64_t nnz = 0;
-        if (gsb200_assemble_host(&st.pb, m_device, &nnz, NULL, NULL, NULL, NULL) != GSB200_OK)
-            GISMO_ERROR("gsB200: " << gsb200_last_error());
-        const index_t n = st.pb.nfree;
-        std::vector<int32_t> outer(n + 1), inner(nnz);
-        std::vector<double> values(nnz);
-        m_rhs.setZero(n, 1);
-        if (gsb200_assemble_host(&st.pb, m_device, &nnz, outer.data(), inner.data(), values.data(),
-                                 m_rhs.data()) != GSB200_OK)
-            GISMO_ERROR("gsB200: " << gsb200_last_error());
-        b200::fillSparse(m_matrix, n, nnz, outer, inner, values);
+        b200::assembleInto(st, m_device, m_handle, m_keepPattern, m_matrix, m_rhs);
     }
 
     gsExprAssembler<T> m_ref;      // used for set-up only (mapper, Dirichlet values)
@@ -161,6 +152,8 @@ private:
     const gsBoundaryConditions<T> * m_bc;
     index_t m_dim;
     int m_device;
+    bool m_keepPattern;
+    b200::gsB200Handle m_handle;
     gsDofMapper m_mapper;
     gsMatrix<T> m_fixed;
     gsSparseMatrix<T> m_matrix;

@@ -25,8 +25,35 @@ static int compare(const char *what, const gsSparseMatrix<real_t> &A, const gsMa
     return ok ? 0 : 1;
 }
 
-int main()
+// config-2 size through the shim: what a gismo caller gets (host flattening, pattern, assembly, delivery straight
+// into gsSparseMatrix / gsMatrix), and the values-only re-assembly on the kept pattern.  No reference run at this size.
+static int big(int m, int p)
 {
+    gsMultiPatch<> mp(*gsNurbsCreator<>::BSplineCube(1, 0, 0, 0));
+    gsMultiBasis<> mb(mp, true); mb.setDegree(p); mb.uniformRefine(m - 1);
+    gsFunctionExpr<> f("3*pi^2*sin(pi*x)*sin(pi*y)*sin(pi*z)", 3), g("0", 3);
+    gsBoundaryConditions<> bc;
+    for (gsMultiPatch<>::const_biterator it = mp.bBegin(); it != mp.bEnd(); ++it) bc.addCondition(*it, condition_type::dirichlet, &g);
+    bc.setGeoMap(mp);
+    gsStopwatch sw;
+    gsPoissonAssemblerB200<> D(mp, mb, bc, f, dirichlet::elimination, iFace::glue);
+    D.options().setInt("DirichletValues", dirichlet::homogeneous);
+    const double t_setup = sw.stop(); sw.restart();
+    D.assemble();
+    const double t_first = sw.stop(); sw.restart();
+    D.setKeepPattern(true);
+    D.assemble();
+    const double t_again = sw.stop();
+    const gsSparseMatrix<real_t> & K = D.matrix();
+    real_t sum = 0; for (index_t k = 0; k < K.nonZeros(); ++k) sum += K.valuePtr()[k];
+    gsInfo << "SHIMBIG m " << m << " p " << p << " dofs " << K.rows() << " nnz " << K.nonZeros() << " setup_s " << t_setup
+           << " assemble_s " << t_first << " reassemble_values_s " << t_again << " sumK " << sum << " rhsnorm " << D.rhs().norm() << "\n";
+    return 0;
+}
+
+int main(int argc, char **argv)
+{
+    if (argc >= 3 && std::string(argv[1]) == "--big") return big(atoi(argv[2]), argc >= 4 ? atoi(argv[3]) : 3);
     int bad = 0;
     {   // visitor path, multi-patch, non-homogeneous Dirichlet by interpolation
         gsMultiPatch<> mp = gsNurbsCreator<>::BSplineSquareGrid(2, 2, 1.0);
@@ -41,6 +68,9 @@ int main()
         gsPoissonAssemblerB200<> D(mp, mb, bc, f, dirichlet::elimination, iFace::glue);
         D.assemble();
         bad += compare("gsPoissonAssemblerB200 2x2 patches p=3", R.matrix(), R.rhs(), D.matrix(), D.rhs());
+        D.setKeepPattern(true);         // values-only re-assembly on the kept device pattern
+        D.assemble();
+        bad += compare("gsPoissonAssemblerB200 re-assembly (values only)", R.matrix(), R.rhs(), D.matrix(), D.rhs());
         // the reference's own solver consumes the device-built matrix
         gsSparseSolver<>::CGDiagonal solver; solver.compute(D.matrix());
         gsMatrix<> x = solver.solve(D.rhs());
