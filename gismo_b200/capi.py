@@ -103,6 +103,8 @@ class Problem:
                  neumann: Optional[List[tuple]] = None):
         self.patches = patches
         self.nfree, self.nfixed, self.form, self.ncomp, self.nrhs = int(nfree), int(nfixed), form, ncomp, nrhs
+        self._ctor = dict(form=form, ncomp=ncomp, nrhs=nrhs, coef=tuple(coef), quA=quA, quB=quB, rhs_programs=rhs_programs,
+                          rank=rank, nranks=nranks, neumann=neumann)
         self.fixed = None if fixed is None else np.asfortranarray(np.asarray(fixed, dtype=np.float64).reshape(nfixed, -1))
         self.rhs_programs = rhs_programs or []
         self._keep = []
@@ -161,6 +163,12 @@ class Problem:
     def dim(self) -> int:
         return self.patches[0].dim
 
+    def with_fixed(self, fixed: Optional[np.ndarray], **changes) -> "Problem":
+        """The same problem with other eliminated-DOF values (and any other constructor argument in `changes`)."""
+        kw = dict(self._ctor)
+        kw.update(changes)
+        return Problem(self.patches, self.nfree, self.nfixed, fixed=fixed, **kw)
+
 
 class CompiledProgram:
     def __init__(self, ops: np.ndarray, consts: np.ndarray, text: str = ""):
@@ -184,7 +192,13 @@ def load_library():
     path = library_path()
     if not os.path.exists(path):
         raise Gsb200Error(f"CUDA extension {path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
-    lib = C.CDLL(path)
+    _LIB = declare(C.CDLL(path))
+    return _LIB
+
+
+def declare(lib, optional=()):
+    """ctypes signatures of every entry point of include/gsb200.h (also used for the interpreter build of the tests);
+    names in `optional` may be absent from `lib`."""
     lib.gsb200_last_error.restype = C.c_char_p
     lib.gsb200_create.argtypes = [C.POINTER(ProblemStruct), C.c_int, C.POINTER(C.c_void_p)]
     lib.gsb200_destroy.argtypes = [C.c_void_p]
@@ -216,7 +230,6 @@ def load_library():
     lib.gsb200_expr_eval_host.argtypes = [C.POINTER(Program), C.c_double, C.c_double, C.c_double, _dp]
     lib.gsb200_measure_peaks.argtypes = [C.c_int, _dp, _dp, _dp]
     lib.gsb200_device_count.argtypes = [C.POINTER(C.c_int)]
-    _LIB = lib
     return lib
 
 

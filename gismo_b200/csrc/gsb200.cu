@@ -178,6 +178,7 @@ struct PatchDev {
     unsigned char *d_colflag = 0; unsigned *d_st = 0; int nrun = 1; i64 *d_ownrec = 0;
     int own_lo = 0, own_hi = 0;     // owner range along the last direction on this rank
     double *d_lc = 0;               // line coefficients of the geometry (fused.cuh, k_line_coefs), 0: fused first sweep not available
+    std::vector<int> sufmin;        // sufmin[x] = smallest free column with a preimage in last-direction layers >= x (scalar spaces): columns below it are final once layers < x are done
     void release() { for (int k = 0; k < 3; ++k) dir[k].release(); dev_free(d_dofmap); dev_free(d_coefs); dev_free(d_weights); dev_free(d_colflag); dev_free(d_st); dev_free(d_ownrec); dev_free(d_lc); }
 };
 
@@ -210,7 +211,10 @@ struct gsb200_assembler {
 #ifndef GSB200_EMULATE
     cudaStream_t copy_stream = 0; cudaEvent_t ev_done = 0;
     void *stage[4] = {0, 0, 0, 0}; cudaEvent_t stage_ev[4] = {0, 0, 0, 0};     // pinned staging ring for pageable destinations
+    std::vector<cudaEvent_t> chunk_ev;  // recorded behind the last kernel of every chunk: finished column ranges travel while later chunks integrate
 #endif
+    int deliver_chunks = 1, plan_chunks = 1;      // chunks the last direction is cut into for streamed delivery (requested / planned)
+    std::vector<int> chunk_cols; std::vector<i64> chunk_off;   // per chunk: first column / value offset that is NOT yet final behind it
     // CG work vectors
     double *cg[6] = {0, 0, 0, 0, 0, 0};
     ~gsb200_assembler() {
@@ -223,6 +227,7 @@ struct gsb200_assembler {
         if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
         if (ev_done) cudaEventDestroy(ev_done);
         for (int k = 0; k < 4; ++k) { if (stage[k]) cudaFreeHost(stage[k]); if (stage_ev[k]) cudaEventDestroy(stage_ev[k]); }
+        for (auto e : chunk_ev) cudaEventDestroy(e);
 #endif
         for (int k = 0; k < 6; ++k) dev_free(cg[k]);
 #ifndef GSB200_EMULATE
@@ -465,10 +470,13 @@ static int assemble_pass(gsb200_assembler *a)
         const i64 minpts = (i64)(dL.p + 1) * dL.q;
         if (maxpts < minpts) { set_error("workspace limit %lld B too small: one slab of patch %zu needs %lld B", (long long)limit, ip, (long long)(perq * 8 * minpts)); return GSB200_ENOMEM; }
         int x_lo = P.own_lo;
+        // streamed delivery (single scalar patch): at most ceil(owned layers / chunks) layers per chunk
+        const bool stream_cols = a->plan_chunks > 1 && a->patches.size() == 1 && !P.sufmin.empty();
+        const int x_cap = stream_cols ? std::max(dL.p + 1, (P.own_hi - P.own_lo + a->plan_chunks - 1) / a->plan_chunks) : P.own_hi - P.own_lo;
         while (x_lo < P.own_hi) {
             // largest chunk [x_lo,x_hi) whose element footprint fits
             int x_hi = x_lo + 1;
-            while (x_hi < P.own_hi && (i64)(dL.flast[x_hi] - dL.ffirst[x_lo] + 1) * dL.q <= maxpts) ++x_hi;
+            while (x_hi < P.own_hi && x_hi - x_lo < x_cap && (i64)(dL.flast[x_hi] - dL.ffirst[x_lo] + 1) * dL.q <= maxpts) ++x_hi;
             const int eL0 = dL.ffirst[x_lo], eL1 = dL.flast[x_hi - 1] + 1, ELc = eL1 - eL0;
             const i64 QLc = (i64)ELc * dL.q;
             const size_t need = (size_t)(perq * QLc) * 8 + 6 * 256;
@@ -740,6 +748,16 @@ static int assemble_pass(gsb200_assembler *a)
                     }
                 }
             }
+            if (stream_cols) {
+                if (dry_run()) a->chunk_cols.push_back(x_hi < P.own_hi ? P.sufmin[x_hi] : N);
+#ifndef GSB200_EMULATE
+                else {
+                    const size_t k = (size_t)a->tm.nchunks - 1;
+                    while (a->chunk_ev.size() <= k) { cudaEvent_t e; GSB_TRY(dev_check(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event")); a->chunk_ev.push_back(e); }
+                    GSB_TRY(dev_check(cudaEventRecord(a->chunk_ev[k], s), "event record"));
+                }
+#endif
+            }
             x_lo = x_hi;
         }
     }
@@ -786,14 +804,20 @@ static int assemble_pass(gsb200_assembler *a)
 // one copy; afterwards assemble() only enqueues kernels, so the stream never waits on the host.
 static int assemble(gsb200_assembler *a)
 {
+    if (a->plan_valid && a->plan_chunks != a->deliver_chunks) a->plan_valid = false;
     if (!a->plan_valid) {
+        a->plan_chunks = a->deliver_chunks;
         g_dry = true;
-        a->seg_host.clear();
+        a->seg_host.clear(); a->chunk_cols.clear(); a->chunk_off.clear();
         const int rc = assemble_pass(a);
         g_dry = false;
         if (rc) return rc;
         if (!a->seg_host.empty()) GSB_TRY(dev_h2d(a->d_seg, a->seg_host.data(), a->seg_host.size() * sizeof(int), a->stream));
         GSB_TRY(dev_sync(a->stream));
+        for (int c : a->chunk_cols) {       // value offsets behind which everything is final once the chunk is done
+            i64 off = 0; GSB_TRY(dev_d2h(&off, a->d_colptr + c, sizeof(i64), a->stream));
+            a->chunk_off.push_back(off);
+        }
         a->plan_valid = true;
     }
     return assemble_pass(a);
@@ -970,6 +994,15 @@ int gsb200_create(const gsb200_problem *pb, int device, gsb200_assembler **out)
         const int nL = P.dir[L].nfun;
         if (pb->npatches == 1) { P.own_lo = (int)((i64)nL * pb->rank / pb->nranks); P.own_hi = (int)((i64)nL * (pb->rank + 1) / pb->nranks); }
         else { P.own_lo = 0; P.own_hi = (ip % pb->nranks == pb->rank) ? nL : 0; }
+        if (pb->npatches == 1 && pb->ncomp == 1) {     // streamed delivery: which columns are final behind a layer of the last direction
+            const i64 per = P.nb / nL;
+            P.sufmin.assign((size_t)nL + 1, pb->nfree);
+            for (int x = nL - 1; x >= 0; --x) {
+                int m = P.sufmin[x + 1];
+                for (i64 i = (i64)x * per; i < (i64)(x + 1) * per; ++i) if (dm[i] < m) m = dm[i];     // eliminated DOFs are >= nfree
+                P.sufmin[x] = m;
+            }
+        }
     }
     if (!rc && pb->fixed) { std::vector<double> fx(pb->fixed, pb->fixed + (size_t)pb->nfixed * pb->nrhs); rc = upload(&a->d_fixed, fx, a->stream); }
     auto upload_program = [&](const gsb200_program &pr, DevProgram *out) -> int {
@@ -1053,6 +1086,7 @@ int gsb200_assemble(gsb200_assembler *a)
     if (!a) { set_error("null assembler"); return GSB200_EINVAL; }
     if (!a->pattern_built) { set_error("gsb200_assemble called before gsb200_build_pattern"); return GSB200_ESTATE; }
     GSB_TRY(select_device(a->device));
+    a->deliver_chunks = 1;      // device-resident result: no column ranges to send ahead
     return assemble(a);
 }
 
@@ -1146,12 +1180,18 @@ static int assemble_deliver(gsb200_assembler *a, int32_t *outer, int32_t *inner,
 {
     if (a->nnz > 2147483647LL) { set_error("nnz = %lld exceeds the 32-bit index_t of gsSparseMatrix; use the device view", (long long)a->nnz); return GSB200_ERANGE; }
     GSB_TRY(select_device(a->device));
+    {   // read at every call: the tests switch them
+        const char *e = getenv("GSB200_DELIVER_CHUNKS"), *m = getenv("GSB200_DELIVER_MIN_NNZ");
+        const int want = e ? atoi(e) : 8; const i64 min_nnz = m ? atoll(m) : ((i64)1 << 25);
+        a->deliver_chunks = (a->patches.size() == 1 && !a->patches[0].sufmin.empty() && a->nnz >= min_nnz) ? std::max(1, want) : 1;
+    }
 #ifndef GSB200_EMULATE
     const int N = a->nfree;
     if (!a->copy_stream) GSB_TRY(dev_check(cudaStreamCreateWithFlags(&a->copy_stream, cudaStreamNonBlocking), "copy stream"));
     if (!a->ev_done) GSB_TRY(dev_check(cudaEventCreateWithFlags(&a->ev_done, cudaEventDisableTiming), "event"));
     cudaStream_t cs = a->copy_stream;
-    // the kernels are enqueued first (asynchronous), so the index arrays travel WHILE the values are being integrated
+    // the kernels are enqueued first (asynchronous), so the index arrays travel WHILE the values are being integrated; for a single
+    // scalar patch the last direction is cut into chunks and the columns a chunk completes travel while the next chunks integrate
     GSB_TRY(assemble(a));
     GSB_TRY(dev_check(cudaEventRecord(a->ev_done, a->stream), "event record"));
     if (outer && inner) {
@@ -1160,8 +1200,17 @@ static int assemble_deliver(gsb200_assembler *a, int32_t *outer, int32_t *inner,
         GSB_TRY(d2h_any(a, outer, a->d_outer32, sizeof(int) * (size_t)(N + 1), cs));
         GSB_TRY(d2h_any(a, inner, a->d_inner, sizeof(int) * (size_t)a->nnz, cs));
     }
+    i64 sent = 0;
+    if (a->plan_chunks > 1 && a->chunk_off.size() == (size_t)a->tm.nchunks)
+        for (size_t k = 0; k + 1 < a->chunk_off.size(); ++k) {
+            const i64 upto = a->chunk_off[k];
+            if (upto <= sent) continue;
+            GSB_TRY(dev_check(cudaStreamWaitEvent(cs, a->chunk_ev[k], 0), "stream wait"));
+            GSB_TRY(d2h_any(a, values + sent, a->d_values + sent, sizeof(double) * (size_t)(upto - sent), cs));
+            sent = upto;
+        }
     GSB_TRY(dev_check(cudaStreamWaitEvent(cs, a->ev_done, 0), "stream wait"));
-    GSB_TRY(d2h_any(a, values, a->d_values, sizeof(double) * (size_t)a->nnz, cs));
+    GSB_TRY(d2h_any(a, values + sent, a->d_values + sent, sizeof(double) * (size_t)(a->nnz - sent), cs));
     if (rhs) GSB_TRY(d2h_any(a, rhs, a->d_rhs, sizeof(double) * (size_t)N * a->nrhs, cs));
     GSB_TRY(dev_check(cudaStreamSynchronize(cs), "copy stream sync"));
     GSB_TRY(dev_sync(a->stream));

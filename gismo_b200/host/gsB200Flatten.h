@@ -210,35 +210,29 @@ void flatten(const gsMultiPatch<T> & mp, const gsMultiBasis<T> & mb, const gsDof
 }
 
 /// RAII handle of a device assembler (gsb200_create ... gsb200_destroy): never leaks a device context when an
-/// exception unwinds between the calls.
+/// exception unwinds between the calls.  Also remembers the host arrays it page-locked for repeated deliveries.
 struct gsB200Handle
 {
     gsb200_assembler * h;
-    gsB200Handle() : h(NULL) { }
+    void * pinned[2];
+    gsB200Handle() : h(NULL) { pinned[0] = pinned[1] = NULL; }
     ~gsB200Handle() { reset(); }
-    void reset() { if (h) gsb200_destroy(h); h = NULL; }
+    void unpin() { for (int k = 0; k != 2; ++k) { if (pinned[k]) gsb200_host_unpin(pinned[k]); pinned[k] = NULL; } }
+    void reset() { unpin(); if (h) gsb200_destroy(h); h = NULL; }
 private:
     gsB200Handle(const gsB200Handle &); gsB200Handle & operator=(const gsB200Handle &);
 };
 
 inline void check(int rc) { if (rc != GSB200_OK) GISMO_ERROR("gsB200: " << gsb200_last_error()); }
 
-/** Assemble on the device and deliver straight into a gsSparseMatrix / gsMatrix: the matrix is sized like Eigen's
-    compressed form (SparseMatrix.h:150-177,626,649) and the library writes outerIndexPtr / innerIndexPtr / valuePtr /
-    rhs.data() itself (pinned staging ring, no intermediate std::vector).  \a handle keeps the device context: a second
-    call with keepPattern = true re-assembles values and right-hand side only (same mesh, new data). */
+/** First assembly on a mesh: pattern + values + right-hand side straight into a gsSparseMatrix / gsMatrix.  The matrix
+    is sized like Eigen's compressed form (SparseMatrix.h:150-177,626,649) and the library writes outerIndexPtr /
+    innerIndexPtr / valuePtr / rhs.data() itself (pinned staging ring drained by host threads, no intermediate
+    std::vector).  \a handle keeps the device context for reassembleInto(). */
 template <class T>
-void assembleInto(gsB200Problem & st, int device, gsB200Handle & handle, bool keepPattern,
-                  gsSparseMatrix<T> & m, gsMatrix<T> & rhs)
+void assembleInto(gsB200Problem & st, int device, gsB200Handle & handle, gsSparseMatrix<T> & m, gsMatrix<T> & rhs)
 {
     const index_t n = st.pb.nfree;
-    rhs.setZero(n, st.pb.nrhs);
-    if (handle.h && keepPattern && m.rows() == n && m.isCompressed())
-    {
-        if (st.pb.fixed) check(gsb200_set_fixed(handle.h, st.pb.fixed));
-        check(gsb200_assemble_values_to_host(handle.h, m.valuePtr(), rhs.data()));
-        return;
-    }
     handle.reset();
     check(gsb200_create(&st.pb, device, &handle.h));
     check(gsb200_build_pattern(handle.h));
@@ -246,9 +240,37 @@ void assembleInto(gsB200Problem & st, int device, gsB200Handle & handle, bool ke
     check(gsb200_nnz(handle.h, &nnz));
     GISMO_ENSURE(nnz <= static_cast<int64_t>(std::numeric_limits<index_t>::max()),
                  "gsB200: nnz exceeds index_t; use the device view (gsb200_device_view_get)");
+    rhs.setZero(n, st.pb.nrhs);
     m.resize(n, n);
     m.resizeNonZeros(static_cast<index_t>(nnz));
     check(gsb200_assemble_to_host(handle.h, m.outerIndexPtr(), m.innerIndexPtr(), m.valuePtr(), rhs.data()));
+}
+
+/// True if \a handle holds the pattern \a m was filled from (same size, still compressed).
+template <class T>
+bool canReassemble(const gsB200Handle & handle, const gsSparseMatrix<T> & m, const gsMatrix<T> & rhs)
+{
+    int64_t nnz = 0;
+    return handle.h && m.isCompressed() && gsb200_nnz(handle.h, &nnz) == GSB200_OK && nnz == m.nonZeros()
+        && rhs.rows() == m.rows() && m.rows() > 0;
+}
+
+/** Re-assembly on the kept device pattern (same mesh, geometry, source term; new eliminated-DOF values \a fixed, may be
+    empty): values and right-hand side only are recomputed and transferred.  The value array and the right-hand side are
+    page-locked once (cudaHostRegister through gsb200_host_pin; released by the handle), so that the copy engine writes
+    them directly at the PCIe rate while the later chunks of the matrix are still being integrated. */
+template <class T>
+void reassembleInto(gsB200Handle & handle, const gsMatrix<T> & fixed, gsSparseMatrix<T> & m, gsMatrix<T> & rhs)
+{
+    if (handle.pinned[0] != static_cast<void*>(m.valuePtr()) || handle.pinned[1] != static_cast<void*>(rhs.data()))
+    {
+        handle.unpin();
+        if (gsb200_host_pin(m.valuePtr(), static_cast<int64_t>(m.nonZeros()) * sizeof(T)) == GSB200_OK) handle.pinned[0] = m.valuePtr();
+        if (gsb200_host_pin(rhs.data(), static_cast<int64_t>(rhs.size()) * sizeof(T)) == GSB200_OK) handle.pinned[1] = rhs.data();
+        // a failed registration is not an error: the staging ring serves pageable memory
+    }
+    if (fixed.size() != 0) check(gsb200_set_fixed(handle.h, fixed.data()));
+    check(gsb200_assemble_values_to_host(handle.h, m.valuePtr(), rhs.data()));
 }
 
 } // namespace b200

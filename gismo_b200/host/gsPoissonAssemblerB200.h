@@ -61,6 +61,13 @@ public:
         // Dirichlet values stay on the reference's host code: they are inputs.
         Base::computeDirichletDofs();
 
+        // repeated assemble() on the same mesh (setKeepPattern): new Dirichlet values go up, values and rhs come back
+        if (m_keepPattern && b200::canReassemble(m_handle, m_system.matrix(), m_system.rhs()))
+        {
+            b200::reassembleInto(m_handle, m_ddof[0], m_system.matrix(), m_system.rhs());
+            return;
+        }
+
         b200::gsB200Problem st;
         b200::flatten(m_pde_ptr->domain(), m_bases[0], m_system.colMapper(0), 1, m_ddof[0],
                       m_options, GSB200_FORM_POISSON, st);
@@ -69,9 +76,8 @@ public:
         b200::flattenSource(*ppde.rhs(), st.pb.nrhs, st);
         b200::flattenNeumann(m_pde_ptr->bc(), m_pde_ptr->domain().parDim(), st);   // gsVisitorNeumann on the device
 
-        // explicit device handle: pattern + values straight into m_system (no static state, no staging vectors);
-        // a repeated assemble() on the same mesh re-assembles values and rhs only
-        b200::assembleInto(st, m_device, m_handle, m_keepPattern, m_system.matrix(), m_system.rhs());
+        // explicit device handle: pattern + values straight into m_system (no static state, no staging vectors)
+        b200::assembleInto(st, m_device, m_handle, m_system.matrix(), m_system.rhs());
     }
 
 protected:
@@ -98,7 +104,7 @@ template <class T = real_t>
 class gsExprAssemblerB200
 {
 public:
-    gsExprAssemblerB200() : m_ref(1,1), m_mp(NULL), m_mb(NULL), m_bc(NULL), m_dim(1), m_device(0), m_keepPattern(false) { }
+    gsExprAssemblerB200() : m_ref(1,1), m_mp(NULL), m_mb(NULL), m_bc(NULL), m_dim(1), m_device(0), m_keepPattern(false), m_lastForm(-1) { }
 
     void setOptions(const gsOptionList & o) { m_ref.setOptions(o); }
     gsOptionList & options() { return m_ref.options(); }
@@ -137,13 +143,19 @@ public:
 private:
     void run(int form, T c0, T c1, const gsFunction<T> & f)
     {
+        if (m_keepPattern && form == m_lastForm && b200::canReassemble(m_handle, m_matrix, m_rhs))
+        {
+            b200::reassembleInto(m_handle, m_fixed, m_matrix, m_rhs);
+            return;
+        }
         b200::gsB200Problem st;
         b200::flatten(*m_mp, *m_mb, m_mapper, m_dim, m_fixed, m_ref.options(), form, st);
         st.pb.coef[0] = c0; st.pb.coef[1] = c1;
         st.pb.nrhs = 1;
         b200::flattenSource(f, form == GSB200_FORM_ELASTICITY ? m_dim : 1, st);
         if (m_bc) b200::flattenNeumann(*m_bc, m_mp->parDim(), st);
-        b200::assembleInto(st, m_device, m_handle, m_keepPattern, m_matrix, m_rhs);
+        b200::assembleInto(st, m_device, m_handle, m_matrix, m_rhs);
+        m_lastForm = form;
     }
 
     gsExprAssembler<T> m_ref;      // used for set-up only (mapper, Dirichlet values)
@@ -153,6 +165,7 @@ private:
     index_t m_dim;
     int m_device;
     bool m_keepPattern;
+    int m_lastForm;
     b200::gsB200Handle m_handle;
     gsDofMapper m_mapper;
     gsMatrix<T> m_fixed;

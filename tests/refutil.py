@@ -219,19 +219,7 @@ def emul_lib():
     if _emul is None:
         build_emul()
         lib = C.CDLL(EMUL_SO)
-        lib.gsb200_last_error.restype = C.c_char_p
-        lib.gsb200_assemble_host.argtypes = [C.POINTER(ProblemStruct), C.c_int, C.POINTER(C.c_int64), _ip, _ip, _dp, _dp]
-        lib.gsb200_expr_compile.argtypes = [C.c_char_p, _ip, C.c_int32, _ip, _dp, C.c_int32, _ip]
-        lib.gsb200_create.argtypes = [C.POINTER(ProblemStruct), C.c_int, C.POINTER(C.c_void_p)]
-        lib.gsb200_destroy.argtypes = [C.c_void_p]
-        lib.gsb200_destroy.restype = None
-        lib.gsb200_set_workspace_limit.argtypes = [C.c_void_p, C.c_int64]
-        lib.gsb200_build_pattern.argtypes = [C.c_void_p]
-        lib.gsb200_assemble.argtypes = [C.c_void_p]
-        lib.gsb200_nnz.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
-        lib.gsb200_download_csc.argtypes = [C.c_void_p, _ip, _ip, _dp]
-        lib.gsb200_download_rhs.argtypes = [C.c_void_p, _dp]
-        lib.gsb200_timings_get.argtypes = [C.c_void_p, C.POINTER(capi.Timings)]
+        capi.declare(lib)
         _emul = lib
     return _emul
 
@@ -270,6 +258,35 @@ def lib_assemble(lib, pb: Problem, device: int = 0, workspace_limit: int = 0):
         tm = capi.Timings()
         lib.gsb200_timings_get(h, C.byref(tm))
         return outer, inner, values, rhs, tm
+    finally:
+        lib.gsb200_destroy(h)
+
+
+def lib_reassemble(lib, pb: Problem, fixed2: np.ndarray, device: int = 0):
+    """First delivery (gsb200_assemble_to_host), then new eliminated-DOF values (gsb200_set_fixed) and a values-only
+    re-assembly on the kept pattern (gsb200_assemble_values_to_host).  Returns both results."""
+    h = C.c_void_p()
+    def chk(rc):
+        if rc:
+            raise RuntimeError(f"gsb200 error {rc}: {lib.gsb200_last_error().decode()}")
+    chk(lib.gsb200_create(C.byref(pb.struct), device, C.byref(h)))
+    try:
+        chk(lib.gsb200_build_pattern(h))
+        nnz = C.c_int64(0)
+        chk(lib.gsb200_nnz(h, C.byref(nnz)))
+        outer = np.zeros(pb.nfree + 1, np.int32)
+        inner = np.zeros(nnz.value, np.int32)
+        values = np.zeros(nnz.value)
+        rhs = np.zeros((pb.nfree, pb.nrhs), order="F")
+        chk(lib.gsb200_assemble_to_host(h, outer.ctypes.data_as(_ip), inner.ctypes.data_as(_ip), values.ctypes.data_as(_dp), rhs.ctypes.data_as(_dp)))
+        tm = capi.Timings()
+        lib.gsb200_timings_get(h, C.byref(tm))
+        first = (outer, inner, values.copy(), rhs.copy(), tm)
+        f2 = np.asfortranarray(fixed2, dtype=np.float64)
+        chk(lib.gsb200_set_fixed(h, f2.ctypes.data_as(_dp)))
+        values[:] = np.nan; rhs[:] = np.nan
+        chk(lib.gsb200_assemble_values_to_host(h, values.ctypes.data_as(_dp), rhs.ctypes.data_as(_dp)))
+        return first, (outer, inner, values, rhs, tm)
     finally:
         lib.gsb200_destroy(h)
 

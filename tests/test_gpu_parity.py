@@ -236,3 +236,22 @@ def test_fused_second_and_last_sweep_opt_in(lib, name, monkeypatch):
     monkeypatch.setenv("GSB200_S23", "1")
     pb, z = G.load(name, g.expr_compile)
     G.check_against(R.lib_assemble(lib, pb), z, TOL)
+
+
+@pytest.mark.parametrize("name,chunks", [("cube_p3_m16", 3), ("cube_p3_curved_m4", 8), ("sq_p2_m64", 4), ("grid2x2_p2_m4", 4)])
+def test_values_only_reassembly_with_streamed_column_ranges(lib, name, chunks, monkeypatch):
+    """gsb200_assemble_to_host, then gsb200_set_fixed + gsb200_assemble_values_to_host on the kept pattern (what
+    gsPoissonAssemblerB200::setKeepPattern drives): finished column ranges travel while later chunks integrate.  Same values
+    bit for bit as a one-piece assembly of the changed problem; multi-patch problems fall back to one delivery."""
+    monkeypatch.setenv("GSB200_DELIVER_CHUNKS", str(chunks))
+    monkeypatch.setenv("GSB200_DELIVER_MIN_NNZ", "0")
+    pb, z = G.load(name, g.expr_compile)
+    rng = np.random.default_rng(5)
+    fixed2 = rng.uniform(-1, 1, (pb.nfixed, pb.nrhs))
+    first, again = R.lib_reassemble(lib, pb, fixed2)
+    G.check_against(first, z, TOL)
+    assert first[4].nchunks > 1 or len(pb.patches) > 1         # (nchunks counts one per patch at least)
+    ref = R.lib_assemble(lib, pb.with_fixed(fixed2))
+    assert np.array_equal(again[2], ref[2])
+    ok, msg = R.compare_csc(again, ref, 1e-13)
+    assert ok, msg
