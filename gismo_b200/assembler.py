@@ -22,16 +22,22 @@ class DeviceAssembler:
     """Handle on a device-resident problem (gsb200_create ... gsb200_destroy)."""
 
     def __init__(self, problem: Problem, device: int = 0, stream: Optional[int] = None,
-                 workspace_limit: int = 0):
-        self.lib = capi.load_library()
+                 workspace_limit: int = 0, lib=None):
+        """lib: another build of the same C ABI (the tests drive the kernel interpreter through this class); default:
+        the CUDA extension, which must exist (no fallback)."""
+        self.lib = lib if lib is not None else capi.load_library()
         self.problem = problem
         self._h = C.c_void_p()
-        check(self.lib.gsb200_create(C.byref(problem.struct), device, C.byref(self._h)))
+        self._check(self.lib.gsb200_create(C.byref(problem.struct), device, C.byref(self._h)))
         if stream is not None:
-            check(self.lib.gsb200_set_stream(self._h, C.c_void_p(stream)))
+            self._check(self.lib.gsb200_set_stream(self._h, C.c_void_p(stream)))
         if workspace_limit:
-            check(self.lib.gsb200_set_workspace_limit(self._h, workspace_limit))
+            self._check(self.lib.gsb200_set_workspace_limit(self._h, workspace_limit))
         self._pattern = False
+
+    def _check(self, status: int) -> None:
+        if status != 0:
+            raise capi.Gsb200Error(f"gsb200 error {status}: {self.lib.gsb200_last_error().decode()}")
 
     def close(self):
         if self._h:
@@ -49,23 +55,23 @@ class DeviceAssembler:
         return self.problem.nfree
 
     def buildPattern(self) -> int:
-        check(self.lib.gsb200_build_pattern(self._h))
+        self._check(self.lib.gsb200_build_pattern(self._h))
         self._pattern = True
         return self.nnz()
 
     def assemble(self, sync: bool = True) -> None:
         if not self._pattern:
             self.buildPattern()
-        check(self.lib.gsb200_assemble(self._h))
+        self._check(self.lib.gsb200_assemble(self._h))
         if sync:
             self.synchronize()
 
     def synchronize(self) -> None:
-        check(self.lib.gsb200_synchronize(self._h))
+        self._check(self.lib.gsb200_synchronize(self._h))
 
     def nnz(self) -> int:
         n = C.c_int64(0)
-        check(self.lib.gsb200_nnz(self._h, C.byref(n)))
+        self._check(self.lib.gsb200_nnz(self._h, C.byref(n)))
         return n.value
 
     def matrix(self) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
@@ -74,12 +80,12 @@ class DeviceAssembler:
         outer = np.zeros(self.problem.nfree + 1, np.int32)
         inner = np.zeros(nnz, np.int32)
         values = np.zeros(nnz, np.float64)
-        check(self.lib.gsb200_download_csc(self._h, outer.ctypes.data_as(_ip), inner.ctypes.data_as(_ip),
+        self._check(self.lib.gsb200_download_csc(self._h, outer.ctypes.data_as(_ip), inner.ctypes.data_as(_ip),
                                            values.ctypes.data_as(_dp)))
         return outer, inner, values
 
     def matrix_into(self, outer: np.ndarray, inner: np.ndarray, values: np.ndarray) -> None:
-        check(self.lib.gsb200_download_csc(self._h, outer.ctypes.data_as(_ip), inner.ctypes.data_as(_ip),
+        self._check(self.lib.gsb200_download_csc(self._h, outer.ctypes.data_as(_ip), inner.ctypes.data_as(_ip),
                                            values.ctypes.data_as(_dp)))
 
     def assemble_into(self, outer: np.ndarray, inner: np.ndarray, values: np.ndarray, rhs: Optional[np.ndarray] = None) -> None:
@@ -87,33 +93,33 @@ class DeviceAssembler:
         the values are integrated).  What gsPoissonAssemblerB200::assemble() does after sizing the matrix."""
         if not self._pattern:
             self.buildPattern()
-        check(self.lib.gsb200_assemble_to_host(self._h, outer.ctypes.data_as(_ip), inner.ctypes.data_as(_ip), values.ctypes.data_as(_dp),
+        self._check(self.lib.gsb200_assemble_to_host(self._h, outer.ctypes.data_as(_ip), inner.ctypes.data_as(_ip), values.ctypes.data_as(_dp),
                                                rhs.ctypes.data_as(_dp) if rhs is not None else None))
 
     def pattern_into(self, outer: np.ndarray, inner: np.ndarray) -> None:
         """gsb200_download_pattern: the index arrays, once per mesh."""
         if not self._pattern:
             self.buildPattern()
-        check(self.lib.gsb200_download_pattern(self._h, outer.ctypes.data_as(_ip), inner.ctypes.data_as(_ip)))
+        self._check(self.lib.gsb200_download_pattern(self._h, outer.ctypes.data_as(_ip), inner.ctypes.data_as(_ip)))
 
     def set_fixed(self, fixed: Optional[np.ndarray]) -> None:
         """gsb200_set_fixed: new eliminated-DOF values (nfixed x nrhs, column-major) on the kept pattern."""
         if fixed is None:
-            check(self.lib.gsb200_set_fixed(self._h, None))
+            self._check(self.lib.gsb200_set_fixed(self._h, None))
         else:
             f = np.asfortranarray(fixed, dtype=np.float64)
-            check(self.lib.gsb200_set_fixed(self._h, f.ctypes.data_as(_dp)))
+            self._check(self.lib.gsb200_set_fixed(self._h, f.ctypes.data_as(_dp)))
 
     def assemble_values_into(self, values: np.ndarray, rhs: Optional[np.ndarray] = None) -> None:
         """gsb200_assemble_values_to_host: re-assembly on the kept pattern, values (+ rhs) only travel."""
         if not self._pattern:
             self.buildPattern()
-        check(self.lib.gsb200_assemble_values_to_host(self._h, values.ctypes.data_as(_dp),
+        self._check(self.lib.gsb200_assemble_values_to_host(self._h, values.ctypes.data_as(_dp),
                                                       rhs.ctypes.data_as(_dp) if rhs is not None else None))
 
     def rhs(self) -> np.ndarray:
         r = np.zeros((self.problem.nfree, self.problem.nrhs), np.float64, order="F")
-        check(self.lib.gsb200_download_rhs(self._h, r.ctypes.data_as(_dp)))
+        self._check(self.lib.gsb200_download_rhs(self._h, r.ctypes.data_as(_dp)))
         return r
 
     def scipy_matrix(self):
@@ -125,32 +131,76 @@ class DeviceAssembler:
     # --- device-side access -----------------------------------------------------------
     def device_view(self) -> DeviceView:
         v = DeviceView()
-        check(self.lib.gsb200_device_view_get(self._h, C.byref(v)))
+        self._check(self.lib.gsb200_device_view_get(self._h, C.byref(v)))
         return v
 
     def timings(self) -> Timings:
         t = Timings()
-        check(self.lib.gsb200_timings_get(self._h, C.byref(t)))
+        self._check(self.lib.gsb200_timings_get(self._h, C.byref(t)))
         return t
 
     def jit_launches(self) -> int:
         """Geometry launches of the last assemble() that ran the NVRTC-compiled source term."""
         n = C.c_int(0)
-        check(self.lib.gsb200_jit_launches(self._h, C.byref(n)))
+        self._check(self.lib.gsb200_jit_launches(self._h, C.byref(n)))
         return n.value
 
     # --- consumer (SURVEY 8f-1) -------------------------------------------------------
     def spmv(self, x: np.ndarray) -> np.ndarray:
         x = np.ascontiguousarray(x, dtype=np.float64)
         y = np.zeros_like(x)
-        check(self.lib.gsb200_spmv_host(self._h, x.ctypes.data_as(_dp), y.ctypes.data_as(_dp)))
+        self._check(self.lib.gsb200_spmv_host(self._h, x.ctypes.data_as(_dp), y.ctypes.data_as(_dp)))
         return y
+
+    def spmv_info(self):
+        """(columns on the regular-stencil path, offset tables) of the SpMV."""
+        n, t = C.c_int64(0), C.c_int32(0)
+        self._check(self.lib.gsb200_spmv_info(self._h, C.byref(n), C.byref(t)))
+        return n.value, t.value
+
+    # --- multi-GPU (SURVEY 8e): the library's own NCCL communicator, or a caller-supplied reduction ------------
+    def comm_init(self, unique_id: bytes) -> None:
+        """gsb200_comm_init (collective): `unique_id` = the 128 bytes rank 0 got from comm_unique_id()."""
+        buf = C.create_string_buffer(bytes(unique_id), capi.COMM_ID_BYTES)
+        self._check(self.lib.gsb200_comm_init(self._h, buf))
+
+    def set_allreduce(self, fn) -> None:
+        """gsb200_set_allreduce: fn(buffer_address, count, stream) sums `count` doubles in place over the ranks."""
+        def trampoline(ctx, buf, count, stream):
+            try:
+                fn(C.addressof(buf.contents), int(count), stream)
+                return 0
+            except Exception:       # noqa: the C side turns the status into an error
+                return 1
+        self._ar_cb = capi.ALLREDUCE_FN(trampoline)        # keep the callback object alive
+        self._check(self.lib.gsb200_set_allreduce(self._h, self._ar_cb, None))
+
+    def exchange(self) -> None:
+        """gsb200_exchange: coupled columns + right-hand side summed over the ranks (after assemble)."""
+        self._check(self.lib.gsb200_exchange(self._h))
+
+    def comm_stats(self):
+        b, n = C.c_int64(0), C.c_int32(0)
+        self._check(self.lib.gsb200_comm_stats(self._h, C.byref(b), C.byref(n)))
+        return b.value, n.value
+
+    def cg_solve(self, b: Optional[np.ndarray] = None, max_iter: int = 1000, tol: float = 1e-10, check_every: int = 10, want_x: bool = True):
+        """gsb200_cg_solve: Jacobi-CG across the ranks; b None = the assembled (exchanged) right-hand side."""
+        bp = None
+        if b is not None:
+            b = np.ascontiguousarray(b, dtype=np.float64).ravel()
+            bp = b.ctypes.data_as(_dp)
+        x = np.zeros(self.problem.nfree) if want_x else None
+        it, res = C.c_int(0), C.c_double(0)
+        self._check(self.lib.gsb200_cg_solve(self._h, bp, x.ctypes.data_as(_dp) if want_x else None, max_iter, tol, check_every,
+                                       C.byref(it), C.byref(res)))
+        return x, it.value, res.value
 
     def cg(self, b: np.ndarray, max_iter: int = 1000, tol: float = 1e-10):
         b = np.ascontiguousarray(b, dtype=np.float64).ravel()
         x = np.zeros_like(b)
         it, res = C.c_int(0), C.c_double(0)
-        check(self.lib.gsb200_cg_host(self._h, b.ctypes.data_as(_dp), x.ctypes.data_as(_dp), max_iter, tol,
+        self._check(self.lib.gsb200_cg_host(self._h, b.ctypes.data_as(_dp), x.ctypes.data_as(_dp), max_iter, tol,
                                       C.byref(it), C.byref(res)))
         return x, it.value, res.value
 

@@ -60,6 +60,11 @@ class Timings(C.Structure):
                 ("nchunks", C.c_int32)]
 
 
+COMM_ID_BYTES = 128
+# int fn(void *ctx, double *buf, int64_t count, void *stream): in-place sum of doubles over the ranks
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_int64, C.c_void_p)
+
+
 class Gsb200Error(RuntimeError):
     pass
 
@@ -230,6 +235,15 @@ def declare(lib, optional=()):
     lib.gsb200_expr_eval_host.argtypes = [C.POINTER(Program), C.c_double, C.c_double, C.c_double, _dp]
     lib.gsb200_measure_peaks.argtypes = [C.c_int, _dp, _dp, _dp]
     lib.gsb200_device_count.argtypes = [C.POINTER(C.c_int)]
+    lib.gsb200_comm_unique_id.argtypes = [C.c_void_p]
+    lib.gsb200_comm_init.argtypes = [C.c_void_p, C.c_void_p]
+    lib.gsb200_set_comm.argtypes = [C.c_void_p, C.c_void_p]
+    lib.gsb200_set_allreduce.argtypes = [C.c_void_p, ALLREDUCE_FN, C.c_void_p]
+    lib.gsb200_exchange.argtypes = [C.c_void_p]
+    lib.gsb200_comm_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
+    lib.gsb200_cg_solve.argtypes = [C.c_void_p, _dp, _dp, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), _dp]
+    lib.gsb200_cg_solution_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.gsb200_spmv_info.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
     return lib
 
 

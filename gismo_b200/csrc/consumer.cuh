@@ -1,0 +1,573 @@
+// consumer.cuh — what follows the assembly on the device (included at the end of gsb200.cu):
+//   K4  exchange of the coupled (patch-interface) columns and of the right-hand side between the ranks of a multi-GPU run,
+//       NCCL collectives issued straight on the final sweep's buffers (the reference has no distributed assembly:
+//       gsExprAssembler.h:661 "// mpi assemly. ???"; its MPI wrappers are gsMpiComm.h);
+//   SpMV on the CSC arrays read as CSR of the symmetric matrix; columns whose row set is a translate of a reference stencil
+//       ("regular": interior columns of a tensor patch) read 8 B per entry instead of 12;
+//   Jacobi-preconditioned CG (gsSparseSolver<>::CGDiagonal, gsSparseSolver.h:71-72; gsConjugateGradient.hpp) with all scalars on
+//       the device; across ranks either a neighbour halo exchange of the search direction (contiguous column slabs) or, for
+//       patch-wise ownership, a full-length reduction of the product.
+// NCCL is loaded at run time (dlopen; the copy a host application already loaded - e.g. torch's - is shared), so the library has no
+// link-time dependency on it and a single-GPU caller never touches it.
+
+namespace gsb {
+
+#ifndef GSB200_EMULATE
+// ------------------------------------------------------------------ NCCL, loaded on demand
+struct NcclApi {
+    void *handle = 0; bool tried = false;
+    int (*GetUniqueId)(void *) = 0;
+    int (*CommInitRank)(void **, int, ncclUniqueIdPod, int) = 0;
+    int (*CommDestroy)(void *) = 0;
+    int (*CommCount)(void *, int *) = 0;
+    int (*CommUserRank)(void *, int *) = 0;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = 0;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = 0;
+    int (*Broadcast)(const void *, void *, size_t, int, int, void *, cudaStream_t) = 0;
+    int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = 0;
+    int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = 0;
+    int (*GroupStart)() = 0;
+    int (*GroupEnd)() = 0;
+    const char *(*GetErrorString)(int) = 0;
+};
+enum { NCCL_INT32 = 2, NCCL_FLOAT64 = 8, NCCL_SUM = 0 };     // nccl.h: ncclInt32, ncclFloat64, ncclSum
+static NcclApi &nccl_api()
+{
+    static NcclApi api; static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (api.tried) return api;
+    api.tried = true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) { api.handle = dlopen(n, RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL); if (api.handle) break; }   // already in the process?
+    if (!api.handle) if (const char *e = getenv("GSB200_NCCL_LIB")) api.handle = dlopen(e, RTLD_NOW | RTLD_GLOBAL);
+    for (const char *n : names) { if (api.handle) break; api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL); }
+    if (!api.handle) return api;
+#define GSB_NCCL_SYM(field, name) *(void **)(&api.field) = dlsym(api.handle, name)
+    GSB_NCCL_SYM(GetUniqueId, "ncclGetUniqueId"); GSB_NCCL_SYM(CommInitRank, "ncclCommInitRank"); GSB_NCCL_SYM(CommDestroy, "ncclCommDestroy");
+    GSB_NCCL_SYM(CommCount, "ncclCommCount"); GSB_NCCL_SYM(CommUserRank, "ncclCommUserRank");
+    GSB_NCCL_SYM(AllReduce, "ncclAllReduce"); GSB_NCCL_SYM(AllGather, "ncclAllGather"); GSB_NCCL_SYM(Broadcast, "ncclBroadcast");
+    GSB_NCCL_SYM(Send, "ncclSend"); GSB_NCCL_SYM(Recv, "ncclRecv"); GSB_NCCL_SYM(GroupStart, "ncclGroupStart"); GSB_NCCL_SYM(GroupEnd, "ncclGroupEnd");
+    GSB_NCCL_SYM(GetErrorString, "ncclGetErrorString");
+#undef GSB_NCCL_SYM
+    if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.Send || !api.Recv || !api.GroupStart || !api.GroupEnd || !api.Broadcast || !api.AllGather) { api.handle = 0; }
+    return api;
+}
+static int nccl_check(int rc, const char *what)
+{
+    if (rc == 0) return 0;
+    NcclApi &N = nccl_api();
+    set_error("%s: NCCL error %d (%s)", what, rc, N.GetErrorString ? N.GetErrorString(rc) : "?");
+    return GSB200_ECUDA;
+}
+void destroy_comm(void *comm) { NcclApi &N = nccl_api(); if (N.handle && N.CommDestroy && comm) N.CommDestroy(comm); }
+static int need_nccl(NcclApi **out)
+{
+    NcclApi &N = nccl_api();
+    if (!N.handle) { set_error("libnccl.so.2 could not be loaded (set GSB200_NCCL_LIB): multi-GPU exchange needs NCCL, there is no fallback"); return GSB200_EUNSUPPORTED; }
+    *out = &N; return 0;
+}
+#endif
+
+// in-place sum of `count` doubles over the ranks, ordered on the assembler's stream
+static int comm_allreduce(gsb200_assembler *a, double *buf, i64 count)
+{
+    if (a->nranks == 1 || count <= 0) return 0;
+    if (a->ar_fn) {
+        const int rc = a->ar_fn(a->ar_ctx, buf, count, (void *)(size_t)a->stream);
+        if (rc) { set_error("all-reduce callback failed with %d", rc); return GSB200_ECUDA; }
+        return 0;
+    }
+#ifndef GSB200_EMULATE
+    if (a->comm) { NcclApi *N; GSB_TRY(need_nccl(&N)); return nccl_check(N->AllReduce(buf, buf, (size_t)count, NCCL_FLOAT64, NCCL_SUM, a->comm, a->stream), "ncclAllReduce"); }
+#endif
+    set_error("nranks = %d but no communicator: call gsb200_comm_init / gsb200_set_comm / gsb200_set_allreduce first", a->nranks);
+    return GSB200_ESTATE;
+}
+static int comm_group(gsb200_assembler *a, bool begin)
+{
+#ifndef GSB200_EMULATE
+    if (a->comm && !a->ar_fn) { NcclApi *N; GSB_TRY(need_nccl(&N)); return nccl_check(begin ? N->GroupStart() : N->GroupEnd(), begin ? "ncclGroupStart" : "ncclGroupEnd"); }
+#endif
+    (void)a; (void)begin; return 0;
+}
+
+// ------------------------------------------------------------------ kernels
+// column c is "regular" with table t if it has the table's length and inner[k] - c equals the table's offsets
+GSB_GLOBAL void k_spmv_classify(int n, const i64 *ptr, const int *idx, int ntab, const int *tlen, const int *toff, int tstride, unsigned char *reg)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const i64 b = ptr[c]; const int len = (int)(ptr[c + 1] - b);
+    unsigned char r = 0;
+    for (int t = 0; t < ntab && !r; ++t) {
+        if (tlen[t] != len || len == 0) continue;
+        const int *o = toff + (i64)t * tstride;
+        bool same = idx[b] - c == o[0] && idx[b + len - 1] - c == o[len - 1];
+        for (int k = 1; same && k + 1 < len; ++k) same = idx[b + k] - c == o[k];
+        if (same) r = (unsigned char)(t + 1);
+    }
+    reg[c] = r;
+}
+#ifndef GSB200_EMULATE
+// One warp per stored column (= row, the forms are symmetric).  Regular columns take their row indices from the offset table
+// (L1-resident), so only the values stream from HBM: 8 B per entry; the others read 12 B.  x is gathered through L1/L2.
+// dot != 0: adds sum_c x[c] * y[c] over the processed columns (CG's p.Ap) with one atomic per warp.
+GSB_GLOBAL void __launch_bounds__(256) k_spmv_reg(int c0, int c1, const i64 *ptr, const int *idx, const double *val, const unsigned char *reg,
+                                                  const int *tlen, const int *toff, int tstride, const double *x, double *y, const double *scale, double *dot)
+{
+    const int lane = threadIdx.x & 31;
+    const i64 warp0 = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = ((i64)gridDim.x * blockDim.x) >> 5;
+    double dsum = 0.0;
+    for (i64 r = c0 + warp0; r < c1; r += nwarp) {
+        const i64 b = ptr[r];
+        const int t = reg[r];
+        double s = 0.0;
+        if (t) {
+            const int len = tlen[t - 1]; const int *o = toff + (i64)(t - 1) * tstride;
+            const double *v = val + b, *xr = x + r;
+#pragma unroll 4
+            for (int k = lane; k < len; k += 32) s = fma(__ldcs(v + k), __ldg(xr + __ldg(o + k)), s);
+        } else {
+            const i64 e = ptr[r + 1];
+            for (i64 k = b + lane; k < e; k += 32) s = fma(__ldcs(val + k), __ldg(x + __ldcs(idx + k)), s);
+        }
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o2);
+        if (lane == 0) {
+            if (scale) s *= scale[r];
+            y[r] = s;
+            if (dot) dsum = fma(x[r], s, dsum);
+        }
+    }
+    if (dot && lane == 0 && dsum != 0.0) atomicAdd(dot, dsum);
+}
+#endif
+GSB_GLOBAL void k_spmv_range(int c0, int c1, const i64 *ptr, const int *idx, const double *val, const double *x, double *y, const double *scale, double *dot)
+{
+    const int r = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= c1) return;
+    double s = 0.0;
+    for (i64 k = ptr[r]; k < ptr[r + 1]; ++k) s = fma(val[k], x[idx[k]], s);
+    if (scale) s *= scale[r];
+    y[r] = s;
+    if (dot) atomic_add(dot, x[r] * s);
+}
+// stored[c] = 1.0 if the rank stores column c; diag[c] = its diagonal entry (0 where not stored)
+GSB_GLOBAL void k_cg_diag(int n, const i64 *ptr, const int *idx, const double *val, double *diag, double *stored)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    double s = 0.0;
+    for (i64 k = ptr[r]; k < ptr[r + 1]; ++k) if (idx[k] == r) s = val[k];
+    diag[r] = s; stored[r] = ptr[r + 1] > ptr[r] ? 1.0 : 0.0;
+}
+// d = holders > 0 ? diag / holders : 1 (a column nobody stores: an isolated DOF), 1 where the diagonal vanishes; h = 1 / max(holders, 1)
+GSB_GLOBAL void k_cg_prep(int n, double *diag, double *holders)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double h = holders[i] > 0.0 ? holders[i] : 1.0;
+    const double d = diag[i] / h;
+    diag[i] = d == 0.0 ? 1.0 : d; holders[i] = 1.0 / h;
+}
+GSB_DEVICE void cg_block_add(double s, double *out)
+{
+#ifndef GSB200_EMULATE
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s != 0.0) atomicAdd(out, s);
+#else
+    if (s != 0.0) *out += s;
+#endif
+}
+// scalars S (device): [0] rz  [1] pq  [2] rz_new  [3] rr  [4] bb
+// r = b, z = r / d, p = z on [c0, c1); rz += r.z, bb += b.b
+GSB_GLOBAL void k_cg_start(int c0, int c1, const double *b, const double *d, double *x, double *r, double *z, double *p, double *S)
+{
+    const int i = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    double s0 = 0.0, s1 = 0.0;
+    if (i < c1) { const double bi = b[i]; const double zi = bi / d[i]; x[i] = 0.0; r[i] = bi; z[i] = zi; p[i] = zi; s0 = bi * zi; s1 = bi * bi; }
+    cg_block_add(s0, S + 0); cg_block_add(s1, S + 4);
+}
+GSB_GLOBAL void k_cg_dot(int c0, int c1, const double *u, const double *v, double *out)
+{
+    const int i = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    cg_block_add(i < c1 ? u[i] * v[i] : 0.0, out);
+}
+// alpha = rz / pq;  x += alpha p;  r -= alpha q;  z = r / d;  rz_new += r.z;  rr += r.r
+GSB_GLOBAL void k_cg_step1(int c0, int c1, const double *p, const double *q, const double *d, double *x, double *r, double *z, double *S)
+{
+    const int i = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    const double alpha = S[0] / S[1];
+    double s0 = 0.0, s1 = 0.0;
+    if (i < c1) {
+        x[i] = fma(alpha, p[i], x[i]);
+        const double ri = fma(-alpha, q[i], r[i]); const double zi = ri / d[i];
+        r[i] = ri; z[i] = zi; s0 = ri * zi; s1 = ri * ri;
+    }
+    cg_block_add(s0, S + 2); cg_block_add(s1, S + 3);
+}
+// beta = rz_new / rz;  p = z + beta p
+GSB_GLOBAL void k_cg_step2(int c0, int c1, const double *z, double *p, const double *S)
+{
+    const int i = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < c1) p[i] = fma(S[2] / S[0], p[i], z[i]);
+}
+// rotate the scalars for the next iteration: rz = rz_new, last_rr = rr; accumulators cleared
+GSB_GLOBAL void k_cg_rotate(double *S)
+{
+    if (blockIdx.x || threadIdx.x) return;
+    S[0] = S[2]; S[5] = S[3]; S[1] = 0.0; S[2] = 0.0; S[3] = 0.0;
+}
+// first / last stored column and smallest / largest row index they reference: out = {c_first, c_last + 1, r_min, r_max + 1, stored count}
+GSB_GLOBAL void k_col_extent(int n, const i64 *ptr, const int *idx, int *out)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n || ptr[c + 1] == ptr[c]) return;
+#ifndef GSB200_EMULATE
+    atomicMin(out + 0, c); atomicMax(out + 1, c + 1); atomicMin(out + 2, idx[ptr[c]]); atomicMax(out + 3, idx[ptr[c + 1] - 1] + 1); atomicAdd(out + 4, 1);
+#else
+    out[0] = std::min(out[0], c); out[1] = std::max(out[1], c + 1); out[2] = std::min(out[2], idx[ptr[c]]); out[3] = std::max(out[3], idx[ptr[c + 1] - 1] + 1); out[4] += 1;
+#endif
+}
+
+// ------------------------------------------------------------------ SpMV set-up: offset tables of the regular columns
+static int spmv_prepare(gsb200_assembler *a)
+{
+    if (a->spmv_ready) return 0;
+    const int N = a->nfree; stream_t s = a->stream;
+    // candidate reference columns: the middle function of every (patch, component)
+    std::vector<int> cand;
+    for (size_t ip = 0; ip < a->patches.size(); ++ip) for (int c = 0; c < a->ncomp; ++c) if (a->mid_dof[ip * a->ncomp + c] >= 0) cand.push_back(a->mid_dof[ip * a->ncomp + c]);
+    std::vector<std::vector<int>> tabs;
+    for (int g : cand) {
+        if ((int)tabs.size() >= 32) break;
+        i64 be[2]; GSB_TRY(dev_d2h(be, a->d_colptr + g, 2 * sizeof(i64), s));
+        const int len = (int)(be[1] - be[0]);
+        if (len <= 0 || len > 4096) continue;
+        std::vector<int> o((size_t)len); GSB_TRY(dev_d2h(o.data(), a->d_inner + be[0], sizeof(int) * (size_t)len, s));
+        for (int &v : o) v -= g;
+        bool dup = false; for (auto &t : tabs) if (t == o) dup = true;
+        if (!dup) tabs.push_back(o);
+    }
+    a->reg_ntab = (int)tabs.size(); a->reg_stride = 1;
+    for (auto &t : tabs) a->reg_stride = std::max(a->reg_stride, (int)t.size());
+    std::vector<int> tlen(std::max(1, a->reg_ntab)), toff((size_t)std::max(1, a->reg_ntab) * a->reg_stride, 0);
+    for (int t = 0; t < a->reg_ntab; ++t) { tlen[t] = (int)tabs[t].size(); std::copy(tabs[t].begin(), tabs[t].end(), toff.begin() + (size_t)t * a->reg_stride); }
+    dev_free(a->d_reg); dev_free(a->d_regoff); dev_free(a->d_reglen); a->d_reg = 0; a->d_regoff = 0; a->d_reglen = 0;
+    GSB_TRY(upload(&a->d_reglen, tlen, s)); GSB_TRY(upload(&a->d_regoff, toff, s));
+    GSB_TRY(dev_malloc((void **)&a->d_reg, (size_t)N + 1));
+    GSB_LAUNCH(k_spmv_classify, dim3((N + 127) / 128), dim3(128), s, N, a->d_colptr, a->d_inner, a->reg_ntab, a->d_reglen, a->d_regoff, a->reg_stride, a->d_reg);
+    // extent of the stored columns (ownership for the distributed CG, gsb200_device_view)
+    int ext[5] = {N, 0, N, 0, 0}; int *d_ext = 0;
+    GSB_TRY(dev_malloc((void **)&d_ext, sizeof ext)); GSB_TRY(dev_h2d(d_ext, ext, sizeof ext, s));
+    GSB_LAUNCH(k_col_extent, dim3((N + 127) / 128), dim3(128), s, N, a->d_colptr, a->d_inner, d_ext);
+    GSB_TRY(dev_d2h(ext, d_ext, sizeof ext, s)); dev_free(d_ext);
+    if (ext[4] == 0) { ext[0] = ext[1] = ext[2] = ext[3] = 0; }
+    a->own_c0 = ext[0]; a->own_c1 = ext[1]; a->need_lo = std::min(ext[2], ext[0]); a->need_hi = std::max(ext[3], ext[1]); a->own_contig = ext[4] == ext[1] - ext[0];
+    a->spmv_ready = true;
+    return 0;
+}
+
+// y[c] = (A x)[c] * scale[c] for the columns [c0, c1) (the others are left alone)
+static int spmv_range(gsb200_assembler *a, int c0, int c1, const double *x, double *y, const double *scale, double *dot)
+{
+    if (c1 <= c0) return 0;
+    GSB_TRY(spmv_prepare(a));
+#ifndef GSB200_EMULATE
+    if (!dry_run()) {
+        k_spmv_reg<<<148 * 8, 256, 0, a->stream>>>(c0, c1, a->d_colptr, a->d_inner, a->d_values, a->d_reg, a->d_reglen, a->d_regoff, a->reg_stride, x, y, scale, dot);
+        note_launch();
+    }
+#else
+    GSB_LAUNCH(k_spmv_range, dim3((c1 - c0 + 127) / 128), dim3(128), a->stream, c0, c1, a->d_colptr, a->d_inner, a->d_values, x, y, scale, dot);
+#endif
+    return 0;
+}
+
+// ------------------------------------------------------------------ K4: coupled columns + right-hand side across the ranks
+static int exchange(gsb200_assembler *a)
+{
+    a->xchg_bytes = 0;
+    if (a->nranks == 1) return 0;
+    GSB_TRY(comm_group(a, true));
+    int rc = 0;
+    for (size_t k = 0; k + 1 < a->coupled_off.size() && !rc; k += 2) {
+        const i64 b = a->coupled_off[k], e = a->coupled_off[k + 1];
+        if (e > b) { rc = comm_allreduce(a, a->d_values + b, e - b); a->xchg_bytes += 8 * (e - b); }
+    }
+    if (!rc) { rc = comm_allreduce(a, a->d_rhs, (i64)a->nfree * a->nrhs); a->xchg_bytes += 8 * (i64)a->nfree * a->nrhs; }
+    const int rc2 = comm_group(a, false);
+    ++a->xchg_calls;
+    return rc ? rc : rc2;
+}
+
+// ------------------------------------------------------------------ CG
+struct CgPlan { bool halo; int c0, c1; std::vector<int> ext; };    // ext: per rank {c0, c1, need_lo, need_hi}
+
+static int cg_plan(gsb200_assembler *a, CgPlan &P)
+{
+    const int N = a->nfree;
+    GSB_TRY(spmv_prepare(a));
+    P.halo = false; P.c0 = 0; P.c1 = N;
+    if (a->nranks == 1) return 0;
+#ifndef GSB200_EMULATE
+    if (a->comm && !a->ar_fn && a->coupled_runs.empty() && a->patches.size() == 1) {
+        // contiguous column slabs: every rank learns everybody's owned range and row reach
+        NcclApi *NC; GSB_TRY(need_nccl(&NC));
+        int mine[4] = {a->own_c0, a->own_c1, a->need_lo, a->need_hi}; int *d_all = 0;
+        if (!a->own_contig) mine[0] = mine[1] = -1;
+        GSB_TRY(dev_malloc((void **)&d_all, sizeof(int) * 4 * (size_t)(a->nranks + 1)));
+        GSB_TRY(dev_h2d(d_all + 4 * a->nranks, mine, sizeof mine, a->stream));
+        GSB_TRY(nccl_check(NC->AllGather(d_all + 4 * a->nranks, d_all, 4, NCCL_INT32, a->comm, a->stream), "ncclAllGather"));
+        P.ext.assign(4 * (size_t)a->nranks, 0);
+        GSB_TRY(dev_d2h(P.ext.data(), d_all, sizeof(int) * 4 * (size_t)a->nranks, a->stream));
+        dev_free(d_all);
+        bool ok = true; int covered = 0;
+        for (int r = 0; r < a->nranks; ++r) { if (P.ext[4 * r] < 0) ok = false; covered += P.ext[4 * r + 1] - P.ext[4 * r]; }
+        if (ok && covered == N) { P.halo = true; P.c0 = a->own_c0; P.c1 = a->own_c1; }
+    }
+#endif
+    return 0;
+}
+
+#ifndef GSB200_EMULATE
+// the pieces of `v` this rank's rows reach into other ranks' slabs, and vice versa
+static int cg_halo(gsb200_assembler *a, const CgPlan &P, double *v)
+{
+    NcclApi *NC; GSB_TRY(need_nccl(&NC));
+    const int me = a->rank;
+    GSB_TRY(nccl_check(NC->GroupStart(), "ncclGroupStart"));
+    int rc = 0;
+    for (int r = 0; r < a->nranks && !rc; ++r) {
+        if (r == me) continue;
+        // what I need from r: [need_lo, need_hi) of mine  intersected with r's slab
+        const int lo = std::max(P.ext[4 * me + 2], P.ext[4 * r]), hi = std::min(P.ext[4 * me + 3], P.ext[4 * r + 1]);
+        if (hi > lo) { rc = nccl_check(NC->Recv(v + lo, (size_t)(hi - lo), NCCL_FLOAT64, r, a->comm, a->stream), "ncclRecv"); a->xchg_bytes += 8 * (i64)(hi - lo); }
+        const int slo = std::max(P.ext[4 * r + 2], P.ext[4 * me]), shi = std::min(P.ext[4 * r + 3], P.ext[4 * me + 1]);
+        if (!rc && shi > slo) rc = nccl_check(NC->Send(v + slo, (size_t)(shi - slo), NCCL_FLOAT64, r, a->comm, a->stream), "ncclSend");
+    }
+    const int rc2 = nccl_check(NC->GroupEnd(), "ncclGroupEnd");
+    return rc ? rc : rc2;
+}
+#endif
+
+static int cg_solve(gsb200_assembler *a, const double *b_dev, int max_iter, double tol, int check_every, int *iters, double *rel_residual)
+{
+    const int N = a->nfree; stream_t s = a->stream;
+    for (int k = 0; k < 8; ++k) if (!a->cgv[k]) GSB_TRY(dev_malloc((void **)&a->cgv[k], sizeof(double) * (size_t)(N + 8)));
+    double *X = a->cgv[0], *R = a->cgv[1], *Z = a->cgv[2], *Pv = a->cgv[3], *Q = a->cgv[4], *Dg = a->cgv[5], *H = a->cgv[6], *S = a->cgv[7];
+    CgPlan P; GSB_TRY(cg_plan(a, P));
+    a->xchg_bytes = 0;
+    const dim3 gN((N + 127) / 128), t(128);
+    const int c0 = P.c0, c1 = P.c1; const dim3 gO((std::max(c1 - c0, 1) + 127) / 128);
+    const bool multi = a->nranks > 1;
+    // preconditioner: diagonal of the stored columns; columns stored by several ranks (coupled, already exchanged) count once
+    GSB_LAUNCH(k_cg_diag, gN, t, s, N, a->d_colptr, a->d_inner, a->d_values, Dg, H);
+    if (multi && !P.halo) { GSB_TRY(comm_allreduce(a, Dg, N)); GSB_TRY(comm_allreduce(a, H, N)); }
+    GSB_LAUNCH(k_cg_prep, gN, t, s, N, Dg, H);
+    GSB_TRY(dev_memset(S, 0, 8 * sizeof(double), s));
+    if (multi && !P.halo) { GSB_TRY(dev_memset(X, 0, sizeof(double) * (size_t)N, s)); }
+    GSB_LAUNCH(k_cg_start, gO, t, s, c0, c1, b_dev, Dg, X, R, Z, Pv, S);
+    if (P.halo) GSB_TRY(comm_allreduce(a, S, 8));
+    double hs[8]; GSB_TRY(dev_d2h(hs, S, sizeof hs, s));
+    const double bb = hs[4]; double rr = bb;
+    const double thr = tol * tol * bb;
+    int it = 0;
+    if (check_every < 1) check_every = 1;
+    while (it < max_iter && rr > thr) {
+        const int burst = std::min(check_every, max_iter - it);
+        for (int k = 0; k < burst; ++k) {
+#ifndef GSB200_EMULATE
+            if (P.halo) GSB_TRY(cg_halo(a, P, Pv));
+#endif
+            if (P.halo || !multi) {
+                GSB_TRY(spmv_range(a, c0, c1, Pv, Q, 0, S + 1));
+                if (P.halo) GSB_TRY(comm_allreduce(a, S + 1, 1));
+            } else {
+                // patch-wise ownership: every rank multiplies the columns it stores (shared ones weighted 1/holders), the products add up
+                GSB_TRY(spmv_range(a, 0, N, Pv, Q, H, 0));
+                GSB_TRY(comm_allreduce(a, Q, N)); a->xchg_bytes += 8 * (i64)N;
+                GSB_LAUNCH(k_cg_dot, gN, t, s, 0, N, Pv, Q, S + 1);
+            }
+            GSB_LAUNCH(k_cg_step1, gO, t, s, c0, c1, Pv, Q, Dg, X, R, Z, S);
+            if (P.halo) GSB_TRY(comm_allreduce(a, S + 2, 2));
+            GSB_LAUNCH(k_cg_step2, gO, t, s, c0, c1, Z, Pv, S);
+            GSB_LAUNCH(k_cg_rotate, dim3(1), dim3(32), s, S);
+            ++it;
+        }
+        GSB_TRY(dev_d2h(hs, S, sizeof hs, s));
+        rr = hs[5];
+        if (!(rr == rr)) { set_error("CG broke down (NaN residual) at iteration %d", it); return GSB200_ECUDA; }
+    }
+#ifndef GSB200_EMULATE
+    if (P.halo) {       // every rank gets the whole solution: each slab is broadcast by its owner
+        NcclApi *NC; GSB_TRY(need_nccl(&NC));
+        GSB_TRY(nccl_check(NC->GroupStart(), "ncclGroupStart"));
+        int rc = 0;
+        for (int r = 0; r < a->nranks && !rc; ++r) {
+            const int lo = P.ext[4 * r], hi = P.ext[4 * r + 1];
+            if (hi > lo) rc = nccl_check(NC->Broadcast(X + lo, X + lo, (size_t)(hi - lo), NCCL_FLOAT64, r, a->comm, s), "ncclBroadcast");
+        }
+        const int rc2 = nccl_check(NC->GroupEnd(), "ncclGroupEnd");
+        if (rc || rc2) return rc ? rc : rc2;
+    }
+#endif
+    GSB_TRY(dev_sync(s));
+    a->cg_halo_mode = P.halo;
+    if (iters) *iters = it;
+    if (rel_residual) *rel_residual = bb > 0 ? sqrt(rr / bb) : 0.0;
+    return 0;
+}
+
+} // namespace gsb
+
+// ====================================================================== C ABI (consumer side)
+extern "C" {
+
+int gsb200_comm_unique_id(void *id128)
+{
+    if (!id128) return GSB200_EINVAL;
+#ifndef GSB200_EMULATE
+    NcclApi *N; GSB_TRY(need_nccl(&N));
+    return nccl_check(N->GetUniqueId(id128), "ncclGetUniqueId");
+#else
+    memset(id128, 0, GSB200_COMM_ID_BYTES); return GSB200_OK;
+#endif
+}
+
+int gsb200_comm_init(gsb200_assembler *a, const void *id128)
+{
+    if (!a || !id128) return GSB200_EINVAL;
+#ifndef GSB200_EMULATE
+    GSB_TRY(select_device(a->device));
+    NcclApi *N; GSB_TRY(need_nccl(&N));
+    if (a->comm && a->comm_owned) N->CommDestroy(a->comm);
+    a->comm = 0; a->comm_owned = false;
+    ncclUniqueIdPod id; memcpy(&id, id128, sizeof id);
+    GSB_TRY(nccl_check(N->CommInitRank(&a->comm, a->nranks, id, a->rank), "ncclCommInitRank"));
+    a->comm_owned = true;
+    return GSB200_OK;
+#else
+    set_error("no NCCL in the interpreter build: use gsb200_set_allreduce"); return GSB200_EUNSUPPORTED;
+#endif
+}
+
+int gsb200_set_comm(gsb200_assembler *a, void *nccl_comm)
+{
+    if (!a) return GSB200_EINVAL;
+#ifndef GSB200_EMULATE
+    NcclApi *N; GSB_TRY(need_nccl(&N));
+    if (nccl_comm && N->CommCount && N->CommUserRank) {
+        int cnt = 0, rk = -1; N->CommCount(nccl_comm, &cnt); N->CommUserRank(nccl_comm, &rk);
+        if (cnt != a->nranks || rk != a->rank) { set_error("communicator has rank %d of %d, the problem says rank %d of %d", rk, cnt, a->rank, a->nranks); return GSB200_EINVAL; }
+    }
+    if (a->comm && a->comm_owned) N->CommDestroy(a->comm);
+    a->comm = nccl_comm; a->comm_owned = false;
+    return GSB200_OK;
+#else
+    (void)nccl_comm; set_error("no NCCL in the interpreter build: use gsb200_set_allreduce"); return GSB200_EUNSUPPORTED;
+#endif
+}
+
+int gsb200_set_allreduce(gsb200_assembler *a, gsb200_allreduce_fn fn, void *ctx)
+{
+    if (!a) return GSB200_EINVAL;
+    a->ar_fn = fn; a->ar_ctx = ctx; return GSB200_OK;
+}
+
+int gsb200_exchange(gsb200_assembler *a)
+{
+    if (!a) { set_error("null assembler"); return GSB200_EINVAL; }
+    if (!a->assembled) { set_error("gsb200_exchange before gsb200_assemble"); return GSB200_ESTATE; }
+    GSB_TRY(select_device(a->device));
+    return exchange(a);
+}
+
+int gsb200_comm_stats(const gsb200_assembler *a, int64_t *bytes_last, int32_t *calls)
+{
+    if (!a) return GSB200_EINVAL;
+    if (bytes_last) *bytes_last = a->xchg_bytes;
+    if (calls) *calls = a->xchg_calls;
+    return GSB200_OK;
+}
+
+int gsb200_spmv_device(gsb200_assembler *a, const double *x_dev, double *y_dev)
+{
+    if (!a || !x_dev || !y_dev) return GSB200_EINVAL;
+    if (!a->assembled) { set_error("spmv before assemble"); return GSB200_ESTATE; }
+    GSB_TRY(select_device(a->device));
+    return spmv_range(a, 0, a->nfree, x_dev, y_dev, 0, 0);
+}
+
+int gsb200_spmv_info(gsb200_assembler *a, int64_t *regular_columns, int32_t *tables)
+{
+    if (!a) return GSB200_EINVAL;
+    if (!a->pattern_built) { set_error("pattern not built"); return GSB200_ESTATE; }
+    GSB_TRY(select_device(a->device));
+    GSB_TRY(spmv_prepare(a));
+    if (regular_columns) {
+        std::vector<unsigned char> reg((size_t)a->nfree + 1);
+        GSB_TRY(dev_d2h(reg.data(), a->d_reg, (size_t)a->nfree, a->stream));
+        int64_t n = 0; for (int c = 0; c < a->nfree; ++c) if (reg[c]) ++n;
+        *regular_columns = n;
+    }
+    if (tables) *tables = a->reg_ntab;
+    return GSB200_OK;
+}
+
+int gsb200_diag_device(gsb200_assembler *a, double *d_dev)
+{
+    if (!a || !d_dev) return GSB200_EINVAL;
+    if (!a->assembled) { set_error("diag before assemble"); return GSB200_ESTATE; }
+    GSB_TRY(select_device(a->device));
+    const int n = a->nfree;
+    GSB_LAUNCH(k_diag, dim3((n + 127) / 128), dim3(128), a->stream, n, a->d_colptr, a->d_inner, a->d_values, d_dev);
+    return GSB200_OK;
+}
+
+int gsb200_spmv_host(gsb200_assembler *a, const double *x, double *y)
+{
+    if (!a || !x || !y) return GSB200_EINVAL;
+    if (!a->assembled) { set_error("spmv before assemble"); return GSB200_ESTATE; }
+    GSB_TRY(select_device(a->device));
+    const int n = a->nfree;
+    for (int k = 0; k < 2; ++k) if (!a->cgv[k]) GSB_TRY(dev_malloc((void **)&a->cgv[k], sizeof(double) * (size_t)(n + 8)));
+    GSB_TRY(dev_h2d(a->cgv[0], x, sizeof(double) * (size_t)n, a->stream));
+    GSB_TRY(dev_memset(a->cgv[1], 0, sizeof(double) * (size_t)n, a->stream));
+    GSB_TRY(spmv_range(a, 0, n, a->cgv[0], a->cgv[1], 0, 0));
+    return dev_d2h(y, a->cgv[1], sizeof(double) * (size_t)n, a->stream);
+}
+
+int gsb200_cg_solve(gsb200_assembler *a, const double *b_host, double *x_host, int max_iter, double tol, int check_every,
+                    int *iters, double *rel_residual)
+{
+    if (!a) return GSB200_EINVAL;
+    if (!a->assembled) { set_error("cg before assemble"); return GSB200_ESTATE; }
+    GSB_TRY(select_device(a->device));
+    const int n = a->nfree;
+    const double *b = a->d_rhs;
+    if (b_host) {
+        if (!a->cg_b) GSB_TRY(dev_malloc((void **)&a->cg_b, sizeof(double) * (size_t)(n + 1)));
+        GSB_TRY(dev_h2d(a->cg_b, b_host, sizeof(double) * (size_t)n, a->stream));
+        b = a->cg_b;
+    }
+    GSB_TRY(cg_solve(a, b, max_iter, tol, check_every, iters, rel_residual));
+    if (x_host) GSB_TRY(dev_d2h(x_host, a->cgv[0], sizeof(double) * (size_t)n, a->stream));
+    return GSB200_OK;
+}
+
+int gsb200_cg_host(gsb200_assembler *a, const double *b, double *x, int max_iter, double tol, int *iters, double *rel_residual)
+{
+    if (!b || !x) return GSB200_EINVAL;
+    return gsb200_cg_solve(a, b, x, max_iter, tol, 1, iters, rel_residual);
+}
+
+int gsb200_cg_solution_device(gsb200_assembler *a, const double **x_dev)
+{
+    if (!a || !x_dev) return GSB200_EINVAL;
+    if (!a->cgv[0]) { set_error("no CG solution yet"); return GSB200_ESTATE; }
+    *x_dev = a->cgv[0]; return GSB200_OK;
+}
+
+} // extern "C"

@@ -12,6 +12,7 @@
 
 #ifndef GSB200_EMULATE
 #include "jit.cuh"
+#include <dlfcn.h>
 #include <atomic>
 #include <memory>
 #include <mutex>
@@ -185,6 +186,7 @@ struct PatchDev {
 } // namespace gsb
 
 using namespace gsb;
+namespace gsb { void destroy_comm(void *comm); struct ncclUniqueIdPod { char internal[128]; }; }
 
 struct gsb200_assembler {
     int device = 0, dim = 0, form = 0, ncomp = 1, nfree = 0, nfixed = 0, nrhs = 1, rhs_kind = 0, rank = 0, nranks = 1;
@@ -215,8 +217,17 @@ struct gsb200_assembler {
 #endif
     int deliver_chunks = 1, plan_chunks = 1;      // chunks the last direction is cut into for streamed delivery (requested / planned)
     std::vector<int> chunk_cols; std::vector<i64> chunk_off;   // per chunk: first column / value offset that is NOT yet final behind it
-    // CG work vectors
-    double *cg[6] = {0, 0, 0, 0, 0, 0};
+    // ---- consumer side (consumer.cuh)
+    std::vector<int> patch_owner;               // rank that integrates each patch (several patches: greedy balance by element count)
+    std::vector<int> mid_dof;                   // per (patch, component): global DOF of a function in the middle of the owned part, -1 if none
+    std::vector<int> coupled_runs;              // [a, b) pairs: runs of columns with pre-images in more than one patch
+    std::vector<i64> coupled_off;               // their value offsets (after the pattern is built)
+    void *comm = 0; bool comm_owned = false;    // ncclComm_t
+    gsb200_allreduce_fn ar_fn = 0; void *ar_ctx = 0;
+    i64 xchg_bytes = 0; int xchg_calls = 0;
+    unsigned char *d_reg = 0; int *d_regoff = 0, *d_reglen = 0; int reg_ntab = 0, reg_stride = 1; bool spmv_ready = false;
+    int own_c0 = 0, own_c1 = 0, need_lo = 0, need_hi = 0; bool own_contig = true, cg_halo_mode = false;
+    double *cgv[8] = {0, 0, 0, 0, 0, 0, 0, 0}, *cg_b = 0;      // CG work vectors x r z p q d h + scalars; user rhs
     ~gsb200_assembler() {
         dev_sync(stream);                  // frees below are not ordered behind this stream's kernels
         for (auto &p : patches) p.release();
@@ -229,9 +240,11 @@ struct gsb200_assembler {
         for (int k = 0; k < 4; ++k) { if (stage[k]) cudaFreeHost(stage[k]); if (stage_ev[k]) cudaEventDestroy(stage_ev[k]); }
         for (auto e : chunk_ev) cudaEventDestroy(e);
 #endif
-        for (int k = 0; k < 6; ++k) dev_free(cg[k]);
+        for (int k = 0; k < 8; ++k) dev_free(cgv[k]);
+        dev_free(cg_b); dev_free(d_reg); dev_free(d_regoff); dev_free(d_reglen);
 #ifndef GSB200_EMULATE
         for (auto e : ev) cudaEventDestroy(e);
+        if (comm && comm_owned) gsb::destroy_comm(comm);
 #endif
     }
 };
@@ -362,7 +375,9 @@ static int build_pattern(gsb200_assembler *a)
     cudaEventRecord(e1, s); cudaEventSynchronize(e1); cudaEventElapsedTime(&a->tm.pattern_ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
 #endif
-    a->pattern_built = true; a->plan_valid = false;
+    a->coupled_off.clear();
+    for (int c : a->coupled_runs) { i64 off = 0; GSB_TRY(dev_d2h(&off, a->d_colptr + c, sizeof(i64), s)); a->coupled_off.push_back(off); }
+    a->pattern_built = true; a->plan_valid = false; a->spmv_ready = false;
     return 0;
 }
 
@@ -905,6 +920,8 @@ static int d2h_any(gsb200_assembler *a, void *dst, const void *src, size_t bytes
 
 } // namespace gsb
 
+#include "consumer.cuh"
+
 // ====================================================================== C ABI
 extern "C" {
 
@@ -990,10 +1007,10 @@ int gsb200_create(const gsb200_problem *pb, int device, gsb200_assembler **out)
         if ((rc = dev_malloc((void **)&P.d_colflag, (size_t)P.nb * pb->ncomp))) break;
         if ((rc = dev_memset(P.d_colflag, 0, (size_t)P.nb * pb->ncomp, a->stream))) break;
         if (pb->ncomp == 1) { if ((rc = dev_malloc((void **)&P.d_st, sizeof(unsigned) * (size_t)P.nb * P.nrun))) break; }
-        // ownership: one patch -> slabs along the last direction; several -> round robin by patch
+        // ownership: one patch -> slabs along the last direction; several -> whole patches, balanced by element count below
         const int nL = P.dir[L].nfun;
         if (pb->npatches == 1) { P.own_lo = (int)((i64)nL * pb->rank / pb->nranks); P.own_hi = (int)((i64)nL * (pb->rank + 1) / pb->nranks); }
-        else { P.own_lo = 0; P.own_hi = (ip % pb->nranks == pb->rank) ? nL : 0; }
+        else { P.own_lo = 0; P.own_hi = nL; }
         if (pb->npatches == 1 && pb->ncomp == 1) {     // streamed delivery: which columns are final behind a layer of the last direction
             const i64 per = P.nb / nL;
             P.sufmin.assign((size_t)nL + 1, pb->nfree);
@@ -1002,6 +1019,36 @@ int gsb200_create(const gsb200_problem *pb, int device, gsb200_assembler **out)
                 for (i64 i = (i64)x * per; i < (i64)(x + 1) * per; ++i) if (dm[i] < m) m = dm[i];     // eliminated DOFs are >= nfree
                 P.sufmin[x] = m;
             }
+        }
+    }
+    if (!rc) {
+        // several patches: longest-processing-time-first assignment (21 patches of yeti_mp2 over 8 GPUs), identical on every rank
+        const int np = pb->npatches;
+        a->patch_owner.assign(np, 0);
+        if (np > 1) {
+            std::vector<i64> cost(np); std::vector<int> order(np);
+            for (int ip = 0; ip < np; ++ip) { i64 c = 1; for (int k = 0; k < dim; ++k) c *= a->patches[ip].dir[k].nel * (a->patches[ip].dir[k].p + 1); cost[ip] = c; order[ip] = ip; }
+            std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost[x] > cost[y]; });
+            std::vector<i64> load(pb->nranks, 0);
+            for (int ip : order) { int best = 0; for (int r = 1; r < pb->nranks; ++r) if (load[r] < load[best]) best = r; a->patch_owner[ip] = best; load[best] += cost[ip]; }
+            for (int ip = 0; ip < np; ++ip) if (a->patch_owner[ip] != pb->rank) a->patches[ip].own_hi = 0;
+        }
+        // reference columns of the regular-stencil SpMV; runs of coupled columns (more than one pre-image over all patches)
+        std::vector<unsigned char> cnt((size_t)pb->nfree + 1, 0);
+        a->mid_dof.assign((size_t)np * pb->ncomp, -1);
+        for (int ip = 0; ip < np; ++ip) {
+            const PatchDev &P = a->patches[ip]; const int *dmp = pb->patches[ip].dofmap;
+            for (i64 i = 0; i < P.nb * pb->ncomp; ++i) { const int g = dmp[i]; if (g < pb->nfree && cnt[g] < 2) ++cnt[g]; }
+            if (P.own_hi > P.own_lo) {
+                i64 mid = 0, stride = 1;
+                for (int k = 0; k < dim; ++k) { const int n = P.dir[k].nfun; const int m = k == dim - 1 ? (P.own_lo + P.own_hi) / 2 : n / 2; mid += stride * m; stride *= n; }
+                for (int c = 0; c < pb->ncomp; ++c) { const int g = dmp[(i64)c * P.nb + mid]; a->mid_dof[(size_t)ip * pb->ncomp + c] = g < pb->nfree ? g : -1; }
+            }
+        }
+        if (np > 1) for (int g = 0; g < pb->nfree; ) {
+            if (cnt[g] < 2) { ++g; continue; }
+            int e = g; while (e < pb->nfree && cnt[e] >= 2) ++e;
+            a->coupled_runs.push_back(g); a->coupled_runs.push_back(e); g = e;
         }
     }
     if (!rc && pb->fixed) { std::vector<double> fx(pb->fixed, pb->fixed + (size_t)pb->nfixed * pb->nrhs); rc = upload(&a->d_fixed, fx, a->stream); }
@@ -1109,7 +1156,10 @@ int gsb200_device_view_get(const gsb200_assembler *a, gsb200_device_view *v)
 {
     if (!a || !v) return GSB200_EINVAL;
     if (!a->pattern_built) { set_error("pattern not built"); return GSB200_ESTATE; }
-    v->nnz = a->nnz; v->ncols = a->nfree; v->col_begin = 0; v->col_end = a->nfree;
+    gsb200_assembler *am = const_cast<gsb200_assembler *>(a);
+    GSB_TRY(select_device(a->device));
+    GSB_TRY(spmv_prepare(am));      // extent of the stored columns
+    v->nnz = a->nnz; v->ncols = a->nfree; v->col_begin = a->own_c0; v->col_end = a->own_c1;
     v->outer = (const int64_t *)a->d_colptr; v->inner = a->d_inner; v->values = a->d_values; v->rhs = a->d_rhs;
     return GSB200_OK;
 }
@@ -1273,96 +1323,6 @@ int gsb200_host_unpin(void *p)
 #else
     (void)p; return GSB200_OK;
 #endif
-}
-
-// ---------------------------------------------------------------- consumer: SpMV + Jacobi-CG
-static int launch_spmv(gsb200_assembler *a, const double *x, double *y)
-{
-    const int n = a->nfree;
-#ifndef GSB200_EMULATE
-    if (!dry_run()) { k_spmv_warp<<<148 * 8, 256, 0, a->stream>>>(n, a->d_colptr, a->d_inner, a->d_values, x, y); note_launch(); }
-#else
-    GSB_LAUNCH(k_spmv, dim3((n + 127) / 128), dim3(128), a->stream, n, a->d_colptr, a->d_inner, a->d_values, x, y);
-#endif
-    return 0;
-}
-
-static int cg_alloc(gsb200_assembler *a)
-{
-    for (int k = 0; k < 6; ++k) if (!a->cg[k]) GSB_TRY(dev_malloc((void **)&a->cg[k], sizeof(double) * (size_t)(a->nfree + 1)));
-    return 0;
-}
-
-int gsb200_spmv_device(gsb200_assembler *a, const double *x_dev, double *y_dev)
-{
-    if (!a || !x_dev || !y_dev) return GSB200_EINVAL;
-    if (!a->assembled) { set_error("spmv before assemble"); return GSB200_ESTATE; }
-    GSB_TRY(select_device(a->device));
-    return launch_spmv(a, x_dev, y_dev);
-}
-
-int gsb200_diag_device(gsb200_assembler *a, double *d_dev)
-{
-    if (!a || !d_dev) return GSB200_EINVAL;
-    if (!a->assembled) { set_error("diag before assemble"); return GSB200_ESTATE; }
-    GSB_TRY(select_device(a->device));
-    const int n = a->nfree;
-    GSB_LAUNCH(k_diag, dim3((n + 127) / 128), dim3(128), a->stream, n, a->d_colptr, a->d_inner, a->d_values, d_dev);
-    return GSB200_OK;
-}
-
-int gsb200_spmv_host(gsb200_assembler *a, const double *x, double *y)
-{
-    if (!a || !x || !y) return GSB200_EINVAL;
-    if (!a->assembled) { set_error("spmv before assemble"); return GSB200_ESTATE; }
-    GSB_TRY(select_device(a->device));
-    GSB_TRY(cg_alloc(a));
-    const int n = a->nfree;
-    GSB_TRY(dev_h2d(a->cg[0], x, sizeof(double) * (size_t)n, a->stream));
-    GSB_TRY(launch_spmv(a, a->cg[0], a->cg[1]));
-    return dev_d2h(y, a->cg[1], sizeof(double) * (size_t)n, a->stream);
-}
-
-static int dev_dot(gsb200_assembler *a, const double *u, const double *v, double *out)
-{
-    double *d = a->cg[5] + a->nfree;   // scalar slot after the vector
-    GSB_TRY(dev_memset(d, 0, sizeof(double), a->stream));
-    GSB_LAUNCH(k_dot, dim3(296), dim3(256), a->stream, a->nfree, u, v, d);
-    return dev_d2h(out, d, sizeof(double), a->stream);
-}
-
-int gsb200_cg_host(gsb200_assembler *a, const double *b, double *x, int max_iter, double tol, int *iters, double *rel_residual)
-{
-    if (!a || !b || !x) return GSB200_EINVAL;
-    if (!a->assembled) { set_error("cg before assemble"); return GSB200_ESTATE; }
-    GSB_TRY(select_device(a->device));
-    GSB_TRY(cg_alloc(a));
-    const int n = a->nfree; stream_t s = a->stream; const dim3 g((n + 127) / 128), t(128);
-    double *X = a->cg[0], *R = a->cg[1], *Z = a->cg[2], *Pv = a->cg[3], *Q = a->cg[4], *Dg = a->cg[5];
-    GSB_TRY(dev_memset(X, 0, sizeof(double) * (size_t)n, s));
-    GSB_TRY(dev_h2d(R, b, sizeof(double) * (size_t)n, s));
-    GSB_LAUNCH(k_diag, g, t, s, n, a->d_colptr, a->d_inner, a->d_values, Dg);
-    GSB_LAUNCH(k_div, g, t, s, n, R, Dg, Z);
-    GSB_TRY(dev_d2d(Pv, Z, sizeof(double) * (size_t)n, s));
-    double rz = 0, bb = 0, rr = 0;
-    GSB_TRY(dev_dot(a, R, Z, &rz)); GSB_TRY(dev_dot(a, R, R, &bb));
-    rr = bb; int it = 0;
-    const double thr = tol * tol * bb;
-    while (it < max_iter && rr > thr) {
-        GSB_TRY(launch_spmv(a, Pv, Q));
-        double pq = 0; GSB_TRY(dev_dot(a, Pv, Q, &pq));
-        const double alpha = rz / pq;
-        GSB_LAUNCH(k_axpy, g, t, s, n, X, alpha, Pv, X);
-        GSB_LAUNCH(k_axpy, g, t, s, n, R, -alpha, Q, R);
-        GSB_LAUNCH(k_div, g, t, s, n, R, Dg, Z);
-        double rz2 = 0; GSB_TRY(dev_dot(a, R, Z, &rz2)); GSB_TRY(dev_dot(a, R, R, &rr));
-        const double beta = rz2 / rz; rz = rz2;
-        GSB_LAUNCH(k_axpy, g, t, s, n, Z, beta, Pv, Pv);
-        ++it;
-    }
-    if (iters) *iters = it;
-    if (rel_residual) *rel_residual = bb > 0 ? sqrt(rr / bb) : 0.0;
-    return dev_d2h(x, X, sizeof(double) * (size_t)n, s);
 }
 
 int gsb200_jit_launches(const gsb200_assembler *a, int *count)

@@ -1,31 +1,54 @@
-"""Multi-GPU plumbing: one process per GPU, torch.distributed for the little that
-has to be exchanged.
+"""Multi-GPU plumbing: one process per GPU.  The data path is in the library (include/gsb200.h,
+csrc/consumer.cuh): it owns the NCCL communicator, sums the coupled interface columns and the right-hand side
+(gsb200_exchange, K4) and runs the CG consumer across the ranks (gsb200_cg_solve).  What is left here is the
+bootstrap a host transport has to do - ship the 128-byte NCCL id from rank 0 to the others - done with
+torch.distributed, and helpers for the tests (a gloo all-reduce for the GPU-less container, gluing the ranks'
+pieces together for verification).
 
-Row/column ownership means the data path needs no collective for a single patch (each rank
-assembles and keeps the CSC columns of its slab).  For multi-patch problems the columns of the
-coupled interface DOFs — the contiguous tail block of the numbering (gsDofMapper.cpp:281-323) —
-receive contributions from every rank that owns an adjacent patch: they are patterned identically
-on all ranks and their value block (and the rhs) is summed with one all_reduce.
+Row/column ownership means the data path needs no collective for a single patch (each rank assembles and keeps
+the CSC columns of its slab).  For multi-patch problems the columns of the coupled interface DOFs — the tail
+block(s) of the numbering (gsDofMapper.cpp:281-323) — receive contributions from every rank that owns an
+adjacent patch: they are patterned identically on all ranks and their value blocks are summed.
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import Optional, Tuple
 
 import numpy as np
 import torch
 import torch.distributed as dist
 
-from .capi import Problem
+from . import capi
+from .capi import Problem, check
 
 
-def first_coupled_column(problem: Problem) -> int:
-    """Global index of the first free DOF shared by more than one (patch, local) pre-image."""
-    counts = np.zeros(problem.nfree, dtype=np.int32)
-    for p in problem.patches:
-        g = p.dofmap[p.dofmap < problem.nfree]
-        np.add.at(counts, g, 1)
-    multi = np.nonzero(counts > 1)[0]
-    return int(multi[0]) if len(multi) else problem.nfree
+def init_comm(assembler, group: Optional[dist.ProcessGroup] = None) -> None:
+    """Give `assembler` (created with problem.rank / problem.nranks = this process's rank / world size) its NCCL
+    communicator: rank 0 draws the id (gsb200_comm_unique_id), torch.distributed ships it, every rank joins
+    (gsb200_comm_init).  Collective."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return
+    box = [None]
+    if dist.get_rank(group) == 0:
+        buf = C.create_string_buffer(capi.COMM_ID_BYTES)
+        check(assembler.lib.gsb200_comm_unique_id(buf))
+        box[0] = bytes(buf.raw)
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    assembler.comm_init(box[0])
+
+
+def use_torch_allreduce(assembler, group: Optional[dist.ProcessGroup] = None, device: Optional[int] = None) -> None:
+    """Route the library's reductions through torch.distributed (gsb200_set_allreduce): the buffer the library hands over
+    is aliased as a tensor - host memory for the interpreter build of the tests (gloo), device memory otherwise."""
+    def allreduce(addr: int, count: int, stream) -> None:
+        if device is None:
+            t = torch.from_numpy(np.ctypeslib.as_array(C.cast(addr, C.POINTER(C.c_double)), shape=(count,)))
+        else:
+            t = device_tensor(addr, count, torch.float64, device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    assembler.set_allreduce(allreduce)
 
 
 class _CudaView:
@@ -40,9 +63,16 @@ def device_tensor(ptr: int, n: int, dtype: torch.dtype, device: int) -> torch.Te
     return torch.as_tensor(_CudaView(ptr, n, typestr), device=torch.device("cuda", device))
 
 
+def first_coupled_column(problem: Problem) -> int:
+    """Global index of the first free DOF shared by more than one (patch, local) pre-image."""
+    runs = coupled_column_ranges(problem)
+    return runs[0][0] if runs else problem.nfree
+
+
 def coupled_column_ranges(problem: Problem):
     """Contiguous runs [a, b) of global columns shared by more than one (patch, local) pre-image: one tail run for a scalar
-    space, one per component block for a vector-valued one (component-major numbering, gsDofMapper.cpp:255-265)."""
+    space, one per component block for a vector-valued one (component-major numbering, gsDofMapper.cpp:255-265).  The
+    library derives the same runs for gsb200_exchange; this copy serves the verification helpers."""
     counts = np.zeros(problem.nfree + 1, dtype=np.int32)
     for p in problem.patches:
         g = p.dofmap[p.dofmap < problem.nfree]
@@ -52,22 +82,21 @@ def coupled_column_ranges(problem: Problem):
     return [(int(edges[k]), int(edges[k + 1])) for k in range(0, len(edges), 2)]
 
 
-def reduce_coupled_columns(values: torch.Tensor, rhs: torch.Tensor, outer: np.ndarray, c0,
-                           group: Optional[dist.ProcessGroup] = None) -> None:
-    """In place: sum the value blocks of the coupled columns (c0 = first coupled column of a scalar space, or the list of
-    runs from coupled_column_ranges) and the whole rhs over all ranks."""
-    n = len(outer) - 1
-    runs = [(int(c0), n)] if np.isscalar(c0) else list(c0)
-    if dist.is_initialized() and dist.get_world_size(group) > 1:
-        for a, b in runs:
-            if a < b and int(outer[b]) > int(outer[a]):
-                block = values[int(outer[a]):int(outer[b])]
-                dist.all_reduce(block, op=dist.ReduceOp.SUM, group=group)
-        dist.all_reduce(rhs, op=dist.ReduceOp.SUM, group=group)
+def patch_owners(costs, nranks: int):
+    """The library's patch -> rank assignment (gsb200_create): longest processing time first onto the least loaded rank."""
+    order = sorted(range(len(costs)), key=lambda i: -costs[i])        # stable, like std::stable_sort
+    load = [0] * nranks
+    owner = [0] * len(costs)
+    for i in order:
+        r = min(range(nranks), key=lambda k: (load[k], k))
+        owner[i] = r
+        load[r] += costs[i]
+    return owner
 
 
-def merge_rank_matrices(parts, c0: int, n: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
-    """Verification helper: glue per-rank CSC pieces (owned columns + reduced coupled block) into one CSC."""
+def merge_rank_matrices(parts, n: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Verification helper: glue per-rank CSC pieces (owned columns + exchanged coupled columns, which every rank holds)
+    into one CSC: each column is taken from the first rank that stores it."""
     lens = np.zeros(n, dtype=np.int64)
     for outer, _, _ in parts:
         ln = np.diff(outer.astype(np.int64))
@@ -85,57 +114,3 @@ def merge_rank_matrices(parts, c0: int, n: int) -> Tuple[np.ndarray, np.ndarray,
             values[new_outer[c]:new_outer[c + 1]] = val[a:b]
             done[c] = True
     return new_outer.astype(np.int32), inner, values
-
-
-class DistributedCG:
-    """Jacobi-preconditioned CG on the device-resident, column-partitioned matrix (mirrors
-    gsSparseSolver<>::CGDiagonal, gsSparseSolver.h:71-72).  Every rank keeps full-length vectors; the matrix product is the
-    library's warp-per-row SpMV over the columns the rank owns (gsb200_spmv_device) followed by ONE all_reduce of y, dot products
-    are local (replicated vectors).  world_size 1 works without a process group."""
-
-    def __init__(self, assembler, device: int, group: Optional[dist.ProcessGroup] = None, reduced: bool = True):
-        """reduced: the coupled columns (multi-patch) already hold the all-reduced values on every rank that stores them
-        (reduce_coupled_columns was called); irrelevant for single-patch slabs."""
-        self.A, self.device, self.group = assembler, device, group
-        self.n = assembler.problem.nfree
-        self.multi = dist.is_initialized() and dist.get_world_size(group) > 1
-        from .capi import check
-        v = assembler.device_view()
-        outer = device_tensor(v.outer, self.n + 1, torch.int64, device)
-        stored = (outer[1:] - outer[:-1]) > 0
-        # diagonal of the columns this rank stores (library kernel: no nnz-sized temporaries), summed over the ranks; coupled
-        # columns hold the full sums on every rank that patterns them after the exchange: divide by the number of holders
-        diag = torch.empty(self.n, dtype=torch.float64, device=outer.device)
-        check(assembler.lib.gsb200_diag_device(assembler._h, diag.data_ptr()))
-        diag = torch.where(stored, diag, torch.zeros_like(diag))
-        holders = stored.to(torch.float64)
-        if self.multi:
-            dist.all_reduce(diag, group=group); dist.all_reduce(holders, group=group)
-        self.holders = torch.clamp(holders, min=1.0) if reduced else torch.ones_like(holders)
-        self.diag = diag / self.holders
-        self.diag = torch.where(self.diag == 0, torch.ones_like(self.diag), self.diag)
-
-    def matvec(self, x: torch.Tensor) -> torch.Tensor:
-        from .capi import check
-        y = torch.empty_like(x)
-        check(self.A.lib.gsb200_spmv_device(self.A._h, x.data_ptr(), y.data_ptr()))
-        if self.multi:
-            y /= self.holders                     # columns patterned on several ranks carry the same (already reduced) values
-            dist.all_reduce(y, group=self.group)
-        return y
-
-    def solve(self, b: torch.Tensor, max_iter: int = 1000, tol: float = 1e-10):
-        x = torch.zeros_like(b); r = b.clone(); z = r / self.diag; p = z.clone()
-        rz = torch.dot(r, z); bb = torch.dot(b, b); it = 0
-        while it < max_iter:
-            q = self.matvec(p)
-            alpha = rz / torch.dot(p, q)
-            x += alpha * p; r -= alpha * q
-            rr = torch.dot(r, r)
-            it += 1
-            if float(rr) <= tol * tol * float(bb):
-                break
-            z = r / self.diag
-            rz2 = torch.dot(r, z)
-            p = z + (rz2 / rz) * p; rz = rz2
-        return x, it, float(torch.sqrt(torch.dot(r, r) / bb))

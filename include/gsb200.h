@@ -142,7 +142,8 @@ typedef struct gsb200_assembler gsb200_assembler; /* opaque device-side state */
 typedef struct gsb200_device_view {
     int64_t nnz;
     int32_t ncols;           /* = nfree                                       */
-    int32_t col_begin, col_end; /* columns owned by this rank                 */
+    int32_t col_begin, col_end; /* smallest range holding the columns this rank stores (its slab; with several
+                                   patches: from its first to its last stored column, others in between are empty) */
     const int64_t *outer;    /* device, ncols+1                               */
     const int32_t *inner;    /* device, nnz                                   */
     const double *values;    /* device, nnz                                   */
@@ -226,6 +227,30 @@ int gsb200_host_unpin(void *p);
 int gsb200_assemble_host(const gsb200_problem *problem, int device, int64_t *nnz,
                          int32_t *outer, int32_t *inner, double *values, double *rhs);
 
+/* ---- Multi-GPU: one rank per GPU, problem.rank / problem.nranks say which share this assembler integrates.
+   A single patch is cut into slabs of matrix columns along the last direction (no exchange needed for the matrix); several
+   patches are distributed whole (longest first onto the least loaded rank), and the columns of DOFs shared by patches of
+   different ranks - patterned identically on every rank - are summed by gsb200_exchange together with the right-hand side.
+   The reference has no distributed assembly (gsExprAssembler.h:661 "mpi assemly. ???"); its transport wrappers are
+   gsMpiComm.h.  The library speaks NCCL itself (loaded at run time, no link dependency):
+     rank 0:      gsb200_comm_unique_id(id)  -> ship the 128 bytes with the host transport at hand (MPI_Bcast, a file, ...)
+     every rank:  gsb200_comm_init(a, id)       (collective: ncclCommInitRank on the assembler's device)
+   or adopts a communicator the application already has (gsb200_set_comm, ncclComm_t; not owned), or - CUDA-aware MPI, tests -
+   calls back for an in-place sum of doubles over the ranks (gsb200_set_allreduce; `buf` is device memory, `stream` the
+   cudaStream_t the data is ordered on). */
+#define GSB200_COMM_ID_BYTES 128
+typedef int (*gsb200_allreduce_fn)(void *ctx, double *buf, int64_t count, void *stream);
+int gsb200_comm_unique_id(void *id128);
+int gsb200_comm_init(gsb200_assembler *a, const void *id128);
+int gsb200_set_comm(gsb200_assembler *a, void *nccl_comm);
+int gsb200_set_allreduce(gsb200_assembler *a, gsb200_allreduce_fn fn, void *ctx);
+/* K4, after gsb200_assemble: one grouped collective on the assembler's stream - an all-reduce per run of coupled columns,
+   straight on the value array the final sweep wrote, plus the right-hand side (afterwards every rank holds the full rhs and
+   the full sums of the coupled columns).  A no-op for nranks == 1. */
+int gsb200_exchange(gsb200_assembler *a);
+/* Bytes this rank contributed to the last gsb200_exchange / gsb200_cg_solve, and the number of exchanges so far. */
+int gsb200_comm_stats(const gsb200_assembler *a, int64_t *bytes_last, int32_t *calls);
+
 /* Consumer: y = A x on the device-resident matrix, and a Jacobi-
    preconditioned CG mirroring gsSparseSolver<>::CGDiagonal (gsSparseSolver.h:71-72).
    x/y/b are host pointers of length nfree. */
@@ -239,6 +264,16 @@ int gsb200_spmv_device(gsb200_assembler *a, const double *x_dev, double *y_dev);
 int gsb200_diag_device(gsb200_assembler *a, double *d_dev);
 int gsb200_cg_host(gsb200_assembler *a, const double *b, double *x, int max_iter,
                    double tol, int *iters, double *rel_residual);
+/* The same solver across the ranks of the communicator, all scalars on the device (the host looks at the residual every
+   `check_every` iterations).  b_host == NULL: the assembled right-hand side (column 0; exchanged, for nranks > 1);
+   x_host may be NULL (gsb200_cg_solution_device).  Column slabs of one patch: every rank iterates on its own slab and
+   trades only the rows its columns reach into the neighbours' slabs (ncclSend/ncclRecv), two scalar reductions per
+   iteration; patch-wise ownership: full-length reduction of the product.  Every rank ends with the whole solution. */
+int gsb200_cg_solve(gsb200_assembler *a, const double *b_host, double *x_host, int max_iter, double tol, int check_every,
+                    int *iters, double *rel_residual);
+int gsb200_cg_solution_device(gsb200_assembler *a, const double **x_dev);
+/* Columns whose row set is a translate of a reference stencil (the SpMV reads 8 instead of 12 bytes per entry there). */
+int gsb200_spmv_info(gsb200_assembler *a, int64_t *regular_columns, int32_t *tables);
 
 /* Compile an exprtk-style source term ("2*pi^2*sin(pi*x)*sin(pi*y)") into a
    reverse-polish program.  Buffers are caller-allocated; on success *nops/*nconsts

@@ -1,5 +1,5 @@
 """N>1 path on CPU: world_size-2 gloo process groups exercising the partition + exchange logic of
-gismo_b200/distributed.py.  Per-rank assembly runs through the kernel interpreter (tests/emul, test
+the library's exchange (gsb200_exchange, gsb200_cg_solve; the reduction goes through gsb200_set_allreduce -> gloo).  Per-rank assembly runs through the kernel interpreter (tests/emul, test
 harness) because this container has no GPU; on the B200 box the same code path runs with nccl
 (bench.py --gpus N, tests/test_gpu_parity.py::test_rank_slabs_cover_the_matrix)."""
 import os
@@ -26,23 +26,34 @@ def _worker(rank, world, port, name, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import goldenutil as G
     import refutil as R
+    import gismo_b200 as g
     from gismo_b200 import distributed as D
     pb, z = G.load(name, R.emul_compile)
-    pb.struct.rank, pb.struct.nranks = rank, world
-    o, i, v, b, _ = R.lib_assemble(R.emul_lib(), pb)
-    c0 = D.first_coupled_column(pb)
-    vt, bt = torch.from_numpy(v), torch.from_numpy(np.ascontiguousarray(b[:, 0]))
-    D.reduce_coupled_columns(vt, bt, o, c0)
-    # gather every rank's piece on rank 0 and verify against the reference fixture
+    pb = pb.with_fixed(pb.fixed, rank=rank, nranks=world)
+    A = g.DeviceAssembler(pb, lib=R.emul_lib())
+    D.use_torch_allreduce(A)                 # gsb200_set_allreduce: the library's K4 exchange over gloo
+    A.assemble()
+    A.exchange()                             # coupled columns + right-hand side
+    o, i, v = A.matrix()
+    b = A.rhs()
+    nbytes, ncalls = A.comm_stats()
+    # the CG consumer across the ranks (patch-wise ownership or slabs over the callback: full-length reduction of the product)
+    x, it, res = A.cg_solve(max_iter=400, tol=1e-10, check_every=5)
     pieces = [None] * world
-    dist.all_gather_object(pieces, (o, i, vt.numpy()))
+    dist.all_gather_object(pieces, (o, i, v))
     if rank == 0:
-        outer, inner, values = D.merge_rank_matrices(pieces, c0, pb.nfree)
+        outer, inner, values = D.merge_rank_matrices(pieces, pb.nfree)
         try:
-            G.check_against((outer, inner, values, bt.numpy()[:, None]), z, 1e-12)
+            G.check_against((outer, inner, values, b), z, 1e-12)
+            assert ncalls == 1 and nbytes >= 8 * pb.nfree
+            import scipy.sparse as sp
+            K = sp.csc_matrix((values, inner, outer), shape=(pb.nfree, pb.nfree))
+            r = K @ x - b[:, 0]
+            assert res <= 1e-10 and np.linalg.norm(r) <= 1e-8 * np.linalg.norm(b[:, 0]), (it, res, np.linalg.norm(r))
             out.put("ok")
         except AssertionError as e:
             out.put("FAIL " + str(e))
+    A.close()
     dist.destroy_process_group()
 
 

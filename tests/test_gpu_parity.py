@@ -176,7 +176,55 @@ def test_consumer_spmv_and_cg(lib):
     assert np.abs(u - uref).max() <= 1e-8 * np.abs(uref).max()
     # manufactured solution u = sin(pi x) sin(pi y) sin(pi z) on the cube centred at 0 -> cos products; just sanity
     assert np.all(np.isfinite(u))
+    nreg, ntab = A.spmv_info()
+    nf = round(pb.nfree ** (1 / 3))
+    assert ntab == 1 and nreg == (nf - 6) ** 3                # interior columns of the cube take the 8-byte path
+    v = A.device_view()
+    assert (v.col_begin, v.col_end) == (0, pb.nfree)
     A.close()
+
+
+@pytest.mark.parametrize("name", ["grid2x2_p2_m4", "elasticity_2cubes_p2", "yeti_mp2_p2_m2", "annulus_nurbs_p3_m6"])
+def test_spmv_regular_and_general_columns(lib, name):
+    """y = K x against scipy on multi-patch / vector-valued / NURBS fixtures: columns matching a reference stencil read no
+    row indices, all others do; same product."""
+    pb, z = G.load(name, g.expr_compile)
+    A = g.DeviceAssembler(pb)
+    A.assemble()
+    K = A.scipy_matrix()
+    x = G.probe_vector(pb.nfree)
+    y = A.spmv(x)
+    assert np.abs(y - K @ x).max() <= 1e-12 * np.abs(y).max()
+    nreg, ntab = A.spmv_info()
+    assert 0 <= nreg <= pb.nfree and ntab >= 1
+    b = A.rhs()[:, 0]
+    if pb.nfixed > 0 and np.linalg.norm(b) > 0:          # (a pure Neumann problem is singular)
+        u, iters, res = A.cg_solve(b, max_iter=5000, tol=1e-11, check_every=7)
+        assert res <= 1e-11
+        assert np.linalg.norm(K @ u - b) <= 1e-9 * np.linalg.norm(b)
+    A.close()
+
+
+def _torchrun(nproc, script, *args, timeout=600):
+    import subprocess, sys, socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), script, *args]
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+
+
+@pytest.mark.parametrize("nproc", [2, 4])
+def test_nccl_exchange_and_distributed_cg(lib, nproc):
+    """N ranks, one per GPU, the library's own NCCL communicator: patch-wise ownership with the coupled-column exchange
+    (grid2x2, yeti_mp2, 8 cubes, elasticity) and column slabs with the neighbour-halo CG (single patches) against the reference
+    fixtures.  Needs N GPUs on the box (tests/nccl_worker.py)."""
+    n = C.c_int(0); lib.gsb200_device_count(C.byref(n))
+    if n.value < nproc:
+        pytest.skip(f"{nproc} GPUs needed, {n.value} visible")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = _torchrun(nproc, os.path.join(here, "nccl_worker.py"), "grid2x2_p2_m4", "yeti_mp2_p2_m2", "grid2x2x2_p2_m3", "elasticity_2cubes_p2",
+                  "cube_p3_m16", "cube_p3_curved_m4")
+    assert r.returncode == 0 and "NCCLWORKER ok" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 
 def test_compiled_source_term_equals_interpreter(lib):
