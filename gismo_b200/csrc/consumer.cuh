@@ -182,11 +182,13 @@ GSB_DEVICE void cg_block_add(double s, double *out)
 }
 // scalars S (device): [0] rz  [1] pq  [2] rz_new  [3] rr  [4] bb
 // r = b, z = r / d, p = z on [c0, c1); rz += r.z, bb += b.b
-GSB_GLOBAL void k_cg_start(int c0, int c1, const double *b, const double *d, double *x, double *r, double *z, double *p, double *S)
+// (the dot products take the entries [d0, d1) only: ranks that keep whole vectors split the index range between them, so that the
+// reduced scalars - and with them every rank's iterates - are bitwise the same everywhere)
+GSB_GLOBAL void k_cg_start(int c0, int c1, int d0, int d1, const double *b, const double *d, double *x, double *r, double *z, double *p, double *S)
 {
     const int i = c0 + blockIdx.x * blockDim.x + threadIdx.x;
     double s0 = 0.0, s1 = 0.0;
-    if (i < c1) { const double bi = b[i]; const double zi = bi / d[i]; x[i] = 0.0; r[i] = bi; z[i] = zi; p[i] = zi; s0 = bi * zi; s1 = bi * bi; }
+    if (i < c1) { const double bi = b[i]; const double zi = bi / d[i]; x[i] = 0.0; r[i] = bi; z[i] = zi; p[i] = zi; if (i >= d0 && i < d1) { s0 = bi * zi; s1 = bi * bi; } }
     cg_block_add(s0, S + 0); cg_block_add(s1, S + 4);
 }
 GSB_GLOBAL void k_cg_dot(int c0, int c1, const double *u, const double *v, double *out)
@@ -195,7 +197,7 @@ GSB_GLOBAL void k_cg_dot(int c0, int c1, const double *u, const double *v, doubl
     cg_block_add(i < c1 ? u[i] * v[i] : 0.0, out);
 }
 // alpha = rz / pq;  x += alpha p;  r -= alpha q;  z = r / d;  rz_new += r.z;  rr += r.r
-GSB_GLOBAL void k_cg_step1(int c0, int c1, const double *p, const double *q, const double *d, double *x, double *r, double *z, double *S)
+GSB_GLOBAL void k_cg_step1(int c0, int c1, int d0, int d1, const double *p, const double *q, const double *d, double *x, double *r, double *z, double *S)
 {
     const int i = c0 + blockIdx.x * blockDim.x + threadIdx.x;
     const double alpha = S[0] / S[1];
@@ -203,7 +205,7 @@ GSB_GLOBAL void k_cg_step1(int c0, int c1, const double *p, const double *q, con
     if (i < c1) {
         x[i] = fma(alpha, p[i], x[i]);
         const double ri = fma(-alpha, q[i], r[i]); const double zi = ri / d[i];
-        r[i] = ri; z[i] = zi; s0 = ri * zi; s1 = ri * ri;
+        r[i] = ri; z[i] = zi; if (i >= d0 && i < d1) { s0 = ri * zi; s1 = ri * ri; }
     }
     cg_block_add(s0, S + 2); cg_block_add(s1, S + 3);
 }
@@ -362,14 +364,17 @@ static int cg_solve(gsb200_assembler *a, const double *b_dev, int max_iter, doub
     const dim3 gN((N + 127) / 128), t(128);
     const int c0 = P.c0, c1 = P.c1; const dim3 gO((std::max(c1 - c0, 1) + 127) / 128);
     const bool multi = a->nranks > 1;
+    const bool rep = multi && !P.halo;          // whole vectors on every rank: the dot products are split by index range and reduced
+    const int d0 = rep ? (int)((i64)N * a->rank / a->nranks) : c0, d1 = rep ? (int)((i64)N * (a->rank + 1) / a->nranks) : c1;
+    const dim3 gD((std::max(d1 - d0, 1) + 127) / 128);
     // preconditioner: diagonal of the stored columns; columns stored by several ranks (coupled, already exchanged) count once
     GSB_LAUNCH(k_cg_diag, gN, t, s, N, a->d_colptr, a->d_inner, a->d_values, Dg, H);
     if (multi && !P.halo) { GSB_TRY(comm_allreduce(a, Dg, N)); GSB_TRY(comm_allreduce(a, H, N)); }
     GSB_LAUNCH(k_cg_prep, gN, t, s, N, Dg, H);
     GSB_TRY(dev_memset(S, 0, 8 * sizeof(double), s));
     if (multi && !P.halo) { GSB_TRY(dev_memset(X, 0, sizeof(double) * (size_t)N, s)); }
-    GSB_LAUNCH(k_cg_start, gO, t, s, c0, c1, b_dev, Dg, X, R, Z, Pv, S);
-    if (P.halo) GSB_TRY(comm_allreduce(a, S, 8));
+    GSB_LAUNCH(k_cg_start, gO, t, s, c0, c1, d0, d1, b_dev, Dg, X, R, Z, Pv, S);
+    if (multi) GSB_TRY(comm_allreduce(a, S, 8));
     double hs[8]; GSB_TRY(dev_d2h(hs, S, sizeof hs, s));
     const double bb = hs[4]; double rr = bb;
     const double thr = tol * tol * bb;
@@ -388,10 +393,11 @@ static int cg_solve(gsb200_assembler *a, const double *b_dev, int max_iter, doub
                 // patch-wise ownership: every rank multiplies the columns it stores (shared ones weighted 1/holders), the products add up
                 GSB_TRY(spmv_range(a, 0, N, Pv, Q, H, 0));
                 GSB_TRY(comm_allreduce(a, Q, N)); a->xchg_bytes += 8 * (i64)N;
-                GSB_LAUNCH(k_cg_dot, gN, t, s, 0, N, Pv, Q, S + 1);
+                GSB_LAUNCH(k_cg_dot, gD, t, s, d0, d1, Pv, Q, S + 1);
+                GSB_TRY(comm_allreduce(a, S + 1, 1));
             }
-            GSB_LAUNCH(k_cg_step1, gO, t, s, c0, c1, Pv, Q, Dg, X, R, Z, S);
-            if (P.halo) GSB_TRY(comm_allreduce(a, S + 2, 2));
+            GSB_LAUNCH(k_cg_step1, gO, t, s, c0, c1, d0, d1, Pv, Q, Dg, X, R, Z, S);
+            if (multi) GSB_TRY(comm_allreduce(a, S + 2, 2));
             GSB_LAUNCH(k_cg_step2, gO, t, s, c0, c1, Z, Pv, S);
             GSB_LAUNCH(k_cg_rotate, dim3(1), dim3(32), s, S);
             ++it;

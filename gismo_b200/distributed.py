@@ -45,9 +45,12 @@ def use_torch_allreduce(assembler, group: Optional[dist.ProcessGroup] = None, de
     def allreduce(addr: int, count: int, stream) -> None:
         if device is None:
             t = torch.from_numpy(np.ctypeslib.as_array(C.cast(addr, C.POINTER(C.c_double)), shape=(count,)))
-        else:
+        else:                                   # the library's kernels run on its own stream: order the two by hand
+            torch.cuda.synchronize(device)
             t = device_tensor(addr, count, torch.float64, device)
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        if device is not None:
+            torch.cuda.synchronize(device)
     assembler.set_allreduce(allreduce)
 
 
