@@ -122,6 +122,9 @@ class DeviceAssembler:
         self._check(self.lib.gsb200_download_rhs(self._h, r.ctypes.data_as(_dp)))
         return r
 
+    def rhs_into(self, rhs: np.ndarray) -> None:
+        self._check(self.lib.gsb200_download_rhs(self._h, rhs.ctypes.data_as(_dp)))
+
     def scipy_matrix(self):
         import scipy.sparse as sp
         o, i, v = self.matrix()

@@ -284,3 +284,115 @@ def multipatch_grid_problem(dim: int, degree: int, grid: Sequence[int], nelem: i
         patches.append(PatchData([degree] * dim, [kv.knots for kv in skv], [kv.degree for kv in gkv], [kv.knots for kv in gkv], C, dm))
     return Problem(patches, nfree, nfixed, form=form, ncomp=ncomp, coef=tuple(coef) + (0.0,) * (4 - len(coef)),
                    rhs_programs=rhs_programs, rank=rank, nranks=nranks)
+
+
+def _side_locals(nfun: Sequence[int], side: int) -> np.ndarray:
+    """Local indices of the functions on side 1..4 of a 2-D patch (gsBoundary.h:58-60: west, east, south, north),
+    ordered by the running index of the other direction."""
+    n0, n1 = int(nfun[0]), int(nfun[1])
+    if side == 1:
+        return np.arange(n1) * n0
+    if side == 2:
+        return np.arange(n1) * n0 + (n0 - 1)
+    if side == 3:
+        return np.arange(n0)
+    return np.arange(n0) + (n1 - 1) * n0
+
+
+def multipatch_topology_2d(problem: Problem):
+    """Interfaces and Dirichlet sides of a flattened 2-D multi-patch discretisation, read off its DOF map: two patch sides
+    that carry the same global indices are glued (gsBoxTopology interface; reversed order = flipped orientation), a side
+    whose functions are all eliminated and glued to nobody is a Dirichlet side.  This is how the topology of a reference
+    geometry (filedata/domain2d/yeti_mp2.xml, read by the reference when the fixture was made) reaches the GPU box, where
+    the reference's XML reader does not exist."""
+    sides = {}
+    for ip, pa in enumerate(problem.patches):
+        nfun = [len(pa.space_knots[k]) - pa.space_degree[k] - 1 for k in range(2)]
+        for s in (1, 2, 3, 4):
+            sides[(ip, s)] = pa.dofmap[_side_locals(nfun, s)]
+    interfaces, glued = [], set()
+    keys = sorted(sides)
+    for a in range(len(keys)):
+        for b in range(a + 1, len(keys)):
+            ka, kb = keys[a], keys[b]
+            if ka[0] == kb[0] or len(sides[ka]) != len(sides[kb]):
+                continue
+            if np.array_equal(sides[ka], sides[kb]):
+                interfaces.append((ka[0], ka[1], kb[0], kb[1], False)); glued.update((ka, kb))
+            elif np.array_equal(sides[ka], sides[kb][::-1]):
+                interfaces.append((ka[0], ka[1], kb[0], kb[1], True)); glued.update((ka, kb))
+    dirichlet = [k for k in keys if k not in glued and np.all(sides[k] >= problem.nfree)]
+    return interfaces, dirichlet
+
+
+def refine_multipatch_2d(problem: Problem, degree: int, nelem: int, rhs_programs=None, rank: int = 0, nranks: int = 1) -> Problem:
+    """The discretisation the reference builds from the same geometry with setDegree(degree) + uniformRefine(nelem - 1)
+    (oracle/ref_driver.cpp geometry 4), at any refinement: knots from the patches' geometry bases, interfaces and Dirichlet
+    sides from multipatch_topology_2d(problem), numbering of gsDofMapper (gsDofMapper.cpp:240-344: standard free DOFs in
+    patch-then-local order, coupled ones by first appearance, eliminated ones last).  Scalar spaces."""
+    assert problem.dim == 2 and problem.ncomp == 1
+    interfaces, dirichlet = multipatch_topology_2d(problem)
+    skvs, nfuns = [], []
+    for pa in problem.patches:
+        kvs = []
+        for k in range(2):
+            kv = KnotVector(pa.geo_degree[k], pa.geo_knots[k])
+            kv.setDegree(degree)
+            if nelem > 1:
+                kv.uniformRefine(nelem - 1)
+            kvs.append(kv)
+        skvs.append(kvs); nfuns.append([kv.size for kv in kvs])
+    sizes = [n[0] * n[1] for n in nfuns]
+    offset = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    total = int(offset[-1])
+    parent = np.arange(total, dtype=np.int64)
+
+    def find(i):
+        r = i
+        while parent[r] != r:
+            r = parent[r]
+        while parent[i] != r:
+            parent[i], i = r, parent[i]
+        return r
+    for pa_, sa, pb_, sb, flip in interfaces:
+        la = offset[pa_] + _side_locals(nfuns[pa_], sa)
+        lb = offset[pb_] + _side_locals(nfuns[pb_], sb)
+        assert len(la) == len(lb), "non-conforming interface"
+        if flip:
+            lb = lb[::-1]
+        for x, y in zip(la.tolist(), lb.tolist()):
+            rx, ry = find(x), find(y)
+            if rx != ry:
+                parent[max(rx, ry)] = min(rx, ry)
+    node = np.arange(total, dtype=np.int64)            # only functions on glued sides can have another root
+    for pa_, sa, pb_, sb, _ in interfaces:
+        for ip, s in ((pa_, sa), (pb_, sb)):
+            for x in (offset[ip] + _side_locals(nfuns[ip], s)).tolist():
+                node[x] = find(x)
+    elim_node = np.zeros(total, dtype=bool)
+    for ip, s in dirichlet:
+        elim_node[node[offset[ip] + _side_locals(nfuns[ip], s)]] = True
+    elim = elim_node[node]
+    multi = np.bincount(node, minlength=total)[node] > 1
+    std, cpl = ~elim & ~multi, ~elim & multi
+    index = np.zeros(total, dtype=np.int64)
+    nstd = int(std.sum())
+    index[std] = np.arange(nstd)
+
+    def first_appearance_rank(sel):
+        ids, first_pos, inv = np.unique(node[sel], return_index=True, return_inverse=True)
+        order = np.argsort(first_pos, kind="stable")
+        rk = np.empty(len(ids), dtype=np.int64); rk[order] = np.arange(len(ids))
+        return rk[inv], len(ids)
+    ncpl = nelim = 0
+    if cpl.any():
+        r, ncpl = first_appearance_rank(cpl); index[cpl] = nstd + r
+    nfree = nstd + ncpl
+    if elim.any():
+        r, nelim = first_appearance_rank(elim); index[elim] = nfree + r
+    patches = []
+    for ip, pa in enumerate(problem.patches):
+        patches.append(PatchData([degree] * 2, [kv.knots for kv in skvs[ip]], pa.geo_degree, pa.geo_knots, pa.geo_coefs,
+                                 index[offset[ip]:offset[ip + 1]].astype(np.int32), pa.geo_weights))
+    return Problem(patches, nfree, nelim, form=problem.form, ncomp=1, rhs_programs=rhs_programs if rhs_programs is not None else problem.rhs_programs,
+                   rank=rank, nranks=nranks)

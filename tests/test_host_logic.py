@@ -158,3 +158,21 @@ def test_coupled_column_ranges_scalar_and_vector():
     runs = D.coupled_column_ranges(pe)
     n1 = pe.nfree // 3
     assert len(runs) == 3 and all(b == (c + 1) * n1 for c, (a, b) in enumerate(runs)) and len({b - a for a, b in runs}) == 1
+
+
+def test_yeti_topology_refines_like_the_reference():
+    """BASELINE config 3 (filedata/domain2d/yeti_mp2.xml, 21 patches): the topology is read off the coarse reference fixture
+    and the discretisation rebuilt at another refinement by the host builder; at nelem = 8 it must reproduce, bit for bit,
+    the DOF map the reference itself produced (tests/golden/yeti_mp2_p2_m8.npz)."""
+    import goldenutil as G
+    small, _ = G.load("yeti_mp2_p2_m2", lambda t: None, with_rhs=False)
+    big, z = G.load("yeti_mp2_p2_m8", lambda t: None, with_rhs=False)
+    interfaces, dirichlet = host.multipatch_topology_2d(small)
+    assert len(small.patches) == 21 and len(interfaces) >= 20 and len(dirichlet) >= 1
+    pb = host.refine_multipatch_2d(small, 2, 8)
+    assert (pb.nfree, pb.nfixed) == (big.nfree, big.nfixed)
+    for a, b in zip(pb.patches, big.patches):
+        assert np.array_equal(a.dofmap, b.dofmap)
+        assert all(np.allclose(x, y, rtol=0, atol=1e-15) for x, y in zip(a.space_knots, b.space_knots))
+    same = host.refine_multipatch_2d(small, 2, 2)
+    assert all(np.array_equal(a.dofmap, b.dofmap) for a, b in zip(same.patches, small.patches))
