@@ -269,6 +269,12 @@ def main():
             reference_arm(args, rank)
         return
 
+    # exactly ONE line on stdout: libraries print banners there (NCCL: "NCCL version ..."), so everything goes to stderr until the
+    # JSON line is written
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     import gismo_b200 as g
@@ -532,10 +538,12 @@ def main():
                 extra[cfg] = {"error": str(e)[:300]}
         res["configs"] = extra
 
-    if rank == 0:
-        print(json.dumps(res), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    if rank == 0:
+        print(json.dumps(res), flush=True)
 
 
 if __name__ == "__main__":
