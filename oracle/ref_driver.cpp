@@ -32,7 +32,8 @@ typedef struct gsref_config {
                                (geometry id 0, source id 1, boundary conditions id 2), nelem = #refinements */
     int32_t grid[3];      /* patches per direction for geometry 3                           */
     int32_t path;         /* 0 visitor (gsPoissonAssembler), 1 expression (gsExprAssembler)  */
-    int32_t form;         /* 0 Poisson, 1 linear elasticity (path 1 only)                   */
+    int32_t form;         /* 0 Poisson, 1 linear elasticity (path 1 only), 2 mass: path 0 = gsGenericAssembler::assembleMass
+                             (gsVisitorMass), path 1 = u*u.tr()*meas(G)                                            */
     int32_t dir_values;   /* 100 homogeneous, 101 interpolation, 102 L2 projection          */
     int32_t threads;      /* OpenMP threads for the assembly (0 = leave default)            */
     int32_t degree_elevate; /* geometry 4: degreeElevate instead of setDegree when >0       */
@@ -43,6 +44,8 @@ typedef struct gsref_config {
     int32_t neumann_mask; /* bit s set: boundary sides with index s (1..6) carry Neumann data `neu`  */
     int32_t neu_n;        /* 1: scalar flux (visitor path), dim: vector data dotted with the outer normal */
     const char *neu[3];
+    int32_t degree_dir[3]; /* >0: degree of the solution basis in that direction (mixed degrees), applied after setDegree */
+    int32_t nrhs;          /* path 0, form 0: right-hand-side columns (components of the source function), 0/1 = one */
 } gsref_config;
 
 struct gsref_result {
@@ -123,11 +126,14 @@ void *gsref_run(const gsref_config *cfg)
         }
         else if (c.geometry == 4 && c.degree_elevate > 0) mb.degreeElevate(c.degree_elevate);
         else mb.setDegree(c.degree);
+        for (int k = 0; k < d; ++k)      // mixed degrees: raise single directions
+            if (c.degree_dir[k] > c.degree) mb.degreeElevate(c.degree_dir[k] - c.degree, k);
         if (c.geometry != 5 && c.nelem > 1) mb.uniformRefine(c.nelem - 1);
 
         const int ncomp = c.form == 1 ? d : 1;
+        const int nfun = (c.form == 0 && c.path == 0 && c.nrhs > 1) ? c.nrhs : ncomp;     // components of the source / Dirichlet functions
         std::vector<std::string> fs, gs;
-        for (int k = 0; k < ncomp; ++k) { fs.push_back(c.rhs[k] ? c.rhs[k] : "0"); gs.push_back(c.dir[k] ? c.dir[k] : "0"); }
+        for (int k = 0; k < nfun; ++k) { fs.push_back(c.rhs[k] ? c.rhs[k] : "0"); gs.push_back(c.dir[k] ? c.dir[k] : "0"); }
         gsFunctionExpr<real_t> f(fs, d), g(gs, d);
 
         std::vector<std::string> ns;
@@ -157,8 +163,22 @@ void *gsref_run(const gsref_config *cfg)
 
         gsStopwatch timer;
         gsOptionList opt;
-        if (c.path == 0) {
-            GISMO_ENSURE(c.form == 0, "visitor path: Poisson only");
+        if (c.path == 0 && c.form == 2) {
+            // gsGenericAssembler::assembleMass -> gsVisitorMass (gsGenericAssembler.hpp:37-60, gsVisitorMass.h:30-157); the load
+            // vector of the same space comes from assembleMoments (gsVisitorMoments.h)
+            gsGenericAssembler<real_t> A(mp, mb, gsGenericAssembler<real_t>::defaultOptions(), &bc);
+            A.options().setInt("DirichletValues", c.dir_values);
+            timer.restart();
+            A.assembleMass();
+            R->assemble_seconds = timer.stop();
+            R->K = A.matrix();          // gsVisitorMass stores both triangles (gsVisitorMass.h:137-139)
+            A.assembleMoments(f);
+            R->rhs = A.rhs();
+            opt = A.options();
+            gsMatrix<real_t> nofixed;
+            b200::flatten(mp, mb, A.system().colMapper(0), 1, nofixed, opt, GSB200_FORM_MASS, R->flat);
+        } else if (c.path == 0) {
+            GISMO_ENSURE(c.form == 0, "visitor path: Poisson or mass");
             gsPoissonAssembler<real_t> A(mp, mb, bc, f, dirichlet::elimination, iFace::glue);
             A.options().setInt("DirichletValues", c.dir_values);
             timer.restart();
@@ -179,7 +199,9 @@ void *gsref_run(const gsref_config *cfg)
             u.setup(bc, (dirichlet::values)c.dir_values, 0);
             A.initSystem();
             timer.restart();
-            if (c.form == 0)
+            if (c.form == 2)
+                A.assemble(u * u.tr() * meas(G), u * ff * meas(G));
+            else if (c.form == 0)
             {
                 A.assemble(igrad(u, G) * igrad(u, G).tr() * meas(G), u * ff * meas(G));
                 if (c.neumann_mask || c.geometry == 5) { auto g_N = A.getBdrFunction(G); A.assembleBdr(bc.get("Neumann"), u * g_N.tr() * nv(G)); }
@@ -194,10 +216,10 @@ void *gsref_run(const gsref_config *cfg)
             R->rhs = A.rhs();
             opt = A.options();
             b200::flatten(mp, mb, u.mapper(), ncomp, u.fixedPart(), opt,
-                          c.form == 0 ? GSB200_FORM_POISSON : GSB200_FORM_ELASTICITY, R->flat);
+                          c.form == 0 ? GSB200_FORM_POISSON : (c.form == 2 ? GSB200_FORM_MASS : GSB200_FORM_ELASTICITY), R->flat);
             R->flat.pb.coef[0] = c.lambda; R->flat.pb.coef[1] = c.mu;
         }
-        R->flat.pb.nrhs = 1;
+        R->flat.pb.nrhs = (c.path == 0 && c.form == 0) ? std::max(1, c.nrhs) : 1;
         R->K.makeCompressed();
         R->elements = 0; R->qpoints = 0;
         for (size_t k = 0; k != mb.nBases(); ++k) {

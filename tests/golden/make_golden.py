@@ -46,6 +46,16 @@ FULL = {
     "poisson2d_bvp_stock_r2": dict(dim=2, degree=0, nelem=2, geometry=5, xml="pde/poisson2d_bvp.xml", path=1, dir_values=102),
     "elasticity_sq_p2": dict(dim=2, degree=2, nelem=4, geometry=1, path=1, form=1, lam=80000.0, mu=80000.0,
                              rhs=["1", "x"], dirichlet=["0", "0.01*x"], dir_values=101),
+    # mass form: gsGenericAssembler::assembleMass (gsVisitorMass.h:30-157) + assembleMoments, and u*u.tr()*meas(G) with
+    # interpolated Dirichlet data through the expression path (elimination term -M g on the right-hand side)
+    "mass_sq_p2_visitor": dict(dim=2, degree=2, nelem=6, geometry=1, path=0, form=2, rhs=["1+x*y"]),
+    "mass_cube_p3_curved_expr": dict(dim=3, degree=3, nelem=2, geometry=1, path=1, form=2, rhs=["x+z"], dirichlet=["x*y"], dir_values=101),
+    "mass_grid2x2_p2_expr": dict(dim=2, degree=2, nelem=3, geometry=3, grid=(2, 2, 1), path=1, form=2, rhs=["x"], dirichlet=["1+y"], dir_values=101),
+    # mixed degrees per direction, several right-hand sides
+    "cube_p232_curved_m3": dict(dim=3, degree=2, nelem=3, geometry=1, rhs=[PI3], dirichlet=["x+y*z"], degree_dir=[2, 3, 2]),
+    "sq_p31_m5": dict(dim=2, degree=1, nelem=5, geometry=1, rhs=[PI2], dirichlet=["x*y"], degree_dir=[3, 1]),
+    "sq_p3_nrhs2": dict(dim=2, degree=3, nelem=5, geometry=1, rhs=["x*y", "1+x"], nrhs=2, dir_values=100),
+    "cube_p2_nrhs3_interp": dict(dim=3, degree=2, nelem=2, geometry=1, rhs=["x", "y*z", "1"], dirichlet=["x", "y", "z*x"], nrhs=3, dir_values=101),
 }
 FINGERPRINT = {
     "cube_p3_m16": dict(dim=3, degree=3, nelem=16, geometry=0, rhs=[PI3], dir_values=100, threads=8),
@@ -58,11 +68,17 @@ FINGERPRINT = {
     "elasticity_8cubes_p2_m5": dict(dim=3, degree=2, nelem=5, geometry=3, grid=(2, 2, 2), path=1, form=1, lam=80000.0, mu=80000.0,
                                     rhs=["0", "0", "-1000"], dirichlet=["0", "0", "0.001*x"], dir_values=101, threads=1),
 }
+# above a million DOFs only samples and norms of the fingerprint vectors are kept (SAMPLE_STRIDE), so the fixture stays small
+SAMPLED = {
+    # curved geometry, non-uniform Jacobian, interpolated Dirichlet data at 1.09 M DOFs (3-D p=3, 100^3 elements)
+    "cube_p3_curved_m50": dict(dim=3, degree=3, nelem=50, geometry=1, rhs=[PI3], dirichlet=["x+y*z"], threads=8),
+}
+SAMPLE_STRIDE = 97
 KEEP_DOFMAP = {"yeti_mp2_p2_m8", "elasticity_8cubes_p2_m5"}
 
 
 def pack_inputs(ref):
-    d = {"nfree": ref.nfree, "nfixed": ref.nfixed, "ncomp": ref.ncomp, "dim": ref.dim, "form": ref.form,
+    d = {"nfree": ref.nfree, "nfixed": ref.nfixed, "ncomp": ref.ncomp, "dim": ref.dim, "form": ref.form, "nrhs": getattr(ref, "nrhs", 1),
          "coef": np.asarray(ref.coef), "quA": ref.quA, "quB": ref.quB, "npatches": len(ref.patches),
          "rhs_text": np.asarray(ref.rhs_text), "fixed": ref.fixed,
          "neumann_sides": np.asarray(ref.neumann_sides, dtype=np.int32).reshape(-1, 2), "neu_text": np.asarray(ref.neu_text)}
@@ -84,13 +100,37 @@ def probe_vector(n):
 
 
 def main():
+    only = set(sys.argv[1:])
+    import scipy.sparse as sp
+    for name, cfg in SAMPLED.items():
+        if only and name not in only:
+            continue
+        ref = R.ref_run(**cfg)
+        d = pack_inputs(ref)
+        K = sp.csc_matrix((ref.values, ref.inner, ref.outer), shape=(ref.nfree, ref.nfree))
+        Kx = K @ probe_vector(ref.nfree)
+        diag = K.diagonal()
+        for k in list(d):
+            if k.endswith("_dofmap"):
+                del d[k]
+        d.update(kind="sampled", config=repr(cfg), stride=SAMPLE_STRIDE, nnz=len(ref.values), sumK=ref.values.sum(), maxK=np.abs(ref.values).max(),
+                 inner_checksum=np.int64(ref.inner.astype(np.int64).sum()), outer_checksum=np.int64(ref.outer.astype(np.int64).sum()),
+                 Kx_s=Kx[::SAMPLE_STRIDE], diag_s=diag[::SAMPLE_STRIDE], rhs_s=ref.rhs[::SAMPLE_STRIDE, 0],
+                 Kx_norm=np.linalg.norm(Kx), diag_norm=np.linalg.norm(diag), rhs_norm=np.linalg.norm(ref.rhs), rhs_max=np.abs(ref.rhs).max(),
+                 seconds=ref.seconds)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
+        print(name, "N", ref.nfree, "nnz", len(ref.values), "reference seconds", ref.seconds)
     for name, cfg in FULL.items():
+        if only and name not in only:
+            continue
         ref = R.ref_run(**cfg)
         d = pack_inputs(ref)
         d.update(outer=ref.outer, inner=ref.inner, values=ref.values, rhs=ref.rhs, kind="full", config=repr(cfg))
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
         print(name, "N", ref.nfree, "nnz", len(ref.values))
     for name, cfg in FINGERPRINT.items():
+        if only and name not in only:
+            continue
         ref = R.ref_run(**cfg)
         d = pack_inputs(ref)
         import scipy.sparse as sp

@@ -44,8 +44,9 @@ def load(name, compile_fn, with_rhs=True):
     if "neumann_sides" in z and len(z["neumann_sides"]):
         neu = [compile_fn(str(t)) for t in z["neu_text"]]
         neumann = [(int(p), int(s), neu) for p, s in z["neumann_sides"]]
+    nrhs = int(z["nrhs"]) if "nrhs" in z else 1
     pb = Problem(patches, int(z["nfree"]), nfixed, form=int(z["form"]), ncomp=ncomp,
-                 fixed=z["fixed"] if nfixed else None, nrhs=1, coef=tuple(z["coef"]), quA=float(z["quA"]),
+                 fixed=z["fixed"] if nfixed and z["fixed"].size else None, nrhs=nrhs, coef=tuple(z["coef"]), quA=float(z["quA"]),
                  quB=int(z["quB"]), rhs_programs=progs, neumann=neumann)
     return pb, z
 
@@ -70,6 +71,19 @@ def check_against(result, z, tol):
         return ev, er
     n = int(z["nfree"])
     assert len(values) == int(z["nnz"])
+    if str(z["kind"]) == "sampled":          # million-DOF cases: samples (every stride-th entry) and norms of the fingerprint vectors
+        st = int(z["stride"])
+        assert int(outer.astype(np.int64).sum()) == int(z["outer_checksum"]) and int(inner.astype(np.int64).sum()) == int(z["inner_checksum"])
+        K = sp.csc_matrix((values, inner, outer), shape=(n, n))
+        scale = float(z["maxK"])
+        Kx, diag = K @ probe_vector(n), K.diagonal()
+        e1 = max(np.abs(Kx[::st] - z["Kx_s"]).max() / (scale * 50), abs(np.linalg.norm(Kx) - float(z["Kx_norm"])) / float(z["Kx_norm"]))
+        e2 = max(np.abs(diag[::st] - z["diag_s"]).max() / scale, abs(np.linalg.norm(diag) - float(z["diag_norm"])) / float(z["diag_norm"]))
+        e3 = abs(values.sum() - float(z["sumK"])) / (scale * np.sqrt(len(values)))
+        er = max(np.abs(rhs[::st, 0] - z["rhs_s"]).max() / float(z["rhs_max"]), abs(np.linalg.norm(rhs) - float(z["rhs_norm"])) / float(z["rhs_norm"]))
+        assert max(e1, e2, e3) <= tol, f"fingerprints differ: Kx {e1:.2e} diag {e2:.2e} sum {e3:.2e}"
+        assert er <= tol, f"rhs differs: {er:.3e}"
+        return max(e1, e2, e3), er
     assert np.array_equal(outer, z["outer"])
     assert int(inner.astype(np.int64).sum()) == int(z["inner_checksum"])
     K = sp.csc_matrix((values, inner, outer), shape=(n, n))

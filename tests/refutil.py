@@ -83,7 +83,8 @@ class RefConfig(C.Structure):
                 ("grid", C.c_int32 * 3), ("path", C.c_int32), ("form", C.c_int32), ("dir_values", C.c_int32),
                 ("threads", C.c_int32), ("degree_elevate", C.c_int32), ("rhs", C.c_char_p * 3),
                 ("dir", C.c_char_p * 3), ("xml", C.c_char_p), ("lambda_", C.c_double), ("mu", C.c_double),
-                ("neumann_mask", C.c_int32), ("neu_n", C.c_int32), ("neu", C.c_char_p * 3)]
+                ("neumann_mask", C.c_int32), ("neu_n", C.c_int32), ("neu", C.c_char_p * 3),
+                ("degree_dir", C.c_int32 * 3), ("nrhs", C.c_int32)]
 
 
 _ref = None
@@ -143,7 +144,7 @@ class RefResult:
 
 def ref_run(dim=3, degree=2, nelem=4, geometry=0, grid=(1, 1, 1), path=0, form=0, dir_values=101,
             threads=1, rhs=None, dirichlet=None, xml=None, lam=0.0, mu=0.0, degree_elevate=0,
-            neumann_mask=0, neu=None) -> RefResult:
+            neumann_mask=0, neu=None, degree_dir=None, nrhs=1) -> RefResult:
     lib = ref_lib()
     cfg = RefConfig()
     cfg.dim, cfg.degree, cfg.nelem, cfg.geometry = dim, degree, nelem, geometry
@@ -151,6 +152,11 @@ def ref_run(dim=3, degree=2, nelem=4, geometry=0, grid=(1, 1, 1), path=0, form=0
         cfg.grid[k] = grid[k] if k < len(grid) else 1
     cfg.path, cfg.form, cfg.dir_values, cfg.threads, cfg.degree_elevate = path, form, dir_values, threads, degree_elevate
     ncomp = dim if form == 1 else 1
+    if form == 0 and path == 0 and nrhs > 1:
+        ncomp = nrhs                      # components of the source / Dirichlet functions = right-hand-side columns
+    cfg.nrhs = nrhs
+    for k, v in enumerate(degree_dir or []):
+        cfg.degree_dir[k] = v
     rhs = list(rhs or ["0"] * ncomp)
     dirichlet = list(dirichlet or ["0"] * ncomp)
     for k in range(ncomp):
@@ -187,8 +193,9 @@ def ref_run(dim=3, degree=2, nelem=4, geometry=0, grid=(1, 1, 1), path=0, form=0
         R.outer = np.zeros(R.nfree + 1, np.int32)
         R.inner = np.zeros(nnz, np.int32)
         R.values = np.zeros(nnz)
-        R.rhs = np.zeros((R.nfree, 1), order="F")
-        R.fixed = np.zeros((max(R.nfixed, 1), 1), order="F")
+        R.nrhs = nrhs if (form == 0 and path == 0) else 1
+        R.rhs = np.zeros((R.nfree, R.nrhs), order="F")
+        R.fixed = np.zeros((max(R.nfixed, 1), R.nrhs), order="F")
         lib.gsref_csc(h, R.outer.ctypes.data_as(_ip), R.inner.ctypes.data_as(_ip), R.values.ctypes.data_as(_dp),
                       R.rhs.ctypes.data_as(_dp), R.fixed.ctypes.data_as(_dp))
         R.fixed = R.fixed[:R.nfixed]

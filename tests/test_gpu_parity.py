@@ -303,3 +303,29 @@ def test_values_only_reassembly_with_streamed_column_ranges(lib, name, chunks, m
     assert np.array_equal(again[2], ref[2])
     ok, msg = R.compare_csc(again, ref, 1e-13)
     assert ok, msg
+
+
+def test_curved_geometry_at_a_million_dofs(lib):
+    """3-D p=3 on the curved cube, 100^3 elements, 1.09 M DOFs, interpolated Dirichlet data: the reference ran this here
+    (tests/golden/make_golden.py, SAMPLED) and left samples + norms of K x, diag K, rhs and checksums of the index arrays."""
+    if "cube_p3_curved_m50" not in G.names("sampled"):
+        pytest.skip("sampled fixture not generated")
+    pb, z = G.load("cube_p3_curved_m50", g.expr_compile)
+    assert pb.nfree == 101 ** 3
+    G.check_against(R.lib_assemble(lib, pb), z, TOL)
+
+
+def test_determinism_with_inhomogeneous_dirichlet_data(lib):
+    """Repeated assemblies with non-zero eliminated values: every matrix entry has exactly one owner thread, so the values are
+    bit-identical; the elimination terms -K g are accumulated on the owner's right-hand-side entry with atomicAdd, whose order is
+    free: the right-hand side may move by a few ulp of its largest term (bound asserted: 1e-14 of max|rhs|)."""
+    pb, z = G.load("cube_p3_curved_m4", g.expr_compile)
+    runs = [R.lib_assemble(lib, pb) for _ in range(4)]
+    for r in runs[1:]:
+        assert np.array_equal(r[2], runs[0][2]) and np.array_equal(r[1], runs[0][1])
+        assert np.abs(r[3] - runs[0][3]).max() <= 1e-14 * np.abs(runs[0][3]).max()
+    G.check_against(runs[-1], z, TOL)
+    # multi-patch: coupled interface columns are summed with atomicAdd as well
+    pb, z = G.load("grid2x2x2_p2_m3", g.expr_compile)
+    a, b = R.lib_assemble(lib, pb), R.lib_assemble(lib, pb)
+    assert np.abs(a[2] - b[2]).max() <= 1e-14 * np.abs(a[2]).max() and np.abs(a[3] - b[3]).max() <= 1e-14 * np.abs(a[3]).max()
