@@ -199,6 +199,12 @@ class DeviceAssembler:
                                        C.byref(it), C.byref(res)))
         return x, it.value, res.value
 
+    def cg_info(self):
+        """(device ms of the last solve's iteration loop, halo-exchange mode?)"""
+        ms, h = C.c_double(0), C.c_int32(0)
+        self._check(self.lib.gsb200_cg_info(self._h, C.byref(ms), C.byref(h)))
+        return ms.value, bool(h.value)
+
     def cg(self, b: np.ndarray, max_iter: int = 1000, tol: float = 1e-10):
         b = np.ascontiguousarray(b, dtype=np.float64).ravel()
         x = np.zeros_like(b)

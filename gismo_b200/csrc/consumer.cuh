@@ -122,14 +122,27 @@ GSB_GLOBAL void __launch_bounds__(256) k_spmv_reg(int c0, int c1, const i64 *ptr
         const i64 b = ptr[r];
         const int t = reg[r];
         double s = 0.0;
+        // tiles of 8 x 32 entries: all value (and index) loads of a tile are issued before the first gather of x depends on them
         if (t) {
             const int len = tlen[t - 1]; const int *o = toff + (i64)(t - 1) * tstride;
             const double *v = val + b, *xr = x + r;
-#pragma unroll 4
-            for (int k = lane; k < len; k += 32) s = fma(__ldcs(v + k), __ldg(xr + __ldg(o + k)), s);
+            for (int base = 0; base < len; base += 256) {
+                double vv[8]; int oo[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { const int k = base + j * 32 + lane; const bool ok = k < len; vv[j] = ok ? __ldcs(v + k) : 0.0; oo[j] = ok ? __ldg(o + k) : 0; }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s = fma(vv[j], __ldg(xr + oo[j]), s);
+            }
         } else {
-            const i64 e = ptr[r + 1];
-            for (i64 k = b + lane; k < e; k += 32) s = fma(__ldcs(val + k), __ldg(x + __ldcs(idx + k)), s);
+            const int len = (int)(ptr[r + 1] - b);
+            const double *v = val + b; const int *ix = idx + b;
+            for (int base = 0; base < len; base += 256) {
+                double vv[8]; int oo[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { const int k = base + j * 32 + lane; const bool ok = k < len; vv[j] = ok ? __ldcs(v + k) : 0.0; oo[j] = ok ? __ldcs(ix + k) : (int)r; }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s = fma(vv[j], __ldg(x + oo[j]), s);
+            }
         }
 #pragma unroll
         for (int o2 = 16; o2 > 0; o2 >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o2);
@@ -183,37 +196,42 @@ GSB_DEVICE void cg_block_add(double s, double *out)
 // scalars S (device): [0] rz  [1] pq  [2] rz_new  [3] rr  [4] bb
 // r = b, z = r / d, p = z on [c0, c1); rz += r.z, bb += b.b
 // (the dot products take the entries [d0, d1) only: ranks that keep whole vectors split the index range between them, so that the
-// reduced scalars - and with them every rank's iterates - are bitwise the same everywhere)
+// reduced scalars - and with them every rank's iterates - are bitwise the same everywhere).  Fixed-size grids, grid-stride loops:
+// one atomic per warp and scalar.
 GSB_GLOBAL void k_cg_start(int c0, int c1, int d0, int d1, const double *b, const double *d, double *x, double *r, double *z, double *p, double *S)
 {
-    const int i = c0 + blockIdx.x * blockDim.x + threadIdx.x;
     double s0 = 0.0, s1 = 0.0;
-    if (i < c1) { const double bi = b[i]; const double zi = bi / d[i]; x[i] = 0.0; r[i] = bi; z[i] = zi; p[i] = zi; if (i >= d0 && i < d1) { s0 = bi * zi; s1 = bi * bi; } }
+    for (i64 i = c0 + (i64)blockIdx.x * blockDim.x + threadIdx.x; i < c1; i += (i64)gridDim.x * blockDim.x) {
+        const double bi = b[i]; const double zi = bi / d[i];
+        x[i] = 0.0; r[i] = bi; z[i] = zi; p[i] = zi;
+        if (i >= d0 && i < d1) { s0 = fma(bi, zi, s0); s1 = fma(bi, bi, s1); }
+    }
     cg_block_add(s0, S + 0); cg_block_add(s1, S + 4);
 }
 GSB_GLOBAL void k_cg_dot(int c0, int c1, const double *u, const double *v, double *out)
 {
-    const int i = c0 + blockIdx.x * blockDim.x + threadIdx.x;
-    cg_block_add(i < c1 ? u[i] * v[i] : 0.0, out);
+    double s0 = 0.0;
+    for (i64 i = c0 + (i64)blockIdx.x * blockDim.x + threadIdx.x; i < c1; i += (i64)gridDim.x * blockDim.x) s0 = fma(u[i], v[i], s0);
+    cg_block_add(s0, out);
 }
 // alpha = rz / pq;  x += alpha p;  r -= alpha q;  z = r / d;  rz_new += r.z;  rr += r.r
 GSB_GLOBAL void k_cg_step1(int c0, int c1, int d0, int d1, const double *p, const double *q, const double *d, double *x, double *r, double *z, double *S)
 {
-    const int i = c0 + blockIdx.x * blockDim.x + threadIdx.x;
     const double alpha = S[0] / S[1];
     double s0 = 0.0, s1 = 0.0;
-    if (i < c1) {
+    for (i64 i = c0 + (i64)blockIdx.x * blockDim.x + threadIdx.x; i < c1; i += (i64)gridDim.x * blockDim.x) {
         x[i] = fma(alpha, p[i], x[i]);
         const double ri = fma(-alpha, q[i], r[i]); const double zi = ri / d[i];
-        r[i] = ri; z[i] = zi; if (i >= d0 && i < d1) { s0 = ri * zi; s1 = ri * ri; }
+        r[i] = ri; z[i] = zi;
+        if (i >= d0 && i < d1) { s0 = fma(ri, zi, s0); s1 = fma(ri, ri, s1); }
     }
     cg_block_add(s0, S + 2); cg_block_add(s1, S + 3);
 }
 // beta = rz_new / rz;  p = z + beta p
 GSB_GLOBAL void k_cg_step2(int c0, int c1, const double *z, double *p, const double *S)
 {
-    const int i = c0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < c1) p[i] = fma(S[2] / S[0], p[i], z[i]);
+    const double beta = S[2] / S[0];
+    for (i64 i = c0 + (i64)blockIdx.x * blockDim.x + threadIdx.x; i < c1; i += (i64)gridDim.x * blockDim.x) p[i] = fma(beta, p[i], z[i]);
 }
 // rotate the scalars for the next iteration: rz = rz_new, last_rr = rr; accumulators cleared
 GSB_GLOBAL void k_cg_rotate(double *S)
@@ -362,44 +380,74 @@ static int cg_solve(gsb200_assembler *a, const double *b_dev, int max_iter, doub
     CgPlan P; GSB_TRY(cg_plan(a, P));
     a->xchg_bytes = 0;
     const dim3 gN((N + 127) / 128), t(128);
-    const int c0 = P.c0, c1 = P.c1; const dim3 gO((std::max(c1 - c0, 1) + 127) / 128);
+    const int c0 = P.c0, c1 = P.c1;
+#ifndef GSB200_EMULATE
+    const dim3 gO(148 * 4), tv(256);        // grid-stride vector kernels
+#else
+    const dim3 gO(1), tv(1);
+#endif
     const bool multi = a->nranks > 1;
     const bool rep = multi && !P.halo;          // whole vectors on every rank: the dot products are split by index range and reduced
     const int d0 = rep ? (int)((i64)N * a->rank / a->nranks) : c0, d1 = rep ? (int)((i64)N * (a->rank + 1) / a->nranks) : c1;
-    const dim3 gD((std::max(d1 - d0, 1) + 127) / 128);
+    const dim3 gD = gO;
     // preconditioner: diagonal of the stored columns; columns stored by several ranks (coupled, already exchanged) count once
     GSB_LAUNCH(k_cg_diag, gN, t, s, N, a->d_colptr, a->d_inner, a->d_values, Dg, H);
     if (multi && !P.halo) { GSB_TRY(comm_allreduce(a, Dg, N)); GSB_TRY(comm_allreduce(a, H, N)); }
     GSB_LAUNCH(k_cg_prep, gN, t, s, N, Dg, H);
     GSB_TRY(dev_memset(S, 0, 8 * sizeof(double), s));
     if (multi && !P.halo) { GSB_TRY(dev_memset(X, 0, sizeof(double) * (size_t)N, s)); }
-    GSB_LAUNCH(k_cg_start, gO, t, s, c0, c1, d0, d1, b_dev, Dg, X, R, Z, Pv, S);
+    GSB_LAUNCH(k_cg_start, gO, tv, s, c0, c1, d0, d1, b_dev, Dg, X, R, Z, Pv, S);
     if (multi) GSB_TRY(comm_allreduce(a, S, 8));
     double hs[8]; GSB_TRY(dev_d2h(hs, S, sizeof hs, s));
     const double bb = hs[4]; double rr = bb;
     const double thr = tol * tol * bb;
     int it = 0;
     if (check_every < 1) check_every = 1;
+#ifndef GSB200_EMULATE
+    // GSB200_CG_PROFILE=1: device time of the phases of the second burst's iterations (events on the stream), printed to stderr
+    const bool prof = getenv("GSB200_CG_PROFILE") != 0;
+    cudaEvent_t pe[6]; float pacc[5] = {0, 0, 0, 0, 0}; int pn = 0;
+    if (prof) for (auto &e : pe) cudaEventCreate(&e);
+#define GSB_CG_MARK(i) do { if (prof && it >= check_every) cudaEventRecord(pe[i], s); } while (0)
+#else
+#define GSB_CG_MARK(i) do { } while (0)
+#endif
+#ifndef GSB200_EMULATE
+    cudaEvent_t le0, le1; cudaEventCreate(&le0); cudaEventCreate(&le1); cudaEventRecord(le0, s);
+#endif
     while (it < max_iter && rr > thr) {
         const int burst = std::min(check_every, max_iter - it);
         for (int k = 0; k < burst; ++k) {
+            GSB_CG_MARK(0);
 #ifndef GSB200_EMULATE
             if (P.halo) GSB_TRY(cg_halo(a, P, Pv));
 #endif
+            GSB_CG_MARK(1);
             if (P.halo || !multi) {
                 GSB_TRY(spmv_range(a, c0, c1, Pv, Q, 0, S + 1));
+                GSB_CG_MARK(2);
                 if (P.halo) GSB_TRY(comm_allreduce(a, S + 1, 1));
             } else {
                 // patch-wise ownership: every rank multiplies the columns it stores (shared ones weighted 1/holders), the products add up
                 GSB_TRY(spmv_range(a, 0, N, Pv, Q, H, 0));
                 GSB_TRY(comm_allreduce(a, Q, N)); a->xchg_bytes += 8 * (i64)N;
-                GSB_LAUNCH(k_cg_dot, gD, t, s, d0, d1, Pv, Q, S + 1);
+                GSB_LAUNCH(k_cg_dot, gD, tv, s, d0, d1, Pv, Q, S + 1);
                 GSB_TRY(comm_allreduce(a, S + 1, 1));
             }
-            GSB_LAUNCH(k_cg_step1, gO, t, s, c0, c1, d0, d1, Pv, Q, Dg, X, R, Z, S);
+            GSB_CG_MARK(3);
+            GSB_LAUNCH(k_cg_step1, gO, tv, s, c0, c1, d0, d1, Pv, Q, Dg, X, R, Z, S);
+            GSB_CG_MARK(4);
             if (multi) GSB_TRY(comm_allreduce(a, S + 2, 2));
-            GSB_LAUNCH(k_cg_step2, gO, t, s, c0, c1, Z, Pv, S);
+            GSB_LAUNCH(k_cg_step2, gO, tv, s, c0, c1, Z, Pv, S);
             GSB_LAUNCH(k_cg_rotate, dim3(1), dim3(32), s, S);
+            GSB_CG_MARK(5);
+#ifndef GSB200_EMULATE
+            if (prof && it >= check_every && it < 2 * check_every) {
+                cudaEventSynchronize(pe[5]);
+                for (int i = 0; i < 5; ++i) { float ms = 0; cudaEventElapsedTime(&ms, pe[i], pe[i + 1]); pacc[i] += ms; }
+                ++pn;
+            }
+#endif
             ++it;
         }
         GSB_TRY(dev_d2h(hs, S, sizeof hs, s));
@@ -407,6 +455,8 @@ static int cg_solve(gsb200_assembler *a, const double *b_dev, int max_iter, doub
         if (!(rr == rr)) { set_error("CG broke down (NaN residual) at iteration %d", it); return GSB200_ECUDA; }
     }
 #ifndef GSB200_EMULATE
+    cudaEventRecord(le1, s); cudaEventSynchronize(le1); { float ms = 0; cudaEventElapsedTime(&ms, le0, le1); a->cg_loop_ms = ms; }
+    cudaEventDestroy(le0); cudaEventDestroy(le1);
     if (P.halo) {       // every rank gets the whole solution: each slab is broadcast by its owner
         NcclApi *NC; GSB_TRY(need_nccl(&NC));
         GSB_TRY(nccl_check(NC->GroupStart(), "ncclGroupStart"));
@@ -420,6 +470,14 @@ static int cg_solve(gsb200_assembler *a, const double *b_dev, int max_iter, doub
     }
 #endif
     GSB_TRY(dev_sync(s));
+#ifndef GSB200_EMULATE
+    if (prof) {
+        if (pn) fprintf(stderr, "[gsb200 cg] rank %d: per iteration (ms, %d samples): halo %.3f  spmv %.3f  reduce(p.Ap) %.3f  update x,r,z %.3f  reduce(r.z, r.r) + update p %.3f\n",
+                        a->rank, pn, pacc[0] / pn, pacc[1] / pn, pacc[2] / pn, pacc[3] / pn, pacc[4] / pn);
+        for (auto &e : pe) cudaEventDestroy(e);
+    }
+#endif
+#undef GSB_CG_MARK
     a->cg_halo_mode = P.halo;
     if (iters) *iters = it;
     if (rel_residual) *rel_residual = bb > 0 ? sqrt(rr / bb) : 0.0;
@@ -567,6 +625,14 @@ int gsb200_cg_host(gsb200_assembler *a, const double *b, double *x, int max_iter
 {
     if (!b || !x) return GSB200_EINVAL;
     return gsb200_cg_solve(a, b, x, max_iter, tol, 1, iters, rel_residual);
+}
+
+int gsb200_cg_info(const gsb200_assembler *a, double *loop_ms, int32_t *halo_exchange)
+{
+    if (!a) return GSB200_EINVAL;
+    if (loop_ms) *loop_ms = a->cg_loop_ms;
+    if (halo_exchange) *halo_exchange = a->cg_halo_mode ? 1 : 0;
+    return GSB200_OK;
 }
 
 int gsb200_cg_solution_device(gsb200_assembler *a, const double **x_dev)

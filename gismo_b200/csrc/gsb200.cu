@@ -226,7 +226,7 @@ struct gsb200_assembler {
     gsb200_allreduce_fn ar_fn = 0; void *ar_ctx = 0;
     i64 xchg_bytes = 0; int xchg_calls = 0;
     unsigned char *d_reg = 0; int *d_regoff = 0, *d_reglen = 0; int reg_ntab = 0, reg_stride = 1; bool spmv_ready = false;
-    int own_c0 = 0, own_c1 = 0, need_lo = 0, need_hi = 0; bool own_contig = true, cg_halo_mode = false;
+    int own_c0 = 0, own_c1 = 0, need_lo = 0, need_hi = 0; bool own_contig = true, cg_halo_mode = false; double cg_loop_ms = 0;
     double *cgv[8] = {0, 0, 0, 0, 0, 0, 0, 0}, *cg_b = 0;      // CG work vectors x r z p q d h + scalars; user rhs
     ~gsb200_assembler() {
         dev_sync(stream);                  // frees below are not ordered behind this stream's kernels

@@ -272,6 +272,9 @@ int gsb200_cg_host(gsb200_assembler *a, const double *b, double *x, int max_iter
 int gsb200_cg_solve(gsb200_assembler *a, const double *b_host, double *x_host, int max_iter, double tol, int check_every,
                     int *iters, double *rel_residual);
 int gsb200_cg_solution_device(gsb200_assembler *a, const double **x_dev);
+/* Device time of the iteration loop of the last gsb200_cg_solve (CUDA events; set-up such as NCCL's lazy connections and the
+   gathering of the solution excluded) and whether the ranks traded halos (1) or reduced full-length products (0). */
+int gsb200_cg_info(const gsb200_assembler *a, double *loop_ms, int32_t *halo_exchange);
 /* Columns whose row set is a translate of a reference stencil (the SpMV reads 8 instead of 12 bytes per entry there). */
 int gsb200_spmv_info(gsb200_assembler *a, int64_t *regular_columns, int32_t *tables);
 
