@@ -228,6 +228,7 @@ def declare(lib, optional=()):
     lib.gsb200_spmv_host.argtypes = [C.c_void_p, _dp, _dp]
     lib.gsb200_spmv_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.gsb200_diag_device.argtypes = [C.c_void_p, C.c_void_p]
+    lib.gsb200_diag_host.argtypes = [C.c_void_p, _dp]
     lib.gsb200_cg_host.argtypes = [C.c_void_p, _dp, _dp, C.c_int, C.c_double, C.POINTER(C.c_int), _dp]
     lib.gsb200_expr_compile.argtypes = [C.c_char_p, _ip, C.c_int32, _ip, _dp, C.c_int32, _ip]
     lib.gsb200_jit_launches.argtypes = [C.c_void_p, C.POINTER(C.c_int)]

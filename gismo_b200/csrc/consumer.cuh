@@ -590,6 +590,17 @@ int gsb200_diag_device(gsb200_assembler *a, double *d_dev)
     return GSB200_OK;
 }
 
+int gsb200_diag_host(gsb200_assembler *a, double *d)
+{
+    if (!a || !d) return GSB200_EINVAL;
+    if (!a->assembled) { set_error("diag before assemble"); return GSB200_ESTATE; }
+    GSB_TRY(select_device(a->device));
+    const int n = a->nfree;
+    if (!a->cgv[1]) GSB_TRY(dev_malloc((void **)&a->cgv[1], sizeof(double) * (size_t)(n + 8)));
+    GSB_LAUNCH(k_diag, dim3((n + 127) / 128), dim3(128), a->stream, n, a->d_colptr, a->d_inner, a->d_values, a->cgv[1]);
+    return dev_d2h(d, a->cgv[1], sizeof(double) * (size_t)n, a->stream);
+}
+
 int gsb200_spmv_host(gsb200_assembler *a, const double *x, double *y)
 {
     if (!a || !x || !y) return GSB200_EINVAL;

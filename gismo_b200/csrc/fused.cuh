@@ -32,6 +32,7 @@ struct FusedArgs {
     int ncolL, nrows;                                   // columns along the last direction (a tile never straddles a row); rows (3-D: Q1, 2-D: 1)
     double *out; i64 out_cs, out_fs, out_bq, out_bs, out_is; int d_off;      // A1 addressing (as SweepArgs); the delta stride is p+1 (blocked layouts)
     i64 out_ds;                                         // ... or, ROWS layout A1[o][i0][d0][q1][q2]: the (runtime) stride of a delta row
+    int half_rows;                                      // blocked layouts: store delta >= 0 only (the next sweep reads delta < 0 at the mirrored pair, T3SymS2U)
     double *v1; i64 v1_cs, v1_fs; int nf;               // first load-vector sweep: V1[c][i0][column]
 };
 
@@ -323,8 +324,10 @@ GSB_DEVICE void geo_sweep_body(const FusedArgs &A)
             } else {
                 if (mine && (FULLG || g < th.ngv)) {
                     double *po = th.pw[g];
+                    if (!A.half_rows) {
 #pragma unroll
-                    for (int j = P1 - 1; j >= 1; --j) st_stream(po - j * DS, th.hold[S][j][g]);
+                        for (int j = P1 - 1; j >= 1; --j) st_stream(po - j * DS, th.hold[S][j][g]);
+                    }
 #pragma unroll
                     for (int b = 0; b < P1; ++b) st_stream(po + b * DS, th.acc[S][(S + b) % P1][g]);
                 }

@@ -467,8 +467,8 @@ static int assemble_pass(gsb200_assembler *a)
         // layout of A1 (3-D): 1 (default) = blocked by last-direction element (A1[o][i0][q1][e2][d0][t]: the second sweep reads whole runs; the
         // first one stores whole rows of deltas at the owner's exit), 2 = A1[o][i0][d0][q1][q2] (coalesced first-sweep stores, the second
         // sweep gathers q-point pieces; measured slower, profiles/r01b_layout_experiments.txt).  GSB200_A1BLK overrides.
-        static const int a1_env = [] { const char *e = getenv("GSB200_A1BLK"); return e ? atoi(e) : -1; }();
-        const int a1_mode = dim != 3 ? 0 : (a1_env >= 0 ? a1_env : 1);
+        const int a1_env = [] { const char *e = getenv("GSB200_A1BLK"); return e ? atoi(e) : -1; }();      // read at every assembly: the tests switch it
+        const int a1_mode = dim != 3 ? 0 : ((a1_env >= 0 && a1_env != 3) ? a1_env : 1);      // (3 = 1 + rows stored for delta >= 0 only, see a1_half)
         // the gathered reads exist in the window kernel only (q = p+1 points); any other rule keeps the blocked layout, which the
         // generic kernels address through the same strides
         const bool a1_gather = a1_mode == 2 && dim == 3 && d1.q == d1.p + 1, a1_blk = a1_mode == 1 || (a1_mode == 2 && !a1_gather);
@@ -478,9 +478,15 @@ static int assemble_pass(gsb200_assembler *a)
         const bool fused = fuse_env && P.d_lc && d0.q == d0.p + 1 && dL.q == d0.q && d0.p >= 1 && d0.p <= 4 && nf <= GSB_FUSE_MAXF;     // (the rows layout is chosen below when the next two sweeps are fused as well)
         // second + last sweep fused (fused23.cuh): A1 in rows layout, A2 never exists.  3-D gradient forms, degrees 1..3, p+1-point rules.
         const bool s23 = fused && dim == 3 && a1_env < 0 && d1.q == d1.p + 1 && dL.q == dL.p + 1 && d1.p == dL.p && s23_available(kind, d1.p + 1);
+        // A1 stored for delta >= 0 only, A1[o][q1][e2][i0][d0 = 0..p][t] (terms.cuh T3SymS2U): symmetric 3-D forms at degree 3 with the
+        // 4-point rule (a span's points fill a 32-byte sector); the second sweep reads delta < 0 at the mirrored pair, a few rows away
+        // in the same (q1, e2) block.  GSB200_A1BLK=1 keeps the full rows.
+        const bool a1_half = fused && !s23 && dim == 3 && kind == KIND_SYM && (a1_env < 0 || a1_env == 3) && d0.p == 3 && d1.p == 3 && d1.q == 4 && dL.q == 4;
+        const i64 A1I0 = a1_half ? (i64)d0.nfun * (d0.p + 1) : NI0;        // (function, stored delta) pairs of direction 0
+        const i64 a1_pad = a1_half ? 64 : 0;
         const int nfv = std::max(nf, 1);
         // doubles of workspace per last-direction quadrature point
-        i64 perq = (fused ? 0 : ncD * Q0 * Q1 + nf * Q0 * Q1) + no1 * NI0 * Q1 + (dim == 3 && !s23 ? no2 * NI1 * NI0 : 0) + nfv * n0 * Q1 + (dim == 3 ? n1 * n0 : 0);
+        i64 perq = (fused ? 0 : ncD * Q0 * Q1 + nf * Q0 * Q1) + no1 * A1I0 * Q1 + (dim == 3 && !s23 ? no2 * NI1 * NI0 : 0) + nfv * n0 * Q1 + (dim == 3 ? n1 * n0 : 0);
         i64 maxpts = limit / (perq * 8);
         const i64 minpts = (i64)(dL.p + 1) * dL.q;
         if (maxpts < minpts) { set_error("workspace limit %lld B too small: one slab of patch %zu needs %lld B", (long long)limit, ip, (long long)(perq * 8 * minpts)); return GSB200_ENOMEM; }
@@ -494,7 +500,7 @@ static int assemble_pass(gsb200_assembler *a)
             while (x_hi < P.own_hi && x_hi - x_lo < x_cap && (i64)(dL.flast[x_hi] - dL.ffirst[x_lo] + 1) * dL.q <= maxpts) ++x_hi;
             const int eL0 = dL.ffirst[x_lo], eL1 = dL.flast[x_hi - 1] + 1, ELc = eL1 - eL0;
             const i64 QLc = (i64)ELc * dL.q;
-            const size_t need = (size_t)(perq * QLc) * 8 + 6 * 256;
+            const size_t need = (size_t)(perq * QLc) * 8 + 6 * 256 + (size_t)a1_pad * 8;
             if (need > a->ws_size) {
                 GSB_TRY(dev_sync(s));
                 dev_free(a->ws); a->ws = 0; a->ws_size = 0;
@@ -503,7 +509,7 @@ static int assemble_pass(gsb200_assembler *a)
             double *w = (double *)a->ws;
             auto carve = [&](i64 count) { double *p = w; w += (count + 31) / 32 * 32; return p; };   // 256-byte aligned pieces
             double *D = carve(fused ? 0 : ncD * Q0 * Q1 * QLc);
-            double *A1 = carve(no1 * NI0 * Q1 * QLc);
+            double *A1 = carve(no1 * A1I0 * Q1 * QLc + a1_pad) + a1_pad;      // (the mirrored reads of the first functions reach a few doubles below)
             double *A2 = carve(dim == 3 && !s23 ? no2 * NI1 * NI0 * QLc : 0);
             double *F = carve(fused ? 0 : nf * Q0 * Q1 * QLc);
             double *V1 = carve(nfv * n0 * Q1 * QLc);
@@ -590,11 +596,11 @@ static int assemble_pass(gsb200_assembler *a)
                         FA.first = d0.d_first; FA.nexit = d0.d_nexit; FA.tab = d0.d_tab; FA.seg = A.seg; FA.lc = P.d_lc; FA.lc_nL = dL.ngeo;
                         FA.ncolL = (int)ncolL; FA.nrows = (int)nrows;
                         FA.out = A.out; FA.out_cs = A.out_cs; FA.out_fs = A.out_fs; FA.out_bq = A.out_bq; FA.out_bs = A.out_bs; FA.out_is = A.out_is;
-                        FA.d_off = A.d_off; FA.out_ds = A.out_ds;
+                        FA.d_off = A.d_off; FA.out_ds = A.out_ds; FA.half_rows = A.half_out;
                         FA.nf = with_load ? nf : 0; FA.v1 = V1; FA.v1_fs = A.ncol; FA.v1_cs = n0 * A.ncol;
                         { FusedCtx fc; fc.progs = &a->progs_host; fc.device = a->device; fc.jit_launches = &a->jit_launches;
                           GSB_TRY(launch_fused(fc, kind, dim, d0.p + 1, FA, (int)seg.size() / 4, s, hot, rat, pgl, s23 || a1_gather, &fpp)); }
-                        account(0, A, seg, fpp, 0, nout, NI0);
+                        account(0, A, seg, fpp, 0, nout, A.half_out ? A1I0 : NI0);
                     } else {
                         GSB_TRY(dispatch_sweep(kind, stage, d0.p + 1, A, (int)seg.size() / 4, s, &fpp));
                         account(0, A, seg, fpp, nin, nout, NI0);
@@ -610,6 +616,11 @@ static int assemble_pass(gsb200_assembler *a)
                         A.out = A1; A.out_cs = NI0 * Q1 * QLc; A.out_fs = (2 * d0.p + 1) * Q1 * QLc; A.out_ds = Q1 * QLc; A.out_os = 0; A.out_bq = A.ncol + 1; A.out_bs = 0; A.out_is = 1;
                         if (a1_blk && !s23) {    // A1[o][i0][q1][e2][d0][t]: the second sweep then reads AND writes whole (d0, t) runs
                             A.out_fs = Q1 * ELc * W0 * dL.q; A.out_ds = dL.q; A.out_bq = dL.q; A.out_bs = W0 * dL.q; A.out_is = 1;
+                        }
+                        if (a1_half) {           // A1[o][q1][e2][i0][d0 >= 0][t]
+                            const i64 P1q = (i64)(d0.p + 1) * dL.q;
+                            A.out_cs = A1I0 * Q1 * QLc; A.out_fs = P1q; A.out_ds = dL.q; A.out_bq = dL.q; A.out_bs = n0 * P1q; A.out_is = 1;
+                            A.half_out = 1; A.d_off = 0;
                         }
                         GSB_TRY(first_sweep(A, 0, QLc, Q1));
                     }
@@ -658,6 +669,13 @@ static int assemble_pass(gsb200_assembler *a)
                             A.ncol = n0 * ELc * W0 * dL.q; A.ninner = ELc * W0 * dL.q;
                             A.out_od = 1; A.out_dshift = 0; A.out_os = W1 * W0 * dL.q; A.out_os2 = 0; A.out_bq = W0 * dL.q; A.out_bs = NI0 * W1 * dL.q; A.out_is = 1;
                         }
+                        if (a1_half) {   // thread = (i0; e2, d0, t); stored rows [q1][e2][i0][d0 >= 0][t]; delta < 0 at the mirrored pair (i0 + d0, -d0)
+                            const i64 P1q = (i64)(d0.p + 1) * dL.q;
+                            A.in = A1 - (i64)d0.p * dL.q;       // slot index d0 + p in the thread mapping, slot d0 in memory
+                            A.in_cs = A1I0 * Q1 * QLc; A.in_ts = ELc * n0 * P1q; A.in_es = (i64)d1.q * A.in_ts; A.in_os = P1q; A.in_is = 1;
+                            A.in_bq2 = W0 * dL.q; A.in_bs2 = n0 * P1q; A.in_bq = dL.q; A.in_bs = dL.q;
+                            A.mir_q = dL.q; A.mir_w = (int)W0; A.mir_p = d0.p; A.mir_n = (int)n0;
+                        }
                         if (a1_gather) { // thread = (i0; e2, d0, t) as above, but A1 keeps whole q2 rows per (i0, d0)
                             A.in_os = W0 * Q1 * QLc; A.in_is = 1; A.in_ts = QLc; A.in_es = (i64)d1.q * QLc;
                             A.in_bq2 = W0 * dL.q; A.in_bs2 = dL.q; A.in_bq = dL.q; A.in_bs = Q1 * QLc;
@@ -668,9 +686,9 @@ static int assemble_pass(gsb200_assembler *a)
                         std::vector<int> seg = make_segments(d1, 0, d1.nfun, nseg);
                         A.seg = a->d_seg + segoff; GSB_TRY(upload_segments(a, seg, &segoff));
                         mark(a, 2);
-                        GSB_TRY(dispatch_sweep(kind, 1, d1.p + 1, A, (int)seg.size() / 4, s, &fpp));
+                        GSB_TRY(dispatch_sweep(kind, a1_half ? 4 : 1, d1.p + 1, A, (int)seg.size() / 4, s, &fpp));
                         stage_io(kind, 1, &nin, &nout);
-                        account(1, A, seg, fpp, nin, nout, NI1);
+                        account(1, A, seg, fpp, a1_half ? nin * (double)(d0.p + 1) / (double)W0 : nin, nout, NI1);      // (every stored value is read once from HBM)
                     }
                     {   // S3: direction 2, scatter into the CSC arrays
                         SweepArgs A = base_args(dL);

@@ -663,7 +663,8 @@ k_sweepw(const GSB_GRID_CONSTANT SweepArgs A)
         constexpr int c = decltype(cc)::value;
         if constexpr (T::uses_c(OMASK, c)) {
             constexpr int mode = T::in_mode(c);
-            pin[c] = ((mode == 2 || (mode == 0 && mir_neg)) ? inp_m : inp) + T::in_src(c) * A.in_cs;
+            const bool at_mirror = mode == 2 || (mode == 0 && mir_neg);
+            pin[c] = at_mirror ? inp_m + T::in_srcm(c) * A.in_cs : inp + T::in_src(c) * A.in_cs;
         }
     });
     auto issue = [&](int e, int st) {

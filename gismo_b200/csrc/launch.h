@@ -31,7 +31,7 @@ constexpr int window_ng(int P1, int NOUT)
     return ng;
 }
 
-// stage: 0 = first of 3-D, 1 = middle of 3-D, 2 = last; 3 = first of 2-D
+// stage: 0 = first of 3-D, 1 = middle of 3-D, 2 = last; 3 = first of 2-D; 4 = middle of 3-D on the half-stored first-sweep output
 int dispatch_sweep(int kind, int stage, int P1, const SweepArgs &A, int nseg, stream_t s, i64 *fpp);
 
 // K0 fused into the first sweep (fused.cuh)

@@ -65,6 +65,10 @@ static int launch_sweep(int P1, const SweepArgs &A, int nseg, stream_t s, i64 *f
 int dispatch_sweep(int kind, int stage, int P1, const SweepArgs &A, int nseg, stream_t s, i64 *fpp)
 {
     if (kind == KIND_MASS) return stage == 2 ? launch_sweep<TMass, true>(P1, A, nseg, s, fpp) : launch_sweep<TMass, false>(P1, A, nseg, s, fpp);
+    if (stage == 4) {      // middle sweep of a symmetric 3-D form on the half-stored first-sweep output (degree 3, window kernel only)
+        if (kind != KIND_SYM || P1 != 4 || A.q != P1) { set_error("half-stored first-sweep output: degree 3 with the 4-point rule only"); return GSB200_EUNSUPPORTED; }
+        return launch_sweep_t<4, T3SymS2U, false>(A, nseg, s, fpp);
+    }
     if (stage == 2) return launch_sweep<TLast, true>(P1, A, nseg, s, fpp);
     if (stage == 0) return kind == KIND_SYM ? launch_sweep<T3SymS1, false>(P1, A, nseg, s, fpp) : launch_sweep<T3GenS1, false>(P1, A, nseg, s, fpp);
     if (stage == 1) return kind == KIND_SYM ? launch_sweep<T3SymS2, false>(P1, A, nseg, s, fpp) : launch_sweep<T3GenS2, false>(P1, A, nseg, s, fpp);

@@ -19,6 +19,7 @@
 #include <gismo.h>
 #include <gsAssembler/gsPoissonAssembler.h>
 #include "gsB200Flatten.h"
+#include "gsB200LinearOperator.h"
 
 namespace gismo
 {
@@ -30,23 +31,34 @@ public:
     typedef gsPoissonAssembler<T> Base;
 
     gsPoissonAssemblerB200(const gsPoissonPde<T> & pde, const gsMultiBasis<T> & bases)
-    : Base(pde, bases), m_device(0), m_keepPattern(false) { }
+    : Base(pde, bases), m_device(0), m_keepPattern(false), m_rank(0), m_nranks(1) { }
 
     gsPoissonAssemblerB200(const gsPoissonPde<T> & pde, const gsMultiBasis<T> & bases,
                            dirichlet::strategy dirStrategy, iFace::strategy intStrategy = iFace::glue)
-    : Base(pde, bases, dirStrategy, intStrategy), m_device(0), m_keepPattern(false) { }
+    : Base(pde, bases, dirStrategy, intStrategy), m_device(0), m_keepPattern(false), m_rank(0), m_nranks(1) { }
 
     gsPoissonAssemblerB200(gsMultiPatch<T> const & patches, gsMultiBasis<T> const & basis,
                            gsBoundaryConditions<T> const & bconditions, const gsFunction<T> & rhs,
                            dirichlet::strategy dirStrategy = dirichlet::elimination,
                            iFace::strategy intStrategy = iFace::glue)
-    : Base(patches, basis, bconditions, rhs, dirStrategy, intStrategy), m_device(0), m_keepPattern(false) { }
+    : Base(patches, basis, bconditions, rhs, dirStrategy, intStrategy), m_device(0), m_keepPattern(false), m_rank(0), m_nranks(1) { }
 
     void setDevice(int device) { m_device = device; }
     /// Re-use the sparsity pattern of the previous assemble() (same mesh and boundary conditions; new data): values and
     /// right-hand side only are recomputed and transferred.  refresh() resets it.
     void setKeepPattern(bool keep) { m_keepPattern = keep; }
     virtual void refresh() { Base::refresh(); m_handle.reset(); }
+
+    /// The device-resident matrix of the last assemble() as a gsLinearOperator (and its Jacobi preconditioner) for the
+    /// reference's iterative solvers; valid until the next refresh() / destruction of this assembler.
+    typename gsB200LinearOperator<T>::Ptr deviceOperator() const
+    { return gsB200LinearOperator<T>::make(m_handle.h, m_system.matrix().rows()); }
+    typename gsB200JacobiOp<T>::Ptr devicePreconditioner() const
+    { return gsB200JacobiOp<T>::make(m_handle.h, m_system.matrix().rows()); }
+    /// Multi-GPU: this process integrates share \a rank of \a nranks (one process per GPU; include/gsb200.h "Multi-GPU").
+    /// After assemble() the caller joins the ranks with gsb200_comm_init(deviceHandle(), id) and gsb200_exchange(deviceHandle()).
+    void setRanks(int rank, int nranks) { m_rank = rank; m_nranks = nranks; }
+    gsb200_assembler * deviceHandle() const { return m_handle.h; }
 
     /// Main assembly routine: same contract as gsPoissonAssembler<T>::assemble().
     virtual void assemble()
@@ -73,6 +85,7 @@ public:
                       m_options, GSB200_FORM_POISSON, st);
         const gsPoissonPde<T> & ppde = static_cast<const gsPoissonPde<T>&>(*m_pde_ptr);
         st.pb.nrhs = ppde.numRhs();          // not inferred from the Dirichlet matrix (it is empty for a pure Neumann problem)
+        st.pb.rank = m_rank; st.pb.nranks = m_nranks;
         b200::flattenSource(*ppde.rhs(), st.pb.nrhs, st);
         b200::flattenNeumann(m_pde_ptr->bc(), m_pde_ptr->domain().parDim(), st);   // gsVisitorNeumann on the device
 
@@ -88,6 +101,7 @@ protected:
     using Base::m_ddof;
     int m_device;
     bool m_keepPattern;
+    int m_rank, m_nranks;
     b200::gsB200Handle m_handle;
 };
 

@@ -262,6 +262,7 @@ int gsb200_spmv_device(gsb200_assembler *a, const double *x_dev, double *y_dev);
 /* Diagonal of the stored columns into a DEVICE vector of length nfree (1.0 where the rank stores no diagonal entry):
    the Jacobi preconditioner of the CG consumer. */
 int gsb200_diag_device(gsb200_assembler *a, double *d_dev);
+int gsb200_diag_host(gsb200_assembler *a, double *d);      /* the same into a host vector (gsB200JacobiOp) */
 int gsb200_cg_host(gsb200_assembler *a, const double *b, double *x, int max_iter,
                    double tol, int *iters, double *rel_residual);
 /* The same solver across the ranks of the communicator, all scalars on the device (the host looks at the residual every

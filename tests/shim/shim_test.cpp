@@ -78,6 +78,21 @@ int main(int argc, char **argv)
         D.setKeepPattern(true);         // values-only re-assembly on the kept device pattern
         D.assemble();
         bad += compare("gsPoissonAssemblerB200 re-assembly (values only)", R.matrix(), R.rhs(), D.matrix(), D.rhs());
+        {   // the reference's own CG (gsConjugateGradient.h) on the DEVICE-resident matrix through gsB200LinearOperator
+            gsB200LinearOperator<>::Ptr op = D.deviceOperator();
+            gsConjugateGradient<> cg(op, D.devicePreconditioner());
+            cg.setTolerance(1e-11); cg.setMaxIterations(2000);
+            gsMatrix<> xd; xd.setZero(D.rhs().rows(), 1);
+            cg.solve(D.rhs(), xd);
+            const real_t res = (R.matrix() * xd - R.rhs()).norm() / R.rhs().norm();
+            gsMatrix<> y1, y2 = R.matrix() * R.rhs();
+            op->apply(R.rhs(), y1);
+            const real_t dop = (y1 - y2).norm() / y2.norm();
+            const bool ok = res < 1e-9 && dop < 1e-13;
+            gsInfo << "gsConjugateGradient on gsB200LinearOperator: " << cg.iterations() << " iterations, |K x - b|/|b| = " << res
+                   << ", operator vs reference product " << dop << (ok ? "  OK\n" : "  FAIL\n");
+            bad += ok ? 0 : 1;
+        }
         // the reference's own solver consumes the device-built matrix
         gsSparseSolver<>::CGDiagonal solver; solver.compute(D.matrix());
         gsMatrix<> x = solver.solve(D.rhs());

@@ -123,3 +123,17 @@ def test_values_only_reassembly_with_streamed_column_ranges(emul, name, chunks, 
     assert np.array_equal(again[2], ref[2])          # chunking never changes a bit (every entry has one owner thread)
     ok, msg = R.compare_csc(again, ref, 1e-14)       # rhs: the -K g terms are accumulated atomically
     assert ok, msg
+
+
+@pytest.mark.parametrize("mode", ["1", "3"])
+def test_first_sweep_output_full_and_half_rows(emul, mode, monkeypatch):
+    """GSB200_A1BLK=1: A1 keeps all 2p+1 deltas per function; 3 (default at 3-D p=3): delta >= 0 only, the second sweep reads the
+    others at the mirrored pair (terms.cuh T3SymS2U).  Same matrix either way; also under a workspace cap and split over ranks."""
+    monkeypatch.setenv("GSB200_A1BLK", mode)
+    pb, z = G.load("cube_p3_curved_m4", R.emul_compile)
+    full = R.lib_assemble(emul, pb)
+    G.check_against(full, z, TOL)
+    capped = R.lib_assemble(emul, pb, workspace_limit=8_000_000)
+    assert capped[4].nchunks > 1 and np.array_equal(capped[2], full[2])
+    pb16, z16 = G.load("cube_p3_m16", R.emul_compile)
+    G.check_against(R.lib_assemble(emul, pb16), z16, TOL)
