@@ -142,7 +142,7 @@ GSB_DEVICE void geo_sweep_body(const FusedArgs &A)
     constexpr int TILE = NC * NPT, DS = P1;                        // doubles per tile buffer; delta stride of A1
     constexpr bool FULLG = NOUT % NG == 0;                         // every group has NG outputs
     GSB_SHARED double Dt[NB * TILE];                               // [buffer][component][point][column]
-    GSB_SHARED double tsel[NB * 2 * P1 * P1];                      // the span's basis table: [buffer][values | derivatives][point][slot]
+    GSB_SHARED GSB_ALIGN16 double tsel[NB * 2 * P1 * P1];                      // the span's basis table: [buffer][values | derivatives][point][slot]
     GSB_SHARED double vacc[GSB_FUSE_MAXF][P1][GSB_FUSE_TC];      // load-vector accumulators of group 0, slot order (kept out of the register budget)
     GSB_SHARED unsigned long long full[NB], empty[NB];
     const GeoArgs &G = A.G;
@@ -269,8 +269,17 @@ GSB_DEVICE void geo_sweep_body(const FusedArgs &A)
                 for (int t = 0; t < P1; ++t) {
                     const double v = pv[t * TC];
                     double bo[P1], bp[P1];
+#ifndef GSB200_EMULATE
+                    if constexpr (P1 % 2 == 0) {      // table rows are 16-byte aligned: half as many shared-memory instructions
+                        const double2 *pa2 = reinterpret_cast<const double2 *>(pa + t * P1), *pb2 = reinterpret_cast<const double2 *>(pb + t * P1);
 #pragma unroll
-                    for (int k = 0; k < P1; ++k) { bo[k] = pa[t * P1 + k]; bp[k] = pb[t * P1 + k]; }
+                        for (int k = 0; k < P1 / 2; ++k) { const double2 u = pa2[k], w = pb2[k]; bo[2 * k] = u.x; bo[2 * k + 1] = u.y; bp[2 * k] = w.x; bp[2 * k + 1] = w.y; }
+                    } else
+#endif
+                    {
+#pragma unroll
+                        for (int k = 0; k < P1; ++k) { bo[k] = pa[t * P1 + k]; bp[k] = pb[t * P1 + k]; }
+                    }
 #pragma unroll
                     for (int a = 0; a < P1; ++a) {
                         const double z = bo[a] * v;

@@ -178,11 +178,13 @@ GSB_DEVICE void geo_finish(const GeoArgs &A, i64 id, const int (&ql)[DIM], const
 #define GSB_GEO_MAXA 48
 #ifndef GSB200_EMULATE
 #define GSB_SHARED __shared__
+#define GSB_ALIGN16 __align__(16)
 #define GSB_SYNCTHREADS() __syncthreads()
 #define GSB_COOP_FIRST ((int)threadIdx.x)
 #define GSB_COOP_STEP ((int)blockDim.x)
 #else
 #define GSB_SHARED
+#define GSB_ALIGN16
 #define GSB_SYNCTHREADS()
 #define GSB_COOP_FIRST 0
 #define GSB_COOP_STEP 1

@@ -480,8 +480,11 @@ static int assemble_pass(gsb200_assembler *a)
         const bool s23 = fused && dim == 3 && a1_env < 0 && d1.q == d1.p + 1 && dL.q == dL.p + 1 && d1.p == dL.p && s23_available(kind, d1.p + 1);
         // A1 stored for delta >= 0 only, A1[o][q1][e2][i0][d0 = 0..p][t] (terms.cuh T3SymS2U): symmetric 3-D forms at degree 3 with the
         // 4-point rule (a span's points fill a 32-byte sector); the second sweep reads delta < 0 at the mirrored pair, a few rows away
-        // in the same (q1, e2) block.  GSB200_A1BLK=1 keeps the full rows.
-        const bool a1_half = fused && !s23 && dim == 3 && kind == KIND_SYM && (a1_env < 0 || a1_env == 3) && d0.p == 3 && d1.p == 3 && d1.q == 4 && dL.q == 4;
+        // in the same (q1, e2) block.
+        // Opt-in (GSB200_A1BLK=3): measured on B200 at config 2 the first sweep does not get faster (5.4 ms either way: it is bound by
+        // instruction issue and shared-memory traffic, not by its stores) and the second sweep loses 1.1 ms (6.0 vs 4.9 ms: the mirrored
+        // 32-byte pieces double the L2 requests per warp): profiles/r02_a1_half_experiment.txt
+        const bool a1_half = fused && !s23 && dim == 3 && kind == KIND_SYM && a1_env == 3 && d0.p == 3 && d1.p == 3 && d1.q == 4 && dL.q == 4;
         const i64 A1I0 = a1_half ? (i64)d0.nfun * (d0.p + 1) : NI0;        // (function, stored delta) pairs of direction 0
         const i64 a1_pad = a1_half ? 64 : 0;
         const int nfv = std::max(nf, 1);

@@ -11,10 +11,15 @@ for r in rows[hi + 1:]:
     d[r[mn]] = float(r[mv].replace(',', ''))
 L = list(launch.values())
 # one assembly = from a geometry kernel to the launch before the next geometry kernel
-starts = [i for i, d in enumerate(L) if 'k_geometry' in d['name'] or 'gsb_jit_geo' in d['name']]
+# round 2: the geometry kernel is fused into the first sweep (k_geo_sweep / its NVRTC build gsb_jit_geo): that launch opens an assembly
+fused = any('k_geo_sweep' in d['name'] for d in L)
+def opens(d): return 'k_geometry' in d['name'] or 'gsb_jit_geo' in d['name'] or 'k_geo_sweep' in d['name']
+starts = [i for i, d in enumerate(L) if opens(d)]
 seq = L[starts[-1]:]
+seq = [d for d in seq if not any(t in d['name'] for t in ('k_spmv', 'k_cg_', 'k_diag', 'k_col_extent', 'k_spmv_classify'))]
 def stage(d):
     n = d['name']
+    if fused and opens(d): return 'sweep0'
     if 'k_geometry' in n or 'gsb_jit_geo' in n: return 'geometry'
     if 'k_vsweep' in n: return 'rhs'
     if 'TLast' in n or ', true' in n or ', 1, ' in n and 'TMass' in n: return 'sweep_last'

@@ -333,7 +333,7 @@ def test_determinism_with_inhomogeneous_dirichlet_data(lib):
 
 @pytest.mark.parametrize("mode", ["1", "3"])
 def test_first_sweep_output_full_and_half_rows(lib, mode, monkeypatch):
-    """GSB200_A1BLK=1: the first sweep stores all 2p+1 deltas per function; 3 (default at 3-D degree 3): delta >= 0 only and the second
+    """GSB200_A1BLK=1: the first sweep stores all 2p+1 deltas per function; 3 (opt-in, 3-D degree 3; measured slower, profiles/r02_a1_half_experiment.txt): delta >= 0 only and the second
     sweep reads the rest at the mirrored pair (43 % less HBM traffic for A1).  Same matrix either way, also chunked."""
     monkeypatch.setenv("GSB200_A1BLK", mode)
     pb, z = G.load("cube_p3_curved_m4", g.expr_compile)

@@ -127,7 +127,7 @@ def test_values_only_reassembly_with_streamed_column_ranges(emul, name, chunks, 
 
 @pytest.mark.parametrize("mode", ["1", "3"])
 def test_first_sweep_output_full_and_half_rows(emul, mode, monkeypatch):
-    """GSB200_A1BLK=1: A1 keeps all 2p+1 deltas per function; 3 (default at 3-D p=3): delta >= 0 only, the second sweep reads the
+    """GSB200_A1BLK=1: A1 keeps all 2p+1 deltas per function; 3 (opt-in, 3-D p=3): delta >= 0 only, the second sweep reads the
     others at the mirrored pair (terms.cuh T3SymS2U).  Same matrix either way; also under a workspace cap and split over ranks."""
     monkeypatch.setenv("GSB200_A1BLK", mode)
     pb, z = G.load("cube_p3_curved_m4", R.emul_compile)
