@@ -199,6 +199,21 @@ class DeviceAssembler:
                                        C.byref(it), C.byref(res)))
         return x, it.value, res.value
 
+    def field_norms(self, u: np.ndarray, exact=None, exact_grad=None) -> np.ndarray:
+        """gsb200_field_norms: [int (u_h-u_ex)^2, int |grad(u_h-u_ex)|^2, int u_h^2, int |grad u_h|^2] of the discrete field with free
+        coefficients u (exact / exact_grad: CompiledProgram / list of dim CompiledPrograms, or None)."""
+        u = np.ascontiguousarray(u, dtype=np.float64).ravel()
+        def prog(cp):
+            return capi.Program(len(cp.ops), cp.ops.ctypes.data_as(_ip), len(cp.consts), cp.consts.ctypes.data_as(_dp))
+        ex = C.byref(prog(exact)) if exact is not None else None
+        eg = None
+        if exact_grad is not None:
+            arr = (capi.Program * len(exact_grad))(*[prog(cp) for cp in exact_grad])
+            eg = arr
+        out = np.zeros(4)
+        self._check(self.lib.gsb200_field_norms(self._h, u.ctypes.data_as(_dp), ex, eg, out.ctypes.data_as(_dp)))
+        return out
+
     def cg_info(self):
         """(device ms of the last solve's iteration loop, halo-exchange mode?)"""
         ms, h = C.c_double(0), C.c_int32(0)

@@ -251,6 +251,102 @@ GSB_GLOBAL void k_col_extent(int n, const i64 *ptr, const int *idx, int *out)
 #endif
 }
 
+// ------------------------------------------------------------------ f4: norms of a discrete field (gsExprEvaluator::integral)
+// One thread per quadrature point of a patch: geometry (point, Jacobian) by the tensor sum over the geometry's own basis, the discrete
+// field and its parametric gradient over the (p+1)^d active functions (free coefficients from u, eliminated ones from `fixed`),
+// physical gradient through the inverse Jacobian; out[0..3] += w |det J| { (u_h - u_ex)^2, |grad(u_h - u_ex)|^2, u_h^2, |grad u_h|^2 }.
+// Replaces ev.integral((u_ex - u_sol).sqNorm() * meas(G)) and ev.integral((igrad(u_ex) - igrad(u_sol, G)).sqNorm() * meas(G))
+// (examples/poisson2_example.cpp:174-177, gsExprEvaluator.h:152-230, 461-518).
+struct NormArgs {
+    int qn[3];
+    const double2 *gtab[3]; const int *gfirst[3]; int pg1[3], ngeo[3];
+    const double *hpt[3]; const double *gwp[3];
+    const double *coefs; const double *weights; i64 ngeo_total;
+    const double2 *tabl[3]; const int *first[3]; int p1[3], q[3], nfun[3];
+    const int *dofmap; const double *u; const double *fixed; int nfree;
+    int has_exact, has_grad; DevProgram ex, exg[3];
+    double *out;
+};
+template <int DIM>
+GSB_GLOBAL void k_field_norms(const NormArgs A)
+{
+    i64 total = 1; for (int k = 0; k < DIM; ++k) total *= A.qn[k];
+    const i64 id = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    if (id < total) {
+        int ql[3] = {0, 0, 0}; { i64 r = id; for (int k = 0; k < DIM; ++k) { ql[k] = (int)(r % A.qn[k]); r /= A.qn[k]; } }
+        // ---- geometry
+        double W = 0.0, dW[3] = {0, 0, 0}, xn[3] = {0, 0, 0}, dxn[3][3];
+        for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) dxn[a][c] = 0.0;
+        int cnt[3] = {0, 0, 0}, gf[3] = {0, 0, 0};
+        for (int k = 0; k < DIM; ++k) gf[k] = A.gfirst[k][ql[k]];
+        for (;;) {
+            i64 idx = 0; double v = 1.0, dv[3] = {0, 0, 0}; double2 b[3];
+            for (int k = DIM - 1; k >= 0; --k) idx = idx * A.ngeo[k] + (gf[k] + cnt[k]);
+            for (int k = 0; k < DIM; ++k) { b[k] = A.gtab[k][(i64)ql[k] * A.pg1[k] + cnt[k]]; v *= b[k].x; }
+            for (int k = 0; k < DIM; ++k) { dv[k] = b[k].y; for (int i = 0; i < DIM; ++i) if (i != k) dv[k] *= b[i].x; }
+            const double wt = A.weights ? A.weights[idx] : 1.0;
+            W += wt * v;
+            for (int k = 0; k < DIM; ++k) dW[k] += wt * dv[k];
+            for (int c = 0; c < DIM; ++c) {
+                const double C = A.coefs[(i64)c * A.ngeo_total + idx];
+                xn[c] += wt * v * C;
+                for (int k = 0; k < DIM; ++k) dxn[k][c] += wt * dv[k] * C;
+            }
+            int k = 0;
+            while (k < DIM && ++cnt[k] >= A.pg1[k]) { cnt[k] = 0; ++k; }
+            if (k == DIM) break;
+        }
+        double x[3] = {0, 0, 0}, Jt[3][3];           // Jt[a][c] = d x_c / d xi_a
+        for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) Jt[a][c] = a == c ? 1.0 : 0.0;
+        for (int c = 0; c < DIM; ++c) { x[c] = xn[c] / W; for (int a = 0; a < DIM; ++a) Jt[a][c] = (dxn[a][c] * W - xn[c] * dW[a]) / (W * W); }
+        // ---- discrete field and its parametric gradient
+        double uh = 0.0, du[3] = {0, 0, 0};
+        int e[3] = {0, 0, 0}, t[3] = {0, 0, 0}, f0[3] = {0, 0, 0};
+        for (int k = 0; k < DIM; ++k) { e[k] = ql[k] / A.q[k]; t[k] = ql[k] - e[k] * A.q[k]; f0[k] = A.first[k][e[k]]; }
+        for (int k = 0; k < 3; ++k) cnt[k] = 0;
+        for (;;) {
+            i64 li = 0; double v = 1.0, dv[3] = {0, 0, 0}; double2 b[3];
+            for (int k = DIM - 1; k >= 0; --k) li = li * A.nfun[k] + (f0[k] + cnt[k]);
+            for (int k = 0; k < DIM; ++k) { b[k] = A.tabl[k][(i64)ql[k] * A.p1[k] + cnt[k]]; v *= b[k].x; }
+            for (int k = 0; k < DIM; ++k) { dv[k] = b[k].y; for (int i = 0; i < DIM; ++i) if (i != k) dv[k] *= b[i].x; }
+            const int g = A.dofmap[li];
+            const double cf = g < A.nfree ? A.u[g] : (A.fixed ? A.fixed[g - A.nfree] : 0.0);
+            uh = fma(cf, v, uh);
+            for (int k = 0; k < DIM; ++k) du[k] = fma(cf, dv[k], du[k]);
+            int k = 0;
+            while (k < DIM && ++cnt[k] >= A.p1[k]) { cnt[k] = 0; ++k; }
+            if (k == DIM) break;
+        }
+        // ---- physical gradient: Jt g = du  (cofactor inverse)
+        double det, gr[3] = {0, 0, 0};
+        if (DIM == 2) {
+            det = Jt[0][0] * Jt[1][1] - Jt[0][1] * Jt[1][0];
+            gr[0] = (Jt[1][1] * du[0] - Jt[0][1] * du[1]) / det;
+            gr[1] = (-Jt[1][0] * du[0] + Jt[0][0] * du[1]) / det;
+        } else {
+            const double c00 = Jt[1][1] * Jt[2][2] - Jt[1][2] * Jt[2][1], c01 = Jt[1][2] * Jt[2][0] - Jt[1][0] * Jt[2][2], c02 = Jt[1][0] * Jt[2][1] - Jt[1][1] * Jt[2][0];
+            det = Jt[0][0] * c00 + Jt[0][1] * c01 + Jt[0][2] * c02;
+            const double c10 = Jt[0][2] * Jt[2][1] - Jt[0][1] * Jt[2][2], c11 = Jt[0][0] * Jt[2][2] - Jt[0][2] * Jt[2][0], c12 = Jt[0][1] * Jt[2][0] - Jt[0][0] * Jt[2][1];
+            const double c20 = Jt[0][1] * Jt[1][2] - Jt[0][2] * Jt[1][1], c21 = Jt[0][2] * Jt[1][0] - Jt[0][0] * Jt[1][2], c22 = Jt[0][0] * Jt[1][1] - Jt[0][1] * Jt[1][0];
+            // inverse(Jt)[r][c] = cofactor[c][r] / det
+            gr[0] = (c00 * du[0] + c10 * du[1] + c20 * du[2]) / det;
+            gr[1] = (c01 * du[0] + c11 * du[1] + c21 * du[2]) / det;
+            gr[2] = (c02 * du[0] + c12 * du[1] + c22 * du[2]) / det;
+        }
+        double w = fabs(det);
+        for (int k = 0; k < DIM; ++k) w *= A.hpt[k][ql[k]] * A.gwp[k][ql[k]];
+        const double ue = A.has_exact ? program_eval(A.ex, x[0], x[1], x[2]) : 0.0;
+        double ge2 = 0.0, g2 = 0.0;
+        for (int c = 0; c < DIM; ++c) {
+            const double gx = A.has_grad ? program_eval(A.exg[c], x[0], x[1], x[2]) : 0.0;
+            ge2 = fma(gr[c] - gx, gr[c] - gx, ge2); g2 = fma(gr[c], gr[c], g2);
+        }
+        s0 = w * (uh - ue) * (uh - ue); s1 = w * ge2; s2 = w * uh * uh; s3 = w * g2;
+    }
+    cg_block_add(s0, A.out + 0); cg_block_add(s1, A.out + 1); cg_block_add(s2, A.out + 2); cg_block_add(s3, A.out + 3);
+}
+
 // ------------------------------------------------------------------ SpMV set-up: offset tables of the regular columns
 static int spmv_prepare(gsb200_assembler *a)
 {
@@ -636,6 +732,43 @@ int gsb200_cg_host(gsb200_assembler *a, const double *b, double *x, int max_iter
 {
     if (!b || !x) return GSB200_EINVAL;
     return gsb200_cg_solve(a, b, x, max_iter, tol, 1, iters, rel_residual);
+}
+
+int gsb200_field_norms(gsb200_assembler *a, const double *u_free, const gsb200_program *exact, const gsb200_program *exact_grad, double *out4)
+{
+    if (!a || !u_free || !out4) { set_error("field_norms: null argument"); return GSB200_EINVAL; }
+    if (a->ncomp != 1) { set_error("field norms: scalar spaces only"); return GSB200_EUNSUPPORTED; }
+    GSB_TRY(select_device(a->device));
+    const int n = a->nfree; stream_t s = a->stream;
+    double *d_u = 0, *d_out = 0;
+    GSB_TRY(dev_malloc((void **)&d_u, sizeof(double) * (size_t)(n + 1)));
+    GSB_TRY(dev_malloc((void **)&d_out, 4 * sizeof(double)));
+    int rc = dev_h2d(d_u, u_free, sizeof(double) * (size_t)n, s);
+    if (!rc) rc = dev_memset(d_out, 0, 4 * sizeof(double), s);
+    NormArgs A; memset(&A, 0, sizeof A);
+    const size_t nbuf0 = a->prog_bufs.size();
+    if (!rc && exact) { rc = upload_device_program(a, *exact, &A.ex); A.has_exact = 1; }
+    if (!rc && exact_grad) { for (int c = 0; c < a->dim && !rc; ++c) rc = upload_device_program(a, exact_grad[c], &A.exg[c]); A.has_grad = 1; }
+    for (size_t ip = 0; ip < a->patches.size() && !rc; ++ip) {
+        const PatchDev &P = a->patches[ip];
+        i64 npt = 1;
+        for (int k = 0; k < a->dim; ++k) {
+            const Dir1D &d = P.dir[k];
+            A.qn[k] = d.Q; A.gtab[k] = d.d_gtab; A.gfirst[k] = d.d_gfirst; A.pg1[k] = d.pg1; A.ngeo[k] = d.ngeo; A.hpt[k] = d.d_hpt; A.gwp[k] = d.d_gwp;
+            A.tabl[k] = d.d_tabl; A.first[k] = d.d_first; A.p1[k] = d.p + 1; A.q[k] = d.q; A.nfun[k] = d.nfun;
+            npt *= d.Q;
+        }
+        A.coefs = P.d_coefs; A.weights = P.d_weights; A.ngeo_total = P.ngeo_total;
+        A.dofmap = P.d_dofmap; A.u = d_u; A.fixed = a->d_fixed; A.nfree = n; A.out = d_out;
+        if (a->dim == 2) GSB_LAUNCH(k_field_norms<2>, dim3((unsigned)((npt + 127) / 128)), dim3(128), s, A);
+        else GSB_LAUNCH(k_field_norms<3>, dim3((unsigned)((npt + 127) / 128)), dim3(128), s, A);
+    }
+    if (!rc) rc = dev_d2h(out4, d_out, 4 * sizeof(double), s);
+    if (!rc && !exact) out4[0] = out4[2];
+    if (!rc && !exact_grad) out4[1] = exact ? -1.0 : out4[3];
+    while (a->prog_bufs.size() > nbuf0) { dev_free(a->prog_bufs.back()); a->prog_bufs.pop_back(); }
+    dev_free(d_u); dev_free(d_out);
+    return rc;
 }
 
 int gsb200_cg_info(const gsb200_assembler *a, double *loop_ms, int32_t *halo_exchange)

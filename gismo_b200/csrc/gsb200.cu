@@ -941,6 +941,26 @@ static int d2h_any(gsb200_assembler *a, void *dst, const void *src, size_t bytes
 
 } // namespace gsb
 
+namespace gsb {
+// a reverse-polish program (source term, boundary data, exact solution) on the device; short ones ride inside the kernel arguments
+static int upload_device_program(gsb200_assembler *a, const gsb200_program &pr, DevProgram *out)
+{
+    if (pr.nops < 1 || pr.nops > GSB200_PROGRAM_MAX_OPS || !pr.ops) { set_error("source/boundary program has bad length %d", pr.nops); return GSB200_EINVAL; }
+    std::vector<int> ops(pr.ops, pr.ops + pr.nops); std::vector<double> cs(pr.consts, pr.consts + pr.nconsts);
+    int *d_ops = 0; double *d_cs = 0;
+    GSB_TRY(upload(&d_ops, ops, a->stream)); a->prog_bufs.push_back(d_ops);
+    GSB_TRY(upload(&d_cs, cs, a->stream)); a->prog_bufs.push_back(d_cs);
+    DevProgram dp; memset(&dp, 0, sizeof dp); dp.ops = d_ops; dp.consts = d_cs; dp.nops = pr.nops;
+    if (pr.nops <= GSB_INLINE_OPS && pr.nconsts <= GSB_INLINE_CONSTS) {
+        dp.inl = 1;
+        for (int k = 0; k < pr.nops; ++k) dp.iops[k] = (signed char)pr.ops[k];
+        for (int k = 0; k < pr.nconsts; ++k) dp.iconsts[k] = pr.consts[k];
+    }
+    *out = dp;
+    return 0;
+}
+} // namespace gsb
+
 #include "consumer.cuh"
 
 // ====================================================================== C ABI
@@ -1073,21 +1093,7 @@ int gsb200_create(const gsb200_problem *pb, int device, gsb200_assembler **out)
         }
     }
     if (!rc && pb->fixed) { std::vector<double> fx(pb->fixed, pb->fixed + (size_t)pb->nfixed * pb->nrhs); rc = upload(&a->d_fixed, fx, a->stream); }
-    auto upload_program = [&](const gsb200_program &pr, DevProgram *out) -> int {
-        if (pr.nops < 1 || pr.nops > GSB200_PROGRAM_MAX_OPS || !pr.ops) { set_error("source/boundary program has bad length %d", pr.nops); return GSB200_EINVAL; }
-        std::vector<int> ops(pr.ops, pr.ops + pr.nops); std::vector<double> cs(pr.consts, pr.consts + pr.nconsts);
-        int *d_ops = 0; double *d_cs = 0;
-        GSB_TRY(upload(&d_ops, ops, a->stream)); a->prog_bufs.push_back(d_ops);
-        GSB_TRY(upload(&d_cs, cs, a->stream)); a->prog_bufs.push_back(d_cs);
-        DevProgram dp; memset(&dp, 0, sizeof dp); dp.ops = d_ops; dp.consts = d_cs; dp.nops = pr.nops;
-        if (pr.nops <= GSB_INLINE_OPS && pr.nconsts <= GSB_INLINE_CONSTS) {
-            dp.inl = 1;
-            for (int k = 0; k < pr.nops; ++k) dp.iops[k] = (signed char)pr.ops[k];
-            for (int k = 0; k < pr.nconsts; ++k) dp.iconsts[k] = pr.consts[k];
-        }
-        *out = dp;
-        return 0;
-    };
+    auto upload_program = [&](const gsb200_program &pr, DevProgram *out) -> int { return upload_device_program(a, pr, out); };
     if (!rc && pb->rhs_kind == GSB200_RHS_PROGRAM) {
         const int np = pb->form == GSB200_FORM_ELASTICITY ? pb->ncomp : pb->nrhs;
         if (!pb->rhs_programs) { set_error("rhs_kind=PROGRAM but no programs"); rc = GSB200_EINVAL; }

@@ -279,6 +279,15 @@ int gsb200_cg_info(const gsb200_assembler *a, double *loop_ms, int32_t *halo_exc
 /* Columns whose row set is a translate of a reference stencil (the SpMV reads 8 instead of 12 bytes per entry there). */
 int gsb200_spmv_info(gsb200_assembler *a, int64_t *regular_columns, int32_t *tables);
 
+/* f4: integrals of a discrete scalar field u_h (free coefficients `u_free`, eliminated ones from the problem's
+   `fixed` / gsb200_set_fixed) over the whole domain, with the quadrature rule of the assembly:
+     out4[0] = int (u_h - u_ex)^2      out4[1] = int |grad(u_h - u_ex)|^2      out4[2] = int u_h^2      out4[3] = int |grad u_h|^2
+   = ev.integral((u_ex - u_sol).sqNorm() * meas(G)), ev.integral((igrad(u_ex) - igrad(u_sol, G)).sqNorm() * meas(G)), ...
+   (gsExprEvaluator.h:152-230, examples/poisson2_example.cpp:174-177).  `exact` may be NULL (out4[0] = out4[2]); `exact_grad`
+   = dim programs for the components of grad u_ex, or NULL (out4[1] = -1: not available). */
+int gsb200_field_norms(gsb200_assembler *a, const double *u_free, const gsb200_program *exact,
+                       const gsb200_program *exact_grad, double *out4);
+
 /* Compile an exprtk-style source term ("2*pi^2*sin(pi*x)*sin(pi*y)") into a
    reverse-polish program.  Buffers are caller-allocated; on success *nops/*nconsts
    hold the used lengths.  Supported: + - * / ^, unary -, parentheses, x y z, pi,

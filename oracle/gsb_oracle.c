@@ -522,3 +522,107 @@ int gsbo_basis_eval(const double *knots, int nknots, int p, double u, int *first
     free(k.span);
     return 0;
 }
+
+/* ------------------------------------------------------------------ */
+/* Norm integrals of a discrete scalar field (test infrastructure, like everything in this file): element loop with the
+ * assembly's Gauss rule, restating ev.integral((u_ex - u_sol).sqNorm() * meas(G)) and
+ * ev.integral((igrad(u_ex) - igrad(u_sol, G)).sqNorm() * meas(G)) of examples/poisson2_example.cpp:174-177
+ * (gsExprEvaluator.h:152-230: the element-wise quadrature loop; gsExpressions.h solution / igrad evaluation).
+ * out4 = { int (u_h-u_ex)^2, int |grad(u_h-u_ex)|^2, int u_h^2, int |grad u_h|^2 }; exact / exact_grad may be NULL. */
+int gsbo_field_norms(const gsb200_problem *pb, const double *u_free, const gsb200_program *exact,
+                     const gsb200_program *exact_grad, double *out4)
+{
+    if (!pb || !u_free || !out4 || pb->ncomp != 1) { snprintf(g_err, sizeof g_err, "field norms: bad arguments"); return -1; }
+    const int d = pb->patches[0].space.dim, N = pb->nfree;
+    for (int k = 0; k < 4; ++k) out4[k] = 0.0;
+    for (int ip = 0; ip < pb->npatches; ++ip) {
+        const gsb200_patch *pa = &pb->patches[ip];
+        kv1d ks[3], kg[3];
+        int q[3], ngeo = 1;
+        double gn[3][MAXQ], gw[3][MAXQ];
+        for (int k = 0; k < d; ++k) {
+            if (kv_init(&ks[k], pa->space.knots[k], pa->space.nknots[k], pa->space.degree[k]) ||
+                kv_init(&kg[k], pa->geo.knots[k], pa->geo.nknots[k], pa->geo.degree[k])) { snprintf(g_err, sizeof g_err, "bad knot vector"); return -1; }
+            q[k] = num_nodes(pb->quA, pb->quB, ks[k].p);
+            gsbo_gauss(q[k], gn[k], gw[k]);
+            ngeo *= kg[k].nfun;
+        }
+        int el[3] = {0, 0, 0};
+        for (;;) {                                   /* elements */
+            int t[3] = {0, 0, 0};
+            for (;;) {                               /* quadrature points of the element */
+                double u[3], w = 1.0, sv[3][MAXP + 1], sd[3][MAXP + 1], gv[3][MAXP + 1], gd[3][MAXP + 1];
+                int s[3], sg[3];
+                for (int k = 0; k < d; ++k) {
+                    s[k] = ks[k].span[el[k]];
+                    const double lo = ks[k].kn[s[k]], h = (ks[k].kn[s[k] + 1] - lo) / 2.0;
+                    u[k] = h * (gn[k][t[k]] + 1.0) + lo; w *= h * gw[k][t[k]];
+                    bspline_ders(ks[k].kn, ks[k].p, s[k], u[k], sv[k], sd[k]);
+                    sg[k] = kv_find(&kg[k], u[k]);
+                    bspline_ders(kg[k].kn, kg[k].p, sg[k], u[k], gv[k], gd[k]);
+                }
+                /* geometry */
+                double W = 0.0, dW[3] = {0, 0, 0}, xn[3] = {0, 0, 0}, dxn[9] = {0}, x[3] = {0, 0, 0}, Jt[9], J[9], Jinv[9];
+                int a[3] = {0, 0, 0};
+                for (;;) {
+                    int idx = 0;
+                    for (int k = d - 1; k >= 0; --k) idx = idx * kg[k].nfun + (sg[k] - kg[k].p + a[k]);
+                    double v = 1.0, dv[3];
+                    for (int k = 0; k < d; ++k) v *= gv[k][a[k]];
+                    for (int k = 0; k < d; ++k) { dv[k] = gd[k][a[k]]; for (int i = 0; i < d; ++i) if (i != k) dv[k] *= gv[i][a[i]]; }
+                    const double wt = pa->geo_weights ? pa->geo_weights[idx] : 1.0;
+                    W += wt * v;
+                    for (int k = 0; k < d; ++k) dW[k] += wt * dv[k];
+                    for (int c = 0; c < d; ++c) {
+                        const double C = pa->geo_coefs[(size_t)c * ngeo + idx];
+                        xn[c] += wt * v * C;
+                        for (int k = 0; k < d; ++k) dxn[k * d + c] += wt * dv[k] * C;
+                    }
+                    int k = 0;
+                    while (k < d && ++a[k] > kg[k].p) { a[k] = 0; ++k; }
+                    if (k == d) break;
+                }
+                for (int c = 0; c < d; ++c) { x[c] = xn[c] / W; for (int k = 0; k < d; ++k) Jt[k * d + c] = (dxn[k * d + c] * W - xn[c] * dW[k]) / (W * W); }
+                for (int r = 0; r < d; ++r) for (int c = 0; c < d; ++c) J[r * d + c] = Jt[c * d + r];
+                const double det = inv_det(J, d, Jinv);
+                /* discrete field */
+                double uh = 0.0, du[3] = {0, 0, 0};
+                a[0] = a[1] = a[2] = 0;
+                for (;;) {
+                    size_t li = 0;
+                    for (int k = d - 1; k >= 0; --k) li = li * (size_t)ks[k].nfun + (size_t)(s[k] - ks[k].p + a[k]);
+                    double v = 1.0, dv[3];
+                    for (int k = 0; k < d; ++k) v *= sv[k][a[k]];
+                    for (int k = 0; k < d; ++k) { dv[k] = sd[k][a[k]]; for (int i = 0; i < d; ++i) if (i != k) dv[k] *= sv[i][a[i]]; }
+                    const int g = pa->dofmap[li];
+                    const double cf = g < N ? u_free[g] : (pb->fixed ? pb->fixed[g - N] : 0.0);
+                    uh += cf * v;
+                    for (int k = 0; k < d; ++k) du[k] += cf * dv[k];
+                    int k = 0;
+                    while (k < d && ++a[k] > ks[k].p) { a[k] = 0; ++k; }
+                    if (k == d) break;
+                }
+                double gr[3] = {0, 0, 0};                 /* J^{-T} du */
+                for (int c = 0; c < d; ++c) for (int k = 0; k < d; ++k) gr[c] += Jinv[k * d + c] * du[k];
+                const double weight = w * fabs(det);
+                const double ue = exact ? prog_eval(exact, x) : 0.0;
+                double ge2 = 0.0, g2 = 0.0;
+                for (int c = 0; c < d; ++c) {
+                    const double gx = exact_grad ? prog_eval(&exact_grad[c], x) : 0.0;
+                    ge2 += (gr[c] - gx) * (gr[c] - gx); g2 += gr[c] * gr[c];
+                }
+                out4[0] += weight * (uh - ue) * (uh - ue); out4[1] += weight * ge2; out4[2] += weight * uh * uh; out4[3] += weight * g2;
+                int k = 0;
+                while (k < d && ++t[k] >= q[k]) { t[k] = 0; ++k; }
+                if (k == d) break;
+            }
+            int k = 0;
+            while (k < d && ++el[k] >= ks[k].nel) { el[k] = 0; ++k; }
+            if (k == d) break;
+        }
+        for (int k = 0; k < d; ++k) { free(ks[k].span); free(kg[k].span); }
+    }
+    if (!exact) out4[0] = out4[2];
+    if (!exact_grad) out4[1] = exact ? -1.0 : out4[3];
+    return 0;
+}

@@ -46,6 +46,8 @@ typedef struct gsref_config {
     const char *neu[3];
     int32_t degree_dir[3]; /* >0: degree of the solution basis in that direction (mixed degrees), applied after setDegree */
     int32_t nrhs;          /* path 0, form 0: right-hand-side columns (components of the source function), 0/1 = one */
+    const char *exact;     /* path 1, form 0: exact solution; the system is solved (SimplicialLDLT) and the error norms are integrated
+                              as in examples/poisson2_example.cpp:174-177 (gsExprEvaluator::integral)                  */
 } gsref_config;
 
 struct gsref_result {
@@ -57,6 +59,8 @@ struct gsref_result {
     std::vector<int32_t> neumann;   // (patch, side) pairs
     std::vector<std::string> rhs_text, neu_text;
     std::string err;
+    gsMatrix<real_t> sol;           // solution coefficients (free DOFs) when `exact` was given
+    double norms[4];                // int (u_ex-u_h)^2, int |grad(u_ex-u_h)|^2, int u_h^2, int |grad u_h|^2
 };
 
 static std::string g_err;
@@ -215,6 +219,19 @@ void *gsref_run(const gsref_config *cfg)
             R->K = A.matrix();
             R->rhs = A.rhs();
             opt = A.options();
+            if (c.exact && c.form == 0) {
+                gsSparseSolver<real_t>::SimplicialLDLT solver;
+                solver.compute(A.matrix());
+                R->sol = solver.solve(A.rhs());
+                gsFunctionExpr<real_t> ex(c.exact, d);
+                gsExprEvaluator<real_t> ev(A);
+                auto u_sol = A.getSolution(u, R->sol);
+                auto u_ex = ev.getVariable(ex, G);
+                R->norms[0] = ev.integral((u_ex - u_sol).sqNorm() * meas(G));
+                R->norms[1] = ev.integral((igrad(u_ex) - igrad(u_sol, G)).sqNorm() * meas(G));
+                R->norms[2] = ev.integral(u_sol.sqNorm() * meas(G));
+                R->norms[3] = ev.integral(igrad(u_sol, G).sqNorm() * meas(G));
+            }
             b200::flatten(mp, mb, u.mapper(), ncomp, u.fixedPart(), opt,
                           c.form == 0 ? GSB200_FORM_POISSON : (c.form == 2 ? GSB200_FORM_MASS : GSB200_FORM_ELASTICITY), R->flat);
             R->flat.pb.coef[0] = c.lambda; R->flat.pb.coef[1] = c.mu;
@@ -315,6 +332,16 @@ int gsref_uniform_refine(const double *knots, int nknots, int degree, int numKno
     std::copy(kv.data(), kv.data() + kv.size(), out);
     *nout = (int)kv.size();
     return 0;
+}
+
+/* solution coefficients (nfree) and the four norm integrals of a run with `exact`; returns 0 if there are none */
+int gsref_solution(void *h, double *sol, double *norms4)
+{
+    gsref_result *R = static_cast<gsref_result *>(h);
+    if (R->sol.size() == 0) return 0;
+    std::copy(R->sol.data(), R->sol.data() + R->sol.size(), sol);
+    for (int k = 0; k < 4; ++k) norms4[k] = R->norms[k];
+    return (int)R->sol.size();
 }
 
 /* which = 0: source-term component idx, 1: Neumann data component idx; returns the length (0 = none) */

@@ -51,6 +51,16 @@ FULL = {
     "mass_sq_p2_visitor": dict(dim=2, degree=2, nelem=6, geometry=1, path=0, form=2, rhs=["1+x*y"]),
     "mass_cube_p3_curved_expr": dict(dim=3, degree=3, nelem=2, geometry=1, path=1, form=2, rhs=["x+z"], dirichlet=["x*y"], dir_values=101),
     "mass_grid2x2_p2_expr": dict(dim=2, degree=2, nelem=3, geometry=3, grid=(2, 2, 1), path=1, form=2, rhs=["x"], dirichlet=["1+y"], dir_values=101),
+    # solved Poisson problems with the reference's error-norm integrals (gsExprEvaluator::integral, poisson2_example.cpp:174-177):
+    # the fixture carries the solution coefficients and int (u_ex-u_h)^2, int |grad(u_ex-u_h)|^2, int u_h^2, int |grad u_h|^2
+    "norms_sq_p2_curved": dict(dim=2, degree=2, nelem=6, geometry=1, path=1, rhs=[PI2], dirichlet=["sin(pi*x)*sin(pi*y)"], dir_values=101,
+                               exact="sin(pi*x)*sin(pi*y)"),
+    "norms_cube_p3_curved": dict(dim=3, degree=3, nelem=2, geometry=1, path=1, rhs=[PI3], dirichlet=["sin(pi*x)*sin(pi*y)*sin(pi*z)"], dir_values=101,
+                                 exact="sin(pi*x)*sin(pi*y)*sin(pi*z)"),
+    "norms_annulus_nurbs_p3": dict(dim=2, degree=3, nelem=5, geometry=2, path=1, rhs=["-2*x-2*y"], dirichlet=["x^2*y+y^2*x"], dir_values=102,
+                                   exact="x^2*y+y^2*x"),
+    "norms_grid2x2_p2": dict(dim=2, degree=2, nelem=4, geometry=3, grid=(2, 2, 1), path=1, rhs=[PI2], dirichlet=["sin(pi*x)*sin(pi*y)"], dir_values=101,
+                             exact="sin(pi*x)*sin(pi*y)"),
     # mixed degrees per direction, several right-hand sides
     "cube_p232_curved_m3": dict(dim=3, degree=2, nelem=3, geometry=1, rhs=[PI3], dirichlet=["x+y*z"], degree_dir=[2, 3, 2]),
     "sq_p31_m5": dict(dim=2, degree=1, nelem=5, geometry=1, rhs=[PI2], dirichlet=["x*y"], degree_dir=[3, 1]),
@@ -126,6 +136,8 @@ def main():
         ref = R.ref_run(**cfg)
         d = pack_inputs(ref)
         d.update(outer=ref.outer, inner=ref.inner, values=ref.values, rhs=ref.rhs, kind="full", config=repr(cfg))
+        if cfg.get("exact"):
+            d.update(solution=ref.solution, norms=ref.norms, exact_text=cfg["exact"])
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
         print(name, "N", ref.nfree, "nnz", len(ref.values))
     for name, cfg in FINGERPRINT.items():

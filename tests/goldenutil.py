@@ -95,3 +95,24 @@ def check_against(result, z, tol):
     assert max(e1, e2, e3) <= tol, f"fingerprints differ: Kx {e1:.2e} diag {e2:.2e} sum {e3:.2e}"
     assert er <= tol, f"rhs differs: {er:.3e}"
     return max(e1, e2, e3), er
+
+
+# Error-norm fixtures (make_golden.py "norms_*"): exact solution and its analytic gradient.  The reference differentiates the exact
+# solution numerically (gsFunctionExpr::deriv_into: exprtk::derivative with h = 1e-5, gsFunctionExpr.hpp:582), so its H1 error integral
+# carries ~1e-10 of finite-difference error: that one entry is compared at 1e-8, the other three at 1e-12.
+NORM_CASES = {
+    "norms_sq_p2_curved": ("sin(pi*x)*sin(pi*y)", ["pi*cos(pi*x)*sin(pi*y)", "pi*sin(pi*x)*cos(pi*y)"]),
+    "norms_cube_p3_curved": ("sin(pi*x)*sin(pi*y)*sin(pi*z)", ["pi*cos(pi*x)*sin(pi*y)*sin(pi*z)", "pi*sin(pi*x)*cos(pi*y)*sin(pi*z)",
+                                                               "pi*sin(pi*x)*sin(pi*y)*cos(pi*z)"]),
+    "norms_annulus_nurbs_p3": ("x^2*y+y^2*x", ["2*x*y+y^2", "x^2+2*y*x"]),
+    "norms_grid2x2_p2": ("sin(pi*x)*sin(pi*y)", ["pi*cos(pi*x)*sin(pi*y)", "pi*sin(pi*x)*cos(pi*y)"]),
+}
+
+
+def check_norms(got, z, tol=1e-12):
+    """got = [int (u_h-u_ex)^2, int |grad(u_h-u_ex)|^2, int u_h^2, int |grad u_h|^2] against the reference's gsExprEvaluator integrals."""
+    ref = z["norms"]
+    assert abs(got[2] - ref[2]) <= tol * abs(ref[2]), f"int u_h^2 differs: {got[2]} vs {ref[2]}"
+    assert abs(got[3] - ref[3]) <= tol * abs(ref[3]), f"int |grad u_h|^2 differs: {got[3]} vs {ref[3]}"
+    assert abs(got[0] - ref[0]) <= tol * abs(ref[2]) and abs(got[0] - ref[0]) <= 1e-9 * abs(ref[0]), f"L2 error differs: {got[0]} vs {ref[0]}"
+    assert abs(got[1] - ref[1]) <= 1e-8 * abs(ref[1]), f"H1 error differs: {got[1]} vs {ref[1]}"

@@ -49,6 +49,7 @@ def oracle_lib():
         lib.gsbo_gauss.argtypes = [C.c_int, _dp, _dp]
         lib.gsbo_basis_eval.argtypes = [_dp, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_int), _dp, _dp]
         lib.gsbo_last_error.restype = C.c_char_p
+        lib.gsbo_field_norms.argtypes = [C.POINTER(ProblemStruct), _dp, C.POINTER(capi.Program), C.POINTER(capi.Program), _dp]
         _oracle = lib
     return _oracle
 
@@ -71,6 +72,20 @@ def oracle_assemble(pb: Problem):
     return outer, inner, values, rhs
 
 
+def oracle_field_norms(pb, u, exact=None, exact_grad=None) -> np.ndarray:
+    """oracle/gsb_oracle.c::gsbo_field_norms (checker only)."""
+    lib = oracle_lib()
+    def prog(cp):
+        return capi.Program(len(cp.ops), cp.ops.ctypes.data_as(_ip), len(cp.consts), cp.consts.ctypes.data_as(_dp))
+    u = np.ascontiguousarray(u, dtype=np.float64).ravel()
+    ex = C.byref(prog(exact)) if exact is not None else None
+    eg = (capi.Program * len(exact_grad))(*[prog(cp) for cp in exact_grad]) if exact_grad is not None else None
+    out = np.zeros(4)
+    if lib.gsbo_field_norms(C.byref(pb.struct), u.ctypes.data_as(_dp), ex, eg, out.ctypes.data_as(_dp)):
+        raise RuntimeError(lib.gsbo_last_error().decode())
+    return out
+
+
 def oracle_gauss(n: int):
     x = np.zeros(n); w = np.zeros(n)
     oracle_lib().gsbo_gauss(n, x.ctypes.data_as(_dp), w.ctypes.data_as(_dp))
@@ -84,7 +99,7 @@ class RefConfig(C.Structure):
                 ("threads", C.c_int32), ("degree_elevate", C.c_int32), ("rhs", C.c_char_p * 3),
                 ("dir", C.c_char_p * 3), ("xml", C.c_char_p), ("lambda_", C.c_double), ("mu", C.c_double),
                 ("neumann_mask", C.c_int32), ("neu_n", C.c_int32), ("neu", C.c_char_p * 3),
-                ("degree_dir", C.c_int32 * 3), ("nrhs", C.c_int32)]
+                ("degree_dir", C.c_int32 * 3), ("nrhs", C.c_int32), ("exact", C.c_char_p)]
 
 
 _ref = None
@@ -102,6 +117,7 @@ def ref_lib():
         lib.gsref_run.argtypes = [C.POINTER(RefConfig)]
         lib.gsref_free.argtypes = [C.c_void_p]
         lib.gsref_sizes.argtypes = [C.c_void_p, C.POINTER(C.c_int64), _dp, _dp, _ip]
+        lib.gsref_solution.argtypes = [C.c_void_p, _dp, _dp]
         lib.gsref_csc.argtypes = [C.c_void_p, _ip, _ip, _dp, _dp, _dp]
         lib.gsref_patch_info.argtypes = [C.c_void_p, C.c_int, _ip]
         lib.gsref_patch_data.argtypes = [C.c_void_p, C.c_int] + [_dp] * 8 + [_ip]
@@ -144,7 +160,7 @@ class RefResult:
 
 def ref_run(dim=3, degree=2, nelem=4, geometry=0, grid=(1, 1, 1), path=0, form=0, dir_values=101,
             threads=1, rhs=None, dirichlet=None, xml=None, lam=0.0, mu=0.0, degree_elevate=0,
-            neumann_mask=0, neu=None, degree_dir=None, nrhs=1) -> RefResult:
+            neumann_mask=0, neu=None, degree_dir=None, nrhs=1, exact=None) -> RefResult:
     lib = ref_lib()
     cfg = RefConfig()
     cfg.dim, cfg.degree, cfg.nelem, cfg.geometry = dim, degree, nelem, geometry
@@ -155,6 +171,7 @@ def ref_run(dim=3, degree=2, nelem=4, geometry=0, grid=(1, 1, 1), path=0, form=0
     if form == 0 and path == 0 and nrhs > 1:
         ncomp = nrhs                      # components of the source / Dirichlet functions = right-hand-side columns
     cfg.nrhs = nrhs
+    cfg.exact = exact.encode() if exact else None
     for k, v in enumerate(degree_dir or []):
         cfg.degree_dir[k] = v
     rhs = list(rhs or ["0"] * ncomp)
@@ -199,6 +216,11 @@ def ref_run(dim=3, degree=2, nelem=4, geometry=0, grid=(1, 1, 1), path=0, form=0
         lib.gsref_csc(h, R.outer.ctypes.data_as(_ip), R.inner.ctypes.data_as(_ip), R.values.ctypes.data_as(_dp),
                       R.rhs.ctypes.data_as(_dp), R.fixed.ctypes.data_as(_dp))
         R.fixed = R.fixed[:R.nfixed]
+        R.solution, R.norms = None, None
+        if exact:
+            sol, nrm = np.zeros(R.nfree), np.zeros(4)
+            if lib.gsref_solution(h, sol.ctypes.data_as(_dp), nrm.ctypes.data_as(_dp)) > 0:
+                R.solution, R.norms = sol, nrm
         for k in range(npatches):
             info = (C.c_int32 * 15)()
             lib.gsref_patch_info(h, k, info)

@@ -343,3 +343,22 @@ def test_first_sweep_output_full_and_half_rows(lib, mode, monkeypatch):
     assert capped[4].nchunks > 1 and np.array_equal(capped[2], full[2])
     pb16, z16 = G.load("cube_p3_m16", g.expr_compile)
     G.check_against(R.lib_assemble(lib, pb16), z16, TOL)
+
+
+@pytest.mark.parametrize("name", sorted(G.NORM_CASES))
+def test_field_norms_match_the_reference(lib, name):
+    """f4: gsb200_field_norms on the reference's own solution against its gsExprEvaluator integrals (L2 / H1 error, poisson2_example.cpp:174-177),
+    and against the C oracle on a random field."""
+    pb, z = G.load(name, g.expr_compile)
+    ex, grads = G.NORM_CASES[name]
+    exp, gp = g.expr_compile(ex), [g.expr_compile(t) for t in grads]
+    A = g.DeviceAssembler(pb)
+    G.check_norms(A.field_norms(z["solution"], exp, gp), z)
+    u = np.random.default_rng(3).uniform(-1, 1, pb.nfree)
+    a, b = A.field_norms(u, exp, gp), R.oracle_field_norms(pb, u, exp, gp)
+    assert np.abs(a - b).max() <= 1e-13 * np.abs(b).max()
+    # the device solve reproduces the reference's solution and therefore its error norms
+    A.assemble()
+    x, it, res = A.cg_solve(A.rhs()[:, 0], max_iter=5000, tol=1e-13, check_every=5)
+    assert np.abs(x - z["solution"]).max() <= 1e-9 * np.abs(z["solution"]).max()
+    A.close()

@@ -137,3 +137,19 @@ def test_first_sweep_output_full_and_half_rows(emul, mode, monkeypatch):
     assert capped[4].nchunks > 1 and np.array_equal(capped[2], full[2])
     pb16, z16 = G.load("cube_p3_m16", R.emul_compile)
     G.check_against(R.lib_assemble(emul, pb16), z16, TOL)
+
+
+@pytest.mark.parametrize("name", sorted(G.NORM_CASES))
+def test_field_norm_kernel_matches_the_reference(emul, name):
+    """gsb200_field_norms (k_field_norms, interpreted) against the reference's gsExprEvaluator integrals and the C oracle."""
+    import gismo_b200 as g
+    pb, z = G.load(name, R.emul_compile)
+    ex, grads = G.NORM_CASES[name]
+    exp, gp = R.emul_compile(ex), [R.emul_compile(t) for t in grads]
+    A = g.DeviceAssembler(pb, lib=emul)
+    got = A.field_norms(z["solution"], exp, gp)
+    G.check_norms(got, z)
+    u = np.random.default_rng(3).uniform(-1, 1, pb.nfree)
+    a, b = A.field_norms(u, exp, gp), R.oracle_field_norms(pb, u, exp, gp)
+    assert np.abs(a - b).max() <= 1e-13 * np.abs(b).max()
+    A.close()

@@ -88,3 +88,15 @@ def test_live_reference_vs_oracle_and_tables():
         lib.gsref_gauss(n, x.ctypes.data_as(C.POINTER(C.c_double)), w.ctypes.data_as(C.POINTER(C.c_double)))
         xo, wo = R.oracle_gauss(n)
         assert np.abs(x - xo).max() <= 2.3e-16 and np.abs(w - wo).max() <= 2.3e-16
+
+
+@pytest.mark.parametrize("name", sorted(G.NORM_CASES))
+def test_oracle_norm_integrals_match_the_reference(name):
+    """gsbo_field_norms against ev.integral((u_ex - u_sol).sqNorm() * meas(G)) etc. of the reference (gsExprEvaluator) on the
+    reference's own solution coefficients."""
+    pb, z = G.load(name, R.emul_compile)
+    ex, grads = G.NORM_CASES[name]
+    got = R.oracle_field_norms(pb, z["solution"], R.emul_compile(ex), [R.emul_compile(t) for t in grads])
+    G.check_norms(got, z)
+    only_field = R.oracle_field_norms(pb, z["solution"])
+    assert only_field[0] == only_field[2] and only_field[1] == only_field[3]
