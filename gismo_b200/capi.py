@@ -236,6 +236,7 @@ def declare(lib, optional=()):
     lib.gsb200_expr_eval_host.argtypes = [C.POINTER(Program), C.c_double, C.c_double, C.c_double, _dp]
     lib.gsb200_measure_peaks.argtypes = [C.c_int, _dp, _dp, _dp]
     lib.gsb200_device_count.argtypes = [C.POINTER(C.c_int)]
+    lib.gsb200_trim.argtypes = [C.c_int]
     lib.gsb200_comm_unique_id.argtypes = [C.c_void_p]
     lib.gsb200_comm_init.argtypes = [C.c_void_p, C.c_void_p]
     lib.gsb200_set_comm.argtypes = [C.c_void_p, C.c_void_p]

@@ -302,6 +302,21 @@ static int build_pattern(gsb200_assembler *a)
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s);
 #endif
     unsigned long long *d_len = 0; int *d_cursor = 0; unsigned char *d_gneed = 0;
+    struct Guard {          // the temporaries and the timing events go on every return path
+        unsigned long long *&len; int *&cursor; unsigned char *&gneed; stream_t s;
+#ifndef GSB200_EMULATE
+        cudaEvent_t e0, e1;
+#endif
+        ~Guard() { dev_sync(s); dev_free(len); dev_free(cursor); dev_free(gneed);
+#ifndef GSB200_EMULATE
+                   cudaEventDestroy(e0); cudaEventDestroy(e1);
+#endif
+        }
+    } guard{d_len, d_cursor, d_gneed, s
+#ifndef GSB200_EMULATE
+            , e0, e1
+#endif
+    };
     GSB_TRY(dev_malloc((void **)&d_len, sizeof(unsigned long long) * (size_t)(N + 1)));
     GSB_TRY(dev_memset(d_len, 0, sizeof(unsigned long long) * (size_t)(N + 1), s));
     GSB_TRY(dev_malloc((void **)&d_cursor, sizeof(int) * (size_t)(N + 1)));
@@ -370,10 +385,8 @@ static int build_pattern(gsb200_assembler *a)
     GSB_TRY(dev_memset(a->d_values, 0, sizeof(double) * (size_t)std::max<i64>(a->nnz, 1), s));
     GSB_TRY(dev_last_error("pattern kernels"));
     GSB_TRY(dev_sync(s));
-    dev_free(d_len); dev_free(d_cursor); dev_free(d_gneed);
 #ifndef GSB200_EMULATE
     cudaEventRecord(e1, s); cudaEventSynchronize(e1); cudaEventElapsedTime(&a->tm.pattern_ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
 #endif
     a->coupled_off.clear();
     for (int c : a->coupled_runs) { i64 off = 0; GSB_TRY(dev_d2h(&off, a->d_colptr + c, sizeof(i64), s)); a->coupled_off.push_back(off); }
@@ -449,7 +462,7 @@ static int assemble_pass(gsb200_assembler *a)
     // workspace budget
     i64 limit = a->plan_valid ? a->plan_limit : a->ws_limit;
 #ifndef GSB200_EMULATE
-    if (limit <= 0) { size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot); limit = (i64)((fr + a->ws_size) * 0.85); }
+    if (limit <= 0) { size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot); limit = (i64)((fr + dev_pool_idle() + a->ws_size) * 0.85); }      // (what the pool holds idle is ours to reuse)
 #else
     if (limit <= 0) limit = (i64)1 << 30;
 #endif
@@ -1133,7 +1146,19 @@ int gsb200_create(const gsb200_problem *pb, int device, gsb200_assembler **out)
     return GSB200_OK;
 }
 
-void gsb200_destroy(gsb200_assembler *a) { delete a; }
+void gsb200_destroy(gsb200_assembler *a)
+{
+    if (!a) return;
+    select_device(a->device);
+    delete a;               // buffers go back to the library's pool (recycled by the next assembler); gsb200_trim returns them to the driver
+}
+
+int gsb200_trim(int device)
+{
+    GSB_TRY(select_device(device));
+    dev_trim();
+    return GSB200_OK;
+}
 
 int gsb200_set_stream(gsb200_assembler *a, void *cuda_stream)
 {

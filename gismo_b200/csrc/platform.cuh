@@ -39,24 +39,30 @@ inline int dev_check(cudaError_t e, const char *what) {
     set_error("%s: %s", what, cudaGetErrorString(e));
     return (e == cudaErrorMemoryAllocation) ? -5 : -4;
 }
-// Device memory comes from the device's default stream-ordered pool (cudaMallocAsync) with the release
-// threshold raised, so that the multi-GB buffers of one assembly (pattern, values, workspace) are recycled by
-// the next one instead of going back to the driver (a cudaMalloc/cudaFree pair of that size costs milliseconds).
-// Callers synchronise their stream before freeing (dev_free is ordered on the pool's own stream only).
+// Device memory comes from a PRIVATE stream-ordered pool per device (cudaMemPoolCreate; the process's default pool and whoever else
+// uses it - e.g. torch's allocator - are left alone) with the release threshold raised, so that the multi-GB buffers of one assembly
+// (pattern, values, workspace) are recycled by the next one instead of going back to the driver (a cudaMalloc/cudaFree pair of that
+// size costs milliseconds).  Callers synchronise their stream before freeing (dev_free is ordered on the pool's own stream only).
+// dev_pool_idle() = bytes the pool holds but nobody uses: the workspace budget counts them as available, and they are given back
+// when an allocation fails (dev_malloc) or on request (dev_trim = gsb200_trim).
 // GSB200_NO_POOL=1 selects plain cudaMalloc/cudaFree.
-struct DevPoolState { cudaStream_t stream; cudaMemPool_t pool; bool init, usable; };
+struct DevPoolState { cudaStream_t stream; cudaMemPool_t pool; bool init, usable; int users; };
 inline DevPoolState &dev_pool()
 {
     static DevPoolState st[64];
     int d = 0; cudaGetDevice(&d); if (d < 0 || d >= 64) d = 0;
     DevPoolState &P = st[d];
     if (!P.init) {
-        P.init = true; P.usable = false;
+        P.init = true; P.usable = false; P.users = 0;
         int sup = 0;
-        if (!getenv("GSB200_NO_POOL") && cudaDeviceGetAttribute(&sup, cudaDevAttrMemoryPoolsSupported, d) == cudaSuccess && sup &&
-            cudaDeviceGetDefaultMemPool(&P.pool, d) == cudaSuccess && cudaStreamCreateWithFlags(&P.stream, cudaStreamNonBlocking) == cudaSuccess) {
-            unsigned long long thr = ~0ull;
-            P.usable = cudaMemPoolSetAttribute(P.pool, cudaMemPoolAttrReleaseThreshold, &thr) == cudaSuccess;
+        if (!getenv("GSB200_NO_POOL") && cudaDeviceGetAttribute(&sup, cudaDevAttrMemoryPoolsSupported, d) == cudaSuccess && sup) {
+            cudaMemPoolProps props; memset(&props, 0, sizeof props);
+            props.allocType = cudaMemAllocationTypePinned; props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice; props.location.id = d;
+            if (cudaMemPoolCreate(&P.pool, &props) == cudaSuccess && cudaStreamCreateWithFlags(&P.stream, cudaStreamNonBlocking) == cudaSuccess) {
+                unsigned long long thr = ~0ull;
+                P.usable = cudaMemPoolSetAttribute(P.pool, cudaMemPoolAttrReleaseThreshold, &thr) == cudaSuccess;
+            }
         }
         cudaGetLastError();
     }
@@ -66,13 +72,22 @@ inline int dev_malloc(void **p, size_t n)
 {
     DevPoolState &P = dev_pool();
     if (!P.usable) return dev_check(cudaMalloc(p, n ? n : 1), "cudaMalloc");
-    cudaError_t e = cudaMallocAsync(p, n ? n : 1, P.stream);
-    if (e != cudaSuccess) { cudaGetLastError(); cudaStreamSynchronize(P.stream); cudaMemPoolTrimTo(P.pool, 0); e = cudaMallocAsync(p, n ? n : 1, P.stream); }
+    cudaError_t e = cudaMallocFromPoolAsync(p, n ? n : 1, P.pool, P.stream);
+    if (e != cudaSuccess) { cudaGetLastError(); cudaStreamSynchronize(P.stream); cudaMemPoolTrimTo(P.pool, 0); e = cudaMallocFromPoolAsync(p, n ? n : 1, P.pool, P.stream); }
     if (e == cudaSuccess) e = cudaStreamSynchronize(P.stream);
-    return dev_check(e, "cudaMallocAsync");
+    return dev_check(e, "cudaMallocFromPoolAsync");
 }
 inline void dev_free(void *p) { if (!p) return; DevPoolState &P = dev_pool(); if (P.usable) cudaFreeAsync(p, P.stream); else cudaFree(p); }
 inline void dev_trim() { DevPoolState &P = dev_pool(); if (P.usable) { cudaStreamSynchronize(P.stream); cudaMemPoolTrimTo(P.pool, 0); } }
+inline size_t dev_pool_idle()
+{
+    DevPoolState &P = dev_pool();
+    if (!P.usable) return 0;
+    cudaStreamSynchronize(P.stream);
+    unsigned long long res = 0, used = 0;
+    if (cudaMemPoolGetAttribute(P.pool, cudaMemPoolAttrReservedMemCurrent, &res) != cudaSuccess || cudaMemPoolGetAttribute(P.pool, cudaMemPoolAttrUsedMemCurrent, &used) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return res > used ? (size_t)(res - used) : 0;
+}
 inline int dev_h2d(void *d, const void *h, size_t n, stream_t s) { return dev_check(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s), "H2D copy"); }
 inline int dev_d2h(void *h, const void *d, size_t n, stream_t s) {
     int r = dev_check(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s), "D2H copy");
@@ -122,6 +137,7 @@ typedef int event_t;
 inline int dev_malloc(void **p, size_t n) { *p = std::calloc(n ? n : 1, 1); return *p ? 0 : -5; }
 inline void dev_free(void *p) { std::free(p); }
 inline void dev_trim() {}
+inline size_t dev_pool_idle() { return 0; }
 inline int dev_h2d(void *d, const void *h, size_t n, stream_t) { std::memcpy(d, h, n); return 0; }
 inline int dev_d2h(void *h, const void *d, size_t n, stream_t) { std::memcpy(h, d, n); return 0; }
 inline int dev_d2d(void *d, const void *s_, size_t n, stream_t) { std::memcpy(d, s_, n); return 0; }

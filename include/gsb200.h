@@ -176,6 +176,10 @@ int gsb200_device_count(int *count);
 /* Upload the problem to `device`, build 1-D basis/quadrature tables there. */
 int gsb200_create(const gsb200_problem *problem, int device, gsb200_assembler **out);
 void gsb200_destroy(gsb200_assembler *a);
+/* Device memory of destroyed assemblers stays in the library's private stream-ordered pool (a later assembler reuses the
+   multi-GB buffers without going to the driver; the automatic workspace budget counts it as available).  gsb200_trim gives
+   it back to the driver, e.g. before another library needs the device memory. */
+int gsb200_trim(int device);
 /* Use an existing cudaStream_t (e.g. torch's current stream); NULL = default stream. */
 int gsb200_set_stream(gsb200_assembler *a, void *cuda_stream);
 /* Cap for intermediate sum-factorisation storage in bytes (0 = automatic). */
