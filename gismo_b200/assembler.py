@@ -214,6 +214,18 @@ class DeviceAssembler:
         self._check(self.lib.gsb200_field_norms(self._h, u.ctypes.data_as(_dp), ex, eg, out.ctypes.data_as(_dp)))
         return out
 
+    def project_dirichlet(self, sides, max_iter: int = 2000, tol: float = 1e-13):
+        """gsb200_project_dirichlet: sides = [(patch, side, CompiledProgram g), ...]; returns (fixed values, iterations, rel. residual)."""
+        nm = (capi.Neumann * max(len(sides), 1))()
+        for i, (patch, side, cp) in enumerate(sides):
+            nm[i].patch, nm[i].side, nm[i].ndata = int(patch), int(side), 1
+            nm[i].data[0].nops = len(cp.ops); nm[i].data[0].ops = cp.ops.ctypes.data_as(_ip)
+            nm[i].data[0].nconsts = len(cp.consts); nm[i].data[0].consts = cp.consts.ctypes.data_as(_dp)
+        out = np.zeros(max(self.problem.nfixed, 1))
+        it, res = C.c_int(0), C.c_double(0)
+        self._check(self.lib.gsb200_project_dirichlet(self._h, nm, len(sides), max_iter, tol, out.ctypes.data_as(_dp), C.byref(it), C.byref(res)))
+        return out[:self.problem.nfixed], it.value, res.value
+
     def cg_info(self):
         """(device ms of the last solve's iteration loop, halo-exchange mode?)"""
         ms, h = C.c_double(0), C.c_int32(0)

@@ -245,6 +245,7 @@ def declare(lib, optional=()):
     lib.gsb200_comm_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
     lib.gsb200_cg_solve.argtypes = [C.c_void_p, _dp, _dp, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), _dp]
     lib.gsb200_field_norms.argtypes = [C.c_void_p, _dp, C.POINTER(Program), C.POINTER(Program), _dp]
+    lib.gsb200_project_dirichlet.argtypes = [C.c_void_p, C.POINTER(Neumann), C.c_int, C.c_int, C.c_double, _dp, C.POINTER(C.c_int), _dp]
     lib.gsb200_cg_info.argtypes = [C.c_void_p, _dp, C.POINTER(C.c_int32)]
     lib.gsb200_cg_solution_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     lib.gsb200_spmv_info.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]

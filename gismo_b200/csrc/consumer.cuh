@@ -347,6 +347,132 @@ GSB_GLOBAL void k_field_norms(const NormArgs A)
     cg_block_add(s0, A.out + 0); cg_block_add(s1, A.out + 1); cg_block_add(s2, A.out + 2); cg_block_add(s3, A.out + 3);
 }
 
+// ------------------------------------------------------------------ f2: Dirichlet values by L2-projection onto the boundary trace space
+// gsDirichletValuesByL2Projection (gsDirichletValues.h:257-435; visitor path: gsAssembler.hpp computeDirichletDofsL2Proj): boundary mass
+// matrix M_ij = sum over Dirichlet sides int N_i N_j m over the ELIMINATED functions, right-hand side int g N_i m (m = |det J|, see below), solved with
+// Jacobi-CG (the reference: gsSparseSolver<>::CGDiagonal).  Here M is never formed: M x = sum_sides B^T (w|n| .* (B x)) with the face
+// kernels (k_face_eval, k_face_load); the weights w m and the data w m g come from k_face_geometry.
+struct ProjSide { FaceArgs F; FaceLoadArgs L; FaceEvalArgs E; i64 npt, nfn; double *Wb, *Gb, *Tb; };
+
+static void proj_side_setup(gsb200_assembler *a, int patch, int side, ProjSide &S)
+{
+    const PatchDev &P = a->patches[patch];
+    const int dim = a->dim, dir = (side - 1) / 2, upper = (side - 1) % 2;
+    memset(&S.F, 0, sizeof S.F); memset(&S.L, 0, sizeof S.L); memset(&S.E, 0, sizeof S.E);
+    S.F.dim = dim; S.F.dir = dir; S.F.upper = upper; S.L.dim = dim; S.L.dir = dir; S.E.dim = dim; S.E.dir = dir;
+    S.npt = 1; S.nfn = 1;
+    for (int k = 0; k < dim; ++k) {
+        const Dir1D &d = P.dir[k];
+        S.F.qn[k] = d.Q; S.F.gtab[k] = d.d_gtab; S.F.gfirst[k] = d.d_gfirst; S.F.pg1[k] = d.pg1; S.F.ngeo[k] = d.ngeo; S.F.hpt[k] = d.d_hpt; S.F.gwp[k] = d.d_gwp;
+        S.L.nfun[k] = d.nfun; S.L.p1[k] = d.p + 1; S.L.q[k] = d.q; S.L.Q[k] = d.Q; S.L.ffirst[k] = d.d_ffirst; S.L.flast[k] = d.d_flast; S.L.tab[k] = d.d_tab;
+        S.E.qn[k] = d.Q; S.E.nfun[k] = d.nfun; S.E.p1[k] = d.p + 1; S.E.q[k] = d.q; S.E.tabl[k] = d.d_tabl; S.E.first[k] = d.d_first;
+        if (k != dir) { S.npt *= d.Q; S.nfn *= d.nfun; }
+    }
+    const Dir1D &dd = P.dir[dir];
+    for (int k2 = 0; k2 < dd.pg1; ++k2) S.F.bgeo[k2] = dd.bgeo[upper][k2];
+    S.F.bgfirst = dd.bgfirst[upper];
+    for (int k2 = 0; k2 <= dd.p; ++k2) { S.L.bval[k2] = dd.bval[upper][k2]; S.E.bval[k2] = dd.bval[upper][k2]; }
+    S.L.bfirst = dd.bfirst[upper]; S.L.nb1 = dd.p + 1; S.E.bfirst = S.L.bfirst; S.E.nb1 = S.L.nb1;
+    S.F.coefs = P.d_coefs; S.F.weights = P.d_weights; S.F.ngeo_total = P.ngeo_total;
+    S.L.dofmap = P.d_dofmap; S.L.nfree = a->nfree; S.L.to_fixed = 1;
+    S.E.dofmap = P.d_dofmap; S.E.nfree = a->nfree;
+}
+template <class K2, class K3, class ARGS>
+static void face_launch(int dim, K2 k2, K3 k3, i64 n, stream_t s, const ARGS &A)
+{
+    if (dim == 2) GSB_LAUNCH(k2, dim3((unsigned)((n + 127) / 128)), dim3(128), s, A);
+    else GSB_LAUNCH(k3, dim3((unsigned)((n + 127) / 128)), dim3(128), s, A);
+}
+
+static int project_dirichlet(gsb200_assembler *a, const gsb200_neumann *sides, int nsides, int max_iter, double tol, double *fixed_out, int *iters, double *relres)
+{
+    const int nb = a->nfixed; stream_t s = a->stream;
+    if (a->ncomp != 1 || a->nrhs != 1) { set_error("Dirichlet L2-projection: scalar problems with one right-hand side"); return GSB200_EUNSUPPORTED; }
+    if (nb == 0) { if (iters) *iters = 0; if (relres) *relres = 0.0; return 0; }
+    std::vector<ProjSide> S((size_t)nsides);
+    std::vector<void *> bufs;
+    auto alloc = [&](size_t n) -> double * { void *p = 0; if (dev_malloc(&p, sizeof(double) * std::max<size_t>(n, 1))) return (double *)0; bufs.push_back(p); return (double *)p; };
+    const size_t nprog0 = a->prog_bufs.size();
+    int rc = 0;
+    gsb200_program one; int one_ops[2] = {GSB200_OP_CONST, 0}; double one_c[1] = {1.0};
+    one.nops = 2; one.ops = one_ops; one.nconsts = 1; one.consts = one_c;
+    double *vec[7];       // x r z p q d + scalars
+    for (int k = 0; k < 7; ++k) { vec[k] = alloc((size_t)nb + 8); if (!vec[k]) rc = GSB200_ENOMEM; }
+    double *X = vec[0], *R = vec[1], *Z = vec[2], *Pv = vec[3], *Q = vec[4], *Dg = vec[5], *Sc = vec[6];
+    for (int i = 0; i < nsides && !rc; ++i) {
+        const gsb200_neumann &sd = sides[i];
+        if (sd.patch < 0 || sd.patch >= (int)a->patches.size() || sd.side < 1 || sd.side > 2 * a->dim || sd.ndata != 1) { set_error("Dirichlet side %d malformed", i); rc = GSB200_EINVAL; break; }
+        ProjSide &P = S[i];
+        proj_side_setup(a, sd.patch, sd.side, P);
+        P.Wb = alloc((size_t)P.npt); P.Gb = alloc((size_t)P.npt); P.Tb = alloc((size_t)P.npt);
+        if (!P.Wb || !P.Gb || !P.Tb) { rc = GSB200_ENOMEM; break; }
+        // the reference integrates with md.measure of a gsMapData whose side is not set (gsDirichletValues.h:273 / gsAssembler.hpp:412):
+        // the VOLUME measure |det J| at the boundary points, not the surface measure; restated as it is
+        P.F.ndata = 1; P.F.vol_measure = 1;
+        if ((rc = upload_device_program(a, one, &P.F.prog[0]))) break;
+        P.F.Fb = P.Wb; face_launch(a->dim, k_face_geometry<2>, k_face_geometry<3>, P.npt, s, P.F);          // w |n|
+        if ((rc = upload_device_program(a, sd.data[0], &P.F.prog[0]))) break;
+        P.F.Fb = P.Gb; face_launch(a->dim, k_face_geometry<2>, k_face_geometry<3>, P.npt, s, P.F);          // w |n| g
+    }
+    auto apply = [&](const double *x, double *y, bool diag) {      // y = M x  (diag: y = diag M)
+        dev_memset(y, 0, sizeof(double) * (size_t)nb, s);
+        for (int i = 0; i < nsides; ++i) {
+            ProjSide &P = S[i];
+            FaceLoadArgs L = P.L; L.rhs = y;
+            if (diag) { L.Fb = P.Wb; L.square = 1; }
+            else {
+                FaceEvalArgs E = P.E; E.x = x; E.Wb = P.Wb; E.out = P.Tb;
+                face_launch(a->dim, k_face_eval<2>, k_face_eval<3>, P.npt, s, E);
+                L.Fb = P.Tb;
+            }
+            face_launch(a->dim, k_face_load<2>, k_face_load<3>, P.nfn, s, L);
+        }
+    };
+    int it = 0; double rr = 0.0, bb = 0.0;
+    if (!rc) {
+#ifndef GSB200_EMULATE
+        const dim3 gO(148 * 2), tv(256);
+#else
+        const dim3 gO(1), tv(1);
+#endif
+        // right-hand side b_i = int g N_i |n| into R; diagonal into Dg (an eliminated DOF no Dirichlet side touches keeps value 0)
+        dev_memset(R, 0, sizeof(double) * (size_t)nb, s);
+        for (int i = 0; i < nsides; ++i) { FaceLoadArgs L = S[i].L; L.rhs = R; L.Fb = S[i].Gb; face_launch(a->dim, k_face_load<2>, k_face_load<3>, S[i].nfn, s, L); }
+        apply(0, Dg, true);
+        dev_memset(Q, 0, sizeof(double) * (size_t)nb, s);
+        GSB_LAUNCH(k_cg_prep, dim3((nb + 127) / 128), dim3(128), s, nb, Dg, Q);      // zero diagonal -> 1 (Q is scratch for the holders slot)
+        rc = dev_d2d(Q, R, sizeof(double) * (size_t)nb, s);                           // b
+        if (!rc) rc = dev_memset(Sc, 0, 8 * sizeof(double), s);
+        if (!rc) {
+            GSB_LAUNCH(k_cg_start, gO, tv, s, 0, nb, 0, nb, Q, Dg, X, R, Z, Pv, Sc);
+            double hs[8]; rc = dev_d2h(hs, Sc, sizeof hs, s);
+            bb = hs[4]; rr = bb;
+            const double thr = tol * tol * bb;
+            while (!rc && it < max_iter && rr > thr) {
+                apply(Pv, Q, false);
+                GSB_LAUNCH(k_cg_dot, gO, tv, s, 0, nb, Pv, Q, Sc + 1);
+                GSB_LAUNCH(k_cg_step1, gO, tv, s, 0, nb, 0, nb, Pv, Q, Dg, X, R, Z, Sc);
+                GSB_LAUNCH(k_cg_step2, gO, tv, s, 0, nb, Z, Pv, Sc);
+                GSB_LAUNCH(k_cg_rotate, dim3(1), dim3(32), s, Sc);
+                ++it;
+                if (it % 5 == 0 || it == max_iter) { rc = dev_d2h(hs, Sc, sizeof hs, s); rr = hs[5]; }
+            }
+            if (!rc) { rc = dev_d2h(hs, Sc, sizeof hs, s); if (it) rr = hs[5]; }
+        }
+        if (!rc && fixed_out) rc = dev_d2h(fixed_out, X, sizeof(double) * (size_t)nb, s);
+        if (!rc) {      // the projected values become the assembler's eliminated-DOF values
+            if (!a->d_fixed) rc = dev_malloc((void **)&a->d_fixed, sizeof(double) * (size_t)nb);
+            if (!rc) rc = dev_d2d(a->d_fixed, X, sizeof(double) * (size_t)nb, s);
+        }
+    }
+    if (!rc) rc = dev_sync(s); else dev_sync(s);
+    for (void *p : bufs) dev_free(p);
+    while (a->prog_bufs.size() > nprog0) { dev_free(a->prog_bufs.back()); a->prog_bufs.pop_back(); }
+    if (iters) *iters = it;
+    if (relres) *relres = bb > 0 ? sqrt(rr / bb) : 0.0;
+    return rc;
+}
+
 // ------------------------------------------------------------------ SpMV set-up: offset tables of the regular columns
 static int spmv_prepare(gsb200_assembler *a)
 {
@@ -769,6 +895,14 @@ int gsb200_field_norms(gsb200_assembler *a, const double *u_free, const gsb200_p
     while (a->prog_bufs.size() > nbuf0) { dev_free(a->prog_bufs.back()); a->prog_bufs.pop_back(); }
     dev_free(d_u); dev_free(d_out);
     return rc;
+}
+
+int gsb200_project_dirichlet(gsb200_assembler *a, const gsb200_neumann *sides, int nsides, int max_iter, double tol,
+                             double *fixed_out, int *iters, double *rel_residual)
+{
+    if (!a || (nsides > 0 && !sides) || nsides < 0) { set_error("project_dirichlet: bad arguments"); return GSB200_EINVAL; }
+    GSB_TRY(select_device(a->device));
+    return project_dirichlet(a, sides, nsides, max_iter, tol, fixed_out, iters, rel_residual);
 }
 
 int gsb200_cg_info(const gsb200_assembler *a, double *loop_ms, int32_t *halo_exchange)

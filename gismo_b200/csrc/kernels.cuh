@@ -131,6 +131,7 @@ struct FaceArgs {
     const double *coefs; const double *weights; i64 ngeo_total;
     int ndata; DevProgram prog[3];
     double *Fb;                                  // [qa][qb], last face direction fastest
+    int vol_measure;                             // scalar data times |det J| instead of |n| (what the reference's Dirichlet L2-projection weighs with)
 };
 template <int DIM>
 GSB_GLOBAL void k_face_geometry(const FaceArgs A)
@@ -183,7 +184,7 @@ GSB_GLOBAL void k_face_geometry(const FaceArgs A)
     double nn = 0.0;
     for (int c = 0; c < DIM; ++c) { nrm[c] *= sgn; nn += nrm[c] * nrm[c]; }
     double flux;
-    if (A.ndata == 1) flux = program_eval(A.prog[0], x[0], x[1], x[2]) * sqrt(nn);
+    if (A.ndata == 1) flux = program_eval(A.prog[0], x[0], x[1], x[2]) * (A.vol_measure ? fabs(det) : sqrt(nn));
     else { flux = 0.0; for (int c = 0; c < DIM; ++c) flux += program_eval(A.prog[c], x[0], x[1], x[2]) * nrm[c]; }
     double w = 1.0;                               // the fixed direction contributes h=0 -> 0.5 and weight 2
     for (int k = 0; k < DIM; ++k) if (k != A.dir) w *= A.hpt[k][ql[k]] * A.gwp[k][ql[k]];
@@ -198,6 +199,8 @@ struct FaceLoadArgs {
     const int *ffirst[3], *flast[3]; const double2 *tab[3];
     double bval[GSB_MAXP + 1]; int bfirst, nb1;   // solution basis values of `dir` at the boundary parameter
     const double *Fb; const int *dofmap; double *rhs; int nfree;
+    // boundary L2-projection (gsDirichletValues.h:257-435): rows are the ELIMINATED DOFs (index - nfree); square: N_i^2 (diagonal)
+    int to_fixed, square;
 };
 template <int DIM>
 GSB_GLOBAL void k_face_load(const FaceLoadArgs A)
@@ -214,13 +217,16 @@ GSB_GLOBAL void k_face_load(const FaceLoadArgs A)
     for (int ea = A.ffirst[a][fi[a]]; ea <= A.flast[a][fi[a]]; ++ea)
         for (int ta = 0; ta < A.q[a]; ++ta) {
             const int qa = ea * A.q[a] + ta;
-            const double va = A.tab[a][(i64)qa * A.p1[a] + fi[a] % A.p1[a]].x;
+            double va = A.tab[a][(i64)qa * A.p1[a] + fi[a] % A.p1[a]].x;
+            if (A.square) va *= va;
             if (DIM == 2) { s = fma(va, A.Fb[qa], s); continue; }
             double sb = 0.0;
             for (int eb = A.ffirst[b][fi[b]]; eb <= A.flast[b][fi[b]]; ++eb)
                 for (int tb = 0; tb < A.q[b]; ++tb) {
                     const int qb = eb * A.q[b] + tb;
-                    sb = fma(A.tab[b][(i64)qb * A.p1[b] + fi[b] % A.p1[b]].x, A.Fb[(i64)qa * A.Q[b] + qb], sb);
+                    double vb = A.tab[b][(i64)qb * A.p1[b] + fi[b] % A.p1[b]].x;
+                    if (A.square) vb *= vb;
+                    sb = fma(vb, A.Fb[(i64)qa * A.Q[b] + qb], sb);
                 }
             s = fma(va, sb, s);
         }
@@ -228,9 +234,55 @@ GSB_GLOBAL void k_face_load(const FaceLoadArgs A)
         fi[A.dir] = A.bfirst + k;
         const i64 li = ((i64)(DIM == 3 ? fi[2] : 0) * A.nfun[1] + fi[1]) * A.nfun[0] + fi[0];
         const int g = A.dofmap[li];
-        const double v = s * A.bval[k];
-        if (g < A.nfree && v != 0.0) atomic_add(A.rhs + g, v);
+        const double v = s * (A.square ? A.bval[k] * A.bval[k] : A.bval[k]);
+        if (A.to_fixed) { if (g >= A.nfree && v != 0.0) atomic_add(A.rhs + (g - A.nfree), v); }
+        else if (g < A.nfree && v != 0.0) atomic_add(A.rhs + g, v);
     }
+}
+
+// Trace of a field of ELIMINATED coefficients x (index - nfree) at the boundary quadrature points of a side, times the point weights
+// Wb (= w |n|, k_face_geometry with data 1): out = Wb .* (B x).  With k_face_load(to_fixed) this applies the boundary mass matrix of
+// the Dirichlet L2-projection without forming it.
+struct FaceEvalArgs {
+    int dim, dir;
+    int qn[3], nfun[3], p1[3], q[3];
+    const double2 *tabl[3]; const int *first[3];
+    double bval[GSB_MAXP + 1]; int bfirst, nb1;
+    const int *dofmap; const double *x; int nfree;
+    const double *Wb; double *out;
+};
+template <int DIM>
+GSB_GLOBAL void k_face_eval(const FaceEvalArgs A)
+{
+    int fd[2] = {0, 0}, nf = 0;
+    for (int k = 0; k < DIM; ++k) if (k != A.dir) fd[nf++] = k;
+    const i64 total = (DIM == 3) ? (i64)A.qn[fd[0]] * A.qn[fd[1]] : (i64)A.qn[fd[0]];
+    const i64 id = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= total) return;
+    int ql[3] = {0, 0, 0};
+    if (DIM == 3) { ql[fd[1]] = (int)(id % A.qn[fd[1]]); ql[fd[0]] = (int)(id / A.qn[fd[1]]); } else ql[fd[0]] = (int)id;
+    const int a = fd[0], b = fd[1];
+    const int fa0 = A.first[a][ql[a] / A.q[a]], fb0 = DIM == 3 ? A.first[b][ql[b] / A.q[b]] : 0;
+    double s = 0.0;
+    for (int k = 0; k < A.nb1; ++k) {
+        if (A.bval[k] == 0.0) continue;
+        int fi[3] = {0, 0, 0};
+        fi[A.dir] = A.bfirst + k;
+        double sk = 0.0;
+        for (int ja = 0; ja < A.p1[a]; ++ja) {
+            fi[a] = fa0 + ja;
+            const double va = A.tabl[a][(i64)ql[a] * A.p1[a] + ja].x;
+            for (int jb = 0; jb < (DIM == 3 ? A.p1[b] : 1); ++jb) {
+                double v = va;
+                if (DIM == 3) { fi[b] = fb0 + jb; v *= A.tabl[b][(i64)ql[b] * A.p1[b] + jb].x; }
+                const i64 li = ((i64)(DIM == 3 ? fi[2] : 0) * A.nfun[1] + fi[1]) * A.nfun[0] + fi[0];
+                const int g = A.dofmap[li];
+                if (g >= A.nfree) sk = fma(v, A.x[g - A.nfree], sk);
+            }
+        }
+        s = fma(A.bval[k], sk, s);
+    }
+    A.out[id] = A.Wb[id] * s;
 }
 
 // ------------------------------------------------------------------------------------

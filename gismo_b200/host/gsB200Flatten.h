@@ -40,6 +40,7 @@ struct gsB200Problem
     std::vector<double> fixed;
     std::vector<gsb200_program> programs;
     std::vector<gsb200_neumann> neumann;
+    std::vector<gsb200_neumann> dirichlet;    // Dirichlet sides with their data, when the values are to be L2-projected on the device
 
     gsB200Problem() { std::memset(&pb, 0, sizeof(pb)); pb.abi_version = GSB200_ABI_VERSION; pb.nranks = 1; }
 private:
@@ -162,6 +163,33 @@ void flattenNeumann(const gsBoundaryConditions<T> & bc, short_t dim, gsB200Probl
     st.pb.neumann = st.neumann.empty() ? NULL : st.neumann.data();
 }
 
+/// Dirichlet sides of a gsBoundaryConditions (bc.dirichletSides(), gsBoundaryConditions.h:433) with scalar gsFunctionExpr data
+/// given in physical coordinates, for gsb200_project_dirichlet (the device-side gsDirichletValuesByL2Projection,
+/// gsDirichletValues.h:257-435).  Returns false (and leaves \a st untouched) if a condition is outside that form.
+template <class T>
+bool flattenDirichlet(const gsBoundaryConditions<T> & bc, gsB200Problem & st)
+{
+    std::vector<gsb200_neumann> sides;
+    for (typename gsBoundaryConditions<T>::const_iterator it = bc.dirichletSides().begin(); it != bc.dirichletSides().end(); ++it)
+    {
+        if (it->unknown() != 0 || it->unkComponent() > 0 || it->parametric()) return false;
+        gsb200_neumann sd;
+        std::memset(&sd, 0, sizeof(sd));
+        sd.patch = it->patch(); sd.side = it->side().index(); sd.ndata = 1;
+        if (it->isHomogeneous())
+            sd.data[0] = internal::compileExpr<T>("0", st);
+        else
+        {
+            const gsFunctionExpr<T> * fe = dynamic_cast<const gsFunctionExpr<T>*>(it->function().get());
+            if (!fe || fe->targetDim() != 1) return false;
+            sd.data[0] = internal::compileExpr<T>(fe->expression(0), st);
+        }
+        sides.push_back(sd);
+    }
+    st.dirichlet.swap(sides);
+    return true;
+}
+
 /** Flatten a whole (multi-patch) discretisation.
     \param mp      geometry patches        \param mb   solution bases (one per patch)
     \param mapper  finalized DOF mapper with \a ncomp components
@@ -230,11 +258,19 @@ inline void check(int rc) { if (rc != GSB200_OK) GISMO_ERROR("gsB200: " << gsb20
     innerIndexPtr / valuePtr / rhs.data() itself (pinned staging ring drained by host threads, no intermediate
     std::vector).  \a handle keeps the device context for reassembleInto(). */
 template <class T>
-void assembleInto(gsB200Problem & st, int device, gsB200Handle & handle, gsSparseMatrix<T> & m, gsMatrix<T> & rhs)
+void assembleInto(gsB200Problem & st, int device, gsB200Handle & handle, gsSparseMatrix<T> & m, gsMatrix<T> & rhs,
+                  gsMatrix<T> * projected = NULL)
 {
     const index_t n = st.pb.nfree;
     handle.reset();
     check(gsb200_create(&st.pb, device, &handle.h));
+    if (projected && !st.dirichlet.empty())
+    {   // eliminated values by L2-projection of the Dirichlet data on the device (they also become the assembly's values)
+        projected->setZero(st.pb.nfixed, 1);
+        int iters = 0; double res = 0;
+        check(gsb200_project_dirichlet(handle.h, st.dirichlet.data(), static_cast<int>(st.dirichlet.size()), 4000, 1e-14,
+                                       projected->data(), &iters, &res));
+    }
     check(gsb200_build_pattern(handle.h));
     int64_t nnz = 0;
     check(gsb200_nnz(handle.h, &nnz));

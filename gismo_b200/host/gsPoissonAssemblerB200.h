@@ -31,17 +31,17 @@ public:
     typedef gsPoissonAssembler<T> Base;
 
     gsPoissonAssemblerB200(const gsPoissonPde<T> & pde, const gsMultiBasis<T> & bases)
-    : Base(pde, bases), m_device(0), m_keepPattern(false), m_rank(0), m_nranks(1) { }
+    : Base(pde, bases), m_device(0), m_keepPattern(false), m_rank(0), m_nranks(1), m_deviceDirichlet(false) { }
 
     gsPoissonAssemblerB200(const gsPoissonPde<T> & pde, const gsMultiBasis<T> & bases,
                            dirichlet::strategy dirStrategy, iFace::strategy intStrategy = iFace::glue)
-    : Base(pde, bases, dirStrategy, intStrategy), m_device(0), m_keepPattern(false), m_rank(0), m_nranks(1) { }
+    : Base(pde, bases, dirStrategy, intStrategy), m_device(0), m_keepPattern(false), m_rank(0), m_nranks(1), m_deviceDirichlet(false) { }
 
     gsPoissonAssemblerB200(gsMultiPatch<T> const & patches, gsMultiBasis<T> const & basis,
                            gsBoundaryConditions<T> const & bconditions, const gsFunction<T> & rhs,
                            dirichlet::strategy dirStrategy = dirichlet::elimination,
                            iFace::strategy intStrategy = iFace::glue)
-    : Base(patches, basis, bconditions, rhs, dirStrategy, intStrategy), m_device(0), m_keepPattern(false), m_rank(0), m_nranks(1) { }
+    : Base(patches, basis, bconditions, rhs, dirStrategy, intStrategy), m_device(0), m_keepPattern(false), m_rank(0), m_nranks(1), m_deviceDirichlet(false) { }
 
     void setDevice(int device) { m_device = device; }
     /// Re-use the sparsity pattern of the previous assemble() (same mesh and boundary conditions; new data): values and
@@ -58,6 +58,9 @@ public:
     /// Multi-GPU: this process integrates share \a rank of \a nranks (one process per GPU; include/gsb200.h "Multi-GPU").
     /// After assemble() the caller joins the ranks with gsb200_comm_init(deviceHandle(), id) and gsb200_exchange(deviceHandle()).
     void setRanks(int rank, int nranks) { m_rank = rank; m_nranks = nranks; }
+    /// With DirichletValues = l2Projection: compute the eliminated values on the device (gsb200_project_dirichlet) instead of
+    /// Base::computeDirichletDofs(); conditions outside its form (non-expression data, parametric data) keep the host code.
+    void setDeviceDirichlet(bool on) { m_deviceDirichlet = on; }
     gsb200_assembler * deviceHandle() const { return m_handle.h; }
 
     /// Main assembly routine: same contract as gsPoissonAssembler<T>::assemble().
@@ -70,8 +73,13 @@ public:
         GISMO_ENSURE(m_options.getInt("InterfaceStrategy") == iFace::glue,
                      "gsB200: only InterfaceStrategy=glue (1) is supported");
 
-        // Dirichlet values stay on the reference's host code: they are inputs.
-        Base::computeDirichletDofs();
+        // Dirichlet values: the reference's host code (inputs of the path), or - L2-projection, on request - the device
+        b200::gsB200Problem st;
+        const bool projectOnDevice = m_deviceDirichlet && m_options.getInt("DirichletValues") == dirichlet::l2Projection
+            && !(m_keepPattern && b200::canReassemble(m_handle, m_system.matrix(), m_system.rhs()))
+            && b200::flattenDirichlet(m_pde_ptr->bc(), st);
+        if (!projectOnDevice) Base::computeDirichletDofs();
+        else m_ddof[0].resize(0, 0);
 
         // repeated assemble() on the same mesh (setKeepPattern): new Dirichlet values go up, values and rhs come back
         if (m_keepPattern && b200::canReassemble(m_handle, m_system.matrix(), m_system.rhs()))
@@ -80,7 +88,6 @@ public:
             return;
         }
 
-        b200::gsB200Problem st;
         b200::flatten(m_pde_ptr->domain(), m_bases[0], m_system.colMapper(0), 1, m_ddof[0],
                       m_options, GSB200_FORM_POISSON, st);
         const gsPoissonPde<T> & ppde = static_cast<const gsPoissonPde<T>&>(*m_pde_ptr);
@@ -90,7 +97,7 @@ public:
         b200::flattenNeumann(m_pde_ptr->bc(), m_pde_ptr->domain().parDim(), st);   // gsVisitorNeumann on the device
 
         // explicit device handle: pattern + values straight into m_system (no static state, no staging vectors)
-        b200::assembleInto(st, m_device, m_handle, m_system.matrix(), m_system.rhs());
+        b200::assembleInto(st, m_device, m_handle, m_system.matrix(), m_system.rhs(), projectOnDevice ? &m_ddof[0] : NULL);
     }
 
 protected:
@@ -102,6 +109,7 @@ protected:
     int m_device;
     bool m_keepPattern;
     int m_rank, m_nranks;
+    bool m_deviceDirichlet;
     b200::gsB200Handle m_handle;
 };
 

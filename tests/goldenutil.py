@@ -116,3 +116,22 @@ def check_norms(got, z, tol=1e-12):
     assert abs(got[3] - ref[3]) <= tol * abs(ref[3]), f"int |grad u_h|^2 differs: {got[3]} vs {ref[3]}"
     assert abs(got[0] - ref[0]) <= tol * abs(ref[2]) and abs(got[0] - ref[0]) <= 1e-9 * abs(ref[0]), f"L2 error differs: {got[0]} vs {ref[0]}"
     assert abs(got[1] - ref[1]) <= 1e-8 * abs(ref[1]), f"H1 error differs: {got[1]} vs {ref[1]}"
+
+
+# Fixtures whose eliminated values the reference computed by L2-projection (DirichletValues = 102): Dirichlet data and the sides that
+# carry it (single patches: sides 1..2d minus the Neumann ones; the 2-D grid: read off the DOF map, host.multipatch_topology_2d)
+L2PROJ_CASES = {
+    "sq_p2_m8_expr_l2proj": ("x+y", [(0, s) for s in (1, 2, 3, 4)]),
+    "norms_annulus_nurbs_p3": ("x^2*y+y^2*x", [(0, s) for s in (1, 2, 3, 4)]),
+    "annulus_p3_neumann_expr": ("x+y", [(0, 2), (0, 4)]),
+    "cube_p2_curved_l2proj": ("x+y*z", [(0, s) for s in range(1, 7)]),
+    "cube_p3_visitor_l2proj": ("x*y+z", [(0, s) for s in range(1, 7)]),
+    "grid2x2_p3_l2proj": ("sin(x)+y", None),
+}
+
+
+def l2proj_sides(name, pb):
+    text, sides = L2PROJ_CASES[name]
+    if sides is None:
+        _, sides = host.multipatch_topology_2d(pb)
+    return text, list(sides)

@@ -362,3 +362,18 @@ def test_field_norms_match_the_reference(lib, name):
     x, it, res = A.cg_solve(A.rhs()[:, 0], max_iter=5000, tol=1e-13, check_every=5)
     assert np.abs(x - z["solution"]).max() <= 1e-9 * np.abs(z["solution"]).max()
     A.close()
+
+
+@pytest.mark.parametrize("name", sorted(G.L2PROJ_CASES))
+def test_dirichlet_l2_projection_matches_the_reference(lib, name):
+    """f2: eliminated-DOF values by L2-projection on the device (gsb200_project_dirichlet) against gsDirichletValuesByL2Projection /
+    computeDirichletDofsL2Proj of the reference (2-D, 3-D, NURBS, with Neumann sides, across patches); then the assembly with them."""
+    pb, z = G.load(name, g.expr_compile)
+    text, sides = G.l2proj_sides(name, pb)
+    A = g.DeviceAssembler(pb.with_fixed(None))
+    fx, it, res = A.project_dirichlet([(p_, s_, g.expr_compile(text)) for p_, s_ in sides])
+    ref = z["fixed"][:, 0]
+    assert res <= 1e-12 and np.abs(fx - ref).max() <= 1e-9 * np.abs(ref).max()
+    A.assemble()
+    G.check_against(A.matrix() + (A.rhs(),), z, 1e-9)
+    A.close()

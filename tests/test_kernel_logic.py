@@ -153,3 +153,19 @@ def test_field_norm_kernel_matches_the_reference(emul, name):
     a, b = A.field_norms(u, exp, gp), R.oracle_field_norms(pb, u, exp, gp)
     assert np.abs(a - b).max() <= 1e-13 * np.abs(b).max()
     A.close()
+
+
+@pytest.mark.parametrize("name", sorted(G.L2PROJ_CASES))
+def test_dirichlet_l2_projection_matches_the_reference(emul, name):
+    """f2: gsb200_project_dirichlet (matrix-free boundary mass + Jacobi-CG, interpreted) against the eliminated values the reference
+    computed with gsDirichletValuesByL2Projection / computeDirichletDofsL2Proj; then the assembly with those values."""
+    import gismo_b200 as g
+    pb, z = G.load(name, R.emul_compile)
+    text, sides = G.l2proj_sides(name, pb)
+    A = g.DeviceAssembler(pb.with_fixed(None), lib=emul)          # no eliminated values given: the device computes them
+    fx, it, res = A.project_dirichlet([(p_, s_, R.emul_compile(text)) for p_, s_ in sides])
+    ref = z["fixed"][:, 0]
+    assert res <= 1e-12 and np.abs(fx - ref).max() <= 1e-9 * np.abs(ref).max()
+    A.assemble()
+    G.check_against(A.matrix() + (A.rhs(),), z, 1e-9)            # the rhs carries -K g with the projected g
+    A.close()
