@@ -79,7 +79,11 @@ public:
             && !(m_keepPattern && b200::canReassemble(m_handle, m_system.matrix(), m_system.rhs()))
             && b200::flattenDirichlet(m_pde_ptr->bc(), st);
         if (!projectOnDevice) Base::computeDirichletDofs();
-        else m_ddof[0].resize(0, 0);
+        else
+        {
+            if (m_ddof.size() == 0) m_ddof.resize(m_system.numUnknowns());      // as gsAssembler::computeDirichletDofs does (gsAssembler.hpp:243-244)
+            m_ddof[0].resize(0, 0);
+        }
 
         // repeated assemble() on the same mesh (setKeepPattern): new Dirichlet values go up, values and rhs come back
         if (m_keepPattern && b200::canReassemble(m_handle, m_system.matrix(), m_system.rhs()))
