@@ -1060,7 +1060,7 @@ int gsb200_create(const gsb200_problem *pb, int device, gsb200_assembler **out)
         }
         if ((rc = dev_malloc((void **)&P.d_colflag, (size_t)P.nb * pb->ncomp))) break;
         if ((rc = dev_memset(P.d_colflag, 0, (size_t)P.nb * pb->ncomp, a->stream))) break;
-        if (pb->ncomp == 1) { if ((rc = dev_malloc((void **)&P.d_st, sizeof(unsigned) * (size_t)P.nb * P.nrun))) break; }
+        if ((rc = dev_malloc((void **)&P.d_st, sizeof(unsigned) * (size_t)P.nb * pb->ncomp * P.nrun))) break;
         // ownership: one patch -> slabs along the last direction; several -> whole patches, balanced by element count below
         const int nL = P.dir[L].nfun;
         if (pb->npatches == 1) { P.own_lo = (int)((i64)nL * pb->rank / pb->nranks); P.own_hi = (int)((i64)nL * (pb->rank + 1) / pb->nranks); }

@@ -295,7 +295,7 @@ struct FinalArgs {
     int brow, bcol;
     const unsigned char *colflag;  // per (comp, local fn): 0 skip, 1 canonical, 2 generic, 3 canonical + full stencil
     const i64 *ownrec;             // per (comp, local fn): (colptr << 2) | flag
-    const unsigned *st; int nrun;  // canonical slot table: per (fn, run) start | mask<<16
+    const unsigned *st; int nrun;  // canonical slot table: per (row component, fn, run) start | mask<<16
     const i64 *colptr; const int *inner; double *values;
     double *rhs; const double *fixed; int nfree, nfixed, nrhs;
 };
@@ -362,7 +362,7 @@ GSB_DEVICE i64 final_prepare(const FinalArgs &F, const FinalCtx &c, const OwnerC
     const i64 lj = li + (i64)dL * c.nlow + c.dj_low;
     if (flag == 1) {
         const int run = (F.dim == 2) ? (dL + F.p[1]) : ((dL + F.p[2]) * (2 * F.p[1] + 1) + c.r_low);
-        const unsigned w = F.st[li * F.nrun + run];
+        const unsigned w = F.st[((i64)F.brow * F.nb + li) * F.nrun + run];
         const unsigned mask = w >> 16;
         if ((mask >> c.bit0) & 1u)                   // partner row is free: its rank in the column is known
             return base + (int)(w & 0xffffu) + popc(mask & ((1u << c.bit0) - 1u));
@@ -590,7 +590,7 @@ GSB_NOINLINE void final_slow(const FinalArgs &F, const FinalCtx &c, int fun, i64
 // eliminated partner goes the slow way (right-hand-side contribution)
 GSB_DEVICE void final_canonical(const FinalArgs &F, const FinalCtx &c, int fun, i64 rec, int dL, int run, double val)
 {
-    const unsigned w = F.st[((i64)fun * c.nlow + c.li_low) * F.nrun + run];
+    const unsigned w = F.st[((i64)F.brow * F.nb + (i64)fun * c.nlow + c.li_low) * F.nrun + run];
     const unsigned mask = w >> 16;
     if ((mask >> c.bit0) & 1u) st_stream(F.values + (rec >> 2) + (int)(w & 0xffffu) + popc(mask & ((1u << c.bit0) - 1u)), val);
     else if (F.fixed) final_slow(F, c, fun, rec, dL, val);
@@ -1114,16 +1114,18 @@ GSB_DEVICE void pattern_column(const PatArgs &A, i64 id, int *stage, i64 *stage_
                     mask |= 1u << (j0 - i[0] + A.p[0]);
                 }
             }
-            if (A.ncomp == 1) {
+            {   // slot table per (row component, function, run): the rows of a column do not depend on the column's own component, so the
+                // columns (cc, li) of a vector-valued space write the same words
                 const int run = (A.dim == 2) ? (j1 - i[1] + A.p[1]) : ((j2 - i[2] + A.p[2]) * (2 * A.p[1] + 1) + (j1 - i[1] + A.p[1]));
-                A.st[li * A.nrun + run] = (unsigned)start | (mask << 16);
+                A.st[((i64)cr * A.nb + li) * A.nrun + run] = (unsigned)start | (mask << 16);
             }
         }
         if (pos - pos_cr != full) all_full = false;
     }
-    // 3: whole (2p+1)^d stencil present (per row component, component-major rows) -> closed-form slots; 1: canonical scalar column
+    // 3: whole (2p+1)^d stencil present (per row component, component-major rows) -> closed-form slots; 1: canonical column (rows
+    // ascending in stencil order, cut by eliminated functions: slots from the (start, mask) words)
     if (mono && all_full) A.colflag[id] = 3;
-    else if (mono && A.ncomp == 1) A.colflag[id] = 1;
+    else if (mono) A.colflag[id] = 1;
     else { A.colflag[id] = 2; if (!mono) A.gneed[gi] = 1; }
     if (stage) { *stage_base = base; *stage_n = (int)(pos - base); }
 }
