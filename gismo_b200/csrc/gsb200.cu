@@ -176,11 +176,11 @@ struct PatchDev {
     Dir1D dir[3];
     i64 nb = 0, ngeo_total = 0;
     int *d_dofmap = 0; double *d_coefs = 0, *d_weights = 0;
-    unsigned char *d_colflag = 0; unsigned *d_st = 0; int nrun = 1; i64 *d_ownrec = 0;
+    unsigned char *d_colflag = 0; unsigned *d_st = 0, *d_st2 = 0; int nrun = 1; i64 *d_ownrec = 0;
     int own_lo = 0, own_hi = 0;     // owner range along the last direction on this rank
     double *d_lc = 0;               // line coefficients of the geometry (fused.cuh, k_line_coefs), 0: fused first sweep not available
     std::vector<int> sufmin;        // sufmin[x] = smallest free column with a preimage in last-direction layers >= x (scalar spaces): columns below it are final once layers < x are done
-    void release() { for (int k = 0; k < 3; ++k) dir[k].release(); dev_free(d_dofmap); dev_free(d_coefs); dev_free(d_weights); dev_free(d_colflag); dev_free(d_st); dev_free(d_ownrec); dev_free(d_lc); }
+    void release() { for (int k = 0; k < 3; ++k) dir[k].release(); dev_free(d_dofmap); dev_free(d_coefs); dev_free(d_weights); dev_free(d_colflag); dev_free(d_st); dev_free(d_st2); dev_free(d_ownrec); dev_free(d_lc); }
 };
 
 } // namespace gsb
@@ -291,7 +291,7 @@ static void fill_pat_args(const gsb200_assembler *a, const PatchDev &P, PatArgs 
         A.plo[k] = k < P.dim ? P.dir[k].d_plo : 0; A.phi[k] = k < P.dim ? P.dir[k].d_phi : 0;
     }
     A.dofmap = P.d_dofmap; A.nb = P.nb; A.nfree = a->nfree; A.own_lo = P.own_lo; A.own_hi = P.own_hi;
-    A.npre = a->d_npre; A.colflag = P.d_colflag; A.st = P.d_st; A.nrun = P.nrun;
+    A.npre = a->d_npre; A.colflag = P.d_colflag; A.st = P.d_st; A.st2 = P.d_st2; A.nrun = P.nrun;
 }
 
 static int build_pattern(gsb200_assembler *a)
@@ -579,7 +579,7 @@ static int assemble_pass(gsb200_assembler *a)
                     Fa.plo[k] = k < dim ? P.dir[k].d_plo : 0; Fa.phi[k] = k < dim ? P.dir[k].d_phi : 0;
                 }
                 Fa.dofmap = P.d_dofmap; Fa.nb = P.nb; Fa.brow = brow; Fa.bcol = bcol;
-                Fa.colflag = P.d_colflag; Fa.ownrec = P.d_ownrec; Fa.st = P.d_st; Fa.nrun = P.nrun;
+                Fa.colflag = P.d_colflag; Fa.ownrec = P.d_ownrec; Fa.st = P.d_st; Fa.st2 = P.d_st2; Fa.nrun = P.nrun;
                 Fa.colptr = a->d_colptr; Fa.inner = a->d_inner; Fa.values = a->d_values;
                 Fa.rhs = a->d_rhs; Fa.fixed = a->d_fixed; Fa.nfree = N; Fa.nfixed = a->nfixed; Fa.nrhs = a->nrhs;
 
@@ -1061,6 +1061,7 @@ int gsb200_create(const gsb200_problem *pb, int device, gsb200_assembler **out)
         if ((rc = dev_malloc((void **)&P.d_colflag, (size_t)P.nb * pb->ncomp))) break;
         if ((rc = dev_memset(P.d_colflag, 0, (size_t)P.nb * pb->ncomp, a->stream))) break;
         if ((rc = dev_malloc((void **)&P.d_st, sizeof(unsigned) * (size_t)P.nb * pb->ncomp * P.nrun))) break;
+        if (pb->npatches > 1 && (rc = dev_malloc((void **)&P.d_st2, sizeof(unsigned) * (size_t)P.nb * pb->ncomp * P.nrun))) break;
         // ownership: one patch -> slabs along the last direction; several -> whole patches, balanced by element count below
         const int nL = P.dir[L].nfun;
         if (pb->npatches == 1) { P.own_lo = (int)((i64)nL * pb->rank / pb->nranks); P.own_hi = (int)((i64)nL * (pb->rank + 1) / pb->nranks); }

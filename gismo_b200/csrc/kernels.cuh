@@ -295,7 +295,8 @@ struct FinalArgs {
     int brow, bcol;
     const unsigned char *colflag;  // per (comp, local fn): 0 skip, 1 canonical, 2 generic, 3 canonical + full stencil
     const i64 *ownrec;             // per (comp, local fn): (colptr << 2) | flag
-    const unsigned *st; int nrun;  // canonical slot table: per (row component, fn, run) start | mask<<16
+    const unsigned *st; int nrun;  // canonical slot table: per (row component, fn, run) start | mask<<16 of the standard rows
+    const unsigned *st2;           // ... and of the rows coupled with other patches (0: single patch)
     const i64 *colptr; const int *inner; double *values;
     double *rhs; const double *fixed; int nfree, nfixed, nrhs;
 };
@@ -366,6 +367,11 @@ GSB_DEVICE i64 final_prepare(const FinalArgs &F, const FinalCtx &c, const OwnerC
         const unsigned mask = w >> 16;
         if ((mask >> c.bit0) & 1u)                   // partner row is free: its rank in the column is known
             return base + (int)(w & 0xffffu) + popc(mask & ((1u << c.bit0) - 1u));
+        if (F.st2) {                                 // ... or a DOF shared with another patch: second sequence of the column
+            const unsigned w2 = F.st2[((i64)F.brow * F.nb + li) * F.nrun + run];
+            const unsigned mask2 = w2 >> 16;
+            if ((mask2 >> c.bit0) & 1u) return base + (int)(w2 & 0xffffu) + popc(mask2 & ((1u << c.bit0) - 1u));
+        }
         if (!F.fixed) return -1;
     }
     const int gi = F.dofmap[F.bcol * F.nb + li];
@@ -592,8 +598,13 @@ GSB_DEVICE void final_canonical(const FinalArgs &F, const FinalCtx &c, int fun, 
 {
     const unsigned w = F.st[((i64)F.brow * F.nb + (i64)fun * c.nlow + c.li_low) * F.nrun + run];
     const unsigned mask = w >> 16;
-    if ((mask >> c.bit0) & 1u) st_stream(F.values + (rec >> 2) + (int)(w & 0xffffu) + popc(mask & ((1u << c.bit0) - 1u)), val);
-    else if (F.fixed) final_slow(F, c, fun, rec, dL, val);
+    if ((mask >> c.bit0) & 1u) { st_stream(F.values + (rec >> 2) + (int)(w & 0xffffu) + popc(mask & ((1u << c.bit0) - 1u)), val); return; }
+    if (F.st2) {
+        const unsigned w2 = F.st2[((i64)F.brow * F.nb + (i64)fun * c.nlow + c.li_low) * F.nrun + run];
+        const unsigned mask2 = w2 >> 16;
+        if ((mask2 >> c.bit0) & 1u) { st_stream(F.values + (rec >> 2) + (int)(w2 & 0xffffu) + popc(mask2 & ((1u << c.bit0) - 1u)), val); return; }
+    }
+    if (F.fixed) final_slow(F, c, fun, rec, dL, val);
 }
 
 
@@ -1025,7 +1036,7 @@ struct PatArgs {
     const int *npre;               // per global dof: number of pre-images
     unsigned long long *len;       // per global column: entry count (upper bound for coupled columns)
     const i64 *colptr; int *inner; int *cursor;
-    unsigned char *colflag; unsigned *st; int nrun;
+    unsigned char *colflag; unsigned *st, *st2; int nrun;      // st2: slot words of the coupled rows (0: single patch)
     unsigned char *gneed;          // per global column: 1 sort, 2 sort+unique
 };
 
@@ -1095,38 +1106,59 @@ GSB_DEVICE void pattern_column(const PatArgs &A, i64 id, int *stage, i64 *stage_
         A.colflag[id] = 2; A.gneed[gi] = 2;
         return;
     }
+    // A column that lives in one patch.  Its rows come in two ascending sequences per row component: the standard DOFs in stencil order,
+    // then the DOFs coupled with other patches (numbered after all standard ones, gsDofMapper.cpp:281-323) in stencil order.  They are
+    // written in that order - which is the sorted order whenever the checks below hold - and every (row component, run) gets two
+    // (start, mask) words, one per sequence, from which the final sweep takes its slots without searching.
     i64 pos = base;
-    int prev = -1; bool mono = true;
+    bool mono = true; int prev_block_last = -1;
     i64 full = 1;
     for (int k = 0; k < A.dim; ++k) full *= 2 * A.p[k] + 1;
-    bool all_full = true;            // every row component contributes the whole (2p+1)^d stencil
+    bool all_full = true;            // every row component contributes the whole (2p+1)^d stencil of standard DOFs
     for (int cr = 0; cr < A.ncomp; ++cr) {
-        const i64 pos_cr = pos;
+        int nstd = 0, ncpl = 0;
+        for (int j2 = lo[2]; j2 <= hi[2]; ++j2) for (int j1 = lo[1]; j1 <= hi[1]; ++j1) for (int j0 = lo[0]; j0 <= hi[0]; ++j0) {
+            const int gj = A.dofmap[(i64)cr * A.nb + ((i64)j2 * A.n[1] + j1) * A.n[0] + j0];
+            if (gj < A.nfree) { if (A.npre[gj] > 1) ++ncpl; else ++nstd; }
+        }
+        i64 ps = pos, pc = pos + nstd;
+        int prev_s = prev_block_last, prev_c = -1;
         for (int j2 = lo[2]; j2 <= hi[2]; ++j2) for (int j1 = lo[1]; j1 <= hi[1]; ++j1) {
-            unsigned mask = 0; const int start = (int)(pos - base);
+            unsigned mask = 0, mask2 = 0; const int start = (int)(ps - base), start2 = (int)(pc - base);
             for (int j0 = lo[0]; j0 <= hi[0]; ++j0) {
                 const int gj = A.dofmap[(i64)cr * A.nb + ((i64)j2 * A.n[1] + j1) * A.n[0] + j0];
-                if (gj < A.nfree) {
-                    if (stage) stage[pos - base] = gj; else A.inner[pos] = gj;
-                    ++pos;
-                    if (gj <= prev) mono = false;
-                    prev = gj;
+                if (gj >= A.nfree) continue;
+                if (A.npre[gj] > 1) {
+                    if (stage) stage[pc - base] = gj; else A.inner[pc] = gj;
+                    ++pc;
+                    if (gj <= prev_c) mono = false;
+                    prev_c = gj;
+                    mask2 |= 1u << (j0 - i[0] + A.p[0]);
+                } else {
+                    if (stage) stage[ps - base] = gj; else A.inner[ps] = gj;
+                    ++ps;
+                    if (gj <= prev_s) mono = false;
+                    prev_s = gj;
                     mask |= 1u << (j0 - i[0] + A.p[0]);
                 }
             }
-            {   // slot table per (row component, function, run): the rows of a column do not depend on the column's own component, so the
-                // columns (cc, li) of a vector-valued space write the same words
-                const int run = (A.dim == 2) ? (j1 - i[1] + A.p[1]) : ((j2 - i[2] + A.p[2]) * (2 * A.p[1] + 1) + (j1 - i[1] + A.p[1]));
-                A.st[((i64)cr * A.nb + li) * A.nrun + run] = (unsigned)start | (mask << 16);
-            }
+            const int run = (A.dim == 2) ? (j1 - i[1] + A.p[1]) : ((j2 - i[2] + A.p[2]) * (2 * A.p[1] + 1) + (j1 - i[1] + A.p[1]));
+            // (the rows of a column do not depend on the column's own component: the columns (cc, li) of a vector-valued space write the same words)
+            A.st[((i64)cr * A.nb + li) * A.nrun + run] = (unsigned)start | (mask << 16);
+            if (A.st2) A.st2[((i64)cr * A.nb + li) * A.nrun + run] = (unsigned)start2 | (mask2 << 16);
+            else if (mask2) mono = false;
         }
-        if (pos - pos_cr != full) all_full = false;
+        // the first coupled row must follow the last standard one, and this block the previous one
+        if (ncpl > 0 && nstd > 0) { const int first_c = stage ? stage[pos + nstd - base] : A.inner[pos + nstd]; if (first_c <= prev_s) mono = false; }
+        prev_block_last = ncpl > 0 ? prev_c : prev_s;
+        if (nstd != full || ncpl != 0) all_full = false;
+        pos += nstd + ncpl;
     }
-    // 3: whole (2p+1)^d stencil present (per row component, component-major rows) -> closed-form slots; 1: canonical column (rows
-    // ascending in stencil order, cut by eliminated functions: slots from the (start, mask) words)
+    // 3: whole (2p+1)^d stencil of standard DOFs (per row component, component-major rows) -> closed-form slots; 1: canonical column
+    // (slots from the (start, mask) words); 2: anything else (rows sorted afterwards, binary search in the final sweep)
     if (mono && all_full) A.colflag[id] = 3;
     else if (mono) A.colflag[id] = 1;
-    else { A.colflag[id] = 2; if (!mono) A.gneed[gi] = 1; }
+    else { A.colflag[id] = 2; A.gneed[gi] = 1; }
     if (stage) { *stage_base = base; *stage_n = (int)(pos - base); }
 }
 
