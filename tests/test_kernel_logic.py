@@ -169,3 +169,47 @@ def test_dirichlet_l2_projection_matches_the_reference(emul, name):
     A.assemble()
     G.check_against(A.matrix() + (A.rhs(),), z, 1e-9)            # the rhs carries -K g with the projected g
     A.close()
+
+
+def test_patches_are_balanced_over_ranks_longest_first(emul):
+    """gsb200_create distributes whole patches over the ranks: longest processing time first onto the least loaded rank (SURVEY 8e:
+    the 21 yeti patches over 8 GPUs).  The library's choice (which columns a rank stores) must be the one of distributed.patch_owners,
+    and the ranks' pieces together give the reference matrix."""
+    from gismo_b200 import distributed as D
+    pb0, z = G.load("yeti_mp2_p2_m2", R.emul_compile)
+    nranks = 8
+    costs = []
+    for pa in pb0.patches:
+        c = 1
+        for k in range(pb0.dim):
+            c *= (len(np.unique(pa.space_knots[k])) - 1) * (pa.space_degree[k] + 1)
+        costs.append(c)
+    owner = D.patch_owners(costs, nranks)
+    assert max(np.bincount(owner, minlength=nranks)) - min(np.bincount(owner, minlength=nranks)) <= 1      # equal patches: 3/3/3/3/3/2/2/2
+    counts = np.zeros(pb0.nfree + 1, np.int32)
+    for pa in pb0.patches:
+        np.add.at(counts, pa.dofmap[pa.dofmap < pb0.nfree], 1)
+    pieces = []
+    for r in range(nranks):
+        pb = pb0.with_fixed(pb0.fixed, rank=r, nranks=nranks)
+        o, i, v, b, _ = R.lib_assemble(emul, pb)
+        stored = np.diff(o) > 0
+        mine = np.zeros(pb0.nfree, bool)
+        for ip, pa in enumerate(pb0.patches):
+            if owner[ip] == r:
+                g_ = pa.dofmap[pa.dofmap < pb0.nfree]
+                mine[g_] = True
+        single = counts[:pb0.nfree] == 1
+        assert np.array_equal(stored & single, mine & single), f"rank {r} stores other patches than the balanced assignment gives it"
+        assert np.all(stored[~single & (counts[:pb0.nfree] > 1)]), "coupled columns are patterned on every rank"
+        pieces.append((o, i, v, b))
+    # sum the coupled columns by hand (what gsb200_exchange does) and compare with the reference
+    lens = np.max([np.diff(p[0]) for p in pieces], axis=0)
+    outer = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    values = np.zeros(outer[-1]); inner = np.zeros(outer[-1], np.int32); rhs = np.zeros_like(pieces[0][3])
+    for o, i, v, b in pieces:
+        rhs += b
+        for c in np.nonzero(np.diff(o) > 0)[0]:
+            values[outer[c]:outer[c + 1]] += v[o[c]:o[c + 1]]
+            inner[outer[c]:outer[c + 1]] = i[o[c]:o[c + 1]]
+    G.check_against((outer, inner, values, rhs), z, TOL)
