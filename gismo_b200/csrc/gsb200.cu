@@ -202,7 +202,10 @@ struct gsb200_assembler {
     std::vector<NeumannSide> neumann; double *d_face = 0; size_t face_cap = 0;
     stream_t stream = 0;
     bool pattern_built = false, assembled = false, any_generic = false;
-    i64 ws_limit = 0; void *ws = 0; size_t ws_size = 0;
+    i64 ws_limit = 0; void *ws[4] = {0, 0, 0, 0}; size_t ws_size[4] = {0, 0, 0, 0};      // one workspace per lane (patches of a multi-patch problem run on up to 3 streams)
+#ifndef GSB200_EMULATE
+    cudaStream_t lanes[4] = {0, 0, 0, 0}; cudaEvent_t lane_ev[4] = {0, 0, 0, 0};
+#endif
     gsb200_timings tm;
     int *d_seg = 0; size_t seg_cap = 0; std::vector<int> seg_host; size_t seg_used = 0;
     bool plan_valid = false; i64 plan_limit = 0; size_t ev_used = 0;
@@ -233,7 +236,11 @@ struct gsb200_assembler {
         for (auto &p : patches) p.release();
         dev_free(d_fixed); dev_free(d_rhs); dev_free(d_values); dev_free(d_colptr); dev_free(d_inner); dev_free(d_npre);
         for (void *b : prog_bufs) dev_free(b);
-        dev_free(ws); dev_free(d_seg); dev_free(d_face); dev_free(d_outer32);
+        for (int k = 0; k < 4; ++k) dev_free(ws[k]);
+        dev_free(d_seg); dev_free(d_face); dev_free(d_outer32);
+#ifndef GSB200_EMULATE
+        for (int k = 0; k < 4; ++k) { if (lanes[k]) { cudaStreamSynchronize(lanes[k]); cudaStreamDestroy(lanes[k]); } if (lane_ev[k]) cudaEventDestroy(lane_ev[k]); }
+#endif
 #ifndef GSB200_EMULATE
         if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
         if (ev_done) cudaEventDestroy(ev_done);
@@ -462,16 +469,45 @@ static int assemble_pass(gsb200_assembler *a)
     // workspace budget
     i64 limit = a->plan_valid ? a->plan_limit : a->ws_limit;
 #ifndef GSB200_EMULATE
-    if (limit <= 0) { size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot); limit = (i64)((fr + dev_pool_idle() + a->ws_size) * 0.85); }      // (what the pool holds idle is ours to reuse)
+    if (limit <= 0) { size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot); limit = (i64)((fr + dev_pool_idle() + a->ws_size[0] + a->ws_size[1] + a->ws_size[2] + a->ws_size[3]) * 0.85); }      // (what the pool holds idle is ours to reuse)
 #else
     if (limit <= 0) limit = (i64)1 << 30;
 #endif
     a->plan_limit = limit;
+    // Lanes: the patches of a multi-patch problem are independent up to the atomically summed interface columns, and their kernels
+    // are short (config 4: 216 launches of ~0.6 ms per step, 17 % of the warp slots busy): they go round-robin onto up to three
+    // streams, each with its own workspace, so that one patch's ramp-up and tail overlap the others' (GSB200_LANES=1: one stream).
+    int NL = 1;
+#ifndef GSB200_EMULATE
+    {
+        static const int lanes_env = [] { const char *e = getenv("GSB200_LANES"); return e ? atoi(e) : 3; }();
+        int owned = 0; for (auto &P : a->patches) if (P.own_hi > P.own_lo) ++owned;
+        NL = std::max(1, std::min(std::min(lanes_env, 4), owned));
+        if (NL > 1 && !dry_run()) {
+            for (int l = 1; l < NL; ++l) {
+                if (!a->lanes[l]) GSB_TRY(dev_check(cudaStreamCreateWithFlags(&a->lanes[l], cudaStreamNonBlocking), "lane stream"));
+                if (!a->lane_ev[l]) GSB_TRY(dev_check(cudaEventCreateWithFlags(&a->lane_ev[l], cudaEventDisableTiming), "lane event"));
+            }
+            if (!a->lane_ev[0]) GSB_TRY(dev_check(cudaEventCreateWithFlags(&a->lane_ev[0], cudaEventDisableTiming), "lane event"));
+            GSB_TRY(dev_check(cudaEventRecord(a->lane_ev[0], a->stream), "event record"));      // the zeroed rhs / values are ready
+            for (int l = 1; l < NL; ++l) GSB_TRY(dev_check(cudaStreamWaitEvent(a->lanes[l], a->lane_ev[0], 0), "stream wait"));
+        }
+    }
+#endif
+    limit /= NL;
+    const bool timed = NL == 1;         // per-stage events only make sense on one stream
+    int owned_seen = 0;
 
     size_t segoff = 0;   // every sweep of every chunk gets its own slice of the segment buffer
     for (size_t ip = 0; ip < a->patches.size(); ++ip) {
         PatchDev &P = a->patches[ip];
         if (P.own_hi <= P.own_lo) continue;
+        const int lane = owned_seen++ % NL;
+#ifndef GSB200_EMULATE
+        stream_t s = lane ? a->lanes[lane] : a->stream;
+#else
+        (void)lane;
+#endif
         const Dir1D &d0 = P.dir[0], &d1 = P.dir[1], &dL = P.dir[L];
         const i64 Q0 = d0.Q, Q1 = dim == 3 ? d1.Q : 1;
         const i64 NI0 = (i64)d0.nfun * (2 * d0.p + 1), NI1 = dim == 3 ? (i64)d1.nfun * (2 * d1.p + 1) : 1;
@@ -517,12 +553,12 @@ static int assemble_pass(gsb200_assembler *a)
             const int eL0 = dL.ffirst[x_lo], eL1 = dL.flast[x_hi - 1] + 1, ELc = eL1 - eL0;
             const i64 QLc = (i64)ELc * dL.q;
             const size_t need = (size_t)(perq * QLc) * 8 + 6 * 256 + (size_t)a1_pad * 8;
-            if (need > a->ws_size) {
+            if (need > a->ws_size[lane]) {
                 GSB_TRY(dev_sync(s));
-                dev_free(a->ws); a->ws = 0; a->ws_size = 0;
-                GSB_TRY(dev_malloc(&a->ws, need)); a->ws_size = need;
+                dev_free(a->ws[lane]); a->ws[lane] = 0; a->ws_size[lane] = 0;
+                GSB_TRY(dev_malloc(&a->ws[lane], need)); a->ws_size[lane] = need;
             }
-            double *w = (double *)a->ws;
+            double *w = (double *)a->ws[lane];
             auto carve = [&](i64 count) { double *p = w; w += (count + 31) / 32 * 32; return p; };   // 256-byte aligned pieces
             double *D = carve(fused ? 0 : ncD * Q0 * Q1 * QLc);
             double *A1 = carve(no1 * A1I0 * Q1 * QLc + a1_pad) + a1_pad;      // (the mirrored reads of the first functions reach a few doubles below)
@@ -553,7 +589,7 @@ static int assemble_pass(gsb200_assembler *a)
                 const int pgl = P.dir[L].pg1;
                 const bool rat = P.d_weights != 0, hot = a->form == GSB200_FORM_POISSON && G.symD;
                 if (!fused) {
-                    mark(a, 0);
+                    if (timed) mark(a, 0);
                     static const int gblk = [] { const char *e = getenv("GSB200_GEO_BLOCK"); const int v = e ? atoi(e) : 128; return (v == 64 || v == 256) ? v : 128; }();
                     const dim3 gg((unsigned)((QLc + gblk - 1) / gblk), dim == 3 ? (unsigned)Q1 : (unsigned)Q0, dim == 3 ? (unsigned)Q0 : 1u);
                     if (gg.y > 65535u || gg.z > 65535u) { set_error("more than 65535 quadrature points per direction"); return GSB200_EUNSUPPORTED; }
@@ -603,7 +639,7 @@ static int assemble_pass(gsb200_assembler *a)
                     const int nseg = nseg_for(A.ncol * (d0.p + 1), d0.nfun, d0.p + 1);
                     std::vector<int> seg = make_segments(d0, 0, d0.nfun, nseg);
                     A.seg = a->d_seg + segoff; GSB_TRY(upload_segments(a, seg, &segoff));
-                    mark(a, 1);
+                    if (timed) mark(a, 1);
                     i64 fpp = 0; int nin, nout;
                     stage_io(kind, stage, &nin, &nout);
                     if (fused) {
@@ -660,7 +696,7 @@ static int assemble_pass(gsb200_assembler *a)
                         std::vector<int> seg1 = make_segments(d1, 0, d1.nfun, nseg1);
                         SA.tiles = a->d_seg + segoff; GSB_TRY(upload_segments(a, tiles, &segoff));
                         SA.seg1 = a->d_seg + segoff; GSB_TRY(upload_segments(a, seg1, &segoff));
-                        mark(a, 2);
+                        if (timed) mark(a, 2);
                         i64 fpp2 = 0, fpp3 = 0;
                         const dim3 grid((unsigned)NI0, (unsigned)(tiles.size() / 4), (unsigned)(seg1.size() / 4));
                         GSB_TRY(launch_s23(kind, d1.p + 1, SA, grid, ne_max, s, &fpp2, &fpp3));
@@ -701,7 +737,7 @@ static int assemble_pass(gsb200_assembler *a)
                         const int nseg = nseg_for(A.ncol * (d1.p + 1), d1.nfun, d1.p + 1);
                         std::vector<int> seg = make_segments(d1, 0, d1.nfun, nseg);
                         A.seg = a->d_seg + segoff; GSB_TRY(upload_segments(a, seg, &segoff));
-                        mark(a, 2);
+                        if (timed) mark(a, 2);
                         GSB_TRY(dispatch_sweep(kind, a1_half ? 4 : 1, d1.p + 1, A, (int)seg.size() / 4, s, &fpp));
                         stage_io(kind, 1, &nin, &nout);
                         account(1, A, seg, fpp, a1_half ? nin * (double)(d0.p + 1) / (double)W0 : nin, nout, NI1);      // (every stored value is read once from HBM)
@@ -713,7 +749,7 @@ static int assemble_pass(gsb200_assembler *a)
                         const int nseg = nseg_for(A.ncol, x_hi - x_lo, dL.p + 1);
                         std::vector<int> seg = make_segments(dL, x_lo, x_hi, nseg);
                         A.seg = a->d_seg + segoff; GSB_TRY(upload_segments(a, seg, &segoff));
-                        mark(a, 3);
+                        if (timed) mark(a, 3);
                         GSB_TRY(dispatch_sweep(kind, 2, dL.p + 1, A, (int)seg.size() / 4, s, &fpp));
                         stage_io(kind, 2, &nin, &nout); account(2, A, seg, fpp, nin, nout, (i64)(x_hi - x_lo) * (2 * dL.p + 1));
                     }
@@ -733,14 +769,14 @@ static int assemble_pass(gsb200_assembler *a)
                         const int nseg = nseg_for(A.ncol, x_hi - x_lo, dL.p + 1);
                         std::vector<int> seg = make_segments(dL, x_lo, x_hi, nseg);
                         A.seg = a->d_seg + segoff; GSB_TRY(upload_segments(a, seg, &segoff));
-                        mark(a, 2);
+                        if (timed) mark(a, 2);
                         GSB_TRY(dispatch_sweep(kind, 2, dL.p + 1, A, (int)seg.size() / 4, s, &fpp));
                         stage_io(kind, 2, &nin, &nout); account(1, A, seg, fpp, nin, nout, (i64)(x_hi - x_lo) * (2 * dL.p + 1));
                     }
                 }
                 // ---------------- K3: load vector (once per chunk)
                 if (with_load) {
-                    mark(a, 4);
+                    if (timed) mark(a, 4);
                     for (int c = 0; c < nf; ++c) {
                         double *V1c = V1 + (fused ? (i64)c * n0 * Q1 * QLc : 0);      // the fused first sweep produced all components at once
                         const int rcol = a->form == GSB200_FORM_ELASTICITY ? 0 : c;   // rhs column
@@ -810,6 +846,13 @@ static int assemble_pass(gsb200_assembler *a)
             x_lo = x_hi;
         }
     }
+#ifndef GSB200_EMULATE
+    if (NL > 1 && !dry_run())
+        for (int l = 1; l < NL; ++l) {
+            GSB_TRY(dev_check(cudaEventRecord(a->lane_ev[l], a->lanes[l]), "event record"));
+            GSB_TRY(dev_check(cudaStreamWaitEvent(a->stream, a->lane_ev[l], 0), "stream wait"));
+        }
+#endif
     // ---------------- Neumann boundary load (rank 0 of a multi-rank run adds it once per side it owns)
     for (const auto &ns : a->neumann) {
         PatchDev &P = a->patches[ns.patch];
