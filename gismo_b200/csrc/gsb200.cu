@@ -202,7 +202,7 @@ struct gsb200_assembler {
     std::vector<NeumannSide> neumann; double *d_face = 0; size_t face_cap = 0;
     stream_t stream = 0;
     bool pattern_built = false, assembled = false, any_generic = false;
-    i64 ws_limit = 0; void *ws[4] = {0, 0, 0, 0}; size_t ws_size[4] = {0, 0, 0, 0};      // one workspace per lane (patches of a multi-patch problem run on up to 3 streams)
+    i64 ws_limit = 0; void *ws[4] = {0, 0, 0, 0}; size_t ws_size[4] = {0, 0, 0, 0};      // one workspace per lane (patches of a multi-patch problem run on up to 4 streams)
 #ifndef GSB200_EMULATE
     cudaStream_t lanes[4] = {0, 0, 0, 0}; cudaEvent_t lane_ev[4] = {0, 0, 0, 0};
 #endif
@@ -475,12 +475,12 @@ static int assemble_pass(gsb200_assembler *a)
 #endif
     a->plan_limit = limit;
     // Lanes: the patches of a multi-patch problem are independent up to the atomically summed interface columns, and their kernels
-    // are short (config 4: 216 launches of ~0.6 ms per step, 17 % of the warp slots busy): they go round-robin onto up to three
+    // are short (config 4: 216 launches of ~0.6 ms per step, 17 % of the warp slots busy): they go round-robin onto up to four
     // streams, each with its own workspace, so that one patch's ramp-up and tail overlap the others' (GSB200_LANES=1: one stream).
     int NL = 1;
 #ifndef GSB200_EMULATE
     {
-        static const int lanes_env = [] { const char *e = getenv("GSB200_LANES"); return e ? atoi(e) : 3; }();
+        static const int lanes_env = [] { const char *e = getenv("GSB200_LANES"); return e ? atoi(e) : 4; }();
         int owned = 0; for (auto &P : a->patches) if (P.own_hi > P.own_lo) ++owned;
         NL = std::max(1, std::min(std::min(lanes_env, 4), owned));
         if (NL > 1 && !dry_run()) {
