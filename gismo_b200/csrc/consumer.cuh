@@ -635,6 +635,11 @@ static int cg_solve(gsb200_assembler *a, const double *b_dev, int max_iter, doub
 #define GSB_CG_MARK(i) do { } while (0)
 #endif
 #ifndef GSB200_EMULATE
+    // NCCL connects its peer-to-peer and ring channels at the first use of each pattern (hundreds of milliseconds): one untimed
+    // round of the loop's collectives (the halo exchange is idempotent, the scalars are scratch) before the clock starts
+    if (P.halo) { GSB_TRY(cg_halo(a, P, Pv)); GSB_TRY(comm_allreduce(a, S + 6, 1)); GSB_TRY(comm_allreduce(a, S + 6, 2)); }
+    else if (multi) { GSB_TRY(comm_allreduce(a, S + 6, 1)); GSB_TRY(comm_allreduce(a, S + 6, 2)); }
+    a->xchg_bytes = 0;
     cudaEvent_t le0, le1; cudaEventCreate(&le0); cudaEventCreate(&le1); cudaEventRecord(le0, s);
 #endif
     while (it < max_iter && rr > thr) {
