@@ -350,8 +350,7 @@ static int build_pattern(gsb200_assembler *a)
         for (int k = 0; k < P.dim; ++k) maxlen *= 2 * P.dir[k].p + 1;
         const int stride = maxlen | 1;
         const size_t smem = (size_t)32 * stride * sizeof(int);
-        static const bool pat_old = getenv("GSB200_PATTERN_OLD") != 0;
-        if (!pat_old && smem <= 200 * 1024) {      // coalesced fill through per-lane shared-memory rows
+        if (smem <= 200 * 1024) {      // coalesced fill through per-lane shared-memory rows
             GSB_TRY(grant_dynamic_smem((const void *)k_pattern_staged, 200 * 1024));
             k_pattern_staged<<<(unsigned)((nt + 31) / 32), 32, smem, s>>>(A, stride); note_launch();
         } else
@@ -623,9 +622,8 @@ static int assemble_pass(gsb200_assembler *a)
                     SweepArgs A; memset(&A, 0, sizeof A);
                     A.first = d.d_first; A.nexit = d.d_nexit; A.tab = d.d_tab; A.tabl = d.d_tabl; A.q = d.q; A.p = d.p; A.fin = Fa;
                     A.out_bq = 1; A.out_od = 1; A.d_off = d.p;
-                    { static const int pf = [] { const char *e = getenv("GSB200_PF"); return e ? atoi(e) : 0; }(); A.pf_dist = pf; }
-                    { static const int wb = [] { const char *e = getenv("GSB200_WB"); return e ? atoi(e) : -1; }();
-                      A.wb_stores = wb >= 0 ? wb : ((dL.q * 8) % 32 != 0); }
+                    A.pf_dist = 0;                                   // (L2 prefetch hints: no gain once cp.async is in, profiles/r01b_layout_experiments.txt)
+                    A.wb_stores = (dL.q * 8) % 32 != 0;              // pieces that do not fill 32-byte sectors wait in L2 for their neighbours
                     return A;
                 };
                 auto account = [&](int slot, const SweepArgs &A, const std::vector<int> &seg, i64 fpp, double nin, double nout, i64 npairs_out) {
@@ -785,9 +783,8 @@ static int assemble_pass(gsb200_assembler *a)
                         auto vbase = [&](const Dir1D &d) { V.ffirst = d.d_ffirst; V.flast = d.d_flast; V.first = d.d_first; V.tab = d.d_tab; V.q = d.q; V.p1 = d.p + 1; };
                         // window kernel when the rule has p+1 points (reads its input once), else one thread per (column, function)
                         auto vlaunch = [&](const Dir1D &d) -> int {
-                            static const bool vold = getenv("GSB200_VSWEEP_OLD") != 0;
                             const int P1 = d.p + 1, nx = V.x_hi - V.x_lo;
-                            if (vold || d.q != P1 || P1 < 2 || P1 > 5) {
+                            if (d.q != P1 || P1 < 2 || P1 > 5) {
                                 GSB_LAUNCH(k_vsweep, dim3((unsigned)((V.ncol + 127) / 128), nx), dim3(128), s, V);
                                 return 0;
                             }
