@@ -213,3 +213,35 @@ def test_patches_are_balanced_over_ranks_longest_first(emul):
             values[outer[c]:outer[c + 1]] += v[o[c]:o[c + 1]]
             inner[outer[c]:outer[c + 1]] = i[o[c]:o[c + 1]]
     G.check_against((outer, inner, values, rhs), z, TOL)
+
+
+def test_consumer_entry_points_reject_bad_states(emul):
+    """Error behaviour of the round-2 entry points (status codes, not crashes): exchange / CG before an assembly, field norms of a
+    vector-valued space, malformed Dirichlet sides, a multi-rank exchange without a communicator."""
+    import ctypes as C
+    import gismo_b200 as g
+    from gismo_b200 import capi
+    pb, _ = G.load("cube_p2_m5", R.emul_compile)
+    A = g.DeviceAssembler(pb, lib=emul)
+    assert emul.gsb200_exchange(A._h) == -7                       # GSB200_ESTATE: nothing assembled yet
+    it, res = C.c_int(0), C.c_double(0)
+    assert emul.gsb200_cg_solve(A._h, None, None, 10, 1e-8, 5, C.byref(it), C.byref(res)) == -7
+    A.assemble()
+    A.exchange()                                                  # one rank: a no-op
+    assert A.comm_stats() == (0, 0) or A.comm_stats()[0] == 0
+    bad = (capi.Neumann * 1)()
+    bad[0].patch, bad[0].side, bad[0].ndata = 0, 9, 1             # side out of range
+    out = np.zeros(pb.nfixed)
+    assert emul.gsb200_project_dirichlet(A._h, bad, 1, 10, 1e-8, out.ctypes.data_as(C.POINTER(C.c_double)), None, None) == -1
+    A.close()
+    pe, _ = G.load("elasticity_sq_p2", R.emul_compile)
+    E = g.DeviceAssembler(pe, lib=emul)
+    with pytest.raises(capi.Gsb200Error):
+        E.field_norms(np.zeros(pe.nfree))                         # scalar spaces only
+    E.close()
+    p2 = pb.with_fixed(pb.fixed, rank=0, nranks=2)
+    B = g.DeviceAssembler(p2, lib=emul)
+    B.assemble()
+    with pytest.raises(capi.Gsb200Error):
+        B.exchange()                                              # two ranks, no communicator / callback: refused, not skipped
+    B.close()
