@@ -130,7 +130,7 @@ template <class T = real_t>
 class gsExprAssemblerB200
 {
 public:
-    gsExprAssemblerB200() : m_ref(1,1), m_mp(NULL), m_mb(NULL), m_bc(NULL), m_dim(1), m_device(0), m_keepPattern(false), m_lastForm(-1) { }
+    gsExprAssemblerB200() : m_ref(1,1), m_mp(NULL), m_mb(NULL), m_bc(NULL), m_dim(1), m_device(0), m_keepPattern(false), m_lastForm(-1), m_deviceDirichlet(false), m_projBc(NULL) { }
 
     void setOptions(const gsOptionList & o) { m_ref.setOptions(o); }
     gsOptionList & options() { return m_ref.options(); }
@@ -138,6 +138,9 @@ public:
     void setGeometry(const gsMultiPatch<T> & mp) { m_mp = &mp; }
     void setDevice(int device) { m_device = device; }
     void setKeepPattern(bool keep) { m_keepPattern = keep; }
+    /// With dirValues = l2Projection in setup(): leave the projection of the Dirichlet data to the device (gsb200_project_dirichlet,
+    /// the device-side gsDirichletValuesByL2Projection); call before setup().  Scalar spaces with gsFunctionExpr data.
+    void setDeviceDirichlet(bool on) { m_deviceDirichlet = on; }
 
     /// getSpace + space::setup (gsExprAssembler.h:166, gsExpressions.h:1091): the DOF
     /// mapper and the Dirichlet values are computed by the reference's own host code.
@@ -148,7 +151,13 @@ public:
         m_dim = dim;
         m_ref.getMap(*m_mp);
         typename gsExprAssembler<T>::space u = m_ref.getSpace(*m_mb, dim);
-        u.setup(bc, dirValues, 0);
+        m_projBc = NULL;
+        if (m_deviceDirichlet && dirValues == dirichlet::l2Projection && dim == 1)
+        {
+            b200::gsB200Problem probe;
+            if (b200::flattenDirichlet(bc, probe)) m_projBc = &bc;          // the conditions fit the device path
+        }
+        u.setup(bc, m_projBc ? dirichlet::homogeneous : dirValues, 0);      // the mapper comes from the reference either way
         m_ref.initSystem();
         m_mapper = u.mapper();
         m_fixed = u.fixedPart();
@@ -175,12 +184,14 @@ private:
             return;
         }
         b200::gsB200Problem st;
-        b200::flatten(*m_mp, *m_mb, m_mapper, m_dim, m_fixed, m_ref.options(), form, st);
+        gsMatrix<T> nofixed;
+        const bool project = m_projBc && b200::flattenDirichlet(*m_projBc, st);
+        b200::flatten(*m_mp, *m_mb, m_mapper, m_dim, project ? nofixed : m_fixed, m_ref.options(), form, st);
         st.pb.coef[0] = c0; st.pb.coef[1] = c1;
         st.pb.nrhs = 1;
         b200::flattenSource(f, form == GSB200_FORM_ELASTICITY ? m_dim : 1, st);
         if (m_bc) b200::flattenNeumann(*m_bc, m_mp->parDim(), st);
-        b200::assembleInto(st, m_device, m_handle, m_matrix, m_rhs);
+        b200::assembleInto(st, m_device, m_handle, m_matrix, m_rhs, project ? &m_fixed : NULL);
         m_lastForm = form;
     }
 
@@ -192,6 +203,8 @@ private:
     int m_device;
     bool m_keepPattern;
     int m_lastForm;
+    bool m_deviceDirichlet;
+    const gsBoundaryConditions<T> * m_projBc;
     b200::gsB200Handle m_handle;
     gsDofMapper m_mapper;
     gsMatrix<T> m_fixed;

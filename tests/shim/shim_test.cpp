@@ -164,6 +164,15 @@ int main(int argc, char **argv)
         B.setup(bc, 1, dirichlet::l2Projection);
         B.assemblePoisson(f, bc);
         bad += compare("gsExprAssemblerB200 NURBS annulus p=2 + Neumann", A.matrix(), A.rhs(), B.matrix(), B.rhs());
+        gsExprAssemblerB200<> C;       // the same with the Dirichlet data projected on the device (gsb200_project_dirichlet)
+        C.setIntegrationElements(mb); C.setGeometry(mp);
+        C.setDeviceDirichlet(true);
+        C.setup(bc, 1, dirichlet::l2Projection);
+        C.assemblePoisson(f, bc);
+        const real_t dfix = (C.fixedPart() - u.fixedPart()).norm() / u.fixedPart().norm();
+        gsInfo << "gsExprAssemblerB200 device L2-projection vs gsDirichletValuesByL2Projection: " << dfix << (dfix < 1e-9 ? "  OK\n" : "  FAIL\n");
+        bad += dfix < 1e-9 ? 0 : 1;
+        bad += compare("gsExprAssemblerB200 with device-projected Dirichlet values", A.matrix(), A.rhs(), C.matrix(), C.rhs(), 1e-9);
     }
     gsInfo << (bad ? "SHIM RESULT FAIL\n" : "SHIM RESULT PASS\n");
     return bad;
