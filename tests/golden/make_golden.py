@@ -76,6 +76,8 @@ FINGERPRINT = {
     "sq_p2_m64": dict(dim=2, degree=2, nelem=64, geometry=0, rhs=[PI2], dir_values=100, threads=8),
     "cube_p4_m8": dict(dim=3, degree=4, nelem=8, geometry=0, rhs=[PI3], dir_values=100, threads=8),
     "cube_p2_m16_expr": dict(dim=3, degree=2, nelem=16, geometry=0, path=1, rhs=[PI3], dirichlet=["x*y*z"], dir_values=101, threads=1),
+    # BASELINE config 1 at its stated size: the stock input of poisson2_example with 6 uniform refinements (-r 6), degree 2
+    "poisson2d_bvp_stock_r6": dict(dim=2, degree=0, nelem=6, geometry=5, xml="pde/poisson2d_bvp.xml", path=1, dir_values=102, threads=8),
     # BASELINE config 3 shape: the 21-patch yeti footprint, p=2, 16x16 elements per patch, glued interfaces
     "yeti_mp2_p2_m8": dict(dim=2, degree=2, nelem=8, geometry=4, xml="domain2d/yeti_mp2.xml", rhs=["1+x"], dirichlet=["0.1*y"], threads=8),
     # BASELINE config 4 shape: 2x2x2 patches, p=2, vector-valued linear elasticity through the expression path
@@ -88,7 +90,7 @@ SAMPLED = {
     "cube_p3_curved_m50": dict(dim=3, degree=3, nelem=50, geometry=1, rhs=[PI3], dirichlet=["x+y*z"], threads=8),
 }
 SAMPLE_STRIDE = 97
-KEEP_DOFMAP = {"yeti_mp2_p2_m8", "elasticity_8cubes_p2_m5"}
+KEEP_DOFMAP = {"yeti_mp2_p2_m8", "elasticity_8cubes_p2_m5", "poisson2d_bvp_stock_r6"}
 
 
 def pack_inputs(ref):

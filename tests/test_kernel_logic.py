@@ -23,7 +23,7 @@ def emul():
     return R.emul_lib()
 
 
-@pytest.mark.parametrize("name", G.names("full") + ["sq_p2_m64", "cube_p2_m16_expr", "yeti_mp2_p2_m8", "elasticity_8cubes_p2_m5"])
+@pytest.mark.parametrize("name", G.names("full") + ["sq_p2_m64", "cube_p2_m16_expr", "yeti_mp2_p2_m8", "elasticity_8cubes_p2_m5", "poisson2d_bvp_stock_r6"])
 def test_interpreted_kernels_match_reference(emul, name):
     pb, z = G.load(name, R.emul_compile)
     G.check_against(R.lib_assemble(emul, pb), z, TOL)
