@@ -303,7 +303,7 @@ int gsb200_project_dirichlet(gsb200_assembler *a, const gsb200_neumann *sides, i
                              double *fixed_out, int *iters, double *rel_residual);
 
 /* Compile an exprtk-style source term ("2*pi^2*sin(pi*x)*sin(pi*y)") into a
-   reverse-polish program.  Buffers are caller-allocated; on success *nops/*nconsts
+   reverse-polish program.  Buffers are caller-allocated; on success *nops and *nconsts
    hold the used lengths.  Supported: + - * / ^, unary -, parentheses, x y z, pi,
    numeric literals, sin cos tan exp log sqrt abs tanh sinh cosh. */
 int gsb200_expr_compile(const char *expr, int32_t *ops, int32_t ops_cap, int32_t *nops,
