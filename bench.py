@@ -399,11 +399,17 @@ def main():
         except Exception:
             pass
         ach = tm.sweep_bytes[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        lanes = dom_ms <= 0          # multi-patch: the patches' kernels overlap on several streams, there are no per-sweep times
+        if lanes:
+            ach = sum(tm.sweep_bytes) / sec / 1e9
         kname = {0: "k_geo_sweep (geometry + source term + sweep of direction 0 fused; D and F stay in shared memory)" if dim == 3 else "first sweep",
                  1: "k_sweepw, sum-factorisation sweep of direction 1", 2: "k_sweepw, final sweep of direction 2 (CSC scatter)"}[dom]
+        if lanes:
+            kname, traffic = "all sweeps of the step (patches run concurrently on lanes: whole-step figure)", None
         roofline = {"kernel": kname, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                     "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": int(tm.sweep_bytes[dom]), "ms_per_launch": dom_ms / max(tm.nchunks, 1),
+                    "algorithmic_bytes_per_launch": int(sum(tm.sweep_bytes) if lanes else tm.sweep_bytes[dom]),
+                    "ms_per_launch": (sec * 1e3 if lanes else dom_ms / max(tm.nchunks, 1)),
                     "note": "achieved = algorithmic bytes of the sweep (its inputs read once + outputs written once, DESIGN.md 3) / its "
                             "event-timed duration; traffic = measured dram read+write bytes of the same launches (profiles/traffic.json). "
                             "per_sweep lists all three; step_vs_* put the WHOLE step against the executed flops and against the compulsory "
