@@ -108,7 +108,7 @@ def cpu_matrix_arm(args):
     if not R.have_ref():
         print(json.dumps({"unavailable": "oracle/_ref/libgsref.so did not travel"}), flush=True)
         return
-    print(json.dumps(cpu_reference_matrix(args.degree or 3, args.ref_nelem, max(8, args.ref_nelem // 2))), flush=True)
+    print(json.dumps(cpu_reference_matrix(args.degree or 3, args.ref_nelem, args.ref_nelem)), flush=True)       # the same sample for every entry
 
 
 def reference_arm(args, rank):
