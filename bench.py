@@ -252,7 +252,7 @@ def main():
     ap.add_argument("--nelem", type=int, default=0, help="elements per direction (per GPU slab / per patch), 0 = the config's size")
     ap.add_argument("--nelem-z", type=int, default=0, help="configs 5/target: element layers per GPU along the last direction")
     ap.add_argument("--ref-nelem", type=int, default=24, help="elements per direction of the CPU sample")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cg-iters", type=int, default=4000)
     ap.add_argument("--cg-tol", type=float, default=1e-8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -529,6 +529,7 @@ def main():
         e2e1 = {"value": n_dofs / float(e2e_s[0].item()), "unit": "DOFs/s", "h2d_bytes_per_step": int(8 * pb.nfixed),
                "d2h_bytes_per_step": int((12 if sharded else 8) * nnz_local + 8 * pb.nfree),
                "steps": args.e2e_steps, "ms_per_step": float(e2e_s[0].item()) * 1e3, "delivery_chunks": int(tm_e2e.nchunks),
+               "d2h_GBps": ((12 if sharded else 8) * nnz_local + 8 * pb.nfree) / float(e2e_s[0].item()) / 1e9,      # the step is the PCIe transfer: this is the box's rate
                "includes": ("repeated assembly on a kept handle (gsb200_set_fixed + gsb200_assemble_values_to_host): eliminated-DOF values "
                             "from pinned host memory, all kernels, values + right-hand side into pinned host memory (finished column "
                             "ranges travel while later chunks integrate); the index arrays travelled with the first assembly; every rank "
