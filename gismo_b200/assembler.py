@@ -217,10 +217,13 @@ class DeviceAssembler:
     def project_dirichlet(self, sides, max_iter: int = 2000, tol: float = 1e-13):
         """gsb200_project_dirichlet: sides = [(patch, side, CompiledProgram g), ...]; returns (fixed values, iterations, rel. residual)."""
         nm = (capi.Neumann * max(len(sides), 1))()
-        for i, (patch, side, cp) in enumerate(sides):
-            nm[i].patch, nm[i].side, nm[i].ndata = int(patch), int(side), 1
-            nm[i].data[0].nops = len(cp.ops); nm[i].data[0].ops = cp.ops.ctypes.data_as(_ip)
-            nm[i].data[0].nconsts = len(cp.consts); nm[i].data[0].consts = cp.consts.ctypes.data_as(_dp)
+        for i, (patch, side, cps) in enumerate(sides):
+            cps = list(cps) if isinstance(cps, (list, tuple)) else [cps]          # one program per component of the space
+            nm[i].patch, nm[i].side, nm[i].ndata = int(patch), int(side), len(cps)
+            for c, cp in enumerate(cps):
+                nm[i].data[c].nops = len(cp.ops); nm[i].data[c].ops = cp.ops.ctypes.data_as(_ip)
+                nm[i].data[c].nconsts = len(cp.consts); nm[i].data[c].consts = cp.consts.ctypes.data_as(_dp)
+        self._keep_sides = sides
         out = np.zeros(max(self.problem.nfixed, 1))
         it, res = C.c_int(0), C.c_double(0)
         self._check(self.lib.gsb200_project_dirichlet(self._h, nm, len(sides), max_iter, tol, out.ctypes.data_as(_dp), C.byref(it), C.byref(res)))

@@ -354,7 +354,7 @@ GSB_GLOBAL void k_field_norms(const NormArgs A)
 // kernels (k_face_eval, k_face_load); the weights w m and the data w m g come from k_face_geometry.
 struct ProjSide { FaceArgs F; FaceLoadArgs L; FaceEvalArgs E; i64 npt, nfn; double *Wb, *Gb, *Tb; };
 
-static void proj_side_setup(gsb200_assembler *a, int patch, int side, ProjSide &S)
+static void proj_side_setup(gsb200_assembler *a, int patch, int side, int comp, ProjSide &S)
 {
     const PatchDev &P = a->patches[patch];
     const int dim = a->dim, dir = (side - 1) / 2, upper = (side - 1) % 2;
@@ -374,8 +374,8 @@ static void proj_side_setup(gsb200_assembler *a, int patch, int side, ProjSide &
     for (int k2 = 0; k2 <= dd.p; ++k2) { S.L.bval[k2] = dd.bval[upper][k2]; S.E.bval[k2] = dd.bval[upper][k2]; }
     S.L.bfirst = dd.bfirst[upper]; S.L.nb1 = dd.p + 1; S.E.bfirst = S.L.bfirst; S.E.nb1 = S.L.nb1;
     S.F.coefs = P.d_coefs; S.F.weights = P.d_weights; S.F.ngeo_total = P.ngeo_total;
-    S.L.dofmap = P.d_dofmap; S.L.nfree = a->nfree; S.L.to_fixed = 1;
-    S.E.dofmap = P.d_dofmap; S.E.nfree = a->nfree;
+    S.L.dofmap = P.d_dofmap + (i64)comp * P.nb; S.L.nfree = a->nfree; S.L.to_fixed = 1;      // component-major blocks of the DOF map
+    S.E.dofmap = P.d_dofmap + (i64)comp * P.nb; S.E.nfree = a->nfree;
 }
 template <class K2, class K3, class ARGS>
 static void face_launch(int dim, K2 k2, K3 k3, i64 n, stream_t s, const ARGS &A)
@@ -387,8 +387,14 @@ static void face_launch(int dim, K2 k2, K3 k3, i64 n, stream_t s, const ARGS &A)
 static int project_dirichlet(gsb200_assembler *a, const gsb200_neumann *sides, int nsides, int max_iter, double tol, double *fixed_out, int *iters, double *relres)
 {
     const int nb = a->nfixed; stream_t s = a->stream;
-    if (a->ncomp != 1 || a->nrhs != 1) { set_error("Dirichlet L2-projection: scalar problems with one right-hand side"); return GSB200_EUNSUPPORTED; }
+    if (a->nrhs != 1) { set_error("Dirichlet L2-projection: one right-hand side"); return GSB200_EUNSUPPORTED; }
     if (nb == 0) { if (iters) *iters = 0; if (relres) *relres = 0.0; return 0; }
+    // one entry per (side, component): a vector-valued space is projected component by component (the boundary mass matrix is block
+    // diagonal), the data of a side has one program per component
+    const int nsides_in = nsides;
+    for (int i = 0; i < nsides_in; ++i)
+        if (sides[i].ndata != a->ncomp) { set_error("Dirichlet side %d carries %d data components, the space has %d", i, sides[i].ndata, a->ncomp); return GSB200_EINVAL; }
+    nsides = nsides_in * a->ncomp;
     std::vector<ProjSide> S((size_t)nsides);
     std::vector<void *> bufs;
     auto alloc = [&](size_t n) -> double * { void *p = 0; if (dev_malloc(&p, sizeof(double) * std::max<size_t>(n, 1))) return (double *)0; bufs.push_back(p); return (double *)p; };
@@ -400,10 +406,11 @@ static int project_dirichlet(gsb200_assembler *a, const gsb200_neumann *sides, i
     for (int k = 0; k < 7; ++k) { vec[k] = alloc((size_t)nb + 8); if (!vec[k]) rc = GSB200_ENOMEM; }
     double *X = vec[0], *R = vec[1], *Z = vec[2], *Pv = vec[3], *Q = vec[4], *Dg = vec[5], *Sc = vec[6];
     for (int i = 0; i < nsides && !rc; ++i) {
-        const gsb200_neumann &sd = sides[i];
-        if (sd.patch < 0 || sd.patch >= (int)a->patches.size() || sd.side < 1 || sd.side > 2 * a->dim || sd.ndata != 1) { set_error("Dirichlet side %d malformed", i); rc = GSB200_EINVAL; break; }
+        const gsb200_neumann &sd = sides[i / a->ncomp];
+        const int comp = i % a->ncomp;
+        if (sd.patch < 0 || sd.patch >= (int)a->patches.size() || sd.side < 1 || sd.side > 2 * a->dim) { set_error("Dirichlet side %d malformed", i / a->ncomp); rc = GSB200_EINVAL; break; }
         ProjSide &P = S[i];
-        proj_side_setup(a, sd.patch, sd.side, P);
+        proj_side_setup(a, sd.patch, sd.side, comp, P);
         P.Wb = alloc((size_t)P.npt); P.Gb = alloc((size_t)P.npt); P.Tb = alloc((size_t)P.npt);
         if (!P.Wb || !P.Gb || !P.Tb) { rc = GSB200_ENOMEM; break; }
         // the reference integrates with md.measure of a gsMapData whose side is not set (gsDirichletValues.h:273 / gsAssembler.hpp:412):
@@ -411,7 +418,7 @@ static int project_dirichlet(gsb200_assembler *a, const gsb200_neumann *sides, i
         P.F.ndata = 1; P.F.vol_measure = 1;
         if ((rc = upload_device_program(a, one, &P.F.prog[0]))) break;
         P.F.Fb = P.Wb; face_launch(a->dim, k_face_geometry<2>, k_face_geometry<3>, P.npt, s, P.F);          // w |n|
-        if ((rc = upload_device_program(a, sd.data[0], &P.F.prog[0]))) break;
+        if ((rc = upload_device_program(a, sd.data[comp], &P.F.prog[0]))) break;
         P.F.Fb = P.Gb; face_launch(a->dim, k_face_geometry<2>, k_face_geometry<3>, P.npt, s, P.F);          // w |n| g
     }
     auto apply = [&](const double *x, double *y, bool diag) {      // y = M x  (diag: y = diag M)

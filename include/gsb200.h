@@ -296,9 +296,9 @@ int gsb200_field_norms(gsb200_assembler *a, const double *u_free, const gsb200_p
    (gsDirichletValuesByL2Projection, gsDirichletValues.h:257-435; option DirichletValues = l2Projection (102)): boundary mass
    matrix over the eliminated functions of the listed sides, right-hand side int g N_i m (m = the measure the reference uses
    there: |det J| at the boundary points), Jacobi-CG like the reference's
-   CGDiagonal - matrix-free on the device.  `sides`: (patch, side 1..2d, ndata = 1, data[0] = g) per Dirichlet side.  The result
+   CGDiagonal - matrix-free on the device.  `sides`: (patch, side 1..2d, ndata = ncomp, data[c] = g_c) per Dirichlet side.  The result
    (nfixed values, numbering of gsDofMapper::global_to_bindex) is written to fixed_out (may be NULL) and becomes the
-   assembler's eliminated values (as gsb200_set_fixed).  Scalar spaces, one right-hand side. */
+   assembler's eliminated values (as gsb200_set_fixed).  Scalar and vector-valued spaces (component by component), one right-hand side. */
 int gsb200_project_dirichlet(gsb200_assembler *a, const gsb200_neumann *sides, int nsides, int max_iter, double tol,
                              double *fixed_out, int *iters, double *rel_residual);
 

@@ -64,6 +64,8 @@ FULL = {
     # Dirichlet values by L2-projection (dirichlet::l2Projection = 102, gsDirichletValues.h:257-435) in 3-D and across patches
     "cube_p2_curved_l2proj": dict(dim=3, degree=2, nelem=3, geometry=1, path=1, rhs=[PI3], dirichlet=["x+y*z"], dir_values=102),
     "grid2x2_p3_l2proj": dict(dim=2, degree=3, nelem=3, geometry=3, grid=(2, 2, 1), path=1, rhs=[PI2], dirichlet=["sin(x)+y"], dir_values=102),
+    "elasticity_sq_p2_l2proj": dict(dim=2, degree=2, nelem=4, geometry=1, path=1, form=1, lam=80000.0, mu=80000.0,
+                                    rhs=["1", "x"], dirichlet=["0.01*y", "0.01*x*y"], dir_values=102),
     "cube_p3_visitor_l2proj": dict(dim=3, degree=3, nelem=2, geometry=1, path=0, rhs=[PI3], dirichlet=["x*y+z"], dir_values=102),
     # mixed degrees per direction, several right-hand sides
     "cube_p232_curved_m3": dict(dim=3, degree=2, nelem=3, geometry=1, rhs=[PI3], dirichlet=["x+y*z"], degree_dir=[2, 3, 2]),

@@ -127,6 +127,7 @@ L2PROJ_CASES = {
     "cube_p2_curved_l2proj": ("x+y*z", [(0, s) for s in range(1, 7)]),
     "cube_p3_visitor_l2proj": ("x*y+z", [(0, s) for s in range(1, 7)]),
     "grid2x2_p3_l2proj": ("sin(x)+y", None),
+    "elasticity_sq_p2_l2proj": (["0.01*y", "0.01*x*y"], [(0, s) for s in (1, 2, 3, 4)]),      # vector-valued: one datum per component
 }
 
 

@@ -163,7 +163,8 @@ def test_dirichlet_l2_projection_matches_the_reference(emul, name):
     pb, z = G.load(name, R.emul_compile)
     text, sides = G.l2proj_sides(name, pb)
     A = g.DeviceAssembler(pb.with_fixed(None), lib=emul)          # no eliminated values given: the device computes them
-    fx, it, res = A.project_dirichlet([(p_, s_, R.emul_compile(text)) for p_, s_ in sides])
+    data = [R.emul_compile(t) for t in text] if isinstance(text, list) else R.emul_compile(text)      # vector-valued: one datum per component
+    fx, it, res = A.project_dirichlet([(p_, s_, data) for p_, s_ in sides])
     ref = z["fixed"][:, 0]
     assert res <= 1e-12 and np.abs(fx - ref).max() <= 1e-9 * np.abs(ref).max()
     A.assemble()
