@@ -167,23 +167,21 @@ void flattenNeumann(const gsBoundaryConditions<T> & bc, short_t dim, gsB200Probl
 /// given in physical coordinates, for gsb200_project_dirichlet (the device-side gsDirichletValuesByL2Projection,
 /// gsDirichletValues.h:257-435).  Returns false (and leaves \a st untouched) if a condition is outside that form.
 template <class T>
-bool flattenDirichlet(const gsBoundaryConditions<T> & bc, gsB200Problem & st)
+bool flattenDirichlet(const gsBoundaryConditions<T> & bc, gsB200Problem & st, index_t ncomp = 1)
 {
     std::vector<gsb200_neumann> sides;
     for (typename gsBoundaryConditions<T>::const_iterator it = bc.dirichletSides().begin(); it != bc.dirichletSides().end(); ++it)
     {
-        if (it->unknown() != 0 || it->unkComponent() > 0 || it->parametric()) return false;
+        // all components of the space at once (unkComponent -1, or 0 for a scalar space), data in physical coordinates
+        if (it->unknown() != 0 || it->parametric() || ncomp > GSB200_MAX_DIM) return false;
+        if (!(it->unkComponent() == -1 || (ncomp == 1 && it->unkComponent() == 0))) return false;
         gsb200_neumann sd;
         std::memset(&sd, 0, sizeof(sd));
-        sd.patch = it->patch(); sd.side = it->side().index(); sd.ndata = 1;
-        if (it->isHomogeneous())
-            sd.data[0] = internal::compileExpr<T>("0", st);
-        else
-        {
-            const gsFunctionExpr<T> * fe = dynamic_cast<const gsFunctionExpr<T>*>(it->function().get());
-            if (!fe || fe->targetDim() != 1) return false;
-            sd.data[0] = internal::compileExpr<T>(fe->expression(0), st);
-        }
+        sd.patch = it->patch(); sd.side = it->side().index(); sd.ndata = static_cast<int32_t>(ncomp);
+        const gsFunctionExpr<T> * fe = it->isHomogeneous() ? NULL : dynamic_cast<const gsFunctionExpr<T>*>(it->function().get());
+        if (!it->isHomogeneous() && (!fe || fe->targetDim() != ncomp)) return false;
+        for (index_t c = 0; c != ncomp; ++c)
+            sd.data[c] = internal::compileExpr<T>(fe ? fe->expression(c) : std::string("0"), st);
         sides.push_back(sd);
     }
     st.dirichlet.swap(sides);

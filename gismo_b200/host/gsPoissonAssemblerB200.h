@@ -139,7 +139,7 @@ public:
     void setDevice(int device) { m_device = device; }
     void setKeepPattern(bool keep) { m_keepPattern = keep; }
     /// With dirValues = l2Projection in setup(): leave the projection of the Dirichlet data to the device (gsb200_project_dirichlet,
-    /// the device-side gsDirichletValuesByL2Projection); call before setup().  Scalar spaces with gsFunctionExpr data.
+    /// the device-side gsDirichletValuesByL2Projection); call before setup().  gsFunctionExpr data for all components of the space.
     void setDeviceDirichlet(bool on) { m_deviceDirichlet = on; }
 
     /// getSpace + space::setup (gsExprAssembler.h:166, gsExpressions.h:1091): the DOF
@@ -152,10 +152,10 @@ public:
         m_ref.getMap(*m_mp);
         typename gsExprAssembler<T>::space u = m_ref.getSpace(*m_mb, dim);
         m_projBc = NULL;
-        if (m_deviceDirichlet && dirValues == dirichlet::l2Projection && dim == 1)
+        if (m_deviceDirichlet && dirValues == dirichlet::l2Projection)
         {
             b200::gsB200Problem probe;
-            if (b200::flattenDirichlet(bc, probe)) m_projBc = &bc;          // the conditions fit the device path
+            if (b200::flattenDirichlet(bc, probe, dim)) m_projBc = &bc;     // the conditions fit the device path
         }
         u.setup(bc, m_projBc ? dirichlet::homogeneous : dirValues, 0);      // the mapper comes from the reference either way
         m_ref.initSystem();
@@ -185,7 +185,7 @@ private:
         }
         b200::gsB200Problem st;
         gsMatrix<T> nofixed;
-        const bool project = m_projBc && b200::flattenDirichlet(*m_projBc, st);
+        const bool project = m_projBc && b200::flattenDirichlet(*m_projBc, st, m_dim);
         b200::flatten(*m_mp, *m_mb, m_mapper, m_dim, project ? nofixed : m_fixed, m_ref.options(), form, st);
         st.pb.coef[0] = c0; st.pb.coef[1] = c1;
         st.pb.nrhs = 1;
